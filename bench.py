@@ -1,0 +1,272 @@
+#!/usr/bin/env python
+"""Benchmark of the Ackermann env-step hot path (see BASELINE.json / SURVEY.md 8d).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # CPU restatement of the reference loop
+
+A "step" is one env.step() of every environment of the batch = frame_skip physics substeps of 2 ms.
+Workloads (BASELINE.json configs):
+  N = 1 : configs[1] "ackermann flat-floor, 4096 batched envs on 1 B200, random actions, frame_skip=4"
+  N > 1 : configs[3] "ackermann flat-floor, 131072 envs per GPU sharded across 2/4/8 B200" (no data-path collective)
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES_F32 = 650.0   # algorithmic HBM bytes per env-step, fp32 state (SURVEY.md 8d / DESIGN.md)
+ALGO_BYTES_F64 = 962.0
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi SM clocks and throttle reasons while the timed region runs."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for nme, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's loop (controller + mj_step) restated in C (oracle/), one process per core
+# ----------------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    seed, n_steps, frame_skip = args
+    from mujoco_playground_b200.models import load_model
+    from oracle.oracle import OracleSim
+    M = load_model("v2")
+    sim = OracleSim(M)
+    sq = M["qpos0"].copy()
+    sq[0:3] = [0, 0, 0.1]
+    sim.rollout(200, frame_skip, 1000, seed + 1000, sq)       # warm-up
+    t0 = time.perf_counter()
+    sim.rollout(n_steps, frame_skip, 1000, seed, sq)
+    return time.perf_counter() - t0
+
+
+def cpu_rollout(n_steps_per_proc: int, frame_skip: int, procs: int):
+    """Returns (env-steps/s aggregated over procs, seconds of the slowest worker)."""
+    import multiprocessing as mp
+    from oracle import oracle as _o
+    _o.build()
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(procs) as pool:
+        times = pool.map(_cpu_worker, [(s, n_steps_per_proc, frame_skip) for s in range(procs)])
+    tmax = max(times)
+    return procs * n_steps_per_proc / tmax, tmax
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    fs = args.frame_skip
+    per = max(50, args.cpu_steps // fs)
+    vals = []
+    for _ in range(args.warmup):
+        cpu_rollout(max(50, per // 10), fs, cores)
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        v, _t = cpu_rollout(per, fs, cores)
+        vals.append(v)
+    wall = time.perf_counter() - t_all
+    value = sum(vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * wall / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args, world), "frame_skip": fs, "l2": "n/a (CPU)"},
+        "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                         "sample": f"{per} env-steps x {cores} processes per step (C restatement of controller + mj_step; "
+                                   "real mujoco is not installable in this image)"},
+        "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args, world):
+    if args.envs:
+        return f"ackermann flat-floor, {args.envs} envs per GPU, random actions, frame_skip={args.frame_skip}"
+    if world == 1:
+        return "configs[1]: ackermann flat-floor, 4096 batched envs on 1 B200, random actions, frame_skip=4"
+    return f"configs[3]: ackermann flat-floor, 131072 envs per GPU sharded across {world} B200, frame_skip=4"
+
+
+# ----------------------------------------------------------------------------------------------------------
+def run_cuda(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+    from mujoco_playground_b200 import BatchedAckermannEnv
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_envs = args.envs or (4096 if world == 1 else 131072)
+    fs = args.frame_skip
+    env = BatchedAckermannEnv(n_envs, device=dev, frame_skip=fs, dtype=args.dtype, seed=1234 + rank, auto_reset=True,
+                              lanes_per_env=args.lanes)
+    env.reset()
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- kernel-resident throughput: synthetic actions generated in the kernel, state resident in HBM --------------
+    for _ in range(args.warmup):
+        env.step(None)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    launches0 = env.launch_count
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall = time.perf_counter()
+    for s0, s1 in evs:
+        flush.zero_()                     # evict state from L2 between timed iterations (not timed)
+        s0.record()
+        env.step(None)
+        s1.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    launches = env.launch_count - launches0
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    value = world * n_envs * args.steps / (total_ms * 1e-3)
+    stats = env.stats()
+
+    # ---- end to end through the C ABI with HOST buffers (H2D actions, D2H obs/reward/flags inside the timed region) ---
+    h_act = torch.empty((n_envs, 2), dtype=torch.float32).uniform_(-1, 1).pin_memory()
+    h_obs = torch.empty((n_envs, env.obs_dim), dtype=torch.float32).pin_memory()
+    h_rew = torch.empty((n_envs,), dtype=torch.float32).pin_memory()
+    h_term = torch.empty((n_envs,), dtype=torch.uint8).pin_memory()
+    h_trunc = torch.empty((n_envs,), dtype=torch.uint8).pin_memory()
+    for _ in range(args.warmup):
+        env.step_host(h_act, h_obs, h_rew, h_term, h_trunc)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        env.step_host(h_act, h_obs, h_rew, h_term, h_trunc)
+    torch.cuda.synchronize(dev)
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = world * n_envs * args.steps / float(e2e_s.item())
+    h2d = n_envs * 2 * 4
+    d2h = n_envs * (env.obs_dim * 4 + 4 + 1 + 1)
+    clocks = sampler.summary() if sampler else None
+
+    if rank == 0:
+        peak, how = measured_peak_gbs()
+        algo = ALGO_BYTES_F32 if args.dtype == "float32" else ALGO_BYTES_F64
+        avg_launch_s = (sum(step_ms) / len(step_ms)) * 1e-3
+        achieved = algo * n_envs / avg_launch_s / 1e9
+        line = {
+            "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.dtype == "float32" else "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args, world), "envs_per_gpu": n_envs, "frame_skip": fs, "lanes_per_env": args.lanes,
+                       "l2": "flushed between timed iterations (256 MiB memset, untimed)", "physics_substeps_per_s": value * fs},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "peak_source": how, "kernel": "step_kernel", "algorithmic_bytes_per_env_step": algo,
+                         "note": "compute/latency bound kernel: see DESIGN.md (HBM fraction is small by construction)"},
+            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "solver": {"mean_newton_iters_per_env_step": stats["solver_iters"] / max(1, stats["env_steps"]),
+                       "episodes": stats["episodes"], "unsupported_contact_steps": stats["unsupported"]},
+            "wall_s_timed_region": t_wall,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            per = max(50, args.cpu_steps // fs)
+            v, tmax = cpu_rollout(per, fs, cores)
+            line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                                    "sample": f"{per} env-steps (frame_skip={fs}) on each of {cores} processes, {tmax:.1f} s; C restatement of "
+                                              "controller + mj_step (real mujoco not installable in this image)"}
+        print(json.dumps(line), flush=True)
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--envs", type=int, default=0, help="override environments per GPU")
+    ap.add_argument("--frame-skip", type=int, default=4)
+    ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
+    ap.add_argument("--lanes", type=int, default=4)
+    ap.add_argument("--cpu-steps", type=int, default=200000, help="physics substeps per CPU process for the CPU arm sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_cuda(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

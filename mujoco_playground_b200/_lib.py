@@ -1,0 +1,60 @@
+"""ctypes binding of libackb.so (include/ackb.h).  There is no CPU fallback: a missing or unloadable
+CUDA library is an error."""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libackb.so")
+_lib = None
+
+
+class AckbStats(ctypes.Structure):
+    _fields_ = [("episodes", ctypes.c_ulonglong), ("successes", ctypes.c_ulonglong), ("env_steps", ctypes.c_ulonglong),
+                ("collisions", ctypes.c_ulonglong), ("unsupported", ctypes.c_ulonglong), ("solver_iters", ctypes.c_ulonglong),
+                ("return_sum", ctypes.c_double), ("length_sum", ctypes.c_double)]
+
+
+# every symbol include/ackb.h declares: (restype, argtypes)
+_vp, _i, _u64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64
+SYMBOLS = {
+    "ackb_consts_len": (_i, []),
+    "ackb_create": (_i, [_vp, ctypes.c_size_t, _i, _i, _i, _u64, _i, ctypes.POINTER(_vp)]),
+    "ackb_destroy": (_i, [_vp]),
+    "ackb_num_envs": (_i, [_vp]),
+    "ackb_obs_dim": (_i, [_vp]),
+    "ackb_dtype": (_i, [_vp]),
+    "ackb_reset": (_i, [_vp, _vp, _vp, _vp]),
+    "ackb_step": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "ackb_step_host": (_i, [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "ackb_get_state": (_i, [_vp, _vp, _vp, _vp]),
+    "ackb_set_state": (_i, [_vp, _vp, _vp, _vp]),
+    "ackb_get_episode": (_i, [_vp, _vp, _vp, _vp]),
+    "ackb_set_episode": (_i, [_vp, _vp, _vp, _vp]),
+    "ackb_stats": (_i, [_vp, ctypes.POINTER(AckbStats)]),
+    "ackb_stats_reset": (_i, [_vp]),
+    "ackb_launch_count": (ctypes.c_ulonglong, [_vp]),
+    "ackb_random_actions": (_i, [_vp, _vp, _vp]),
+    "ackb_last_error": (ctypes.c_char_p, [_vp]),
+}
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(the simulator has no CPU fallback)")
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def check(rc: int, handle=None):
+    if rc != 0:
+        msg = load().ackb_last_error(handle)
+        raise RuntimeError(f"ackb error {rc}: {msg.decode() if msg else '?'}")

@@ -1,0 +1,972 @@
+// ackb_core.cuh -- per-environment physics of the Ackermann robot, specialised to its topology.
+//
+// Replaces, for one environment, what the reference obtains from `mujoco.mj_step`
+// (src/rl/envs/ackermann_env.py:200) plus the controller / observation / reward glue around it
+// (src/core/controller.py:98-140, src/core/odometry.py:62-103,154-170,
+//  src/rl/envs/ackermann_env.py:187-312).
+//
+// Design:
+//   * The kinematic tree is fixed (free chassis + 2 rear spin hinges + 2 x (steer hinge -> spin hinge)),
+//     every hinge-mounted body has isotropic inertia with its centre of mass on the hinge anchor
+//     (checked by the model compiler).  Expressed in the chassis body frame with generalised
+//     accelerations a~ = [R^T a_lin ; a_ang ; hinges], the CRB mass matrix collapses to
+//     compile-time constants plus the steer-dependent wheel axes, and the RNE bias has the closed
+//     form implemented in `smooth_forces`.
+//   * LANES lanes cooperate on one environment (LANES = 4: one lane per wheel).  Each lane owns
+//     WPL = 4/LANES wheels: their spin dof, contacts and pyramid rows.  The 8 "shared" dofs
+//     (3 lin, 3 ang, 2 steer) are replicated in every lane; wheel contributions to them are summed
+//     with warp shuffles (`Team::sum`).
+//   * Newton solver on MuJoCo's convex primal cost.  The Hessian is arrow shaped: the spin dofs are
+//     eliminated per lane (1x1 pivots), the 8x8 Schur complement is LDL^T-factorised in registers.
+//   * The same header compiles for the host with LANES = 1 (tests/hostsim) so that the arithmetic
+//     can be debugged against the oracle without a GPU.  That build is test-only.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define ACKB_HD __host__ __device__ __forceinline__
+#define ACKB_D __device__ __forceinline__
+#else
+#define ACKB_HD inline
+#define ACKB_D inline
+#endif
+
+namespace ackb {
+
+// ------------------------------------------------------------------------------------------------
+// constants block
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct Consts {
+#define ACKB_FIELD(name, count) T name[count];
+#include "ackb_consts.def"
+#undef ACKB_FIELD
+};
+constexpr int kNumConsts = sizeof(Consts<double>) / sizeof(double);
+
+template <typename T>
+ACKB_HD T mjmin(T a, T b) { return a < b ? a : b; }
+template <typename T>
+ACKB_HD T mjmax(T a, T b) { return a > b ? a : b; }
+template <typename T>
+ACKB_HD T mjclip(T x, T lo, T hi) { return x < lo ? lo : (x > hi ? hi : x); }  // NaN passes through, like mju_clip
+
+template <typename T> struct Num;
+template <> struct Num<float> {
+  static constexpr float minval = 1e-15f;
+  ACKB_HD static float sqrt_(float x) { return sqrtf(x); }
+  ACKB_HD static float abs_(float x) { return fabsf(x); }
+  ACKB_HD static float sin_(float x) { return sinf(x); }
+  ACKB_HD static float cos_(float x) { return cosf(x); }
+  ACKB_HD static float atan_(float x) { return atanf(x); }
+  ACKB_HD static float tan_(float x) { return tanf(x); }
+  ACKB_HD static float atan2_(float y, float x) { return atan2f(y, x); }
+  ACKB_HD static float pow_(float x, float y) { return powf(x, y); }
+  // Newton exit thresholds usable at this precision
+  static constexpr float tol_floor = 1e-6f;
+  static constexpr float ls_rel = 1e-3f;
+};
+template <> struct Num<double> {
+  static constexpr double minval = 1e-15;
+  ACKB_HD static double sqrt_(double x) { return sqrt(x); }
+  ACKB_HD static double abs_(double x) { return fabs(x); }
+  ACKB_HD static double sin_(double x) { return sin(x); }
+  ACKB_HD static double cos_(double x) { return cos(x); }
+  ACKB_HD static double atan_(double x) { return atan(x); }
+  ACKB_HD static double tan_(double x) { return tan(x); }
+  ACKB_HD static double atan2_(double y, double x) { return atan2(y, x); }
+  ACKB_HD static double pow_(double x, double y) { return pow(x, y); }
+  static constexpr double tol_floor = 0.0;
+  static constexpr double ls_rel = 1e-10;
+};
+
+// ------------------------------------------------------------------------------------------------
+// team of LANES lanes working on one environment
+// ------------------------------------------------------------------------------------------------
+template <int LANES>
+struct Team {
+  // lanes of this environment inside the warp: team-uniform (not warp-uniform) branches stay legal
+  ACKB_D static unsigned mask() {
+#if defined(__CUDA_ARCH__)
+    return LANES >= 32 ? 0xffffffffu : (((1u << LANES) - 1u) << ((threadIdx.x & 31u) & ~(unsigned)(LANES - 1)));
+#else
+    return 1u;
+#endif
+  }
+  template <typename T>
+  ACKB_D static T sum(T v) {
+#if defined(__CUDA_ARCH__)
+    const unsigned m = mask();
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o);
+#else
+    static_assert(LANES == 1, "host build supports LANES == 1 only");
+#endif
+    return v;
+  }
+  template <typename T>
+  ACKB_D static T min(T v) {
+#if defined(__CUDA_ARCH__)
+    const unsigned m = mask();
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) { T other = __shfl_xor_sync(m, v, o); v = other < v ? other : v; }
+#endif
+    return v;
+  }
+  template <typename T, int N>
+  ACKB_D static void sum_n(T (&v)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = sum(v[i]);
+  }
+  ACKB_D static void sync() {
+#if defined(__CUDA_ARCH__)
+    __syncwarp(mask());
+#endif
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// small vector helpers
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+ACKB_HD T dot3(const T* a, const T* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+template <typename T>
+ACKB_HD void cross3(T* r, const T* a, const T* b) {
+  T t0 = a[1] * b[2] - a[2] * b[1], t1 = a[2] * b[0] - a[0] * b[2], t2 = a[0] * b[1] - a[1] * b[0];
+  r[0] = t0; r[1] = t1; r[2] = t2;
+}
+
+// per-environment state held in registers.  Velocities and warm start use MuJoCo's convention
+// (linear part in the world frame, angular part in the chassis frame).
+template <typename T, int WPL>
+struct EnvState {
+  T p[3], q[4], st[2], sp[WPL];
+  T vw[3], om[3], dst[2], dsp[WPL];
+  T warm_l[3], warm_a[3], warm_st[2], warm_sp[WPL];
+};
+
+// quantities of the position stage that the observation needs (pre-integration, reference quirk Q3)
+template <typename T>
+struct Kin {
+  T R[9];      // chassis rotation (row major), from the normalised quaternion
+  T n[3], t1[3], t2[3];  // floor contact frame expressed in the body frame
+};
+
+struct StepDiag {
+  int ncon;         // contacts detected (dist <= 0) over all wheels of this lane
+  int unsupported;  // geometry outside the supported contact set
+  int niter;
+};
+
+// index of element (i, j), i >= j, in a packed lower triangle
+ACKB_HD constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
+
+// ------------------------------------------------------------------------------------------------
+// impedance  d(|pos - margin|)  
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+ACKB_HD T impedance(const T* solimp, T pos) {
+  const T lo = T(0.0001), hi = T(0.9999);
+  T d0 = mjclip(solimp[0], lo, hi), d1 = mjclip(solimp[1], lo, hi), width = mjmax(T(0), solimp[2]);
+  T mid = mjclip(solimp[3], lo, hi), power = mjmax(T(1), solimp[4]);
+  if (d0 == d1 || width <= Num<T>::minval) return T(0.5) * (d0 + d1);
+  T x = Num<T>::abs_(pos) / width;
+  if (x >= T(1)) return d1;
+  if (x <= T(0)) return d0;
+  T y;
+  if (power == T(2)) y = (x <= mid) ? x * x / mid : T(1) - (T(1) - x) * (T(1) - x) / (T(1) - mid);
+  else if (power == T(1)) y = x;
+  else y = (x <= mid) ? Num<T>::pow_(x, power) / Num<T>::pow_(mid, power - 1)
+                      : T(1) - Num<T>::pow_(T(1) - x, power) / Num<T>::pow_(T(1) - mid, power - 1);
+  return d0 + y * (d1 - d0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// controllers (reference: src/core/controller.py)
+// ------------------------------------------------------------------------------------------------
+// BicycleController.cmd_vel_to_controls + apply_cmd_vel (controller.py:98-140), every branch and
+// epsilon kept, including the inf*0 = NaN corner that MuJoCo answers by zeroing all controls.
+template <typename T>
+ACKB_HD void bicycle_controller(const Consts<T>& C, T v, T omega, T* ctrl) {
+  const T eps = T(1e-5);
+  const T L = C.wheelbase[0], Tw = C.track_width[0], rw = C.wheel_radius[0];
+  T delta;
+  if (Num<T>::abs_(omega) < T(1e-6)) delta = T(0);
+  else {
+    T sgn = omega > T(0) ? T(1) : (omega < T(0) ? T(-1) : T(0));
+    T den = (Num<T>::abs_(v) > eps) ? v : sgn * eps;
+    delta = Num<T>::atan_((L * omega) / den);
+  }
+  const T lim = T(0.6108652381980153);  // deg2rad(35)
+  delta = mjclip(delta, -lim, lim);
+  T vl, vr;
+  if (Num<T>::abs_(delta) < T(1e-6)) vl = vr = v;
+  else {
+    T tn = Num<T>::tan_(delta);
+    T Rt = (Num<T>::abs_(tn) > eps) ? L / tn : T(INFINITY);
+    T omega_turn = (Num<T>::abs_(Rt) > eps) ? v / Rt : T(0);
+    vl = omega_turn * (Rt - Tw / T(2));
+    vr = omega_turn * (Rt + Tw / T(2));
+  }
+  ctrl[0] = mjclip(delta, T(-0.61), T(0.61));
+  ctrl[1] = mjclip(vl / rw, T(-50), T(50));
+  ctrl[2] = mjclip(vr / rw, T(-50), T(50));
+  ctrl[3] = T(0);
+}
+
+// AckermannController (controller.py:42-78) for the 4-actuator scene model.
+template <typename T>
+ACKB_HD void ackermann_controller(const Consts<T>& C, T v, T omega, T* ctrl) {
+  const T L = C.wheelbase[0], Tw = C.track_width[0], rw = C.wheel_radius[0];
+  T dl, dr, vl, vr;
+  if (Num<T>::abs_(omega) < T(1e-4)) { dl = dr = T(0); vl = vr = v; }
+  else {
+    T Rt = v / omega;
+    T Ri = Rt - Tw / T(2), Ro = Rt + Tw / T(2);
+    T ai = Num<T>::atan_(L / Ri), ao = Num<T>::atan_(L / Ro);  // Ri == 0 raises in Python; here atan(inf)
+    if (omega > T(0)) { dl = ai; dr = ao; } else { dl = ao; dr = ai; }
+    vl = omega * Ri; vr = omega * Ro;
+  }
+  ctrl[0] = mjclip(dl, T(-0.61), T(0.61));
+  ctrl[1] = mjclip(dr, T(-0.61), T(0.61));
+  ctrl[2] = mjclip(vl / rw, T(-50), T(50));
+  ctrl[3] = mjclip(vr / rw, T(-50), T(50));
+}
+
+// action (float32, as in the env) -> ctrl; mirrors ackermann_env.py:190-197
+template <typename T>
+ACKB_HD void action_to_ctrl(const Consts<T>& C, float a0, float a1, T* ctrl) {
+  a0 = mjclip(a0, -1.0f, 1.0f);
+  a1 = mjclip(a1, -1.0f, 1.0f);
+  float lin = a0 * (float)C.max_linear_velocity[0];   // stays float32 in the reference (NumPy scalar rules)
+  float ang = a1 * (float)C.max_angular_velocity[0];
+  if (C.ctrl_kind[0] == T(0)) bicycle_controller<T>(C, (T)lin, (T)ang, ctrl);
+  else ackermann_controller<T>(C, (T)lin, (T)ang, ctrl);
+  // MuJoCo: a bad number in ctrl zeroes all controls for this step (mjWARN_BADCTRL)
+  bool bad = false;
+  for (int i = 0; i < 4; ++i) bad = bad || !(Num<T>::abs_(ctrl[i]) <= T(1e10));
+  if (bad) for (int i = 0; i < 4; ++i) ctrl[i] = T(0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-wheel working set
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct Contact {
+  T x[3];     // contact point, body frame
+  T u[3];     // axis x r          (spin column of the point Jacobian)
+  T w[3];     // ez x r            (steer column; used by front wheels only)
+  T D;        // 1/R of its pyramid rows (0: contact absent or excluded)
+  T aref[3];  // reference acceleration along n, t1, t2
+  T mu;
+};
+
+template <typename T>
+struct Wheel {
+  T c[3];        // centre (hinge anchor)
+  T a[3];        // spin axis, body frame
+  T isL, isR;    // 1 if this wheel hangs on steer L / R
+  T J, cdiag;    // spin inertia, J + armature
+  T dsteer;      // steer rate of the owning steer joint (0 for rear wheels)
+  int hidx;      // hinge index h2..h5
+  Contact<T> con[2];
+};
+
+// point "acceleration" y = a_lin + a_ang x X + a_spin (axis x r) + a_steer (ez x r), projected on the frame
+template <typename T>
+ACKB_HD void project_point(const Kin<T>& k, const Contact<T>& c, const T* alin, const T* aang, T aspin, T asteer, T* out) {
+  T y[3];
+  cross3(y, aang, c.x);
+  for (int i = 0; i < 3; ++i) y[i] += alin[i] + aspin * c.u[i] + asteer * c.w[i];
+  out[0] = dot3(k.n, y); out[1] = dot3(k.t1, y); out[2] = dot3(k.t2, y);
+}
+
+// forces of the four pyramid rows of a contact at residual z (3-vector in the contact frame);
+// returns cost, fills phi = contact-frame force and the quadratic-zone flags q[4]
+template <typename T>
+ACKB_HD T pyramid_rows(const Contact<T>& c, const T* z, T* phi, T* q) {
+  T x[4] = {z[0] + c.mu * z[1], z[0] - c.mu * z[1], z[0] + c.mu * z[2], z[0] - c.mu * z[2]};
+  T f[4], cost = T(0);
+  for (int i = 0; i < 4; ++i) {
+    bool act = x[i] < T(0);
+    q[i] = act ? T(1) : T(0);
+    f[i] = act ? -c.D * x[i] : T(0);
+    cost += act ? T(0.5) * c.D * x[i] * x[i] : T(0);
+  }
+  phi[0] = f[0] + f[1] + f[2] + f[3];
+  phi[1] = c.mu * (f[0] - f[1]);
+  phi[2] = c.mu * (f[2] - f[3]);
+  return cost;
+}
+
+// friction-loss (Huber) row: returns cost, force and quadratic flag
+template <typename T>
+ACKB_HD T floss_row(T x, T f, T R, T* force, T* quad) {
+  T rf = R * f;
+  if (x <= -rf) { *force = f; *quad = T(0); return f * (T(-0.5) * rf - x); }
+  if (x >= rf) { *force = -f; *quad = T(0); return f * (T(-0.5) * rf + x); }
+  T D = T(1) / R;
+  *force = -D * x; *quad = T(1);
+  return T(0.5) * D * x * x;
+}
+
+// rows that involve only the shared dofs: steering equality, steer friction loss, steer limits
+template <typename T>
+struct SharedRows {
+  T eqD, eq_aref;            // D = 0 when the model has no equality
+  T flD[2], flR[2], flf[2], fl_aref[2];
+  T limD[2], lim_sign[2], lim_aref[2];  // sign = +1 lower limit active, -1 upper; D = 0 inactive
+};
+
+// evaluate shared rows at steer accelerations (aL, aR): cost, generalised force on (sL, sR) and
+// the Hessian contribution (3 numbers: LL, LR, RR)
+template <typename T>
+ACKB_HD T shared_rows_eval(const SharedRows<T>& s, T aL, T aR, T* fL, T* fR, T* hLL, T* hLR, T* hRR) {
+  T cost = T(0);
+  *fL = *fR = T(0); *hLL = *hLR = *hRR = T(0);
+  {  // equality  (aL - aR) - aref
+    T x = aL - aR - s.eq_aref, f = -s.eqD * x;
+    cost += T(0.5) * s.eqD * x * x;
+    *fL += f; *fR -= f; *hLL += s.eqD; *hRR += s.eqD; *hLR -= s.eqD;
+  }
+  const T a[2] = {aL, aR};
+  T* fo[2] = {fL, fR};
+  T* ho[2] = {hLL, hRR};
+  for (int i = 0; i < 2; ++i) {
+    T f, q;
+    cost += floss_row(a[i] - s.fl_aref[i], s.flf[i], s.flR[i], &f, &q);
+    *fo[i] += f; *ho[i] += q * s.flD[i];
+    T x = s.lim_sign[i] * a[i] - s.lim_aref[i];
+    bool act = x < T(0);
+    T fl = act ? -s.limD[i] * x : T(0);
+    cost += act ? T(0.5) * s.limD[i] * x * x : T(0);
+    *fo[i] += s.lim_sign[i] * fl;
+    *ho[i] += act ? s.limD[i] : T(0);
+  }
+  return cost;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// LDL^T of a packed symmetric positive definite 8x8, in registers (fully unrolled).
+// On exit the strict lower triangle holds L and the diagonal holds 1/d.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+ACKB_HD void ldl8_factor(T* S) {
+  T d[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    T v[8];
+    T dj = S[tri(j, j)];
+#pragma unroll
+    for (int k = 0; k < j; ++k) { v[k] = S[tri(j, k)] * d[k]; dj -= S[tri(j, k)] * v[k]; }
+    d[j] = dj;
+    T dinv = T(1) / dj;
+    S[tri(j, j)] = dinv;
+#pragma unroll
+    for (int i = j + 1; i < 8; ++i) {
+      T s = S[tri(i, j)];
+#pragma unroll
+      for (int k = 0; k < j; ++k) s -= S[tri(i, k)] * v[k];
+      S[tri(i, j)] = s * dinv;
+    }
+  }
+}
+template <typename T>
+ACKB_HD void ldl8_solve(const T* S, T* x /* in: rhs, out: solution */) {
+#pragma unroll
+  for (int i = 1; i < 8; ++i)
+#pragma unroll
+    for (int k = 0; k < i; ++k) x[i] -= S[tri(i, k)] * x[k];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] *= S[tri(i, i)];
+#pragma unroll
+  for (int i = 6; i >= 0; --i)
+#pragma unroll
+    for (int k = i + 1; k < 8; ++k) x[i] -= S[tri(k, i)] * x[k];
+}
+
+// Philox4x32-10 counter-based generator (Salmon et al. 2011), used for goals, spawn jitter and the
+// synthetic random actions of the benchmark.
+ACKB_HD void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+ACKB_HD float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }  // [0, 1)
+
+// debugging taps for the host build (tests/hostsim); null on the device
+template <typename T>
+struct DebugTap {
+  T tau[12], a_smooth[12], a[12], fc[12];  // internal order: lin3 ang3 sL sR spinRL spinRR spinFL spinFR
+  int niter, nls;
+};
+
+// ------------------------------------------------------------------------------------------------
+// the simulator
+// ------------------------------------------------------------------------------------------------
+template <typename T, int LANES>
+struct Sim {
+  static constexpr int WPL = 4 / LANES;
+  using Tm = Team<LANES>;
+  using N = Num<T>;
+  using State = EnvState<T, WPL>;
+
+  // ---- B1 kinematics: normalise the quaternion (written back, like mj_kinematics), rotation, floor frame
+  ACKB_HD static void kinematics(State& e, Kin<T>& k) {
+    T qn = N::sqrt_(e.q[0] * e.q[0] + e.q[1] * e.q[1] + e.q[2] * e.q[2] + e.q[3] * e.q[3]);
+    if (qn < N::minval) { e.q[0] = T(1); e.q[1] = e.q[2] = e.q[3] = T(0); }
+    else { T inv = T(1) / qn; for (int i = 0; i < 4; ++i) e.q[i] *= inv; }
+    const T w = e.q[0], x = e.q[1], y = e.q[2], z = e.q[3];
+    k.R[0] = w * w + x * x - y * y - z * z; k.R[1] = T(2) * (x * y - w * z); k.R[2] = T(2) * (x * z + w * y);
+    k.R[3] = T(2) * (x * y + w * z); k.R[4] = w * w - x * x + y * y - z * z; k.R[5] = T(2) * (y * z - w * x);
+    k.R[6] = T(2) * (x * z - w * y); k.R[7] = T(2) * (y * z + w * x); k.R[8] = w * w - x * x - y * y + z * z;
+    // contact frame of a floor contact in world axes is (n, t1, t2) = (+z, +y, -x); body components = R^T d
+    for (int i = 0; i < 3; ++i) { k.n[i] = k.R[6 + i]; k.t1[i] = k.R[3 + i]; k.t2[i] = -k.R[i]; }
+  }
+
+  ACKB_HD static void setup_wheel(const Consts<T>& C, const State& e, int wi, int slot, Wheel<T>& w) {
+    for (int i = 0; i < 3; ++i) w.c[i] = C.w_center[3 * wi + i];
+    w.isL = (wi == 2) ? T(1) : T(0);
+    w.isR = (wi == 3) ? T(1) : T(0);
+    T s = w.isL * e.st[0] + w.isR * e.st[1];
+    w.a[0] = -N::sin_(s); w.a[1] = N::cos_(s); w.a[2] = T(0);  // Rz(s) * (0, 1, 0)
+    w.J = C.h_inertia[2 + wi];
+    w.cdiag = w.J + C.h_armature[2 + wi];
+    w.dsteer = w.isL * e.dst[0] + w.isR * e.dst[1];
+    w.hidx = 2 + wi;
+    (void)slot;
+  }
+
+  // ---- B6/B7 floor contacts of one wheel (plane vs cylinder, in the body frame) and their row parameters
+  ACKB_HD static void collide_wheel(const Consts<T>& C, const State& e, const Kin<T>& k, const T* vb, int wi, int slot,
+                                    Wheel<T>& w, StepDiag& diag) {
+    const T r = C.w_radius[wi], hl = C.w_halflen[wi];
+    const T hO = e.p[2] - C.plane_z[0];
+    T ax[3] = {w.a[0], w.a[1], w.a[2]};
+    T prjaxis = dot3(k.n, ax);
+    if (prjaxis > T(0)) { for (int i = 0; i < 3; ++i) ax[i] = -ax[i]; prjaxis = -prjaxis; }
+    const T dist = dot3(k.n, w.c) + hO;
+    T vec[3];
+    for (int i = 0; i < 3; ++i) vec[i] = ax[i] * prjaxis - k.n[i];
+    T len = N::sqrt_(dot3(vec, vec));
+    if (len < N::minval) { diag.unsupported = 1; len = T(1); }  // disk parallel to the floor
+    for (int i = 0; i < 3; ++i) vec[i] *= r / len;
+    const T prjvec = dot3(vec, k.n);
+    for (int i = 0; i < 3; ++i) ax[i] *= hl;
+    prjaxis *= hl;
+    const T d0 = dist + prjaxis + prjvec, d1 = dist - prjaxis + prjvec;
+    const bool has0 = d0 <= T(0), has1 = has0 && (d1 <= T(0));
+    if (has0 && (dist + prjaxis - T(0.5) * prjvec <= T(0))) diag.unsupported = 1;  // cap faces the floor
+    diag.ncon += (has0 ? 1 : 0) + (has1 ? 1 : 0);
+    const T dd[2] = {d0, d1};
+    const bool has[2] = {has0, has1};
+    const T sgn[2] = {T(1), T(-1)};
+    const T mu = C.w_mu[wi];
+    for (int c = 0; c < 2; ++c) {
+      Contact<T>& con = w.con[c];
+      T rr[3];
+      for (int i = 0; i < 3; ++i) {
+        con.x[i] = w.c[i] + vec[i] + sgn[c] * ax[i] - k.n[i] * dd[c] * T(0.5);
+        rr[i] = con.x[i] - w.c[i];
+      }
+      cross3(con.u, w.a, rr);
+      const T st = w.isL + w.isR;
+      con.w[0] = -rr[1] * st; con.w[1] = rr[0] * st; con.w[2] = T(0);
+      con.mu = mu;
+      const bool active = has[c] && (dd[c] < T(0));  // dist >= includemargin(0): counted but excluded
+      T imp = impedance(&C.w_solimp[5 * wi], dd[c]);
+      T R0 = mjmax(N::minval, (T(1) - imp) / imp * C.w_tran[wi] * (T(1) + mu * mu));
+      con.D = active ? T(1) / (T(2) * C.w_mureg2[wi] * R0) : T(0);
+      T vel[3];
+      project_point(k, con, vb, e.om, e.dsp[slot], w.dsteer, vel);
+      con.aref[0] = -C.w_B[wi] * vel[0] - C.w_K[wi] * imp * dd[c];
+      con.aref[1] = -C.w_B[wi] * vel[1];
+      con.aref[2] = -C.w_B[wi] * vel[2];
+    }
+  }
+
+  ACKB_HD static void make_shared_rows(const Consts<T>& C, const State& e, SharedRows<T>& s) {
+    if (C.has_eq[0] != T(0)) {
+      T pos = e.st[0] - e.st[1];
+      T imp = impedance(C.eq_solimp, pos);
+      T R = mjmax(N::minval, (T(1) - imp) / imp * C.eq_invweight[0]);
+      s.eqD = T(1) / R;
+      s.eq_aref = -C.eq_B[0] * (e.dst[0] - e.dst[1]) - C.eq_K[0] * imp * pos;
+    } else { s.eqD = T(0); s.eq_aref = T(0); }
+    for (int i = 0; i < 2; ++i) {
+      s.flf[i] = C.h_floss[i]; s.flR[i] = C.h_flR[i]; s.flD[i] = T(1) / C.h_flR[i];
+      s.fl_aref[i] = -C.h_flB[i] * e.dst[i];
+      s.limD[i] = T(0); s.lim_sign[i] = T(1); s.lim_aref[i] = T(0);
+      if (C.st_limited[i] != T(0)) {
+        T dlo = e.st[i] - C.st_lo[i], dhi = C.st_hi[i] - e.st[i];
+        T pos = T(0), sign = T(0);
+        if (dlo < T(0)) { pos = dlo; sign = T(1); }
+        else if (dhi < T(0)) { pos = dhi; sign = T(-1); }
+        if (sign != T(0)) {
+          T imp = impedance(&C.lim_solimp[5 * i], pos);
+          T R = mjmax(N::minval, (T(1) - imp) / imp * C.h_invweight[i]);
+          s.limD[i] = T(1) / R; s.lim_sign[i] = sign;
+          s.lim_aref[i] = -C.lim_B[i] * (sign * e.dst[i]) - C.lim_K[i] * imp * pos;
+        }
+      }
+    }
+  }
+
+  // ---- actuator force on hinge h (B12); sums every actuator that targets it
+  ACKB_HD static T actuator_force(const Consts<T>& C, const T* ctrl, int h, T len, T vel) {
+    T f = T(0);
+    const int nact = (int)C.nact[0];
+    for (int u = 0; u < 4; ++u) {
+      if (u >= nact || (int)C.act_hinge[u] != h) continue;
+      T c = ctrl[u];
+      if (C.act_ctrllimited[u] != T(0)) c = mjclip(c, C.act_ctrlrange[2 * u], C.act_ctrlrange[2 * u + 1]);
+      T fu = C.act_gain[u] * c + C.act_bias[3 * u] + C.act_bias[3 * u + 1] * len + C.act_bias[3 * u + 2] * vel;
+      if (C.act_forcelimited[u] != T(0)) fu = mjclip(fu, C.act_forcerange[2 * u], C.act_forcerange[2 * u + 1]);
+      f += fu;
+    }
+    return f;
+  }
+
+  // ---- B10/B12/B13 smooth generalised force  tau = passive - bias + actuation  (closed-form RNE, see header)
+  ACKB_HD static void smooth_forces(const Consts<T>& C, const State& e, const Kin<T>& k, const Wheel<T>* wh, const T* ctrl,
+                                    int lane, T* tau_sh, T* tau_sp) {
+    // wheel-derived terms: relative angular momentum, gyroscopic torque on the chassis and on the steer dofs
+    T part[8];
+    for (int i = 0; i < 8; ++i) part[i] = T(0);  // [hrel(3), gyro(3), steerL, steerR]
+    const T ez[3] = {T(0), T(0), T(1)};
+    for (int s = 0; s < WPL; ++s) {
+      const Wheel<T>& w = wh[s];
+      T ezxa[3], omxa[3], omxez[3];
+      cross3(ezxa, ez, w.a);
+      cross3(omxa, e.om, w.a);
+      cross3(omxez, e.om, ez);
+      for (int i = 0; i < 3; ++i) {
+        part[i] += w.J * e.dsp[s] * w.a[i];
+        part[3 + i] += w.J * e.dsp[s] * w.dsteer * ezxa[i];
+      }
+      T bias_steer = w.J * e.dsp[s] * omxa[2];  // ez . (om x a)
+      part[6] += w.isL * bias_steer;
+      part[7] += w.isR * bias_steer;
+      T bias_spin = w.J * w.dsteer * dot3(w.a, omxez);
+      tau_sp[s] = -C.h_damping[w.hidx] * e.dsp[s] - bias_spin + actuator_force(C, ctrl, w.hidx, e.sp[s], e.dsp[s]);
+    }
+    Tm::sum_n(part);
+    T gb[3];  // gravity in the body frame
+    for (int i = 0; i < 3; ++i) gb[i] = k.R[i] * C.gravity[0] + k.R[3 + i] * C.gravity[1] + k.R[6 + i] * C.gravity[2];
+    T Iw[3], h[3], t0[3], t1[3], t2[3];
+    const T* I = C.inertiaO;
+    Iw[0] = I[0] * e.om[0] + I[3] * e.om[1] + I[4] * e.om[2];
+    Iw[1] = I[3] * e.om[0] + I[1] * e.om[1] + I[5] * e.om[2];
+    Iw[2] = I[4] * e.om[0] + I[5] * e.om[1] + I[2] * e.om[2];
+    for (int i = 0; i < 3; ++i) h[i] = Iw[i] + part[i];
+    h[2] += C.h_inertia[0] * e.dst[0] + C.h_inertia[1] * e.dst[1];
+    cross3(t0, e.om, h);                 // om x (I_O om + h_rel)
+    cross3(t1, C.mcom, gb);              // m c x g
+    cross3(t2, e.om, C.mcom);
+    T t3[3];
+    cross3(t3, e.om, t2);                // om x (om x m c)
+    for (int i = 0; i < 3; ++i) {
+      tau_sh[i] = -(t3[i] - C.mass[0] * gb[i]);
+      tau_sh[3 + i] = -(t0[i] + part[3 + i] - t1[i]);
+    }
+    for (int i = 0; i < 2; ++i)
+      tau_sh[6 + i] = -C.h_damping[i] * e.dst[i] - part[6 + i] + actuator_force(C, ctrl, i, e.st[i], e.dst[i]);
+    (void)lane;
+  }
+
+  // ---- M~ x  (B4 CRB, folded): shared part needs one 3-value team sum
+  ACKB_HD static void mul_M(const Consts<T>& C, const Wheel<T>* wh, const T* x_sh, const T* x_sp, T* y_sh, T* y_sp) {
+    T acc[3] = {T(0), T(0), T(0)};
+    for (int s = 0; s < WPL; ++s) {
+      const Wheel<T>& w = wh[s];
+      for (int i = 0; i < 3; ++i) acc[i] += w.J * w.a[i] * x_sp[s];
+      y_sp[s] = w.J * dot3(w.a, x_sh + 3) + w.cdiag * x_sp[s];
+    }
+    Tm::sum_n(acc);
+    T c1[3], c2[3];
+    cross3(c1, C.mcom, x_sh + 3);  // m c x a_ang
+    cross3(c2, C.mcom, x_sh);      // m c x a_lin
+    const T* I = C.inertiaO;
+    const T* a = x_sh + 3;
+    for (int i = 0; i < 3; ++i) y_sh[i] = C.mass[0] * x_sh[i] - c1[i];
+    y_sh[3] = c2[0] + I[0] * a[0] + I[3] * a[1] + I[4] * a[2] + acc[0];
+    y_sh[4] = c2[1] + I[3] * a[0] + I[1] * a[1] + I[5] * a[2] + acc[1];
+    y_sh[5] = c2[2] + I[4] * a[0] + I[5] * a[1] + I[2] * a[2] + acc[2] + C.h_inertia[0] * x_sh[6] + C.h_inertia[1] * x_sh[7];
+    for (int i = 0; i < 2; ++i) y_sh[6 + i] = C.h_inertia[i] * a[2] + (C.h_inertia[i] + C.h_armature[i]) * x_sh[6 + i];
+  }
+
+  // constant shared block of M~ (packed lower triangle), optionally with h * damping on the steer diagonal
+  ACKB_HD static void shared_mass(const Consts<T>& C, T hdamp, T* S) {
+    for (int i = 0; i < 36; ++i) S[i] = T(0);
+    const T m = C.mass[0], cx = C.mcom[0], cy = C.mcom[1], cz = C.mcom[2];
+    S[tri(0, 0)] = S[tri(1, 1)] = S[tri(2, 2)] = m;
+    // (ang, lin) block = [m c]x
+    S[tri(3, 1)] = -cz; S[tri(3, 2)] = cy;
+    S[tri(4, 0)] = cz;  S[tri(4, 2)] = -cx;
+    S[tri(5, 0)] = -cy; S[tri(5, 1)] = cx;
+    const T* I = C.inertiaO;
+    S[tri(3, 3)] = I[0]; S[tri(4, 4)] = I[1]; S[tri(5, 5)] = I[2];
+    S[tri(4, 3)] = I[3]; S[tri(5, 3)] = I[4]; S[tri(5, 4)] = I[5];
+    for (int i = 0; i < 2; ++i) {
+      S[tri(6 + i, 5)] = C.h_inertia[i];
+      S[tri(6 + i, 6 + i)] = C.h_inertia[i] + C.h_armature[i] + hdamp * C.h_damping[i];
+    }
+  }
+
+  // solve (M~ + hdamp * diag(damping)) x = rhs   (B5 / B16: spin dofs eliminated per lane, 8x8 LDL^T)
+  ACKB_HD static void solve_M(const Consts<T>& C, const Wheel<T>* wh, T hdamp, const T* rhs_sh, const T* rhs_sp, T* x_sh, T* x_sp) {
+    T part[9];
+    for (int i = 0; i < 9; ++i) part[i] = T(0);  // Schur update of the ang block (6) and of the ang rhs (3)
+    T cinv[WPL];
+    for (int s = 0; s < WPL; ++s) {
+      const Wheel<T>& w = wh[s];
+      cinv[s] = T(1) / (w.cdiag + hdamp * C.h_damping[w.hidx]);
+      T b[3] = {w.J * w.a[0], w.J * w.a[1], w.J * w.a[2]};
+      part[0] -= b[0] * b[0] * cinv[s]; part[1] -= b[1] * b[0] * cinv[s]; part[2] -= b[1] * b[1] * cinv[s];
+      part[3] -= b[2] * b[0] * cinv[s]; part[4] -= b[2] * b[1] * cinv[s]; part[5] -= b[2] * b[2] * cinv[s];
+      for (int i = 0; i < 3; ++i) part[6 + i] -= b[i] * rhs_sp[s] * cinv[s];
+    }
+    Tm::sum_n(part);
+    T S[36];
+    shared_mass(C, hdamp, S);
+    S[tri(3, 3)] += part[0]; S[tri(4, 3)] += part[1]; S[tri(4, 4)] += part[2];
+    S[tri(5, 3)] += part[3]; S[tri(5, 4)] += part[4]; S[tri(5, 5)] += part[5];
+    for (int i = 0; i < 8; ++i) x_sh[i] = rhs_sh[i];
+    for (int i = 0; i < 3; ++i) x_sh[3 + i] += part[6 + i];
+    ldl8_factor(S);
+    ldl8_solve(S, x_sh);
+    for (int s = 0; s < WPL; ++s) {
+      const Wheel<T>& w = wh[s];
+      x_sp[s] = (rhs_sp[s] - w.J * dot3(w.a, x_sh + 3)) * cinv[s];
+    }
+  }
+
+  // residuals z = F Jp a - aref of the wheel contacts at accelerations (a_sh, a_sp)
+  ACKB_HD static void contact_residuals(const Kin<T>& k, const Wheel<T>* wh, const T* a_sh, const T* a_sp, T (*z)[2][3], bool sub_aref) {
+    for (int s = 0; s < WPL; ++s) {
+      const Wheel<T>& w = wh[s];
+      T ast = w.isL * a_sh[6] + w.isR * a_sh[7];
+      for (int c = 0; c < 2; ++c) {
+        project_point(k, w.con[c], a_sh, a_sh + 3, a_sp[s], ast, z[s][c]);
+        if (sub_aref) for (int i = 0; i < 3; ++i) z[s][c][i] -= w.con[c].aref[i];
+      }
+    }
+  }
+
+  // constraint cost at a point (needs Ma for the Gauss term); returns the team-summed total
+  ACKB_HD static T total_cost(const Consts<T>& C, const State& e, const Wheel<T>* wh, const SharedRows<T>& sr, const T* a_sh,
+                              const T* a_sp, const T* Ma_sh, const T* Ma_sp, const T* tau_sh, const T* tau_sp, const T* as_sh,
+                              const T* as_sp, const T (*z)[2][3]) {
+    T priv = T(0);
+    for (int s = 0; s < WPL; ++s) {
+      const Wheel<T>& w = wh[s];
+      T f, q, phi[3], qq[4];
+      priv += floss_row(a_sp[s] + C.h_flB[w.hidx] * e.dsp[s], C.h_floss[w.hidx], C.h_flR[w.hidx], &f, &q);
+      for (int c = 0; c < 2; ++c) priv += pyramid_rows(w.con[c], z[s][c], phi, qq);
+      priv += T(0.5) * (Ma_sp[s] - tau_sp[s]) * (a_sp[s] - as_sp[s]);
+    }
+    priv = Tm::sum(priv);
+    T fL, fR, hLL, hLR, hRR;
+    T cost = shared_rows_eval(sr, a_sh[6], a_sh[7], &fL, &fR, &hLL, &hLR, &hRR);
+    T g = T(0);
+    for (int i = 0; i < 8; ++i) g += (Ma_sh[i] - tau_sh[i]) * (a_sh[i] - as_sh[i]);
+    return cost + T(0.5) * g + priv;
+  }
+
+  // ---- one physics substep (mj_step): everything between kinematics and integration.
+  // `k` must hold the kinematics of the current state.
+  ACKB_HD static void dynamics(const Consts<T>& C, State& e, const Kin<T>& k, const T* ctrl, int lane, StepDiag& diag,
+                               DebugTap<T>* tap) {
+    const T h = C.timestep[0];
+    T vb[3];
+    for (int i = 0; i < 3; ++i) vb[i] = k.R[i] * e.vw[0] + k.R[3 + i] * e.vw[1] + k.R[6 + i] * e.vw[2];
+
+    Wheel<T> wh[WPL];
+    for (int s = 0; s < WPL; ++s) {
+      setup_wheel(C, e, lane * WPL + s, s, wh[s]);
+      collide_wheel(C, e, k, vb, lane * WPL + s, s, wh[s], diag);
+    }
+    // plate hull vs floor: flagged only (35 mm clearance; reachable only after a roll-over)
+    if (lane == 0) {
+      const int nh = (int)C.nhull[0];
+      const T hO = e.p[2] - C.plane_z[0];
+      for (int i = 0; i < nh; ++i) if (dot3(k.n, &C.hull_pts[3 * i]) + hO <= T(0)) diag.unsupported = 1;
+    }
+    SharedRows<T> sr;
+    make_shared_rows(C, e, sr);
+
+    T tau_sh[8], tau_sp[WPL], as_sh[8], as_sp[WPL];
+    smooth_forces(C, e, k, wh, ctrl, lane, tau_sh, tau_sp);
+    solve_M(C, wh, T(0), tau_sh, tau_sp, as_sh, as_sp);
+
+    // ---- warm start (stored in MuJoCo coordinates): keep it if its cost beats qacc_smooth
+    T a_sh[8], a_sp[WPL], Ma_sh[8], Ma_sp[WPL];
+    for (int i = 0; i < 3; ++i) {
+      a_sh[i] = k.R[i] * e.warm_l[0] + k.R[3 + i] * e.warm_l[1] + k.R[6 + i] * e.warm_l[2];
+      a_sh[3 + i] = e.warm_a[i];
+    }
+    a_sh[6] = e.warm_st[0]; a_sh[7] = e.warm_st[1];
+    for (int s = 0; s < WPL; ++s) a_sp[s] = e.warm_sp[s];
+    mul_M(C, wh, a_sh, a_sp, Ma_sh, Ma_sp);
+    T z[WPL][2][3], zs[WPL][2][3];
+    contact_residuals(k, wh, a_sh, a_sp, z, true);
+    contact_residuals(k, wh, as_sh, as_sp, zs, true);
+    T cost_w = total_cost(C, e, wh, sr, a_sh, a_sp, Ma_sh, Ma_sp, tau_sh, tau_sp, as_sh, as_sp, z);
+    T cost_s = total_cost(C, e, wh, sr, as_sh, as_sp, tau_sh, tau_sp, tau_sh, tau_sp, as_sh, as_sp, zs);
+    if (!(cost_w <= cost_s)) {  // also taken when the warm start is NaN
+      for (int i = 0; i < 8; ++i) { a_sh[i] = as_sh[i]; Ma_sh[i] = tau_sh[i]; }
+      for (int s = 0; s < WPL; ++s) {
+        a_sp[s] = as_sp[s]; Ma_sp[s] = tau_sp[s];
+        for (int c = 0; c < 2; ++c) for (int i = 0; i < 3; ++i) z[s][c][i] = zs[s][c][i];
+      }
+    }
+
+    // ---- B14 Newton iterations on the primal cost
+    const T tol = mjmax(C.tolerance[0], N::tol_floor);
+    const int maxit = (int)C.iterations[0], maxls = (int)C.ls_iterations[0];
+    int iter = 0, nls = 0;
+    for (;;) {
+      // Hessian in arrow form and gradient; per-lane parts: S(36), reduced rhs(8), sum gsp^2/c (1)
+      T part[45];
+      for (int i = 0; i < 45; ++i) part[i] = T(0);
+      T gsp[WPL], cw[WPL], b[WPL][8];
+      for (int s = 0; s < WPL; ++s) {
+        const Wheel<T>& w = wh[s];
+        T gsh_w[8];
+        for (int i = 0; i < 8; ++i) { gsh_w[i] = T(0); b[s][i] = T(0); }
+        for (int i = 0; i < 3; ++i) b[s][3 + i] = w.J * w.a[i];
+        T f, q;
+        floss_row(a_sp[s] + C.h_flB[w.hidx] * e.dsp[s], C.h_floss[w.hidx], C.h_flR[w.hidx], &f, &q);
+        gsp[s] = Ma_sp[s] - tau_sp[s] - f;
+        cw[s] = w.cdiag + q / C.h_flR[w.hidx];
+        for (int c = 0; c < 2; ++c) {
+          const Contact<T>& con = w.con[c];
+          T phi[3], qq[4];
+          pyramid_rows(con, z[s][c], phi, qq);
+          // W = weights of (n, t1, t2) outer products for the active rows; S3 = D F^T W F (body frame, symmetric)
+          const T mu = con.mu;
+          T W00 = qq[0] + qq[1] + qq[2] + qq[3], W01 = mu * (qq[0] - qq[1]), W02 = mu * (qq[2] - qq[3]);
+          T W11 = mu * mu * (qq[0] + qq[1]), W22 = mu * mu * (qq[2] + qq[3]);
+          T S3[3][3];
+          for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j)
+              S3[i][j] = con.D * (W00 * k.n[i] * k.n[j] + W01 * (k.n[i] * k.t1[j] + k.t1[i] * k.n[j]) +
+                                  W02 * (k.n[i] * k.t2[j] + k.t2[i] * k.n[j]) + W11 * k.t1[i] * k.t1[j] + W22 * k.t2[i] * k.t2[j]);
+          // point Jacobian columns for the shared dofs: [e0 e1 e2 | e_i x X | isL w | isR w], spin column u
+          T Jc[9][3];
+          for (int j = 0; j < 3; ++j) {
+            Jc[0][j] = (j == 0) ? T(1) : T(0); Jc[1][j] = (j == 1) ? T(1) : T(0); Jc[2][j] = (j == 2) ? T(1) : T(0);
+          }
+          Jc[3][0] = T(0);       Jc[3][1] = -con.x[2]; Jc[3][2] = con.x[1];    // ex x X
+          Jc[4][0] = con.x[2];   Jc[4][1] = T(0);      Jc[4][2] = -con.x[0];   // ey x X
+          Jc[5][0] = -con.x[1];  Jc[5][1] = con.x[0];  Jc[5][2] = T(0);        // ez x X
+          for (int j = 0; j < 3; ++j) { Jc[6][j] = w.isL * con.w[j]; Jc[7][j] = w.isR * con.w[j]; Jc[8][j] = con.u[j]; }
+          T P[9][3];  // S3 * column
+          for (int a = 0; a < 9; ++a)
+            for (int i = 0; i < 3; ++i) P[a][i] = S3[i][0] * Jc[a][0] + S3[i][1] * Jc[a][1] + S3[i][2] * Jc[a][2];
+          for (int a = 0; a < 8; ++a)
+            for (int bb = 0; bb <= a; ++bb) part[tri(a, bb)] += dot3(Jc[a], P[bb]);
+          for (int a = 0; a < 8; ++a) b[s][a] += dot3(Jc[a], P[8]);
+          cw[s] += dot3(Jc[8], P[8]);
+          // body-frame contact force and its generalised image (enters the gradient with a minus sign)
+          T Phi[3];
+          for (int i = 0; i < 3; ++i) Phi[i] = k.n[i] * phi[0] + k.t1[i] * phi[1] + k.t2[i] * phi[2];
+          for (int a = 0; a < 8; ++a) gsh_w[a] -= dot3(Jc[a], Phi);
+          gsp[s] -= dot3(Jc[8], Phi);
+        }
+        const T ci = T(1) / cw[s];
+        for (int a = 0; a < 8; ++a) {
+          for (int bb = 0; bb <= a; ++bb) part[tri(a, bb)] -= b[s][a] * b[s][bb] * ci;
+          part[36 + a] += gsh_w[a] - b[s][a] * gsp[s] * ci;
+        }
+        part[44] += gsp[s] * gsp[s] * ci;
+      }
+      Tm::sum_n(part);
+      T S[36];
+      shared_mass(C, T(0), S);
+      for (int i = 0; i < 36; ++i) S[i] += part[i];
+      T fL, fR, hLL, hLR, hRR;
+      shared_rows_eval(sr, a_sh[6], a_sh[7], &fL, &fR, &hLL, &hLR, &hRR);
+      S[tri(6, 6)] += hLL; S[tri(7, 6)] += hLR; S[tri(7, 7)] += hRR;
+      T rhs[8], x_sh[8], x_sp[WPL];
+      for (int i = 0; i < 8; ++i) rhs[i] = Ma_sh[i] - tau_sh[i] + part[36 + i];
+      rhs[6] -= fL; rhs[7] -= fR;
+      for (int i = 0; i < 8; ++i) x_sh[i] = rhs[i];
+      ldl8_factor(S);
+      ldl8_solve(S, x_sh);
+      T lam2 = part[44];  // Newton decrement g^T H^-1 g
+      for (int i = 0; i < 8; ++i) lam2 += rhs[i] * x_sh[i];
+      // predicted improvement of a full Newton step is lam2/2: stop when it is below tolerance
+      if (!(C.solver_scale[0] * T(0.5) * lam2 >= tol) || iter >= maxit) break;
+      // search = -H^-1 g
+      for (int s = 0; s < WPL; ++s) {
+        T dotb = T(0);
+        for (int a = 0; a < 8; ++a) dotb += b[s][a] * x_sh[a];
+        x_sp[s] = -(gsp[s] - dotb) / cw[s];
+      }
+      for (int i = 0; i < 8; ++i) x_sh[i] = -x_sh[i];
+      T Mv_sh[8], Mv_sp[WPL], zv[WPL][2][3];
+      mul_M(C, wh, x_sh, x_sp, Mv_sh, Mv_sp);
+      contact_residuals(k, wh, x_sh, x_sp, zv, false);
+      // exact line search: safeguarded Newton on f'(alpha); f'(0) = -lam2, f''(0) = lam2 so alpha_1 = 1
+      T quad[2] = {T(0), T(0)};  // team-summed private parts of s.M.s and s.(Ma - tau)
+      for (int s = 0; s < WPL; ++s) { quad[0] += x_sp[s] * Mv_sp[s]; quad[1] += x_sp[s] * (Ma_sp[s] - tau_sp[s]); }
+      Tm::sum_n(quad);
+      T sMs = quad[0], sg = quad[1];
+      for (int i = 0; i < 8; ++i) { sMs += x_sh[i] * Mv_sh[i]; sg += x_sh[i] * (Ma_sh[i] - tau_sh[i]); }
+      T alpha = T(1), lo = T(0), hi = T(-1);
+      for (int ls = 0; ls < maxls; ++ls) {
+        T d[2] = {T(0), T(0)};
+        for (int s = 0; s < WPL; ++s) {
+          const Wheel<T>& w = wh[s];
+          T f, q;
+          floss_row(a_sp[s] + alpha * x_sp[s] + C.h_flB[w.hidx] * e.dsp[s], C.h_floss[w.hidx], C.h_flR[w.hidx], &f, &q);
+          d[0] -= f * x_sp[s];
+          d[1] += q / C.h_flR[w.hidx] * x_sp[s] * x_sp[s];
+          for (int c = 0; c < 2; ++c) {
+            const Contact<T>& con = w.con[c];
+            const T* z0 = z[s][c]; const T* z1 = zv[s][c];
+            const T xr[4] = {z0[0] + con.mu * z0[1] + alpha * (z1[0] + con.mu * z1[1]), z0[0] - con.mu * z0[1] + alpha * (z1[0] - con.mu * z1[1]),
+                             z0[0] + con.mu * z0[2] + alpha * (z1[0] + con.mu * z1[2]), z0[0] - con.mu * z0[2] + alpha * (z1[0] - con.mu * z1[2])};
+            const T jr[4] = {z1[0] + con.mu * z1[1], z1[0] - con.mu * z1[1], z1[0] + con.mu * z1[2], z1[0] - con.mu * z1[2]};
+            for (int r = 0; r < 4; ++r)
+              if (xr[r] < T(0)) { d[0] += con.D * xr[r] * jr[r]; d[1] += con.D * jr[r] * jr[r]; }
+          }
+        }
+        Tm::sum_n(d);
+        T gL, gR, kLL, kLR, kRR;
+        shared_rows_eval(sr, a_sh[6] + alpha * x_sh[6], a_sh[7] + alpha * x_sh[7], &gL, &gR, &kLL, &kLR, &kRR);
+        T d1 = alpha * sMs + sg + d[0] - gL * x_sh[6] - gR * x_sh[7];
+        T d2 = sMs + d[1] + kLL * x_sh[6] * x_sh[6] + T(2) * kLR * x_sh[6] * x_sh[7] + kRR * x_sh[7] * x_sh[7];
+        ++nls;
+        if (N::abs_(d1) <= N::ls_rel * lam2) break;
+        if (d1 < T(0)) lo = alpha; else hi = alpha;
+        T an = alpha - d1 / d2;
+        if (hi >= T(0) && (an <= lo || an >= hi)) an = T(0.5) * (lo + hi);
+        if (an == alpha) break;
+        alpha = an;
+      }
+      for (int i = 0; i < 8; ++i) { a_sh[i] += alpha * x_sh[i]; Ma_sh[i] += alpha * Mv_sh[i]; }
+      for (int s = 0; s < WPL; ++s) {
+        a_sp[s] += alpha * x_sp[s]; Ma_sp[s] += alpha * Mv_sp[s];
+        for (int c = 0; c < 2; ++c) for (int i = 0; i < 3; ++i) z[s][c][i] += alpha * zv[s][c][i];
+      }
+      ++iter;
+    }
+    diag.niter = iter;
+
+    // ---- constraint force J^T f at the solution
+    T fc_part[8], fc_sp[WPL];
+    for (int i = 0; i < 8; ++i) fc_part[i] = T(0);
+    for (int s = 0; s < WPL; ++s) {
+      const Wheel<T>& w = wh[s];
+      T f, q;
+      floss_row(a_sp[s] + C.h_flB[w.hidx] * e.dsp[s], C.h_floss[w.hidx], C.h_flR[w.hidx], &f, &q);
+      fc_sp[s] = f;
+      for (int c = 0; c < 2; ++c) {
+        const Contact<T>& con = w.con[c];
+        T phi[3], qq[4], Phi[3], xF[3];
+        pyramid_rows(con, z[s][c], phi, qq);
+        for (int i = 0; i < 3; ++i) Phi[i] = k.n[i] * phi[0] + k.t1[i] * phi[1] + k.t2[i] * phi[2];
+        cross3(xF, con.x, Phi);
+        for (int i = 0; i < 3; ++i) { fc_part[i] += Phi[i]; fc_part[3 + i] += xF[i]; }
+        T ws = dot3(con.w, Phi);
+        fc_part[6] += w.isL * ws; fc_part[7] += w.isR * ws;
+        fc_sp[s] += dot3(con.u, Phi);
+      }
+    }
+    Tm::sum_n(fc_part);
+    {
+      T fL, fR, hLL, hLR, hRR;
+      shared_rows_eval(sr, a_sh[6], a_sh[7], &fL, &fR, &hLL, &hLR, &hRR);
+      fc_part[6] += fL; fc_part[7] += fR;
+    }
+
+    // ---- B16 Euler with implicit joint damping
+    T rhs_sh[8], rhs_sp[WPL], ai_sh[8], ai_sp[WPL];
+    for (int i = 0; i < 8; ++i) rhs_sh[i] = tau_sh[i] + fc_part[i];
+    for (int s = 0; s < WPL; ++s) rhs_sp[s] = tau_sp[s] + fc_sp[s];
+    solve_M(C, wh, h, rhs_sh, rhs_sp, ai_sh, ai_sp);
+
+    if (tap) {
+      for (int i = 0; i < 8; ++i) { tap->tau[i] = tau_sh[i]; tap->a_smooth[i] = as_sh[i]; tap->a[i] = a_sh[i]; tap->fc[i] = fc_part[i]; }
+      for (int s = 0; s < WPL; ++s) {
+        int wi = lane * WPL + s;
+        tap->tau[8 + wi] = tau_sp[s]; tap->a_smooth[8 + wi] = as_sp[s]; tap->a[8 + wi] = a_sp[s]; tap->fc[8 + wi] = fc_sp[s];
+      }
+      tap->niter = iter; tap->nls = nls;
+    }
+
+    // warm start for the next step = solver acceleration, MuJoCo coordinates
+    for (int i = 0; i < 3; ++i) {
+      e.warm_l[i] = k.R[3 * i] * a_sh[0] + k.R[3 * i + 1] * a_sh[1] + k.R[3 * i + 2] * a_sh[2];
+      e.warm_a[i] = a_sh[3 + i];
+    }
+    e.warm_st[0] = a_sh[6]; e.warm_st[1] = a_sh[7];
+    for (int s = 0; s < WPL; ++s) e.warm_sp[s] = a_sp[s];
+
+    // velocities, then positions with the new velocities (semi-implicit)
+    for (int i = 0; i < 3; ++i) {
+      e.vw[i] += h * (k.R[3 * i] * ai_sh[0] + k.R[3 * i + 1] * ai_sh[1] + k.R[3 * i + 2] * ai_sh[2]);
+      e.om[i] += h * ai_sh[3 + i];
+    }
+    for (int i = 0; i < 2; ++i) { e.dst[i] += h * ai_sh[6 + i]; e.st[i] += h * e.dst[i]; }
+    for (int s = 0; s < WPL; ++s) { e.dsp[s] += h * ai_sp[s]; e.sp[s] += h * e.dsp[s]; }
+    for (int i = 0; i < 3; ++i) e.p[i] += h * e.vw[i];
+    {
+      T wn = N::sqrt_(dot3(e.om, e.om));
+      T ax[3] = {T(1), T(0), T(0)};
+      if (wn >= N::minval) { ax[0] = e.om[0] / wn; ax[1] = e.om[1] / wn; ax[2] = e.om[2] / wn; }
+      T half = T(0.5) * h * wn, sn = N::sin_(half), cs = N::cos_(half);
+      T r0 = cs, r1 = ax[0] * sn, r2 = ax[1] * sn, r3 = ax[2] * sn;
+      T q0 = e.q[0], q1 = e.q[1], q2 = e.q[2], q3 = e.q[3];
+      e.q[0] = q0 * r0 - q1 * r1 - q2 * r2 - q3 * r3;
+      e.q[1] = q0 * r1 + q1 * r0 + q2 * r3 - q3 * r2;
+      e.q[2] = q0 * r2 - q1 * r3 + q2 * r0 + q3 * r1;
+      e.q[3] = q0 * r3 + q1 * r2 - q2 * r1 + q3 * r0;
+    }
+  }
+
+  // ---- B9 rangefinder of observation slot `slot` (ray against the floor plane; boxes in the scene)
+  ACKB_HD static T lidar_ray(const Consts<T>& C, const State& e, const Kin<T>& k, int beam) {
+    const T cb = C.lidar_cos[beam], sb = C.lidar_sin[beam];
+    const T o[3] = {C.lidar_pos[0] + C.lidar_r[0] * cb, C.lidar_pos[1] + C.lidar_r[0] * sb, C.lidar_pos[2]};
+    T best = T(-1);
+    // floor: local z of the ray = n . d ; height of the origin = n . o + hO
+    const T lvz = k.n[0] * cb + k.n[1] * sb;
+    const T ow[3] = {e.p[0] + k.R[0] * o[0] + k.R[1] * o[1] + k.R[2] * o[2], e.p[1] + k.R[3] * o[0] + k.R[4] * o[1] + k.R[5] * o[2],
+                     e.p[2] + k.R[6] * o[0] + k.R[7] * o[1] + k.R[8] * o[2]};
+    const T dw[3] = {k.R[0] * cb + k.R[1] * sb, k.R[3] * cb + k.R[4] * sb, lvz};
+    if (!(lvz > -N::minval)) {
+      T x = -(ow[2] - C.plane_z[0]) / lvz;
+      if (x >= T(0)) {
+        T px = ow[0] + x * dw[0], py = ow[1] + x * dw[1];
+        if ((C.plane_half[0] <= T(0) || N::abs_(px) <= C.plane_half[0]) && (C.plane_half[1] <= T(0) || N::abs_(py) <= C.plane_half[1])) best = x;
+      }
+    }
+    const int nbox = (int)C.nbox[0];
+    for (int bi = 0; bi < nbox; ++bi) {
+      const T lp[3] = {ow[0] - C.box_cx[bi], ow[1] - C.box_cy[bi], ow[2] - C.box_z[0]};
+      for (int i = 0; i < 3; ++i) {
+        if (N::abs_(dw[i]) <= N::minval) continue;
+        const int a = (i + 1) % 3, b = (i + 2) % 3;
+        for (int side = -1; side <= 1; side += 2) {
+          T sol = (T(side) * C.box_half[i] - lp[i]) / dw[i];
+          if (sol < T(0)) continue;
+          T pa = lp[a] + sol * dw[a], pb = lp[b] + sol * dw[b];
+          if (N::abs_(pa) <= C.box_half[a] && N::abs_(pb) <= C.box_half[b] && (best < T(0) || sol < best)) best = sol;
+        }
+      }
+    }
+    if (C.lidar_cutoff[0] > T(0) && best > C.lidar_cutoff[0]) best = C.lidar_cutoff[0];
+    return best;
+  }
+};
+
+}  // namespace ackb

@@ -1,0 +1,508 @@
+// ackb_kernels.cu -- sm_100a kernels and the C ABI (include/ackb.h) of the batched Ackermann simulator.
+//
+// HBM layout (per handle): structure of arrays, env index fastest:
+//   qpos[13][N] qvel[12][N] warm[12][N] goal[2][N] ref[2][N]   (T = float | double)
+//   step_count[N] i32, episode[N] u32, ep_return[N] f32
+// One fused kernel per env.step(): LANES lanes per environment (4 = one per wheel), state loaded once,
+// frame_skip substeps in registers, observation staged per warp in shared memory and written with
+// coalesced stores, auto-reset fused.  No tensor cores: the largest dense object is 8 x 8.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+
+#include "ackb.h"
+#include "ackb_env.cuh"
+
+using namespace ackb;
+
+namespace {
+
+__constant__ Consts<float> g_consts_f;
+__constant__ Consts<double> g_consts_d;
+template <typename T> __device__ __forceinline__ const Consts<T>& dev_consts();
+template <> __device__ __forceinline__ const Consts<float>& dev_consts<float>() { return g_consts_f; }
+template <> __device__ __forceinline__ const Consts<double>& dev_consts<double>() { return g_consts_d; }
+
+template <typename T>
+struct DevState {
+  T *qpos, *qvel, *warm, *goal, *ref;
+  int32_t* step_count;
+  uint32_t* episode;
+  float* ep_return;
+  int n;
+};
+
+struct StepArgs {
+  const float* action;
+  float* obs;
+  float* reward;
+  uint8_t* terminated;
+  uint8_t* truncated;
+  float* terminal_obs;
+  int32_t* ncon;
+  const uint8_t* mask;
+  ackb_stats_t* stats;
+  unsigned long long seed;
+  uint32_t step_index;
+  int frame_skip, auto_reset, obs_dim;
+};
+
+template <typename T>
+struct SoAAcc {
+  const DevState<T>& s;
+  int env;
+  __device__ __forceinline__ T qpos(int i) const { return s.qpos[(size_t)i * s.n + env]; }
+  __device__ __forceinline__ T qvel(int i) const { return s.qvel[(size_t)i * s.n + env]; }
+  __device__ __forceinline__ T warm(int i) const { return s.warm[(size_t)i * s.n + env]; }
+  __device__ __forceinline__ void set_qpos(int i, T v) { s.qpos[(size_t)i * s.n + env] = v; }
+  __device__ __forceinline__ void set_qvel(int i, T v) { s.qvel[(size_t)i * s.n + env] = v; }
+  __device__ __forceinline__ void set_warm(int i, T v) { s.warm[(size_t)i * s.n + env] = v; }
+};
+struct RowSink {
+  float* row;
+  __device__ __forceinline__ void put(int slot, float v) { row[slot] = v; }
+};
+
+__device__ __forceinline__ unsigned warp_sum_u32(unsigned v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+constexpr int kBlock = 128;
+
+// synthetic action of (step, env): Philox(seed) with counter (step, env, 2, tag) -> U(-1, 1)^2
+__device__ __forceinline__ void synth_action(unsigned long long seed, uint32_t step, uint32_t env, float* a0, float* a1) {
+  uint32_t r[4];
+  philox4x32(step, env, 2u, 0x41434B42u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+  *a0 = 2.0f * u01(r[0]) - 1.0f;
+  *a1 = 2.0f * u01(r[1]) - 1.0f;
+}
+
+template <typename T, int LANES>
+__global__ void __launch_bounds__(kBlock) step_kernel(DevState<T> st, StepArgs a) {
+  using E = EnvOps<T, LANES>;
+  constexpr int EPW = 32 / LANES;
+  extern __shared__ float tile[];
+  const Consts<T>& C = dev_consts<T>();
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int env_raw = tid / LANES, lane = tid % LANES;
+  const bool valid = env_raw < st.n;
+  const int env = valid ? env_raw : st.n - 1;
+  const int warp = threadIdx.x >> 5, lid = threadIdx.x & 31;
+  float* wtile = tile + (size_t)warp * EPW * a.obs_dim;
+  RowSink sink{wtile + (lid / LANES) * a.obs_dim};
+
+  typename E::State e;
+  SoAAcc<T> acc{st, env};
+  E::load_state(acc, lane, e);
+  Episode<T> ep;
+  ep.goal[0] = st.goal[env]; ep.goal[1] = st.goal[(size_t)st.n + env];
+  ep.ref[0] = st.ref[env]; ep.ref[1] = st.ref[(size_t)st.n + env];
+  ep.step_count = st.step_count[env];
+  ep.episode = st.episode[env];
+  float a0, a1;
+  if (a.action) { float2 v = reinterpret_cast<const float2*>(a.action)[env]; a0 = v.x; a1 = v.y; }
+  else synth_action(a.seed, a.step_index, (uint32_t)env, &a0, &a1);
+
+  StepOut<T> out;
+  StepDiag diag{0, 0, 0};
+  E::step_env(C, e, ep, a0, a1, a.frame_skip, lane, sink, out, diag, (DebugTap<T>*)nullptr);
+  __syncwarp();
+
+  // contact count of the last substep, summed over the lanes of the environment
+  int ncon = diag.ncon, unsup = diag.unsupported;
+  ncon = Team<LANES>::sum(ncon);
+  unsup = Team<LANES>::sum(unsup);
+
+  const bool done = out.terminated || out.truncated;
+  float ret = st.ep_return[env] + out.reward;
+  const int ep_len = ep.step_count;
+  if (done && a.auto_reset) {
+    if (a.terminal_obs && valid)
+      for (int j = lane; j < a.obs_dim; j += LANES) a.terminal_obs[(size_t)env * a.obs_dim + j] = sink.row[j];
+    Team<LANES>::sync();
+    E::reset_env(C, e, ep, lane, a.seed, (uint32_t)env);
+    Kin<T> k;
+    E::S::kinematics(e, k);
+    T dist, minl;
+    // all lanes of the team take this branch together (done is team-uniform), so the team shuffles are safe
+    E::observe(C, e, k, ep, lane, sink, &dist, &minl);
+  }
+  __syncwarp();
+
+  // statistics: one atomic per warp and counter
+  if (a.stats) {
+    const bool lead = valid && lane == 0;
+    unsigned v_done = warp_sum_u32(lead && done ? 1u : 0u), v_succ = warp_sum_u32(lead && out.terminated ? 1u : 0u);
+    unsigned v_coll = warp_sum_u32(lead && out.collision ? 1u : 0u), v_uns = warp_sum_u32(lead && unsup ? 1u : 0u);
+    unsigned v_it = warp_sum_u32(lead ? (unsigned)diag.niter : 0u);
+    float r_sum = lead && done ? ret : 0.f, l_sum = lead && done ? (float)ep_len : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { r_sum += __shfl_xor_sync(0xffffffffu, r_sum, o); l_sum += __shfl_xor_sync(0xffffffffu, l_sum, o); }
+    if (lid == 0) {
+      if (v_done) { atomicAdd(&a.stats->episodes, (unsigned long long)v_done); atomicAdd(&a.stats->return_sum, (double)r_sum); atomicAdd(&a.stats->length_sum, (double)l_sum); }
+      if (v_succ) atomicAdd(&a.stats->successes, (unsigned long long)v_succ);
+      if (v_coll) atomicAdd(&a.stats->collisions, (unsigned long long)v_coll);
+      if (v_uns) atomicAdd(&a.stats->unsupported, (unsigned long long)v_uns);
+      atomicAdd(&a.stats->solver_iters, (unsigned long long)v_it);
+    }
+  }
+
+  // coalesced store of the warp's observation tile (the warp's environments are consecutive rows)
+  {
+    const int env0 = (blockIdx.x * blockDim.x + warp * 32) / LANES;
+    int nrow = st.n - env0;
+    nrow = nrow < 0 ? 0 : (nrow > EPW ? EPW : nrow);
+    const int total = nrow * a.obs_dim;
+    float* dst = a.obs + (size_t)env0 * a.obs_dim;
+    for (int i = lid; i < total; i += 32) dst[i] = wtile[i];
+  }
+  if (valid) {
+    E::store_state(acc, lane, e);
+    if (lane == 0) {
+      st.goal[env] = ep.goal[0]; st.goal[(size_t)st.n + env] = ep.goal[1];
+      st.ref[env] = ep.ref[0]; st.ref[(size_t)st.n + env] = ep.ref[1];
+      st.step_count[env] = ep.step_count;
+      st.episode[env] = ep.episode;
+      st.ep_return[env] = (done && a.auto_reset) ? 0.f : ret;
+      a.reward[env] = out.reward;
+      a.terminated[env] = out.terminated;
+      a.truncated[env] = out.truncated;
+      if (a.ncon) a.ncon[env] = ncon;
+    }
+  }
+}
+
+template <typename T, int LANES>
+__global__ void __launch_bounds__(kBlock) reset_kernel(DevState<T> st, StepArgs a) {
+  using E = EnvOps<T, LANES>;
+  constexpr int EPW = 32 / LANES;
+  extern __shared__ float tile[];
+  const Consts<T>& C = dev_consts<T>();
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int env_raw = tid / LANES, lane = tid % LANES;
+  const bool valid = env_raw < st.n;
+  const int env = valid ? env_raw : st.n - 1;
+  const int warp = threadIdx.x >> 5, lid = threadIdx.x & 31;
+  RowSink sink{tile + ((size_t)warp * EPW + lid / LANES) * a.obs_dim};
+  const bool sel = (a.mask ? (a.mask[env] != 0) : true) && valid;   // team-uniform
+  typename E::State e;
+  Episode<T> ep;
+  ep.episode = st.episode[env];
+  E::reset_env(C, e, ep, lane, a.seed, (uint32_t)env);
+  Kin<T> k;
+  E::S::kinematics(e, k);
+  T dist, minl;
+  E::observe(C, e, k, ep, lane, sink, &dist, &minl);
+  __syncwarp();
+  if (!sel) return;
+  for (int j = lane; j < a.obs_dim; j += LANES) a.obs[(size_t)env * a.obs_dim + j] = sink.row[j];
+  SoAAcc<T> acc{st, env};
+  E::store_state(acc, lane, e);
+  if (lane == 0) {
+    st.goal[env] = ep.goal[0]; st.goal[(size_t)st.n + env] = ep.goal[1];
+    st.ref[env] = ep.ref[0]; st.ref[(size_t)st.n + env] = ep.ref[1];
+    st.step_count[env] = 0;
+    st.episode[env] = ep.episode;
+    st.ep_return[env] = 0.f;
+  }
+}
+
+__global__ void random_action_kernel(float* action, int n, unsigned long long seed, uint32_t step) {
+  int env = blockIdx.x * blockDim.x + threadIdx.x;
+  if (env >= n) return;
+  float a0, a1;
+  synth_action(seed, step, (uint32_t)env, &a0, &a1);
+  reinterpret_cast<float2*>(action)[env] = make_float2(a0, a1);
+}
+
+thread_local std::string g_last_error;
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// handle
+// ------------------------------------------------------------------------------------------------
+struct ackb_handle {
+  int n = 0, device = 0, dtype = ACKB_F32, lanes = 4, obs_dim = 0;
+  unsigned long long seed = 0;
+  uint32_t step_index = 0;
+  unsigned long long stat_steps = 0;
+  unsigned long long launches = 0;
+  double* consts_host = nullptr;
+  void* state = nullptr;        // one allocation holding every SoA array
+  size_t elem = 4;
+  DevState<float> sf{};
+  DevState<double> sd{};
+  ackb_stats_t* stats = nullptr;
+  // staging for ackb_step_host
+  float *d_action = nullptr, *d_obs = nullptr, *d_reward = nullptr;
+  uint8_t *d_term = nullptr, *d_trunc = nullptr;
+  cudaStream_t own_stream = nullptr;
+  std::string err;
+};
+
+namespace {
+ackb_handle* g_const_owner[64] = {nullptr};   // per device: whose constants are in __constant__ memory
+
+int fail(ackb_handle* h, int code, const std::string& msg) {
+  g_last_error = msg;
+  if (h) h->err = msg;
+  return code;
+}
+#define CK(call)                                                                                          \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess) return fail(h, ACKB_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+template <typename T>
+void carve(ackb_handle* h, DevState<T>& s) {
+  T* p = static_cast<T*>(h->state);
+  const size_t n = h->n;
+  s.n = h->n;
+  s.qpos = p; p += 13 * n;
+  s.qvel = p; p += 12 * n;
+  s.warm = p; p += 12 * n;
+  s.goal = p; p += 2 * n;
+  s.ref = p; p += 2 * n;
+  s.step_count = reinterpret_cast<int32_t*>(p);
+  s.episode = reinterpret_cast<uint32_t*>(s.step_count + n);
+  s.ep_return = reinterpret_cast<float*>(s.episode + n);
+}
+
+int ensure_consts(ackb_handle* h, cudaStream_t stream) {
+  if (g_const_owner[h->device] == h) return ACKB_OK;
+  CK(cudaDeviceSynchronize());
+  if (h->dtype == ACKB_F32) {
+    static thread_local Consts<float> tmp;
+    float* d = reinterpret_cast<float*>(&tmp);
+    for (int i = 0; i < kNumConsts; ++i) d[i] = (float)h->consts_host[i];
+    CK(cudaMemcpyToSymbol(g_consts_f, &tmp, sizeof tmp));
+  } else {
+    CK(cudaMemcpyToSymbol(g_consts_d, h->consts_host, sizeof(Consts<double>)));
+  }
+  g_const_owner[h->device] = h;
+  (void)stream;
+  return ACKB_OK;
+}
+
+template <typename T>
+int launch_step(ackb_handle* h, DevState<T>& st, const StepArgs& a, cudaStream_t stream, bool is_reset) {
+  const int lanes = h->lanes;
+  const long long threads = (long long)h->n * lanes;
+  const int grid = (int)((threads + kBlock - 1) / kBlock);
+  const size_t smem = (size_t)(kBlock / lanes) * a.obs_dim * sizeof(float);
+#define LAUNCH(L)                                                                \
+  if (is_reset) reset_kernel<T, L><<<grid, kBlock, smem, stream>>>(st, a);        \
+  else step_kernel<T, L><<<grid, kBlock, smem, stream>>>(st, a);
+  if (lanes == 4) { LAUNCH(4) }
+  else if (lanes == 2) { LAUNCH(2) }
+  else { LAUNCH(1) }
+#undef LAUNCH
+  h->launches++;
+  CK(cudaGetLastError());
+  return ACKB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int ackb_consts_len(void) { return kNumConsts; }
+
+const char* ackb_last_error(const ackb_handle* h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+int ackb_create(const double* consts, size_t consts_len, int num_envs, int device, int dtype, uint64_t seed, int lanes_per_env,
+                ackb_handle** out) {
+  ackb_handle* h = nullptr;
+  if (!consts || !out || num_envs <= 0) return fail(nullptr, ACKB_ERR_ARG, "ackb_create: null pointer or num_envs <= 0");
+  if ((int)consts_len != kNumConsts) return fail(nullptr, ACKB_ERR_ARG, "ackb_create: constants blob has the wrong length");
+  if (dtype != ACKB_F32 && dtype != ACKB_F64) return fail(nullptr, ACKB_ERR_ARG, "ackb_create: dtype must be ACKB_F32 or ACKB_F64");
+  if (lanes_per_env == 0) lanes_per_env = 4;
+  if (lanes_per_env != 1 && lanes_per_env != 2 && lanes_per_env != 4) return fail(nullptr, ACKB_ERR_ARG, "ackb_create: lanes_per_env must be 1, 2 or 4");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, ACKB_ERR_NO_DEVICE, "ackb_create: no CUDA device (there is no CPU fallback)");
+  if (device < 0 || device >= ndev || device >= 64) return fail(nullptr, ACKB_ERR_ARG, "ackb_create: bad device index");
+  h = new (std::nothrow) ackb_handle();
+  if (!h) return fail(nullptr, ACKB_ERR_ARG, "ackb_create: out of host memory");
+  h->n = num_envs; h->device = device; h->dtype = dtype; h->seed = seed; h->lanes = lanes_per_env;
+  h->elem = dtype == ACKB_F32 ? 4 : 8;
+  h->consts_host = new double[kNumConsts];
+  memcpy(h->consts_host, consts, sizeof(double) * kNumConsts);
+  h->obs_dim = (int)reinterpret_cast<const Consts<double>*>(consts)->nbeam[0] + 7;
+  CK(cudaSetDevice(device));
+  const size_t n = num_envs;
+  const size_t bytes = (13 + 12 + 12 + 2 + 2) * n * h->elem + 3 * n * 4;
+  CK(cudaMalloc(&h->state, bytes));
+  CK(cudaMemset(h->state, 0, bytes));
+  if (dtype == ACKB_F32) carve(h, h->sf); else carve(h, h->sd);
+  CK(cudaMalloc(&h->stats, sizeof(ackb_stats_t)));
+  CK(cudaMemset(h->stats, 0, sizeof(ackb_stats_t)));
+  CK(cudaMalloc(&h->d_action, n * 2 * sizeof(float)));
+  CK(cudaMalloc(&h->d_obs, n * h->obs_dim * sizeof(float)));
+  CK(cudaMalloc(&h->d_reward, n * sizeof(float)));
+  CK(cudaMalloc(&h->d_term, n));
+  CK(cudaMalloc(&h->d_trunc, n));
+  CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  *out = h;
+  return ACKB_OK;
+}
+
+int ackb_destroy(ackb_handle* h) {
+  if (!h) return ACKB_ERR_ARG;
+  cudaSetDevice(h->device);
+  if (g_const_owner[h->device] == h) g_const_owner[h->device] = nullptr;
+  cudaFree(h->state); cudaFree(h->stats); cudaFree(h->d_action); cudaFree(h->d_obs); cudaFree(h->d_reward);
+  cudaFree(h->d_term); cudaFree(h->d_trunc);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete[] h->consts_host;
+  delete h;
+  return ACKB_OK;
+}
+
+int ackb_num_envs(const ackb_handle* h) { return h ? h->n : ACKB_ERR_ARG; }
+int ackb_obs_dim(const ackb_handle* h) { return h ? h->obs_dim : ACKB_ERR_ARG; }
+int ackb_dtype(const ackb_handle* h) { return h ? h->dtype : ACKB_ERR_ARG; }
+unsigned long long ackb_launch_count(const ackb_handle* h) { return h ? h->launches : 0ull; }
+
+int ackb_reset(ackb_handle* h, const uint8_t* dev_mask, float* dev_obs, void* stream) {
+  if (!h || !dev_obs) return fail(h, ACKB_ERR_ARG, "ackb_reset: null pointer");
+  CK(cudaSetDevice(h->device));
+  int rc = ensure_consts(h, (cudaStream_t)stream);
+  if (rc) return rc;
+  StepArgs a{};
+  a.obs = dev_obs; a.mask = dev_mask; a.seed = h->seed; a.obs_dim = h->obs_dim; a.stats = h->stats;
+  return h->dtype == ACKB_F32 ? launch_step(h, h->sf, a, (cudaStream_t)stream, true) : launch_step(h, h->sd, a, (cudaStream_t)stream, true);
+}
+
+int ackb_step(ackb_handle* h, const float* dev_action, int frame_skip, int auto_reset, float* dev_obs, float* dev_reward,
+              uint8_t* dev_terminated, uint8_t* dev_truncated, float* dev_terminal_obs, int32_t* dev_ncon, void* stream) {
+  if (!h || !dev_obs || !dev_reward || !dev_terminated || !dev_truncated) return fail(h, ACKB_ERR_ARG, "ackb_step: null output pointer");
+  if (frame_skip < 1) return fail(h, ACKB_ERR_ARG, "ackb_step: frame_skip must be >= 1");
+  CK(cudaSetDevice(h->device));
+  int rc = ensure_consts(h, (cudaStream_t)stream);
+  if (rc) return rc;
+  StepArgs a{};
+  a.action = dev_action; a.obs = dev_obs; a.reward = dev_reward; a.terminated = dev_terminated; a.truncated = dev_truncated;
+  a.terminal_obs = dev_terminal_obs; a.ncon = dev_ncon; a.stats = h->stats; a.seed = h->seed; a.step_index = h->step_index++;
+  h->stat_steps += (unsigned long long)h->n;
+  a.frame_skip = frame_skip; a.auto_reset = auto_reset; a.obs_dim = h->obs_dim;
+  return h->dtype == ACKB_F32 ? launch_step(h, h->sf, a, (cudaStream_t)stream, false) : launch_step(h, h->sd, a, (cudaStream_t)stream, false);
+}
+
+int ackb_step_host(ackb_handle* h, const float* host_action, int frame_skip, int auto_reset, float* host_obs, float* host_reward,
+                   uint8_t* host_terminated, uint8_t* host_truncated) {
+  if (!h || !host_action || !host_obs || !host_reward || !host_terminated || !host_truncated) return fail(h, ACKB_ERR_ARG, "ackb_step_host: null pointer");
+  CK(cudaSetDevice(h->device));
+  const size_t n = h->n;
+  cudaStream_t s = h->own_stream;
+  CK(cudaMemcpyAsync(h->d_action, host_action, n * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+  int rc = ackb_step(h, h->d_action, frame_skip, auto_reset, h->d_obs, h->d_reward, h->d_term, h->d_trunc, nullptr, nullptr, s);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(host_obs, h->d_obs, n * h->obs_dim * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(host_reward, h->d_reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(host_terminated, h->d_term, n, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(host_truncated, h->d_trunc, n, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return ACKB_OK;
+}
+
+int ackb_random_actions(ackb_handle* h, float* dev_action, void* stream) {
+  if (!h || !dev_action) return fail(h, ACKB_ERR_ARG, "ackb_random_actions: null pointer");
+  CK(cudaSetDevice(h->device));
+  random_action_kernel<<<(h->n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dev_action, h->n, h->seed, h->step_index);
+  h->launches++;
+  CK(cudaGetLastError());
+  return ACKB_OK;
+}
+
+}  // extern "C"
+
+// ---- state access (tests): row-major host doubles <-> SoA device arrays -----------------------------
+namespace {
+template <typename T>
+int xfer(ackb_handle* h, T* dev, double* host, int rows, bool to_host) {
+  const size_t n = h->n;
+  T* tmp = new T[rows * n];
+  if (to_host) {
+    CK(cudaMemcpy(tmp, dev, rows * n * sizeof(T), cudaMemcpyDeviceToHost));
+    for (size_t e = 0; e < n; ++e) for (int r = 0; r < rows; ++r) host[e * rows + r] = (double)tmp[r * n + e];
+  } else {
+    for (size_t e = 0; e < n; ++e) for (int r = 0; r < rows; ++r) tmp[r * n + e] = (T)host[e * rows + r];
+    CK(cudaMemcpy(dev, tmp, rows * n * sizeof(T), cudaMemcpyHostToDevice));
+  }
+  delete[] tmp;
+  return ACKB_OK;
+}
+template <typename T>
+int state_io(ackb_handle* h, DevState<T>& s, double* qpos, double* qvel, double* warm, bool to_host) {
+  int rc = 0;
+  if (qpos && (rc = xfer(h, s.qpos, qpos, 13, to_host))) return rc;
+  if (qvel && (rc = xfer(h, s.qvel, qvel, 12, to_host))) return rc;
+  if (warm && (rc = xfer(h, s.warm, warm, 12, to_host))) return rc;
+  return ACKB_OK;
+}
+template <typename T>
+int episode_io(ackb_handle* h, DevState<T>& s, double* goal, double* ref, int32_t* sc, bool to_host) {
+  int rc = 0;
+  if (goal && (rc = xfer(h, s.goal, goal, 2, to_host))) return rc;
+  if (ref && (rc = xfer(h, s.ref, ref, 2, to_host))) return rc;
+  if (sc) {
+    if (to_host) CK(cudaMemcpy(sc, s.step_count, h->n * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    else CK(cudaMemcpy(s.step_count, sc, h->n * sizeof(int32_t), cudaMemcpyHostToDevice));
+  }
+  return ACKB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int ackb_get_state(ackb_handle* h, double* q, double* v, double* w) {
+  if (!h) return ACKB_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  return h->dtype == ACKB_F32 ? state_io(h, h->sf, q, v, w, true) : state_io(h, h->sd, q, v, w, true);
+}
+int ackb_set_state(ackb_handle* h, const double* q, const double* v, const double* w) {
+  if (!h) return ACKB_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  return h->dtype == ACKB_F32 ? state_io(h, h->sf, (double*)q, (double*)v, (double*)w, false)
+                              : state_io(h, h->sd, (double*)q, (double*)v, (double*)w, false);
+}
+int ackb_get_episode(ackb_handle* h, double* goal, double* ref, int32_t* sc) {
+  if (!h) return ACKB_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  return h->dtype == ACKB_F32 ? episode_io(h, h->sf, goal, ref, sc, true) : episode_io(h, h->sd, goal, ref, sc, true);
+}
+int ackb_set_episode(ackb_handle* h, const double* goal, const double* ref, const int32_t* sc) {
+  if (!h) return ACKB_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  return h->dtype == ACKB_F32 ? episode_io(h, h->sf, (double*)goal, (double*)ref, (int32_t*)sc, false)
+                              : episode_io(h, h->sd, (double*)goal, (double*)ref, (int32_t*)sc, false);
+}
+
+int ackb_stats(ackb_handle* h, ackb_stats_t* out) {
+  if (!h || !out) return ACKB_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out, h->stats, sizeof(ackb_stats_t), cudaMemcpyDeviceToHost));
+  out->env_steps = h->stat_steps;
+  return ACKB_OK;
+}
+int ackb_stats_reset(ackb_handle* h) {
+  if (!h) return ACKB_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemset(h->stats, 0, sizeof(ackb_stats_t)));
+  h->stat_steps = 0;
+  return ACKB_OK;
+}
+
+}  // extern "C"

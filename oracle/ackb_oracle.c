@@ -1136,3 +1136,47 @@ int orc_contact(const OData* d, int i, double* out) {
   out[17] = c->mu;
   return 0;
 }
+
+/* ------------------------------------------------------------------------- */
+/*  CPU baseline loop: the reference's per-step work, restated in C            */
+/*  (action -> BicycleController (src/core/controller.py:98-140) -> mj_step),  */
+/*  used by bench.py's cpu_baseline / --impl reference legs only.              */
+/* ------------------------------------------------------------------------- */
+static void bicycle_ctrl_c(double v, double omega, double* ctrl) {
+  const double eps = 1e-5, L = 0.20, Tw = 0.174, rw = 0.0325;
+  double delta;
+  if (fabs(omega) < 1e-6) delta = 0;
+  else {
+    double sgn = omega > 0 ? 1.0 : (omega < 0 ? -1.0 : 0.0);
+    delta = atan((L * omega) / (fabs(v) > eps ? v : sgn * eps));
+  }
+  const double lim = 0.6108652381980153;
+  delta = delta < -lim ? -lim : (delta > lim ? lim : delta);
+  double vl, vr;
+  if (fabs(delta) < 1e-6) vl = vr = v;
+  else {
+    double tn = tan(delta), R = fabs(tn) > eps ? L / tn : INFINITY;
+    double ot = fabs(R) > eps ? v / R : 0.0;
+    vl = ot * (R - Tw / 2); vr = ot * (R + Tw / 2);
+  }
+  ctrl[0] = delta < -0.61 ? -0.61 : (delta > 0.61 ? 0.61 : delta);
+  double wl = vl / rw, wr = vr / rw;
+  ctrl[1] = wl < -50 ? -50 : (wl > 50 ? 50 : wl);
+  ctrl[2] = wr < -50 ? -50 : (wr > 50 ? 50 : wr);
+  if (!(fabs(ctrl[0]) <= 1e10 && fabs(ctrl[1]) <= 1e10 && fabs(ctrl[2]) <= 1e10)) ctrl[0] = ctrl[1] = ctrl[2] = 0;
+}
+/* n_steps env steps of frame_skip substeps with U(-1,1) actions (xorshift), episodes of max_steps; returns substeps done */
+long orc_rollout(const OModel* m, OData* d, long n_steps, int frame_skip, int max_steps, unsigned long long seed, const double* spawn_qpos) {
+  unsigned long long s = seed * 2685821657736338717ULL + 1442695040888963407ULL;
+  long sub = 0;
+  int ep = 0;
+  for (long i = 0; i < n_steps; i++) {
+    if (ep == 0) { orc_reset(m, d); memcpy(d->qpos, spawn_qpos, sizeof(double) * m->nq); }
+    double a[2];
+    for (int k = 0; k < 2; k++) { s ^= s << 13; s ^= s >> 7; s ^= s << 17; a[k] = (double)(float)(2.0 * ((s >> 11) * (1.0 / 9007199254740992.0)) - 1.0); }
+    bicycle_ctrl_c(a[0], a[1], d->ctrl);
+    for (int f = 0; f < frame_skip; f++) { orc_step(m, d); sub++; }
+    if (++ep >= max_steps) ep = 0;
+  }
+  return sub;
+}

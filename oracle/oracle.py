@@ -38,6 +38,8 @@ def lib():
             fn.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int)]
             fn.restype = ctypes.c_int
         L.orc_contact.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+        L.orc_rollout.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_ulonglong, ctypes.c_void_p]
+        L.orc_rollout.restype = ctypes.c_long
         _lib = L
     return _lib
 
@@ -167,3 +169,8 @@ class OracleSim:
 
     def step(self, n: int = 1):
         lib().orc_step_n(self.m, self.d, n)
+
+    def rollout(self, n_steps: int, frame_skip: int = 1, max_steps: int = 1000, seed: int = 0, spawn_qpos=None) -> int:
+        """C loop: random action -> BicycleController -> frame_skip x step, with episode resets (bench CPU baseline)."""
+        sq = np.ascontiguousarray(self.model["qpos0"] if spawn_qpos is None else spawn_qpos, dtype=np.float64)
+        return int(lib().orc_rollout(self.m, self.d, n_steps, frame_skip, max_steps, seed, sq.ctypes.data_as(ctypes.c_void_p)))

@@ -1,0 +1,119 @@
+// hostsim.cpp -- TEST-ONLY host build of the per-environment device code (LANES = 1).
+// Lets the arithmetic of mujoco_playground_b200/csrc/ackb_core.cuh / ackb_env.cuh be checked against
+// the oracle on a machine without a GPU.  It is not part of the product and is never loaded by it.
+#include <cstring>
+#include "../../mujoco_playground_b200/csrc/ackb_env.cuh"
+
+using namespace ackb;
+
+namespace {
+template <typename T>
+struct ArrAcc {
+  double *qp, *qv, *wm;
+  T qpos(int i) const { return (T)qp[i]; }
+  T qvel(int i) const { return (T)qv[i]; }
+  T warm(int i) const { return (T)wm[i]; }
+  void set_qpos(int i, T v) { qp[i] = (double)v; }
+  void set_qvel(int i, T v) { qv[i] = (double)v; }
+  void set_warm(int i, T v) { wm[i] = (double)v; }
+};
+struct ObsSink {
+  float* o;
+  void put(int slot, float v) { o[slot] = v; }
+};
+template <typename T>
+void to_consts(const double* blob, Consts<T>& C) {
+  T* dst = reinterpret_cast<T*>(&C);
+  for (int i = 0; i < kNumConsts; ++i) dst[i] = (T)blob[i];
+}
+
+template <typename T>
+void substep(const double* blob, double* qpos, double* qvel, double* warm, const double* ctrl_in, int nsteps, double* tap_out, int* diag_out) {
+  using E = EnvOps<T, 1>;
+  Consts<T> C;
+  to_consts(blob, C);
+  typename E::State e;
+  ArrAcc<T> acc{qpos, qvel, warm};
+  E::load_state(acc, 0, e);
+  T ctrl[4];
+  for (int i = 0; i < 4; ++i) ctrl[i] = (T)ctrl_in[i];
+  StepDiag diag{0, 0, 0};
+  DebugTap<T> tap;
+  for (int s = 0; s < nsteps; ++s) {
+    Kin<T> k;
+    E::S::kinematics(e, k);
+    diag.ncon = 0;
+    E::S::dynamics(C, e, k, ctrl, 0, diag, &tap);
+  }
+  E::store_state(acc, 0, e);
+  if (tap_out) {
+    for (int i = 0; i < 12; ++i) { tap_out[i] = tap.tau[i]; tap_out[12 + i] = tap.a_smooth[i]; tap_out[24 + i] = tap.a[i]; tap_out[36 + i] = tap.fc[i]; }
+    tap_out[48] = tap.niter; tap_out[49] = tap.nls;
+  }
+  if (diag_out) { diag_out[0] = diag.ncon; diag_out[1] = diag.unsupported; diag_out[2] = diag.niter; }
+}
+
+template <typename T>
+void env_step(const double* blob, double* qpos, double* qvel, double* warm, double* epd /*goal2 ref2*/, int* epi /*step_count episode*/,
+              const float* action, int frame_skip, float* obs, float* out, int* diag_out) {
+  using E = EnvOps<T, 1>;
+  Consts<T> C;
+  to_consts(blob, C);
+  typename E::State e;
+  ArrAcc<T> acc{qpos, qvel, warm};
+  E::load_state(acc, 0, e);
+  Episode<T> ep;
+  ep.goal[0] = (T)epd[0]; ep.goal[1] = (T)epd[1]; ep.ref[0] = (T)epd[2]; ep.ref[1] = (T)epd[3];
+  ep.step_count = epi[0]; ep.episode = (uint32_t)epi[1];
+  ObsSink sink{obs};
+  StepOut<T> so;
+  StepDiag diag{0, 0, 0};
+  E::step_env(C, e, ep, action[0], action[1], frame_skip, 0, sink, so, diag, (DebugTap<T>*)nullptr);
+  E::store_state(acc, 0, e);
+  epi[0] = ep.step_count;
+  out[0] = so.reward; out[1] = so.terminated; out[2] = so.truncated; out[3] = so.collision; out[4] = so.goal_distance; out[5] = so.min_lidar;
+  if (diag_out) { diag_out[0] = diag.ncon; diag_out[1] = diag.unsupported; diag_out[2] = diag.niter; }
+}
+
+template <typename T>
+void env_reset(const double* blob, double* qpos, double* qvel, double* warm, double* epd, int* epi, unsigned long long seed, unsigned env_id, float* obs) {
+  using E = EnvOps<T, 1>;
+  Consts<T> C;
+  to_consts(blob, C);
+  typename E::State e;
+  Episode<T> ep;
+  ep.episode = (uint32_t)epi[1];
+  E::reset_env(C, e, ep, 0, seed, env_id);
+  Kin<T> k;
+  E::S::kinematics(e, k);
+  ObsSink sink{obs};
+  T dist, minl;
+  E::observe(C, e, k, ep, 0, sink, &dist, &minl);
+  ArrAcc<T> acc{qpos, qvel, warm};
+  E::store_state(acc, 0, e);
+  epd[0] = (double)ep.goal[0]; epd[1] = (double)ep.goal[1]; epd[2] = (double)ep.ref[0]; epd[3] = (double)ep.ref[1];
+  epi[0] = ep.step_count; epi[1] = (int)ep.episode;
+}
+}  // namespace
+
+extern "C" {
+int hs_nconsts() { return kNumConsts; }
+void hs_substep(int f32, const double* blob, double* qpos, double* qvel, double* warm, const double* ctrl, int nsteps, double* tap, int* diag) {
+  if (f32) substep<float>(blob, qpos, qvel, warm, ctrl, nsteps, tap, diag);
+  else substep<double>(blob, qpos, qvel, warm, ctrl, nsteps, tap, diag);
+}
+void hs_env_step(int f32, const double* blob, double* qpos, double* qvel, double* warm, double* epd, int* epi, const float* action,
+                 int frame_skip, float* obs, float* out, int* diag) {
+  if (f32) env_step<float>(blob, qpos, qvel, warm, epd, epi, action, frame_skip, obs, out, diag);
+  else env_step<double>(blob, qpos, qvel, warm, epd, epi, action, frame_skip, obs, out, diag);
+}
+void hs_env_reset(int f32, const double* blob, double* qpos, double* qvel, double* warm, double* epd, int* epi, unsigned long long seed,
+                  unsigned env_id, float* obs) {
+  if (f32) env_reset<float>(blob, qpos, qvel, warm, epd, epi, seed, env_id, obs);
+  else env_reset<double>(blob, qpos, qvel, warm, epd, epi, seed, env_id, obs);
+}
+void hs_action_to_ctrl(int f32, const double* blob, float a0, float a1, double* ctrl) {
+  if (f32) { Consts<float> C; to_consts(blob, C); float c[4]; action_to_ctrl<float>(C, a0, a1, c); for (int i = 0; i < 4; ++i) ctrl[i] = c[i]; }
+  else { Consts<double> C; to_consts(blob, C); double c[4]; action_to_ctrl<double>(C, a0, a1, c); for (int i = 0; i < 4; ++i) ctrl[i] = c[i]; }
+}
+}

@@ -1,0 +1,187 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Run with -m gpu on a B200.
+
+Tolerances (BASELINE.json north_star): single-step qpos/qvel within 1e-5 relative in fp64 mode and
+1e-3 in fp32 mode; <=100-step trajectories within the tolerance stated in each test; integer contact
+counts and done flags exact.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _models():
+    from mujoco_playground_b200.models import load_model
+    return load_model("v2")
+
+
+def _random_states(M, n, rng, ground_frac=0.5):
+    qpos = np.tile(M["qpos0"], (n, 1))
+    qvel = np.zeros((n, 12))
+    for i in range(n):
+        if rng.uniform() < ground_frac:
+            qpos[i, 2] = 0.0645 + rng.uniform(-0.0005, 0.002)
+            ang = rng.normal(size=3) * 0.02
+            q = np.array([1.0, *ang])
+            qvel[i] = rng.normal(size=12) * np.array([1, 1, .1, .3, .3, 1, 20, 20, 3, 20, 3, 20]) * 0.5
+        else:
+            qpos[i, 2] = rng.uniform(0.1, 0.5)
+            q = rng.normal(size=4)
+            qvel[i] = rng.normal(size=12) * np.array([1, 1, 1, 3, 3, 3, 20, 20, 3, 20, 3, 20])
+        qpos[i, 0:2] = rng.uniform(-5, 5, 2)
+        qpos[i, 3:7] = q / np.linalg.norm(q)
+        qpos[i, 7:] = rng.uniform(-0.5, 0.5, 6)
+        if rng.uniform() < 0.2:
+            qpos[i, 9] = 0.62   # beyond the steer limit
+    return qpos, qvel
+
+
+def _rel(a, b):
+    return np.abs(a - b).max() / max(1e-9, np.abs(b).max())
+
+
+@pytest.mark.parametrize("dtype,tol", [("float64", 1e-5), ("float32", 1e-3)])
+def test_single_step_matches_oracle(dtype, tol):
+    from mujoco_playground_b200 import BatchedAckermannEnv
+    from oracle.env_oracle import OracleEnv
+    M = _models()
+    n = 96
+    rng = np.random.default_rng(5)
+    qpos, qvel = _random_states(M, n, rng)
+    warm = rng.normal(size=(n, 12))
+    acts = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+    env = BatchedAckermannEnv(n, dtype=dtype, auto_reset=False, solver_tolerance=1e-12 if dtype == "float64" else None)
+    env.reset()
+    env.set_state(qpos, qvel, warm)
+    _, _, _, _, info = env.step(torch.from_numpy(acts).cuda())
+    q2, v2, w2 = env.get_state()
+    ncon = info["ncon"].cpu().numpy()
+    o = OracleEnv(M, tolerance=1e-12)
+    worst_q = worst_v = 0.0
+    for i in range(n):
+        o.reset(np.zeros(2))
+        o.sim.qpos[:] = qpos[i]; o.sim.qvel[:] = qvel[i]; o.sim.qacc_warmstart[:] = warm[i]
+        o.step(acts[i])
+        assert ncon[i] == o.sim.ncon, f"env {i}: contact count {ncon[i]} != oracle {o.sim.ncon}"
+        worst_q = max(worst_q, _rel(q2[i], o.sim.qpos))
+        worst_v = max(worst_v, _rel(v2[i], o.sim.qvel))
+    print(f"{dtype}: worst relative qpos {worst_q:.3e} qvel {worst_v:.3e}")
+    assert worst_q < tol and worst_v < tol
+    env.close()
+
+
+@pytest.mark.parametrize("dtype,steps,tol_q,tol_obs", [("float64", 100, 1e-7, 1e-4), ("float32", 60, 5e-4, 5e-3)])
+def test_trajectory_from_reset(dtype, steps, tol_q, tol_obs):
+    """<=100-step trajectories from the reference reset state with U(-1,1) actions.  fp32 tolerance is absolute
+    5e-4 on qpos over 60 steps; beyond ~150 steps fp32 diverges chaotically through contact switching."""
+    from mujoco_playground_b200 import BatchedAckermannEnv
+    from oracle.env_oracle import OracleEnv
+    M = _models()
+    n = 6
+    env = BatchedAckermannEnv(n, dtype=dtype, seed=3, auto_reset=False, solver_tolerance=1e-12 if dtype == "float64" else None)
+    obs0 = env.reset().cpu().numpy().copy()
+    goal, ref, _ = env.get_episode()
+    rng = np.random.default_rng(11)
+    oracles = [OracleEnv(M, tolerance=1e-12) for _ in range(n)]
+    for k, o in enumerate(oracles):
+        assert np.abs(o.reset(goal[k]) - obs0[k]).max() < 1e-5
+    for t in range(steps):
+        a = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+        obs, rew, term, trunc, info = env.step(torch.from_numpy(a).cuda())
+        obs, rew, term, trunc, ncon = (x.cpu().numpy() for x in (obs, rew, term, trunc, info["ncon"]))
+        for k, o in enumerate(oracles):
+            oo, r, te, tr, inf = o.step(a[k])
+            if dtype == "float64":
+                assert ncon[k] == inf["ncon"], f"step {t} env {k}: ncon {ncon[k]} vs {inf['ncon']}"
+                assert bool(term[k]) == te and bool(trunc[k]) == tr
+                assert np.abs(oo - obs[k]).max() < tol_obs
+                assert abs(r - rew[k]) < 1e-4 * max(1.0, abs(r))
+    q, v, _ = env.get_state()
+    for k, o in enumerate(oracles):
+        assert np.abs(q[k] - o.sim.qpos).max() < tol_q, f"{dtype} env {k}: qpos error {np.abs(q[k] - o.sim.qpos).max()}"
+    env.close()
+
+
+def test_lane_layouts_agree():
+    """1, 2 and 4 lanes per environment run the same arithmetic up to summation order."""
+    from mujoco_playground_b200 import BatchedAckermannEnv
+    res = []
+    rng = np.random.default_rng(2)
+    acts = rng.uniform(-1, 1, (40, 33, 2)).astype(np.float32)
+    for lanes in (1, 2, 4):
+        env = BatchedAckermannEnv(33, dtype="float64", seed=9, lanes_per_env=lanes, auto_reset=False, frame_skip=2)
+        env.reset()
+        for t in range(40):
+            obs, *_ = env.step(torch.from_numpy(acts[t]).cuda())
+        res.append((env.get_state()[0], obs.cpu().numpy().copy()))
+        env.close()
+    for q, o in res[1:]:
+        assert np.abs(q - res[0][0]).max() < 1e-9
+        assert np.abs(o - res[0][1]).max() < 1e-5
+
+
+def test_auto_reset_truncation_and_terminal_obs():
+    from mujoco_playground_b200 import BatchedAckermannEnv
+    n = 70
+    env = BatchedAckermannEnv(n, dtype="float32", seed=4, max_episode_steps=5, auto_reset=True)
+    obs0 = env.reset().cpu().numpy().copy()
+    last = None
+    for t in range(5):
+        obs, rew, term, trunc, info = env.step(None)
+        if t < 4:
+            assert int(trunc.sum().item()) == 0
+            last = obs.cpu().numpy().copy()
+    assert int(trunc.sum().item()) == n, "every env must truncate at max_episode_steps (ackermann_env.py:219-220)"
+    tobs = info["terminal_observation"].cpu().numpy()
+    new = obs.cpu().numpy()
+    # the new episode starts from the spawn pose: lidar all -1 (level robot), odometry zero
+    assert np.allclose(new[:, 72:75], 0.0, atol=1e-6)
+    assert np.allclose(new[:, :72], obs0[:, :72])
+    # terminal observation continues the old episode (odometry moved a little, same goal as before the reset)
+    assert np.allclose(tobs[:, 75:77] + tobs[:, 72:74], last[:, 75:77] + last[:, 72:74], atol=1e-5)
+    _, _, sc = env.get_episode()
+    assert (sc == 0).all()
+    st = env.stats()
+    assert st["episodes"] == n and st["env_steps"] == 5 * n
+    env.close()
+
+
+def test_step_host_matches_device_step():
+    from mujoco_playground_b200 import BatchedAckermannEnv
+    n = 50
+    rng = np.random.default_rng(8)
+    a = torch.from_numpy(rng.uniform(-1, 1, (n, 2)).astype(np.float32))
+    e1 = BatchedAckermannEnv(n, seed=5, auto_reset=True)
+    e2 = BatchedAckermannEnv(n, seed=5, auto_reset=True)
+    e1.reset(); e2.reset()
+    h = [torch.empty((n, e2.obs_dim)).pin_memory(), torch.empty(n).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory(),
+         torch.empty(n, dtype=torch.uint8).pin_memory()]
+    for _ in range(30):
+        o1, r1, t1, u1, _ = e1.step(a.cuda())
+        e2.step_host(a.pin_memory(), *h)
+    assert torch.equal(o1.cpu(), h[0]) and torch.equal(r1.cpu(), h[1]) and torch.equal(t1.cpu(), h[2])
+    e1.close(); e2.close()
+
+
+def test_gym_adapter_signature():
+    from mujoco_playground_b200 import AckermannRobotEnv
+    env = AckermannRobotEnv()
+    obs, info = env.reset(seed=0)
+    assert obs.shape == (79,) and obs.dtype == np.float32 and set(info) == {"map_name", "goal_position", "start_position"}
+    obs, r, te, tr, info = env.step(np.array([0.5, 0.1], np.float32))
+    assert obs.shape == (79,) and isinstance(r, float) and isinstance(te, bool) and isinstance(tr, bool)
+    assert {"goal_distance", "collision", "min_lidar", "step", "linear_velocity", "angular_velocity"} <= set(info)
+    # reference quirk Q2: no lidar hit (-1) counts as a collision => -50 on an open floor
+    assert info["collision"] and r < -50
+    env.close()
+
+
+def test_no_cpu_fallback_message():
+    from mujoco_playground_b200 import _lib
+    L = _lib.load()
+    import ctypes
+    h = ctypes.c_void_p()
+    rc = L.ackb_create(None, 0, 1, 0, 0, 0, 4, ctypes.byref(h))
+    assert rc < 0 and b"null" in L.ackb_last_error(None)
