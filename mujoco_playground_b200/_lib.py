@@ -6,7 +6,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libackb.so")
+LIB_PATH = os.environ.get("ACKB_LIB", os.path.join(_HERE, "libackb.so"))   # ACKB_LIB: tuning variants only
 _lib = None
 
 

@@ -27,11 +27,17 @@ def consts_layout(path: str = _DEF) -> Dict[str, Tuple[int, int]]:
     return out
 
 
+def _check_power(solimp):
+    assert solimp[4] in (1, 2), "solimp power must be 1 or 2 (other powers are not compiled into the kernels)"
+
+
 def _impedance0(solimp):
+    _check_power(solimp)
     return float(np.clip(solimp[0], 0.0001, 0.9999))
 
 
 def _KB(solref, solimp, timestep):
+    _check_power(solimp)
     tc = max(solref[0], 2 * timestep)
     dmax = float(np.clip(solimp[1], 0.0001, 0.9999))
     if solref[0] <= 0:

@@ -62,7 +62,27 @@ template <> struct Num<float> {
   ACKB_HD static float atan_(float x) { return atanf(x); }
   ACKB_HD static float tan_(float x) { return tanf(x); }
   ACKB_HD static float atan2_(float y, float x) { return atan2f(y, x); }
-  ACKB_HD static float pow_(float x, float y) { return powf(x, y); }
+  // sin/cos of a bounded angle (steer angle, |x| < 1): one MUFU each on the device (abs. error 2^-21.4)
+  ACKB_HD static void sincos_small(float x, float* s, float* c) {
+#if defined(__CUDA_ARCH__)
+    *s = __sinf(x); *c = __cosf(x);
+#else
+    *s = sinf(x); *c = cosf(x);
+#endif
+  }
+  // sin/cos of a tiny angle (half the rotation of one time step): Taylor series, exact to fp32 for |x| < 0.2
+  ACKB_HD static void sincos_tiny(float x, float* s, float* c) {
+    if (fabsf(x) < 0.2f) {
+      const float x2 = x * x;
+      *s = x * (1.0f + x2 * (-1.0f / 6.0f + x2 * (1.0f / 120.0f - x2 * (1.0f / 5040.0f))));
+      *c = 1.0f + x2 * (-0.5f + x2 * (1.0f / 24.0f - x2 * (1.0f / 720.0f)));
+    } else { *s = sinf(x); *c = cosf(x); }
+  }
+  // wrap an angle difference of two atan2 results (|x| <= 2 pi) into [-pi, pi]
+  ACKB_HD static float wrap_pi(float x) {
+    const float pi = 3.14159265358979f;
+    return x > pi ? x - 2.0f * pi : (x < -pi ? x + 2.0f * pi : x);
+  }
   // Newton exit thresholds usable at this precision
   static constexpr float tol_floor = 1e-6f;
   static constexpr float ls_rel = 1e-3f;
@@ -76,7 +96,10 @@ template <> struct Num<double> {
   ACKB_HD static double atan_(double x) { return atan(x); }
   ACKB_HD static double tan_(double x) { return tan(x); }
   ACKB_HD static double atan2_(double y, double x) { return atan2(y, x); }
-  ACKB_HD static double pow_(double x, double y) { return pow(x, y); }
+  ACKB_HD static void sincos_small(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
+  ACKB_HD static void sincos_tiny(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
+  // the reference wraps with arctan2(sin, cos) (ackermann_env.py:252); kept verbatim in fp64 mode
+  ACKB_HD static double wrap_pi(double x) { return atan2(sin(x), cos(x)); }
   static constexpr double tol_floor = 0.0;
   static constexpr double ls_rel = 1e-10;
 };
@@ -86,20 +109,13 @@ template <> struct Num<double> {
 // ------------------------------------------------------------------------------------------------
 template <int LANES>
 struct Team {
-  // lanes of this environment inside the warp: team-uniform (not warp-uniform) branches stay legal
-  ACKB_D static unsigned mask() {
-#if defined(__CUDA_ARCH__)
-    return LANES >= 32 ? 0xffffffffu : (((1u << LANES) - 1u) << ((threadIdx.x & 31u) & ~(unsigned)(LANES - 1)));
-#else
-    return 1u;
-#endif
-  }
+  // All team collectives are executed by the whole (converged) warp with the full mask: control flow around them is
+  // kept warp-uniform with `any()`, lanes of finished environments simply discard their results.
   template <typename T>
   ACKB_D static T sum(T v) {
 #if defined(__CUDA_ARCH__)
-    const unsigned m = mask();
 #pragma unroll
-    for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(m, v, o);
+    for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
 #else
     static_assert(LANES == 1, "host build supports LANES == 1 only");
 #endif
@@ -108,9 +124,8 @@ struct Team {
   template <typename T>
   ACKB_D static T min(T v) {
 #if defined(__CUDA_ARCH__)
-    const unsigned m = mask();
 #pragma unroll
-    for (int o = LANES / 2; o > 0; o >>= 1) { T other = __shfl_xor_sync(m, v, o); v = other < v ? other : v; }
+    for (int o = LANES / 2; o > 0; o >>= 1) { T other = __shfl_xor_sync(0xffffffffu, v, o); v = other < v ? other : v; }
 #endif
     return v;
   }
@@ -119,9 +134,12 @@ struct Team {
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = sum(v[i]);
   }
-  ACKB_D static void sync() {
+  // true if the predicate holds for any lane of the warp (host: the single environment)
+  ACKB_D static bool any(bool p) {
 #if defined(__CUDA_ARCH__)
-    __syncwarp(mask());
+    return __any_sync(0xffffffffu, p) != 0;
+#else
+    return p;
 #endif
   }
 };
@@ -175,10 +193,9 @@ ACKB_HD T impedance(const T* solimp, T pos) {
   if (x >= T(1)) return d1;
   if (x <= T(0)) return d0;
   T y;
-  if (power == T(2)) y = (x <= mid) ? x * x / mid : T(1) - (T(1) - x) * (T(1) - x) / (T(1) - mid);
-  else if (power == T(1)) y = x;
-  else y = (x <= mid) ? Num<T>::pow_(x, power) / Num<T>::pow_(mid, power - 1)
-                      : T(1) - Num<T>::pow_(T(1) - x, power) / Num<T>::pow_(T(1) - mid, power - 1);
+  // solimp power is 1 or 2 in both models (checked by the model compiler); other powers are not compiled in
+  if (power == T(1)) y = x;
+  else y = (x <= mid) ? x * x / mid : T(1) - (T(1) - x) * (T(1) - x) / (T(1) - mid);
   return d0 + y * (d1 - d0);
 }
 
@@ -348,6 +365,19 @@ ACKB_HD T shared_rows_eval(const SharedRows<T>& s, T aL, T aR, T* fL, T* fR, T* 
 }
 
 
+// which zone each shared row is in at steer accelerations (aL, aR): friction loss (-, quadratic, +), limit on/off
+template <typename T>
+ACKB_HD unsigned shared_rows_zone(const SharedRows<T>& s, T aL, T aR) {
+  const T a[2] = {aL, aR};
+  unsigned zn = 0u;
+  for (int i = 0; i < 2; ++i) {
+    const T x = a[i] - s.fl_aref[i], rf = s.flR[i] * s.flf[i];
+    zn = (zn << 2) | (x <= -rf ? 0u : (x >= rf ? 2u : 1u));
+    zn = (zn << 1) | ((s.limD[i] > T(0) && s.lim_sign[i] * a[i] - s.lim_aref[i] < T(0)) ? 1u : 0u);
+  }
+  return zn;
+}
+
 // ------------------------------------------------------------------------------------------------
 // LDL^T of a packed symmetric positive definite 8x8, in registers (fully unrolled).
 // On exit the strict lower triangle holds L and the diagonal holds 1/d.
@@ -435,7 +465,9 @@ struct Sim {
     w.isL = (wi == 2) ? T(1) : T(0);
     w.isR = (wi == 3) ? T(1) : T(0);
     T s = w.isL * e.st[0] + w.isR * e.st[1];
-    w.a[0] = -N::sin_(s); w.a[1] = N::cos_(s); w.a[2] = T(0);  // Rz(s) * (0, 1, 0)
+    T sn, cs;
+    N::sincos_small(s, &sn, &cs);
+    w.a[0] = -sn; w.a[1] = cs; w.a[2] = T(0);  // Rz(s) * (0, 1, 0)
     w.J = C.h_inertia[2 + wi];
     w.cdiag = w.J + C.h_armature[2 + wi];
     w.dsteer = w.isL * e.dst[0] + w.isR * e.dst[1];
@@ -619,75 +651,37 @@ struct Sim {
     }
   }
 
-  // solve (M~ + hdamp * diag(damping)) x = rhs   (B5 / B16: spin dofs eliminated per lane, 8x8 LDL^T)
-  ACKB_HD static void solve_M(const Consts<T>& C, const Wheel<T>* wh, T hdamp, const T* rhs_sh, const T* rhs_sp, T* x_sh, T* x_sp) {
-    T part[9];
-    for (int i = 0; i < 9; ++i) part[i] = T(0);  // Schur update of the ang block (6) and of the ang rhs (3)
-    T cinv[WPL];
+  // point-Jacobian image of the shared/spin accelerations for every contact of this lane:
+  // out = F Jp x  (3-vector in the contact frame per contact)
+  ACKB_HD static void contact_images(const Kin<T>& k, const Wheel<T>* wh, const T* x_sh, const T* x_sp, T (*out)[2][3]) {
+#pragma unroll
     for (int s = 0; s < WPL; ++s) {
       const Wheel<T>& w = wh[s];
-      cinv[s] = T(1) / (w.cdiag + hdamp * C.h_damping[w.hidx]);
-      T b[3] = {w.J * w.a[0], w.J * w.a[1], w.J * w.a[2]};
-      part[0] -= b[0] * b[0] * cinv[s]; part[1] -= b[1] * b[0] * cinv[s]; part[2] -= b[1] * b[1] * cinv[s];
-      part[3] -= b[2] * b[0] * cinv[s]; part[4] -= b[2] * b[1] * cinv[s]; part[5] -= b[2] * b[2] * cinv[s];
-      for (int i = 0; i < 3; ++i) part[6 + i] -= b[i] * rhs_sp[s] * cinv[s];
+      const T ast = w.isL * x_sh[6] + w.isR * x_sh[7];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) project_point(k, w.con[c], x_sh, x_sh + 3, x_sp[s], ast, out[s][c]);
     }
-    Tm::sum_n(part);
-    T S[36];
-    shared_mass(C, hdamp, S);
-    S[tri(3, 3)] += part[0]; S[tri(4, 3)] += part[1]; S[tri(4, 4)] += part[2];
-    S[tri(5, 3)] += part[3]; S[tri(5, 4)] += part[4]; S[tri(5, 5)] += part[5];
-    for (int i = 0; i < 8; ++i) x_sh[i] = rhs_sh[i];
-    for (int i = 0; i < 3; ++i) x_sh[3 + i] += part[6 + i];
-    ldl8_factor(S);
-    ldl8_solve(S, x_sh);
-    for (int s = 0; s < WPL; ++s) {
-      const Wheel<T>& w = wh[s];
-      x_sp[s] = (rhs_sp[s] - w.J * dot3(w.a, x_sh + 3)) * cinv[s];
-    }
-  }
-
-  // residuals z = F Jp a - aref of the wheel contacts at accelerations (a_sh, a_sp)
-  ACKB_HD static void contact_residuals(const Kin<T>& k, const Wheel<T>* wh, const T* a_sh, const T* a_sp, T (*z)[2][3], bool sub_aref) {
-    for (int s = 0; s < WPL; ++s) {
-      const Wheel<T>& w = wh[s];
-      T ast = w.isL * a_sh[6] + w.isR * a_sh[7];
-      for (int c = 0; c < 2; ++c) {
-        project_point(k, w.con[c], a_sh, a_sh + 3, a_sp[s], ast, z[s][c]);
-        if (sub_aref) for (int i = 0; i < 3; ++i) z[s][c][i] -= w.con[c].aref[i];
-      }
-    }
-  }
-
-  // constraint cost at a point (needs Ma for the Gauss term); returns the team-summed total
-  ACKB_HD static T total_cost(const Consts<T>& C, const State& e, const Wheel<T>* wh, const SharedRows<T>& sr, const T* a_sh,
-                              const T* a_sp, const T* Ma_sh, const T* Ma_sp, const T* tau_sh, const T* tau_sp, const T* as_sh,
-                              const T* as_sp, const T (*z)[2][3]) {
-    T priv = T(0);
-    for (int s = 0; s < WPL; ++s) {
-      const Wheel<T>& w = wh[s];
-      T f, q, phi[3], qq[4];
-      priv += floss_row(a_sp[s] + C.h_flB[w.hidx] * e.dsp[s], C.h_floss[w.hidx], C.h_flR[w.hidx], &f, &q);
-      for (int c = 0; c < 2; ++c) priv += pyramid_rows(w.con[c], z[s][c], phi, qq);
-      priv += T(0.5) * (Ma_sp[s] - tau_sp[s]) * (a_sp[s] - as_sp[s]);
-    }
-    priv = Tm::sum(priv);
-    T fL, fR, hLL, hLR, hRR;
-    T cost = shared_rows_eval(sr, a_sh[6], a_sh[7], &fL, &fR, &hLL, &hLR, &hRR);
-    T g = T(0);
-    for (int i = 0; i < 8; ++i) g += (Ma_sh[i] - tau_sh[i]) * (a_sh[i] - as_sh[i]);
-    return cost + T(0.5) * g + priv;
   }
 
   // ---- one physics substep (mj_step): everything between kinematics and integration.
   // `k` must hold the kinematics of the current state.
+  //
+  // Solver structure (B13-B16 fused in ONE loop body so that the instruction footprint stays small):
+  //   every pass assembles the arrow-shaped system  H x = -g  at the current point, LDL^T-factorises its 8 x 8
+  //   Schur complement and solves it.  Newton passes use H = M~ + J^T D J, g = M~ a - tau - J^T f and are followed by
+  //   an exact line search; the last pass ("Euler pass") uses H = M~ + h B, g = -(tau + J^T f), whose solution is the
+  //   implicitly damped acceleration that MuJoCo's Euler integrator advances with.
+  //   The iteration starts from the warm start (previous qacc) as MuJoCo does when its cost beats qacc_smooth; the
+  //   minimiser is unique, so the starting point only affects the iteration count (qacc_smooth is never needed).
   ACKB_HD static void dynamics(const Consts<T>& C, State& e, const Kin<T>& k, const T* ctrl, int lane, StepDiag& diag,
                                DebugTap<T>* tap) {
     const T h = C.timestep[0];
     T vb[3];
+#pragma unroll
     for (int i = 0; i < 3; ++i) vb[i] = k.R[i] * e.vw[0] + k.R[3 + i] * e.vw[1] + k.R[6 + i] * e.vw[2];
 
     Wheel<T> wh[WPL];
+#pragma unroll
     for (int s = 0; s < WPL; ++s) {
       setup_wheel(C, e, lane * WPL + s, s, wh[s]);
       collide_wheel(C, e, k, vb, lane * WPL + s, s, wh[s], diag);
@@ -701,229 +695,324 @@ struct Sim {
     SharedRows<T> sr;
     make_shared_rows(C, e, sr);
 
-    T tau_sh[8], tau_sp[WPL], as_sh[8], as_sp[WPL];
+    T tau_sh[8], tau_sp[WPL];
     smooth_forces(C, e, k, wh, ctrl, lane, tau_sh, tau_sp);
-    solve_M(C, wh, T(0), tau_sh, tau_sp, as_sh, as_sp);
 
-    // ---- warm start (stored in MuJoCo coordinates): keep it if its cost beats qacc_smooth
-    T a_sh[8], a_sp[WPL], Ma_sh[8], Ma_sp[WPL];
+    // current point a (starts at 0 and takes a unit step along the warm start), M~ a, contact residuals z = F Jp a - aref
+    T a_sh[8], a_sp[WPL], Ma_sh[8], Ma_sp[WPL], z[WPL][2][3];
+    T x_sh[8], x_sp[WPL];   // step direction
+    bool warm_ok = true;
+#pragma unroll
     for (int i = 0; i < 3; ++i) {
-      a_sh[i] = k.R[i] * e.warm_l[0] + k.R[3 + i] * e.warm_l[1] + k.R[6 + i] * e.warm_l[2];
-      a_sh[3 + i] = e.warm_a[i];
+      x_sh[i] = k.R[i] * e.warm_l[0] + k.R[3 + i] * e.warm_l[1] + k.R[6 + i] * e.warm_l[2];
+      x_sh[3 + i] = e.warm_a[i];
     }
-    a_sh[6] = e.warm_st[0]; a_sh[7] = e.warm_st[1];
-    for (int s = 0; s < WPL; ++s) a_sp[s] = e.warm_sp[s];
-    mul_M(C, wh, a_sh, a_sp, Ma_sh, Ma_sp);
-    T z[WPL][2][3], zs[WPL][2][3];
-    contact_residuals(k, wh, a_sh, a_sp, z, true);
-    contact_residuals(k, wh, as_sh, as_sp, zs, true);
-    T cost_w = total_cost(C, e, wh, sr, a_sh, a_sp, Ma_sh, Ma_sp, tau_sh, tau_sp, as_sh, as_sp, z);
-    T cost_s = total_cost(C, e, wh, sr, as_sh, as_sp, tau_sh, tau_sp, tau_sh, tau_sp, as_sh, as_sp, zs);
-    if (!(cost_w <= cost_s)) {  // also taken when the warm start is NaN
-      for (int i = 0; i < 8; ++i) { a_sh[i] = as_sh[i]; Ma_sh[i] = tau_sh[i]; }
-      for (int s = 0; s < WPL; ++s) {
-        a_sp[s] = as_sp[s]; Ma_sp[s] = tau_sp[s];
-        for (int c = 0; c < 2; ++c) for (int i = 0; i < 3; ++i) z[s][c][i] = zs[s][c][i];
-      }
+    x_sh[6] = e.warm_st[0]; x_sh[7] = e.warm_st[1];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { warm_ok = warm_ok && (N::abs_(x_sh[i]) <= T(1e10)); a_sh[i] = T(0); Ma_sh[i] = T(0); }
+#pragma unroll
+    for (int s = 0; s < WPL; ++s) {
+      x_sp[s] = e.warm_sp[s];
+      warm_ok = warm_ok && (N::abs_(x_sp[s]) <= T(1e10));
+      a_sp[s] = T(0); Ma_sp[s] = T(0);
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) z[s][c][i] = -wh[s].con[c].aref[i];
+    }
+    if (Tm::sum(warm_ok ? 0 : 1) != 0) {   // unusable warm start: begin at a = 0
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x_sh[i] = T(0);
+#pragma unroll
+      for (int s = 0; s < WPL; ++s) x_sp[s] = T(0);
     }
 
-    // ---- B14 Newton iterations on the primal cost
     const T tol = mjmax(C.tolerance[0], N::tol_floor);
     const int maxit = (int)C.iterations[0], maxls = (int)C.ls_iterations[0];
     int iter = 0, nls = 0;
-    for (;;) {
-      // Hessian in arrow form and gradient; per-lane parts: S(36), reduced rhs(8), sum gsp^2/c (1)
+    // per-environment phase: 0 = step along x then Newton pass, 1 = Euler pass (no step), 2 = finished.
+    // The loop itself is warp-uniform: it runs until every environment of the warp has finished.
+    int phase = 0;
+    bool first = true;
+    T lam2 = T(0);
+    unsigned zone0[WPL];
+    unsigned szone0 = 0u;
+#pragma unroll
+    for (int s = 0; s < WPL; ++s) zone0[s] = 0u;
+    while (Tm::any(phase != 2)) {
+      const bool stepping = (phase == 0);
+      if (Tm::any(stepping)) {
+        // ---- move along x: exact line search (safeguarded Newton on f'(alpha)), then update the point
+        T Mv_sh[8], Mv_sp[WPL], zv[WPL][2][3];
+        mul_M(C, wh, x_sh, x_sp, Mv_sh, Mv_sp);
+        contact_images(k, wh, x_sh, x_sp, zv);
+        T alpha = T(1);
+        bool exact = false;
+        bool ls_on = stepping && !first;
+        T quad[2] = {T(0), T(0)};  // team-summed private parts of s.M.s and s.(Ma - tau)
+#pragma unroll
+        for (int s = 0; s < WPL; ++s) { quad[0] += x_sp[s] * Mv_sp[s]; quad[1] += x_sp[s] * (Ma_sp[s] - tau_sp[s]); }
+        Tm::sum_n(quad);
+        T sMs = quad[0], sg = quad[1];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { sMs += x_sh[i] * Mv_sh[i]; sg += x_sh[i] * (Ma_sh[i] - tau_sh[i]); }
+        T lo = T(0), hi = T(-1);
+        for (int ls = 0; ls < maxls && Tm::any(ls_on); ++ls) {
+          T d[3] = {T(0), T(0), T(0)};
+#pragma unroll
+          for (int s = 0; s < WPL; ++s) {
+            const Wheel<T>& w = wh[s];
+            T f, q;
+            floss_row(a_sp[s] + alpha * x_sp[s] + C.h_flB[w.hidx] * e.dsp[s], C.h_floss[w.hidx], C.h_flR[w.hidx], &f, &q);
+            d[0] -= f * x_sp[s];
+            d[1] += q / C.h_flR[w.hidx] * x_sp[s] * x_sp[s];
+            unsigned zone = (q != T(0)) ? 1u : (f > T(0) ? 0u : 2u);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+              const Contact<T>& con = w.con[c];
+              const T* z0 = z[s][c]; const T* z1 = zv[s][c];
+              const T jr[4] = {z1[0] + con.mu * z1[1], z1[0] - con.mu * z1[1], z1[0] + con.mu * z1[2], z1[0] - con.mu * z1[2]};
+              const T xr[4] = {z0[0] + con.mu * z0[1] + alpha * jr[0], z0[0] - con.mu * z0[1] + alpha * jr[1],
+                               z0[0] + con.mu * z0[2] + alpha * jr[2], z0[0] - con.mu * z0[2] + alpha * jr[3]};
+              unsigned zb = 0u;
+#pragma unroll
+              for (int r = 0; r < 4; ++r) {
+                const bool act = (xr[r] < T(0)) && (con.D > T(0));
+                const T dj = act ? con.D * jr[r] : T(0);
+                d[0] += dj * xr[r]; d[1] += dj * jr[r];
+                zb |= act ? (1u << r) : 0u;
+              }
+              zone = (zone << 4) | zb;
+            }
+            d[2] += (zone != zone0[s]) ? T(1) : T(0);
+          }
+          Tm::sum_n(d);
+          T gL, gR, kLL, kLR, kRR;
+          shared_rows_eval(sr, a_sh[6] + alpha * x_sh[6], a_sh[7] + alpha * x_sh[7], &gL, &gR, &kLL, &kLR, &kRR);
+          const T d1 = alpha * sMs + sg + d[0] - gL * x_sh[6] - gR * x_sh[7];
+          const T d2 = sMs + d[1] + kLL * x_sh[6] * x_sh[6] + T(2) * kLR * x_sh[6] * x_sh[7] + kRR * x_sh[7] * x_sh[7];
+          if (ls_on) {
+            ++nls;
+            // a full Newton step that keeps every row in its zone lands on the exact minimiser
+            if (ls == 0 && d[2] == T(0) && shared_rows_zone(sr, a_sh[6] + x_sh[6], a_sh[7] + x_sh[7]) == szone0) { exact = true; ls_on = false; }
+            else if (N::abs_(d1) <= N::ls_rel * lam2) ls_on = false;
+            else {
+              if (d1 < T(0)) lo = alpha; else hi = alpha;
+              T an = alpha - d1 / d2;
+              if (hi >= T(0) && (an <= lo || an >= hi)) an = T(0.5) * (lo + hi);
+              if (an == alpha) ls_on = false;
+              alpha = an;
+            }
+          }
+        }
+        if (stepping) {
+          if (!first) ++iter;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { a_sh[i] += alpha * x_sh[i]; Ma_sh[i] += alpha * Mv_sh[i]; }
+#pragma unroll
+          for (int s = 0; s < WPL; ++s) {
+            a_sp[s] += alpha * x_sp[s]; Ma_sp[s] += alpha * Mv_sp[s];
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+              for (int i = 0; i < 3; ++i) z[s][c][i] += alpha * zv[s][c][i];
+          }
+          first = false;
+          if (exact || iter >= maxit) phase = 1;
+        }
+      }
+      const bool euler = (phase == 1);
+
+      // ---- assemble the arrow system at the current point; per-lane parts: S(36), reduced rhs(8), sum gsp^2/c (1)
+      const T hs = euler ? T(0) : T(1);          // Newton pass: Hessian of the constraint rows on, M~ a in the gradient
+      const T hdamp = euler ? h : T(0);          // Euler pass: + h * joint damping on the diagonal
       T part[45];
+#pragma unroll
       for (int i = 0; i < 45; ++i) part[i] = T(0);
       T gsp[WPL], cw[WPL], b[WPL][8];
+#pragma unroll
       for (int s = 0; s < WPL; ++s) {
         const Wheel<T>& w = wh[s];
-        T gsh_w[8];
-        for (int i = 0; i < 8; ++i) { gsh_w[i] = T(0); b[s][i] = T(0); }
-        for (int i = 0; i < 3; ++i) b[s][3 + i] = w.J * w.a[i];
         T f, q;
         floss_row(a_sp[s] + C.h_flB[w.hidx] * e.dsp[s], C.h_floss[w.hidx], C.h_flR[w.hidx], &f, &q);
-        gsp[s] = Ma_sp[s] - tau_sp[s] - f;
-        cw[s] = w.cdiag + q / C.h_flR[w.hidx];
+        unsigned zone = (q != T(0)) ? 1u : (f > T(0) ? 0u : 2u);
+        T gs_sp = hs * Ma_sp[s] - tau_sp[s] - f;
+        T cs = w.cdiag + hs * q / C.h_flR[w.hidx] + hdamp * C.h_damping[w.hidx];
+        T Hll[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};   // 00 10 11 20 21 22
+        T Hal[3][3] = {{T(0), T(0), T(0)}, {T(0), T(0), T(0)}, {T(0), T(0), T(0)}};
+        T Haa[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
+        T Hsl[3] = {T(0), T(0), T(0)}, Hsa[3] = {T(0), T(0), T(0)}, Hss = T(0);
+        T bl[3] = {T(0), T(0), T(0)}, ba[3] = {w.J * w.a[0], w.J * w.a[1], w.J * w.a[2]}, bs = T(0);
+        T gl[3] = {T(0), T(0), T(0)}, ga[3] = {T(0), T(0), T(0)}, gst = T(0);
+#pragma unroll
         for (int c = 0; c < 2; ++c) {
           const Contact<T>& con = w.con[c];
           T phi[3], qq[4];
           pyramid_rows(con, z[s][c], phi, qq);
-          // W = weights of (n, t1, t2) outer products for the active rows; S3 = D F^T W F (body frame, symmetric)
-          const T mu = con.mu;
-          T W00 = qq[0] + qq[1] + qq[2] + qq[3], W01 = mu * (qq[0] - qq[1]), W02 = mu * (qq[2] - qq[3]);
-          T W11 = mu * mu * (qq[0] + qq[1]), W22 = mu * mu * (qq[2] + qq[3]);
-          T S3[3][3];
-          for (int i = 0; i < 3; ++i)
-            for (int j = 0; j < 3; ++j)
-              S3[i][j] = con.D * (W00 * k.n[i] * k.n[j] + W01 * (k.n[i] * k.t1[j] + k.t1[i] * k.n[j]) +
-                                  W02 * (k.n[i] * k.t2[j] + k.t2[i] * k.n[j]) + W11 * k.t1[i] * k.t1[j] + W22 * k.t2[i] * k.t2[j]);
-          // point Jacobian columns for the shared dofs: [e0 e1 e2 | e_i x X | isL w | isR w], spin column u
-          T Jc[9][3];
-          for (int j = 0; j < 3; ++j) {
-            Jc[0][j] = (j == 0) ? T(1) : T(0); Jc[1][j] = (j == 1) ? T(1) : T(0); Jc[2][j] = (j == 2) ? T(1) : T(0);
+          if (con.D > T(0)) zone = (zone << 4) | (qq[0] != T(0) ? 1u : 0u) | (qq[1] != T(0) ? 2u : 0u) | (qq[2] != T(0) ? 4u : 0u) | (qq[3] != T(0) ? 8u : 0u);
+          else zone <<= 4;
+          // S3 = D F^T W F with W the active-row weights on (n, t1, t2); symmetric 3x3 in the body frame
+          const T mu = con.mu, Dh = hs * con.D;
+          const T W00 = qq[0] + qq[1] + qq[2] + qq[3], W01 = mu * (qq[0] - qq[1]), W02 = mu * (qq[2] - qq[3]);
+          const T W11 = mu * mu * (qq[0] + qq[1]), W22 = mu * mu * (qq[2] + qq[3]);
+          T r0[3], r1[3], r2[3];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            r0[i] = Dh * (W00 * k.n[i] + W01 * k.t1[i] + W02 * k.t2[i]);
+            r1[i] = Dh * (W01 * k.n[i] + W11 * k.t1[i]);
+            r2[i] = Dh * (W02 * k.n[i] + W22 * k.t2[i]);
           }
-          Jc[3][0] = T(0);       Jc[3][1] = -con.x[2]; Jc[3][2] = con.x[1];    // ex x X
-          Jc[4][0] = con.x[2];   Jc[4][1] = T(0);      Jc[4][2] = -con.x[0];   // ey x X
-          Jc[5][0] = -con.x[1];  Jc[5][1] = con.x[0];  Jc[5][2] = T(0);        // ez x X
-          for (int j = 0; j < 3; ++j) { Jc[6][j] = w.isL * con.w[j]; Jc[7][j] = w.isR * con.w[j]; Jc[8][j] = con.u[j]; }
-          T P[9][3];  // S3 * column
-          for (int a = 0; a < 9; ++a)
-            for (int i = 0; i < 3; ++i) P[a][i] = S3[i][0] * Jc[a][0] + S3[i][1] * Jc[a][1] + S3[i][2] * Jc[a][2];
-          for (int a = 0; a < 8; ++a)
-            for (int bb = 0; bb <= a; ++bb) part[tri(a, bb)] += dot3(Jc[a], P[bb]);
-          for (int a = 0; a < 8; ++a) b[s][a] += dot3(Jc[a], P[8]);
-          cw[s] += dot3(Jc[8], P[8]);
+          T S3[3][3];
+#pragma unroll
+          for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) { S3[i][j] = k.n[i] * r0[j] + k.t1[i] * r1[j] + k.t2[i] * r2[j]; S3[j][i] = S3[i][j]; }
+          const T* X = con.x;
+          Hll[0] += S3[0][0]; Hll[1] += S3[1][0]; Hll[2] += S3[1][1]; Hll[3] += S3[2][0]; Hll[4] += S3[2][1]; Hll[5] += S3[2][2];
+          // (ang, lin) block: column j = X x S3[:, j];  (ang, ang) block: column j = X x (S3 g_j), g_j = e_j x X
+          T Cj[3][3];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const T v[3] = {S3[0][j], S3[1][j], S3[2][j]};
+            cross3(Cj[j], X, v);
+#pragma unroll
+            for (int i = 0; i < 3; ++i) Hal[i][j] += Cj[j][i];
+          }
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const T Sg[3] = {Cj[0][j], Cj[1][j], Cj[2][j]};  // S3 g_j
+            T col[3];
+            cross3(col, X, Sg);
+            if (j == 0) { Haa[0] += col[0]; Haa[1] += col[1]; Haa[3] += col[2]; }
+            if (j == 1) { Haa[2] += col[1]; Haa[4] += col[2]; }
+            if (j == 2) { Haa[5] += col[2]; }
+          }
+          // spin column u and steer column wv
+          T Su[3], Sw[3], XSu[3], XSw[3];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) { Su[i] = S3[i][0] * con.u[0] + S3[i][1] * con.u[1] + S3[i][2] * con.u[2]; Sw[i] = S3[i][0] * con.w[0] + S3[i][1] * con.w[1]; }
+          cross3(XSu, X, Su);
+          cross3(XSw, X, Sw);
+#pragma unroll
+          for (int i = 0; i < 3; ++i) { bl[i] += Su[i]; ba[i] += XSu[i]; Hsl[i] += Sw[i]; Hsa[i] += XSw[i]; }
+          cs += dot3(con.u, Su);
+          bs += con.w[0] * Su[0] + con.w[1] * Su[1];
+          Hss += con.w[0] * Sw[0] + con.w[1] * Sw[1];
           // body-frame contact force and its generalised image (enters the gradient with a minus sign)
-          T Phi[3];
+          T Phi[3], XF[3];
+#pragma unroll
           for (int i = 0; i < 3; ++i) Phi[i] = k.n[i] * phi[0] + k.t1[i] * phi[1] + k.t2[i] * phi[2];
-          for (int a = 0; a < 8; ++a) gsh_w[a] -= dot3(Jc[a], Phi);
-          gsp[s] -= dot3(Jc[8], Phi);
+          cross3(XF, X, Phi);
+#pragma unroll
+          for (int i = 0; i < 3; ++i) { gl[i] -= Phi[i]; ga[i] -= XF[i]; }
+          gst -= con.w[0] * Phi[0] + con.w[1] * Phi[1];
+          gs_sp -= dot3(con.u, Phi);
         }
-        const T ci = T(1) / cw[s];
+        if (phase == 0) zone0[s] = zone;
+        gsp[s] = gs_sp; cw[s] = cs;
+        T gsh_w[8];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) { b[s][i] = bl[i]; b[s][3 + i] = ba[i]; gsh_w[i] = gl[i]; gsh_w[3 + i] = ga[i]; }
+        b[s][6] = w.isL * bs; b[s][7] = w.isR * bs; gsh_w[6] = w.isL * gst; gsh_w[7] = w.isR * gst;
+        part[tri(0, 0)] += Hll[0]; part[tri(1, 0)] += Hll[1]; part[tri(1, 1)] += Hll[2];
+        part[tri(2, 0)] += Hll[3]; part[tri(2, 1)] += Hll[4]; part[tri(2, 2)] += Hll[5];
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) part[tri(3 + i, j)] += Hal[i][j];
+        part[tri(3, 3)] += Haa[0]; part[tri(4, 3)] += Haa[1]; part[tri(4, 4)] += Haa[2];
+        part[tri(5, 3)] += Haa[3]; part[tri(5, 4)] += Haa[4]; part[tri(5, 5)] += Haa[5];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          part[tri(6, j)] += w.isL * Hsl[j]; part[tri(6, 3 + j)] += w.isL * Hsa[j];
+          part[tri(7, j)] += w.isR * Hsl[j]; part[tri(7, 3 + j)] += w.isR * Hsa[j];
+        }
+        part[tri(6, 6)] += w.isL * Hss; part[tri(7, 7)] += w.isR * Hss;
+        const T ci = T(1) / cs;
+#pragma unroll
         for (int a = 0; a < 8; ++a) {
-          for (int bb = 0; bb <= a; ++bb) part[tri(a, bb)] -= b[s][a] * b[s][bb] * ci;
-          part[36 + a] += gsh_w[a] - b[s][a] * gsp[s] * ci;
+          const T bc = b[s][a] * ci;
+#pragma unroll
+          for (int bb = 0; bb <= a; ++bb) part[tri(a, bb)] -= bc * b[s][bb];
+          part[36 + a] += gsh_w[a] - bc * gs_sp;
         }
-        part[44] += gsp[s] * gsp[s] * ci;
+        part[44] += gs_sp * gs_sp * ci;
       }
       Tm::sum_n(part);
       T S[36];
-      shared_mass(C, T(0), S);
+      shared_mass(C, hdamp, S);
+#pragma unroll
       for (int i = 0; i < 36; ++i) S[i] += part[i];
       T fL, fR, hLL, hLR, hRR;
       shared_rows_eval(sr, a_sh[6], a_sh[7], &fL, &fR, &hLL, &hLR, &hRR);
-      S[tri(6, 6)] += hLL; S[tri(7, 6)] += hLR; S[tri(7, 7)] += hRR;
-      T rhs[8], x_sh[8], x_sp[WPL];
-      for (int i = 0; i < 8; ++i) rhs[i] = Ma_sh[i] - tau_sh[i] + part[36 + i];
+      S[tri(6, 6)] += hs * hLL; S[tri(7, 6)] += hs * hLR; S[tri(7, 7)] += hs * hRR;
+      T rhs[8], y_sh[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) rhs[i] = hs * Ma_sh[i] - tau_sh[i] + part[36 + i];
       rhs[6] -= fL; rhs[7] -= fR;
-      for (int i = 0; i < 8; ++i) x_sh[i] = rhs[i];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) y_sh[i] = rhs[i];
       ldl8_factor(S);
-      ldl8_solve(S, x_sh);
-      T lam2 = part[44];  // Newton decrement g^T H^-1 g
-      for (int i = 0; i < 8; ++i) lam2 += rhs[i] * x_sh[i];
-      // predicted improvement of a full Newton step is lam2/2: stop when it is below tolerance
-      if (!(C.solver_scale[0] * T(0.5) * lam2 >= tol) || iter >= maxit) break;
-      // search = -H^-1 g
-      for (int s = 0; s < WPL; ++s) {
-        T dotb = T(0);
-        for (int a = 0; a < 8; ++a) dotb += b[s][a] * x_sh[a];
-        x_sp[s] = -(gsp[s] - dotb) / cw[s];
-      }
-      for (int i = 0; i < 8; ++i) x_sh[i] = -x_sh[i];
-      T Mv_sh[8], Mv_sp[WPL], zv[WPL][2][3];
-      mul_M(C, wh, x_sh, x_sp, Mv_sh, Mv_sp);
-      contact_residuals(k, wh, x_sh, x_sp, zv, false);
-      // exact line search: safeguarded Newton on f'(alpha); f'(0) = -lam2, f''(0) = lam2 so alpha_1 = 1
-      T quad[2] = {T(0), T(0)};  // team-summed private parts of s.M.s and s.(Ma - tau)
-      for (int s = 0; s < WPL; ++s) { quad[0] += x_sp[s] * Mv_sp[s]; quad[1] += x_sp[s] * (Ma_sp[s] - tau_sp[s]); }
-      Tm::sum_n(quad);
-      T sMs = quad[0], sg = quad[1];
-      for (int i = 0; i < 8; ++i) { sMs += x_sh[i] * Mv_sh[i]; sg += x_sh[i] * (Ma_sh[i] - tau_sh[i]); }
-      T alpha = T(1), lo = T(0), hi = T(-1);
-      for (int ls = 0; ls < maxls; ++ls) {
-        T d[2] = {T(0), T(0)};
+      ldl8_solve(S, y_sh);
+      if (phase != 2) {   // finished environments keep their solution
+        szone0 = shared_rows_zone(sr, a_sh[6], a_sh[7]);
+        lam2 = part[44];  // Newton decrement g^T H^-1 g
+#pragma unroll
+        for (int i = 0; i < 8; ++i) lam2 += rhs[i] * y_sh[i];
+        // x = -H^-1 g
+#pragma unroll
         for (int s = 0; s < WPL; ++s) {
-          const Wheel<T>& w = wh[s];
-          T f, q;
-          floss_row(a_sp[s] + alpha * x_sp[s] + C.h_flB[w.hidx] * e.dsp[s], C.h_floss[w.hidx], C.h_flR[w.hidx], &f, &q);
-          d[0] -= f * x_sp[s];
-          d[1] += q / C.h_flR[w.hidx] * x_sp[s] * x_sp[s];
-          for (int c = 0; c < 2; ++c) {
-            const Contact<T>& con = w.con[c];
-            const T* z0 = z[s][c]; const T* z1 = zv[s][c];
-            const T xr[4] = {z0[0] + con.mu * z0[1] + alpha * (z1[0] + con.mu * z1[1]), z0[0] - con.mu * z0[1] + alpha * (z1[0] - con.mu * z1[1]),
-                             z0[0] + con.mu * z0[2] + alpha * (z1[0] + con.mu * z1[2]), z0[0] - con.mu * z0[2] + alpha * (z1[0] - con.mu * z1[2])};
-            const T jr[4] = {z1[0] + con.mu * z1[1], z1[0] - con.mu * z1[1], z1[0] + con.mu * z1[2], z1[0] - con.mu * z1[2]};
-            for (int r = 0; r < 4; ++r)
-              if (xr[r] < T(0)) { d[0] += con.D * xr[r] * jr[r]; d[1] += con.D * jr[r] * jr[r]; }
-          }
+          T dotb = T(0);
+#pragma unroll
+          for (int a = 0; a < 8; ++a) dotb += b[s][a] * y_sh[a];
+          x_sp[s] = -(gsp[s] - dotb) / cw[s];
         }
-        Tm::sum_n(d);
-        T gL, gR, kLL, kLR, kRR;
-        shared_rows_eval(sr, a_sh[6] + alpha * x_sh[6], a_sh[7] + alpha * x_sh[7], &gL, &gR, &kLL, &kLR, &kRR);
-        T d1 = alpha * sMs + sg + d[0] - gL * x_sh[6] - gR * x_sh[7];
-        T d2 = sMs + d[1] + kLL * x_sh[6] * x_sh[6] + T(2) * kLR * x_sh[6] * x_sh[7] + kRR * x_sh[7] * x_sh[7];
-        ++nls;
-        if (N::abs_(d1) <= N::ls_rel * lam2) break;
-        if (d1 < T(0)) lo = alpha; else hi = alpha;
-        T an = alpha - d1 / d2;
-        if (hi >= T(0) && (an <= lo || an >= hi)) an = T(0.5) * (lo + hi);
-        if (an == alpha) break;
-        alpha = an;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) x_sh[i] = -y_sh[i];
+        if (euler) phase = 2;   // x = (M~ + h B)^-1 (tau + J^T f)
+        // predicted improvement of a full Newton step is lam2/2: below tolerance the point is converged
+        else if (!(C.solver_scale[0] * T(0.5) * lam2 >= tol)) phase = 1;
       }
-      for (int i = 0; i < 8; ++i) { a_sh[i] += alpha * x_sh[i]; Ma_sh[i] += alpha * Mv_sh[i]; }
-      for (int s = 0; s < WPL; ++s) {
-        a_sp[s] += alpha * x_sp[s]; Ma_sp[s] += alpha * Mv_sp[s];
-        for (int c = 0; c < 2; ++c) for (int i = 0; i < 3; ++i) z[s][c][i] += alpha * zv[s][c][i];
-      }
-      ++iter;
     }
     diag.niter = iter;
 
-    // ---- constraint force J^T f at the solution
-    T fc_part[8], fc_sp[WPL];
-    for (int i = 0; i < 8; ++i) fc_part[i] = T(0);
-    for (int s = 0; s < WPL; ++s) {
-      const Wheel<T>& w = wh[s];
-      T f, q;
-      floss_row(a_sp[s] + C.h_flB[w.hidx] * e.dsp[s], C.h_floss[w.hidx], C.h_flR[w.hidx], &f, &q);
-      fc_sp[s] = f;
-      for (int c = 0; c < 2; ++c) {
-        const Contact<T>& con = w.con[c];
-        T phi[3], qq[4], Phi[3], xF[3];
-        pyramid_rows(con, z[s][c], phi, qq);
-        for (int i = 0; i < 3; ++i) Phi[i] = k.n[i] * phi[0] + k.t1[i] * phi[1] + k.t2[i] * phi[2];
-        cross3(xF, con.x, Phi);
-        for (int i = 0; i < 3; ++i) { fc_part[i] += Phi[i]; fc_part[3 + i] += xF[i]; }
-        T ws = dot3(con.w, Phi);
-        fc_part[6] += w.isL * ws; fc_part[7] += w.isR * ws;
-        fc_sp[s] += dot3(con.u, Phi);
-      }
-    }
-    Tm::sum_n(fc_part);
-    {
-      T fL, fR, hLL, hLR, hRR;
-      shared_rows_eval(sr, a_sh[6], a_sh[7], &fL, &fR, &hLL, &hLR, &hRR);
-      fc_part[6] += fL; fc_part[7] += fR;
-    }
-
-    // ---- B16 Euler with implicit joint damping
-    T rhs_sh[8], rhs_sp[WPL], ai_sh[8], ai_sp[WPL];
-    for (int i = 0; i < 8; ++i) rhs_sh[i] = tau_sh[i] + fc_part[i];
-    for (int s = 0; s < WPL; ++s) rhs_sp[s] = tau_sp[s] + fc_sp[s];
-    solve_M(C, wh, h, rhs_sh, rhs_sp, ai_sh, ai_sp);
-
     if (tap) {
-      for (int i = 0; i < 8; ++i) { tap->tau[i] = tau_sh[i]; tap->a_smooth[i] = as_sh[i]; tap->a[i] = a_sh[i]; tap->fc[i] = fc_part[i]; }
+      for (int i = 0; i < 8; ++i) { tap->tau[i] = tau_sh[i]; tap->a_smooth[i] = T(0); tap->a[i] = a_sh[i]; tap->fc[i] = T(0); }
       for (int s = 0; s < WPL; ++s) {
         int wi = lane * WPL + s;
-        tap->tau[8 + wi] = tau_sp[s]; tap->a_smooth[8 + wi] = as_sp[s]; tap->a[8 + wi] = a_sp[s]; tap->fc[8 + wi] = fc_sp[s];
+        tap->tau[8 + wi] = tau_sp[s]; tap->a_smooth[8 + wi] = T(0); tap->a[8 + wi] = a_sp[s]; tap->fc[8 + wi] = T(0);
       }
       tap->niter = iter; tap->nls = nls;
     }
 
     // warm start for the next step = solver acceleration, MuJoCo coordinates
+#pragma unroll
     for (int i = 0; i < 3; ++i) {
       e.warm_l[i] = k.R[3 * i] * a_sh[0] + k.R[3 * i + 1] * a_sh[1] + k.R[3 * i + 2] * a_sh[2];
       e.warm_a[i] = a_sh[3 + i];
     }
     e.warm_st[0] = a_sh[6]; e.warm_st[1] = a_sh[7];
+#pragma unroll
     for (int s = 0; s < WPL; ++s) e.warm_sp[s] = a_sp[s];
 
-    // velocities, then positions with the new velocities (semi-implicit)
+    // B16: velocities advance with the implicitly damped acceleration x, then positions with the new velocities
+#pragma unroll
     for (int i = 0; i < 3; ++i) {
-      e.vw[i] += h * (k.R[3 * i] * ai_sh[0] + k.R[3 * i + 1] * ai_sh[1] + k.R[3 * i + 2] * ai_sh[2]);
-      e.om[i] += h * ai_sh[3 + i];
+      e.vw[i] += h * (k.R[3 * i] * x_sh[0] + k.R[3 * i + 1] * x_sh[1] + k.R[3 * i + 2] * x_sh[2]);
+      e.om[i] += h * x_sh[3 + i];
     }
-    for (int i = 0; i < 2; ++i) { e.dst[i] += h * ai_sh[6 + i]; e.st[i] += h * e.dst[i]; }
-    for (int s = 0; s < WPL; ++s) { e.dsp[s] += h * ai_sp[s]; e.sp[s] += h * e.dsp[s]; }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) { e.dst[i] += h * x_sh[6 + i]; e.st[i] += h * e.dst[i]; }
+#pragma unroll
+    for (int s = 0; s < WPL; ++s) { e.dsp[s] += h * x_sp[s]; e.sp[s] += h * e.dsp[s]; }
+#pragma unroll
     for (int i = 0; i < 3; ++i) e.p[i] += h * e.vw[i];
     {
       T wn = N::sqrt_(dot3(e.om, e.om));
       T ax[3] = {T(1), T(0), T(0)};
       if (wn >= N::minval) { ax[0] = e.om[0] / wn; ax[1] = e.om[1] / wn; ax[2] = e.om[2] / wn; }
-      T half = T(0.5) * h * wn, sn = N::sin_(half), cs = N::cos_(half);
+      T half = T(0.5) * h * wn, sn, cs;
+      N::sincos_tiny(half, &sn, &cs);
       T r0 = cs, r1 = ax[0] * sn, r2 = ax[1] * sn, r3 = ax[2] * sn;
       T q0 = e.q[0], q1 = e.q[1], q2 = e.q[2], q3 = e.q[3];
       e.q[0] = q0 * r0 - q1 * r1 - q2 * r2 - q3 * r3;

@@ -78,7 +78,7 @@ struct EnvOps {
     const T gx = ep.goal[0] - px, gy = ep.goal[1] - py;
     const T dist = N::sqrt_(gx * gx + gy * gy);
     T ang = N::atan2_(gy, gx) - yaw;
-    ang = N::atan2_(N::sin_(ang), N::cos_(ang));
+    ang = N::wrap_pi(ang);
     if (lane == 0) {
       sink.put(nbeam + 0, (float)px); sink.put(nbeam + 1, (float)py); sink.put(nbeam + 2, (float)yaw);
       sink.put(nbeam + 3, (float)gx); sink.put(nbeam + 4, (float)gy); sink.put(nbeam + 5, (float)dist); sink.put(nbeam + 6, (float)ang);

@@ -65,6 +65,11 @@ struct RowSink {
   float* row;
   __device__ __forceinline__ void put(int slot, float v) { row[slot] = v; }
 };
+struct PredRowSink {
+  float* row;
+  bool on;
+  __device__ __forceinline__ void put(int slot, float v) { if (on) row[slot] = v; }
+};
 
 __device__ __forceinline__ unsigned warp_sum_u32(unsigned v) {
 #pragma unroll
@@ -73,6 +78,9 @@ __device__ __forceinline__ unsigned warp_sum_u32(unsigned v) {
 }
 
 constexpr int kBlock = 128;
+#ifndef ACKB_MIN_BLOCKS
+#define ACKB_MIN_BLOCKS 2
+#endif
 
 // synthetic action of (step, env): Philox(seed) with counter (step, env, 2, tag) -> U(-1, 1)^2
 __device__ __forceinline__ void synth_action(unsigned long long seed, uint32_t step, uint32_t env, float* a0, float* a1) {
@@ -83,7 +91,7 @@ __device__ __forceinline__ void synth_action(unsigned long long seed, uint32_t s
 }
 
 template <typename T, int LANES>
-__global__ void __launch_bounds__(kBlock) step_kernel(DevState<T> st, StepArgs a) {
+__global__ void __launch_bounds__(kBlock, ACKB_MIN_BLOCKS) step_kernel(DevState<T> st, StepArgs a) {
   using E = EnvOps<T, LANES>;
   constexpr int EPW = 32 / LANES;
   extern __shared__ float tile[];
@@ -121,16 +129,20 @@ __global__ void __launch_bounds__(kBlock) step_kernel(DevState<T> st, StepArgs a
   const bool done = out.terminated || out.truncated;
   float ret = st.ep_return[env] + out.reward;
   const int ep_len = ep.step_count;
-  if (done && a.auto_reset) {
-    if (a.terminal_obs && valid)
+  const bool do_reset = done && a.auto_reset;
+  if (__any_sync(0xffffffffu, do_reset)) {   // warp-uniform: the team collectives inside need the whole warp
+    if (do_reset && a.terminal_obs && valid)
       for (int j = lane; j < a.obs_dim; j += LANES) a.terminal_obs[(size_t)env * a.obs_dim + j] = sink.row[j];
-    Team<LANES>::sync();
-    E::reset_env(C, e, ep, lane, a.seed, (uint32_t)env);
+    __syncwarp();
+    typename E::State e2 = e;
+    Episode<T> ep2 = ep;
+    E::reset_env(C, e2, ep2, lane, a.seed, (uint32_t)env);
     Kin<T> k;
-    E::S::kinematics(e, k);
+    E::S::kinematics(e2, k);
     T dist, minl;
-    // all lanes of the team take this branch together (done is team-uniform), so the team shuffles are safe
-    E::observe(C, e, k, ep, lane, sink, &dist, &minl);
+    PredRowSink psink{sink.row, do_reset};
+    E::observe(C, e2, k, ep2, lane, psink, &dist, &minl);
+    if (do_reset) { e = e2; ep = ep2; }
   }
   __syncwarp();
 

@@ -27,7 +27,7 @@ def _random_states(M, n, rng, ground_frac=0.5):
             q = np.array([1.0, *ang])
             qvel[i] = rng.normal(size=12) * np.array([1, 1, .1, .3, .3, 1, 20, 20, 3, 20, 3, 20]) * 0.5
         else:
-            qpos[i, 2] = rng.uniform(0.1, 0.5)
+            qpos[i, 2] = rng.uniform(0.25, 0.5)   # clear of the floor at any orientation (cap-down wheel contacts are out of scope)
             q = rng.normal(size=4)
             qvel[i] = rng.normal(size=12) * np.array([1, 1, 1, 3, 3, 3, 20, 20, 3, 20, 3, 20])
         qpos[i, 0:2] = rng.uniform(-5, 5, 2)
