@@ -112,6 +112,32 @@ void hs_env_reset(int f32, const double* blob, double* qpos, double* qvel, doubl
   if (f32) env_reset<float>(blob, qpos, qvel, warm, epd, epi, seed, env_id, obs);
   else env_reset<double>(blob, qpos, qvel, warm, epd, epi, seed, env_id, obs);
 }
+// observation of a given state (qpos) with given episode data; out = goal distance, min lidar
+void hs_observe(int f32, const double* blob, double* qpos, double* qvel, double* warm, const double* epd, float* obs, double* out) {
+  if (f32) {
+    using E = EnvOps<float, 1>; Consts<float> C; to_consts(blob, C);
+    E::State e; ArrAcc<float> acc{qpos, qvel, warm}; E::load_state(acc, 0, e);
+    Episode<float> ep; ep.goal[0] = epd[0]; ep.goal[1] = epd[1]; ep.ref[0] = epd[2]; ep.ref[1] = epd[3]; ep.step_count = 0; ep.episode = 0;
+    Kin<float> k; E::S::kinematics(e, k); ObsSink sink{obs}; float d, m; E::observe(C, e, k, ep, 0, sink, &d, &m); out[0] = d; out[1] = m;
+  } else {
+    using E = EnvOps<double, 1>; Consts<double> C; to_consts(blob, C);
+    E::State e; ArrAcc<double> acc{qpos, qvel, warm}; E::load_state(acc, 0, e);
+    Episode<double> ep; ep.goal[0] = epd[0]; ep.goal[1] = epd[1]; ep.ref[0] = epd[2]; ep.ref[1] = epd[3]; ep.step_count = 0; ep.episode = 0;
+    Kin<double> k; E::S::kinematics(e, k); ObsSink sink{obs}; double d, m; E::observe(C, e, k, ep, 0, sink, &d, &m); out[0] = d; out[1] = m;
+  }
+}
+// reward / flags from (goal distance, min lidar, step counter before the step); out = reward, terminated, truncated, collision, new counter
+void hs_reward(int f32, const double* blob, double dist, double min_lidar, int step_count, double* out) {
+  if (f32) {
+    Consts<float> C; to_consts(blob, C); Episode<float> ep; ep.step_count = step_count; StepOut<float> so;
+    EnvOps<float, 1>::reward_done(C, ep, (float)dist, (float)min_lidar, so);
+    out[0] = so.reward; out[1] = so.terminated; out[2] = so.truncated; out[3] = so.collision; out[4] = ep.step_count;
+  } else {
+    Consts<double> C; to_consts(blob, C); Episode<double> ep; ep.step_count = step_count; StepOut<double> so;
+    EnvOps<double, 1>::reward_done(C, ep, dist, min_lidar, so);
+    out[0] = so.reward; out[1] = so.terminated; out[2] = so.truncated; out[3] = so.collision; out[4] = ep.step_count;
+  }
+}
 void hs_action_to_ctrl(int f32, const double* blob, float a0, float a1, double* ctrl) {
   if (f32) { Consts<float> C; to_consts(blob, C); float c[4]; action_to_ctrl<float>(C, a0, a1, c); for (int i = 0; i < 4; ++i) ctrl[i] = c[i]; }
   else { Consts<double> C; to_consts(blob, C); double c[4]; action_to_ctrl<double>(C, a0, a1, c); for (int i = 0; i < 4; ++i) ctrl[i] = c[i]; }

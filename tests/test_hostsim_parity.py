@@ -1,0 +1,97 @@
+"""Arithmetic of the CUDA per-environment code, compiled for the host (tests/hostsim, LANES = 1), against the CPU oracle.
+This is the CPU-side check of the kernel's numerics; the GPU run of the same comparison is tests/test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+from mujoco_playground_b200.compiler.constants import build_consts
+from mujoco_playground_b200.models import load_model
+from oracle.env_oracle import OracleEnv
+from oracle.oracle import OracleSim
+from tests.hostsim.hostsim import HostSim
+
+M = load_model("v2")
+
+
+def _rand_state(rng, ground):
+    qpos = M["qpos0"].copy()
+    if ground:
+        qpos[2] = 0.0645 + rng.uniform(-0.0005, 0.002)
+        q = np.array([1.0, *(rng.normal(size=3) * 0.02)])
+        qvel = rng.normal(size=12) * np.array([1, 1, .1, .3, .3, 1, 20, 20, 3, 20, 3, 20]) * 0.5
+    else:
+        qpos[2] = rng.uniform(0.25, 0.5)
+        q = rng.normal(size=4)
+        qvel = rng.normal(size=12) * np.array([1, 1, 1, 3, 3, 3, 20, 20, 3, 20, 3, 20])
+    qpos[:2] = rng.uniform(-5, 5, 2)
+    qpos[3:7] = q / np.linalg.norm(q)
+    qpos[7:] = rng.uniform(-0.5, 0.5, 6)
+    return qpos, qvel
+
+
+@pytest.mark.parametrize("f32,tol", [(False, 1e-9), (True, 1e-3)])
+def test_single_substep_matches_oracle(f32, tol):
+    rng = np.random.default_rng(1)
+    h = HostSim(build_consts(M, model_kind=0, tolerance=1e-13), f32)
+    o = OracleSim(M, tolerance=1e-13)
+    for i in range(40):
+        qpos, qvel = _rand_state(rng, ground=i % 2 == 0)
+        if i % 7 == 0:
+            qpos[9] = 0.63                    # beyond the steer limit
+        warm = rng.normal(size=12)
+        ctrl = rng.uniform(-1, 1, 3) * np.array([0.61, 50, 50])
+        o.reset(); o.qpos[:] = qpos; o.qvel[:] = qvel; o.qacc_warmstart[:] = warm; o.ctrl[:] = ctrl
+        o.step()
+        h.qpos[:], h.qvel[:], h.warm[:] = qpos, qvel, warm
+        h.substep(ctrl)
+        assert h.diag[0] == o.ncon and h.diag[1] == 0
+        scale_v = max(1.0, np.abs(o.qvel).max())
+        assert np.abs(h.qpos - o.qpos).max() < tol * max(1.0, np.abs(o.qpos).max())
+        assert np.abs(h.qvel - o.qvel).max() < tol * scale_v
+        assert np.abs(h.warm - o.qacc_warmstart).max() < (1e-6 if not f32 else 0.5) * max(1.0, np.abs(o.qacc_warmstart).max())
+
+
+def test_trajectory_1000_steps_fp64():
+    """config[0]-style reference trajectory: reset state, 1000 random-action steps; the two independent fp64
+    implementations stay together to ~1e-8 (the system is chaotic, errors grow along the rollout)."""
+    h = HostSim(build_consts(M, model_kind=0, tolerance=1e-12), False)
+    h.reset(seed=0)
+    o = OracleEnv(M, tolerance=1e-12)
+    o.reset(h.epd[:2])
+    rng = np.random.default_rng(0)
+    for t in range(1000):
+        a = rng.uniform(-1, 1, 2).astype(np.float32)
+        obs, r, te, tr, info = h.step(a)
+        oo, ro, teo, tro, io = o.step(a)
+        assert info["ncon"] == io["ncon"], f"step {t}"
+        assert te == teo and tr == tro
+        assert abs(r - ro) < 1e-4 * max(1.0, abs(ro))
+        if t < 100:
+            assert np.abs(h.qpos - o.sim.qpos).max() < 1e-11
+            assert np.abs(obs - oo).max() < 1e-5
+    assert tr and np.abs(h.qpos - o.sim.qpos).max() < 1e-6
+
+
+def test_frame_skip_is_repeated_substeps():
+    c = build_consts(M, model_kind=0)
+    h1, h4 = HostSim(c), HostSim(c)
+    h1.reset(seed=3); h4.reset(seed=3)
+    rng = np.random.default_rng(3)
+    for _ in range(30):
+        a = rng.uniform(-1, 1, 2).astype(np.float32)
+        for _k in range(4):
+            h1.step(a, frame_skip=1)
+        h4.step(a, frame_skip=4)
+    assert np.abs(h1.qpos - h4.qpos).max() == 0 and h1.epi[0] == 4 * h4.epi[0]
+
+
+def test_unsupported_contact_flag_when_plate_touches_floor():
+    """Chassis pushed 45 mm into the floor: plane-vs-hull contact of the plates is outside the supported set and must be flagged."""
+    h = HostSim(build_consts(M, model_kind=0))
+    h.qpos[:] = M["qpos0"]
+    h.qpos[2] = 0.02
+    h.substep(np.zeros(3))
+    assert h.diag[1] == 1
+    o = OracleSim(M)
+    o.qpos[2] = 0.02
+    o.forward()
+    assert int(o.f("unsupported_contact")[0]) == 1
