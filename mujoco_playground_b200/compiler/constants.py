@@ -146,6 +146,27 @@ def build_consts(M: dict, *, model_kind: int, max_episode_steps: int = 1000, goa
     put("h_flB", flB)
     put("h_invweight", [M["dof_invweight0"][d] for d in hinge_dof])
 
+    # ---- implicit joint damping: constant part of the 8x8 Schur complement of (M~ + h B) and its inverse ------------
+    hin = np.array([Js[0] + Jw[2], Js[1] + Jw[3], Jw[0], Jw[1], Jw[2], Jw[3]])
+    arm = np.array([M["dof_armature"][d] for d in hinge_dof])
+    dmp = np.array([M["dof_damping"][d] for d in hinge_dof])
+    Sc = np.zeros((8, 8))
+    Sc[:3, :3] = mass * np.eye(3)
+    cx, cy, cz = mcom
+    Sc[3:6, :3] = np.array([[0, -cz, cy], [cz, 0, -cx], [-cy, cx, 0]])
+    Sc[:3, 3:6] = Sc[3:6, :3].T
+    Sc[3:6, 3:6] = IO
+    for i in range(2):
+        Sc[6 + i, 5] = Sc[5, 6 + i] = hin[i]
+        Sc[6 + i, 6 + i] = hin[i] + arm[i] + h * dmp[i]
+    cE = hin[2:] + arm[2:] + h * dmp[2:]
+    for wI in (0, 1):                               # rear wheels: constant spin axis e_y
+        Sc[4, 4] -= hin[2 + wI] ** 2 / cE[wI]
+    P = np.linalg.inv(Sc)
+    put("eulerP", [P[i, j] for i in range(8) for j in range(i + 1)])
+    put("euler_kappa", [hin[4] ** 2 / cE[2], hin[5] ** 2 / cE[3]])
+    put("w_cEinv", 1.0 / cE)
+
     # ---- steer limits -------------------------------------------------------------------------------
     put("st_limited", [M["jnt_limited"][j] for j in hinge_j[:2]])
     put("st_lo", [M["jnt_range"][j][0] for j in hinge_j[:2]])

@@ -134,6 +134,21 @@ struct Team {
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = sum(v[i]);
   }
+  // Instruction-cache locality: the warps of a CTA re-converge here so that they walk the same code together and share
+  // the fetched lines (the kernel is instruction-fetch bound).  Must be reached by every thread of the CTA.
+  ACKB_D static void block_sync() {
+#if defined(__CUDA_ARCH__) && defined(ACKB_SYNC_SUBSTEP)
+    __syncthreads();
+#endif
+  }
+  // loop predicate of the solver: warp-wide by default, CTA-wide when ACKB_SYNC_PASS is defined
+  ACKB_D static bool loop_any(bool p) {
+#if defined(__CUDA_ARCH__) && defined(ACKB_SYNC_PASS)
+    return __syncthreads_or(p ? 1 : 0) != 0;
+#else
+    return any(p);
+#endif
+  }
   // true if the predicate holds for any lane of the warp (host: the single environment)
   ACKB_D static bool any(bool p) {
 #if defined(__CUDA_ARCH__)
@@ -730,8 +745,8 @@ struct Sim {
     const T tol = mjmax(C.tolerance[0], N::tol_floor);
     const int maxit = (int)C.iterations[0], maxls = (int)C.ls_iterations[0];
     int iter = 0, nls = 0;
-    // per-environment phase: 0 = step along x then Newton pass, 1 = Euler pass (no step), 2 = finished.
-    // The loop itself is warp-uniform: it runs until every environment of the warp has finished.
+    // per-environment phase: 0 = iterating (step along x, then Newton pass), 2 = converged.
+    // The loop itself is warp-uniform: it runs until every environment of the warp has converged.
     int phase = 0;
     bool first = true;
     T lam2 = T(0);
@@ -739,7 +754,7 @@ struct Sim {
     unsigned szone0 = 0u;
 #pragma unroll
     for (int s = 0; s < WPL; ++s) zone0[s] = 0u;
-    while (Tm::any(phase != 2)) {
+    while (Tm::loop_any(phase != 2)) {
       const bool stepping = (phase == 0);
       if (Tm::any(stepping)) {
         // ---- move along x: exact line search (safeguarded Newton on f'(alpha)), then update the point
@@ -818,14 +833,14 @@ struct Sim {
               for (int i = 0; i < 3; ++i) z[s][c][i] += alpha * zv[s][c][i];
           }
           first = false;
-          if (exact || iter >= maxit) phase = 1;
+          if (exact || iter >= maxit) phase = 2;
         }
       }
-      const bool euler = (phase == 1);
+#if !defined(ACKB_SYNC_PASS)
+      if (!Tm::any(phase != 2)) break;   // every environment of the warp landed on its exact minimiser
+#endif
 
       // ---- assemble the arrow system at the current point; per-lane parts: S(36), reduced rhs(8), sum gsp^2/c (1)
-      const T hs = euler ? T(0) : T(1);          // Newton pass: Hessian of the constraint rows on, M~ a in the gradient
-      const T hdamp = euler ? h : T(0);          // Euler pass: + h * joint damping on the diagonal
       T part[45];
 #pragma unroll
       for (int i = 0; i < 45; ++i) part[i] = T(0);
@@ -836,8 +851,8 @@ struct Sim {
         T f, q;
         floss_row(a_sp[s] + C.h_flB[w.hidx] * e.dsp[s], C.h_floss[w.hidx], C.h_flR[w.hidx], &f, &q);
         unsigned zone = (q != T(0)) ? 1u : (f > T(0) ? 0u : 2u);
-        T gs_sp = hs * Ma_sp[s] - tau_sp[s] - f;
-        T cs = w.cdiag + hs * q / C.h_flR[w.hidx] + hdamp * C.h_damping[w.hidx];
+        T gs_sp = Ma_sp[s] - tau_sp[s] - f;
+        T cs = w.cdiag + q / C.h_flR[w.hidx];
         T Hll[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};   // 00 10 11 20 21 22
         T Hal[3][3] = {{T(0), T(0), T(0)}, {T(0), T(0), T(0)}, {T(0), T(0), T(0)}};
         T Haa[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
@@ -852,7 +867,7 @@ struct Sim {
           if (con.D > T(0)) zone = (zone << 4) | (qq[0] != T(0) ? 1u : 0u) | (qq[1] != T(0) ? 2u : 0u) | (qq[2] != T(0) ? 4u : 0u) | (qq[3] != T(0) ? 8u : 0u);
           else zone <<= 4;
           // S3 = D F^T W F with W the active-row weights on (n, t1, t2); symmetric 3x3 in the body frame
-          const T mu = con.mu, Dh = hs * con.D;
+          const T mu = con.mu, Dh = con.D;
           const T W00 = qq[0] + qq[1] + qq[2] + qq[3], W01 = mu * (qq[0] - qq[1]), W02 = mu * (qq[2] - qq[3]);
           const T W11 = mu * mu * (qq[0] + qq[1]), W22 = mu * mu * (qq[2] + qq[3]);
           T r0[3], r1[3], r2[3];
@@ -940,15 +955,15 @@ struct Sim {
       }
       Tm::sum_n(part);
       T S[36];
-      shared_mass(C, hdamp, S);
+      shared_mass(C, T(0), S);
 #pragma unroll
       for (int i = 0; i < 36; ++i) S[i] += part[i];
       T fL, fR, hLL, hLR, hRR;
       shared_rows_eval(sr, a_sh[6], a_sh[7], &fL, &fR, &hLL, &hLR, &hRR);
-      S[tri(6, 6)] += hs * hLL; S[tri(7, 6)] += hs * hLR; S[tri(7, 7)] += hs * hRR;
+      S[tri(6, 6)] += hLL; S[tri(7, 6)] += hLR; S[tri(7, 7)] += hRR;
       T rhs[8], y_sh[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) rhs[i] = hs * Ma_sh[i] - tau_sh[i] + part[36 + i];
+      for (int i = 0; i < 8; ++i) rhs[i] = Ma_sh[i] - tau_sh[i] + part[36 + i];
       rhs[6] -= fL; rhs[7] -= fR;
 #pragma unroll
       for (int i = 0; i < 8; ++i) y_sh[i] = rhs[i];
@@ -969,10 +984,65 @@ struct Sim {
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) x_sh[i] = -y_sh[i];
-        if (euler) phase = 2;   // x = (M~ + h B)^-1 (tau + J^T f)
         // predicted improvement of a full Newton step is lam2/2: below tolerance the point is converged
-        else if (!(C.solver_scale[0] * T(0.5) * lam2 >= tol)) phase = 1;
+        if (!(C.solver_scale[0] * T(0.5) * lam2 >= tol)) phase = 2;
       }
+    }
+
+    // ---- B16 implicit joint damping.  At the minimiser M~ a = tau + J^T f, so MuJoCo's integration acceleration
+    // (M~ + hB)^-1 (tau + J^T f) equals a - y with (M~ + hB) y = hB a.  B acts on the hinges only; after eliminating the
+    // spin dofs the 8x8 system matrix is a constant (inverse P precomputed by the model compiler) minus a rank-2 term
+    // from the two front spin axes, handled with the Woodbury identity.
+    T yi_sh[8], yi_sp[WPL];
+    {
+      T part3[3] = {T(0), T(0), T(0)};
+      T dsp[WPL];
+#pragma unroll
+      for (int s = 0; s < WPL; ++s) {
+        const Wheel<T>& w = wh[s];
+        dsp[s] = h * C.h_damping[w.hidx] * a_sp[s];
+        const T coef = w.J * dsp[s] * C.w_cEinv[w.hidx - 2];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) part3[i] -= coef * w.a[i];
+      }
+      Tm::sum_n(part3);
+      T r[8] = {T(0), T(0), T(0), part3[0], part3[1], part3[2], h * C.h_damping[0] * a_sh[6], h * C.h_damping[1] * a_sh[7]};
+      T t[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        T acc = T(0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc += C.eulerP[i >= j ? tri(i, j) : tri(j, i)] * r[j];
+        t[i] = acc;
+      }
+      // front spin axes (both are needed by every lane): u_w = (-sin s_w, cos s_w, 0) in the angular rows
+      T ux[2], uy[2];
+#pragma unroll
+      for (int f = 0; f < 2; ++f) { T sn, cs; N::sincos_small(e.st[f], &sn, &cs); ux[f] = -sn; uy[f] = cs; }
+      const T Pxx = C.eulerP[tri(3, 3)], Pxy = C.eulerP[tri(4, 3)], Pyy = C.eulerP[tri(4, 4)];
+      T G[2][2], ut[2];
+#pragma unroll
+      for (int f = 0; f < 2; ++f) {
+        ut[f] = ux[f] * t[3] + uy[f] * t[4];
+#pragma unroll
+        for (int g = 0; g < 2; ++g) G[f][g] = -(ux[f] * (Pxx * ux[g] + Pxy * uy[g]) + uy[f] * (Pxy * ux[g] + Pyy * uy[g]));
+        G[f][f] += T(1) / C.euler_kappa[f];
+      }
+      const T det = G[0][0] * G[1][1] - G[0][1] * G[1][0];
+      const T m0 = (G[1][1] * ut[0] - G[0][1] * ut[1]) / det, m1 = (G[0][0] * ut[1] - G[1][0] * ut[0]) / det;
+      const T vx = ux[0] * m0 + ux[1] * m1, vy = uy[0] * m0 + uy[1] * m1;   // U m, angular x / y rows
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        yi_sh[i] = t[i] + C.eulerP[i >= 3 ? tri(i, 3) : tri(3, i)] * vx + C.eulerP[i >= 4 ? tri(i, 4) : tri(4, i)] * vy;
+#pragma unroll
+      for (int s = 0; s < WPL; ++s) {
+        const Wheel<T>& w = wh[s];
+        yi_sp[s] = (dsp[s] - w.J * dot3(w.a, yi_sh + 3)) * C.w_cEinv[w.hidx - 2];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x_sh[i] = a_sh[i] - yi_sh[i];   // integration acceleration
+#pragma unroll
+      for (int s = 0; s < WPL; ++s) x_sp[s] = a_sp[s] - yi_sp[s];
     }
     diag.niter = iter;
 

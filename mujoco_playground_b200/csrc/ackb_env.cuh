@@ -141,6 +141,7 @@ struct EnvOps {
     action_to_ctrl<T>(C, a0, a1, ctrl);
     T dist = T(0), minl = T(0);
     for (int s = 0; s < frame_skip; ++s) {
+      Tm::block_sync();
       Kin<T> k;
       S::kinematics(e, k);
       if (s == frame_skip - 1) observe(C, e, k, ep, lane, sink, &dist, &minl);

@@ -77,7 +77,10 @@ __device__ __forceinline__ unsigned warp_sum_u32(unsigned v) {
   return v;
 }
 
-constexpr int kBlock = 128;
+#ifndef ACKB_BLOCK
+#define ACKB_BLOCK 128
+#endif
+constexpr int kBlock = ACKB_BLOCK;
 #ifndef ACKB_MIN_BLOCKS
 #define ACKB_MIN_BLOCKS 2
 #endif
