@@ -141,6 +141,11 @@ struct Team {
     __syncthreads();
 #endif
   }
+  ACKB_D static void warp_sync() {
+#if defined(__CUDA_ARCH__)
+    __syncwarp();
+#endif
+  }
   // loop predicate of the solver: warp-wide by default, CTA-wide when ACKB_SYNC_PASS is defined
   ACKB_D static bool loop_any(bool p) {
 #if defined(__CUDA_ARCH__) && defined(ACKB_SYNC_PASS)
@@ -172,11 +177,12 @@ ACKB_HD void cross3(T* r, const T* a, const T* b) {
 
 // per-environment state held in registers.  Velocities and warm start use MuJoCo's convention
 // (linear part in the world frame, angular part in the chassis frame).
-template <typename T, int WPL>
+// The spin angle / rate / warm start of each wheel live in its Wheel record (below).
+template <typename T>
 struct EnvState {
-  T p[3], q[4], st[2], sp[WPL];
-  T vw[3], om[3], dst[2], dsp[WPL];
-  T warm_l[3], warm_a[3], warm_st[2], warm_sp[WPL];
+  T p[3], q[4], st[2];
+  T vw[3], om[3], dst[2];
+  T warm_l[3], warm_a[3], warm_st[2];
 };
 
 // quantities of the position stage that the observation needs (pre-integration, reference quirk Q3)
@@ -282,53 +288,86 @@ ACKB_HD void action_to_ctrl(const Consts<T>& C, float a0, float a1, T* ctrl) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// per-wheel working set
+// per-wheel working set.  With 4 lanes per environment each lane keeps ONE record in registers; with 1 lane per
+// environment the 4 records of a thread live in shared memory (odd per-thread stride, conflict free) and the wheel /
+// contact loops stay rolled, which keeps the instruction footprint of the solver loop inside the instruction cache.
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 struct Contact {
   T x[3];     // contact point, body frame
-  T u[3];     // axis x r          (spin column of the point Jacobian)
-  T w[3];     // ez x r            (steer column; used by front wheels only)
   T D;        // 1/R of its pyramid rows (0: contact absent or excluded)
-  T aref[3];  // reference acceleration along n, t1, t2
-  T mu;
+  T z[3];     // residual F Jp a - aref along (n, t1, t2) at the current point
+  T zv[3];    // image F Jp x of the current step direction
 };
 
 template <typename T>
 struct Wheel {
-  T c[3];        // centre (hinge anchor)
-  T a[3];        // spin axis, body frame
-  T isL, isR;    // 1 if this wheel hangs on steer L / R
-  T J, cdiag;    // spin inertia, J + armature
-  T dsteer;      // steer rate of the owning steer joint (0 for rear wheels)
-  int hidx;      // hinge index h2..h5
+  T sp, dsp, warm;   // state: spin angle, rate, warm-start acceleration
+  T ax, ay;          // spin axis (ax, ay, 0) in the body frame
+  T a, x, tau;       // solver: spin acceleration, step direction, smooth force
+  T g, cw;           // gradient entry and Schur pivot of the spin dof at the last assembly
+  T b[7];            // coupling of the spin dof with (lin3, ang3, own steer)
+  unsigned zone0;    // activity pattern of the wheel's rows at the last assembly
   Contact<T> con[2];
 };
 
-// point "acceleration" y = a_lin + a_ang x X + a_spin (axis x r) + a_steer (ez x r), projected on the frame
+// wheel constants by wheel index wi (RL, RR, FL, FR)
 template <typename T>
-ACKB_HD void project_point(const Kin<T>& k, const Contact<T>& c, const T* alin, const T* aang, T aspin, T asteer, T* out) {
+struct WheelK {
+  T c[3], isL, isR, J, cdiag, mu, flf, flR, flB, damp;
+  int hidx;
+};
+template <typename T>
+ACKB_HD WheelK<T> wheel_consts(const Consts<T>& C, int wi) {
+  WheelK<T> k;
+  k.c[0] = C.w_center[3 * wi]; k.c[1] = C.w_center[3 * wi + 1]; k.c[2] = C.w_center[3 * wi + 2];
+  k.isL = (wi == 2) ? T(1) : T(0);
+  k.isR = (wi == 3) ? T(1) : T(0);
+  k.hidx = 2 + wi;
+  k.J = C.h_inertia[2 + wi];
+  k.cdiag = k.J + C.h_armature[2 + wi];
+  k.mu = C.w_mu[wi];
+  k.flf = C.h_floss[2 + wi]; k.flR = C.h_flR[2 + wi]; k.flB = C.h_flB[2 + wi];
+  k.damp = C.h_damping[2 + wi];
+  return k;
+}
+
+// spin column u = axis x r and steer column w = ez x r of the point Jacobian (r = X - centre)
+template <typename T>
+ACKB_HD void contact_cols(const Wheel<T>& w, const WheelK<T>& wk, const T* X, T* u, T* wv) {
+  const T r0 = X[0] - wk.c[0], r1 = X[1] - wk.c[1], r2 = X[2] - wk.c[2];
+  u[0] = w.ay * r2; u[1] = -w.ax * r2; u[2] = w.ax * r1 - w.ay * r0;   // (ax, ay, 0) x r
+  const T st = wk.isL + wk.isR;
+  wv[0] = -r1 * st; wv[1] = r0 * st;
+}
+
+// point "acceleration" y = a_lin + a_ang x X + a_spin u + a_steer w, projected on the contact frame (n, t1, t2)
+template <typename T>
+ACKB_HD void project_point(const Kin<T>& k, const T* X, const T* u, const T* wv, const T* alin, const T* aang, T aspin, T asteer, T* out) {
   T y[3];
-  cross3(y, aang, c.x);
-  for (int i = 0; i < 3; ++i) y[i] += alin[i] + aspin * c.u[i] + asteer * c.w[i];
+  cross3(y, aang, X);
+  y[0] += alin[0] + aspin * u[0] + asteer * wv[0];
+  y[1] += alin[1] + aspin * u[1] + asteer * wv[1];
+  y[2] += alin[2] + aspin * u[2];
   out[0] = dot3(k.n, y); out[1] = dot3(k.t1, y); out[2] = dot3(k.t2, y);
 }
 
 // forces of the four pyramid rows of a contact at residual z (3-vector in the contact frame);
 // returns cost, fills phi = contact-frame force and the quadratic-zone flags q[4]
 template <typename T>
-ACKB_HD T pyramid_rows(const Contact<T>& c, const T* z, T* phi, T* q) {
-  T x[4] = {z[0] + c.mu * z[1], z[0] - c.mu * z[1], z[0] + c.mu * z[2], z[0] - c.mu * z[2]};
+ACKB_HD T pyramid_rows(T D, T mu, const T* z, T* phi, T* q) {
+  T x[4] = {z[0] + mu * z[1], z[0] - mu * z[1], z[0] + mu * z[2], z[0] - mu * z[2]};
   T f[4], cost = T(0);
+#pragma unroll
   for (int i = 0; i < 4; ++i) {
     bool act = x[i] < T(0);
     q[i] = act ? T(1) : T(0);
-    f[i] = act ? -c.D * x[i] : T(0);
-    cost += act ? T(0.5) * c.D * x[i] * x[i] : T(0);
+    f[i] = act ? -D * x[i] : T(0);
+    cost += act ? T(0.5) * D * x[i] * x[i] : T(0);
   }
   phi[0] = f[0] + f[1] + f[2] + f[3];
-  phi[1] = c.mu * (f[0] - f[1]);
-  phi[2] = c.mu * (f[2] - f[3]);
+  phi[1] = mu * (f[0] - f[1]);
+  phi[2] = mu * (f[2] - f[3]);
   return cost;
 }
 
@@ -460,7 +499,9 @@ struct Sim {
   static constexpr int WPL = 4 / LANES;
   using Tm = Team<LANES>;
   using N = Num<T>;
-  using State = EnvState<T, WPL>;
+  using State = EnvState<T>;
+  // contact loops are unrolled when the wheel record lives in registers (WPL == 1) and rolled when it is in shared memory
+  static constexpr int CU = (WPL == 1) ? 2 : 1;
 
   // ---- B1 kinematics: normalise the quaternion (written back, like mj_kinematics), rotation, floor frame
   ACKB_HD static void kinematics(State& e, Kin<T>& k) {
@@ -475,66 +516,54 @@ struct Sim {
     for (int i = 0; i < 3; ++i) { k.n[i] = k.R[6 + i]; k.t1[i] = k.R[3 + i]; k.t2[i] = -k.R[i]; }
   }
 
-  ACKB_HD static void setup_wheel(const Consts<T>& C, const State& e, int wi, int slot, Wheel<T>& w) {
-    for (int i = 0; i < 3; ++i) w.c[i] = C.w_center[3 * wi + i];
-    w.isL = (wi == 2) ? T(1) : T(0);
-    w.isR = (wi == 3) ? T(1) : T(0);
-    T s = w.isL * e.st[0] + w.isR * e.st[1];
+  // ---- B6/B7 floor contacts of one wheel (plane vs cylinder, in the body frame) and their row parameters
+  ACKB_HD static void collide_wheel(const Consts<T>& C, const State& e, const Kin<T>& k, const T* vb, int wi, const WheelK<T>& wk,
+                                    Wheel<T>& w, StepDiag& diag) {
+    const T s = wk.isL * e.st[0] + wk.isR * e.st[1];
     T sn, cs;
     N::sincos_small(s, &sn, &cs);
-    w.a[0] = -sn; w.a[1] = cs; w.a[2] = T(0);  // Rz(s) * (0, 1, 0)
-    w.J = C.h_inertia[2 + wi];
-    w.cdiag = w.J + C.h_armature[2 + wi];
-    w.dsteer = w.isL * e.dst[0] + w.isR * e.dst[1];
-    w.hidx = 2 + wi;
-    (void)slot;
-  }
-
-  // ---- B6/B7 floor contacts of one wheel (plane vs cylinder, in the body frame) and their row parameters
-  ACKB_HD static void collide_wheel(const Consts<T>& C, const State& e, const Kin<T>& k, const T* vb, int wi, int slot,
-                                    Wheel<T>& w, StepDiag& diag) {
+    w.ax = -sn; w.ay = cs;                       // Rz(s) * (0, 1, 0)
+    const T dsteer = wk.isL * e.dst[0] + wk.isR * e.dst[1];
     const T r = C.w_radius[wi], hl = C.w_halflen[wi];
     const T hO = e.p[2] - C.plane_z[0];
-    T ax[3] = {w.a[0], w.a[1], w.a[2]};
+    T ax[3] = {w.ax, w.ay, T(0)};
     T prjaxis = dot3(k.n, ax);
-    if (prjaxis > T(0)) { for (int i = 0; i < 3; ++i) ax[i] = -ax[i]; prjaxis = -prjaxis; }
-    const T dist = dot3(k.n, w.c) + hO;
+    if (prjaxis > T(0)) { ax[0] = -ax[0]; ax[1] = -ax[1]; prjaxis = -prjaxis; }
+    const T dist = dot3(k.n, wk.c) + hO;
     T vec[3];
+#pragma unroll
     for (int i = 0; i < 3; ++i) vec[i] = ax[i] * prjaxis - k.n[i];
     T len = N::sqrt_(dot3(vec, vec));
     if (len < N::minval) { diag.unsupported = 1; len = T(1); }  // disk parallel to the floor
+#pragma unroll
     for (int i = 0; i < 3; ++i) vec[i] *= r / len;
     const T prjvec = dot3(vec, k.n);
-    for (int i = 0; i < 3; ++i) ax[i] *= hl;
+    ax[0] *= hl; ax[1] *= hl;
     prjaxis *= hl;
     const T d0 = dist + prjaxis + prjvec, d1 = dist - prjaxis + prjvec;
     const bool has0 = d0 <= T(0), has1 = has0 && (d1 <= T(0));
     if (has0 && (dist + prjaxis - T(0.5) * prjvec <= T(0))) diag.unsupported = 1;  // cap faces the floor
     diag.ncon += (has0 ? 1 : 0) + (has1 ? 1 : 0);
-    const T dd[2] = {d0, d1};
-    const bool has[2] = {has0, has1};
-    const T sgn[2] = {T(1), T(-1)};
-    const T mu = C.w_mu[wi];
+    const T mu = wk.mu;
+#pragma unroll(CU)
     for (int c = 0; c < 2; ++c) {
       Contact<T>& con = w.con[c];
-      T rr[3];
-      for (int i = 0; i < 3; ++i) {
-        con.x[i] = w.c[i] + vec[i] + sgn[c] * ax[i] - k.n[i] * dd[c] * T(0.5);
-        rr[i] = con.x[i] - w.c[i];
-      }
-      cross3(con.u, w.a, rr);
-      const T st = w.isL + w.isR;
-      con.w[0] = -rr[1] * st; con.w[1] = rr[0] * st; con.w[2] = T(0);
-      con.mu = mu;
-      const bool active = has[c] && (dd[c] < T(0));  // dist >= includemargin(0): counted but excluded
-      T imp = impedance(&C.w_solimp[5 * wi], dd[c]);
-      T R0 = mjmax(N::minval, (T(1) - imp) / imp * C.w_tran[wi] * (T(1) + mu * mu));
+      const T dd = (c == 0) ? d0 : d1, sg = (c == 0) ? T(1) : T(-1);
+      const bool has = (c == 0) ? has0 : has1;
+      con.x[0] = wk.c[0] + vec[0] + sg * ax[0] - k.n[0] * dd * T(0.5);
+      con.x[1] = wk.c[1] + vec[1] + sg * ax[1] - k.n[1] * dd * T(0.5);
+      con.x[2] = wk.c[2] + vec[2] - k.n[2] * dd * T(0.5);
+      const bool active = has && (dd < T(0));  // dist >= includemargin(0): counted but excluded
+      const T imp = impedance(&C.w_solimp[5 * wi], dd);
+      const T R0 = mjmax(N::minval, (T(1) - imp) / imp * C.w_tran[wi] * (T(1) + mu * mu));
       con.D = active ? T(1) / (T(2) * C.w_mureg2[wi] * R0) : T(0);
-      T vel[3];
-      project_point(k, con, vb, e.om, e.dsp[slot], w.dsteer, vel);
-      con.aref[0] = -C.w_B[wi] * vel[0] - C.w_K[wi] * imp * dd[c];
-      con.aref[1] = -C.w_B[wi] * vel[1];
-      con.aref[2] = -C.w_B[wi] * vel[2];
+      T u[3], wv[2], vel[3];
+      contact_cols(w, wk, con.x, u, wv);
+      project_point(k, con.x, u, wv, vb, e.om, w.dsp, dsteer, vel);
+      // residual at a = 0 is minus the reference acceleration
+      con.z[0] = C.w_B[wi] * vel[0] + C.w_K[wi] * imp * dd;
+      con.z[1] = C.w_B[wi] * vel[1];
+      con.z[2] = C.w_B[wi] * vel[2];
     }
   }
 
@@ -546,6 +575,7 @@ struct Sim {
       s.eqD = T(1) / R;
       s.eq_aref = -C.eq_B[0] * (e.dst[0] - e.dst[1]) - C.eq_K[0] * imp * pos;
     } else { s.eqD = T(0); s.eq_aref = T(0); }
+#pragma unroll
     for (int i = 0; i < 2; ++i) {
       s.flf[i] = C.h_floss[i]; s.flR[i] = C.h_flR[i]; s.flD[i] = T(1) / C.h_flR[i];
       s.fl_aref[i] = -C.h_flB[i] * e.dst[i];
@@ -569,8 +599,9 @@ struct Sim {
   ACKB_HD static T actuator_force(const Consts<T>& C, const T* ctrl, int h, T len, T vel) {
     T f = T(0);
     const int nact = (int)C.nact[0];
-    for (int u = 0; u < 4; ++u) {
-      if (u >= nact || (int)C.act_hinge[u] != h) continue;
+#pragma unroll 1
+    for (int u = 0; u < nact; ++u) {
+      if ((int)C.act_hinge[u] != h) continue;
       T c = ctrl[u];
       if (C.act_ctrllimited[u] != T(0)) c = mjclip(c, C.act_ctrlrange[2 * u], C.act_ctrlrange[2 * u + 1]);
       T fu = C.act_gain[u] * c + C.act_bias[3 * u] + C.act_bias[3 * u + 1] * len + C.act_bias[3 * u + 2] * vel;
@@ -580,76 +611,9 @@ struct Sim {
     return f;
   }
 
-  // ---- B10/B12/B13 smooth generalised force  tau = passive - bias + actuation  (closed-form RNE, see header)
-  ACKB_HD static void smooth_forces(const Consts<T>& C, const State& e, const Kin<T>& k, const Wheel<T>* wh, const T* ctrl,
-                                    int lane, T* tau_sh, T* tau_sp) {
-    // wheel-derived terms: relative angular momentum, gyroscopic torque on the chassis and on the steer dofs
-    T part[8];
-    for (int i = 0; i < 8; ++i) part[i] = T(0);  // [hrel(3), gyro(3), steerL, steerR]
-    const T ez[3] = {T(0), T(0), T(1)};
-    for (int s = 0; s < WPL; ++s) {
-      const Wheel<T>& w = wh[s];
-      T ezxa[3], omxa[3], omxez[3];
-      cross3(ezxa, ez, w.a);
-      cross3(omxa, e.om, w.a);
-      cross3(omxez, e.om, ez);
-      for (int i = 0; i < 3; ++i) {
-        part[i] += w.J * e.dsp[s] * w.a[i];
-        part[3 + i] += w.J * e.dsp[s] * w.dsteer * ezxa[i];
-      }
-      T bias_steer = w.J * e.dsp[s] * omxa[2];  // ez . (om x a)
-      part[6] += w.isL * bias_steer;
-      part[7] += w.isR * bias_steer;
-      T bias_spin = w.J * w.dsteer * dot3(w.a, omxez);
-      tau_sp[s] = -C.h_damping[w.hidx] * e.dsp[s] - bias_spin + actuator_force(C, ctrl, w.hidx, e.sp[s], e.dsp[s]);
-    }
-    Tm::sum_n(part);
-    T gb[3];  // gravity in the body frame
-    for (int i = 0; i < 3; ++i) gb[i] = k.R[i] * C.gravity[0] + k.R[3 + i] * C.gravity[1] + k.R[6 + i] * C.gravity[2];
-    T Iw[3], h[3], t0[3], t1[3], t2[3];
-    const T* I = C.inertiaO;
-    Iw[0] = I[0] * e.om[0] + I[3] * e.om[1] + I[4] * e.om[2];
-    Iw[1] = I[3] * e.om[0] + I[1] * e.om[1] + I[5] * e.om[2];
-    Iw[2] = I[4] * e.om[0] + I[5] * e.om[1] + I[2] * e.om[2];
-    for (int i = 0; i < 3; ++i) h[i] = Iw[i] + part[i];
-    h[2] += C.h_inertia[0] * e.dst[0] + C.h_inertia[1] * e.dst[1];
-    cross3(t0, e.om, h);                 // om x (I_O om + h_rel)
-    cross3(t1, C.mcom, gb);              // m c x g
-    cross3(t2, e.om, C.mcom);
-    T t3[3];
-    cross3(t3, e.om, t2);                // om x (om x m c)
-    for (int i = 0; i < 3; ++i) {
-      tau_sh[i] = -(t3[i] - C.mass[0] * gb[i]);
-      tau_sh[3 + i] = -(t0[i] + part[3 + i] - t1[i]);
-    }
-    for (int i = 0; i < 2; ++i)
-      tau_sh[6 + i] = -C.h_damping[i] * e.dst[i] - part[6 + i] + actuator_force(C, ctrl, i, e.st[i], e.dst[i]);
-    (void)lane;
-  }
-
-  // ---- M~ x  (B4 CRB, folded): shared part needs one 3-value team sum
-  ACKB_HD static void mul_M(const Consts<T>& C, const Wheel<T>* wh, const T* x_sh, const T* x_sp, T* y_sh, T* y_sp) {
-    T acc[3] = {T(0), T(0), T(0)};
-    for (int s = 0; s < WPL; ++s) {
-      const Wheel<T>& w = wh[s];
-      for (int i = 0; i < 3; ++i) acc[i] += w.J * w.a[i] * x_sp[s];
-      y_sp[s] = w.J * dot3(w.a, x_sh + 3) + w.cdiag * x_sp[s];
-    }
-    Tm::sum_n(acc);
-    T c1[3], c2[3];
-    cross3(c1, C.mcom, x_sh + 3);  // m c x a_ang
-    cross3(c2, C.mcom, x_sh);      // m c x a_lin
-    const T* I = C.inertiaO;
-    const T* a = x_sh + 3;
-    for (int i = 0; i < 3; ++i) y_sh[i] = C.mass[0] * x_sh[i] - c1[i];
-    y_sh[3] = c2[0] + I[0] * a[0] + I[3] * a[1] + I[4] * a[2] + acc[0];
-    y_sh[4] = c2[1] + I[3] * a[0] + I[1] * a[1] + I[5] * a[2] + acc[1];
-    y_sh[5] = c2[2] + I[4] * a[0] + I[5] * a[1] + I[2] * a[2] + acc[2] + C.h_inertia[0] * x_sh[6] + C.h_inertia[1] * x_sh[7];
-    for (int i = 0; i < 2; ++i) y_sh[6 + i] = C.h_inertia[i] * a[2] + (C.h_inertia[i] + C.h_armature[i]) * x_sh[6 + i];
-  }
-
-  // constant shared block of M~ (packed lower triangle), optionally with h * damping on the steer diagonal
-  ACKB_HD static void shared_mass(const Consts<T>& C, T hdamp, T* S) {
+  // constant shared block of M~ (packed lower triangle)
+  ACKB_HD static void shared_mass(const Consts<T>& C, T* S) {
+#pragma unroll
     for (int i = 0; i < 36; ++i) S[i] = T(0);
     const T m = C.mass[0], cx = C.mcom[0], cy = C.mcom[1], cz = C.mcom[2];
     S[tri(0, 0)] = S[tri(1, 1)] = S[tri(2, 2)] = m;
@@ -660,63 +624,118 @@ struct Sim {
     const T* I = C.inertiaO;
     S[tri(3, 3)] = I[0]; S[tri(4, 4)] = I[1]; S[tri(5, 5)] = I[2];
     S[tri(4, 3)] = I[3]; S[tri(5, 3)] = I[4]; S[tri(5, 4)] = I[5];
+#pragma unroll
     for (int i = 0; i < 2; ++i) {
       S[tri(6 + i, 5)] = C.h_inertia[i];
-      S[tri(6 + i, 6 + i)] = C.h_inertia[i] + C.h_armature[i] + hdamp * C.h_damping[i];
+      S[tri(6 + i, 6 + i)] = C.h_inertia[i] + C.h_armature[i];
     }
   }
 
-  // point-Jacobian image of the shared/spin accelerations for every contact of this lane:
-  // out = F Jp x  (3-vector in the contact frame per contact)
-  ACKB_HD static void contact_images(const Kin<T>& k, const Wheel<T>* wh, const T* x_sh, const T* x_sp, T (*out)[2][3]) {
+  // shared part of M~ x given the team-summed wheel term acc = sum_w J a_w x_spin,w
+  ACKB_HD static void mul_M_shared(const Consts<T>& C, const T* x_sh, const T* acc, T* y_sh) {
+    T c1[3], c2[3];
+    cross3(c1, C.mcom, x_sh + 3);  // m c x a_ang
+    cross3(c2, C.mcom, x_sh);      // m c x a_lin
+    const T* I = C.inertiaO;
+    const T* a = x_sh + 3;
 #pragma unroll
-    for (int s = 0; s < WPL; ++s) {
-      const Wheel<T>& w = wh[s];
-      const T ast = w.isL * x_sh[6] + w.isR * x_sh[7];
+    for (int i = 0; i < 3; ++i) y_sh[i] = C.mass[0] * x_sh[i] - c1[i];
+    y_sh[3] = c2[0] + I[0] * a[0] + I[3] * a[1] + I[4] * a[2] + acc[0];
+    y_sh[4] = c2[1] + I[3] * a[0] + I[1] * a[1] + I[5] * a[2] + acc[1];
+    y_sh[5] = c2[2] + I[4] * a[0] + I[5] * a[1] + I[2] * a[2] + acc[2] + C.h_inertia[0] * x_sh[6] + C.h_inertia[1] * x_sh[7];
 #pragma unroll
-      for (int c = 0; c < 2; ++c) project_point(k, w.con[c], x_sh, x_sh + 3, x_sp[s], ast, out[s][c]);
-    }
+    for (int i = 0; i < 2; ++i) y_sh[6 + i] = C.h_inertia[i] * a[2] + (C.h_inertia[i] + C.h_armature[i]) * x_sh[6 + i];
   }
 
   // ---- one physics substep (mj_step): everything between kinematics and integration.
-  // `k` must hold the kinematics of the current state.
+  // `k` must hold the kinematics of the current state; `wh` are the WPL wheel records of this lane.
   //
-  // Solver structure (B13-B16 fused in ONE loop body so that the instruction footprint stays small):
-  //   every pass assembles the arrow-shaped system  H x = -g  at the current point, LDL^T-factorises its 8 x 8
-  //   Schur complement and solves it.  Newton passes use H = M~ + J^T D J, g = M~ a - tau - J^T f and are followed by
-  //   an exact line search; the last pass ("Euler pass") uses H = M~ + h B, g = -(tau + J^T f), whose solution is the
-  //   implicitly damped acceleration that MuJoCo's Euler integrator advances with.
-  //   The iteration starts from the warm start (previous qacc) as MuJoCo does when its cost beats qacc_smooth; the
-  //   minimiser is unique, so the starting point only affects the iteration count (qacc_smooth is never needed).
-  ACKB_HD static void dynamics(const Consts<T>& C, State& e, const Kin<T>& k, const T* ctrl, int lane, StepDiag& diag,
+  // Solver structure (B13-B16): ONE loop body.  Every trip moves along the current direction x with an exact line
+  // search and then assembles the arrow-shaped Newton system  H x = -g  (H = M~ + J^T D J, g = M~ a - tau - J^T f),
+  // LDL^T-factorises its 8 x 8 Schur complement and solves it.  The iteration starts at a = 0 with a unit step along
+  // the warm start (previous qacc), as MuJoCo does when its cost beats qacc_smooth; the minimiser is unique, so the
+  // starting point only affects the iteration count (qacc_smooth is never needed).
+  ACKB_HD static void dynamics(const Consts<T>& C, State& e, const Kin<T>& k, const T* ctrl, int lane, Wheel<T>* wh, StepDiag& diag,
                                DebugTap<T>* tap) {
     const T h = C.timestep[0];
     T vb[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) vb[i] = k.R[i] * e.vw[0] + k.R[3 + i] * e.vw[1] + k.R[6 + i] * e.vw[2];
 
-    Wheel<T> wh[WPL];
+    // ---- wheels: collision, spin-dof smooth force; wheel-derived parts of the chassis / steer bias (closed-form RNE)
+    T bpart[8];   // [hrel(3), gyro(3), steerL, steerR]
 #pragma unroll
+    for (int i = 0; i < 8; ++i) bpart[i] = T(0);
+    bool warm_ok = true;
+#pragma unroll 1
     for (int s = 0; s < WPL; ++s) {
-      setup_wheel(C, e, lane * WPL + s, s, wh[s]);
-      collide_wheel(C, e, k, vb, lane * WPL + s, s, wh[s], diag);
+      const int wi = lane * WPL + s;
+      const WheelK<T> wk = wheel_consts(C, wi);
+      Wheel<T>& w = wh[s];
+      collide_wheel(C, e, k, vb, wi, wk, w, diag);
+      const T dsteer = wk.isL * e.dst[0] + wk.isR * e.dst[1];
+      const T aw[3] = {w.ax, w.ay, T(0)};
+      const T ez[3] = {T(0), T(0), T(1)};
+      T ezxa[3], omxa[3], omxez[3];
+      cross3(ezxa, ez, aw);
+      cross3(omxa, e.om, aw);
+      cross3(omxez, e.om, ez);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        bpart[i] += wk.J * w.dsp * aw[i];
+        bpart[3 + i] += wk.J * w.dsp * dsteer * ezxa[i];
+      }
+      const T bias_steer = wk.J * w.dsp * omxa[2];  // ez . (om x a)
+      bpart[6] += wk.isL * bias_steer;
+      bpart[7] += wk.isR * bias_steer;
+      const T bias_spin = wk.J * dsteer * dot3(aw, omxez);
+      w.tau = -wk.damp * w.dsp - bias_spin + actuator_force(C, ctrl, wk.hidx, w.sp, w.dsp);
+      w.a = T(0);
+      w.x = w.warm;
+      w.zone0 = 0u;
+      warm_ok = warm_ok && (N::abs_(w.warm) <= T(1e10));
     }
+    Tm::sum_n(bpart);
     // plate hull vs floor: flagged only (35 mm clearance; reachable only after a roll-over)
     if (lane == 0) {
       const int nh = (int)C.nhull[0];
       const T hO = e.p[2] - C.plane_z[0];
+#pragma unroll 1
       for (int i = 0; i < nh; ++i) if (dot3(k.n, &C.hull_pts[3 * i]) + hO <= T(0)) diag.unsupported = 1;
     }
     SharedRows<T> sr;
     make_shared_rows(C, e, sr);
 
-    T tau_sh[8], tau_sp[WPL];
-    smooth_forces(C, e, k, wh, ctrl, lane, tau_sh, tau_sp);
+    // ---- B10/B12/B13 shared smooth force  tau = passive - bias + actuation  (closed-form RNE, see header)
+    T tau_sh[8];
+    {
+      T gb[3];  // gravity in the body frame
+#pragma unroll
+      for (int i = 0; i < 3; ++i) gb[i] = k.R[i] * C.gravity[0] + k.R[3 + i] * C.gravity[1] + k.R[6 + i] * C.gravity[2];
+      T Iw[3], hh[3], t0[3], t1[3], t2[3], t3[3];
+      const T* I = C.inertiaO;
+      Iw[0] = I[0] * e.om[0] + I[3] * e.om[1] + I[4] * e.om[2];
+      Iw[1] = I[3] * e.om[0] + I[1] * e.om[1] + I[5] * e.om[2];
+      Iw[2] = I[4] * e.om[0] + I[5] * e.om[1] + I[2] * e.om[2];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) hh[i] = Iw[i] + bpart[i];
+      hh[2] += C.h_inertia[0] * e.dst[0] + C.h_inertia[1] * e.dst[1];
+      cross3(t0, e.om, hh);                // om x (I_O om + h_rel)
+      cross3(t1, C.mcom, gb);              // m c x g
+      cross3(t2, e.om, C.mcom);
+      cross3(t3, e.om, t2);                // om x (om x m c)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        tau_sh[i] = -(t3[i] - C.mass[0] * gb[i]);
+        tau_sh[3 + i] = -(t0[i] + bpart[3 + i] - t1[i]);
+      }
+#pragma unroll 1
+      for (int i = 0; i < 2; ++i)
+        tau_sh[6 + i] = -C.h_damping[i] * e.dst[i] - bpart[6 + i] + actuator_force(C, ctrl, i, e.st[i], e.dst[i]);
+    }
 
-    // current point a (starts at 0 and takes a unit step along the warm start), M~ a, contact residuals z = F Jp a - aref
-    T a_sh[8], a_sp[WPL], Ma_sh[8], Ma_sp[WPL], z[WPL][2][3];
-    T x_sh[8], x_sp[WPL];   // step direction
-    bool warm_ok = true;
+    // current point a (starts at 0 and takes a unit step along the warm start), M~ a
+    T a_sh[8], Ma_sh[8], x_sh[8];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       x_sh[i] = k.R[i] * e.warm_l[0] + k.R[3 + i] * e.warm_l[1] + k.R[6 + i] * e.warm_l[2];
@@ -725,21 +744,11 @@ struct Sim {
     x_sh[6] = e.warm_st[0]; x_sh[7] = e.warm_st[1];
 #pragma unroll
     for (int i = 0; i < 8; ++i) { warm_ok = warm_ok && (N::abs_(x_sh[i]) <= T(1e10)); a_sh[i] = T(0); Ma_sh[i] = T(0); }
-#pragma unroll
-    for (int s = 0; s < WPL; ++s) {
-      x_sp[s] = e.warm_sp[s];
-      warm_ok = warm_ok && (N::abs_(x_sp[s]) <= T(1e10));
-      a_sp[s] = T(0); Ma_sp[s] = T(0);
-#pragma unroll
-      for (int c = 0; c < 2; ++c)
-#pragma unroll
-        for (int i = 0; i < 3; ++i) z[s][c][i] = -wh[s].con[c].aref[i];
-    }
     if (Tm::sum(warm_ok ? 0 : 1) != 0) {   // unusable warm start: begin at a = 0
 #pragma unroll
       for (int i = 0; i < 8; ++i) x_sh[i] = T(0);
-#pragma unroll
-      for (int s = 0; s < WPL; ++s) x_sp[s] = T(0);
+#pragma unroll 1
+      for (int s = 0; s < WPL; ++s) wh[s].x = T(0);
     }
 
     const T tol = mjmax(C.tolerance[0], N::tol_floor);
@@ -750,45 +759,61 @@ struct Sim {
     int phase = 0;
     bool first = true;
     T lam2 = T(0);
-    unsigned zone0[WPL];
     unsigned szone0 = 0u;
-#pragma unroll
-    for (int s = 0; s < WPL; ++s) zone0[s] = 0u;
     while (Tm::loop_any(phase != 2)) {
       const bool stepping = (phase == 0);
-      if (Tm::any(stepping)) {
-        // ---- move along x: exact line search (safeguarded Newton on f'(alpha)), then update the point
-        T Mv_sh[8], Mv_sp[WPL], zv[WPL][2][3];
-        mul_M(C, wh, x_sh, x_sp, Mv_sh, Mv_sp);
-        contact_images(k, wh, x_sh, x_sp, zv);
+      // ---- move along x: exact line search (safeguarded Newton on f'(alpha)), then update the point
+      {
+        // M~ x (shared part), contact images of x, line-search constants
+        T acc[5] = {T(0), T(0), T(0), T(0), T(0)};  // sum_w J a_w x_w (3), private parts of x.Mx and x.(Ma - tau)
+#pragma unroll 1
+        for (int s = 0; s < WPL; ++s) {
+          const int wi = lane * WPL + s;
+          const WheelK<T> wk = wheel_consts(C, wi);
+          Wheel<T>& w = wh[s];
+          const T aw_aang_x = w.ax * x_sh[3] + w.ay * x_sh[4], aw_aang_a = w.ax * a_sh[3] + w.ay * a_sh[4];
+          const T Mv_sp = wk.J * aw_aang_x + wk.cdiag * w.x, Ma_sp = wk.J * aw_aang_a + wk.cdiag * w.a;
+          acc[0] += wk.J * w.ax * w.x; acc[1] += wk.J * w.ay * w.x;
+          acc[3] += w.x * Mv_sp; acc[4] += w.x * (Ma_sp - w.tau);
+          const T ast = wk.isL * x_sh[6] + wk.isR * x_sh[7];
+#pragma unroll(CU)
+          for (int c = 0; c < 2; ++c) {
+            Contact<T>& con = w.con[c];
+            T u[3], wv[2];
+            contact_cols(w, wk, con.x, u, wv);
+            project_point(k, con.x, u, wv, x_sh, x_sh + 3, w.x, ast, con.zv);
+          }
+        }
+        Tm::sum_n(acc);
+        T Mv_sh[8];
+        mul_M_shared(C, x_sh, acc, Mv_sh);
+        T sMs = acc[3], sg = acc[4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { sMs += x_sh[i] * Mv_sh[i]; sg += x_sh[i] * (Ma_sh[i] - tau_sh[i]); }
         T alpha = T(1);
         bool exact = false;
         bool ls_on = stepping && !first;
-        T quad[2] = {T(0), T(0)};  // team-summed private parts of s.M.s and s.(Ma - tau)
-#pragma unroll
-        for (int s = 0; s < WPL; ++s) { quad[0] += x_sp[s] * Mv_sp[s]; quad[1] += x_sp[s] * (Ma_sp[s] - tau_sp[s]); }
-        Tm::sum_n(quad);
-        T sMs = quad[0], sg = quad[1];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { sMs += x_sh[i] * Mv_sh[i]; sg += x_sh[i] * (Ma_sh[i] - tau_sh[i]); }
         T lo = T(0), hi = T(-1);
         for (int ls = 0; ls < maxls && Tm::any(ls_on); ++ls) {
           T d[3] = {T(0), T(0), T(0)};
-#pragma unroll
+#pragma unroll 1
           for (int s = 0; s < WPL; ++s) {
+            const int wi = lane * WPL + s;
+            const WheelK<T> wk = wheel_consts(C, wi);
             const Wheel<T>& w = wh[s];
             T f, q;
-            floss_row(a_sp[s] + alpha * x_sp[s] + C.h_flB[w.hidx] * e.dsp[s], C.h_floss[w.hidx], C.h_flR[w.hidx], &f, &q);
-            d[0] -= f * x_sp[s];
-            d[1] += q / C.h_flR[w.hidx] * x_sp[s] * x_sp[s];
+            floss_row(w.a + alpha * w.x + wk.flB * w.dsp, wk.flf, wk.flR, &f, &q);
+            d[0] -= f * w.x;
+            d[1] += q / wk.flR * w.x * w.x;
             unsigned zone = (q != T(0)) ? 1u : (f > T(0) ? 0u : 2u);
-#pragma unroll
+#pragma unroll(CU)
             for (int c = 0; c < 2; ++c) {
               const Contact<T>& con = w.con[c];
-              const T* z0 = z[s][c]; const T* z1 = zv[s][c];
-              const T jr[4] = {z1[0] + con.mu * z1[1], z1[0] - con.mu * z1[1], z1[0] + con.mu * z1[2], z1[0] - con.mu * z1[2]};
-              const T xr[4] = {z0[0] + con.mu * z0[1] + alpha * jr[0], z0[0] - con.mu * z0[1] + alpha * jr[1],
-                               z0[0] + con.mu * z0[2] + alpha * jr[2], z0[0] - con.mu * z0[2] + alpha * jr[3]};
+              const T* z0 = con.z; const T* z1 = con.zv;
+              const T mu = wk.mu;
+              const T jr[4] = {z1[0] + mu * z1[1], z1[0] - mu * z1[1], z1[0] + mu * z1[2], z1[0] - mu * z1[2]};
+              const T xr[4] = {z0[0] + mu * z0[1] + alpha * jr[0], z0[0] - mu * z0[1] + alpha * jr[1],
+                               z0[0] + mu * z0[2] + alpha * jr[2], z0[0] - mu * z0[2] + alpha * jr[3]};
               unsigned zb = 0u;
 #pragma unroll
               for (int r = 0; r < 4; ++r) {
@@ -799,7 +824,7 @@ struct Sim {
               }
               zone = (zone << 4) | zb;
             }
-            d[2] += (zone != zone0[s]) ? T(1) : T(0);
+            d[2] += (zone != w.zone0) ? T(1) : T(0);
           }
           Tm::sum_n(d);
           T gL, gR, kLL, kLR, kRR;
@@ -824,13 +849,14 @@ struct Sim {
           if (!first) ++iter;
 #pragma unroll
           for (int i = 0; i < 8; ++i) { a_sh[i] += alpha * x_sh[i]; Ma_sh[i] += alpha * Mv_sh[i]; }
-#pragma unroll
+#pragma unroll 1
           for (int s = 0; s < WPL; ++s) {
-            a_sp[s] += alpha * x_sp[s]; Ma_sp[s] += alpha * Mv_sp[s];
-#pragma unroll
+            Wheel<T>& w = wh[s];
+            w.a += alpha * w.x;
+#pragma unroll(CU)
             for (int c = 0; c < 2; ++c)
 #pragma unroll
-              for (int i = 0; i < 3; ++i) z[s][c][i] += alpha * zv[s][c][i];
+              for (int i = 0; i < 3; ++i) w.con[c].z[i] += alpha * w.con[c].zv[i];
           }
           first = false;
           if (exact || iter >= maxit) phase = 2;
@@ -844,45 +870,48 @@ struct Sim {
       T part[45];
 #pragma unroll
       for (int i = 0; i < 45; ++i) part[i] = T(0);
-      T gsp[WPL], cw[WPL], b[WPL][8];
-#pragma unroll
+#pragma unroll 1
       for (int s = 0; s < WPL; ++s) {
-        const Wheel<T>& w = wh[s];
+        const int wi = lane * WPL + s;
+        const WheelK<T> wk = wheel_consts(C, wi);
+        Wheel<T>& w = wh[s];
         T f, q;
-        floss_row(a_sp[s] + C.h_flB[w.hidx] * e.dsp[s], C.h_floss[w.hidx], C.h_flR[w.hidx], &f, &q);
+        floss_row(w.a + wk.flB * w.dsp, wk.flf, wk.flR, &f, &q);
         unsigned zone = (q != T(0)) ? 1u : (f > T(0) ? 0u : 2u);
-        T gs_sp = Ma_sp[s] - tau_sp[s] - f;
-        T cs = w.cdiag + q / C.h_flR[w.hidx];
+        T gs_sp = wk.J * (w.ax * a_sh[3] + w.ay * a_sh[4]) + wk.cdiag * w.a - w.tau - f;
+        T cs = wk.cdiag + q / wk.flR;
         T Hll[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};   // 00 10 11 20 21 22
         T Hal[3][3] = {{T(0), T(0), T(0)}, {T(0), T(0), T(0)}, {T(0), T(0), T(0)}};
         T Haa[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
         T Hsl[3] = {T(0), T(0), T(0)}, Hsa[3] = {T(0), T(0), T(0)}, Hss = T(0);
-        T bl[3] = {T(0), T(0), T(0)}, ba[3] = {w.J * w.a[0], w.J * w.a[1], w.J * w.a[2]}, bs = T(0);
+        T bl[3] = {T(0), T(0), T(0)}, ba[3] = {wk.J * w.ax, wk.J * w.ay, T(0)}, bs = T(0);
         T gl[3] = {T(0), T(0), T(0)}, ga[3] = {T(0), T(0), T(0)}, gst = T(0);
-#pragma unroll
+        const T mu = wk.mu;
+#pragma unroll(CU)
         for (int c = 0; c < 2; ++c) {
           const Contact<T>& con = w.con[c];
           T phi[3], qq[4];
-          pyramid_rows(con, z[s][c], phi, qq);
+          pyramid_rows(con.D, mu, con.z, phi, qq);
           if (con.D > T(0)) zone = (zone << 4) | (qq[0] != T(0) ? 1u : 0u) | (qq[1] != T(0) ? 2u : 0u) | (qq[2] != T(0) ? 4u : 0u) | (qq[3] != T(0) ? 8u : 0u);
           else zone <<= 4;
           // S3 = D F^T W F with W the active-row weights on (n, t1, t2); symmetric 3x3 in the body frame
-          const T mu = con.mu, Dh = con.D;
           const T W00 = qq[0] + qq[1] + qq[2] + qq[3], W01 = mu * (qq[0] - qq[1]), W02 = mu * (qq[2] - qq[3]);
           const T W11 = mu * mu * (qq[0] + qq[1]), W22 = mu * mu * (qq[2] + qq[3]);
           T r0[3], r1[3], r2[3];
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
-            r0[i] = Dh * (W00 * k.n[i] + W01 * k.t1[i] + W02 * k.t2[i]);
-            r1[i] = Dh * (W01 * k.n[i] + W11 * k.t1[i]);
-            r2[i] = Dh * (W02 * k.n[i] + W22 * k.t2[i]);
+            r0[i] = con.D * (W00 * k.n[i] + W01 * k.t1[i] + W02 * k.t2[i]);
+            r1[i] = con.D * (W01 * k.n[i] + W11 * k.t1[i]);
+            r2[i] = con.D * (W02 * k.n[i] + W22 * k.t2[i]);
           }
           T S3[3][3];
 #pragma unroll
           for (int i = 0; i < 3; ++i)
 #pragma unroll
             for (int j = 0; j <= i; ++j) { S3[i][j] = k.n[i] * r0[j] + k.t1[i] * r1[j] + k.t2[i] * r2[j]; S3[j][i] = S3[i][j]; }
-          const T* X = con.x;
+          const T X[3] = {con.x[0], con.x[1], con.x[2]};
+          T u[3], wv[2];
+          contact_cols(w, wk, X, u, wv);
           Hll[0] += S3[0][0]; Hll[1] += S3[1][0]; Hll[2] += S3[1][1]; Hll[3] += S3[2][0]; Hll[4] += S3[2][1]; Hll[5] += S3[2][2];
           // (ang, lin) block: column j = X x S3[:, j];  (ang, ang) block: column j = X x (S3 g_j), g_j = e_j x X
           T Cj[3][3];
@@ -905,14 +934,14 @@ struct Sim {
           // spin column u and steer column wv
           T Su[3], Sw[3], XSu[3], XSw[3];
 #pragma unroll
-          for (int i = 0; i < 3; ++i) { Su[i] = S3[i][0] * con.u[0] + S3[i][1] * con.u[1] + S3[i][2] * con.u[2]; Sw[i] = S3[i][0] * con.w[0] + S3[i][1] * con.w[1]; }
+          for (int i = 0; i < 3; ++i) { Su[i] = S3[i][0] * u[0] + S3[i][1] * u[1] + S3[i][2] * u[2]; Sw[i] = S3[i][0] * wv[0] + S3[i][1] * wv[1]; }
           cross3(XSu, X, Su);
           cross3(XSw, X, Sw);
 #pragma unroll
           for (int i = 0; i < 3; ++i) { bl[i] += Su[i]; ba[i] += XSu[i]; Hsl[i] += Sw[i]; Hsa[i] += XSw[i]; }
-          cs += dot3(con.u, Su);
-          bs += con.w[0] * Su[0] + con.w[1] * Su[1];
-          Hss += con.w[0] * Sw[0] + con.w[1] * Sw[1];
+          cs += dot3(u, Su);
+          bs += wv[0] * Su[0] + wv[1] * Su[1];
+          Hss += wv[0] * Sw[0] + wv[1] * Sw[1];
           // body-frame contact force and its generalised image (enters the gradient with a minus sign)
           T Phi[3], XF[3];
 #pragma unroll
@@ -920,15 +949,16 @@ struct Sim {
           cross3(XF, X, Phi);
 #pragma unroll
           for (int i = 0; i < 3; ++i) { gl[i] -= Phi[i]; ga[i] -= XF[i]; }
-          gst -= con.w[0] * Phi[0] + con.w[1] * Phi[1];
-          gs_sp -= dot3(con.u, Phi);
+          gst -= wv[0] * Phi[0] + wv[1] * Phi[1];
+          gs_sp -= dot3(u, Phi);
         }
-        if (phase == 0) zone0[s] = zone;
-        gsp[s] = gs_sp; cw[s] = cs;
-        T gsh_w[8];
+        if (phase == 0) w.zone0 = zone;
+        w.g = gs_sp; w.cw = cs;
+        T b8[8], gsh_w[8];
 #pragma unroll
-        for (int i = 0; i < 3; ++i) { b[s][i] = bl[i]; b[s][3 + i] = ba[i]; gsh_w[i] = gl[i]; gsh_w[3 + i] = ga[i]; }
-        b[s][6] = w.isL * bs; b[s][7] = w.isR * bs; gsh_w[6] = w.isL * gst; gsh_w[7] = w.isR * gst;
+        for (int i = 0; i < 3; ++i) { b8[i] = bl[i]; b8[3 + i] = ba[i]; w.b[i] = bl[i]; w.b[3 + i] = ba[i]; gsh_w[i] = gl[i]; gsh_w[3 + i] = ga[i]; }
+        w.b[6] = bs;
+        b8[6] = wk.isL * bs; b8[7] = wk.isR * bs; gsh_w[6] = wk.isL * gst; gsh_w[7] = wk.isR * gst;
         part[tri(0, 0)] += Hll[0]; part[tri(1, 0)] += Hll[1]; part[tri(1, 1)] += Hll[2];
         part[tri(2, 0)] += Hll[3]; part[tri(2, 1)] += Hll[4]; part[tri(2, 2)] += Hll[5];
 #pragma unroll
@@ -939,23 +969,23 @@ struct Sim {
         part[tri(5, 3)] += Haa[3]; part[tri(5, 4)] += Haa[4]; part[tri(5, 5)] += Haa[5];
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-          part[tri(6, j)] += w.isL * Hsl[j]; part[tri(6, 3 + j)] += w.isL * Hsa[j];
-          part[tri(7, j)] += w.isR * Hsl[j]; part[tri(7, 3 + j)] += w.isR * Hsa[j];
+          part[tri(6, j)] += wk.isL * Hsl[j]; part[tri(6, 3 + j)] += wk.isL * Hsa[j];
+          part[tri(7, j)] += wk.isR * Hsl[j]; part[tri(7, 3 + j)] += wk.isR * Hsa[j];
         }
-        part[tri(6, 6)] += w.isL * Hss; part[tri(7, 7)] += w.isR * Hss;
+        part[tri(6, 6)] += wk.isL * Hss; part[tri(7, 7)] += wk.isR * Hss;
         const T ci = T(1) / cs;
 #pragma unroll
         for (int a = 0; a < 8; ++a) {
-          const T bc = b[s][a] * ci;
+          const T bc = b8[a] * ci;
 #pragma unroll
-          for (int bb = 0; bb <= a; ++bb) part[tri(a, bb)] -= bc * b[s][bb];
+          for (int bb = 0; bb <= a; ++bb) part[tri(a, bb)] -= bc * b8[bb];
           part[36 + a] += gsh_w[a] - bc * gs_sp;
         }
         part[44] += gs_sp * gs_sp * ci;
       }
       Tm::sum_n(part);
       T S[36];
-      shared_mass(C, T(0), S);
+      shared_mass(C, S);
 #pragma unroll
       for (int i = 0; i < 36; ++i) S[i] += part[i];
       T fL, fR, hLL, hLR, hRR;
@@ -969,18 +999,21 @@ struct Sim {
       for (int i = 0; i < 8; ++i) y_sh[i] = rhs[i];
       ldl8_factor(S);
       ldl8_solve(S, y_sh);
-      if (phase != 2) {   // finished environments keep their solution
+      if (phase != 2) {   // converged environments keep their solution
         szone0 = shared_rows_zone(sr, a_sh[6], a_sh[7]);
         lam2 = part[44];  // Newton decrement g^T H^-1 g
 #pragma unroll
         for (int i = 0; i < 8; ++i) lam2 += rhs[i] * y_sh[i];
         // x = -H^-1 g
-#pragma unroll
+#pragma unroll 1
         for (int s = 0; s < WPL; ++s) {
+          const int wi = lane * WPL + s;
+          Wheel<T>& w = wh[s];
           T dotb = T(0);
 #pragma unroll
-          for (int a = 0; a < 8; ++a) dotb += b[s][a] * y_sh[a];
-          x_sp[s] = -(gsp[s] - dotb) / cw[s];
+          for (int a = 0; a < 6; ++a) dotb += w.b[a] * y_sh[a];
+          dotb += w.b[6] * ((wi == 2) ? y_sh[6] : ((wi == 3) ? y_sh[7] : T(0)));
+          w.x = -(w.g - dotb) / w.cw;
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) x_sh[i] = -y_sh[i];
@@ -988,22 +1021,22 @@ struct Sim {
         if (!(C.solver_scale[0] * T(0.5) * lam2 >= tol)) phase = 2;
       }
     }
+    diag.niter = iter;
 
     // ---- B16 implicit joint damping.  At the minimiser M~ a = tau + J^T f, so MuJoCo's integration acceleration
     // (M~ + hB)^-1 (tau + J^T f) equals a - y with (M~ + hB) y = hB a.  B acts on the hinges only; after eliminating the
     // spin dofs the 8x8 system matrix is a constant (inverse P precomputed by the model compiler) minus a rank-2 term
     // from the two front spin axes, handled with the Woodbury identity.
-    T yi_sh[8], yi_sp[WPL];
+    T yi_sh[8];
     {
       T part3[3] = {T(0), T(0), T(0)};
-      T dsp[WPL];
-#pragma unroll
+#pragma unroll 1
       for (int s = 0; s < WPL; ++s) {
+        const int wi = lane * WPL + s;
+        const WheelK<T> wk = wheel_consts(C, wi);
         const Wheel<T>& w = wh[s];
-        dsp[s] = h * C.h_damping[w.hidx] * a_sp[s];
-        const T coef = w.J * dsp[s] * C.w_cEinv[w.hidx - 2];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) part3[i] -= coef * w.a[i];
+        const T coef = wk.J * (h * wk.damp * w.a) * C.w_cEinv[wi];
+        part3[0] -= coef * w.ax; part3[1] -= coef * w.ay;
       }
       Tm::sum_n(part3);
       T r[8] = {T(0), T(0), T(0), part3[0], part3[1], part3[2], h * C.h_damping[0] * a_sh[6], h * C.h_damping[1] * a_sh[7]};
@@ -1034,47 +1067,42 @@ struct Sim {
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         yi_sh[i] = t[i] + C.eulerP[i >= 3 ? tri(i, 3) : tri(3, i)] * vx + C.eulerP[i >= 4 ? tri(i, 4) : tri(4, i)] * vy;
-#pragma unroll
-      for (int s = 0; s < WPL; ++s) {
-        const Wheel<T>& w = wh[s];
-        yi_sp[s] = (dsp[s] - w.J * dot3(w.a, yi_sh + 3)) * C.w_cEinv[w.hidx - 2];
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) x_sh[i] = a_sh[i] - yi_sh[i];   // integration acceleration
-#pragma unroll
-      for (int s = 0; s < WPL; ++s) x_sp[s] = a_sp[s] - yi_sp[s];
     }
-    diag.niter = iter;
 
     if (tap) {
       for (int i = 0; i < 8; ++i) { tap->tau[i] = tau_sh[i]; tap->a_smooth[i] = T(0); tap->a[i] = a_sh[i]; tap->fc[i] = T(0); }
       for (int s = 0; s < WPL; ++s) {
         int wi = lane * WPL + s;
-        tap->tau[8 + wi] = tau_sp[s]; tap->a_smooth[8 + wi] = T(0); tap->a[8 + wi] = a_sp[s]; tap->fc[8 + wi] = T(0);
+        tap->tau[8 + wi] = wh[s].tau; tap->a_smooth[8 + wi] = T(0); tap->a[8 + wi] = wh[s].a; tap->fc[8 + wi] = T(0);
       }
       tap->niter = iter; tap->nls = nls;
     }
 
-    // warm start for the next step = solver acceleration, MuJoCo coordinates
+    // warm start for the next step = solver acceleration (MuJoCo coordinates); B16: velocities advance with the
+    // implicitly damped acceleration a - y, then positions with the new velocities (semi-implicit Euler)
+#pragma unroll 1
+    for (int s = 0; s < WPL; ++s) {
+      const int wi = lane * WPL + s;
+      const WheelK<T> wk = wheel_consts(C, wi);
+      Wheel<T>& w = wh[s];
+      const T yi = (h * wk.damp * w.a - wk.J * (w.ax * yi_sh[3] + w.ay * yi_sh[4])) * C.w_cEinv[wi];
+      w.warm = w.a;
+      w.dsp += h * (w.a - yi);
+      w.sp += h * w.dsp;
+    }
+    T ai[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ai[i] = a_sh[i] - yi_sh[i];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       e.warm_l[i] = k.R[3 * i] * a_sh[0] + k.R[3 * i + 1] * a_sh[1] + k.R[3 * i + 2] * a_sh[2];
       e.warm_a[i] = a_sh[3 + i];
+      e.vw[i] += h * (k.R[3 * i] * ai[0] + k.R[3 * i + 1] * ai[1] + k.R[3 * i + 2] * ai[2]);
+      e.om[i] += h * ai[3 + i];
     }
     e.warm_st[0] = a_sh[6]; e.warm_st[1] = a_sh[7];
 #pragma unroll
-    for (int s = 0; s < WPL; ++s) e.warm_sp[s] = a_sp[s];
-
-    // B16: velocities advance with the implicitly damped acceleration x, then positions with the new velocities
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      e.vw[i] += h * (k.R[3 * i] * x_sh[0] + k.R[3 * i + 1] * x_sh[1] + k.R[3 * i + 2] * x_sh[2]);
-      e.om[i] += h * x_sh[3 + i];
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) { e.dst[i] += h * x_sh[6 + i]; e.st[i] += h * e.dst[i]; }
-#pragma unroll
-    for (int s = 0; s < WPL; ++s) { e.dsp[s] += h * x_sp[s]; e.sp[s] += h * e.dsp[s]; }
+    for (int i = 0; i < 2; ++i) { e.dst[i] += h * ai[6 + i]; e.st[i] += h * e.dst[i]; }
 #pragma unroll
     for (int i = 0; i < 3; ++i) e.p[i] += h * e.vw[i];
     {

@@ -36,25 +36,27 @@ struct EnvOps {
 
   // A is any accessor with T qpos(int i), T qvel(int i), T warm(int i) and the matching setters
   template <class A>
-  ACKB_HD static void load_state(const A& a, int lane, State& e) {
+  ACKB_HD static void load_state(const A& a, int lane, State& e, Wheel<T>* wh) {
     for (int i = 0; i < 3; ++i) { e.p[i] = a.qpos(i); e.vw[i] = a.qvel(i); e.om[i] = a.qvel(3 + i); e.warm_l[i] = a.warm(i); e.warm_a[i] = a.warm(3 + i); }
     for (int i = 0; i < 4; ++i) e.q[i] = a.qpos(3 + i);
     for (int i = 0; i < 2; ++i) { e.st[i] = a.qpos(hinge_qadr(i)); e.dst[i] = a.qvel(hinge_dadr(i)); e.warm_st[i] = a.warm(hinge_dadr(i)); }
+#pragma unroll 1
     for (int s = 0; s < WPL; ++s) {
       int h = 2 + lane * WPL + s;
-      e.sp[s] = a.qpos(hinge_qadr(h)); e.dsp[s] = a.qvel(hinge_dadr(h)); e.warm_sp[s] = a.warm(hinge_dadr(h));
+      wh[s].sp = a.qpos(hinge_qadr(h)); wh[s].dsp = a.qvel(hinge_dadr(h)); wh[s].warm = a.warm(hinge_dadr(h));
     }
   }
   template <class A>
-  ACKB_HD static void store_state(A& a, int lane, const State& e) {
+  ACKB_HD static void store_state(A& a, int lane, const State& e, const Wheel<T>* wh) {
     if (lane == 0) {
       for (int i = 0; i < 3; ++i) { a.set_qpos(i, e.p[i]); a.set_qvel(i, e.vw[i]); a.set_qvel(3 + i, e.om[i]); a.set_warm(i, e.warm_l[i]); a.set_warm(3 + i, e.warm_a[i]); }
       for (int i = 0; i < 4; ++i) a.set_qpos(3 + i, e.q[i]);
       for (int i = 0; i < 2; ++i) { a.set_qpos(hinge_qadr(i), e.st[i]); a.set_qvel(hinge_dadr(i), e.dst[i]); a.set_warm(hinge_dadr(i), e.warm_st[i]); }
     }
+#pragma unroll 1
     for (int s = 0; s < WPL; ++s) {
       int h = 2 + lane * WPL + s;
-      a.set_qpos(hinge_qadr(h), e.sp[s]); a.set_qvel(hinge_dadr(h), e.dsp[s]); a.set_warm(hinge_dadr(h), e.warm_sp[s]);
+      a.set_qpos(hinge_qadr(h), wh[s].sp); a.set_qvel(hinge_dadr(h), wh[s].dsp); a.set_warm(hinge_dadr(h), wh[s].warm);
     }
   }
 
@@ -107,7 +109,7 @@ struct EnvOps {
 
   // reset (ackermann_env.py:143-172 + simple_map_spawner.py:37-52): spawn pose, zero velocity and warm start,
   // odometry reference := chassis position, goal at U(dmin, dmax) metres in a U(0, 2pi) direction.
-  ACKB_HD static void reset_env(const Consts<T>& C, State& e, Episode<T>& ep, int lane, uint64_t seed, uint32_t env_id) {
+  ACKB_HD static void reset_env(const Consts<T>& C, State& e, Wheel<T>* wh, Episode<T>& ep, int lane, uint64_t seed, uint32_t env_id) {
     uint32_t r[4];
     philox4x32(ep.episode, env_id, 0u, 0x41434B42u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
     for (int i = 0; i < 3; ++i) { e.p[i] = C.spawn_qpos[i]; e.vw[i] = e.om[i] = e.warm_l[i] = e.warm_a[i] = T(0); }
@@ -123,7 +125,8 @@ struct EnvOps {
       e.q[0] = cz * q0 - sz * q3; e.q[1] = cz * q1 - sz * q2; e.q[2] = cz * q2 + sz * q1; e.q[3] = cz * q3 + sz * q0;
     }
     for (int i = 0; i < 2; ++i) { e.st[i] = C.spawn_qpos[hinge_qadr(i)]; e.dst[i] = e.warm_st[i] = T(0); }
-    for (int s = 0; s < WPL; ++s) { e.sp[s] = C.spawn_qpos[hinge_qadr(2 + lane * WPL + s)]; e.dsp[s] = e.warm_sp[s] = T(0); }
+#pragma unroll 1
+    for (int s = 0; s < WPL; ++s) { wh[s].sp = C.spawn_qpos[hinge_qadr(2 + lane * WPL + s)]; wh[s].dsp = wh[s].warm = T(0); }
     ep.ref[0] = e.p[0]; ep.ref[1] = e.p[1];
     ep.step_count = 0;
     const T d = C.goal_dmin[0] + (C.goal_dmax[0] - C.goal_dmin[0]) * (T)u01(r[0]);
@@ -133,10 +136,12 @@ struct EnvOps {
     ep.episode += 1;
   }
 
-  // one env.step(): frame_skip x mj_step, observation from the kinematics of the last substep (quirk Q3)
-  template <class Sink>
-  ACKB_HD static void step_env(const Consts<T>& C, State& e, Episode<T>& ep, float a0, float a1, int frame_skip, int lane, Sink& sink,
-                               StepOut<T>& out, StepDiag& diag, DebugTap<T>* tap) {
+  // one env.step(): frame_skip x mj_step, observation from the kinematics of the last substep (quirk Q3).
+  // `emit` is called right after the observation has been written into the sink (before the last substep's dynamics),
+  // so that the sink's storage may alias the wheel records.
+  template <class Sink, class Emit>
+  ACKB_HD static void step_env(const Consts<T>& C, State& e, Wheel<T>* wh, Episode<T>& ep, float a0, float a1, int frame_skip, int lane,
+                               Sink& sink, Emit&& emit, StepOut<T>& out, StepDiag& diag, DebugTap<T>* tap) {
     T ctrl[4];
     action_to_ctrl<T>(C, a0, a1, ctrl);
     T dist = T(0), minl = T(0);
@@ -144,9 +149,23 @@ struct EnvOps {
       Tm::block_sync();
       Kin<T> k;
       S::kinematics(e, k);
-      if (s == frame_skip - 1) observe(C, e, k, ep, lane, sink, &dist, &minl);
+      if (s == frame_skip - 1) {
+        // the sink's storage may alias the wheel records (1 lane per environment): park the live spin state in registers
+        T keep[Sink::kAliasesWheels ? 3 * WPL : 1];
+        if (Sink::kAliasesWheels) {
+#pragma unroll
+          for (int i = 0; i < WPL; ++i) { keep[3 * i] = wh[i].sp; keep[3 * i + 1] = wh[i].dsp; keep[3 * i + 2] = wh[i].warm; }
+          Tm::warp_sync();
+        }
+        observe(C, e, k, ep, lane, sink, &dist, &minl);
+        emit();
+        if (Sink::kAliasesWheels) {
+#pragma unroll
+          for (int i = 0; i < WPL; ++i) { wh[i].sp = keep[3 * i]; wh[i].dsp = keep[3 * i + 1]; wh[i].warm = keep[3 * i + 2]; }
+        }
+      }
       diag.ncon = 0;
-      S::dynamics(C, e, k, ctrl, lane, diag, tap);
+      S::dynamics(C, e, k, ctrl, lane, wh, diag, tap);
     }
     reward_done(C, ep, dist, minl, out);
   }

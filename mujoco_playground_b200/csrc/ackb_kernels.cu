@@ -61,11 +61,14 @@ struct SoAAcc {
   __device__ __forceinline__ void set_qvel(int i, T v) { s.qvel[(size_t)i * s.n + env] = v; }
   __device__ __forceinline__ void set_warm(int i, T v) { s.warm[(size_t)i * s.n + env] = v; }
 };
+template <bool ALIAS>
 struct RowSink {
+  static constexpr bool kAliasesWheels = ALIAS;
   float* row;
   __device__ __forceinline__ void put(int slot, float v) { row[slot] = v; }
 };
 struct PredRowSink {
+  static constexpr bool kAliasesWheels = false;
   float* row;
   bool on;
   __device__ __forceinline__ void put(int slot, float v) { if (on) row[slot] = v; }
@@ -77,13 +80,24 @@ __device__ __forceinline__ unsigned warp_sum_u32(unsigned v) {
   return v;
 }
 
-#ifndef ACKB_BLOCK
-#define ACKB_BLOCK 128
-#endif
-constexpr int kBlock = ACKB_BLOCK;
-#ifndef ACKB_MIN_BLOCKS
-#define ACKB_MIN_BLOCKS 2
-#endif
+// Per-(T, LANES) launch geometry.  With fewer than 4 lanes per environment the wheel records of a thread live in
+// shared memory with an odd per-thread stride (conflict free) and the per-warp observation tile aliases that region
+// (the tile is flushed to HBM before the dynamics of the last substep reuse it).
+template <typename T, int LANES>
+struct Geo {
+  static constexpr int WPL = 4 / LANES;
+  static constexpr bool kSmemWheels = WPL > 1;
+  static constexpr int kWheelUnits = sizeof(Wheel<T>) / sizeof(T);          // record size in units of T
+  static constexpr int kStride = WPL * kWheelUnits + ((WPL * kWheelUnits) % 2 == 0 ? 1 : 0);   // odd
+  static constexpr int kBlock = kSmemWheels ? (sizeof(T) == 4 ? 128 : 64) : 128;
+  static constexpr int kMinBlocks = kSmemWheels ? 2 : 2;
+  static size_t smem_bytes(int obs_dim) {
+    const size_t tile = (size_t)(kBlock / LANES) * obs_dim * sizeof(float);
+    const size_t wheels = kSmemWheels ? (size_t)kBlock * kStride * sizeof(T) : 0;
+    return tile > wheels ? tile : wheels;
+  }
+};
+static_assert(sizeof(Wheel<float>) % sizeof(float) == 0 && sizeof(Wheel<double>) % sizeof(double) == 0, "Wheel must be a whole number of T");
 
 // synthetic action of (step, env): Philox(seed) with counter (step, env, 2, tag) -> U(-1, 1)^2
 __device__ __forceinline__ void synth_action(unsigned long long seed, uint32_t step, uint32_t env, float* a0, float* a1) {
@@ -93,23 +107,38 @@ __device__ __forceinline__ void synth_action(unsigned long long seed, uint32_t s
   *a1 = 2.0f * u01(r[1]) - 1.0f;
 }
 
+// wheel records of this thread: registers (4 lanes per env) or the thread's slice of shared memory
 template <typename T, int LANES>
-__global__ void __launch_bounds__(kBlock, ACKB_MIN_BLOCKS) step_kernel(DevState<T> st, StepArgs a) {
+struct WheelStore {
+  Wheel<T> reg[Geo<T, LANES>::kSmemWheels ? 1 : Geo<T, LANES>::WPL];
+  __device__ __forceinline__ Wheel<T>* get(unsigned char* smem) {
+    if constexpr (Geo<T, LANES>::kSmemWheels) return reinterpret_cast<Wheel<T>*>(reinterpret_cast<T*>(smem) + (size_t)threadIdx.x * Geo<T, LANES>::kStride);
+    else return reg;
+  }
+};
+
+template <typename T, int LANES>
+__global__ void __launch_bounds__(Geo<T, LANES>::kBlock, Geo<T, LANES>::kMinBlocks) step_kernel(DevState<T> st, StepArgs a) {
   using E = EnvOps<T, LANES>;
+  using G = Geo<T, LANES>;
   constexpr int EPW = 32 / LANES;
-  extern __shared__ float tile[];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const Consts<T>& C = dev_consts<T>();
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int env_raw = tid / LANES, lane = tid % LANES;
   const bool valid = env_raw < st.n;
   const int env = valid ? env_raw : st.n - 1;
   const int warp = threadIdx.x >> 5, lid = threadIdx.x & 31;
-  float* wtile = tile + (size_t)warp * EPW * a.obs_dim;
-  RowSink sink{wtile + (lid / LANES) * a.obs_dim};
+  // per-warp observation tile: its own region (4 lanes) or aliasing the warp's wheel records
+  float* wtile = G::kSmemWheels ? reinterpret_cast<float*>(reinterpret_cast<T*>(smem_raw) + (size_t)warp * 32 * G::kStride)
+                                : reinterpret_cast<float*>(smem_raw) + (size_t)warp * EPW * a.obs_dim;
+  RowSink<G::kSmemWheels> sink{wtile + (lid / LANES) * a.obs_dim};
+  WheelStore<T, LANES> store;
+  Wheel<T>* wh = store.get(smem_raw);
 
   typename E::State e;
   SoAAcc<T> acc{st, env};
-  E::load_state(acc, lane, e);
+  E::load_state(acc, lane, e, wh);
   Episode<T> ep;
   ep.goal[0] = st.goal[env]; ep.goal[1] = st.goal[(size_t)st.n + env];
   ep.ref[0] = st.ref[env]; ep.ref[1] = st.ref[(size_t)st.n + env];
@@ -119,9 +148,22 @@ __global__ void __launch_bounds__(kBlock, ACKB_MIN_BLOCKS) step_kernel(DevState<
   if (a.action) { float2 v = reinterpret_cast<const float2*>(a.action)[env]; a0 = v.x; a1 = v.y; }
   else synth_action(a.seed, a.step_index, (uint32_t)env, &a0, &a1);
 
+  const int env0 = (blockIdx.x * blockDim.x + warp * 32) / LANES;
+  int nrow = st.n - env0;
+  nrow = nrow < 0 ? 0 : (nrow > EPW ? EPW : nrow);
+  // coalesced store of the warp's observation tile (the warp's environments are consecutive rows), issued as soon as
+  // the observation exists so that the tile storage can be reused by the last substep
+  auto emit = [&]() {
+    __syncwarp();
+    const int total = nrow * a.obs_dim;
+    float* dst = a.obs + (size_t)env0 * a.obs_dim;
+    for (int i = lid; i < total; i += 32) dst[i] = wtile[i];
+    __syncwarp();
+  };
+
   StepOut<T> out;
   StepDiag diag{0, 0, 0};
-  E::step_env(C, e, ep, a0, a1, a.frame_skip, lane, sink, out, diag, (DebugTap<T>*)nullptr);
+  E::step_env(C, e, wh, ep, a0, a1, a.frame_skip, lane, sink, emit, out, diag, (DebugTap<T>*)nullptr);
   __syncwarp();
 
   // contact count of the last substep, summed over the lanes of the environment
@@ -132,22 +174,6 @@ __global__ void __launch_bounds__(kBlock, ACKB_MIN_BLOCKS) step_kernel(DevState<
   const bool done = out.terminated || out.truncated;
   float ret = st.ep_return[env] + out.reward;
   const int ep_len = ep.step_count;
-  const bool do_reset = done && a.auto_reset;
-  if (__any_sync(0xffffffffu, do_reset)) {   // warp-uniform: the team collectives inside need the whole warp
-    if (do_reset && a.terminal_obs && valid)
-      for (int j = lane; j < a.obs_dim; j += LANES) a.terminal_obs[(size_t)env * a.obs_dim + j] = sink.row[j];
-    __syncwarp();
-    typename E::State e2 = e;
-    Episode<T> ep2 = ep;
-    E::reset_env(C, e2, ep2, lane, a.seed, (uint32_t)env);
-    Kin<T> k;
-    E::S::kinematics(e2, k);
-    T dist, minl;
-    PredRowSink psink{sink.row, do_reset};
-    E::observe(C, e2, k, ep2, lane, psink, &dist, &minl);
-    if (do_reset) { e = e2; ep = ep2; }
-  }
-  __syncwarp();
 
   // statistics: one atomic per warp and counter
   if (a.stats) {
@@ -167,23 +193,39 @@ __global__ void __launch_bounds__(kBlock, ACKB_MIN_BLOCKS) step_kernel(DevState<
     }
   }
 
-  // coalesced store of the warp's observation tile (the warp's environments are consecutive rows)
-  {
-    const int env0 = (blockIdx.x * blockDim.x + warp * 32) / LANES;
-    int nrow = st.n - env0;
-    nrow = nrow < 0 ? 0 : (nrow > EPW ? EPW : nrow);
-    const int total = nrow * a.obs_dim;
-    float* dst = a.obs + (size_t)env0 * a.obs_dim;
-    for (int i = lid; i < total; i += 32) dst[i] = wtile[i];
+  const bool do_reset = done && a.auto_reset;
+  if (__any_sync(0xffffffffu, do_reset)) {   // warp-uniform: the team collectives inside need the whole warp
+    if (do_reset && valid) {
+      if (a.terminal_obs)   // the finished episode's last observation was flushed to dev_obs by emit()
+        for (int j = lane; j < a.obs_dim; j += LANES) a.terminal_obs[(size_t)env * a.obs_dim + j] = a.obs[(size_t)env * a.obs_dim + j];
+    }
+    __syncwarp();
+    if (do_reset) E::reset_env(C, e, wh, ep, lane, a.seed, (uint32_t)env);
+    Kin<T> k;
+    E::S::kinematics(e, k);
+    T dist, minl;
+    PredRowSink psink{sink.row, do_reset};
+    // the wheel records in shared memory are about to be overwritten by the tile: keep the spin state in registers
+    T keep[3 * G::WPL];
+    if (G::kSmemWheels) for (int s = 0; s < G::WPL; ++s) { keep[3 * s] = wh[s].sp; keep[3 * s + 1] = wh[s].dsp; keep[3 * s + 2] = wh[s].warm; }
+    __syncwarp();
+    E::observe(C, e, k, ep, lane, psink, &dist, &minl);
+    __syncwarp();
+    if (do_reset && valid)
+      for (int j = lane; j < a.obs_dim; j += LANES) a.obs[(size_t)env * a.obs_dim + j] = sink.row[j];
+    __syncwarp();
+    if (G::kSmemWheels) for (int s = 0; s < G::WPL; ++s) { wh[s].sp = keep[3 * s]; wh[s].dsp = keep[3 * s + 1]; wh[s].warm = keep[3 * s + 2]; }
   }
+  __syncwarp();
+
   if (valid) {
-    E::store_state(acc, lane, e);
+    E::store_state(acc, lane, e, wh);
     if (lane == 0) {
       st.goal[env] = ep.goal[0]; st.goal[(size_t)st.n + env] = ep.goal[1];
       st.ref[env] = ep.ref[0]; st.ref[(size_t)st.n + env] = ep.ref[1];
       st.step_count[env] = ep.step_count;
       st.episode[env] = ep.episode;
-      st.ep_return[env] = (done && a.auto_reset) ? 0.f : ret;
+      st.ep_return[env] = do_reset ? 0.f : ret;
       a.reward[env] = out.reward;
       a.terminated[env] = out.terminated;
       a.truncated[env] = out.truncated;
@@ -193,22 +235,24 @@ __global__ void __launch_bounds__(kBlock, ACKB_MIN_BLOCKS) step_kernel(DevState<
 }
 
 template <typename T, int LANES>
-__global__ void __launch_bounds__(kBlock) reset_kernel(DevState<T> st, StepArgs a) {
+__global__ void __launch_bounds__(Geo<T, LANES>::kBlock) reset_kernel(DevState<T> st, StepArgs a) {
   using E = EnvOps<T, LANES>;
-  constexpr int EPW = 32 / LANES;
-  extern __shared__ float tile[];
+  using G = Geo<T, LANES>;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   const Consts<T>& C = dev_consts<T>();
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int env_raw = tid / LANES, lane = tid % LANES;
   const bool valid = env_raw < st.n;
   const int env = valid ? env_raw : st.n - 1;
-  const int warp = threadIdx.x >> 5, lid = threadIdx.x & 31;
-  RowSink sink{tile + ((size_t)warp * EPW + lid / LANES) * a.obs_dim};
   const bool sel = (a.mask ? (a.mask[env] != 0) : true) && valid;   // team-uniform
+  // the reset kernel keeps wheel records in local storage and uses shared memory for the observation rows only
+  Wheel<T> wh[G::WPL];
+  float* row = reinterpret_cast<float*>(smem_raw) + (size_t)(threadIdx.x / LANES) * a.obs_dim;
+  RowSink<false> sink{row};
   typename E::State e;
   Episode<T> ep;
   ep.episode = st.episode[env];
-  E::reset_env(C, e, ep, lane, a.seed, (uint32_t)env);
+  E::reset_env(C, e, wh, ep, lane, a.seed, (uint32_t)env);
   Kin<T> k;
   E::S::kinematics(e, k);
   T dist, minl;
@@ -217,7 +261,7 @@ __global__ void __launch_bounds__(kBlock) reset_kernel(DevState<T> st, StepArgs 
   if (!sel) return;
   for (int j = lane; j < a.obs_dim; j += LANES) a.obs[(size_t)env * a.obs_dim + j] = sink.row[j];
   SoAAcc<T> acc{st, env};
-  E::store_state(acc, lane, e);
+  E::store_state(acc, lane, e, wh);
   if (lane == 0) {
     st.goal[env] = ep.goal[0]; st.goal[(size_t)st.n + env] = ep.goal[1];
     st.ref[env] = ep.ref[0]; st.ref[(size_t)st.n + env] = ep.ref[1];
@@ -306,22 +350,31 @@ int ensure_consts(ackb_handle* h, cudaStream_t stream) {
   return ACKB_OK;
 }
 
-template <typename T>
-int launch_step(ackb_handle* h, DevState<T>& st, const StepArgs& a, cudaStream_t stream, bool is_reset) {
-  const int lanes = h->lanes;
-  const long long threads = (long long)h->n * lanes;
-  const int grid = (int)((threads + kBlock - 1) / kBlock);
-  const size_t smem = (size_t)(kBlock / lanes) * a.obs_dim * sizeof(float);
-#define LAUNCH(L)                                                                \
-  if (is_reset) reset_kernel<T, L><<<grid, kBlock, smem, stream>>>(st, a);        \
-  else step_kernel<T, L><<<grid, kBlock, smem, stream>>>(st, a);
-  if (lanes == 4) { LAUNCH(4) }
-  else if (lanes == 2) { LAUNCH(2) }
-  else { LAUNCH(1) }
-#undef LAUNCH
+template <typename T, int LANES>
+int launch_one(ackb_handle* h, DevState<T>& st, const StepArgs& a, cudaStream_t stream, bool is_reset) {
+  using G = Geo<T, LANES>;
+  const long long threads = (long long)h->n * LANES;
+  const int grid = (int)((threads + G::kBlock - 1) / G::kBlock);
+  if (is_reset) {
+    const size_t smem = (size_t)(G::kBlock / LANES) * a.obs_dim * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done && smem > 48 * 1024) { CK(cudaFuncSetAttribute(reset_kernel<T, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done = true; }
+    reset_kernel<T, LANES><<<grid, G::kBlock, smem, stream>>>(st, a);
+  } else {
+    const size_t smem = G::smem_bytes(a.obs_dim);
+    static bool attr_done = false;
+    if (!attr_done && smem > 48 * 1024) { CK(cudaFuncSetAttribute(step_kernel<T, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done = true; }
+    step_kernel<T, LANES><<<grid, G::kBlock, smem, stream>>>(st, a);
+  }
   h->launches++;
   CK(cudaGetLastError());
   return ACKB_OK;
+}
+
+template <typename T>
+int launch_step(ackb_handle* h, DevState<T>& st, const StepArgs& a, cudaStream_t stream, bool is_reset) {
+  if (h->lanes == 4) return launch_one<T, 4>(h, st, a, stream, is_reset);
+  return launch_one<T, 1>(h, st, a, stream, is_reset);
 }
 }  // namespace
 
@@ -337,8 +390,8 @@ int ackb_create(const double* consts, size_t consts_len, int num_envs, int devic
   if (!consts || !out || num_envs <= 0) return fail(nullptr, ACKB_ERR_ARG, "ackb_create: null pointer or num_envs <= 0");
   if ((int)consts_len != kNumConsts) return fail(nullptr, ACKB_ERR_ARG, "ackb_create: constants blob has the wrong length");
   if (dtype != ACKB_F32 && dtype != ACKB_F64) return fail(nullptr, ACKB_ERR_ARG, "ackb_create: dtype must be ACKB_F32 or ACKB_F64");
-  if (lanes_per_env == 0) lanes_per_env = 4;
-  if (lanes_per_env != 1 && lanes_per_env != 2 && lanes_per_env != 4) return fail(nullptr, ACKB_ERR_ARG, "ackb_create: lanes_per_env must be 1, 2 or 4");
+  if (lanes_per_env == 0) lanes_per_env = num_envs >= 32768 ? 1 : 4;   // throughput layout for big batches, latency layout otherwise
+  if (lanes_per_env != 1 && lanes_per_env != 4) return fail(nullptr, ACKB_ERR_ARG, "ackb_create: lanes_per_env must be 1 or 4");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, ACKB_ERR_NO_DEVICE, "ackb_create: no CUDA device (there is no CPU fallback)");
   if (device < 0 || device >= ndev || device >= 64) return fail(nullptr, ACKB_ERR_ARG, "ackb_create: bad device index");

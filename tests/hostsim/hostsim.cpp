@@ -18,6 +18,7 @@ struct ArrAcc {
   void set_warm(int i, T v) { wm[i] = (double)v; }
 };
 struct ObsSink {
+  static constexpr bool kAliasesWheels = false;
   float* o;
   void put(int slot, float v) { o[slot] = v; }
 };
@@ -33,8 +34,9 @@ void substep(const double* blob, double* qpos, double* qvel, double* warm, const
   Consts<T> C;
   to_consts(blob, C);
   typename E::State e;
+  Wheel<T> wh[4];
   ArrAcc<T> acc{qpos, qvel, warm};
-  E::load_state(acc, 0, e);
+  E::load_state(acc, 0, e, wh);
   T ctrl[4];
   for (int i = 0; i < 4; ++i) ctrl[i] = (T)ctrl_in[i];
   StepDiag diag{0, 0, 0};
@@ -43,9 +45,9 @@ void substep(const double* blob, double* qpos, double* qvel, double* warm, const
     Kin<T> k;
     E::S::kinematics(e, k);
     diag.ncon = 0;
-    E::S::dynamics(C, e, k, ctrl, 0, diag, &tap);
+    E::S::dynamics(C, e, k, ctrl, 0, wh, diag, &tap);
   }
-  E::store_state(acc, 0, e);
+  E::store_state(acc, 0, e, wh);
   if (tap_out) {
     for (int i = 0; i < 12; ++i) { tap_out[i] = tap.tau[i]; tap_out[12 + i] = tap.a_smooth[i]; tap_out[24 + i] = tap.a[i]; tap_out[36 + i] = tap.fc[i]; }
     tap_out[48] = tap.niter; tap_out[49] = tap.nls;
@@ -60,16 +62,17 @@ void env_step(const double* blob, double* qpos, double* qvel, double* warm, doub
   Consts<T> C;
   to_consts(blob, C);
   typename E::State e;
+  Wheel<T> wh[4];
   ArrAcc<T> acc{qpos, qvel, warm};
-  E::load_state(acc, 0, e);
+  E::load_state(acc, 0, e, wh);
   Episode<T> ep;
   ep.goal[0] = (T)epd[0]; ep.goal[1] = (T)epd[1]; ep.ref[0] = (T)epd[2]; ep.ref[1] = (T)epd[3];
   ep.step_count = epi[0]; ep.episode = (uint32_t)epi[1];
   ObsSink sink{obs};
   StepOut<T> so;
   StepDiag diag{0, 0, 0};
-  E::step_env(C, e, ep, action[0], action[1], frame_skip, 0, sink, so, diag, (DebugTap<T>*)nullptr);
-  E::store_state(acc, 0, e);
+  E::step_env(C, e, wh, ep, action[0], action[1], frame_skip, 0, sink, [] {}, so, diag, (DebugTap<T>*)nullptr);
+  E::store_state(acc, 0, e, wh);
   epi[0] = ep.step_count;
   out[0] = so.reward; out[1] = so.terminated; out[2] = so.truncated; out[3] = so.collision; out[4] = so.goal_distance; out[5] = so.min_lidar;
   if (diag_out) { diag_out[0] = diag.ncon; diag_out[1] = diag.unsupported; diag_out[2] = diag.niter; }
@@ -81,16 +84,17 @@ void env_reset(const double* blob, double* qpos, double* qvel, double* warm, dou
   Consts<T> C;
   to_consts(blob, C);
   typename E::State e;
+  Wheel<T> wh[4];
   Episode<T> ep;
   ep.episode = (uint32_t)epi[1];
-  E::reset_env(C, e, ep, 0, seed, env_id);
+  E::reset_env(C, e, wh, ep, 0, seed, env_id);
   Kin<T> k;
   E::S::kinematics(e, k);
   ObsSink sink{obs};
   T dist, minl;
   E::observe(C, e, k, ep, 0, sink, &dist, &minl);
   ArrAcc<T> acc{qpos, qvel, warm};
-  E::store_state(acc, 0, e);
+  E::store_state(acc, 0, e, wh);
   epd[0] = (double)ep.goal[0]; epd[1] = (double)ep.goal[1]; epd[2] = (double)ep.ref[0]; epd[3] = (double)ep.ref[1];
   epi[0] = ep.step_count; epi[1] = (int)ep.episode;
 }
@@ -116,12 +120,12 @@ void hs_env_reset(int f32, const double* blob, double* qpos, double* qvel, doubl
 void hs_observe(int f32, const double* blob, double* qpos, double* qvel, double* warm, const double* epd, float* obs, double* out) {
   if (f32) {
     using E = EnvOps<float, 1>; Consts<float> C; to_consts(blob, C);
-    E::State e; ArrAcc<float> acc{qpos, qvel, warm}; E::load_state(acc, 0, e);
+    E::State e; Wheel<float> wh[4]; ArrAcc<float> acc{qpos, qvel, warm}; E::load_state(acc, 0, e, wh);
     Episode<float> ep; ep.goal[0] = epd[0]; ep.goal[1] = epd[1]; ep.ref[0] = epd[2]; ep.ref[1] = epd[3]; ep.step_count = 0; ep.episode = 0;
     Kin<float> k; E::S::kinematics(e, k); ObsSink sink{obs}; float d, m; E::observe(C, e, k, ep, 0, sink, &d, &m); out[0] = d; out[1] = m;
   } else {
     using E = EnvOps<double, 1>; Consts<double> C; to_consts(blob, C);
-    E::State e; ArrAcc<double> acc{qpos, qvel, warm}; E::load_state(acc, 0, e);
+    E::State e; Wheel<double> wh[4]; ArrAcc<double> acc{qpos, qvel, warm}; E::load_state(acc, 0, e, wh);
     Episode<double> ep; ep.goal[0] = epd[0]; ep.goal[1] = epd[1]; ep.ref[0] = epd[2]; ep.ref[1] = epd[3]; ep.step_count = 0; ep.episode = 0;
     Kin<double> k; E::S::kinematics(e, k); ObsSink sink{obs}; double d, m; E::observe(C, e, k, ep, 0, sink, &d, &m); out[0] = d; out[1] = m;
   }

@@ -110,7 +110,7 @@ def test_lane_layouts_agree():
     res = []
     rng = np.random.default_rng(2)
     acts = rng.uniform(-1, 1, (40, 33, 2)).astype(np.float32)
-    for lanes in (1, 2, 4):
+    for lanes in (1, 4):
         env = BatchedAckermannEnv(33, dtype="float64", seed=9, lanes_per_env=lanes, auto_reset=False, frame_skip=2)
         env.reset()
         for t in range(40):
