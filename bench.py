@@ -55,7 +55,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.05)
 
     def summary(self):
         self.stop_flag.set()
@@ -171,12 +171,12 @@ def run_cuda(args, rank, local_rank, world):
         torch.cuda.synchronize(dev)
 
     # ---- kernel-resident throughput: synthetic actions generated in the kernel, state resident in HBM --------------
-    for _ in range(args.warmup):
-        env.step(None)
-    barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
+    for _ in range(args.warmup):
+        env.step(None)
+    barrier()
     launches0 = env.launch_count
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
@@ -239,6 +239,27 @@ def run_cuda(args, rank, local_rank, world):
                        "episodes": stats["episodes"], "unsupported_contact_steps": stats["unsupported"]},
             "wall_s_timed_region": t_wall,
         }
+        if world == 1 and not args.envs and not args.no_aux:
+            # the same kernel at the per-GPU batch of configs[3] (131072 envs), for context next to the 4096-env headline
+            env.close()
+            big = BatchedAckermannEnv(131072, device=dev, frame_skip=fs, dtype=args.dtype, seed=99, auto_reset=True, lanes_per_env=args.lanes)
+            big.reset()
+            big.set_episode(step_count=np.random.default_rng(7).integers(0, 1000, 131072).astype(np.int32))
+            for _ in range((400 + fs - 1) // fs):
+                big.step(None)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            nb = 30
+            torch.cuda.synchronize(dev)
+            e0.record()
+            for _ in range(nb):
+                big.step(None)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / nb
+            line["aux"] = {"workload": f"131072 envs on 1 B200, frame_skip={fs}, back-to-back launches (state 85 MB < L2)",
+                           "value": 131072 / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms,
+                           "roofline_frac": algo * 131072 / (ms * 1e-3) / 1e9 / peak}
+            big.close()
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             per = max(50, args.cpu_steps // fs)
@@ -255,14 +276,15 @@ def run_cuda(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--envs", type=int, default=0, help="override environments per GPU")
     ap.add_argument("--frame-skip", type=int, default=4)
     ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
-    ap.add_argument("--lanes", type=int, default=4)
-    ap.add_argument("--cpu-steps", type=int, default=200000, help="physics substeps per CPU process for the CPU arm sample")
+    ap.add_argument("--lanes", type=int, default=0, help="lanes per env: 0 = auto (1 for >= 32768 envs, else 4)")
+    ap.add_argument("--no-aux", action="store_true", help="skip the extra large-batch measurement at N=1")
+    ap.add_argument("--cpu-steps", type=int, default=800000, help="physics substeps per CPU process for the CPU arm sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
