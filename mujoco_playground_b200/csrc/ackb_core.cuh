@@ -300,7 +300,31 @@ struct Contact {
   T zv[3];    // image F Jp x of the current step direction
 };
 
+// Contact frames.  Slots 0,1 of a wheel are floor contacts (frame of the floor normal +z).  Slots 2,3 (obstacle scene)
+// are wheel-vs-box contacts whose frame is one of the world-axis-aligned frames below, selected by a face code; the
+// contact normal points from the wheel (geom1) to the box (geom2), so the rows act on the wheel with a minus sign,
+// which is folded into the frame (all three rows negated).
+//   code 0: floor (+z)   1: normal +x   2: normal -x   3: normal +y   4: normal -y   5: normal -z (box top)
 template <typename T>
+ACKB_HD void contact_frame(const Kin<T>& k, int code, T* n, T* t1, T* t2) {
+  // rows of R are the world axes expressed in the body frame
+  const T* Rx = k.R; const T* Ry = k.R + 3; const T* Rz = k.R + 6;
+  T sn = T(1), s2 = T(1);
+  const T *pn = Rz, *p1 = Ry, *p2 = Rx;
+  switch (code) {
+    case 0: sn = T(1); pn = Rz; p1 = Ry; p2 = Rx; s2 = T(-1); break;                    // (+z, +y, -x)
+    case 1: pn = Rx; p1 = Ry; p2 = Rz; sn = T(-1); s2 = T(-1); break;                    // -( +x, +y, +z)
+    case 2: pn = Rx; p1 = Ry; p2 = Rz; sn = T(1); s2 = T(1); break;                      // -( -x, +y, -z)
+    case 3: pn = Ry; p1 = Rz; p2 = Rx; sn = T(-1); s2 = T(-1); break;                    // -( +y, +z, +x)
+    case 4: pn = Ry; p1 = Rz; p2 = Rx; sn = T(1); s2 = T(1); break;                      // -( -y, +z, -x)
+    default: pn = Rz; p1 = Ry; p2 = Rx; sn = T(1); s2 = T(-1); break;                    // -( -z, +y, +x)
+  }
+  const T s1 = (code == 0) ? T(1) : T(-1);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { n[i] = sn * pn[i]; t1[i] = s1 * p1[i]; t2[i] = s2 * p2[i]; }
+}
+
+template <typename T, int NC>
 struct Wheel {
   T sp, dsp, warm;   // state: spin angle, rate, warm-start acceleration
   T ax, ay;          // spin axis (ax, ay, 0) in the body frame
@@ -308,7 +332,8 @@ struct Wheel {
   T g, cw;           // gradient entry and Schur pivot of the spin dof at the last assembly
   T b[7];            // coupling of the spin dof with (lin3, ang3, own steer)
   unsigned zone0;    // activity pattern of the wheel's rows at the last assembly
-  Contact<T> con[2];
+  unsigned fcode;    // frame codes of the box contact slots (4 bits each, slots 2 and 3)
+  Contact<T> con[NC];
 };
 
 // wheel constants by wheel index wi (RL, RR, FL, FR)
@@ -333,8 +358,8 @@ ACKB_HD WheelK<T> wheel_consts(const Consts<T>& C, int wi) {
 }
 
 // spin column u = axis x r and steer column w = ez x r of the point Jacobian (r = X - centre)
-template <typename T>
-ACKB_HD void contact_cols(const Wheel<T>& w, const WheelK<T>& wk, const T* X, T* u, T* wv) {
+template <typename T, int NC>
+ACKB_HD void contact_cols(const Wheel<T, NC>& w, const WheelK<T>& wk, const T* X, T* u, T* wv) {
   const T r0 = X[0] - wk.c[0], r1 = X[1] - wk.c[1], r2 = X[2] - wk.c[2];
   u[0] = w.ay * r2; u[1] = -w.ax * r2; u[2] = w.ax * r1 - w.ay * r0;   // (ax, ay, 0) x r
   const T st = wk.isL + wk.isR;
@@ -343,13 +368,14 @@ ACKB_HD void contact_cols(const Wheel<T>& w, const WheelK<T>& wk, const T* X, T*
 
 // point "acceleration" y = a_lin + a_ang x X + a_spin u + a_steer w, projected on the contact frame (n, t1, t2)
 template <typename T>
-ACKB_HD void project_point(const Kin<T>& k, const T* X, const T* u, const T* wv, const T* alin, const T* aang, T aspin, T asteer, T* out) {
+ACKB_HD void project_point(const T* fn, const T* ft1, const T* ft2, const T* X, const T* u, const T* wv, const T* alin, const T* aang, T aspin,
+                           T asteer, T* out) {
   T y[3];
   cross3(y, aang, X);
   y[0] += alin[0] + aspin * u[0] + asteer * wv[0];
   y[1] += alin[1] + aspin * u[1] + asteer * wv[1];
   y[2] += alin[2] + aspin * u[2];
-  out[0] = dot3(k.n, y); out[1] = dot3(k.t1, y); out[2] = dot3(k.t2, y);
+  out[0] = dot3(fn, y); out[1] = dot3(ft1, y); out[2] = dot3(ft2, y);
 }
 
 // forces of the four pyramid rows of a contact at residual z (3-vector in the contact frame);
@@ -494,14 +520,15 @@ struct DebugTap {
 // ------------------------------------------------------------------------------------------------
 // the simulator
 // ------------------------------------------------------------------------------------------------
-template <typename T, int LANES>
+template <typename T, int LANES, int NC>
 struct Sim {
   static constexpr int WPL = 4 / LANES;
+  using WheelT = Wheel<T, NC>;
   using Tm = Team<LANES>;
   using N = Num<T>;
   using State = EnvState<T>;
   // contact loops are unrolled when the wheel record lives in registers (WPL == 1) and rolled when it is in shared memory
-  static constexpr int CU = (WPL == 1) ? 2 : 1;
+  static constexpr int CU = (WPL == 1) ? NC : 1;
 
   // ---- B1 kinematics: normalise the quaternion (written back, like mj_kinematics), rotation, floor frame
   ACKB_HD static void kinematics(State& e, Kin<T>& k) {
@@ -518,7 +545,7 @@ struct Sim {
 
   // ---- B6/B7 floor contacts of one wheel (plane vs cylinder, in the body frame) and their row parameters
   ACKB_HD static void collide_wheel(const Consts<T>& C, const State& e, const Kin<T>& k, const T* vb, int wi, const WheelK<T>& wk,
-                                    Wheel<T>& w, StepDiag& diag) {
+                                    WheelT& w, StepDiag& diag) {
     const T s = wk.isL * e.st[0] + wk.isR * e.st[1];
     T sn, cs;
     N::sincos_small(s, &sn, &cs);
@@ -559,12 +586,82 @@ struct Sim {
       con.D = active ? T(1) / (T(2) * C.w_mureg2[wi] * R0) : T(0);
       T u[3], wv[2], vel[3];
       contact_cols(w, wk, con.x, u, wv);
-      project_point(k, con.x, u, wv, vb, e.om, w.dsp, dsteer, vel);
+      project_point(k.n, k.t1, k.t2, con.x, u, wv, vb, e.om, w.dsp, dsteer, vel);
       // residual at a = 0 is minus the reference acceleration
       con.z[0] = C.w_B[wi] * vel[0] + C.w_K[wi] * imp * dd;
       con.z[1] = C.w_B[wi] * vel[1];
       con.z[2] = C.w_B[wi] * vel[2];
     }
+  }
+
+  // ---- wheel vs static axis-aligned boxes (obstacle scene).  MuJoCo sends cylinder-box pairs to its general convex
+  // collider (one contact along the minimum-penetration direction); here that contact is computed in closed form over the
+  // box's face normals with the cylinder's support point (see oracle cylinder_box, DESIGN.md for the deviation).
+  // Up to two box contacts per wheel are kept (slots 2, 3); more are flagged as unsupported.
+  ACKB_HD static void collide_boxes(const Consts<T>& C, const State& e, const Kin<T>& k, const T* vb, int wi, const WheelK<T>& wk,
+                                    WheelT& w, StepDiag& diag) {
+    const T r = C.w_radius[wi], hl = C.w_halflen[wi];
+    // wheel centre and axis in the world frame
+    T cw[3], aw[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      cw[i] = e.p[i] + k.R[3 * i] * wk.c[0] + k.R[3 * i + 1] * wk.c[1] + k.R[3 * i + 2] * wk.c[2];
+      aw[i] = k.R[3 * i] * w.ax + k.R[3 * i + 1] * w.ay;
+    }
+    const T dsteer = wk.isL * e.dst[0] + wk.isR * e.dst[1];
+    const T reach = N::sqrt_(r * r + hl * hl);
+    const int nbox = (int)C.nbox[0];
+    int nfound = 0;
+    unsigned fcode = 0u;
+    if (NC > 2) { w.con[NC - 2].D = T(0); w.con[NC - 1].D = T(0); for (int i = 0; i < 3; ++i) { w.con[NC - 2].x[i] = w.con[NC - 1].x[i] = T(0); w.con[NC - 2].z[i] = w.con[NC - 1].z[i] = T(0); } }
+#pragma unroll 1
+    for (int bi = 0; bi < nbox; ++bi) {
+      const T c[3] = {cw[0] - C.box_cx[bi], cw[1] - C.box_cy[bi], cw[2] - C.box_z[0]};
+      if (N::abs_(c[0]) > C.box_half[0] + reach || N::abs_(c[1]) > C.box_half[1] + reach || N::abs_(c[2]) > C.box_half[2] + reach) continue;
+      T best = T(-1e30), bp[3] = {T(0), T(0), T(0)};
+      int bk = 0, bs = 1;
+#pragma unroll
+      for (int kk = 0; kk < 3; ++kk)
+#pragma unroll
+        for (int sgn = -1; sgn <= 1; sgn += 2) {
+          const T an = aw[kk] * T(sgn);
+          T wv3[3] = {an * aw[0], an * aw[1], an * aw[2]};
+          wv3[kk] -= T(sgn);
+          const T wl = N::sqrt_(dot3(wv3, wv3));
+          const T tcl = mjclip(-an * T(50), T(-1), T(1));     // smooth axial support: full rim corner beyond ~1.1 deg of tilt
+          const T sc = wl > T(1e-12) ? r / wl : T(0);
+          T pp[3];
+#pragma unroll
+          for (int i = 0; i < 3; ++i) pp[i] = c[i] + tcl * hl * aw[i] + sc * wv3[i];
+          const T sep = T(sgn) * pp[kk] - C.box_half[kk];
+          if (sep > best) { best = sep; bk = kk; bs = sgn; bp[0] = pp[0]; bp[1] = pp[1]; bp[2] = pp[2]; }
+        }
+      if (best > T(0)) continue;
+      diag.ncon += 1;
+      if (nfound >= 2) { diag.unsupported = 1; continue; }
+      // contact point midway between the surfaces, world -> body frame
+      T pw[3] = {bp[0] + C.box_cx[bi] - e.p[0], bp[1] + C.box_cy[bi] - e.p[1], bp[2] + C.box_z[0] - e.p[2]};
+      pw[bk] -= T(bs) * best * T(0.5);
+      Contact<T>& con = w.con[NC > 2 ? 2 + nfound : 0];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) con.x[i] = k.R[i] * pw[0] + k.R[3 + i] * pw[1] + k.R[6 + i] * pw[2];
+      // normal from the wheel to the box is -s e_k:  +x 1, -x 2, +y 3, -y 4, -z 5 (+z: wheel below a box, never happens)
+      const int code = (bk == 0) ? (bs < 0 ? 1 : 2) : ((bk == 1) ? (bs < 0 ? 3 : 4) : 5);
+      fcode |= (unsigned)code << (4 * nfound);
+      const T mu = wk.mu;
+      const T imp = impedance(&C.w_solimp[5 * wi], best);
+      const T R0 = mjmax(N::minval, (T(1) - imp) / imp * C.w_tran[wi] * (T(1) + mu * mu));
+      con.D = (best < T(0)) ? T(1) / (T(2) * C.w_mureg2[wi] * R0) : T(0);
+      T u[3], wv[2], vel[3], fn[3], ft1[3], ft2[3];
+      contact_cols(w, wk, con.x, u, wv);
+      contact_frame(k, code, fn, ft1, ft2);
+      project_point(fn, ft1, ft2, con.x, u, wv, vb, e.om, w.dsp, dsteer, vel);
+      con.z[0] = C.w_B[wi] * vel[0] + C.w_K[wi] * imp * best;
+      con.z[1] = C.w_B[wi] * vel[1];
+      con.z[2] = C.w_B[wi] * vel[2];
+      ++nfound;
+    }
+    w.fcode = fcode;
   }
 
   ACKB_HD static void make_shared_rows(const Consts<T>& C, const State& e, SharedRows<T>& s) {
@@ -655,7 +752,7 @@ struct Sim {
   // LDL^T-factorises its 8 x 8 Schur complement and solves it.  The iteration starts at a = 0 with a unit step along
   // the warm start (previous qacc), as MuJoCo does when its cost beats qacc_smooth; the minimiser is unique, so the
   // starting point only affects the iteration count (qacc_smooth is never needed).
-  ACKB_HD static void dynamics(const Consts<T>& C, State& e, const Kin<T>& k, const T* ctrl, int lane, Wheel<T>* wh, StepDiag& diag,
+  ACKB_HD static void dynamics(const Consts<T>& C, State& e, const Kin<T>& k, const T* ctrl, int lane, WheelT* wh, StepDiag& diag,
                                DebugTap<T>* tap) {
     const T h = C.timestep[0];
     T vb[3];
@@ -671,8 +768,9 @@ struct Sim {
     for (int s = 0; s < WPL; ++s) {
       const int wi = lane * WPL + s;
       const WheelK<T> wk = wheel_consts(C, wi);
-      Wheel<T>& w = wh[s];
+      WheelT& w = wh[s];
       collide_wheel(C, e, k, vb, wi, wk, w, diag);
+      if (NC > 2) collide_boxes(C, e, k, vb, wi, wk, w, diag);
       const T dsteer = wk.isL * e.dst[0] + wk.isR * e.dst[1];
       const T aw[3] = {w.ax, w.ay, T(0)};
       const T ez[3] = {T(0), T(0), T(1)};
@@ -693,6 +791,7 @@ struct Sim {
       w.a = T(0);
       w.x = w.warm;
       w.zone0 = 0u;
+      if (NC <= 2) w.fcode = 0u;
       warm_ok = warm_ok && (N::abs_(w.warm) <= T(1e10));
     }
     Tm::sum_n(bpart);
@@ -770,18 +869,19 @@ struct Sim {
         for (int s = 0; s < WPL; ++s) {
           const int wi = lane * WPL + s;
           const WheelK<T> wk = wheel_consts(C, wi);
-          Wheel<T>& w = wh[s];
+          WheelT& w = wh[s];
           const T aw_aang_x = w.ax * x_sh[3] + w.ay * x_sh[4], aw_aang_a = w.ax * a_sh[3] + w.ay * a_sh[4];
           const T Mv_sp = wk.J * aw_aang_x + wk.cdiag * w.x, Ma_sp = wk.J * aw_aang_a + wk.cdiag * w.a;
           acc[0] += wk.J * w.ax * w.x; acc[1] += wk.J * w.ay * w.x;
           acc[3] += w.x * Mv_sp; acc[4] += w.x * (Ma_sp - w.tau);
           const T ast = wk.isL * x_sh[6] + wk.isR * x_sh[7];
 #pragma unroll(CU)
-          for (int c = 0; c < 2; ++c) {
+          for (int c = 0; c < NC; ++c) {
             Contact<T>& con = w.con[c];
-            T u[3], wv[2];
+            T u[3], wv[2], fn[3], ft1[3], ft2[3];
             contact_cols(w, wk, con.x, u, wv);
-            project_point(k, con.x, u, wv, x_sh, x_sh + 3, w.x, ast, con.zv);
+            contact_frame(k, c < 2 ? 0 : (int)((w.fcode >> (4 * (c - 2))) & 15u), fn, ft1, ft2);
+            project_point(fn, ft1, ft2, con.x, u, wv, x_sh, x_sh + 3, w.x, ast, con.zv);
           }
         }
         Tm::sum_n(acc);
@@ -800,14 +900,14 @@ struct Sim {
           for (int s = 0; s < WPL; ++s) {
             const int wi = lane * WPL + s;
             const WheelK<T> wk = wheel_consts(C, wi);
-            const Wheel<T>& w = wh[s];
+            const WheelT& w = wh[s];
             T f, q;
             floss_row(w.a + alpha * w.x + wk.flB * w.dsp, wk.flf, wk.flR, &f, &q);
             d[0] -= f * w.x;
             d[1] += q / wk.flR * w.x * w.x;
             unsigned zone = (q != T(0)) ? 1u : (f > T(0) ? 0u : 2u);
 #pragma unroll(CU)
-            for (int c = 0; c < 2; ++c) {
+            for (int c = 0; c < NC; ++c) {
               const Contact<T>& con = w.con[c];
               const T* z0 = con.z; const T* z1 = con.zv;
               const T mu = wk.mu;
@@ -851,10 +951,10 @@ struct Sim {
           for (int i = 0; i < 8; ++i) { a_sh[i] += alpha * x_sh[i]; Ma_sh[i] += alpha * Mv_sh[i]; }
 #pragma unroll 1
           for (int s = 0; s < WPL; ++s) {
-            Wheel<T>& w = wh[s];
+            WheelT& w = wh[s];
             w.a += alpha * w.x;
 #pragma unroll(CU)
-            for (int c = 0; c < 2; ++c)
+            for (int c = 0; c < NC; ++c)
 #pragma unroll
               for (int i = 0; i < 3; ++i) w.con[c].z[i] += alpha * w.con[c].zv[i];
           }
@@ -874,7 +974,7 @@ struct Sim {
       for (int s = 0; s < WPL; ++s) {
         const int wi = lane * WPL + s;
         const WheelK<T> wk = wheel_consts(C, wi);
-        Wheel<T>& w = wh[s];
+        WheelT& w = wh[s];
         T f, q;
         floss_row(w.a + wk.flB * w.dsp, wk.flf, wk.flR, &f, &q);
         unsigned zone = (q != T(0)) ? 1u : (f > T(0) ? 0u : 2u);
@@ -888,9 +988,10 @@ struct Sim {
         T gl[3] = {T(0), T(0), T(0)}, ga[3] = {T(0), T(0), T(0)}, gst = T(0);
         const T mu = wk.mu;
 #pragma unroll(CU)
-        for (int c = 0; c < 2; ++c) {
+        for (int c = 0; c < NC; ++c) {
           const Contact<T>& con = w.con[c];
-          T phi[3], qq[4];
+          T phi[3], qq[4], fn[3], ft1[3], ft2[3];
+          contact_frame(k, c < 2 ? 0 : (int)((w.fcode >> (4 * (c - 2))) & 15u), fn, ft1, ft2);
           pyramid_rows(con.D, mu, con.z, phi, qq);
           if (con.D > T(0)) zone = (zone << 4) | (qq[0] != T(0) ? 1u : 0u) | (qq[1] != T(0) ? 2u : 0u) | (qq[2] != T(0) ? 4u : 0u) | (qq[3] != T(0) ? 8u : 0u);
           else zone <<= 4;
@@ -900,15 +1001,15 @@ struct Sim {
           T r0[3], r1[3], r2[3];
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
-            r0[i] = con.D * (W00 * k.n[i] + W01 * k.t1[i] + W02 * k.t2[i]);
-            r1[i] = con.D * (W01 * k.n[i] + W11 * k.t1[i]);
-            r2[i] = con.D * (W02 * k.n[i] + W22 * k.t2[i]);
+            r0[i] = con.D * (W00 * fn[i] + W01 * ft1[i] + W02 * ft2[i]);
+            r1[i] = con.D * (W01 * fn[i] + W11 * ft1[i]);
+            r2[i] = con.D * (W02 * fn[i] + W22 * ft2[i]);
           }
           T S3[3][3];
 #pragma unroll
           for (int i = 0; i < 3; ++i)
 #pragma unroll
-            for (int j = 0; j <= i; ++j) { S3[i][j] = k.n[i] * r0[j] + k.t1[i] * r1[j] + k.t2[i] * r2[j]; S3[j][i] = S3[i][j]; }
+            for (int j = 0; j <= i; ++j) { S3[i][j] = fn[i] * r0[j] + ft1[i] * r1[j] + ft2[i] * r2[j]; S3[j][i] = S3[i][j]; }
           const T X[3] = {con.x[0], con.x[1], con.x[2]};
           T u[3], wv[2];
           contact_cols(w, wk, X, u, wv);
@@ -945,7 +1046,7 @@ struct Sim {
           // body-frame contact force and its generalised image (enters the gradient with a minus sign)
           T Phi[3], XF[3];
 #pragma unroll
-          for (int i = 0; i < 3; ++i) Phi[i] = k.n[i] * phi[0] + k.t1[i] * phi[1] + k.t2[i] * phi[2];
+          for (int i = 0; i < 3; ++i) Phi[i] = fn[i] * phi[0] + ft1[i] * phi[1] + ft2[i] * phi[2];
           cross3(XF, X, Phi);
 #pragma unroll
           for (int i = 0; i < 3; ++i) { gl[i] -= Phi[i]; ga[i] -= XF[i]; }
@@ -1008,7 +1109,7 @@ struct Sim {
 #pragma unroll 1
         for (int s = 0; s < WPL; ++s) {
           const int wi = lane * WPL + s;
-          Wheel<T>& w = wh[s];
+          WheelT& w = wh[s];
           T dotb = T(0);
 #pragma unroll
           for (int a = 0; a < 6; ++a) dotb += w.b[a] * y_sh[a];
@@ -1034,7 +1135,7 @@ struct Sim {
       for (int s = 0; s < WPL; ++s) {
         const int wi = lane * WPL + s;
         const WheelK<T> wk = wheel_consts(C, wi);
-        const Wheel<T>& w = wh[s];
+        const WheelT& w = wh[s];
         const T coef = wk.J * (h * wk.damp * w.a) * C.w_cEinv[wi];
         part3[0] -= coef * w.ax; part3[1] -= coef * w.ay;
       }
@@ -1084,7 +1185,7 @@ struct Sim {
     for (int s = 0; s < WPL; ++s) {
       const int wi = lane * WPL + s;
       const WheelK<T> wk = wheel_consts(C, wi);
-      Wheel<T>& w = wh[s];
+      WheelT& w = wh[s];
       const T yi = (h * wk.damp * w.a - wk.J * (w.ax * yi_sh[3] + w.ay * yi_sh[4])) * C.w_cEinv[wi];
       w.warm = w.a;
       w.dsp += h * (w.a - yi);

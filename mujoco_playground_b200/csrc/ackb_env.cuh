@@ -22,9 +22,10 @@ struct StepOut {
   float goal_distance, min_lidar;
 };
 
-template <typename T, int LANES>
+template <typename T, int LANES, int NC>
 struct EnvOps {
-  using S = Sim<T, LANES>;
+  using S = Sim<T, LANES, NC>;
+  using WheelT = Wheel<T, NC>;
   using N = Num<T>;
   using Tm = Team<LANES>;
   static constexpr int WPL = S::WPL;
@@ -36,7 +37,7 @@ struct EnvOps {
 
   // A is any accessor with T qpos(int i), T qvel(int i), T warm(int i) and the matching setters
   template <class A>
-  ACKB_HD static void load_state(const A& a, int lane, State& e, Wheel<T>* wh) {
+  ACKB_HD static void load_state(const A& a, int lane, State& e, WheelT* wh) {
     for (int i = 0; i < 3; ++i) { e.p[i] = a.qpos(i); e.vw[i] = a.qvel(i); e.om[i] = a.qvel(3 + i); e.warm_l[i] = a.warm(i); e.warm_a[i] = a.warm(3 + i); }
     for (int i = 0; i < 4; ++i) e.q[i] = a.qpos(3 + i);
     for (int i = 0; i < 2; ++i) { e.st[i] = a.qpos(hinge_qadr(i)); e.dst[i] = a.qvel(hinge_dadr(i)); e.warm_st[i] = a.warm(hinge_dadr(i)); }
@@ -47,7 +48,7 @@ struct EnvOps {
     }
   }
   template <class A>
-  ACKB_HD static void store_state(A& a, int lane, const State& e, const Wheel<T>* wh) {
+  ACKB_HD static void store_state(A& a, int lane, const State& e, const WheelT* wh) {
     if (lane == 0) {
       for (int i = 0; i < 3; ++i) { a.set_qpos(i, e.p[i]); a.set_qvel(i, e.vw[i]); a.set_qvel(3 + i, e.om[i]); a.set_warm(i, e.warm_l[i]); a.set_warm(3 + i, e.warm_a[i]); }
       for (int i = 0; i < 4; ++i) a.set_qpos(3 + i, e.q[i]);
@@ -109,7 +110,7 @@ struct EnvOps {
 
   // reset (ackermann_env.py:143-172 + simple_map_spawner.py:37-52): spawn pose, zero velocity and warm start,
   // odometry reference := chassis position, goal at U(dmin, dmax) metres in a U(0, 2pi) direction.
-  ACKB_HD static void reset_env(const Consts<T>& C, State& e, Wheel<T>* wh, Episode<T>& ep, int lane, uint64_t seed, uint32_t env_id) {
+  ACKB_HD static void reset_env(const Consts<T>& C, State& e, WheelT* wh, Episode<T>& ep, int lane, uint64_t seed, uint32_t env_id) {
     uint32_t r[4];
     philox4x32(ep.episode, env_id, 0u, 0x41434B42u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
     for (int i = 0; i < 3; ++i) { e.p[i] = C.spawn_qpos[i]; e.vw[i] = e.om[i] = e.warm_l[i] = e.warm_a[i] = T(0); }
@@ -140,7 +141,7 @@ struct EnvOps {
   // `emit` is called right after the observation has been written into the sink (before the last substep's dynamics),
   // so that the sink's storage may alias the wheel records.
   template <class Sink, class Emit>
-  ACKB_HD static void step_env(const Consts<T>& C, State& e, Wheel<T>* wh, Episode<T>& ep, float a0, float a1, int frame_skip, int lane,
+  ACKB_HD static void step_env(const Consts<T>& C, State& e, WheelT* wh, Episode<T>& ep, float a0, float a1, int frame_skip, int lane,
                                Sink& sink, Emit&& emit, StepOut<T>& out, StepDiag& diag, DebugTap<T>* tap) {
     T ctrl[4];
     action_to_ctrl<T>(C, a0, a1, ctrl);

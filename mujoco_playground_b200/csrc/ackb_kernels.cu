@@ -83,11 +83,11 @@ __device__ __forceinline__ unsigned warp_sum_u32(unsigned v) {
 // Per-(T, LANES) launch geometry.  With fewer than 4 lanes per environment the wheel records of a thread live in
 // shared memory with an odd per-thread stride (conflict free) and the per-warp observation tile aliases that region
 // (the tile is flushed to HBM before the dynamics of the last substep reuse it).
-template <typename T, int LANES>
+template <typename T, int LANES, int NC>
 struct Geo {
   static constexpr int WPL = 4 / LANES;
   static constexpr bool kSmemWheels = WPL > 1;
-  static constexpr int kWheelUnits = sizeof(Wheel<T>) / sizeof(T);          // record size in units of T
+  static constexpr int kWheelUnits = sizeof(Wheel<T, NC>) / sizeof(T);          // record size in units of T
   static constexpr int kStride = WPL * kWheelUnits + ((WPL * kWheelUnits) % 2 == 0 ? 1 : 0);   // odd
   static constexpr int kBlock = kSmemWheels ? (sizeof(T) == 4 ? 128 : 64) : 128;
   static constexpr int kMinBlocks = kSmemWheels ? 2 : 2;
@@ -97,7 +97,7 @@ struct Geo {
     return tile > wheels ? tile : wheels;
   }
 };
-static_assert(sizeof(Wheel<float>) % sizeof(float) == 0 && sizeof(Wheel<double>) % sizeof(double) == 0, "Wheel must be a whole number of T");
+static_assert(sizeof(Wheel<float, 2>) % sizeof(float) == 0 && sizeof(Wheel<double, 2>) % sizeof(double) == 0 && sizeof(Wheel<double, 4>) % sizeof(double) == 0, "Wheel must be a whole number of T");
 
 // synthetic action of (step, env): Philox(seed) with counter (step, env, 2, tag) -> U(-1, 1)^2
 __device__ __forceinline__ void synth_action(unsigned long long seed, uint32_t step, uint32_t env, float* a0, float* a1) {
@@ -108,19 +108,19 @@ __device__ __forceinline__ void synth_action(unsigned long long seed, uint32_t s
 }
 
 // wheel records of this thread: registers (4 lanes per env) or the thread's slice of shared memory
-template <typename T, int LANES>
+template <typename T, int LANES, int NC>
 struct WheelStore {
-  Wheel<T> reg[Geo<T, LANES>::kSmemWheels ? 1 : Geo<T, LANES>::WPL];
-  __device__ __forceinline__ Wheel<T>* get(unsigned char* smem) {
-    if constexpr (Geo<T, LANES>::kSmemWheels) return reinterpret_cast<Wheel<T>*>(reinterpret_cast<T*>(smem) + (size_t)threadIdx.x * Geo<T, LANES>::kStride);
+  Wheel<T, NC> reg[Geo<T, LANES, NC>::kSmemWheels ? 1 : Geo<T, LANES, NC>::WPL];
+  __device__ __forceinline__ Wheel<T, NC>* get(unsigned char* smem) {
+    if constexpr (Geo<T, LANES, NC>::kSmemWheels) return reinterpret_cast<Wheel<T, NC>*>(reinterpret_cast<T*>(smem) + (size_t)threadIdx.x * Geo<T, LANES, NC>::kStride);
     else return reg;
   }
 };
 
-template <typename T, int LANES>
-__global__ void __launch_bounds__(Geo<T, LANES>::kBlock, Geo<T, LANES>::kMinBlocks) step_kernel(DevState<T> st, StepArgs a) {
-  using E = EnvOps<T, LANES>;
-  using G = Geo<T, LANES>;
+template <typename T, int LANES, int NC>
+__global__ void __launch_bounds__(Geo<T, LANES, NC>::kBlock, Geo<T, LANES, NC>::kMinBlocks) step_kernel(DevState<T> st, StepArgs a) {
+  using E = EnvOps<T, LANES, NC>;
+  using G = Geo<T, LANES, NC>;
   constexpr int EPW = 32 / LANES;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Consts<T>& C = dev_consts<T>();
@@ -133,8 +133,8 @@ __global__ void __launch_bounds__(Geo<T, LANES>::kBlock, Geo<T, LANES>::kMinBloc
   float* wtile = G::kSmemWheels ? reinterpret_cast<float*>(reinterpret_cast<T*>(smem_raw) + (size_t)warp * 32 * G::kStride)
                                 : reinterpret_cast<float*>(smem_raw) + (size_t)warp * EPW * a.obs_dim;
   RowSink<G::kSmemWheels> sink{wtile + (lid / LANES) * a.obs_dim};
-  WheelStore<T, LANES> store;
-  Wheel<T>* wh = store.get(smem_raw);
+  WheelStore<T, LANES, NC> store;
+  Wheel<T, NC>* wh = store.get(smem_raw);
 
   typename E::State e;
   SoAAcc<T> acc{st, env};
@@ -235,9 +235,9 @@ __global__ void __launch_bounds__(Geo<T, LANES>::kBlock, Geo<T, LANES>::kMinBloc
 }
 
 template <typename T, int LANES>
-__global__ void __launch_bounds__(Geo<T, LANES>::kBlock) reset_kernel(DevState<T> st, StepArgs a) {
-  using E = EnvOps<T, LANES>;
-  using G = Geo<T, LANES>;
+__global__ void __launch_bounds__(Geo<T, LANES, 2>::kBlock) reset_kernel(DevState<T> st, StepArgs a) {
+  using E = EnvOps<T, LANES, 2>;
+  using G = Geo<T, LANES, 2>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Consts<T>& C = dev_consts<T>();
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(Geo<T, LANES>::kBlock) reset_kernel(DevState<T
   const int env = valid ? env_raw : st.n - 1;
   const bool sel = (a.mask ? (a.mask[env] != 0) : true) && valid;   // team-uniform
   // the reset kernel keeps wheel records in local storage and uses shared memory for the observation rows only
-  Wheel<T> wh[G::WPL];
+  Wheel<T, 2> wh[G::WPL];
   float* row = reinterpret_cast<float*>(smem_raw) + (size_t)(threadIdx.x / LANES) * a.obs_dim;
   RowSink<false> sink{row};
   typename E::State e;
@@ -350,21 +350,19 @@ int ensure_consts(ackb_handle* h, cudaStream_t stream) {
   return ACKB_OK;
 }
 
-template <typename T, int LANES>
+template <typename T, int LANES, int NC>
 int launch_one(ackb_handle* h, DevState<T>& st, const StepArgs& a, cudaStream_t stream, bool is_reset) {
-  using G = Geo<T, LANES>;
+  using G = Geo<T, LANES, NC>;
   const long long threads = (long long)h->n * LANES;
   const int grid = (int)((threads + G::kBlock - 1) / G::kBlock);
   if (is_reset) {
     const size_t smem = (size_t)(G::kBlock / LANES) * a.obs_dim * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done && smem > 48 * 1024) { CK(cudaFuncSetAttribute(reset_kernel<T, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done = true; }
-    reset_kernel<T, LANES><<<grid, G::kBlock, smem, stream>>>(st, a);
+    reset_kernel<T, LANES><<<grid, Geo<T, LANES, 2>::kBlock, smem, stream>>>(st, a);
   } else {
     const size_t smem = G::smem_bytes(a.obs_dim);
     static bool attr_done = false;
-    if (!attr_done && smem > 48 * 1024) { CK(cudaFuncSetAttribute(step_kernel<T, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done = true; }
-    step_kernel<T, LANES><<<grid, G::kBlock, smem, stream>>>(st, a);
+    if (!attr_done && smem > 48 * 1024) { CK(cudaFuncSetAttribute(step_kernel<T, LANES, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done = true; }
+    step_kernel<T, LANES, NC><<<grid, G::kBlock, smem, stream>>>(st, a);
   }
   h->launches++;
   CK(cudaGetLastError());
@@ -373,8 +371,9 @@ int launch_one(ackb_handle* h, DevState<T>& st, const StepArgs& a, cudaStream_t 
 
 template <typename T>
 int launch_step(ackb_handle* h, DevState<T>& st, const StepArgs& a, cudaStream_t stream, bool is_reset) {
-  if (h->lanes == 4) return launch_one<T, 4>(h, st, a, stream, is_reset);
-  return launch_one<T, 1>(h, st, a, stream, is_reset);
+  const bool scene = h->consts_host[0] != 0.0;   // model_kind: the obstacle scene needs the two box-contact slots per wheel
+  if (h->lanes == 4) return scene ? launch_one<T, 4, 4>(h, st, a, stream, is_reset) : launch_one<T, 4, 2>(h, st, a, stream, is_reset);
+  return scene ? launch_one<T, 1, 4>(h, st, a, stream, is_reset) : launch_one<T, 1, 2>(h, st, a, stream, is_reset);
 }
 }  // namespace
 

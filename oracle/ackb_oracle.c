@@ -453,46 +453,42 @@ static int plane_cylinder(const double* pos1, const double* mat1, const double* 
   return cnt;
 }
 
-/* Cylinder (g1) vs static axis-aligned-in-its-own-frame box (g2): analytic single contact.
-   MuJoCo sends this pair to its general convex collider (one contact along the minimum
-   penetration direction); here that minimum-translation contact is computed in closed form over
-   the box's face normals using the cylinder's support point.  Normal points from cylinder to box. */
+/* Cylinder (g1) vs box (g2): analytic single contact.
+   MuJoCo sends this pair to its general convex collider (one contact along the minimum-penetration direction).  Here that
+   contact is computed in closed form: over the six face normals n of the box, take the cylinder's support point in
+   direction -n (axial part blended over ~1 degree of tilt so that a rim parallel to the face contacts at its centre);
+   the face with the largest separation is the contact face; contact if that separation <= margin.  Edge/corner axes are
+   not tested (documented deviation).  Normal points from the cylinder to the box; pos is midway between the surfaces. */
 static int cylinder_box(const double* cpos, const double* cmat, const double* csize, const double* bpos,
                         const double* bmat, const double* bsize, double margin, double* dist_out, double* pos_out,
                         double* normal_out) {
-  /* work in box frame */
   double rel[3], c[3], a[3];
   for (int k = 0; k < 3; k++) rel[k] = cpos[k] - bpos[k];
   mulmatTvec3(c, bmat, rel);
   double axw[3] = {cmat[2], cmat[5], cmat[8]};
   mulmatTvec3(a, bmat, axw);
+  /* the spin axis direction sign is irrelevant for the support function */
   double r = csize[0], h = csize[1];
-  double best = -1e300; int bestk = -1, bests = 0; double bestp[3] = {0, 0, 0};
+  double best = -1e300; int bestk = 0, bests = 1; double bestp[3] = {0, 0, 0};
   for (int k = 0; k < 3; k++)
     for (int s = -1; s <= 1; s += 2) {
-      /* face with outward normal n = s*e_k; cylinder support point in direction -n */
-      double n[3] = {0, 0, 0};
-      n[k] = s;
-      double an = dot3(a, n);
-      double perp[3] = {-n[0] + an * a[0], -n[1] + an * a[1], -n[2] + an * a[2]}; /* -n minus its axis part */
-      double pl = norm3(perp);
-      double sp[3];
-      double sgn = (-an >= 0) ? 1.0 : -1.0;
-      for (int q = 0; q < 3; q++) sp[q] = c[q] + sgn * h * a[q] + (pl > 1e-12 ? perp[q] * (r / pl) : 0.0);
-      double sep = dot3(sp, n) - bsize[k]; /* >0: separated along this face normal */
-      if (sep > best) { best = sep; bestk = k; bests = s; memcpy(bestp, sp, sizeof sp); }
+      double an = a[k] * s;
+      double w[3] = {an * a[0], an * a[1], an * a[2]};
+      w[k] -= s;
+      double wl = norm3(w);
+      double tcl = -an * 50.0;
+      tcl = tcl < -1 ? -1 : (tcl > 1 ? 1 : tcl);
+      double sc = wl > 1e-12 ? r / wl : 0.0;
+      double p[3];
+      for (int q = 0; q < 3; q++) p[q] = c[q] + tcl * h * a[q] + sc * w[q];
+      double sep = s * p[k] - bsize[k];
+      if (sep > best) { best = sep; bestk = k; bests = s; memcpy(bestp, p, sizeof p); }
     }
   if (best > margin) return 0;
-  /* the support point must project inside the face (otherwise an edge/corner case: reject unless inside slab) */
-  for (int k = 0; k < 3; k++)
-    if (k != bestk && fabs(bestp[k]) > bsize[k] + 1e-12) {
-      /* clamp: treat as contact against the extended face only if the cylinder centre projects onto the face */
-      if (fabs(c[k]) > bsize[k] + r) return 0;
-    }
-  double n[3] = {0, 0, 0};
-  n[bestk] = -bests; /* from cylinder into box */
-  double pmid[3];
-  for (int k = 0; k < 3; k++) pmid[k] = bestp[k] - n[k] * best * 0.5; /* midway between surfaces */
+  double n[3] = {0, 0, 0}, pmid[3];
+  n[bestk] = -bests; /* from the cylinder into the box */
+  memcpy(pmid, bestp, sizeof pmid);
+  pmid[bestk] -= bests * best * 0.5;
   double pw[3], nw[3];
   mulmatvec3(pw, bmat, pmid);
   mulmatvec3(nw, bmat, n);

@@ -28,13 +28,13 @@ void to_consts(const double* blob, Consts<T>& C) {
   for (int i = 0; i < kNumConsts; ++i) dst[i] = (T)blob[i];
 }
 
-template <typename T>
+template <typename T, int NC>
 void substep(const double* blob, double* qpos, double* qvel, double* warm, const double* ctrl_in, int nsteps, double* tap_out, int* diag_out) {
-  using E = EnvOps<T, 1>;
+  using E = EnvOps<T, 1, NC>;
   Consts<T> C;
   to_consts(blob, C);
   typename E::State e;
-  Wheel<T> wh[4];
+  Wheel<T, NC> wh[4];
   ArrAcc<T> acc{qpos, qvel, warm};
   E::load_state(acc, 0, e, wh);
   T ctrl[4];
@@ -55,14 +55,14 @@ void substep(const double* blob, double* qpos, double* qvel, double* warm, const
   if (diag_out) { diag_out[0] = diag.ncon; diag_out[1] = diag.unsupported; diag_out[2] = diag.niter; }
 }
 
-template <typename T>
+template <typename T, int NC>
 void env_step(const double* blob, double* qpos, double* qvel, double* warm, double* epd /*goal2 ref2*/, int* epi /*step_count episode*/,
               const float* action, int frame_skip, float* obs, float* out, int* diag_out) {
-  using E = EnvOps<T, 1>;
+  using E = EnvOps<T, 1, NC>;
   Consts<T> C;
   to_consts(blob, C);
   typename E::State e;
-  Wheel<T> wh[4];
+  Wheel<T, NC> wh[4];
   ArrAcc<T> acc{qpos, qvel, warm};
   E::load_state(acc, 0, e, wh);
   Episode<T> ep;
@@ -78,13 +78,13 @@ void env_step(const double* blob, double* qpos, double* qvel, double* warm, doub
   if (diag_out) { diag_out[0] = diag.ncon; diag_out[1] = diag.unsupported; diag_out[2] = diag.niter; }
 }
 
-template <typename T>
+template <typename T, int NC>
 void env_reset(const double* blob, double* qpos, double* qvel, double* warm, double* epd, int* epi, unsigned long long seed, unsigned env_id, float* obs) {
-  using E = EnvOps<T, 1>;
+  using E = EnvOps<T, 1, NC>;
   Consts<T> C;
   to_consts(blob, C);
   typename E::State e;
-  Wheel<T> wh[4];
+  Wheel<T, NC> wh[4];
   Episode<T> ep;
   ep.episode = (uint32_t)epi[1];
   E::reset_env(C, e, wh, ep, 0, seed, env_id);
@@ -103,29 +103,31 @@ void env_reset(const double* blob, double* qpos, double* qvel, double* warm, dou
 extern "C" {
 int hs_nconsts() { return kNumConsts; }
 void hs_substep(int f32, const double* blob, double* qpos, double* qvel, double* warm, const double* ctrl, int nsteps, double* tap, int* diag) {
-  if (f32) substep<float>(blob, qpos, qvel, warm, ctrl, nsteps, tap, diag);
-  else substep<double>(blob, qpos, qvel, warm, ctrl, nsteps, tap, diag);
+  const bool scene = blob[0] != 0.0;   // model_kind: the obstacle scene has two extra box-contact slots per wheel
+  if (f32) { if (scene) substep<float, 4>(blob, qpos, qvel, warm, ctrl, nsteps, tap, diag); else substep<float, 2>(blob, qpos, qvel, warm, ctrl, nsteps, tap, diag); }
+  else { if (scene) substep<double, 4>(blob, qpos, qvel, warm, ctrl, nsteps, tap, diag); else substep<double, 2>(blob, qpos, qvel, warm, ctrl, nsteps, tap, diag); }
 }
 void hs_env_step(int f32, const double* blob, double* qpos, double* qvel, double* warm, double* epd, int* epi, const float* action,
                  int frame_skip, float* obs, float* out, int* diag) {
-  if (f32) env_step<float>(blob, qpos, qvel, warm, epd, epi, action, frame_skip, obs, out, diag);
-  else env_step<double>(blob, qpos, qvel, warm, epd, epi, action, frame_skip, obs, out, diag);
+  const bool scene = blob[0] != 0.0;
+  if (f32) { if (scene) env_step<float, 4>(blob, qpos, qvel, warm, epd, epi, action, frame_skip, obs, out, diag); else env_step<float, 2>(blob, qpos, qvel, warm, epd, epi, action, frame_skip, obs, out, diag); }
+  else { if (scene) env_step<double, 4>(blob, qpos, qvel, warm, epd, epi, action, frame_skip, obs, out, diag); else env_step<double, 2>(blob, qpos, qvel, warm, epd, epi, action, frame_skip, obs, out, diag); }
 }
 void hs_env_reset(int f32, const double* blob, double* qpos, double* qvel, double* warm, double* epd, int* epi, unsigned long long seed,
                   unsigned env_id, float* obs) {
-  if (f32) env_reset<float>(blob, qpos, qvel, warm, epd, epi, seed, env_id, obs);
-  else env_reset<double>(blob, qpos, qvel, warm, epd, epi, seed, env_id, obs);
+  if (f32) env_reset<float, 2>(blob, qpos, qvel, warm, epd, epi, seed, env_id, obs);
+  else env_reset<double, 2>(blob, qpos, qvel, warm, epd, epi, seed, env_id, obs);
 }
 // observation of a given state (qpos) with given episode data; out = goal distance, min lidar
 void hs_observe(int f32, const double* blob, double* qpos, double* qvel, double* warm, const double* epd, float* obs, double* out) {
   if (f32) {
-    using E = EnvOps<float, 1>; Consts<float> C; to_consts(blob, C);
-    E::State e; Wheel<float> wh[4]; ArrAcc<float> acc{qpos, qvel, warm}; E::load_state(acc, 0, e, wh);
+    using E = EnvOps<float, 1, 2>; Consts<float> C; to_consts(blob, C);
+    E::State e; Wheel<float, 2> wh[4]; ArrAcc<float> acc{qpos, qvel, warm}; E::load_state(acc, 0, e, wh);
     Episode<float> ep; ep.goal[0] = epd[0]; ep.goal[1] = epd[1]; ep.ref[0] = epd[2]; ep.ref[1] = epd[3]; ep.step_count = 0; ep.episode = 0;
     Kin<float> k; E::S::kinematics(e, k); ObsSink sink{obs}; float d, m; E::observe(C, e, k, ep, 0, sink, &d, &m); out[0] = d; out[1] = m;
   } else {
-    using E = EnvOps<double, 1>; Consts<double> C; to_consts(blob, C);
-    E::State e; Wheel<double> wh[4]; ArrAcc<double> acc{qpos, qvel, warm}; E::load_state(acc, 0, e, wh);
+    using E = EnvOps<double, 1, 2>; Consts<double> C; to_consts(blob, C);
+    E::State e; Wheel<double, 2> wh[4]; ArrAcc<double> acc{qpos, qvel, warm}; E::load_state(acc, 0, e, wh);
     Episode<double> ep; ep.goal[0] = epd[0]; ep.goal[1] = epd[1]; ep.ref[0] = epd[2]; ep.ref[1] = epd[3]; ep.step_count = 0; ep.episode = 0;
     Kin<double> k; E::S::kinematics(e, k); ObsSink sink{obs}; double d, m; E::observe(C, e, k, ep, 0, sink, &d, &m); out[0] = d; out[1] = m;
   }
@@ -134,11 +136,11 @@ void hs_observe(int f32, const double* blob, double* qpos, double* qvel, double*
 void hs_reward(int f32, const double* blob, double dist, double min_lidar, int step_count, double* out) {
   if (f32) {
     Consts<float> C; to_consts(blob, C); Episode<float> ep; ep.step_count = step_count; StepOut<float> so;
-    EnvOps<float, 1>::reward_done(C, ep, (float)dist, (float)min_lidar, so);
+    EnvOps<float, 1, 2>::reward_done(C, ep, (float)dist, (float)min_lidar, so);
     out[0] = so.reward; out[1] = so.terminated; out[2] = so.truncated; out[3] = so.collision; out[4] = ep.step_count;
   } else {
     Consts<double> C; to_consts(blob, C); Episode<double> ep; ep.step_count = step_count; StepOut<double> so;
-    EnvOps<double, 1>::reward_done(C, ep, dist, min_lidar, so);
+    EnvOps<double, 1, 2>::reward_done(C, ep, dist, min_lidar, so);
     out[0] = so.reward; out[1] = so.terminated; out[2] = so.truncated; out[3] = so.collision; out[4] = ep.step_count;
   }
 }

@@ -185,3 +185,73 @@ def test_no_cpu_fallback_message():
     h = ctypes.c_void_p()
     rc = L.ackb_create(None, 0, 1, 0, 0, 0, 4, ctypes.byref(h))
     assert rc < 0 and b"null" in L.ackb_last_error(None)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# obstacle scene (models/environments/ackermann_maze_flat.xml): 4 actuators, AckermannController, 38 boxes, 36 beams
+# ---------------------------------------------------------------------------------------------------------------
+def _scene_states(S, n, rng):
+    qpos = np.tile(S["qpos0"], (n, 1))
+    qvel = np.zeros((n, 12))
+    for i in range(n):
+        qpos[i, 0] = rng.uniform(-3.45, -2.55)       # spawn cell: walls at x = -3.5, y = -3.5 and the block at (-3, -2)
+        qpos[i, 1] = rng.uniform(-3.45, -2.55)
+        qpos[i, 2] = 0.0648 + rng.uniform(-0.0003, 0.001)
+        yaw = rng.uniform(-np.pi, np.pi)
+        ang = rng.normal(size=2) * 0.01
+        q = np.array([np.cos(yaw / 2), ang[0], ang[1], np.sin(yaw / 2)])
+        qpos[i, 3:7] = q / np.linalg.norm(q)
+        qpos[i, 7:] = rng.uniform(-0.4, 0.4, 6)
+        qvel[i] = rng.normal(size=12) * np.array([.5, .5, .05, .2, .2, .5, 10, 10, 2, 10, 2, 10])
+    return qpos, qvel
+
+
+@pytest.mark.parametrize("dtype,tol,lanes", [("float64", 1e-5, 4), ("float64", 1e-5, 1), ("float32", 1e-3, 4)])
+def test_scene_single_step_matches_oracle(dtype, tol, lanes):
+    from mujoco_playground_b200 import BatchedAckermannEnv
+    from mujoco_playground_b200.models import load_model
+    from oracle.env_oracle import OracleEnv
+    S = load_model("scene")
+    n = 128
+    rng = np.random.default_rng(21)
+    qpos, qvel = _scene_states(S, n, rng)
+    acts = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+    env = BatchedAckermannEnv(n, model="scene", dtype=dtype, auto_reset=False, lanes_per_env=lanes,
+                              solver_tolerance=1e-12 if dtype == "float64" else None)
+    assert env.obs_dim == 43
+    env.reset()
+    env.set_state(qpos, qvel, np.zeros((n, 12)))
+    obs, _, _, _, info = env.step(torch.from_numpy(acts).cuda())
+    obs = obs.cpu().numpy()
+    q2, v2, _ = env.get_state()
+    ncon = info["ncon"].cpu().numpy()
+    o = OracleEnv(S, kind="scene", tolerance=1e-12)
+    worst, nbox = 0.0, 0
+    for i in range(n):
+        o.reset(np.zeros(2))
+        o.sim.qpos[:] = qpos[i]; o.sim.qvel[:] = qvel[i]
+        oo, *_ = o.step(acts[i])
+        nbox += int(any(c["geom1"] != 0 for c in o.sim.contacts()))
+        if dtype == "float64":
+            assert ncon[i] == o.sim.ncon
+            assert np.abs(oo[:36] - obs[i, :36]).max() < 1e-4, "36-beam lidar against the maze walls"
+        worst = max(worst, _rel(q2[i], o.sim.qpos), _rel(v2[i], o.sim.qvel))
+    assert nbox > 10, "the sample must exercise wheel-box contacts"
+    assert worst < tol
+    env.close()
+
+
+def test_scene_rollout_with_spawn_jitter_stays_supported():
+    """config[2]-style rollout: per-env yaw / xy jitter at spawn so that wheels hit the maze walls."""
+    from mujoco_playground_b200 import BatchedAckermannEnv
+    env = BatchedAckermannEnv(2048, model="scene", dtype="float32", seed=3, frame_skip=4, spawn_yaw_range=np.pi, spawn_xy_jitter=0.25)
+    env.reset()
+    hit = 0
+    for _ in range(150):
+        obs, rew, term, trunc, info = env.step(None)
+        hit = max(hit, int((info["ncon"] > 8).sum().item()))
+    assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+    assert hit > 0, "some environments must be in contact with obstacles"
+    st = env.stats()
+    assert st["unsupported"] < 0.01 * st["env_steps"]
+    env.close()

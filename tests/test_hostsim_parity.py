@@ -95,3 +95,53 @@ def test_unsupported_contact_flag_when_plate_touches_floor():
     o.qpos[2] = 0.02
     o.forward()
     assert int(o.f("unsupported_contact")[0]) == 1
+
+
+def test_scene_single_substep_matches_oracle():
+    """Obstacle scene (ackermann_maze_flat.xml): wheel-vs-box contacts, 4 actuators, no steering equality."""
+    S = load_model("scene")
+    h = HostSim(build_consts(S, model_kind=1, tolerance=1e-13), False)
+    o = OracleSim(S, tolerance=1e-13)
+    rng = np.random.default_rng(0)
+    nbox = 0
+    for t in range(150):
+        qpos = S["qpos0"].copy()
+        qpos[0] = rng.uniform(-3.45, -2.55); qpos[1] = rng.uniform(-3.45, -2.55); qpos[2] = 0.0648 + rng.uniform(-0.0003, 0.001)
+        yaw = rng.uniform(-np.pi, np.pi)
+        ang = rng.normal(size=2) * 0.01
+        q = np.array([np.cos(yaw / 2), ang[0], ang[1], np.sin(yaw / 2)])
+        qpos[3:7] = q / np.linalg.norm(q)
+        qpos[7:] = rng.uniform(-0.4, 0.4, 6)
+        qvel = rng.normal(size=12) * np.array([.5, .5, .05, .2, .2, .5, 10, 10, 2, 10, 2, 10])
+        ctrl = rng.uniform(-1, 1, 4) * np.array([0.6, 0.6, 50, 50])
+        o.reset(); o.qpos[:] = qpos; o.qvel[:] = qvel; o.ctrl[:] = ctrl
+        o.step()
+        h.qpos[:], h.qvel[:], h.warm[:] = qpos, qvel, 0
+        h.substep(ctrl)
+        nbox += int(any(c["geom1"] != 0 for c in o.contacts()))
+        assert h.diag[0] == o.ncon and h.diag[1] == int(o.f("unsupported_contact")[0]) == 0
+        assert np.abs(h.qpos - o.qpos).max() < 1e-10
+        assert np.abs(h.qvel - o.qvel).max() < 1e-9 * max(1.0, np.abs(o.qvel).max())
+    assert nbox > 20
+
+
+def test_scene_observation_matches_oracle_rays():
+    """36 beams against floor + 38 boxes: kernel ray code (host build) vs the oracle's generic ray caster."""
+    from oracle.env_oracle import OracleEnv
+    S = load_model("scene")
+    h = HostSim(build_consts(S, model_kind=1), False)
+    o = OracleEnv(S, kind="scene")
+    rng = np.random.default_rng(4)
+    for _ in range(20):
+        qpos = S["qpos0"].copy()
+        qpos[0], qpos[1] = rng.uniform(-3.3, -2.7), rng.uniform(-3.3, -2.7)
+        yaw = rng.uniform(-np.pi, np.pi)
+        qpos[3:7] = [np.cos(yaw / 2), 0, 0, np.sin(yaw / 2)]
+        goal = rng.uniform(-3, 3, 2)
+        want = o.reset(goal, spawn_qpos=qpos)
+        h.qpos[:] = qpos
+        h.epd[:2] = goal
+        h.epd[2:4] = qpos[:2]
+        got, _, _ = h.observe()
+        assert got.shape == (43,)
+        np.testing.assert_allclose(got, want, atol=2e-6)
