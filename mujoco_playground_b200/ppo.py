@@ -1,0 +1,230 @@
+"""PPO driver for the batched Ackermann environment: the caller side of the hot path.
+
+Mirrors what the reference gets from Stable-Baselines3 in ``train_with_stable_baselines3`` (src/rl/train.py:44-186):
+PPO('MlpPolicy', lr=3e-4, n_epochs=10, gamma=0.99, gae_lambda=0.95, clip_range=0.2, ent_coef=0.01) with SB3's defaults
+vf_coef=0.5, max_grad_norm=0.5, Adam(eps=1e-5), advantage normalisation, separate tanh MLPs 79->64->64 for policy and
+value, state-independent log_std, action clipping to the Box bounds, and value bootstrapping on time-limit truncation.
+Deviation: with 10^4..10^5 environments per GPU, n_steps=2048 / batch_size=64 are replaced by a short
+rollout (n_steps, default 16) and large minibatches.
+
+Multi-GPU: one process per GPU, each owns an independent environment shard; the ONLY collectives are one flattened
+gradient all-reduce per optimiser step (18 757 fp32 = 75 KB) and one statistics all-reduce per rollout.
+"""
+from __future__ import annotations
+
+import math
+import time
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from .shard import reduce_stats
+
+
+class ActorCritic(nn.Module):
+    """SB3 MlpPolicy layout (parameter names match policy.pth inside rl_logs/ppo/*.zip): 18 757 parameters for obs 79."""
+
+    def __init__(self, obs_dim: int = 79, act_dim: int = 2, hidden: int = 64, log_std_init: float = 0.0):
+        super().__init__()
+        self.mlp_extractor = nn.ModuleDict({
+            "policy_net": nn.Sequential(nn.Linear(obs_dim, hidden), nn.Tanh(), nn.Linear(hidden, hidden), nn.Tanh()),
+            "value_net": nn.Sequential(nn.Linear(obs_dim, hidden), nn.Tanh(), nn.Linear(hidden, hidden), nn.Tanh()),
+        })
+        self.action_net = nn.Linear(hidden, act_dim)
+        self.value_net = nn.Linear(hidden, 1)
+        self.log_std = nn.Parameter(torch.full((act_dim,), float(log_std_init)))
+        for seq, gain in ((self.mlp_extractor["policy_net"], math.sqrt(2)), (self.mlp_extractor["value_net"], math.sqrt(2))):
+            for m in seq:
+                if isinstance(m, nn.Linear):
+                    nn.init.orthogonal_(m.weight, gain)
+                    nn.init.zeros_(m.bias)
+        nn.init.orthogonal_(self.action_net.weight, 0.01)
+        nn.init.zeros_(self.action_net.bias)
+        nn.init.orthogonal_(self.value_net.weight, 1.0)
+        nn.init.zeros_(self.value_net.bias)
+
+    def value(self, obs):
+        return self.value_net(self.mlp_extractor["value_net"](obs)).squeeze(-1)
+
+    def dist_params(self, obs):
+        return self.action_net(self.mlp_extractor["policy_net"](obs)), self.log_std
+
+    @staticmethod
+    def log_prob(mean, log_std, act):
+        var = torch.exp(2 * log_std)
+        return (-((act - mean) ** 2) / (2 * var) - log_std - 0.5 * math.log(2 * math.pi)).sum(-1)
+
+    def act(self, obs):
+        mean, log_std = self.dist_params(obs)
+        act = mean + torch.exp(log_std) * torch.randn_like(mean)
+        return act, self.log_prob(mean, log_std, act), self.value(obs)
+
+    def evaluate(self, obs, act):
+        mean, log_std = self.dist_params(obs)
+        entropy = (0.5 + 0.5 * math.log(2 * math.pi) + log_std).sum(-1)
+        return self.log_prob(mean, log_std, act), entropy.expand(obs.shape[0]), self.value(obs)
+
+
+def sanitize_obs(obs: torch.Tensor) -> torch.Tensor:
+    """Observations are finite by construction (lidar -1..12, metres, radians); kept as a hook for input scaling."""
+    return obs
+
+
+@dataclass
+class PPOConfig:
+    n_steps: int = 16
+    n_epochs: int = 10
+    minibatches: int = 4
+    learning_rate: float = 3e-4
+    gamma: float = 0.99
+    gae_lambda: float = 0.95
+    clip_range: float = 0.2
+    ent_coef: float = 0.01
+    vf_coef: float = 0.5
+    max_grad_norm: float = 0.5
+    adam_eps: float = 1e-5
+
+
+def allreduce_gradients_(params, world: int, group=None) -> int:
+    """Average gradients over ranks with ONE flattened all-reduce; returns the number of bytes reduced."""
+    grads = [p.grad for p in params if p.grad is not None]
+    if world <= 1 or not grads:
+        return 0
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.div_(world)
+    off = 0
+    for g in grads:
+        n = g.numel()
+        g.copy_(flat[off:off + n].view_as(g))
+        off += n
+    return flat.numel() * flat.element_size()
+
+
+def compute_gae(rewards, values, dones, last_value, gamma: float, lam: float):
+    """rewards/values/dones: [T, N]; dones[t] = episode ended after step t.  Returns (advantages, returns)."""
+    T = rewards.shape[0]
+    adv = torch.zeros_like(rewards)
+    last = torch.zeros_like(last_value)
+    next_value = last_value
+    for t in range(T - 1, -1, -1):
+        nonterminal = 1.0 - dones[t]
+        delta = rewards[t] + gamma * next_value * nonterminal - values[t]
+        last = delta + gamma * lam * nonterminal * last
+        adv[t] = last
+        next_value = values[t]
+    return adv, adv + values
+
+
+def ppo_update(policy: ActorCritic, opt: torch.optim.Optimizer, batch: Dict[str, torch.Tensor], cfg: PPOConfig, world: int = 1,
+               generator: Optional[torch.Generator] = None) -> Dict[str, float]:
+    """n_epochs passes over the flattened rollout in `minibatches` shuffled minibatches, gradient all-reduce per step."""
+    n = batch["obs"].shape[0]
+    mb = max(1, n // cfg.minibatches)
+    stats = dict(pg_loss=0.0, v_loss=0.0, entropy=0.0, approx_kl=0.0, clip_frac=0.0, steps=0, allreduce_bytes=0)
+    params = [p for p in policy.parameters() if p.requires_grad]
+    for _ in range(cfg.n_epochs):
+        perm = torch.randperm(n, device=batch["obs"].device, generator=generator)
+        for i in range(cfg.minibatches):
+            idx = perm[i * mb:(i + 1) * mb]
+            obs, act, old_logp, adv, ret = (batch[k][idx] for k in ("obs", "act", "logp", "adv", "ret"))
+            adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+            logp, ent, val = policy.evaluate(obs, act)
+            ratio = torch.exp(logp - old_logp)
+            pg = -torch.min(adv * ratio, adv * torch.clamp(ratio, 1 - cfg.clip_range, 1 + cfg.clip_range)).mean()
+            vl = torch.nn.functional.mse_loss(val, ret)
+            loss = pg + cfg.vf_coef * vl - cfg.ent_coef * ent.mean()
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            stats["allreduce_bytes"] += allreduce_gradients_(params, world)
+            torch.nn.utils.clip_grad_norm_(params, cfg.max_grad_norm)
+            opt.step()
+            with torch.no_grad():
+                stats["pg_loss"] += float(pg); stats["v_loss"] += float(vl); stats["entropy"] += float(ent.mean())
+                stats["approx_kl"] += float(((ratio - 1) - (logp - old_logp)).mean())
+                stats["clip_frac"] += float(((ratio - 1).abs() > cfg.clip_range).float().mean())
+                stats["steps"] += 1
+    for k in ("pg_loss", "v_loss", "entropy", "approx_kl", "clip_frac"):
+        stats[k] /= max(1, stats["steps"])
+    return stats
+
+
+class PPOTrainer:
+    """Rollout collection on the batched CUDA environment + PPO updates; one instance per rank."""
+
+    def __init__(self, env, cfg: PPOConfig = PPOConfig(), seed: int = 0):
+        self.env, self.cfg = env, cfg
+        self.device = env.device
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank() if self.world > 1 else 0
+        torch.manual_seed(seed)                       # identical initial weights on every rank
+        self.policy = ActorCritic(env.obs_dim).to(self.device)
+        torch.manual_seed(seed * 1000003 + self.rank)  # distinct exploration noise per rank
+        self.opt = torch.optim.Adam(self.policy.parameters(), lr=cfg.learning_rate, eps=cfg.adam_eps)
+        T, N, D = cfg.n_steps, env.num_envs, env.obs_dim
+        f = dict(device=self.device, dtype=torch.float32)
+        self.buf = dict(obs=torch.empty((T, N, D), **f), act=torch.empty((T, N, 2), **f), logp=torch.empty((T, N), **f),
+                        val=torch.empty((T, N), **f), rew=torch.empty((T, N), **f), done=torch.empty((T, N), **f))
+        self.obs = env.reset().clone()
+        self.num_timesteps = 0
+
+    @torch.no_grad()
+    def collect(self) -> float:
+        cfg, env, b = self.cfg, self.env, self.buf
+        t0 = time.perf_counter()
+        for t in range(cfg.n_steps):
+            obs = sanitize_obs(self.obs)
+            act, logp, val = self.policy.act(obs)
+            b["obs"][t], b["act"][t], b["logp"][t], b["val"][t] = obs, act, logp, val
+            nobs, rew, term, trunc, info = env.step(torch.clamp(act, -1.0, 1.0))     # SB3 clips to the Box bounds
+            rew = rew.clone()
+            only_trunc = (trunc != 0) & (term == 0)
+            if bool(only_trunc.any()):                # bootstrap with V(terminal observation) on time-limit truncation
+                tv = self.policy.value(sanitize_obs(info["terminal_observation"][only_trunc]))
+                rew[only_trunc] += cfg.gamma * tv
+            b["rew"][t] = rew
+            b["done"][t] = ((term != 0) | (trunc != 0)).float()
+            self.obs.copy_(nobs)
+        self.num_timesteps += cfg.n_steps * env.num_envs * self.world
+        torch.cuda.synchronize(self.device)
+        return time.perf_counter() - t0
+
+    def update(self) -> Dict[str, float]:
+        cfg, b = self.cfg, self.buf
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            last_val = self.policy.value(sanitize_obs(self.obs))
+            adv, ret = compute_gae(b["rew"], b["val"], b["done"], last_val, cfg.gamma, cfg.gae_lambda)
+        flat = dict(obs=b["obs"].flatten(0, 1), act=b["act"].flatten(0, 1), logp=b["logp"].flatten(), adv=adv.flatten(), ret=ret.flatten())
+        st = ppo_update(self.policy, self.opt, flat, cfg, self.world)
+        torch.cuda.synchronize(self.device)
+        st["update_s"] = time.perf_counter() - t0
+        return st
+
+    def train(self, total_timesteps: int, log=print) -> Dict[str, float]:
+        out = {}
+        it = 0
+        while self.num_timesteps < total_timesteps:
+            self.env.stats_reset()
+            tr = self.collect()
+            st = self.update()
+            es = reduce_stats(self.env.stats(), device=self.device)
+            n_roll = self.cfg.n_steps * self.env.num_envs * self.world
+            out = dict(iteration=it, timesteps=self.num_timesteps, rollout_s=tr, update_s=st["update_s"],
+                       rollout_env_steps_per_s=n_roll / tr, end_to_end_env_steps_per_s=n_roll / (tr + st["update_s"]),
+                       episodes=es["episodes"], successes=es["successes"],
+                       ep_rew_mean=(es["return_sum"] / es["episodes"]) if es["episodes"] else float("nan"),
+                       ep_len_mean=(es["length_sum"] / es["episodes"]) if es["episodes"] else float("nan"),
+                       **{k: st[k] for k in ("pg_loss", "v_loss", "entropy", "approx_kl", "clip_frac", "allreduce_bytes")})
+            if self.rank == 0 and log:
+                log(out)
+            it += 1
+        return out
+
+    def save(self, path: str):
+        """Checkpoint: policy + optimiser state (replaces CheckpointCallback / model.save, train.py:140-144,182-183)."""
+        if self.rank == 0:
+            torch.save({"policy": self.policy.state_dict(), "optimizer": self.opt.state_dict(), "num_timesteps": self.num_timesteps}, path)
