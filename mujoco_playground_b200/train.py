@@ -42,6 +42,8 @@ def main(argv=None):
     rank = int(os.environ.get("RANK", 0))
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
+    torch.backends.cuda.matmul.allow_tf32 = True      # learner GEMMs (18 757-parameter MLP) on TF32 tensor cores; the simulator is unaffected
+    torch.backends.cudnn.allow_tf32 = True
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)

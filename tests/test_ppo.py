@@ -94,7 +94,7 @@ def test_gradient_allreduce_gloo_world2():
 def test_ppo_short_run_on_cuda():
     from mujoco_playground_b200 import BatchedAckermannEnv
     from mujoco_playground_b200.ppo import PPOTrainer
-    env = BatchedAckermannEnv(512, seed=1, max_episode_steps=50)
+    env = BatchedAckermannEnv(512, seed=1, max_episode_steps=8)   # every rollout of 8 steps ends all episodes by truncation
     tr = PPOTrainer(env, PPOConfig(n_steps=8, n_epochs=2, minibatches=2), seed=0)
     w0 = tr.policy.action_net.weight.detach().clone()
     out = tr.train(512 * 8 * 8, log=None)
