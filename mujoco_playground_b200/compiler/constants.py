@@ -58,7 +58,8 @@ def build_consts(M: dict, *, model_kind: int, max_episode_steps: int = 1000, goa
                  collision_threshold: float = 0.15, max_linear_velocity: float = 1.0, max_angular_velocity: float = 1.0,
                  spawn_qpos: Optional[np.ndarray] = None, lidar_index_map: str = "reference",
                  spawn_yaw_range: float = 0.0, spawn_xy_jitter: float = 0.0,
-                 tolerance: Optional[float] = None) -> np.ndarray:
+                 tolerance: Optional[float] = None, ls_iterations: Optional[int] = None,
+                 ls_fast_cap: int = 1, ls_fast_iters: int = 3, ls_mid_cap: int = 2, ls_mid_iters: int = 6) -> np.ndarray:
     lay = consts_layout()
     total = sum(c for _, c in lay.values())
     blob = np.zeros(total)
@@ -110,7 +111,11 @@ def build_consts(M: dict, *, model_kind: int, max_episode_steps: int = 1000, goa
     put("gravity", M["opt_gravity"])
     put("tolerance", float(M["opt_tolerance"][0]) if tolerance is None else tolerance)
     put("iterations", int(M["opt_iterations"][0]))
-    put("ls_iterations", int(M["opt_ls_iterations"][0]))
+    put("ls_iterations", int(M["opt_ls_iterations"][0]) if ls_iterations is None else int(ls_iterations))
+    put("ls_fast_cap", ls_fast_cap)
+    put("ls_fast_iters", ls_fast_iters)
+    put("ls_mid_cap", ls_mid_cap)
+    put("ls_mid_iters", ls_mid_iters)
     put("solver_scale", 1.0 / (float(M["stat_meaninertia"][0]) * max(1, M["nv"])))
 
     # ---- composite inertia about the chassis origin, chassis frame (hinges at 0) -------------------

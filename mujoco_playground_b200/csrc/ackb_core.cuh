@@ -851,7 +851,9 @@ struct Sim {
     }
 
     const T tol = mjmax(C.tolerance[0], N::tol_floor);
-    const int maxit = (int)C.iterations[0], maxls = (int)C.ls_iterations[0];
+    const int maxit = (int)C.iterations[0], maxls_exact = (int)C.ls_iterations[0];
+    const int ls_fast_cap = (int)C.ls_fast_cap[0], ls_fast_iters = (int)C.ls_fast_iters[0];
+    const int ls_mid_cap = (int)C.ls_mid_cap[0], ls_mid_iters = (int)C.ls_mid_iters[0];
     int iter = 0, nls = 0;
     // per-environment phase: 0 = iterating (step along x, then Newton pass), 2 = converged.
     // The loop itself is warp-uniform: it runs until every environment of the warp has converged.
@@ -894,7 +896,11 @@ struct Sim {
         bool exact = false;
         bool ls_on = stepping && !first;
         T lo = T(0), hi = T(-1);
-        for (int ls = 0; ls < maxls && Tm::any(ls_on); ++ls) {
+        // The search is exact (safeguarded Newton to ls_rel) only for environments that are slow to converge; during their
+        // first ls_fast_iters iterations at most ls_fast_cap evaluations are spent and the next candidate is taken, which keeps
+        // the warp-wide trip count of this loop small (the outer Newton iteration absorbs the inexactness).
+        const int my_maxls = (iter < ls_fast_iters) ? ls_fast_cap : ((iter < ls_mid_iters) ? ls_mid_cap : maxls_exact);
+        for (int ls = 0; ls < maxls_exact && Tm::any(ls_on); ++ls) {
           T d[3] = {T(0), T(0), T(0)};
 #pragma unroll 1
           for (int s = 0; s < WPL; ++s) {
@@ -940,7 +946,7 @@ struct Sim {
               if (d1 < T(0)) lo = alpha; else hi = alpha;
               T an = alpha - d1 / d2;
               if (hi >= T(0) && (an <= lo || an >= hi)) an = T(0.5) * (lo + hi);
-              if (an == alpha) ls_on = false;
+              if (an == alpha || ls + 1 >= my_maxls) ls_on = false;
               alpha = an;
             }
           }

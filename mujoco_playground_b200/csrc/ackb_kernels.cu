@@ -89,8 +89,14 @@ struct Geo {
   static constexpr bool kSmemWheels = WPL > 1;
   static constexpr int kWheelUnits = sizeof(Wheel<T, NC>) / sizeof(T);          // record size in units of T
   static constexpr int kStride = WPL * kWheelUnits + ((WPL * kWheelUnits) % 2 == 0 ? 1 : 0);   // odd
-  static constexpr int kBlock = kSmemWheels ? (sizeof(T) == 4 ? 128 : 64) : 128;
-  static constexpr int kMinBlocks = kSmemWheels ? 2 : 2;
+#ifndef ACKB_L1_BLOCK
+#define ACKB_L1_BLOCK 128
+#endif
+#ifndef ACKB_L1_MINB
+#define ACKB_L1_MINB 2
+#endif
+  static constexpr int kBlock = kSmemWheels ? (sizeof(T) == 4 ? ACKB_L1_BLOCK : ACKB_L1_BLOCK / 2) : 128;
+  static constexpr int kMinBlocks = kSmemWheels ? ACKB_L1_MINB : 2;
   static size_t smem_bytes(int obs_dim) {
     const size_t tile = (size_t)(kBlock / LANES) * obs_dim * sizeof(float);
     const size_t wheels = kSmemWheels ? (size_t)kBlock * kStride * sizeof(T) : 0;
