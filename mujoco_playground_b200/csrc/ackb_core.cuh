@@ -107,6 +107,31 @@ template <> struct Num<double> {
 // ------------------------------------------------------------------------------------------------
 // team of LANES lanes working on one environment
 // ------------------------------------------------------------------------------------------------
+#if !defined(__CUDACC__)
+}  // namespace ackb
+#include <barrier>
+namespace ackb {
+// Host emulation of a team of lanes (tests/hostsim only): LANES std::threads run the per-lane code in lock step and meet
+// at every collective.  The device code keeps all collectives warp-uniform, so the same call sequence is valid here.
+struct HostTeamCtx {
+  int lanes;
+  std::barrier<>* bar;
+  double slot[32];
+};
+inline thread_local HostTeamCtx* g_host_team = nullptr;
+inline thread_local int g_host_lane = 0;
+template <typename T, typename F>
+inline T host_collective(T v, F&& combine) {
+  HostTeamCtx* c = g_host_team;
+  c->slot[g_host_lane] = (double)v;
+  c->bar->arrive_and_wait();
+  T r = (T)c->slot[0];
+  for (int i = 1; i < c->lanes; ++i) r = combine(r, (T)c->slot[i]);
+  c->bar->arrive_and_wait();
+  return r;
+}
+#endif
+
 template <int LANES>
 struct Team {
   // All team collectives are executed by the whole (converged) warp with the full mask: control flow around them is
@@ -116,8 +141,25 @@ struct Team {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
     for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-#else
-    static_assert(LANES == 1, "host build supports LANES == 1 only");
+#elif !defined(__CUDACC__)
+    if (LANES > 1) v = host_collective(v, [](T a, T b) { return a + b; });
+#endif
+    return v;
+  }
+  // sum over the two lanes that share a wheel (8 lanes per environment: lane = 2 * wheel + contact)
+  template <typename T>
+  ACKB_D static T pair_sum(T v) {
+#if defined(__CUDA_ARCH__)
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+#elif !defined(__CUDACC__)
+    if (LANES > 1) {
+      HostTeamCtx* c = g_host_team;
+      c->slot[g_host_lane] = (double)v;
+      c->bar->arrive_and_wait();
+      const T lo = (T)c->slot[g_host_lane & ~1], hi = (T)c->slot[g_host_lane | 1];
+      c->bar->arrive_and_wait();
+      v = lo + hi;
+    }
 #endif
     return v;
   }
@@ -126,6 +168,8 @@ struct Team {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
     for (int o = LANES / 2; o > 0; o >>= 1) { T other = __shfl_xor_sync(0xffffffffu, v, o); v = other < v ? other : v; }
+#elif !defined(__CUDACC__)
+    if (LANES > 1) v = host_collective(v, [](T a, T b) { return b < a ? b : a; });
 #endif
     return v;
   }
@@ -154,10 +198,13 @@ struct Team {
     return any(p);
 #endif
   }
-  // true if the predicate holds for any lane of the warp (host: the single environment)
+  // true if the predicate holds for any lane of the warp (host: any lane of the single environment)
   ACKB_D static bool any(bool p) {
 #if defined(__CUDA_ARCH__)
     return __any_sync(0xffffffffu, p) != 0;
+#elif !defined(__CUDACC__)
+    if (LANES > 1) return host_collective(p ? 1 : 0, [](int a, int b) { return a | b; }) != 0;
+    return p;
 #else
     return p;
 #endif
@@ -520,10 +567,18 @@ struct DebugTap {
 // ------------------------------------------------------------------------------------------------
 // the simulator
 // ------------------------------------------------------------------------------------------------
+// LANES lanes per environment.  1, 2, 4: each lane owns WPL = 4/LANES whole wheels (records with NC contact slots).
+// 8: each lane owns ONE floor contact of a wheel (lane = 2 * wheel + contact, records with NC = 1 slot); the spin dof of
+// the wheel is replicated in the two lanes of the pair, its contact-dependent pivots are pair-summed, and every per-wheel
+// term that enters a team sum carries the weight 1/2.
 template <typename T, int LANES, int NC>
 struct Sim {
-  static constexpr int WPL = 4 / LANES;
+  static constexpr bool PAIR = (LANES == 8);
+  static constexpr int WPL = PAIR ? 1 : 4 / LANES;
+  static constexpr int NCF = PAIR ? 1 : 2;          // floor-contact slots of a record
   using WheelT = Wheel<T, NC>;
+  ACKB_HD static int wheel_index(int lane, int s) { return PAIR ? (lane >> 1) : lane * WPL + s; }
+  ACKB_HD static T pair_weight() { return PAIR ? T(0.5) : T(1); }
   using Tm = Team<LANES>;
   using N = Num<T>;
   using State = EnvState<T>;
@@ -544,7 +599,7 @@ struct Sim {
   }
 
   // ---- B6/B7 floor contacts of one wheel (plane vs cylinder, in the body frame) and their row parameters
-  ACKB_HD static void collide_wheel(const Consts<T>& C, const State& e, const Kin<T>& k, const T* vb, int wi, const WheelK<T>& wk,
+  ACKB_HD static void collide_wheel(const Consts<T>& C, const State& e, const Kin<T>& k, const T* vb, int wi, int cown, const WheelK<T>& wk,
                                     WheelT& w, StepDiag& diag) {
     const T s = wk.isL * e.st[0] + wk.isR * e.st[1];
     T sn, cs;
@@ -570,11 +625,13 @@ struct Sim {
     const T d0 = dist + prjaxis + prjvec, d1 = dist - prjaxis + prjvec;
     const bool has0 = d0 <= T(0), has1 = has0 && (d1 <= T(0));
     if (has0 && (dist + prjaxis - T(0.5) * prjvec <= T(0))) diag.unsupported = 1;  // cap faces the floor
-    diag.ncon += (has0 ? 1 : 0) + (has1 ? 1 : 0);
+    if (PAIR) diag.ncon += (cown == 0) ? (has0 ? 1 : 0) : (has1 ? 1 : 0);
+    else diag.ncon += (has0 ? 1 : 0) + (has1 ? 1 : 0);
     const T mu = wk.mu;
 #pragma unroll(CU)
-    for (int c = 0; c < 2; ++c) {
-      Contact<T>& con = w.con[c];
+    for (int cc = 0; cc < NCF; ++cc) {
+      const int c = PAIR ? cown : cc;
+      Contact<T>& con = w.con[cc];
       const T dd = (c == 0) ? d0 : d1, sg = (c == 0) ? T(1) : T(-1);
       const bool has = (c == 0) ? has0 : has1;
       con.x[0] = wk.c[0] + vec[0] + sg * ax[0] - k.n[0] * dd * T(0.5);
@@ -766,10 +823,10 @@ struct Sim {
     bool warm_ok = true;
 #pragma unroll 1
     for (int s = 0; s < WPL; ++s) {
-      const int wi = lane * WPL + s;
+      const int wi = wheel_index(lane, s);
       const WheelK<T> wk = wheel_consts(C, wi);
       WheelT& w = wh[s];
-      collide_wheel(C, e, k, vb, wi, wk, w, diag);
+      collide_wheel(C, e, k, vb, wi, lane & 1, wk, w, diag);
       if (NC > 2) collide_boxes(C, e, k, vb, wi, wk, w, diag);
       const T dsteer = wk.isL * e.dst[0] + wk.isR * e.dst[1];
       const T aw[3] = {w.ax, w.ay, T(0)};
@@ -778,12 +835,13 @@ struct Sim {
       cross3(ezxa, ez, aw);
       cross3(omxa, e.om, aw);
       cross3(omxez, e.om, ez);
+      const T pwt = pair_weight();
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
-        bpart[i] += wk.J * w.dsp * aw[i];
-        bpart[3 + i] += wk.J * w.dsp * dsteer * ezxa[i];
+        bpart[i] += pwt * wk.J * w.dsp * aw[i];
+        bpart[3 + i] += pwt * wk.J * w.dsp * dsteer * ezxa[i];
       }
-      const T bias_steer = wk.J * w.dsp * omxa[2];  // ez . (om x a)
+      const T bias_steer = pwt * wk.J * w.dsp * omxa[2];  // ez . (om x a)
       bpart[6] += wk.isL * bias_steer;
       bpart[7] += wk.isR * bias_steer;
       const T bias_spin = wk.J * dsteer * dot3(aw, omxez);
@@ -869,13 +927,14 @@ struct Sim {
         T acc[5] = {T(0), T(0), T(0), T(0), T(0)};  // sum_w J a_w x_w (3), private parts of x.Mx and x.(Ma - tau)
 #pragma unroll 1
         for (int s = 0; s < WPL; ++s) {
-          const int wi = lane * WPL + s;
+          const int wi = wheel_index(lane, s);
           const WheelK<T> wk = wheel_consts(C, wi);
           WheelT& w = wh[s];
           const T aw_aang_x = w.ax * x_sh[3] + w.ay * x_sh[4], aw_aang_a = w.ax * a_sh[3] + w.ay * a_sh[4];
           const T Mv_sp = wk.J * aw_aang_x + wk.cdiag * w.x, Ma_sp = wk.J * aw_aang_a + wk.cdiag * w.a;
-          acc[0] += wk.J * w.ax * w.x; acc[1] += wk.J * w.ay * w.x;
-          acc[3] += w.x * Mv_sp; acc[4] += w.x * (Ma_sp - w.tau);
+          const T pwt = pair_weight();
+          acc[0] += pwt * wk.J * w.ax * w.x; acc[1] += pwt * wk.J * w.ay * w.x;
+          acc[3] += pwt * w.x * Mv_sp; acc[4] += pwt * w.x * (Ma_sp - w.tau);
           const T ast = wk.isL * x_sh[6] + wk.isR * x_sh[7];
 #pragma unroll(CU)
           for (int c = 0; c < NC; ++c) {
@@ -904,13 +963,13 @@ struct Sim {
           T d[3] = {T(0), T(0), T(0)};
 #pragma unroll 1
           for (int s = 0; s < WPL; ++s) {
-            const int wi = lane * WPL + s;
+            const int wi = wheel_index(lane, s);
             const WheelK<T> wk = wheel_consts(C, wi);
             const WheelT& w = wh[s];
             T f, q;
             floss_row(w.a + alpha * w.x + wk.flB * w.dsp, wk.flf, wk.flR, &f, &q);
-            d[0] -= f * w.x;
-            d[1] += q / wk.flR * w.x * w.x;
+            d[0] -= pair_weight() * f * w.x;
+            d[1] += pair_weight() * q / wk.flR * w.x * w.x;
             unsigned zone = (q != T(0)) ? 1u : (f > T(0) ? 0u : 2u);
 #pragma unroll(CU)
             for (int c = 0; c < NC; ++c) {
@@ -978,19 +1037,18 @@ struct Sim {
       for (int i = 0; i < 45; ++i) part[i] = T(0);
 #pragma unroll 1
       for (int s = 0; s < WPL; ++s) {
-        const int wi = lane * WPL + s;
+        const int wi = wheel_index(lane, s);
         const WheelK<T> wk = wheel_consts(C, wi);
         WheelT& w = wh[s];
         T f, q;
         floss_row(w.a + wk.flB * w.dsp, wk.flf, wk.flR, &f, &q);
         unsigned zone = (q != T(0)) ? 1u : (f > T(0) ? 0u : 2u);
-        T gs_sp = wk.J * (w.ax * a_sh[3] + w.ay * a_sh[4]) + wk.cdiag * w.a - w.tau - f;
-        T cs = wk.cdiag + q / wk.flR;
+        T gs_sp = T(0), cs = T(0);   // contact parts first (pair-summed with 8 lanes), wheel parts added below
         T Hll[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};   // 00 10 11 20 21 22
         T Hal[3][3] = {{T(0), T(0), T(0)}, {T(0), T(0), T(0)}, {T(0), T(0), T(0)}};
         T Haa[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};
         T Hsl[3] = {T(0), T(0), T(0)}, Hsa[3] = {T(0), T(0), T(0)}, Hss = T(0);
-        T bl[3] = {T(0), T(0), T(0)}, ba[3] = {wk.J * w.ax, wk.J * w.ay, T(0)}, bs = T(0);
+        T bl[3] = {T(0), T(0), T(0)}, ba[3] = {T(0), T(0), T(0)}, bs = T(0);
         T gl[3] = {T(0), T(0), T(0)}, ga[3] = {T(0), T(0), T(0)}, gst = T(0);
         const T mu = wk.mu;
 #pragma unroll(CU)
@@ -1059,6 +1117,14 @@ struct Sim {
           gst -= wv[0] * Phi[0] + wv[1] * Phi[1];
           gs_sp -= dot3(u, Phi);
         }
+        if (PAIR) {
+          gs_sp = Tm::pair_sum(gs_sp); cs = Tm::pair_sum(cs); bs = Tm::pair_sum(bs);
+#pragma unroll
+          for (int i = 0; i < 3; ++i) { bl[i] = Tm::pair_sum(bl[i]); ba[i] = Tm::pair_sum(ba[i]); }
+        }
+        gs_sp += wk.J * (w.ax * a_sh[3] + w.ay * a_sh[4]) + wk.cdiag * w.a - w.tau - f;
+        cs += wk.cdiag + q / wk.flR;
+        ba[0] += wk.J * w.ax; ba[1] += wk.J * w.ay;
         if (phase == 0) w.zone0 = zone;
         w.g = gs_sp; w.cw = cs;
         T b8[8], gsh_w[8];
@@ -1080,7 +1146,7 @@ struct Sim {
           part[tri(7, j)] += wk.isR * Hsl[j]; part[tri(7, 3 + j)] += wk.isR * Hsa[j];
         }
         part[tri(6, 6)] += wk.isL * Hss; part[tri(7, 7)] += wk.isR * Hss;
-        const T ci = T(1) / cs;
+        const T ci = pair_weight() / cs;     // the Schur terms of a wheel are counted once per team
 #pragma unroll
         for (int a = 0; a < 8; ++a) {
           const T bc = b8[a] * ci;
@@ -1114,7 +1180,7 @@ struct Sim {
         // x = -H^-1 g
 #pragma unroll 1
         for (int s = 0; s < WPL; ++s) {
-          const int wi = lane * WPL + s;
+          const int wi = wheel_index(lane, s);
           WheelT& w = wh[s];
           T dotb = T(0);
 #pragma unroll
@@ -1139,10 +1205,10 @@ struct Sim {
       T part3[3] = {T(0), T(0), T(0)};
 #pragma unroll 1
       for (int s = 0; s < WPL; ++s) {
-        const int wi = lane * WPL + s;
+        const int wi = wheel_index(lane, s);
         const WheelK<T> wk = wheel_consts(C, wi);
         const WheelT& w = wh[s];
-        const T coef = wk.J * (h * wk.damp * w.a) * C.w_cEinv[wi];
+        const T coef = pair_weight() * wk.J * (h * wk.damp * w.a) * C.w_cEinv[wi];
         part3[0] -= coef * w.ax; part3[1] -= coef * w.ay;
       }
       Tm::sum_n(part3);
@@ -1179,7 +1245,7 @@ struct Sim {
     if (tap) {
       for (int i = 0; i < 8; ++i) { tap->tau[i] = tau_sh[i]; tap->a_smooth[i] = T(0); tap->a[i] = a_sh[i]; tap->fc[i] = T(0); }
       for (int s = 0; s < WPL; ++s) {
-        int wi = lane * WPL + s;
+        int wi = wheel_index(lane, s);
         tap->tau[8 + wi] = wh[s].tau; tap->a_smooth[8 + wi] = T(0); tap->a[8 + wi] = wh[s].a; tap->fc[8 + wi] = T(0);
       }
       tap->niter = iter; tap->nls = nls;
@@ -1189,7 +1255,7 @@ struct Sim {
     // implicitly damped acceleration a - y, then positions with the new velocities (semi-implicit Euler)
 #pragma unroll 1
     for (int s = 0; s < WPL; ++s) {
-      const int wi = lane * WPL + s;
+      const int wi = wheel_index(lane, s);
       const WheelK<T> wk = wheel_consts(C, wi);
       WheelT& w = wh[s];
       const T yi = (h * wk.damp * w.a - wk.J * (w.ax * yi_sh[3] + w.ay * yi_sh[4])) * C.w_cEinv[wi];

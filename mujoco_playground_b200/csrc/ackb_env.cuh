@@ -43,7 +43,7 @@ struct EnvOps {
     for (int i = 0; i < 2; ++i) { e.st[i] = a.qpos(hinge_qadr(i)); e.dst[i] = a.qvel(hinge_dadr(i)); e.warm_st[i] = a.warm(hinge_dadr(i)); }
 #pragma unroll 1
     for (int s = 0; s < WPL; ++s) {
-      int h = 2 + lane * WPL + s;
+      int h = 2 + S::wheel_index(lane, s);
       wh[s].sp = a.qpos(hinge_qadr(h)); wh[s].dsp = a.qvel(hinge_dadr(h)); wh[s].warm = a.warm(hinge_dadr(h));
     }
   }
@@ -56,7 +56,8 @@ struct EnvOps {
     }
 #pragma unroll 1
     for (int s = 0; s < WPL; ++s) {
-      int h = 2 + lane * WPL + s;
+      int h = 2 + S::wheel_index(lane, s);
+      if (S::PAIR && (lane & 1)) continue;
       a.set_qpos(hinge_qadr(h), wh[s].sp); a.set_qvel(hinge_dadr(h), wh[s].dsp); a.set_warm(hinge_dadr(h), wh[s].warm);
     }
   }
@@ -127,7 +128,7 @@ struct EnvOps {
     }
     for (int i = 0; i < 2; ++i) { e.st[i] = C.spawn_qpos[hinge_qadr(i)]; e.dst[i] = e.warm_st[i] = T(0); }
 #pragma unroll 1
-    for (int s = 0; s < WPL; ++s) { wh[s].sp = C.spawn_qpos[hinge_qadr(2 + lane * WPL + s)]; wh[s].dsp = wh[s].warm = T(0); }
+    for (int s = 0; s < WPL; ++s) { wh[s].sp = C.spawn_qpos[hinge_qadr(2 + S::wheel_index(lane, s))]; wh[s].dsp = wh[s].warm = T(0); }
     ep.ref[0] = e.p[0]; ep.ref[1] = e.p[1];
     ep.step_count = 0;
     const T d = C.goal_dmin[0] + (C.goal_dmax[0] - C.goal_dmin[0]) * (T)u01(r[0]);

@@ -85,7 +85,7 @@ __device__ __forceinline__ unsigned warp_sum_u32(unsigned v) {
 // (the tile is flushed to HBM before the dynamics of the last substep reuse it).
 template <typename T, int LANES, int NC>
 struct Geo {
-  static constexpr int WPL = 4 / LANES;
+  static constexpr int WPL = LANES == 8 ? 1 : 4 / LANES;
   static constexpr bool kSmemWheels = WPL > 1;
   static constexpr int kWheelUnits = sizeof(Wheel<T, NC>) / sizeof(T);          // record size in units of T
   static constexpr int kStride = WPL * kWheelUnits + ((WPL * kWheelUnits) % 2 == 0 ? 1 : 0);   // odd
@@ -378,7 +378,8 @@ int launch_one(ackb_handle* h, DevState<T>& st, const StepArgs& a, cudaStream_t 
 template <typename T>
 int launch_step(ackb_handle* h, DevState<T>& st, const StepArgs& a, cudaStream_t stream, bool is_reset) {
   const bool scene = h->consts_host[0] != 0.0;   // model_kind: the obstacle scene needs the two box-contact slots per wheel
-  if (h->lanes == 4) return scene ? launch_one<T, 4, 4>(h, st, a, stream, is_reset) : launch_one<T, 4, 2>(h, st, a, stream, is_reset);
+  if (h->lanes == 8 && !scene) return launch_one<T, 8, 1>(h, st, a, stream, is_reset);   // one lane per floor contact (flat-floor model)
+  if (h->lanes >= 4) return scene ? launch_one<T, 4, 4>(h, st, a, stream, is_reset) : launch_one<T, 4, 2>(h, st, a, stream, is_reset);
   return scene ? launch_one<T, 1, 4>(h, st, a, stream, is_reset) : launch_one<T, 1, 2>(h, st, a, stream, is_reset);
 }
 }  // namespace
@@ -396,7 +397,7 @@ int ackb_create(const double* consts, size_t consts_len, int num_envs, int devic
   if ((int)consts_len != kNumConsts) return fail(nullptr, ACKB_ERR_ARG, "ackb_create: constants blob has the wrong length");
   if (dtype != ACKB_F32 && dtype != ACKB_F64) return fail(nullptr, ACKB_ERR_ARG, "ackb_create: dtype must be ACKB_F32 or ACKB_F64");
   if (lanes_per_env == 0) lanes_per_env = num_envs >= 32768 ? 1 : 4;   // throughput layout for big batches, latency layout otherwise
-  if (lanes_per_env != 1 && lanes_per_env != 4) return fail(nullptr, ACKB_ERR_ARG, "ackb_create: lanes_per_env must be 1 or 4");
+  if (lanes_per_env != 1 && lanes_per_env != 4 && lanes_per_env != 8) return fail(nullptr, ACKB_ERR_ARG, "ackb_create: lanes_per_env must be 1, 4 or 8");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, ACKB_ERR_NO_DEVICE, "ackb_create: no CUDA device (there is no CPU fallback)");
   if (device < 0 || device >= ndev || device >= 64) return fail(nullptr, ACKB_ERR_ARG, "ackb_create: bad device index");

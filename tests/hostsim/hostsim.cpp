@@ -2,6 +2,8 @@
 // Lets the arithmetic of mujoco_playground_b200/csrc/ackb_core.cuh / ackb_env.cuh be checked against
 // the oracle on a machine without a GPU.  It is not part of the product and is never loaded by it.
 #include <cstring>
+#include <thread>
+#include <vector>
 #include "../../mujoco_playground_b200/csrc/ackb_env.cuh"
 
 using namespace ackb;
@@ -98,9 +100,55 @@ void env_reset(const double* blob, double* qpos, double* qvel, double* warm, dou
   epd[0] = (double)ep.goal[0]; epd[1] = (double)ep.goal[1]; epd[2] = (double)ep.ref[0]; epd[3] = (double)ep.ref[1];
   epi[0] = ep.step_count; epi[1] = (int)ep.episode;
 }
+// LANES host threads emulate the lanes of one environment (collectives meet at a std::barrier): exercises the
+// multi-lane code paths (4 lanes = one per wheel, 8 lanes = one per floor contact) without a GPU.
+template <typename T, int LANES, int NC>
+void env_step_team(const double* blob, double* qpos, double* qvel, double* warm, double* epd, int* epi, const float* action, int frame_skip,
+                   float* obs, float* out, int* diag_out) {
+  using E = EnvOps<T, LANES, NC>;
+  Consts<T> C;
+  to_consts(blob, C);
+  std::barrier<> bar(LANES);
+  HostTeamCtx ctx{LANES, &bar, {0}};
+  std::vector<std::thread> th;
+  int ncon_lane[LANES], unsup_lane[LANES], niter_lane[LANES];
+  for (int lane = 0; lane < LANES; ++lane)
+    th.emplace_back([&, lane] {
+      g_host_team = &ctx; g_host_lane = lane;
+      typename E::State e;
+      Wheel<T, NC> wh[E::WPL];
+      ArrAcc<T> acc{qpos, qvel, warm};
+      E::load_state(acc, lane, e, wh);
+      Episode<T> ep;
+      ep.goal[0] = (T)epd[0]; ep.goal[1] = (T)epd[1]; ep.ref[0] = (T)epd[2]; ep.ref[1] = (T)epd[3];
+      ep.step_count = epi[0]; ep.episode = (uint32_t)epi[1];
+      ObsSink sink{obs};
+      StepOut<T> so;
+      StepDiag diag{0, 0, 0};
+      E::step_env(C, e, wh, ep, action[0], action[1], frame_skip, lane, sink, [] {}, so, diag, (DebugTap<T>*)nullptr);
+      bar.arrive_and_wait();           // every lane finished reading the shared state arrays
+      E::store_state(acc, lane, e, wh);
+      ncon_lane[lane] = diag.ncon; unsup_lane[lane] = diag.unsupported; niter_lane[lane] = diag.niter;
+      if (lane == 0) {
+        epi[0] = ep.step_count;
+        out[0] = so.reward; out[1] = so.terminated; out[2] = so.truncated; out[3] = so.collision; out[4] = so.goal_distance; out[5] = so.min_lidar;
+      }
+    });
+  for (auto& t : th) t.join();
+  if (diag_out) {
+    diag_out[0] = diag_out[1] = 0; diag_out[2] = niter_lane[0];
+    for (int l = 0; l < LANES; ++l) { diag_out[0] += ncon_lane[l]; diag_out[1] |= unsup_lane[l]; }
+  }
+}
 }  // namespace
 
 extern "C" {
+// multi-lane emulation (v2 model only): lanes = 4 or 8
+void hs_env_step_lanes(int lanes, int f32, const double* blob, double* qpos, double* qvel, double* warm, double* epd, int* epi, const float* action,
+                       int frame_skip, float* obs, float* out, int* diag) {
+  if (lanes == 4) { if (f32) env_step_team<float, 4, 2>(blob, qpos, qvel, warm, epd, epi, action, frame_skip, obs, out, diag); else env_step_team<double, 4, 2>(blob, qpos, qvel, warm, epd, epi, action, frame_skip, obs, out, diag); }
+  else { if (f32) env_step_team<float, 8, 1>(blob, qpos, qvel, warm, epd, epi, action, frame_skip, obs, out, diag); else env_step_team<double, 8, 1>(blob, qpos, qvel, warm, epd, epi, action, frame_skip, obs, out, diag); }
+}
 int hs_nconsts() { return kNumConsts; }
 void hs_substep(int f32, const double* blob, double* qpos, double* qvel, double* warm, const double* ctrl, int nsteps, double* tap, int* diag) {
   const bool scene = blob[0] != 0.0;   // model_kind: the obstacle scene has two extra box-contact slots per wheel

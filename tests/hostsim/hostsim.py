@@ -18,7 +18,7 @@ def lib():
         srcs = [os.path.join(_HERE, "hostsim.cpp"), os.path.join(csrc, "ackb_core.cuh"), os.path.join(csrc, "ackb_env.cuh"),
                 os.path.join(_ROOT, "include", "ackb_consts.def")]
         if not os.path.exists(tgt) or any(os.path.getmtime(s) > os.path.getmtime(tgt) for s in srcs):
-            subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-I" + os.path.join(_ROOT, "include"),
+            subprocess.check_call(["g++", "-O2", "-std=c++20", "-pthread", "-shared", "-fPIC", "-ffp-contract=off", "-I" + os.path.join(_ROOT, "include"),
                                    "-o", tgt, srcs[0]])
         _lib = ctypes.CDLL(tgt)
         _lib.hs_hs = None
@@ -54,9 +54,15 @@ class HostSim:
         c4[: len(ctrl)] = ctrl
         self.L.hs_substep(self.f32, _p(self.blob), _p(self.qpos), _p(self.qvel), _p(self.warm), _p(c4), n, _p(self.tap), _p(self.diag))
 
-    def step(self, action, frame_skip=1):
+    def step(self, action, frame_skip=1, lanes=1):
         a = np.ascontiguousarray(action, dtype=np.float32)
         out = np.zeros(6, np.float32)
+        if lanes > 1:   # LANES host threads emulate the lanes of the environment
+            self.L.hs_env_step_lanes(lanes, self.f32, _p(self.blob), _p(self.qpos), _p(self.qvel), _p(self.warm), _p(self.epd), _p(self.epi), _p(a),
+                                     frame_skip, _p(self.obs), _p(out), _p(self.diag))
+            return self.obs.copy(), float(out[0]), bool(out[1]), bool(out[2]), dict(collision=bool(out[3]), goal_distance=float(out[4]),
+                                                                                     min_lidar=float(out[5]), ncon=int(self.diag[0]),
+                                                                                     unsupported=int(self.diag[1]), niter=int(self.diag[2]))
         self.L.hs_env_step(self.f32, _p(self.blob), _p(self.qpos), _p(self.qvel), _p(self.warm), _p(self.epd), _p(self.epi), _p(a),
                            frame_skip, _p(self.obs), _p(out), _p(self.diag))
         return self.obs.copy(), float(out[0]), bool(out[1]), bool(out[2]), dict(collision=bool(out[3]), goal_distance=float(out[4]),
