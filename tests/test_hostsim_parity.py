@@ -145,3 +145,20 @@ def test_scene_observation_matches_oracle_rays():
         got, _, _ = h.observe()
         assert got.shape == (43,)
         np.testing.assert_allclose(got, want, atol=2e-6)
+
+
+@pytest.mark.parametrize("lanes", [4, 8])
+def test_multi_lane_code_paths_agree_with_single_lane(lanes):
+    """The 4-lane (one lane per wheel) and 8-lane (one lane per floor contact) decompositions, run on the host with one
+    thread per lane and a barrier at every team collective, against the 1-lane path: same arithmetic up to summation order."""
+    blob = build_consts(M, model_kind=0, tolerance=1e-13)
+    h1, hL = HostSim(blob), HostSim(blob)
+    h1.reset(seed=2); hL.reset(seed=2)
+    rng = np.random.default_rng(1)
+    for t in range(60):
+        a = rng.uniform(-1, 1, 2).astype(np.float32)
+        o1, r1, te1, tr1, i1 = h1.step(a, frame_skip=2)
+        oL, rL, teL, trL, iL = hL.step(a, frame_skip=2, lanes=lanes)
+        assert i1["ncon"] == iL["ncon"] and te1 == teL and tr1 == trL and abs(r1 - rL) < 1e-6
+        assert np.abs(o1 - oL).max() < 1e-5
+    assert np.abs(h1.qpos - hL.qpos).max() < 1e-9 and np.abs(h1.qvel - hL.qvel).max() < 1e-8
