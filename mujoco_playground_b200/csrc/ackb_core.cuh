@@ -180,9 +180,10 @@ struct Team {
   }
   // Instruction-cache locality: the warps of a CTA re-converge here so that they walk the same code together and share
   // the fetched lines (the kernel is instruction-fetch bound).  Must be reached by every thread of the CTA.
+  // (With 1 lane per environment the rolled wheel loops keep the footprint small and the barrier is not needed.)
   ACKB_D static void block_sync() {
-#if defined(__CUDA_ARCH__) && defined(ACKB_SYNC_SUBSTEP)
-    __syncthreads();
+#if defined(__CUDA_ARCH__)
+    if (LANES > 1) __syncthreads();
 #endif
   }
   ACKB_D static void warp_sync() {

@@ -105,13 +105,14 @@ def test_trajectory_from_reset(dtype, steps, tol_q, tol_obs):
 
 
 def test_lane_layouts_agree():
-    """1, 2 and 4 lanes per environment run the same arithmetic up to summation order."""
+    """1, 4 and 8 lanes per environment run the same arithmetic up to summation order (tight solver tolerance so that the
+    different orders cannot stop the Newton iteration at different points)."""
     from mujoco_playground_b200 import BatchedAckermannEnv
     res = []
     rng = np.random.default_rng(2)
     acts = rng.uniform(-1, 1, (40, 33, 2)).astype(np.float32)
-    for lanes in (1, 4):
-        env = BatchedAckermannEnv(33, dtype="float64", seed=9, lanes_per_env=lanes, auto_reset=False, frame_skip=2)
+    for lanes in (1, 4, 8):
+        env = BatchedAckermannEnv(33, dtype="float64", seed=9, lanes_per_env=lanes, auto_reset=False, frame_skip=2, solver_tolerance=1e-12)
         env.reset()
         for t in range(40):
             obs, *_ = env.step(torch.from_numpy(acts[t]).cuda())

@@ -25,7 +25,7 @@ def main():
     a = ap.parse_args()
     csrc = os.path.join(ROOT, "mujoco_playground_b200", "csrc")
     if not a.no_build:
-        cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xptxas", "-v",
+        cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-diag-suppress", "177", "-Xptxas", "-v",
                "-I" + os.path.join(ROOT, "include"), "-I" + csrc, "-shared", "-Xcompiler", "-fPIC", "-o", a.out,
                os.path.join(csrc, "ackb_kernels.cu")] + ["-D" + d for d in a.defs.split(",") if d]
         r = subprocess.run(cmd, capture_output=True, text=True)
