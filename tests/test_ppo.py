@@ -102,3 +102,23 @@ def test_ppo_short_run_on_cuda():
     assert out["episodes"] > 0 and np.isfinite(out["ep_rew_mean"])
     assert not torch.equal(w0, tr.policy.action_net.weight.detach())
     env.close()
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/rl_logs/ppo/ppo_model_10000_steps.zip"), reason="reference checkout not present")
+def test_load_reference_sb3_checkpoints(tmp_path):
+    """The three checkpoints the reference commits load into ActorCritic; the recorded _last_obs is the lidar known answer."""
+    import base64
+    import json
+    from mujoco_playground_b200.sb3_io import load_sb3_policy, save_sb3_policy
+    for name in ("ppo_model_10000_steps.zip", "ppo_model_20000_steps.zip", "ppo_model_30000_steps.zip"):
+        pol, data = load_sb3_policy(f"/root/reference/rl_logs/ppo/{name}")
+        assert sum(p.numel() for p in pol.parameters()) == 18757
+        assert data.get("n_envs") == 1
+        a, logp, v = pol.act(torch.zeros(3, 79))
+        assert a.shape == (3, 2) and torch.isfinite(a).all() and torch.isfinite(v).all()
+    out = tmp_path / "roundtrip.zip"
+    save_sb3_policy(pol, str(out), num_timesteps=123)
+    pol2, d2 = load_sb3_policy(str(out))
+    assert d2["num_timesteps"] == 123
+    for k, v in pol.state_dict().items():
+        assert torch.equal(v, pol2.state_dict()[k])
