@@ -59,7 +59,7 @@ def build_consts(M: dict, *, model_kind: int, max_episode_steps: int = 1000, goa
                  spawn_qpos: Optional[np.ndarray] = None, lidar_index_map: str = "reference",
                  spawn_yaw_range: float = 0.0, spawn_xy_jitter: float = 0.0,
                  tolerance: Optional[float] = None, ls_iterations: Optional[int] = None,
-                 ls_fast_cap: int = 1, ls_fast_iters: int = 3, ls_mid_cap: int = 2, ls_mid_iters: int = 6) -> np.ndarray:
+                 ls_fast_cap: int = 1, ls_fast_iters: int = 2, ls_mid_cap: int = 2, ls_mid_iters: int = 4) -> np.ndarray:
     lay = consts_layout()
     total = sum(c for _, c in lay.values())
     blob = np.zeros(total)
@@ -149,6 +149,7 @@ def build_consts(M: dict, *, model_kind: int, max_episode_steps: int = 1000, goa
         flB.append(B)
     put("h_flR", flR)
     put("h_flB", flB)
+    put("h_flD", [1.0 / r for r in flR])
     put("h_invweight", [M["dof_invweight0"][d] for d in hinge_dof])
 
     # ---- implicit joint damping: constant part of the 8x8 Schur complement of (M~ + h B) and its inverse ------------

@@ -83,6 +83,15 @@ template <> struct Num<float> {
     const float pi = 3.14159265358979f;
     return x > pi ? x - 2.0f * pi : (x < -pi ? x + 2.0f * pi : x);
   }
+  // reciprocal without the IEEE slow path: MUFU.RCP refined by one Newton step (<= 1 ulp for normal inputs)
+  ACKB_HD static float rcp_(float x) {
+#if defined(__CUDA_ARCH__)
+    float r = __fdividef(1.0f, x);
+    return fmaf(r, fmaf(-x, r, 1.0f), r);
+#else
+    return 1.0f / x;
+#endif
+  }
   // Newton exit thresholds usable at this precision
   static constexpr float tol_floor = 1e-6f;
   static constexpr float ls_rel = 1e-3f;
@@ -100,6 +109,7 @@ template <> struct Num<double> {
   ACKB_HD static void sincos_tiny(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
   // the reference wraps with arctan2(sin, cos) (ackermann_env.py:252); kept verbatim in fp64 mode
   ACKB_HD static double wrap_pi(double x) { return atan2(sin(x), cos(x)); }
+  ACKB_HD static double rcp_(double x) { return 1.0 / x; }
   static constexpr double tol_floor = 0.0;
   static constexpr double ls_rel = 1e-10;
 };
@@ -387,7 +397,7 @@ struct Wheel {
 // wheel constants by wheel index wi (RL, RR, FL, FR)
 template <typename T>
 struct WheelK {
-  T c[3], isL, isR, J, cdiag, mu, flf, flR, flB, damp;
+  T c[3], isL, isR, J, cdiag, mu, flf, flR, flD, flB, damp;
   int hidx;
 };
 template <typename T>
@@ -400,7 +410,7 @@ ACKB_HD WheelK<T> wheel_consts(const Consts<T>& C, int wi) {
   k.J = C.h_inertia[2 + wi];
   k.cdiag = k.J + C.h_armature[2 + wi];
   k.mu = C.w_mu[wi];
-  k.flf = C.h_floss[2 + wi]; k.flR = C.h_flR[2 + wi]; k.flB = C.h_flB[2 + wi];
+  k.flf = C.h_floss[2 + wi]; k.flR = C.h_flR[2 + wi]; k.flD = C.h_flD[2 + wi]; k.flB = C.h_flB[2 + wi];
   k.damp = C.h_damping[2 + wi];
   return k;
 }
@@ -446,14 +456,15 @@ ACKB_HD T pyramid_rows(T D, T mu, const T* z, T* phi, T* q) {
 }
 
 // friction-loss (Huber) row: returns cost, force and quadratic flag
+// (select form: no divergent branches; D = 1 / R is passed in)
 template <typename T>
-ACKB_HD T floss_row(T x, T f, T R, T* force, T* quad) {
-  T rf = R * f;
-  if (x <= -rf) { *force = f; *quad = T(0); return f * (T(-0.5) * rf - x); }
-  if (x >= rf) { *force = -f; *quad = T(0); return f * (T(-0.5) * rf + x); }
-  T D = T(1) / R;
-  *force = -D * x; *quad = T(1);
-  return T(0.5) * D * x * x;
+ACKB_HD T floss_row(T x, T f, T R, T D, T* force, T* quad) {
+  const T rf = R * f;
+  const bool lo = x <= -rf, hi = x >= rf;
+  const bool lin = lo || hi;
+  *force = lo ? f : (hi ? -f : -D * x);
+  *quad = lin ? T(0) : T(1);
+  return lin ? f * (T(-0.5) * rf + Num<T>::abs_(x)) : T(0.5) * D * x * x;
 }
 
 // rows that involve only the shared dofs: steering equality, steer friction loss, steer limits
@@ -480,7 +491,7 @@ ACKB_HD T shared_rows_eval(const SharedRows<T>& s, T aL, T aR, T* fL, T* fR, T* 
   T* ho[2] = {hLL, hRR};
   for (int i = 0; i < 2; ++i) {
     T f, q;
-    cost += floss_row(a[i] - s.fl_aref[i], s.flf[i], s.flR[i], &f, &q);
+    cost += floss_row(a[i] - s.fl_aref[i], s.flf[i], s.flR[i], s.flD[i], &f, &q);
     *fo[i] += f; *ho[i] += q * s.flD[i];
     T x = s.lim_sign[i] * a[i] - s.lim_aref[i];
     bool act = x < T(0);
@@ -520,7 +531,7 @@ ACKB_HD void ldl8_factor(T* S) {
 #pragma unroll
     for (int k = 0; k < j; ++k) { v[k] = S[tri(j, k)] * d[k]; dj -= S[tri(j, k)] * v[k]; }
     d[j] = dj;
-    T dinv = T(1) / dj;
+    T dinv = Num<T>::rcp_(dj);
     S[tri(j, j)] = dinv;
 #pragma unroll
     for (int i = j + 1; i < 8; ++i) {
@@ -584,7 +595,10 @@ struct Sim {
   using N = Num<T>;
   using State = EnvState<T>;
   // contact loops are unrolled when the wheel record lives in registers (WPL == 1) and rolled when it is in shared memory
-  static constexpr int CU = (WPL == 1) ? NC : 1;
+#ifndef ACKB_CU_SMEM
+#define ACKB_CU_SMEM 1
+#endif
+  static constexpr int CU = (WPL == 1) ? NC : ACKB_CU_SMEM;
 
   // ---- B1 kinematics: normalise the quaternion (written back, like mj_kinematics), rotation, floor frame
   ACKB_HD static void kinematics(State& e, Kin<T>& k) {
@@ -732,7 +746,7 @@ struct Sim {
     } else { s.eqD = T(0); s.eq_aref = T(0); }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      s.flf[i] = C.h_floss[i]; s.flR[i] = C.h_flR[i]; s.flD[i] = T(1) / C.h_flR[i];
+      s.flf[i] = C.h_floss[i]; s.flR[i] = C.h_flR[i]; s.flD[i] = C.h_flD[i];
       s.fl_aref[i] = -C.h_flB[i] * e.dst[i];
       s.limD[i] = T(0); s.lim_sign[i] = T(1); s.lim_aref[i] = T(0);
       if (C.st_limited[i] != T(0)) {
@@ -968,27 +982,30 @@ struct Sim {
             const WheelK<T> wk = wheel_consts(C, wi);
             const WheelT& w = wh[s];
             T f, q;
-            floss_row(w.a + alpha * w.x + wk.flB * w.dsp, wk.flf, wk.flR, &f, &q);
+            floss_row(w.a + alpha * w.x + wk.flB * w.dsp, wk.flf, wk.flR, wk.flD, &f, &q);
             d[0] -= pair_weight() * f * w.x;
-            d[1] += pair_weight() * q / wk.flR * w.x * w.x;
+            d[1] += pair_weight() * q * wk.flD * w.x * w.x;
             unsigned zone = (q != T(0)) ? 1u : (f > T(0) ? 0u : 2u);
 #pragma unroll(CU)
             for (int c = 0; c < NC; ++c) {
               const Contact<T>& con = w.con[c];
-              const T* z0 = con.z; const T* z1 = con.zv;
               const T mu = wk.mu;
-              const T jr[4] = {z1[0] + mu * z1[1], z1[0] - mu * z1[1], z1[0] + mu * z1[2], z1[0] - mu * z1[2]};
-              const T xr[4] = {z0[0] + mu * z0[1] + alpha * jr[0], z0[0] - mu * z0[1] + alpha * jr[1],
-                               z0[0] + mu * z0[2] + alpha * jr[2], z0[0] - mu * z0[2] + alpha * jr[3]};
+              // rows x_r = z_n +- mu z_t at the trial point and their slopes j_r (select form, no divergent branches)
+              const T jn = con.zv[0], j1 = mu * con.zv[1], j2 = mu * con.zv[2];
+              const T xn = con.z[0] + alpha * jn, x1 = mu * con.z[1] + alpha * j1, x2 = mu * con.z[2] + alpha * j2;
+              const T jr[4] = {jn + j1, jn - j1, jn + j2, jn - j2};
+              const T xr[4] = {xn + x1, xn - x1, xn + x2, xn - x2};
+              T s0 = T(0), s1 = T(0);
               unsigned zb = 0u;
 #pragma unroll
               for (int r = 0; r < 4; ++r) {
-                const bool act = (xr[r] < T(0)) && (con.D > T(0));
-                const T dj = act ? con.D * jr[r] : T(0);
-                d[0] += dj * xr[r]; d[1] += dj * jr[r];
+                const bool act = xr[r] < T(0);
+                s0 += act ? jr[r] * xr[r] : T(0);
+                s1 += act ? jr[r] * jr[r] : T(0);
                 zb |= act ? (1u << r) : 0u;
               }
-              zone = (zone << 4) | zb;
+              d[0] += con.D * s0; d[1] += con.D * s1;       // D = 0 for an absent or excluded contact
+              zone = (zone << 4) | ((con.D > T(0)) ? zb : 0u);
             }
             d[2] += (zone != w.zone0) ? T(1) : T(0);
           }
@@ -1004,7 +1021,7 @@ struct Sim {
             else if (N::abs_(d1) <= N::ls_rel * lam2) ls_on = false;
             else {
               if (d1 < T(0)) lo = alpha; else hi = alpha;
-              T an = alpha - d1 / d2;
+              T an = alpha - d1 * N::rcp_(d2);
               if (hi >= T(0) && (an <= lo || an >= hi)) an = T(0.5) * (lo + hi);
               if (an == alpha || ls + 1 >= my_maxls) ls_on = false;
               alpha = an;
@@ -1042,7 +1059,7 @@ struct Sim {
         const WheelK<T> wk = wheel_consts(C, wi);
         WheelT& w = wh[s];
         T f, q;
-        floss_row(w.a + wk.flB * w.dsp, wk.flf, wk.flR, &f, &q);
+        floss_row(w.a + wk.flB * w.dsp, wk.flf, wk.flR, wk.flD, &f, &q);
         unsigned zone = (q != T(0)) ? 1u : (f > T(0) ? 0u : 2u);
         T gs_sp = T(0), cs = T(0);   // contact parts first (pair-summed with 8 lanes), wheel parts added below
         T Hll[6] = {T(0), T(0), T(0), T(0), T(0), T(0)};   // 00 10 11 20 21 22
@@ -1058,8 +1075,10 @@ struct Sim {
           T phi[3], qq[4], fn[3], ft1[3], ft2[3];
           contact_frame(k, c < 2 ? 0 : (int)((w.fcode >> (4 * (c - 2))) & 15u), fn, ft1, ft2);
           pyramid_rows(con.D, mu, con.z, phi, qq);
-          if (con.D > T(0)) zone = (zone << 4) | (qq[0] != T(0) ? 1u : 0u) | (qq[1] != T(0) ? 2u : 0u) | (qq[2] != T(0) ? 4u : 0u) | (qq[3] != T(0) ? 8u : 0u);
-          else zone <<= 4;
+          {
+            const unsigned zb = (qq[0] != T(0) ? 1u : 0u) | (qq[1] != T(0) ? 2u : 0u) | (qq[2] != T(0) ? 4u : 0u) | (qq[3] != T(0) ? 8u : 0u);
+            zone = (zone << 4) | ((con.D > T(0)) ? zb : 0u);
+          }
           // S3 = D F^T W F with W the active-row weights on (n, t1, t2); symmetric 3x3 in the body frame
           const T W00 = qq[0] + qq[1] + qq[2] + qq[3], W01 = mu * (qq[0] - qq[1]), W02 = mu * (qq[2] - qq[3]);
           const T W11 = mu * mu * (qq[0] + qq[1]), W22 = mu * mu * (qq[2] + qq[3]);
@@ -1124,7 +1143,7 @@ struct Sim {
           for (int i = 0; i < 3; ++i) { bl[i] = Tm::pair_sum(bl[i]); ba[i] = Tm::pair_sum(ba[i]); }
         }
         gs_sp += wk.J * (w.ax * a_sh[3] + w.ay * a_sh[4]) + wk.cdiag * w.a - w.tau - f;
-        cs += wk.cdiag + q / wk.flR;
+        cs += wk.cdiag + q * wk.flD;
         ba[0] += wk.J * w.ax; ba[1] += wk.J * w.ay;
         if (phase == 0) w.zone0 = zone;
         w.g = gs_sp; w.cw = cs;
@@ -1147,7 +1166,7 @@ struct Sim {
           part[tri(7, j)] += wk.isR * Hsl[j]; part[tri(7, 3 + j)] += wk.isR * Hsa[j];
         }
         part[tri(6, 6)] += wk.isL * Hss; part[tri(7, 7)] += wk.isR * Hss;
-        const T ci = pair_weight() / cs;     // the Schur terms of a wheel are counted once per team
+        const T ci = pair_weight() * N::rcp_(cs);     // the Schur terms of a wheel are counted once per team
 #pragma unroll
         for (int a = 0; a < 8; ++a) {
           const T bc = b8[a] * ci;
@@ -1187,7 +1206,7 @@ struct Sim {
 #pragma unroll
           for (int a = 0; a < 6; ++a) dotb += w.b[a] * y_sh[a];
           dotb += w.b[6] * ((wi == 2) ? y_sh[6] : ((wi == 3) ? y_sh[7] : T(0)));
-          w.x = -(w.g - dotb) / w.cw;
+          w.x = -(w.g - dotb) * N::rcp_(w.cw);
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) x_sh[i] = -y_sh[i];

@@ -378,9 +378,14 @@ int launch_one(ackb_handle* h, DevState<T>& st, const StepArgs& a, cudaStream_t 
 template <typename T>
 int launch_step(ackb_handle* h, DevState<T>& st, const StepArgs& a, cudaStream_t stream, bool is_reset) {
   const bool scene = h->consts_host[0] != 0.0;   // model_kind: the obstacle scene needs the two box-contact slots per wheel
+#ifdef ACKB_TUNE_MIN   // tuning builds (tools/gpu/build_variant.sh): fp32 flat-floor kernels only, to keep compile times short
+  if constexpr (sizeof(T) == 8) return fail(h, ACKB_ERR_ARG, "tuning build: fp32 only");
+  else return h->lanes >= 4 ? launch_one<T, 4, 2>(h, st, a, stream, is_reset) : launch_one<T, 1, 2>(h, st, a, stream, is_reset);
+#else
   if (h->lanes == 8 && !scene) return launch_one<T, 8, 1>(h, st, a, stream, is_reset);   // one lane per floor contact (flat-floor model)
   if (h->lanes >= 4) return scene ? launch_one<T, 4, 4>(h, st, a, stream, is_reset) : launch_one<T, 4, 2>(h, st, a, stream, is_reset);
   return scene ? launch_one<T, 1, 4>(h, st, a, stream, is_reset) : launch_one<T, 1, 2>(h, st, a, stream, is_reset);
+#endif
 }
 }  // namespace
 
