@@ -55,7 +55,17 @@ ACKB_HD T mjclip(T x, T lo, T hi) { return x < lo ? lo : (x > hi ? hi : x); }  /
 template <typename T> struct Num;
 template <> struct Num<float> {
   static constexpr float minval = 1e-15f;
-  ACKB_HD static float sqrt_(float x) { return sqrtf(x); }
+  // device: MUFU.RSQ refined by one Newton step (no IEEE slow path; <= 1 ulp for normal inputs, sqrt(0) = 0, NaN propagates)
+  ACKB_HD static float sqrt_(float x) {
+#if defined(__CUDA_ARCH__)
+    const float r = rsqrtf(x);
+    float s = x * r;
+    s = fmaf(fmaf(-s, s, x), 0.5f * r, s);
+    return x == 0.0f ? 0.0f : s;
+#else
+    return sqrtf(x);
+#endif
+  }
   ACKB_HD static float abs_(float x) { return fabsf(x); }
   ACKB_HD static float sin_(float x) { return sinf(x); }
   ACKB_HD static float cos_(float x) { return cosf(x); }
@@ -268,13 +278,13 @@ ACKB_HD T impedance(const T* solimp, T pos) {
   T d0 = mjclip(solimp[0], lo, hi), d1 = mjclip(solimp[1], lo, hi), width = mjmax(T(0), solimp[2]);
   T mid = mjclip(solimp[3], lo, hi), power = mjmax(T(1), solimp[4]);
   if (d0 == d1 || width <= Num<T>::minval) return T(0.5) * (d0 + d1);
-  T x = Num<T>::abs_(pos) / width;
+  T x = Num<T>::abs_(pos) * Num<T>::rcp_(width);
   if (x >= T(1)) return d1;
   if (x <= T(0)) return d0;
   T y;
   // solimp power is 1 or 2 in both models (checked by the model compiler); other powers are not compiled in
   if (power == T(1)) y = x;
-  else y = (x <= mid) ? x * x / mid : T(1) - (T(1) - x) * (T(1) - x) / (T(1) - mid);
+  else y = (x <= mid) ? x * x * Num<T>::rcp_(mid) : T(1) - (T(1) - x) * (T(1) - x) * Num<T>::rcp_(T(1) - mid);
   return d0 + y * (d1 - d0);
 }
 
@@ -521,6 +531,8 @@ ACKB_HD unsigned shared_rows_zone(const SharedRows<T>& s, T aL, T aR) {
 // LDL^T of a packed symmetric positive definite 8x8, in registers (fully unrolled).
 // On exit the strict lower triangle holds L and the diagonal holds 1/d.
 // ------------------------------------------------------------------------------------------------
+// All loops have constant trip counts (the triangular bounds are expressed as conditions on the unrolled indices) so
+// that every access has a compile-time index and S stays in registers.
 template <typename T>
 ACKB_HD void ldl8_factor(T* S) {
   T d[8];
@@ -529,17 +541,20 @@ ACKB_HD void ldl8_factor(T* S) {
     T v[8];
     T dj = S[tri(j, j)];
 #pragma unroll
-    for (int k = 0; k < j; ++k) { v[k] = S[tri(j, k)] * d[k]; dj -= S[tri(j, k)] * v[k]; }
+    for (int k = 0; k < 8; ++k)
+      if (k < j) { v[k] = S[tri(j, k)] * d[k]; dj -= S[tri(j, k)] * v[k]; }
     d[j] = dj;
     T dinv = Num<T>::rcp_(dj);
     S[tri(j, j)] = dinv;
 #pragma unroll
-    for (int i = j + 1; i < 8; ++i) {
-      T s = S[tri(i, j)];
+    for (int i = 0; i < 8; ++i)
+      if (i > j) {
+        T s = S[tri(i, j)];
 #pragma unroll
-      for (int k = 0; k < j; ++k) s -= S[tri(i, k)] * v[k];
-      S[tri(i, j)] = s * dinv;
-    }
+        for (int k = 0; k < 8; ++k)
+          if (k < j) s -= S[tri(i, k)] * v[k];
+        S[tri(i, j)] = s * dinv;
+      }
   }
 }
 template <typename T>
@@ -547,13 +562,15 @@ ACKB_HD void ldl8_solve(const T* S, T* x /* in: rhs, out: solution */) {
 #pragma unroll
   for (int i = 1; i < 8; ++i)
 #pragma unroll
-    for (int k = 0; k < i; ++k) x[i] -= S[tri(i, k)] * x[k];
+    for (int k = 0; k < 8; ++k)
+      if (k < i) x[i] -= S[tri(i, k)] * x[k];
 #pragma unroll
   for (int i = 0; i < 8; ++i) x[i] *= S[tri(i, i)];
 #pragma unroll
   for (int i = 6; i >= 0; --i)
 #pragma unroll
-    for (int k = i + 1; k < 8; ++k) x[i] -= S[tri(k, i)] * x[k];
+    for (int k = 0; k < 8; ++k)
+      if (k > i) x[i] -= S[tri(k, i)] * x[k];
 }
 
 // Philox4x32-10 counter-based generator (Salmon et al. 2011), used for goals, spawn jitter and the
@@ -596,7 +613,7 @@ struct Sim {
   using State = EnvState<T>;
   // contact loops are unrolled when the wheel record lives in registers (WPL == 1) and rolled when it is in shared memory
 #ifndef ACKB_CU_SMEM
-#define ACKB_CU_SMEM 1
+#define ACKB_CU_SMEM 2   // contacts of a wheel unrolled (ILP), wheels rolled (code size)
 #endif
   static constexpr int CU = (WPL == 1) ? NC : ACKB_CU_SMEM;
 
@@ -604,7 +621,7 @@ struct Sim {
   ACKB_HD static void kinematics(State& e, Kin<T>& k) {
     T qn = N::sqrt_(e.q[0] * e.q[0] + e.q[1] * e.q[1] + e.q[2] * e.q[2] + e.q[3] * e.q[3]);
     if (qn < N::minval) { e.q[0] = T(1); e.q[1] = e.q[2] = e.q[3] = T(0); }
-    else { T inv = T(1) / qn; for (int i = 0; i < 4; ++i) e.q[i] *= inv; }
+    else { T inv = N::rcp_(qn); for (int i = 0; i < 4; ++i) e.q[i] *= inv; }
     const T w = e.q[0], x = e.q[1], y = e.q[2], z = e.q[3];
     k.R[0] = w * w + x * x - y * y - z * z; k.R[1] = T(2) * (x * y - w * z); k.R[2] = T(2) * (x * z + w * y);
     k.R[3] = T(2) * (x * y + w * z); k.R[4] = w * w - x * x + y * y - z * z; k.R[5] = T(2) * (y * z - w * x);
@@ -632,8 +649,9 @@ struct Sim {
     for (int i = 0; i < 3; ++i) vec[i] = ax[i] * prjaxis - k.n[i];
     T len = N::sqrt_(dot3(vec, vec));
     if (len < N::minval) { diag.unsupported = 1; len = T(1); }  // disk parallel to the floor
+    const T rlen = r * N::rcp_(len);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) vec[i] *= r / len;
+    for (int i = 0; i < 3; ++i) vec[i] *= rlen;
     const T prjvec = dot3(vec, k.n);
     ax[0] *= hl; ax[1] *= hl;
     prjaxis *= hl;
@@ -654,8 +672,8 @@ struct Sim {
       con.x[2] = wk.c[2] + vec[2] - k.n[2] * dd * T(0.5);
       const bool active = has && (dd < T(0));  // dist >= includemargin(0): counted but excluded
       const T imp = impedance(&C.w_solimp[5 * wi], dd);
-      const T R0 = mjmax(N::minval, (T(1) - imp) / imp * C.w_tran[wi] * (T(1) + mu * mu));
-      con.D = active ? T(1) / (T(2) * C.w_mureg2[wi] * R0) : T(0);
+      const T R0 = mjmax(N::minval, (T(1) - imp) * N::rcp_(imp) * C.w_tran[wi] * (T(1) + mu * mu));
+      con.D = active ? N::rcp_(T(2) * C.w_mureg2[wi] * R0) : T(0);
       T u[3], wv[2], vel[3];
       contact_cols(w, wk, con.x, u, wv);
       project_point(k.n, k.t1, k.t2, con.x, u, wv, vb, e.om, w.dsp, dsteer, vel);
@@ -722,8 +740,8 @@ struct Sim {
       fcode |= (unsigned)code << (4 * nfound);
       const T mu = wk.mu;
       const T imp = impedance(&C.w_solimp[5 * wi], best);
-      const T R0 = mjmax(N::minval, (T(1) - imp) / imp * C.w_tran[wi] * (T(1) + mu * mu));
-      con.D = (best < T(0)) ? T(1) / (T(2) * C.w_mureg2[wi] * R0) : T(0);
+      const T R0 = mjmax(N::minval, (T(1) - imp) * N::rcp_(imp) * C.w_tran[wi] * (T(1) + mu * mu));
+      con.D = (best < T(0)) ? N::rcp_(T(2) * C.w_mureg2[wi] * R0) : T(0);
       T u[3], wv[2], vel[3], fn[3], ft1[3], ft2[3];
       contact_cols(w, wk, con.x, u, wv);
       contact_frame(k, code, fn, ft1, ft2);
@@ -740,8 +758,8 @@ struct Sim {
     if (C.has_eq[0] != T(0)) {
       T pos = e.st[0] - e.st[1];
       T imp = impedance(C.eq_solimp, pos);
-      T R = mjmax(N::minval, (T(1) - imp) / imp * C.eq_invweight[0]);
-      s.eqD = T(1) / R;
+      T R = mjmax(N::minval, (T(1) - imp) * N::rcp_(imp) * C.eq_invweight[0]);
+      s.eqD = N::rcp_(R);
       s.eq_aref = -C.eq_B[0] * (e.dst[0] - e.dst[1]) - C.eq_K[0] * imp * pos;
     } else { s.eqD = T(0); s.eq_aref = T(0); }
 #pragma unroll
@@ -756,8 +774,8 @@ struct Sim {
         else if (dhi < T(0)) { pos = dhi; sign = T(-1); }
         if (sign != T(0)) {
           T imp = impedance(&C.lim_solimp[5 * i], pos);
-          T R = mjmax(N::minval, (T(1) - imp) / imp * C.h_invweight[i]);
-          s.limD[i] = T(1) / R; s.lim_sign[i] = sign;
+          T R = mjmax(N::minval, (T(1) - imp) * N::rcp_(imp) * C.h_invweight[i]);
+          s.limD[i] = N::rcp_(R); s.lim_sign[i] = sign;
           s.lim_aref[i] = -C.lim_B[i] * (sign * e.dst[i]) - C.lim_K[i] * imp * pos;
         }
       }
@@ -901,8 +919,8 @@ struct Sim {
         tau_sh[i] = -(t3[i] - C.mass[0] * gb[i]);
         tau_sh[3 + i] = -(t0[i] + bpart[3 + i] - t1[i]);
       }
-#pragma unroll 1
-      for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int i = 0; i < 2; ++i)   // unrolled: a rolled loop would index tau_sh / bpart / e.st dynamically and push them to local memory
         tau_sh[6 + i] = -C.h_damping[i] * e.dst[i] - bpart[6 + i] + actuator_force(C, ctrl, i, e.st[i], e.dst[i]);
     }
 
@@ -1255,7 +1273,8 @@ struct Sim {
         G[f][f] += T(1) / C.euler_kappa[f];
       }
       const T det = G[0][0] * G[1][1] - G[0][1] * G[1][0];
-      const T m0 = (G[1][1] * ut[0] - G[0][1] * ut[1]) / det, m1 = (G[0][0] * ut[1] - G[1][0] * ut[0]) / det;
+      const T idet = N::rcp_(det);
+      const T m0 = (G[1][1] * ut[0] - G[0][1] * ut[1]) * idet, m1 = (G[0][0] * ut[1] - G[1][0] * ut[0]) * idet;
       const T vx = ux[0] * m0 + ux[1] * m1, vy = uy[0] * m0 + uy[1] * m1;   // U m, angular x / y rows
 #pragma unroll
       for (int i = 0; i < 8; ++i)
@@ -1301,7 +1320,7 @@ struct Sim {
     {
       T wn = N::sqrt_(dot3(e.om, e.om));
       T ax[3] = {T(1), T(0), T(0)};
-      if (wn >= N::minval) { ax[0] = e.om[0] / wn; ax[1] = e.om[1] / wn; ax[2] = e.om[2] / wn; }
+      if (wn >= N::minval) { const T iw = N::rcp_(wn); ax[0] = e.om[0] * iw; ax[1] = e.om[1] * iw; ax[2] = e.om[2] * iw; }
       T half = T(0.5) * h * wn, sn, cs;
       N::sincos_tiny(half, &sn, &cs);
       T r0 = cs, r1 = ax[0] * sn, r2 = ax[1] * sn, r3 = ax[2] * sn;
@@ -1324,7 +1343,7 @@ struct Sim {
                      e.p[2] + k.R[6] * o[0] + k.R[7] * o[1] + k.R[8] * o[2]};
     const T dw[3] = {k.R[0] * cb + k.R[1] * sb, k.R[3] * cb + k.R[4] * sb, lvz};
     if (!(lvz > -N::minval)) {
-      T x = -(ow[2] - C.plane_z[0]) / lvz;
+      T x = -(ow[2] - C.plane_z[0]) * N::rcp_(lvz);
       if (x >= T(0)) {
         T px = ow[0] + x * dw[0], py = ow[1] + x * dw[1];
         if ((C.plane_half[0] <= T(0) || N::abs_(px) <= C.plane_half[0]) && (C.plane_half[1] <= T(0) || N::abs_(py) <= C.plane_half[1])) best = x;

@@ -143,12 +143,12 @@ struct EnvOps {
   // so that the sink's storage may alias the wheel records.
   template <class Sink, class Emit>
   ACKB_HD static void step_env(const Consts<T>& C, State& e, WheelT* wh, Episode<T>& ep, float a0, float a1, int frame_skip, int lane,
-                               Sink& sink, Emit&& emit, StepOut<T>& out, StepDiag& diag, DebugTap<T>* tap) {
+                               Sink& sink, Emit&& emit, StepOut<T>& out, StepDiag& diag, DebugTap<T>* tap, bool cta_sync = false) {
     T ctrl[4];
     action_to_ctrl<T>(C, a0, a1, ctrl);
     T dist = T(0), minl = T(0);
     for (int s = 0; s < frame_skip; ++s) {
-      Tm::block_sync();
+      if (cta_sync) Tm::block_sync();   // CTA-uniform flag (see Team::block_sync)
       Kin<T> k;
       S::kinematics(e, k);
       if (s == frame_skip - 1) {

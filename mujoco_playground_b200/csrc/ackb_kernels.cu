@@ -8,6 +8,7 @@
 // coalesced stores, auto-reset fused.  No tensor cores: the largest dense object is 8 x 8.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -48,6 +49,7 @@ struct StepArgs {
   unsigned long long seed;
   uint32_t step_index;
   int frame_skip, auto_reset, obs_dim;
+  int cta_sync;   // multi-lane kernels: re-converge the CTA once per substep (pays off only when several warps share a scheduler)
 };
 
 template <typename T>
@@ -169,7 +171,7 @@ __global__ void __launch_bounds__(Geo<T, LANES, NC>::kBlock, Geo<T, LANES, NC>::
 
   StepOut<T> out;
   StepDiag diag{0, 0, 0};
-  E::step_env(C, e, wh, ep, a0, a1, a.frame_skip, lane, sink, emit, out, diag, (DebugTap<T>*)nullptr);
+  E::step_env(C, e, wh, ep, a0, a1, a.frame_skip, lane, sink, emit, out, diag, (DebugTap<T>*)nullptr, a.cta_sync != 0);
   __syncwarp();
 
   // contact count of the last substep, summed over the lanes of the environment
@@ -294,6 +296,8 @@ thread_local std::string g_last_error;
 // ------------------------------------------------------------------------------------------------
 struct ackb_handle {
   int n = 0, device = 0, dtype = ACKB_F32, lanes = 4, obs_dim = 0;
+  int num_sms = 148;
+  int cta_sync = -1;            // -1 = auto (by grid size), 0 / 1 forced through ACKB_CTA_SYNC (tuning)
   unsigned long long seed = 0;
   uint32_t step_index = 0;
   unsigned long long stat_steps = 0;
@@ -366,9 +370,11 @@ int launch_one(ackb_handle* h, DevState<T>& st, const StepArgs& a, cudaStream_t 
     reset_kernel<T, LANES><<<grid, Geo<T, LANES, 2>::kBlock, smem, stream>>>(st, a);
   } else {
     const size_t smem = G::smem_bytes(a.obs_dim);
+    StepArgs a2 = a;
+    a2.cta_sync = h->cta_sync >= 0 ? h->cta_sync : 1;   // measured on B200: faster at every batch size from 4096 to 131072 envs
     static bool attr_done = false;
     if (!attr_done && smem > 48 * 1024) { CK(cudaFuncSetAttribute(step_kernel<T, LANES, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done = true; }
-    step_kernel<T, LANES, NC><<<grid, G::kBlock, smem, stream>>>(st, a);
+    step_kernel<T, LANES, NC><<<grid, G::kBlock, smem, stream>>>(st, a2);
   }
   h->launches++;
   CK(cudaGetLastError());
@@ -414,6 +420,8 @@ int ackb_create(const double* consts, size_t consts_len, int num_envs, int devic
   memcpy(h->consts_host, consts, sizeof(double) * kNumConsts);
   h->obs_dim = (int)reinterpret_cast<const Consts<double>*>(consts)->nbeam[0] + 7;
   CK(cudaSetDevice(device));
+  CK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
+  if (const char* ev = getenv("ACKB_CTA_SYNC")) h->cta_sync = atoi(ev);
   const size_t n = num_envs;
   const size_t bytes = (13 + 12 + 12 + 2 + 2) * n * h->elem + 3 * n * 4;
   CK(cudaMalloc(&h->state, bytes));
