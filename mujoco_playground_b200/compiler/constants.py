@@ -54,12 +54,39 @@ def _mix(M, g1, g2):
     return fr, solref, solimp
 
 
+def _box_grid(centres: np.ndarray, half: np.ndarray):
+    """Occupancy grid of identical axis-aligned boxes, or None if they do not sit on a lattice of box-sized cells
+    listed in (x, y) lexicographic order (the order fixes the contact slot order of wheel-box contacts)."""
+    pitch = 2.0 * float(half[0])
+    if not np.isclose(half[0], half[1]) or pitch <= 0:
+        return None
+    x0, y0 = centres[:, 0].min() - half[0], centres[:, 1].min() - half[1]
+    fx, fy = (centres[:, 0] - x0) / pitch - 0.5, (centres[:, 1] - y0) / pitch - 0.5
+    ix, iy = np.rint(fx).astype(int), np.rint(fy).astype(int)
+    if not (np.allclose(fx, ix, atol=1e-9) and np.allclose(fy, iy, atol=1e-9)):
+        return None
+    nx, ny = int(ix.max()) + 1, int(iy.max()) + 1
+    if nx > 24 or ny > 16 or len(set(zip(ix.tolist(), iy.tolist()))) != len(ix):
+        return None
+    order = sorted(range(len(ix)), key=lambda i: (ix[i], iy[i]))
+    if order != list(range(len(ix))):
+        return None
+    # cell centres must reproduce the box centres exactly (the kernel recomputes them from the indices)
+    if not (np.array_equal(x0 + (ix + 0.5) * pitch, centres[:, 0]) and np.array_equal(y0 + (iy + 0.5) * pitch, centres[:, 1])):
+        return None
+    rows = np.zeros(16)
+    for a, b in zip(ix, iy):
+        rows[b] += float(1 << int(a))
+    return dict(x0=x0, y0=y0, pitch=pitch, nx=nx, ny=ny, rows=rows)
+
+
 def build_consts(M: dict, *, model_kind: int, max_episode_steps: int = 1000, goal_distance_threshold: float = 0.5,
                  collision_threshold: float = 0.15, max_linear_velocity: float = 1.0, max_angular_velocity: float = 1.0,
                  spawn_qpos: Optional[np.ndarray] = None, lidar_index_map: str = "reference",
                  spawn_yaw_range: float = 0.0, spawn_xy_jitter: float = 0.0,
                  tolerance: Optional[float] = None, ls_iterations: Optional[int] = None,
-                 ls_fast_cap: int = 1, ls_fast_iters: int = 2, ls_mid_cap: int = 2, ls_mid_iters: int = 4) -> np.ndarray:
+                 ls_fast_cap: int = 1, ls_fast_iters: int = 2, ls_mid_cap: int = 2, ls_mid_iters: int = 4,
+                 use_box_grid: bool = True) -> np.ndarray:
     lay = consts_layout()
     total = sum(c for _, c in lay.values())
     blob = np.zeros(total)
@@ -241,6 +268,11 @@ def build_consts(M: dict, *, model_kind: int, max_episode_steps: int = 1000, goa
         put("nbox", len(boxes)); put("box_half", hs); put("box_z", M["geom_pos"][boxes[0]][2])
         put("box_cx", [M["geom_pos"][g][0] + M["body_pos"][M["geom_bodyid"][g]][0] for g in boxes])
         put("box_cy", [M["geom_pos"][g][1] + M["body_pos"][M["geom_bodyid"][g]][1] for g in boxes])
+        grid = _box_grid(np.array([[M["geom_pos"][g][0] + M["body_pos"][M["geom_bodyid"][g]][0],
+                                    M["geom_pos"][g][1] + M["body_pos"][M["geom_bodyid"][g]][1]] for g in boxes]), np.asarray(hs, float))
+        if grid is not None and use_box_grid:
+            put("grid_on", 1); put("grid_x0", grid["x0"]); put("grid_y0", grid["y0"]); put("grid_pitch", grid["pitch"])
+            put("grid_nx", grid["nx"]); put("grid_ny", grid["ny"]); put("grid_rows", grid["rows"])
 
     # plate hull points (only if the plates can collide with the floor)
     pts = []

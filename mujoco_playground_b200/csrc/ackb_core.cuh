@@ -616,6 +616,16 @@ struct Sim {
 #define ACKB_CU_SMEM 2   // contacts of a wheel unrolled (ILP), wheels rolled (code size)
 #endif
   static constexpr int CU = (WPL == 1) ? NC : ACKB_CU_SMEM;
+  // Contact loops of the solver: slots are visited in groups of CSTEP; groups at or beyond `ncs` (a warp-uniform count: 2 when no
+  // environment of the warp has a wheel-box contact in this substep) are skipped.  Register records: fully unrolled (static
+  // indices); shared-memory records: the group loop stays rolled.
+  static constexpr int CSTEP = (NC >= 2) ? ((WPL == 1) ? 2 : (ACKB_CU_SMEM >= 2 ? 2 : 1)) : 1;
+  static constexpr int CO = (WPL == 1) ? (NC / CSTEP) : 1;
+#define ACKB_CONTACTS_BEGIN(c)                                                     \
+  _Pragma("unroll(CO)") for (int c##_g = 0; c##_g < NC; c##_g += CSTEP) {          \
+    if (c##_g < ncs) {                                                             \
+      _Pragma("unroll") for (int c = c##_g; c < c##_g + CSTEP; ++c) {
+#define ACKB_CONTACTS_END }}}
 
   // ---- B1 kinematics: normalise the quaternion (written back, like mj_kinematics), rotation, floor frame
   ACKB_HD static void kinematics(State& e, Kin<T>& k) {
@@ -704,9 +714,27 @@ struct Sim {
     int nfound = 0;
     unsigned fcode = 0u;
     if (NC > 2) { w.con[NC - 2].D = T(0); w.con[NC - 1].D = T(0); for (int i = 0; i < 3; ++i) { w.con[NC - 2].x[i] = w.con[NC - 1].x[i] = T(0); w.con[NC - 2].z[i] = w.con[NC - 1].z[i] = T(0); } }
+    // candidates: every box (no grid), or the occupied cells under the wheel's bounding square, visited in box order
+    const bool grid = C.grid_on[0] != T(0);
+    int gx0 = 0, gy0 = 0, gny = 1, ncand = nbox;
+    if (grid) {
+      const T ip = N::rcp_(C.grid_pitch[0]);
+      gx0 = (int)floor((cw[0] - reach - C.grid_x0[0]) * ip); gy0 = (int)floor((cw[1] - reach - C.grid_y0[0]) * ip);
+      const int gx1 = (int)floor((cw[0] + reach - C.grid_x0[0]) * ip), gy1 = (int)floor((cw[1] + reach - C.grid_y0[0]) * ip);
+      gny = gy1 - gy0 + 1;
+      ncand = (gx1 - gx0 + 1) * gny;
+      if (ncand > 16) ncand = 16;   // reach << pitch: 1 to 4 cells
+    }
 #pragma unroll 1
-    for (int bi = 0; bi < nbox; ++bi) {
-      const T c[3] = {cw[0] - C.box_cx[bi], cw[1] - C.box_cy[bi], cw[2] - C.box_z[0]};
+    for (int bi = 0; bi < ncand; ++bi) {
+      T bcx, bcy;
+      if (grid) {
+        const int ix = gx0 + bi / gny, iy = gy0 + bi % gny;
+        if (ix < 0 || iy < 0 || ix >= (int)C.grid_nx[0] || iy >= (int)C.grid_ny[0]) continue;
+        if (!(((unsigned)C.grid_rows[iy] >> ix) & 1u)) continue;
+        bcx = C.grid_x0[0] + (T(ix) + T(0.5)) * C.grid_pitch[0]; bcy = C.grid_y0[0] + (T(iy) + T(0.5)) * C.grid_pitch[0];
+      } else { bcx = C.box_cx[bi]; bcy = C.box_cy[bi]; }
+      const T c[3] = {cw[0] - bcx, cw[1] - bcy, cw[2] - C.box_z[0]};
       if (N::abs_(c[0]) > C.box_half[0] + reach || N::abs_(c[1]) > C.box_half[1] + reach || N::abs_(c[2]) > C.box_half[2] + reach) continue;
       T best = T(-1e30), bp[3] = {T(0), T(0), T(0)};
       int bk = 0, bs = 1;
@@ -730,9 +758,10 @@ struct Sim {
       diag.ncon += 1;
       if (nfound >= 2) { diag.unsupported = 1; continue; }
       // contact point midway between the surfaces, world -> body frame
-      T pw[3] = {bp[0] + C.box_cx[bi] - e.p[0], bp[1] + C.box_cy[bi] - e.p[1], bp[2] + C.box_z[0] - e.p[2]};
+      T pw[3] = {bp[0] + bcx - e.p[0], bp[1] + bcy - e.p[1], bp[2] + C.box_z[0] - e.p[2]};
       pw[bk] -= T(bs) * best * T(0.5);
-      Contact<T>& con = w.con[NC > 2 ? 2 + nfound : 0];
+      Contact<T> con;   // filled here, then copied to slot NC-2 or NC-1 with static indices (keeps register records in registers)
+      con.zv[0] = con.zv[1] = con.zv[2] = T(0);
 #pragma unroll
       for (int i = 0; i < 3; ++i) con.x[i] = k.R[i] * pw[0] + k.R[3 + i] * pw[1] + k.R[6 + i] * pw[2];
       // normal from the wheel to the box is -s e_k:  +x 1, -x 2, +y 3, -y 4, -z 5 (+z: wheel below a box, never happens)
@@ -749,6 +778,7 @@ struct Sim {
       con.z[0] = C.w_B[wi] * vel[0] + C.w_K[wi] * imp * best;
       con.z[1] = C.w_B[wi] * vel[1];
       con.z[2] = C.w_B[wi] * vel[2];
+      if (NC > 2) { if (nfound == 0) w.con[NC > 2 ? NC - 2 : 0] = con; else w.con[NC - 1] = con; }
       ++nfound;
     }
     w.fcode = fcode;
@@ -886,6 +916,14 @@ struct Sim {
       warm_ok = warm_ok && (N::abs_(w.warm) <= T(1e10));
     }
     Tm::sum_n(bpart);
+    // number of contact slots the solver has to look at (warp-uniform): the box slots only if some environment of the warp uses them
+    int ncs = NC;
+    if (NC > 2) {
+      bool has_box = false;
+#pragma unroll 1
+      for (int s = 0; s < WPL; ++s) has_box = has_box || (wh[s].con[NC - 2].D > T(0)) || (wh[s].con[NC - 1].D > T(0));
+      ncs = Tm::any(has_box) ? NC : 2;
+    }
     // plate hull vs floor: flagged only (35 mm clearance; reachable only after a roll-over)
     if (lane == 0) {
       const int nh = (int)C.nhull[0];
@@ -969,14 +1007,13 @@ struct Sim {
           acc[0] += pwt * wk.J * w.ax * w.x; acc[1] += pwt * wk.J * w.ay * w.x;
           acc[3] += pwt * w.x * Mv_sp; acc[4] += pwt * w.x * (Ma_sp - w.tau);
           const T ast = wk.isL * x_sh[6] + wk.isR * x_sh[7];
-#pragma unroll(CU)
-          for (int c = 0; c < NC; ++c) {
+          ACKB_CONTACTS_BEGIN(c)
             Contact<T>& con = w.con[c];
             T u[3], wv[2], fn[3], ft1[3], ft2[3];
             contact_cols(w, wk, con.x, u, wv);
             contact_frame(k, c < 2 ? 0 : (int)((w.fcode >> (4 * (c - 2))) & 15u), fn, ft1, ft2);
             project_point(fn, ft1, ft2, con.x, u, wv, x_sh, x_sh + 3, w.x, ast, con.zv);
-          }
+          ACKB_CONTACTS_END
         }
         Tm::sum_n(acc);
         T Mv_sh[8];
@@ -1004,8 +1041,7 @@ struct Sim {
             d[0] -= pair_weight() * f * w.x;
             d[1] += pair_weight() * q * wk.flD * w.x * w.x;
             unsigned zone = (q != T(0)) ? 1u : (f > T(0) ? 0u : 2u);
-#pragma unroll(CU)
-            for (int c = 0; c < NC; ++c) {
+            ACKB_CONTACTS_BEGIN(c)
               const Contact<T>& con = w.con[c];
               const T mu = wk.mu;
               // rows x_r = z_n +- mu z_t at the trial point and their slopes j_r (select form, no divergent branches)
@@ -1018,13 +1054,14 @@ struct Sim {
 #pragma unroll
               for (int r = 0; r < 4; ++r) {
                 const bool act = xr[r] < T(0);
-                s0 += act ? jr[r] * xr[r] : T(0);
-                s1 += act ? jr[r] * jr[r] : T(0);
+                const T jm = act ? jr[r] : T(0);      // one select, then two fused multiply-adds
+                s0 += jm * xr[r];
+                s1 += jm * jr[r];
                 zb |= act ? (1u << r) : 0u;
               }
               d[0] += con.D * s0; d[1] += con.D * s1;       // D = 0 for an absent or excluded contact
               zone = (zone << 4) | ((con.D > T(0)) ? zb : 0u);
-            }
+            ACKB_CONTACTS_END
             d[2] += (zone != w.zone0) ? T(1) : T(0);
           }
           Tm::sum_n(d);
@@ -1054,10 +1091,10 @@ struct Sim {
           for (int s = 0; s < WPL; ++s) {
             WheelT& w = wh[s];
             w.a += alpha * w.x;
-#pragma unroll(CU)
-            for (int c = 0; c < NC; ++c)
+            ACKB_CONTACTS_BEGIN(c)
 #pragma unroll
               for (int i = 0; i < 3; ++i) w.con[c].z[i] += alpha * w.con[c].zv[i];
+            ACKB_CONTACTS_END
           }
           first = false;
           if (exact || iter >= maxit) phase = 2;
@@ -1087,8 +1124,7 @@ struct Sim {
         T bl[3] = {T(0), T(0), T(0)}, ba[3] = {T(0), T(0), T(0)}, bs = T(0);
         T gl[3] = {T(0), T(0), T(0)}, ga[3] = {T(0), T(0), T(0)}, gst = T(0);
         const T mu = wk.mu;
-#pragma unroll(CU)
-        for (int c = 0; c < NC; ++c) {
+        ACKB_CONTACTS_BEGIN(c)
           const Contact<T>& con = w.con[c];
           T phi[3], qq[4], fn[3], ft1[3], ft2[3];
           contact_frame(k, c < 2 ? 0 : (int)((w.fcode >> (4 * (c - 2))) & 15u), fn, ft1, ft2);
@@ -1154,7 +1190,7 @@ struct Sim {
           for (int i = 0; i < 3; ++i) { gl[i] -= Phi[i]; ga[i] -= XF[i]; }
           gst -= wv[0] * Phi[0] + wv[1] * Phi[1];
           gs_sp -= dot3(u, Phi);
-        }
+        ACKB_CONTACTS_END
         if (PAIR) {
           gs_sp = Tm::pair_sum(gs_sp); cs = Tm::pair_sum(cs); bs = Tm::pair_sum(bs);
 #pragma unroll
@@ -1332,6 +1368,26 @@ struct Sim {
     }
   }
 
+  // nearest intersection (ray parameter >= 0) of the ray lp + t dw with one obstacle box centred at the origin, or -1
+  ACKB_HD static T box_ray(const Consts<T>& C, T lx, T ly, T lz, const T* dw) {
+    const T lp[3] = {lx, ly, lz};
+    T best = T(-1);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      if (N::abs_(dw[i]) <= N::minval) continue;
+      const int a = (i + 1) % 3, b = (i + 2) % 3;
+      const T id = N::rcp_(dw[i]);
+#pragma unroll
+      for (int side = -1; side <= 1; side += 2) {
+        const T sol = (T(side) * C.box_half[i] - lp[i]) * id;
+        const T pa = lp[a] + sol * dw[a], pb = lp[b] + sol * dw[b];
+        const bool ok = sol >= T(0) && N::abs_(pa) <= C.box_half[a] && N::abs_(pb) <= C.box_half[b] && (best < T(0) || sol < best);
+        best = ok ? sol : best;
+      }
+    }
+    return best;
+  }
+
   // ---- B9 rangefinder of observation slot `slot` (ray against the floor plane; boxes in the scene)
   ACKB_HD static T lidar_ray(const Consts<T>& C, const State& e, const Kin<T>& k, int beam) {
     const T cb = C.lidar_cos[beam], sb = C.lidar_sin[beam];
@@ -1350,17 +1406,44 @@ struct Sim {
       }
     }
     const int nbox = (int)C.nbox[0];
-    for (int bi = 0; bi < nbox; ++bi) {
-      const T lp[3] = {ow[0] - C.box_cx[bi], ow[1] - C.box_cy[bi], ow[2] - C.box_z[0]};
-      for (int i = 0; i < 3; ++i) {
-        if (N::abs_(dw[i]) <= N::minval) continue;
-        const int a = (i + 1) % 3, b = (i + 2) % 3;
-        for (int side = -1; side <= 1; side += 2) {
-          T sol = (T(side) * C.box_half[i] - lp[i]) / dw[i];
-          if (sol < T(0)) continue;
-          T pa = lp[a] + sol * dw[a], pb = lp[b] + sol * dw[b];
-          if (N::abs_(pa) <= C.box_half[a] && N::abs_(pb) <= C.box_half[b] && (best < T(0) || sol < best)) best = sol;
+    if (C.grid_on[0] != T(0)) {
+      // boxes on a lattice: walk the cells along the ray (2-D DDA) and test only the boxes met; the first box hit is the
+      // nearest one because the boxes are disjoint and cells are visited in order of entry distance
+      const T pitch = C.grid_pitch[0], ip = N::rcp_(pitch);
+      const T gx = (ow[0] - C.grid_x0[0]) * ip, gy = (ow[1] - C.grid_y0[0]) * ip;
+      int ix = (int)floor(gx), iy = (int)floor(gy);
+      const int nx = (int)C.grid_nx[0], ny = (int)C.grid_ny[0];
+      if (ix >= 0 && iy >= 0 && ix < nx && iy < ny) {
+        const int sx = dw[0] > T(0) ? 1 : -1, sy = dw[1] > T(0) ? 1 : -1;
+        const T big = T(1e30);
+        const bool mx = N::abs_(dw[0]) > N::minval, my = N::abs_(dw[1]) > N::minval;
+        const T idx = mx ? N::rcp_(dw[0]) : T(0), idy = my ? N::rcp_(dw[1]) : T(0);
+        const T tdx = mx ? N::abs_(pitch * idx) : big, tdy = my ? N::abs_(pitch * idy) : big;
+        T tmx = mx ? ((T)(ix + (sx > 0 ? 1 : 0)) - gx) * pitch * idx : big;
+        T tmy = my ? ((T)(iy + (sy > 0 ? 1 : 0)) - gy) * pitch * idy : big;
+        const int budget = nx + ny + 2;
+#pragma unroll 1
+        for (int step = 0; step < budget; ++step) {
+          if (((unsigned)C.grid_rows[iy] >> ix) & 1u) {
+            const T h = box_ray(C, ow[0] - (C.grid_x0[0] + (T(ix) + T(0.5)) * pitch), ow[1] - (C.grid_y0[0] + (T(iy) + T(0.5)) * pitch),
+                                ow[2] - C.box_z[0], dw);
+            if (h >= T(0)) { if (best < T(0) || h < best) best = h; break; }
+          }
+          const T tn = tmx < tmy ? tmx : tmy;             // ray parameter at which the next cell is entered
+          if (best >= T(0) && tn > best) break;            // the floor is hit first
+          if (tmx < tmy) { ix += sx; tmx += tdx; } else { iy += sy; tmy += tdy; }
+          if (ix < 0 || iy < 0 || ix >= nx || iy >= ny) break;
         }
+      } else {
+        for (int bi = 0; bi < nbox; ++bi) {
+          const T h = box_ray(C, ow[0] - C.box_cx[bi], ow[1] - C.box_cy[bi], ow[2] - C.box_z[0], dw);
+          if (h >= T(0) && (best < T(0) || h < best)) best = h;
+        }
+      }
+    } else {
+      for (int bi = 0; bi < nbox; ++bi) {
+        const T h = box_ray(C, ow[0] - C.box_cx[bi], ow[1] - C.box_cy[bi], ow[2] - C.box_z[0], dw);
+        if (h >= T(0) && (best < T(0) || h < best)) best = h;
       }
     }
     if (C.lidar_cutoff[0] > T(0) && best > C.lidar_cutoff[0]) best = C.lidar_cutoff[0];

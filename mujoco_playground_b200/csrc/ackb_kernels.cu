@@ -91,13 +91,31 @@ struct Geo {
   static constexpr bool kSmemWheels = WPL > 1;
   static constexpr int kWheelUnits = sizeof(Wheel<T, NC>) / sizeof(T);          // record size in units of T
   static constexpr int kStride = WPL * kWheelUnits + ((WPL * kWheelUnits) % 2 == 0 ? 1 : 0);   // odd
-#ifndef ACKB_L1_BLOCK
-#define ACKB_L1_BLOCK 128
+  // shared-memory layouts: pick the CTA size (128, 64 or 32 threads) that fits the most warps into the 227 KB of an SM
+  // (1 KB per CTA is reserved by the system); registers allow 2 CTAs of 128 threads at most (<= 255 registers per thread)
+  static constexpr int warps_per_sm(int block) {
+    const long per_cta = (long)block * kStride * (long)sizeof(T) + 1024;
+    long ctas = (227L * 1024) / per_cta;
+    const long reg_ctas = 65536 / (232L * block);      // register allocation of this kernel: 232 per thread
+    if (ctas > reg_ctas) ctas = reg_ctas;
+    return (int)(ctas * block / 32);
+  }
+  static constexpr int pick_block() {
+#ifdef ACKB_L1_BLOCK
+    return sizeof(T) == 4 ? ACKB_L1_BLOCK : ACKB_L1_BLOCK / 2;
+#else
+    int best = sizeof(T) == 4 ? 128 : 64;
+    if (sizeof(T) == 4) {   // fp64 kernels sit at the 255-register cap and measured slower with smaller CTAs
+      if (warps_per_sm(64) > warps_per_sm(best)) best = 64;
+      if (warps_per_sm(32) > warps_per_sm(best)) best = 32;
+    }
+    return best;
 #endif
+  }
 #ifndef ACKB_L1_MINB
-#define ACKB_L1_MINB 2
+#define ACKB_L1_MINB (warps_per_sm(pick_block()) * 32 / pick_block())
 #endif
-  static constexpr int kBlock = kSmemWheels ? (sizeof(T) == 4 ? ACKB_L1_BLOCK : ACKB_L1_BLOCK / 2) : 128;
+  static constexpr int kBlock = kSmemWheels ? pick_block() : 128;
   static constexpr int kMinBlocks = kSmemWheels ? ACKB_L1_MINB : 2;
   static size_t smem_bytes(int obs_dim) {
     const size_t tile = (size_t)(kBlock / LANES) * obs_dim * sizeof(float);
@@ -366,8 +384,10 @@ int launch_one(ackb_handle* h, DevState<T>& st, const StepArgs& a, cudaStream_t 
   const long long threads = (long long)h->n * LANES;
   const int grid = (int)((threads + G::kBlock - 1) / G::kBlock);
   if (is_reset) {
-    const size_t smem = (size_t)(G::kBlock / LANES) * a.obs_dim * sizeof(float);
-    reset_kernel<T, LANES><<<grid, Geo<T, LANES, 2>::kBlock, smem, stream>>>(st, a);
+    using GR = Geo<T, LANES, 2>;   // the reset kernel has its own geometry (records in local storage)
+    const int rgrid = (int)((threads + GR::kBlock - 1) / GR::kBlock);
+    const size_t smem = (size_t)(GR::kBlock / LANES) * a.obs_dim * sizeof(float);
+    reset_kernel<T, LANES><<<rgrid, GR::kBlock, smem, stream>>>(st, a);
   } else {
     const size_t smem = G::smem_bytes(a.obs_dim);
     StepArgs a2 = a;
@@ -407,7 +427,10 @@ int ackb_create(const double* consts, size_t consts_len, int num_envs, int devic
   if (!consts || !out || num_envs <= 0) return fail(nullptr, ACKB_ERR_ARG, "ackb_create: null pointer or num_envs <= 0");
   if ((int)consts_len != kNumConsts) return fail(nullptr, ACKB_ERR_ARG, "ackb_create: constants blob has the wrong length");
   if (dtype != ACKB_F32 && dtype != ACKB_F64) return fail(nullptr, ACKB_ERR_ARG, "ackb_create: dtype must be ACKB_F32 or ACKB_F64");
-  if (lanes_per_env == 0) lanes_per_env = num_envs >= 32768 ? 1 : 4;   // throughput layout for big batches, latency layout otherwise
+  if (lanes_per_env == 0) {   // throughput layout (1 lane) for big flat-floor batches, latency layout (4 lanes) otherwise and for the obstacle scene
+    const bool scene_model = consts[0] != 0.0;
+    lanes_per_env = (num_envs >= 32768 && !scene_model) ? 1 : 4;
+  }
   if (lanes_per_env != 1 && lanes_per_env != 4 && lanes_per_env != 8) return fail(nullptr, ACKB_ERR_ARG, "ackb_create: lanes_per_env must be 1, 4 or 8");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(nullptr, ACKB_ERR_NO_DEVICE, "ackb_create: no CUDA device (there is no CPU fallback)");

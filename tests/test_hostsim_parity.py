@@ -7,7 +7,7 @@ from mujoco_playground_b200.compiler.constants import build_consts
 from mujoco_playground_b200.models import load_model
 from oracle.env_oracle import OracleEnv
 from oracle.oracle import OracleSim
-from tests.hostsim.hostsim import HostSim
+from tests.hostsim.hostsim import HostSim, consts_field
 
 M = load_model("v2")
 
@@ -145,6 +145,52 @@ def test_scene_observation_matches_oracle_rays():
         got, _, _ = h.observe()
         assert got.shape == (43,)
         np.testing.assert_allclose(got, want, atol=2e-6)
+
+
+def test_scene_grid_ray_walk_matches_oracle_everywhere():
+    """Occupancy-grid ray walk (DDA over the maze cells) vs the oracle's brute-force caster: poses all over the maze, tilted chassis,
+    rays that hit the floor first, rays leaving the maze; and grid vs no-grid constants give the same wheel-box contacts."""
+    from oracle.env_oracle import OracleEnv
+    S = load_model("scene")
+    h = HostSim(build_consts(S, model_kind=1), False)
+    h0 = HostSim(build_consts(S, model_kind=1, use_box_grid=False), False)
+    o = OracleEnv(S, kind="scene")
+    rng = np.random.default_rng(11)
+    occupied = {(int(round(x)), int(round(y))) for x, y in zip(consts_field(h.blob, "box_cx")[:38], consts_field(h.blob, "box_cy")[:38])}
+    assert consts_field(h.blob, "grid_on") == 1 and consts_field(h0.blob, "grid_on") == 0
+    n = 0
+    while n < 120:
+        x, y = rng.uniform(-5.0, 4.0, 2)
+        if (int(round(x)), int(round(y))) in occupied:
+            continue
+        qpos = S["qpos0"].copy()
+        qpos[0], qpos[1], qpos[2] = x, y, rng.uniform(0.06, 0.12)
+        yaw = rng.uniform(-np.pi, np.pi)
+        tilt = rng.normal(size=2) * 0.04
+        q = np.array([np.cos(yaw / 2), tilt[0], tilt[1], np.sin(yaw / 2)])
+        qpos[3:7] = q / np.linalg.norm(q)
+        goal = rng.uniform(-3, 3, 2)
+        want = o.reset(goal, spawn_qpos=qpos)
+        for sim in (h, h0):
+            sim.qpos[:] = qpos
+            sim.epd[:2] = goal
+            sim.epd[2:4] = qpos[:2]
+            got, _, _ = sim.observe()
+            np.testing.assert_allclose(got[:36], want[:36], atol=2e-6, err_msg=f"pose {qpos[:7]}")
+        n += 1
+    # wheel-box detection through the grid: same contacts, same order as the exhaustive loop
+    for t in range(60):
+        qpos = S["qpos0"].copy()
+        qpos[0] = rng.uniform(-3.45, -2.55); qpos[1] = rng.uniform(-3.45, -2.55); qpos[2] = 0.0648 + rng.uniform(-0.0003, 0.001)
+        yaw = rng.uniform(-np.pi, np.pi)
+        qpos[3:7] = [np.cos(yaw / 2), 0, 0, np.sin(yaw / 2)]
+        qvel = rng.normal(size=12) * np.array([.5, .5, .05, .2, .2, .5, 10, 10, 2, 10, 2, 10])
+        ctrl = rng.uniform(-1, 1, 4) * np.array([0.6, 0.6, 50, 50])
+        for sim in (h, h0):
+            sim.qpos[:], sim.qvel[:], sim.warm[:] = qpos, qvel, 0
+            sim.substep(ctrl)
+        assert h.diag[0] == h0.diag[0]
+        assert np.array_equal(h.qpos, h0.qpos) and np.array_equal(h.qvel, h0.qvel)
 
 
 @pytest.mark.parametrize("lanes", [4, 8])
