@@ -316,6 +316,7 @@ struct ackb_handle {
   int n = 0, device = 0, dtype = ACKB_F32, lanes = 4, obs_dim = 0;
   int num_sms = 148;
   int cta_sync = -1;            // -1 = auto (by grid size), 0 / 1 forced through ACKB_CTA_SYNC (tuning)
+  int zero_copy = 1;            // ackb_step_host: let the kernel access pinned caller buffers directly (ACKB_ZERO_COPY=0 disables)
   unsigned long long seed = 0;
   uint32_t step_index = 0;
   unsigned long long stat_steps = 0;
@@ -445,6 +446,7 @@ int ackb_create(const double* consts, size_t consts_len, int num_envs, int devic
   CK(cudaSetDevice(device));
   CK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
   if (const char* ev = getenv("ACKB_CTA_SYNC")) h->cta_sync = atoi(ev);
+  if (const char* ev = getenv("ACKB_ZERO_COPY")) h->zero_copy = atoi(ev);
   const size_t n = num_envs;
   const size_t bytes = (13 + 12 + 12 + 2 + 2) * n * h->elem + 3 * n * 4;
   CK(cudaMalloc(&h->state, bytes));
@@ -504,12 +506,35 @@ int ackb_step(ackb_handle* h, const float* dev_action, int frame_skip, int auto_
   return h->dtype == ACKB_F32 ? launch_step(h, h->sf, a, (cudaStream_t)stream, false) : launch_step(h, h->sd, a, (cudaStream_t)stream, false);
 }
 
+// Device-visible alias of a host pointer: pinned (cudaHostAlloc / cudaHostRegister) memory is mapped into the device address
+// space under unified addressing, so the kernel can read the actions from it and write its results into it directly over
+// PCIe/NVLink-C2C, overlapped with the computation (no staging copies).  Returns null for pageable memory.
+static void* device_alias(const void* host_ptr) {
+  cudaPointerAttributes at{};
+  if (cudaPointerGetAttributes(&at, host_ptr) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (at.type == cudaMemoryTypeHost && at.devicePointer) return at.devicePointer;
+  return nullptr;
+}
+
 int ackb_step_host(ackb_handle* h, const float* host_action, int frame_skip, int auto_reset, float* host_obs, float* host_reward,
                    uint8_t* host_terminated, uint8_t* host_truncated) {
   if (!h || !host_action || !host_obs || !host_reward || !host_terminated || !host_truncated) return fail(h, ACKB_ERR_ARG, "ackb_step_host: null pointer");
   CK(cudaSetDevice(h->device));
   const size_t n = h->n;
   cudaStream_t s = h->own_stream;
+  // pinned caller buffers: zero-copy (the kernel's coalesced observation stores go straight to host memory)
+  float* z_act = (float*)device_alias(host_action);
+  float* z_obs = (float*)device_alias(host_obs);
+  float* z_rew = (float*)device_alias(host_reward);
+  uint8_t* z_term = (uint8_t*)device_alias(host_terminated);
+  uint8_t* z_trunc = (uint8_t*)device_alias(host_truncated);
+  const bool zero_copy = h->zero_copy && z_act && z_obs && z_rew && z_term && z_trunc;
+  if (zero_copy) {
+    int rc = ackb_step(h, z_act, frame_skip, auto_reset, z_obs, z_rew, z_term, z_trunc, nullptr, nullptr, s);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(s));
+    return ACKB_OK;
+  }
   CK(cudaMemcpyAsync(h->d_action, host_action, n * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
   int rc = ackb_step(h, h->d_action, frame_skip, auto_reset, h->d_obs, h->d_reward, h->d_term, h->d_trunc, nullptr, nullptr, s);
   if (rc) return rc;

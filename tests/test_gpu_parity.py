@@ -149,20 +149,27 @@ def test_auto_reset_truncation_and_terminal_obs():
     env.close()
 
 
-def test_step_host_matches_device_step():
+@pytest.mark.parametrize("pinned", [True, False])
+def test_step_host_matches_device_step(pinned):
+    """ackb_step_host with pinned caller buffers (zero-copy: the kernel reads / writes host memory directly) and with
+    pageable ones (staged copies) returns exactly what the device-tensor step returns, auto-reset rows included."""
     from mujoco_playground_b200 import BatchedAckermannEnv
     n = 50
     rng = np.random.default_rng(8)
     a = torch.from_numpy(rng.uniform(-1, 1, (n, 2)).astype(np.float32))
-    e1 = BatchedAckermannEnv(n, seed=5, auto_reset=True)
-    e2 = BatchedAckermannEnv(n, seed=5, auto_reset=True)
+    e1 = BatchedAckermannEnv(n, seed=5, auto_reset=True, max_episode_steps=12)
+    e2 = BatchedAckermannEnv(n, seed=5, auto_reset=True, max_episode_steps=12)
     e1.reset(); e2.reset()
-    h = [torch.empty((n, e2.obs_dim)).pin_memory(), torch.empty(n).pin_memory(), torch.empty(n, dtype=torch.uint8).pin_memory(),
-         torch.empty(n, dtype=torch.uint8).pin_memory()]
+    mk = (lambda t: t.pin_memory()) if pinned else (lambda t: t)
+    h = [mk(torch.empty((n, e2.obs_dim))), mk(torch.empty(n)), mk(torch.empty(n, dtype=torch.uint8)), mk(torch.empty(n, dtype=torch.uint8))]
+    ah = mk(a.clone())
+    ntrunc = 0
     for _ in range(30):
         o1, r1, t1, u1, _ = e1.step(a.cuda())
-        e2.step_host(a.pin_memory(), *h)
-    assert torch.equal(o1.cpu(), h[0]) and torch.equal(r1.cpu(), h[1]) and torch.equal(t1.cpu(), h[2])
+        e2.step_host(ah, *h)
+        assert torch.equal(o1.cpu(), h[0]) and torch.equal(r1.cpu(), h[1]) and torch.equal(t1.cpu(), h[2]) and torch.equal(u1.cpu(), h[3])
+        ntrunc += int(h[3].sum())
+    assert ntrunc == 2 * n, "two truncations (with auto-reset observations) per environment in 30 steps"
     e1.close(); e2.close()
 
 
