@@ -28,13 +28,14 @@ ALGO_BYTES_F64 = 962.0
 
 
 def measured_traffic(dtype, n_envs, fs):
-    """DRAM bytes per launch of the step kernel from the committed ncu capture of the same configuration, or None."""
+    """(DRAM bytes, note, warp instructions) per launch of the step kernel from the committed ncu capture of the same
+    configuration, or Nones."""
     p = os.path.join(ROOT, "profiles", "r01_traffic.json")
     try:
         d = json.load(open(p)).get(f"{'f32' if dtype == 'float32' else 'f64'}_{n_envs}_fs{fs}")
-        return (d["dram_bytes_read"] + d["dram_bytes_write"], d["note"]) if d else (None, None)
+        return (d["dram_bytes_read"] + d["dram_bytes_write"], d["note"], d.get("warp_instructions")) if d else (None, None, None)
     except Exception:
-        return None, None
+        return None, None, None
 
 
 def measured_peak_gbs():
@@ -233,7 +234,15 @@ def run_cuda(args, rank, local_rank, world):
         algo = ALGO_BYTES_F32 if args.dtype == "float32" else ALGO_BYTES_F64
         avg_launch_s = (sum(step_ms) / len(step_ms)) * 1e-3
         achieved = algo * n_envs / avg_launch_s / 1e9
-        traffic, traffic_note = measured_traffic(args.dtype, n_envs, fs)
+        traffic, traffic_note, warp_inst = measured_traffic(args.dtype, n_envs, fs)
+        # the bound that actually binds: warp-instruction issue.  Peak = SMs x 4 schedulers x SM clock.
+        issue = None
+        if warp_inst:
+            sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
+            peak_issue = 148 * 4 * sm_clock * 1e6
+            issue = {"bound": "issue", "unit": "warp-instr/s", "achieved": warp_inst / avg_launch_s, "peak": peak_issue,
+                     "frac": warp_inst / avg_launch_s / peak_issue, "warp_instructions_per_launch": warp_inst,
+                     "note": "instruction count from the committed ncu capture of this configuration, time measured live"}
         line = {
             "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -242,7 +251,7 @@ def run_cuda(args, rank, local_rank, world):
                        "l2": "flushed between timed iterations (256 MiB memset, untimed)", "physics_substeps_per_s": value * fs},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
                          "peak_source": how, "kernel": "step_kernel", "algorithmic_bytes_per_env_step": algo, "algorithmic_bytes_per_launch": algo * n_envs,
-                         "note": "compute/latency bound kernel: see DESIGN.md (HBM fraction is small by construction)"},
+                         "note": "compute/latency bound kernel: see DESIGN.md (HBM fraction is small by construction)", "issue": issue},
             "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches),
             "clocks": clocks,

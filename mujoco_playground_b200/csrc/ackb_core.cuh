@@ -200,10 +200,10 @@ struct Team {
   }
   // Instruction-cache locality: the warps of a CTA re-converge here so that they walk the same code together and share
   // the fetched lines (the kernel is instruction-fetch bound).  Must be reached by every thread of the CTA.
-  // (With 1 lane per environment the rolled wheel loops keep the footprint small and the barrier is not needed.)
+  // Measured on B200 for every layout (1-lane layout with tail mode: 136 M -> 152 M env-steps/s at 131072 envs, frame_skip 4).
   ACKB_D static void block_sync() {
 #if defined(__CUDA_ARCH__)
-    if (LANES > 1) __syncthreads();
+    __syncthreads();
 #endif
   }
   ACKB_D static void warp_sync() {
@@ -626,6 +626,25 @@ struct Sim {
     if (c##_g < ncs) {                                                             \
       _Pragma("unroll") for (int c = c##_g; c < c##_g + CSTEP; ++c) {
 #define ACKB_CONTACTS_END }}}
+#ifndef ACKB_TAIL_MODE
+#define ACKB_TAIL_MODE 1
+#endif
+#ifndef ACKB_TAIL_ENVS
+#define ACKB_TAIL_ENVS 8
+#endif
+  static constexpr int kTailEnvs = ACKB_TAIL_ENVS;
+  // team sum inside the solver loop: the layout's own team, or the 4-lane teams of tail mode
+  template <int NN>
+  ACKB_D static void team_sum_n(T (&v)[NN], bool TL) {
+#if defined(__CUDA_ARCH__)
+    if (TL) {
+#pragma unroll
+      for (int i = 0; i < NN; ++i) { v[i] += __shfl_xor_sync(0xffffffffu, v[i], 1); v[i] += __shfl_xor_sync(0xffffffffu, v[i], 2); }
+      return;
+    }
+#endif
+    Tm::sum_n(v);
+  }
 
   // ---- B1 kinematics: normalise the quaternion (written back, like mj_kinematics), rotation, floor frame
   ACKB_HD static void kinematics(State& e, Kin<T>& k) {
@@ -864,143 +883,48 @@ struct Sim {
     for (int i = 0; i < 2; ++i) y_sh[6 + i] = C.h_inertia[i] * a[2] + (C.h_inertia[i] + C.h_armature[i]) * x_sh[6 + i];
   }
 
-  // ---- one physics substep (mj_step): everything between kinematics and integration.
-  // `k` must hold the kinematics of the current state; `wh` are the WPL wheel records of this lane.
-  //
-  // Solver structure (B13-B16): ONE loop body.  Every trip moves along the current direction x with an exact line
-  // search and then assembles the arrow-shaped Newton system  H x = -g  (H = M~ + J^T D J, g = M~ a - tau - J^T f),
-  // LDL^T-factorises its 8 x 8 Schur complement and solves it.  The iteration starts at a = 0 with a unit step along
-  // the warm start (previous qacc), as MuJoCo does when its cost beats qacc_smooth; the minimiser is unique, so the
-  // starting point only affects the iteration count (qacc_smooth is never needed).
-  ACKB_HD static void dynamics(const Consts<T>& C, State& e, const Kin<T>& k, const T* ctrl, int lane, WheelT* wh, StepDiag& diag,
-                               DebugTap<T>* tap) {
-    const T h = C.timestep[0];
-    T vb[3];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) vb[i] = k.R[i] * e.vw[0] + k.R[3 + i] * e.vw[1] + k.R[6 + i] * e.vw[2];
-
-    // ---- wheels: collision, spin-dof smooth force; wheel-derived parts of the chassis / steer bias (closed-form RNE)
-    T bpart[8];   // [hrel(3), gyro(3), steerL, steerR]
-#pragma unroll
-    for (int i = 0; i < 8; ++i) bpart[i] = T(0);
-    bool warm_ok = true;
-#pragma unroll 1
-    for (int s = 0; s < WPL; ++s) {
-      const int wi = wheel_index(lane, s);
-      const WheelK<T> wk = wheel_consts(C, wi);
-      WheelT& w = wh[s];
-      collide_wheel(C, e, k, vb, wi, lane & 1, wk, w, diag);
-      if (NC > 2) collide_boxes(C, e, k, vb, wi, wk, w, diag);
-      const T dsteer = wk.isL * e.dst[0] + wk.isR * e.dst[1];
-      const T aw[3] = {w.ax, w.ay, T(0)};
-      const T ez[3] = {T(0), T(0), T(1)};
-      T ezxa[3], omxa[3], omxez[3];
-      cross3(ezxa, ez, aw);
-      cross3(omxa, e.om, aw);
-      cross3(omxez, e.om, ez);
-      const T pwt = pair_weight();
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        bpart[i] += pwt * wk.J * w.dsp * aw[i];
-        bpart[3 + i] += pwt * wk.J * w.dsp * dsteer * ezxa[i];
-      }
-      const T bias_steer = pwt * wk.J * w.dsp * omxa[2];  // ez . (om x a)
-      bpart[6] += wk.isL * bias_steer;
-      bpart[7] += wk.isR * bias_steer;
-      const T bias_spin = wk.J * dsteer * dot3(aw, omxez);
-      w.tau = -wk.damp * w.dsp - bias_spin + actuator_force(C, ctrl, wk.hidx, w.sp, w.dsp);
-      w.a = T(0);
-      w.x = w.warm;
-      w.zone0 = 0u;
-      if (NC <= 2) w.fcode = 0u;
-      warm_ok = warm_ok && (N::abs_(w.warm) <= T(1e10));
-    }
-    Tm::sum_n(bpart);
-    // number of contact slots the solver has to look at (warp-uniform): the box slots only if some environment of the warp uses them
-    int ncs = NC;
-    if (NC > 2) {
-      bool has_box = false;
-#pragma unroll 1
-      for (int s = 0; s < WPL; ++s) has_box = has_box || (wh[s].con[NC - 2].D > T(0)) || (wh[s].con[NC - 1].D > T(0));
-      ncs = Tm::any(has_box) ? NC : 2;
-    }
-    // plate hull vs floor: flagged only (35 mm clearance; reachable only after a roll-over)
-    if (lane == 0) {
-      const int nh = (int)C.nhull[0];
-      const T hO = e.p[2] - C.plane_z[0];
-#pragma unroll 1
-      for (int i = 0; i < nh; ++i) if (dot3(k.n, &C.hull_pts[3 * i]) + hO <= T(0)) diag.unsupported = 1;
-    }
+  // solver variables that live across the Newton loop (kept in registers; a struct so that the loop can be instantiated twice)
+  struct SolverVars {
+    T a_sh[8], Ma_sh[8], x_sh[8], tau_sh[8];
     SharedRows<T> sr;
-    make_shared_rows(C, e, sr);
+    int iter, nls, phase;
+    bool first;
+    T lam2;
+    unsigned szone0;
+  };
 
-    // ---- B10/B12/B13 shared smooth force  tau = passive - bias + actuation  (closed-form RNE, see header)
-    T tau_sh[8];
-    {
-      T gb[3];  // gravity in the body frame
-#pragma unroll
-      for (int i = 0; i < 3; ++i) gb[i] = k.R[i] * C.gravity[0] + k.R[3 + i] * C.gravity[1] + k.R[6 + i] * C.gravity[2];
-      T Iw[3], hh[3], t0[3], t1[3], t2[3], t3[3];
-      const T* I = C.inertiaO;
-      Iw[0] = I[0] * e.om[0] + I[3] * e.om[1] + I[4] * e.om[2];
-      Iw[1] = I[3] * e.om[0] + I[1] * e.om[1] + I[5] * e.om[2];
-      Iw[2] = I[4] * e.om[0] + I[5] * e.om[1] + I[2] * e.om[2];
-#pragma unroll
-      for (int i = 0; i < 3; ++i) hh[i] = Iw[i] + bpart[i];
-      hh[2] += C.h_inertia[0] * e.dst[0] + C.h_inertia[1] * e.dst[1];
-      cross3(t0, e.om, hh);                // om x (I_O om + h_rel)
-      cross3(t1, C.mcom, gb);              // m c x g
-      cross3(t2, e.om, C.mcom);
-      cross3(t3, e.om, t2);                // om x (om x m c)
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        tau_sh[i] = -(t3[i] - C.mass[0] * gb[i]);
-        tau_sh[3 + i] = -(t0[i] + bpart[3 + i] - t1[i]);
-      }
-#pragma unroll
-      for (int i = 0; i < 2; ++i)   // unrolled: a rolled loop would index tau_sh / bpart / e.st dynamically and push them to local memory
-        tau_sh[6 + i] = -C.h_damping[i] * e.dst[i] - bpart[6 + i] + actuator_force(C, ctrl, i, e.st[i], e.dst[i]);
-    }
-
-    // current point a (starts at 0 and takes a unit step along the warm start), M~ a
-    T a_sh[8], Ma_sh[8], x_sh[8];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      x_sh[i] = k.R[i] * e.warm_l[0] + k.R[3 + i] * e.warm_l[1] + k.R[6 + i] * e.warm_l[2];
-      x_sh[3 + i] = e.warm_a[i];
-    }
-    x_sh[6] = e.warm_st[0]; x_sh[7] = e.warm_st[1];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { warm_ok = warm_ok && (N::abs_(x_sh[i]) <= T(1e10)); a_sh[i] = T(0); Ma_sh[i] = T(0); }
-    if (Tm::sum(warm_ok ? 0 : 1) != 0) {   // unusable warm start: begin at a = 0
-#pragma unroll
-      for (int i = 0; i < 8; ++i) x_sh[i] = T(0);
-#pragma unroll 1
-      for (int s = 0; s < WPL; ++s) wh[s].x = T(0);
-    }
-
+  // ---- the Newton loop (B13-B15), see `dynamics`.  TL = false: the layout's own team (LANES lanes, WPL wheels per lane).
+  // TL = true (tail mode of the 1-lane layout): 4 lanes per environment, one wheel record each, reached through `whp`.
+  // (TL is a warp-uniform run-time flag and the loop is instantiated ONCE: a second copy of the body costs more in instruction
+  // fetch than tail mode saves -- measured: 134 M -> 106 M env-steps/s at 131072 envs, frame_skip 4.)
+  ACKB_HD static void solve_loop(const Consts<T>& C, const Kin<T>& kl, WheelT* whp, const int wbase, const int ncs, SolverVars& sv,
+                                 const bool exit_for_tail, const bool TL) {
+    const int wpl = TL ? 1 : WPL;
+    T (&a_sh)[8] = sv.a_sh; T (&Ma_sh)[8] = sv.Ma_sh; T (&x_sh)[8] = sv.x_sh; T (&tau_sh)[8] = sv.tau_sh;
+    SharedRows<T>& sr = sv.sr;
+    int& iter = sv.iter; int& nls = sv.nls; int& phase = sv.phase;
+    bool& first = sv.first;
+    T& lam2 = sv.lam2;
+    unsigned& szone0 = sv.szone0;
     const T tol = mjmax(C.tolerance[0], N::tol_floor);
     const int maxit = (int)C.iterations[0], maxls_exact = (int)C.ls_iterations[0];
     const int ls_fast_cap = (int)C.ls_fast_cap[0], ls_fast_iters = (int)C.ls_fast_iters[0];
     const int ls_mid_cap = (int)C.ls_mid_cap[0], ls_mid_iters = (int)C.ls_mid_iters[0];
-    int iter = 0, nls = 0;
-    // per-environment phase: 0 = iterating (step along x, then Newton pass), 2 = converged.
-    // The loop itself is warp-uniform: it runs until every environment of the warp has converged.
-    int phase = 0;
-    bool first = true;
-    T lam2 = T(0);
-    unsigned szone0 = 0u;
     while (Tm::loop_any(phase != 2)) {
+#if defined(__CUDA_ARCH__)
+      // plain 1-lane pass: leave as soon as few enough environments of the warp are still iterating (the caller re-spreads them)
+      if (!TL && exit_for_tail && __popc(__ballot_sync(0xffffffffu, phase != 2)) <= kTailEnvs) return;
+#endif
       const bool stepping = (phase == 0);
       // ---- move along x: exact line search (safeguarded Newton on f'(alpha)), then update the point
       {
         // M~ x (shared part), contact images of x, line-search constants
         T acc[5] = {T(0), T(0), T(0), T(0), T(0)};  // sum_w J a_w x_w (3), private parts of x.Mx and x.(Ma - tau)
 #pragma unroll 1
-        for (int s = 0; s < WPL; ++s) {
-          const int wi = wheel_index(lane, s);
+        for (int s = 0; s < wpl; ++s) {
+          const int wi = wbase + s;
           const WheelK<T> wk = wheel_consts(C, wi);
-          WheelT& w = wh[s];
+          WheelT& w = whp[s];
           const T aw_aang_x = w.ax * x_sh[3] + w.ay * x_sh[4], aw_aang_a = w.ax * a_sh[3] + w.ay * a_sh[4];
           const T Mv_sp = wk.J * aw_aang_x + wk.cdiag * w.x, Ma_sp = wk.J * aw_aang_a + wk.cdiag * w.a;
           const T pwt = pair_weight();
@@ -1011,11 +935,11 @@ struct Sim {
             Contact<T>& con = w.con[c];
             T u[3], wv[2], fn[3], ft1[3], ft2[3];
             contact_cols(w, wk, con.x, u, wv);
-            contact_frame(k, c < 2 ? 0 : (int)((w.fcode >> (4 * (c - 2))) & 15u), fn, ft1, ft2);
+            contact_frame(kl, c < 2 ? 0 : (int)((w.fcode >> (4 * (c - 2))) & 15u), fn, ft1, ft2);
             project_point(fn, ft1, ft2, con.x, u, wv, x_sh, x_sh + 3, w.x, ast, con.zv);
           ACKB_CONTACTS_END
         }
-        Tm::sum_n(acc);
+        team_sum_n(acc, TL);
         T Mv_sh[8];
         mul_M_shared(C, x_sh, acc, Mv_sh);
         T sMs = acc[3], sg = acc[4];
@@ -1032,10 +956,10 @@ struct Sim {
         for (int ls = 0; ls < maxls_exact && Tm::any(ls_on); ++ls) {
           T d[3] = {T(0), T(0), T(0)};
 #pragma unroll 1
-          for (int s = 0; s < WPL; ++s) {
-            const int wi = wheel_index(lane, s);
+          for (int s = 0; s < wpl; ++s) {
+            const int wi = wbase + s;
             const WheelK<T> wk = wheel_consts(C, wi);
-            const WheelT& w = wh[s];
+            const WheelT& w = whp[s];
             T f, q;
             floss_row(w.a + alpha * w.x + wk.flB * w.dsp, wk.flf, wk.flR, wk.flD, &f, &q);
             d[0] -= pair_weight() * f * w.x;
@@ -1064,7 +988,7 @@ struct Sim {
             ACKB_CONTACTS_END
             d[2] += (zone != w.zone0) ? T(1) : T(0);
           }
-          Tm::sum_n(d);
+          team_sum_n(d, TL);
           T gL, gR, kLL, kLR, kRR;
           shared_rows_eval(sr, a_sh[6] + alpha * x_sh[6], a_sh[7] + alpha * x_sh[7], &gL, &gR, &kLL, &kLR, &kRR);
           const T d1 = alpha * sMs + sg + d[0] - gL * x_sh[6] - gR * x_sh[7];
@@ -1088,8 +1012,8 @@ struct Sim {
 #pragma unroll
           for (int i = 0; i < 8; ++i) { a_sh[i] += alpha * x_sh[i]; Ma_sh[i] += alpha * Mv_sh[i]; }
 #pragma unroll 1
-          for (int s = 0; s < WPL; ++s) {
-            WheelT& w = wh[s];
+          for (int s = 0; s < wpl; ++s) {
+            WheelT& w = whp[s];
             w.a += alpha * w.x;
             ACKB_CONTACTS_BEGIN(c)
 #pragma unroll
@@ -1109,10 +1033,10 @@ struct Sim {
 #pragma unroll
       for (int i = 0; i < 45; ++i) part[i] = T(0);
 #pragma unroll 1
-      for (int s = 0; s < WPL; ++s) {
-        const int wi = wheel_index(lane, s);
+      for (int s = 0; s < wpl; ++s) {
+        const int wi = wbase + s;
         const WheelK<T> wk = wheel_consts(C, wi);
-        WheelT& w = wh[s];
+        WheelT& w = whp[s];
         T f, q;
         floss_row(w.a + wk.flB * w.dsp, wk.flf, wk.flR, wk.flD, &f, &q);
         unsigned zone = (q != T(0)) ? 1u : (f > T(0) ? 0u : 2u);
@@ -1127,7 +1051,7 @@ struct Sim {
         ACKB_CONTACTS_BEGIN(c)
           const Contact<T>& con = w.con[c];
           T phi[3], qq[4], fn[3], ft1[3], ft2[3];
-          contact_frame(k, c < 2 ? 0 : (int)((w.fcode >> (4 * (c - 2))) & 15u), fn, ft1, ft2);
+          contact_frame(kl, c < 2 ? 0 : (int)((w.fcode >> (4 * (c - 2))) & 15u), fn, ft1, ft2);
           pyramid_rows(con.D, mu, con.z, phi, qq);
           {
             const unsigned zb = (qq[0] != T(0) ? 1u : 0u) | (qq[1] != T(0) ? 2u : 0u) | (qq[2] != T(0) ? 4u : 0u) | (qq[3] != T(0) ? 8u : 0u);
@@ -1230,7 +1154,7 @@ struct Sim {
         }
         part[44] += gs_sp * gs_sp * ci;
       }
-      Tm::sum_n(part);
+      team_sum_n(part, TL);
       T S[36];
       shared_mass(C, S);
 #pragma unroll
@@ -1253,9 +1177,9 @@ struct Sim {
         for (int i = 0; i < 8; ++i) lam2 += rhs[i] * y_sh[i];
         // x = -H^-1 g
 #pragma unroll 1
-        for (int s = 0; s < WPL; ++s) {
-          const int wi = wheel_index(lane, s);
-          WheelT& w = wh[s];
+        for (int s = 0; s < wpl; ++s) {
+          const int wi = wbase + s;
+          WheelT& w = whp[s];
           T dotb = T(0);
 #pragma unroll
           for (int a = 0; a < 6; ++a) dotb += w.b[a] * y_sh[a];
@@ -1268,6 +1192,203 @@ struct Sim {
         if (!(C.solver_scale[0] * T(0.5) * lam2 >= tol)) phase = 2;
       }
     }
+  }
+
+  // ---- one physics substep (mj_step): everything between kinematics and integration.
+  // `k` must hold the kinematics of the current state; `wh` are the WPL wheel records of this lane.
+  //
+  // Solver structure (B13-B16): ONE loop body.  Every trip moves along the current direction x with an exact line
+  // search and then assembles the arrow-shaped Newton system  H x = -g  (H = M~ + J^T D J, g = M~ a - tau - J^T f),
+  // LDL^T-factorises its 8 x 8 Schur complement and solves it.  The iteration starts at a = 0 with a unit step along
+  // the warm start (previous qacc), as MuJoCo does when its cost beats qacc_smooth; the minimiser is unique, so the
+  // starting point only affects the iteration count (qacc_smooth is never needed).
+  ACKB_HD static void dynamics(const Consts<T>& C, State& e, const Kin<T>& k, const T* ctrl, int lane, WheelT* wh, StepDiag& diag,
+                               DebugTap<T>* tap, int rec_stride = 0) {
+    const T h = C.timestep[0];
+    T vb[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) vb[i] = k.R[i] * e.vw[0] + k.R[3 + i] * e.vw[1] + k.R[6 + i] * e.vw[2];
+
+    // ---- wheels: collision, spin-dof smooth force; wheel-derived parts of the chassis / steer bias (closed-form RNE)
+    T bpart[8];   // [hrel(3), gyro(3), steerL, steerR]
+#pragma unroll
+    for (int i = 0; i < 8; ++i) bpart[i] = T(0);
+    bool warm_ok = true;
+#pragma unroll 1
+    for (int s = 0; s < WPL; ++s) {
+      const int wi = wheel_index(lane, s);
+      const WheelK<T> wk = wheel_consts(C, wi);
+      WheelT& w = wh[s];
+      collide_wheel(C, e, k, vb, wi, lane & 1, wk, w, diag);
+      if (NC > 2) collide_boxes(C, e, k, vb, wi, wk, w, diag);
+      const T dsteer = wk.isL * e.dst[0] + wk.isR * e.dst[1];
+      const T aw[3] = {w.ax, w.ay, T(0)};
+      const T ez[3] = {T(0), T(0), T(1)};
+      T ezxa[3], omxa[3], omxez[3];
+      cross3(ezxa, ez, aw);
+      cross3(omxa, e.om, aw);
+      cross3(omxez, e.om, ez);
+      const T pwt = pair_weight();
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        bpart[i] += pwt * wk.J * w.dsp * aw[i];
+        bpart[3 + i] += pwt * wk.J * w.dsp * dsteer * ezxa[i];
+      }
+      const T bias_steer = pwt * wk.J * w.dsp * omxa[2];  // ez . (om x a)
+      bpart[6] += wk.isL * bias_steer;
+      bpart[7] += wk.isR * bias_steer;
+      const T bias_spin = wk.J * dsteer * dot3(aw, omxez);
+      w.tau = -wk.damp * w.dsp - bias_spin + actuator_force(C, ctrl, wk.hidx, w.sp, w.dsp);
+      w.a = T(0);
+      w.x = w.warm;
+      w.zone0 = 0u;
+      if (NC <= 2) w.fcode = 0u;
+      warm_ok = warm_ok && (N::abs_(w.warm) <= T(1e10));
+    }
+    Tm::sum_n(bpart);
+    // number of contact slots the solver has to look at (warp-uniform): the box slots only if some environment of the warp uses them
+    int ncs = NC;
+    if (NC > 2) {
+      bool has_box = false;
+#pragma unroll 1
+      for (int s = 0; s < WPL; ++s) has_box = has_box || (wh[s].con[NC - 2].D > T(0)) || (wh[s].con[NC - 1].D > T(0));
+      ncs = Tm::any(has_box) ? NC : 2;
+    }
+    // plate hull vs floor: flagged only (35 mm clearance; reachable only after a roll-over)
+    if (lane == 0) {
+      const int nh = (int)C.nhull[0];
+      const T hO = e.p[2] - C.plane_z[0];
+#pragma unroll 1
+      for (int i = 0; i < nh; ++i) if (dot3(k.n, &C.hull_pts[3 * i]) + hO <= T(0)) diag.unsupported = 1;
+    }
+    SolverVars sv;
+    SharedRows<T>& sr = sv.sr;
+    make_shared_rows(C, e, sr);
+
+    // ---- B10/B12/B13 shared smooth force  tau = passive - bias + actuation  (closed-form RNE, see header)
+    T (&tau_sh)[8] = sv.tau_sh;
+    {
+      T gb[3];  // gravity in the body frame
+#pragma unroll
+      for (int i = 0; i < 3; ++i) gb[i] = k.R[i] * C.gravity[0] + k.R[3 + i] * C.gravity[1] + k.R[6 + i] * C.gravity[2];
+      T Iw[3], hh[3], t0[3], t1[3], t2[3], t3[3];
+      const T* I = C.inertiaO;
+      Iw[0] = I[0] * e.om[0] + I[3] * e.om[1] + I[4] * e.om[2];
+      Iw[1] = I[3] * e.om[0] + I[1] * e.om[1] + I[5] * e.om[2];
+      Iw[2] = I[4] * e.om[0] + I[5] * e.om[1] + I[2] * e.om[2];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) hh[i] = Iw[i] + bpart[i];
+      hh[2] += C.h_inertia[0] * e.dst[0] + C.h_inertia[1] * e.dst[1];
+      cross3(t0, e.om, hh);                // om x (I_O om + h_rel)
+      cross3(t1, C.mcom, gb);              // m c x g
+      cross3(t2, e.om, C.mcom);
+      cross3(t3, e.om, t2);                // om x (om x m c)
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        tau_sh[i] = -(t3[i] - C.mass[0] * gb[i]);
+        tau_sh[3 + i] = -(t0[i] + bpart[3 + i] - t1[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)   // unrolled: a rolled loop would index tau_sh / bpart / e.st dynamically and push them to local memory
+        tau_sh[6 + i] = -C.h_damping[i] * e.dst[i] - bpart[6 + i] + actuator_force(C, ctrl, i, e.st[i], e.dst[i]);
+    }
+
+    // current point a (starts at 0 and takes a unit step along the warm start), M~ a
+    T (&a_sh)[8] = sv.a_sh; T (&Ma_sh)[8] = sv.Ma_sh; T (&x_sh)[8] = sv.x_sh;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      x_sh[i] = k.R[i] * e.warm_l[0] + k.R[3 + i] * e.warm_l[1] + k.R[6 + i] * e.warm_l[2];
+      x_sh[3 + i] = e.warm_a[i];
+    }
+    x_sh[6] = e.warm_st[0]; x_sh[7] = e.warm_st[1];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { warm_ok = warm_ok && (N::abs_(x_sh[i]) <= T(1e10)); a_sh[i] = T(0); Ma_sh[i] = T(0); }
+    if (Tm::sum(warm_ok ? 0 : 1) != 0) {   // unusable warm start: begin at a = 0
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x_sh[i] = T(0);
+#pragma unroll 1
+      for (int s = 0; s < WPL; ++s) wh[s].x = T(0);
+    }
+
+    sv.iter = 0; sv.nls = 0;
+    // per-environment phase: 0 = iterating (step along x, then Newton pass), 2 = converged.
+    // The loop itself is warp-uniform: it runs until every environment of the warp has converged.
+    sv.phase = 0; sv.first = true; sv.lam2 = T(0); sv.szone0 = 0u;
+#if defined(__CUDA_ARCH__)
+    constexpr bool TAIL = (LANES == 1) && (sizeof(T) == 4) && (ACKB_TAIL_MODE != 0);   // fp64 kernels are at the register cap already
+    const bool tail_ok = TAIL && rec_stride != 0;   // needs the records in shared memory (rec_stride = per-thread stride in units of T)
+#else
+    const bool tail_ok = false;
+#endif
+    // pass 0: the layout's own team.  pass 1 (tail mode, 1-lane layout with records in shared memory only): once at most kTailEnvs
+    // environments of the warp are still iterating, pass 0 returns and they are re-spread over the warp with 4 lanes each
+    // (lane = wheel, as in the 4-lane layout): the solver state of environment number r moves to lanes 4r .. 4r+3 by shuffles,
+    // the wheel records are reached in place.
+    Kin<T> kl = k;
+    WheelT* whp = wh;
+    int wb = wheel_index(lane, 0);
+    bool tail = false;
+#if defined(__CUDA_ARCH__)
+    T a_keep[8];
+    int iter_keep = 0, my_src = 0;
+    bool my_active = false;
+#endif
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      solve_loop(C, kl, whp, wb, ncs, sv, tail_ok && pass == 0, tail);
+#if defined(__CUDA_ARCH__)
+      if (!TAIL) break;
+      const unsigned act = __ballot_sync(0xffffffffu, sv.phase != 2);
+      if (pass == 1 || !tail_ok || act == 0u) break;   // warp-uniform
+      const int cnt = __popc(act);
+      const int lid = (int)(threadIdx.x & 31u);
+      my_active = (sv.phase != 2);
+      my_src = my_active ? 4 * __popc(act & ((1u << lid) - 1u)) : lid;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a_keep[i] = sv.a_sh[i];
+      iter_keep = sv.iter;
+      const int slot = lid >> 2;
+      const bool serve = slot < cnt;
+      const int owner = serve ? (int)__fns(act, 0u, slot + 1) : (__ffs((int)~act) - 1);   // idle lanes shadow a finished environment
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        sv.a_sh[i] = __shfl_sync(0xffffffffu, sv.a_sh[i], owner); sv.Ma_sh[i] = __shfl_sync(0xffffffffu, sv.Ma_sh[i], owner);
+        sv.x_sh[i] = __shfl_sync(0xffffffffu, sv.x_sh[i], owner); sv.tau_sh[i] = __shfl_sync(0xffffffffu, sv.tau_sh[i], owner);
+      }
+#pragma unroll
+      for (int i = 0; i < 9; ++i) kl.R[i] = __shfl_sync(0xffffffffu, k.R[i], owner);
+      SharedRows<T>& sr2 = sv.sr;
+      sr2.eqD = __shfl_sync(0xffffffffu, sr2.eqD, owner); sr2.eq_aref = __shfl_sync(0xffffffffu, sr2.eq_aref, owner);
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        sr2.flD[i] = __shfl_sync(0xffffffffu, sr2.flD[i], owner); sr2.flR[i] = __shfl_sync(0xffffffffu, sr2.flR[i], owner);
+        sr2.flf[i] = __shfl_sync(0xffffffffu, sr2.flf[i], owner); sr2.fl_aref[i] = __shfl_sync(0xffffffffu, sr2.fl_aref[i], owner);
+        sr2.limD[i] = __shfl_sync(0xffffffffu, sr2.limD[i], owner); sr2.lim_sign[i] = __shfl_sync(0xffffffffu, sr2.lim_sign[i], owner);
+        sr2.lim_aref[i] = __shfl_sync(0xffffffffu, sr2.lim_aref[i], owner);
+      }
+      sv.iter = __shfl_sync(0xffffffffu, sv.iter, owner);
+      sv.lam2 = __shfl_sync(0xffffffffu, sv.lam2, owner);
+      sv.szone0 = __shfl_sync(0xffffffffu, sv.szone0, owner);
+      sv.first = __shfl_sync(0xffffffffu, sv.first ? 1 : 0, owner) != 0;
+      sv.phase = serve ? 0 : 2;
+      wb = lid & 3;
+      whp = reinterpret_cast<WheelT*>(reinterpret_cast<T*>(wh) + (owner - lid) * rec_stride) + wb;
+      tail = true;
+      __syncwarp();
+#else
+      break;
+#endif
+    }
+#if defined(__CUDA_ARCH__)
+    if (TAIL && tail) {   // warp-uniform: hand the accelerations back to the lanes that own the environments
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const T v = __shfl_sync(0xffffffffu, sv.a_sh[i], my_src); sv.a_sh[i] = my_active ? v : a_keep[i]; }
+      const int it2 = __shfl_sync(0xffffffffu, sv.iter, my_src);
+      sv.iter = my_active ? it2 : iter_keep;
+    }
+#endif
+    const int iter = sv.iter, nls = sv.nls;
     diag.niter = iter;
 
     // ---- B16 implicit joint damping.  At the minimiser M~ a = tau + J^T f, so MuJoCo's integration acceleration

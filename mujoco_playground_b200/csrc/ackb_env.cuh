@@ -143,7 +143,7 @@ struct EnvOps {
   // so that the sink's storage may alias the wheel records.
   template <class Sink, class Emit>
   ACKB_HD static void step_env(const Consts<T>& C, State& e, WheelT* wh, Episode<T>& ep, float a0, float a1, int frame_skip, int lane,
-                               Sink& sink, Emit&& emit, StepOut<T>& out, StepDiag& diag, DebugTap<T>* tap, bool cta_sync = false) {
+                               Sink& sink, Emit&& emit, StepOut<T>& out, StepDiag& diag, DebugTap<T>* tap, bool cta_sync = false, int rec_stride = 0) {
     T ctrl[4];
     action_to_ctrl<T>(C, a0, a1, ctrl);
     T dist = T(0), minl = T(0);
@@ -167,7 +167,7 @@ struct EnvOps {
         }
       }
       diag.ncon = 0;
-      S::dynamics(C, e, k, ctrl, lane, wh, diag, tap);
+      S::dynamics(C, e, k, ctrl, lane, wh, diag, tap, rec_stride);
     }
     reward_done(C, ep, dist, minl, out);
   }

@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(Geo<T, LANES, NC>::kBlock, Geo<T, LANES, NC>::
 
   StepOut<T> out;
   StepDiag diag{0, 0, 0};
-  E::step_env(C, e, wh, ep, a0, a1, a.frame_skip, lane, sink, emit, out, diag, (DebugTap<T>*)nullptr, a.cta_sync != 0);
+  E::step_env(C, e, wh, ep, a0, a1, a.frame_skip, lane, sink, emit, out, diag, (DebugTap<T>*)nullptr, a.cta_sync != 0, G::kSmemWheels ? G::kStride : 0);
   __syncwarp();
 
   // contact count of the last substep, summed over the lanes of the environment

@@ -1,0 +1,5 @@
+cd $GRAFT_REPO_ROOT
+for v in tail2off l1sync l1syncpass l1sync64; do
+  ACKB_LIB=build/variants/$v.so python tools/gpu/time_step.py --envs 131072 --lanes 1 --tag $v
+  ACKB_LIB=build/variants/$v.so python tools/gpu/time_step.py --envs 131072 --lanes 1 --fs 1 --tag $v
+done
