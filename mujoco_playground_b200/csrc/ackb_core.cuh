@@ -362,7 +362,7 @@ ACKB_HD void action_to_ctrl(const Consts<T>& C, float a0, float a1, T* ctrl) {
 // ------------------------------------------------------------------------------------------------
 template <typename T>
 struct Contact {
-  T x[3];     // contact point, body frame
+  T x[3];     // contact point relative to the chassis origin, WORLD axes (the solver works in world axes, see Sim::solve_loop)
   T D;        // 1/R of its pyramid rows (0: contact absent or excluded)
   T z[3];     // residual F Jp a - aref along (n, t1, t2) at the current point
   T zv[3];    // image F Jp x of the current step direction
@@ -392,15 +392,64 @@ ACKB_HD void contact_frame(const Kin<T>& k, int code, T* n, T* t1, T* t2) {
   for (int i = 0; i < 3; ++i) { n[i] = sn * pn[i]; t1[i] = s1 * p1[i]; t2[i] = s2 * p2[i]; }
 }
 
+// Every contact frame of the two models is a signed permutation of the world axes (floor: (n, t1, t2) = (+z, +y, -x); box
+// faces: see contact_frame).  In world axes a frame is therefore applied with selects instead of 3 x 3 products:
+//   pat 0: (n, t1, t2) along (x, y, z)   pat 1: along (y, z, x)   pat 2: along (z, y, x);  sn, s1, s2 = +-1.
+// Packed form (8 bits): pat | (sn < 0) << 2 | (s1 < 0) << 3 | (s2 < 0) << 4.
+template <typename T>
+struct Perm {
+  int pat;
+  T sn, s1, s2;
+};
+ACKB_HD constexpr unsigned perm_pack(int code) {
+  // code 0 floor (+z,+y,-x); 1: -(+x,+y,+z); 2: -(-x,+y,-z); 3: -(+y,+z,+x); 4: -(-y,+z,-x); 5: -(-z,+y,+x)   (contact_frame)
+  return code == 0 ? (2u | 16u) : code == 1 ? (0u | 4u | 8u | 16u) : code == 2 ? (0u | 8u) : code == 3 ? (1u | 4u | 8u | 16u)
+       : code == 4 ? (1u | 8u) : (2u | 8u | 16u);
+}
+template <typename T>
+ACKB_HD Perm<T> perm_unpack(unsigned p) {
+  Perm<T> q;
+  q.pat = (int)(p & 3u);
+  q.sn = (p & 4u) ? T(-1) : T(1); q.s1 = (p & 8u) ? T(-1) : T(1); q.s2 = (p & 16u) ? T(-1) : T(1);
+  return q;
+}
+// frame components (n, t1, t2) of a world vector y
+template <typename T>
+ACKB_HD void perm_apply(const Perm<T>& q, const T* y, T* out) {
+  out[0] = q.sn * (q.pat == 0 ? y[0] : (q.pat == 1 ? y[1] : y[2]));
+  out[1] = q.s1 * (q.pat == 1 ? y[2] : y[1]);
+  out[2] = q.s2 * (q.pat == 0 ? y[2] : y[0]);
+}
+// world vector of frame components phi
+template <typename T>
+ACKB_HD void perm_apply_t(const Perm<T>& q, const T* phi, T* out) {
+  const T a = q.sn * phi[0], b = q.s1 * phi[1], c = q.s2 * phi[2];
+  out[0] = q.pat == 0 ? a : c;
+  out[1] = q.pat == 1 ? a : b;
+  out[2] = q.pat == 0 ? c : (q.pat == 1 ? b : a);
+}
+// world 3 x 3 (symmetric) of the frame-space matrix [[A, E, F], [E, B, 0], [F, 0, Cc]] (rows / columns n, t1, t2)
+template <typename T>
+ACKB_HD void perm_sym(const Perm<T>& q, T A, T B, T Cc, T E, T F, T (*S3)[3]) {
+  E *= q.sn * q.s1; F *= q.sn * q.s2;
+  S3[0][0] = q.pat == 0 ? A : Cc;
+  S3[1][1] = q.pat == 1 ? A : B;
+  S3[2][2] = q.pat == 0 ? Cc : (q.pat == 1 ? B : A);
+  S3[0][1] = S3[1][0] = q.pat == 0 ? E : (q.pat == 1 ? F : T(0));
+  S3[0][2] = S3[2][0] = q.pat == 1 ? T(0) : F;
+  S3[1][2] = S3[2][1] = q.pat == 0 ? T(0) : E;
+}
+
 template <typename T, int NC>
 struct Wheel {
   T sp, dsp, warm;   // state: spin angle, rate, warm-start acceleration
   T ax, ay;          // spin axis (ax, ay, 0) in the body frame
+  T axw[3], cww[3];  // spin axis and wheel centre (relative to the chassis origin) in world axes
   T a, x, tau;       // solver: spin acceleration, step direction, smooth force
   T g, cw;           // gradient entry and Schur pivot of the spin dof at the last assembly
   T b[7];            // coupling of the spin dof with (lin3, ang3, own steer)
   unsigned zone0;    // activity pattern of the wheel's rows at the last assembly
-  unsigned fcode;    // frame codes of the box contact slots (4 bits each, slots 2 and 3)
+  unsigned fcode;    // packed frame permutations of the box contact slots (8 bits each, slots 2 and 3; see Perm)
   Contact<T> con[NC];
 };
 
@@ -432,6 +481,22 @@ ACKB_HD void contact_cols(const Wheel<T, NC>& w, const WheelK<T>& wk, const T* X
   u[0] = w.ay * r2; u[1] = -w.ax * r2; u[2] = w.ax * r1 - w.ay * r0;   // (ax, ay, 0) x r
   const T st = wk.isL + wk.isR;
   wv[0] = -r1 * st; wv[1] = r0 * st;
+}
+
+// world axes: spin column u = axis_w x r and steer column wv = st * (ez_w x r) of the point Jacobian, r = X - centre_w
+template <typename T, int NC>
+ACKB_HD void contact_cols_w(const Wheel<T, NC>& w, T st, const T* ezw, const T* X, T* u, T* wv) {
+  const T r[3] = {X[0] - w.cww[0], X[1] - w.cww[1], X[2] - w.cww[2]};
+  cross3(u, w.axw, r);
+  cross3(wv, ezw, r);
+  wv[0] *= st; wv[1] *= st; wv[2] *= st;
+}
+// world axes: point "acceleration" y = a_lin + a_ang x X + a_spin u + a_steer wv
+template <typename T>
+ACKB_HD void point_accel_w(const T* X, const T* u, const T* wv, const T* alin, const T* aang, T aspin, T asteer, T* y) {
+  cross3(y, aang, X);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) y[i] += alin[i] + aspin * u[i] + asteer * wv[i];
 }
 
 // point "acceleration" y = a_lin + a_ang x X + a_spin u + a_steer w, projected on the contact frame (n, t1, t2)
@@ -710,6 +775,10 @@ struct Sim {
       con.z[0] = C.w_B[wi] * vel[0] + C.w_K[wi] * imp * dd;
       con.z[1] = C.w_B[wi] * vel[1];
       con.z[2] = C.w_B[wi] * vel[2];
+      // the solver works in world axes: keep the point as R X (relative to the chassis origin)
+      const T xb[3] = {con.x[0], con.x[1], con.x[2]};
+#pragma unroll
+      for (int i = 0; i < 3; ++i) con.x[i] = k.R[3 * i] * xb[0] + k.R[3 * i + 1] * xb[1] + k.R[3 * i + 2] * xb[2];
     }
   }
 
@@ -781,19 +850,20 @@ struct Sim {
       pw[bk] -= T(bs) * best * T(0.5);
       Contact<T> con;   // filled here, then copied to slot NC-2 or NC-1 with static indices (keeps register records in registers)
       con.zv[0] = con.zv[1] = con.zv[2] = T(0);
+      T xb[3];          // body-frame point for the velocity of the contact; the record keeps the world-axes point pw
 #pragma unroll
-      for (int i = 0; i < 3; ++i) con.x[i] = k.R[i] * pw[0] + k.R[3 + i] * pw[1] + k.R[6 + i] * pw[2];
+      for (int i = 0; i < 3; ++i) { xb[i] = k.R[i] * pw[0] + k.R[3 + i] * pw[1] + k.R[6 + i] * pw[2]; con.x[i] = pw[i]; }
       // normal from the wheel to the box is -s e_k:  +x 1, -x 2, +y 3, -y 4, -z 5 (+z: wheel below a box, never happens)
       const int code = (bk == 0) ? (bs < 0 ? 1 : 2) : ((bk == 1) ? (bs < 0 ? 3 : 4) : 5);
-      fcode |= (unsigned)code << (4 * nfound);
+      fcode |= perm_pack(code) << (8 * nfound);
       const T mu = wk.mu;
       const T imp = impedance(&C.w_solimp[5 * wi], best);
       const T R0 = mjmax(N::minval, (T(1) - imp) * N::rcp_(imp) * C.w_tran[wi] * (T(1) + mu * mu));
       con.D = (best < T(0)) ? N::rcp_(T(2) * C.w_mureg2[wi] * R0) : T(0);
       T u[3], wv[2], vel[3], fn[3], ft1[3], ft2[3];
-      contact_cols(w, wk, con.x, u, wv);
+      contact_cols(w, wk, xb, u, wv);
       contact_frame(k, code, fn, ft1, ft2);
-      project_point(fn, ft1, ft2, con.x, u, wv, vb, e.om, w.dsp, dsteer, vel);
+      project_point(fn, ft1, ft2, xb, u, wv, vb, e.om, w.dsp, dsteer, vel);
       con.z[0] = C.w_B[wi] * vel[0] + C.w_K[wi] * imp * best;
       con.z[1] = C.w_B[wi] * vel[1];
       con.z[2] = C.w_B[wi] * vel[2];
@@ -847,45 +917,10 @@ struct Sim {
     return f;
   }
 
-  // constant shared block of M~ (packed lower triangle)
-  ACKB_HD static void shared_mass(const Consts<T>& C, T* S) {
-#pragma unroll
-    for (int i = 0; i < 36; ++i) S[i] = T(0);
-    const T m = C.mass[0], cx = C.mcom[0], cy = C.mcom[1], cz = C.mcom[2];
-    S[tri(0, 0)] = S[tri(1, 1)] = S[tri(2, 2)] = m;
-    // (ang, lin) block = [m c]x
-    S[tri(3, 1)] = -cz; S[tri(3, 2)] = cy;
-    S[tri(4, 0)] = cz;  S[tri(4, 2)] = -cx;
-    S[tri(5, 0)] = -cy; S[tri(5, 1)] = cx;
-    const T* I = C.inertiaO;
-    S[tri(3, 3)] = I[0]; S[tri(4, 4)] = I[1]; S[tri(5, 5)] = I[2];
-    S[tri(4, 3)] = I[3]; S[tri(5, 3)] = I[4]; S[tri(5, 4)] = I[5];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      S[tri(6 + i, 5)] = C.h_inertia[i];
-      S[tri(6 + i, 6 + i)] = C.h_inertia[i] + C.h_armature[i];
-    }
-  }
-
-  // shared part of M~ x given the team-summed wheel term acc = sum_w J a_w x_spin,w
-  ACKB_HD static void mul_M_shared(const Consts<T>& C, const T* x_sh, const T* acc, T* y_sh) {
-    T c1[3], c2[3];
-    cross3(c1, C.mcom, x_sh + 3);  // m c x a_ang
-    cross3(c2, C.mcom, x_sh);      // m c x a_lin
-    const T* I = C.inertiaO;
-    const T* a = x_sh + 3;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) y_sh[i] = C.mass[0] * x_sh[i] - c1[i];
-    y_sh[3] = c2[0] + I[0] * a[0] + I[3] * a[1] + I[4] * a[2] + acc[0];
-    y_sh[4] = c2[1] + I[3] * a[0] + I[1] * a[1] + I[5] * a[2] + acc[1];
-    y_sh[5] = c2[2] + I[4] * a[0] + I[5] * a[1] + I[2] * a[2] + acc[2] + C.h_inertia[0] * x_sh[6] + C.h_inertia[1] * x_sh[7];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) y_sh[6 + i] = C.h_inertia[i] * a[2] + (C.h_inertia[i] + C.h_armature[i]) * x_sh[6 + i];
-  }
-
   // solver variables that live across the Newton loop (kept in registers; a struct so that the loop can be instantiated twice)
   struct SolverVars {
-    T a_sh[8], Ma_sh[8], x_sh[8], tau_sh[8];
+    T a_sh[8], Ma_sh[8], x_sh[8], tau_sh[8];   // shared dofs in WORLD axes: lin3, ang3, steer L, steer R
+    T mcw[3], Iw[6], ezw[3];                    // m c, inertia about the chassis origin (xx yy zz xy xz yz), steer axis: world axes
     SharedRows<T> sr;
     int iter, nls, phase;
     bool first;
@@ -893,11 +928,52 @@ struct Sim {
     unsigned szone0;
   };
 
+  // shared block of M~ in world axes (packed lower triangle)
+  ACKB_HD static void shared_mass(const Consts<T>& C, const SolverVars& sv, T* S) {
+#pragma unroll
+    for (int i = 0; i < 36; ++i) S[i] = T(0);
+    const T m = C.mass[0], cx = sv.mcw[0], cy = sv.mcw[1], cz = sv.mcw[2];
+    S[tri(0, 0)] = S[tri(1, 1)] = S[tri(2, 2)] = m;
+    // (ang, lin) block = [m c]x
+    S[tri(3, 1)] = -cz; S[tri(3, 2)] = cy;
+    S[tri(4, 0)] = cz;  S[tri(4, 2)] = -cx;
+    S[tri(5, 0)] = -cy; S[tri(5, 1)] = cx;
+    const T* I = sv.Iw;
+    S[tri(3, 3)] = I[0]; S[tri(4, 4)] = I[1]; S[tri(5, 5)] = I[2];
+    S[tri(4, 3)] = I[3]; S[tri(5, 3)] = I[4]; S[tri(5, 4)] = I[5];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j) S[tri(6 + i, 3 + j)] = C.h_inertia[i] * sv.ezw[j];
+      S[tri(6 + i, 6 + i)] = C.h_inertia[i] + C.h_armature[i];
+    }
+  }
+
+  // shared part of M~ x (world axes) given the team-summed wheel term acc = sum_w J axis_w x_spin,w
+  ACKB_HD static void mul_M_shared(const Consts<T>& C, const SolverVars& sv, const T* x_sh, const T* acc, T* y_sh) {
+    T c1[3], c2[3];
+    cross3(c1, sv.mcw, x_sh + 3);  // m c x a_ang
+    cross3(c2, sv.mcw, x_sh);      // m c x a_lin
+    const T* I = sv.Iw;
+    const T* a = x_sh + 3;
+    const T hs = C.h_inertia[0] * x_sh[6] + C.h_inertia[1] * x_sh[7];
+    const T eza = dot3(sv.ezw, a);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) y_sh[i] = C.mass[0] * x_sh[i] - c1[i];
+    y_sh[3] = c2[0] + I[0] * a[0] + I[3] * a[1] + I[4] * a[2] + acc[0] + sv.ezw[0] * hs;
+    y_sh[4] = c2[1] + I[3] * a[0] + I[1] * a[1] + I[5] * a[2] + acc[1] + sv.ezw[1] * hs;
+    y_sh[5] = c2[2] + I[4] * a[0] + I[5] * a[1] + I[2] * a[2] + acc[2] + sv.ezw[2] * hs;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) y_sh[6 + i] = C.h_inertia[i] * eza + (C.h_inertia[i] + C.h_armature[i]) * x_sh[6 + i];
+  }
+
   // ---- the Newton loop (B13-B15), see `dynamics`.  TL = false: the layout's own team (LANES lanes, WPL wheels per lane).
   // TL = true (tail mode of the 1-lane layout): 4 lanes per environment, one wheel record each, reached through `whp`.
   // (TL is a warp-uniform run-time flag and the loop is instantiated ONCE: a second copy of the body costs more in instruction
   // fetch than tail mode saves -- measured: 134 M -> 106 M env-steps/s at 131072 envs, frame_skip 4.)
-  ACKB_HD static void solve_loop(const Consts<T>& C, const Kin<T>& kl, WheelT* whp, const int wbase, const int ncs, SolverVars& sv,
+  // The shared dofs are expressed in WORLD axes (lin3, ang3, steer L, steer R): every contact frame is then a signed permutation
+  // of the axes (Perm), so rows, forces and the 3 x 3 contact Hessians need no frame products.
+  ACKB_HD static void solve_loop(const Consts<T>& C, WheelT* whp, const int wbase, const int ncs, SolverVars& sv,
                                  const bool exit_for_tail, const bool TL) {
     const int wpl = TL ? 1 : WPL;
     T (&a_sh)[8] = sv.a_sh; T (&Ma_sh)[8] = sv.Ma_sh; T (&x_sh)[8] = sv.x_sh; T (&tau_sh)[8] = sv.tau_sh;
@@ -925,23 +1001,25 @@ struct Sim {
           const int wi = wbase + s;
           const WheelK<T> wk = wheel_consts(C, wi);
           WheelT& w = whp[s];
-          const T aw_aang_x = w.ax * x_sh[3] + w.ay * x_sh[4], aw_aang_a = w.ax * a_sh[3] + w.ay * a_sh[4];
+          const T aw_aang_x = dot3(w.axw, x_sh + 3), aw_aang_a = dot3(w.axw, a_sh + 3);
           const T Mv_sp = wk.J * aw_aang_x + wk.cdiag * w.x, Ma_sp = wk.J * aw_aang_a + wk.cdiag * w.a;
           const T pwt = pair_weight();
-          acc[0] += pwt * wk.J * w.ax * w.x; acc[1] += pwt * wk.J * w.ay * w.x;
+          const T jx = pwt * wk.J * w.x;
+          acc[0] += jx * w.axw[0]; acc[1] += jx * w.axw[1]; acc[2] += jx * w.axw[2];
           acc[3] += pwt * w.x * Mv_sp; acc[4] += pwt * w.x * (Ma_sp - w.tau);
           const T ast = wk.isL * x_sh[6] + wk.isR * x_sh[7];
+          const T stw = wk.isL + wk.isR;
           ACKB_CONTACTS_BEGIN(c)
             Contact<T>& con = w.con[c];
-            T u[3], wv[2], fn[3], ft1[3], ft2[3];
-            contact_cols(w, wk, con.x, u, wv);
-            contact_frame(kl, c < 2 ? 0 : (int)((w.fcode >> (4 * (c - 2))) & 15u), fn, ft1, ft2);
-            project_point(fn, ft1, ft2, con.x, u, wv, x_sh, x_sh + 3, w.x, ast, con.zv);
+            T u[3], wv[3], y[3];
+            contact_cols_w(w, stw, sv.ezw, con.x, u, wv);
+            point_accel_w(con.x, u, wv, x_sh, x_sh + 3, w.x, ast, y);
+            perm_apply(perm_unpack<T>(c < 2 ? perm_pack(0) : ((w.fcode >> (8 * (c - 2))) & 255u)), y, con.zv);
           ACKB_CONTACTS_END
         }
         team_sum_n(acc, TL);
         T Mv_sh[8];
-        mul_M_shared(C, x_sh, acc, Mv_sh);
+        mul_M_shared(C, sv, x_sh, acc, Mv_sh);
         T sMs = acc[3], sg = acc[4];
 #pragma unroll
         for (int i = 0; i < 8; ++i) { sMs += x_sh[i] * Mv_sh[i]; sg += x_sh[i] * (Ma_sh[i] - tau_sh[i]); }
@@ -1050,31 +1128,21 @@ struct Sim {
         const T mu = wk.mu;
         ACKB_CONTACTS_BEGIN(c)
           const Contact<T>& con = w.con[c];
-          T phi[3], qq[4], fn[3], ft1[3], ft2[3];
-          contact_frame(kl, c < 2 ? 0 : (int)((w.fcode >> (4 * (c - 2))) & 15u), fn, ft1, ft2);
+          T phi[3], qq[4];
+          const Perm<T> pf = perm_unpack<T>(c < 2 ? perm_pack(0) : ((w.fcode >> (8 * (c - 2))) & 255u));
           pyramid_rows(con.D, mu, con.z, phi, qq);
           {
             const unsigned zb = (qq[0] != T(0) ? 1u : 0u) | (qq[1] != T(0) ? 2u : 0u) | (qq[2] != T(0) ? 4u : 0u) | (qq[3] != T(0) ? 8u : 0u);
             zone = (zone << 4) | ((con.D > T(0)) ? zb : 0u);
           }
-          // S3 = D F^T W F with W the active-row weights on (n, t1, t2); symmetric 3x3 in the body frame
+          // S3 = D F^T W F with W the active-row weights on (n, t1, t2); F is a signed permutation of the world axes
           const T W00 = qq[0] + qq[1] + qq[2] + qq[3], W01 = mu * (qq[0] - qq[1]), W02 = mu * (qq[2] - qq[3]);
           const T W11 = mu * mu * (qq[0] + qq[1]), W22 = mu * mu * (qq[2] + qq[3]);
-          T r0[3], r1[3], r2[3];
-#pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            r0[i] = con.D * (W00 * fn[i] + W01 * ft1[i] + W02 * ft2[i]);
-            r1[i] = con.D * (W01 * fn[i] + W11 * ft1[i]);
-            r2[i] = con.D * (W02 * fn[i] + W22 * ft2[i]);
-          }
           T S3[3][3];
-#pragma unroll
-          for (int i = 0; i < 3; ++i)
-#pragma unroll
-            for (int j = 0; j <= i; ++j) { S3[i][j] = fn[i] * r0[j] + ft1[i] * r1[j] + ft2[i] * r2[j]; S3[j][i] = S3[i][j]; }
+          perm_sym(pf, con.D * W00, con.D * W11, con.D * W22, con.D * W01, con.D * W02, S3);
           const T X[3] = {con.x[0], con.x[1], con.x[2]};
-          T u[3], wv[2];
-          contact_cols(w, wk, X, u, wv);
+          T u[3], wv[3];
+          contact_cols_w(w, wk.isL + wk.isR, sv.ezw, X, u, wv);
           Hll[0] += S3[0][0]; Hll[1] += S3[1][0]; Hll[2] += S3[1][1]; Hll[3] += S3[2][0]; Hll[4] += S3[2][1]; Hll[5] += S3[2][2];
           // (ang, lin) block: column j = X x S3[:, j];  (ang, ang) block: column j = X x (S3 g_j), g_j = e_j x X
           T Cj[3][3];
@@ -1097,22 +1165,21 @@ struct Sim {
           // spin column u and steer column wv
           T Su[3], Sw[3], XSu[3], XSw[3];
 #pragma unroll
-          for (int i = 0; i < 3; ++i) { Su[i] = S3[i][0] * u[0] + S3[i][1] * u[1] + S3[i][2] * u[2]; Sw[i] = S3[i][0] * wv[0] + S3[i][1] * wv[1]; }
+          for (int i = 0; i < 3; ++i) { Su[i] = S3[i][0] * u[0] + S3[i][1] * u[1] + S3[i][2] * u[2]; Sw[i] = S3[i][0] * wv[0] + S3[i][1] * wv[1] + S3[i][2] * wv[2]; }
           cross3(XSu, X, Su);
           cross3(XSw, X, Sw);
 #pragma unroll
           for (int i = 0; i < 3; ++i) { bl[i] += Su[i]; ba[i] += XSu[i]; Hsl[i] += Sw[i]; Hsa[i] += XSw[i]; }
           cs += dot3(u, Su);
-          bs += wv[0] * Su[0] + wv[1] * Su[1];
-          Hss += wv[0] * Sw[0] + wv[1] * Sw[1];
+          bs += dot3(wv, Su);
+          Hss += dot3(wv, Sw);
           // body-frame contact force and its generalised image (enters the gradient with a minus sign)
           T Phi[3], XF[3];
-#pragma unroll
-          for (int i = 0; i < 3; ++i) Phi[i] = fn[i] * phi[0] + ft1[i] * phi[1] + ft2[i] * phi[2];
+          perm_apply_t(pf, phi, Phi);
           cross3(XF, X, Phi);
 #pragma unroll
           for (int i = 0; i < 3; ++i) { gl[i] -= Phi[i]; ga[i] -= XF[i]; }
-          gst -= wv[0] * Phi[0] + wv[1] * Phi[1];
+          gst -= dot3(wv, Phi);
           gs_sp -= dot3(u, Phi);
         ACKB_CONTACTS_END
         if (PAIR) {
@@ -1120,9 +1187,9 @@ struct Sim {
 #pragma unroll
           for (int i = 0; i < 3; ++i) { bl[i] = Tm::pair_sum(bl[i]); ba[i] = Tm::pair_sum(ba[i]); }
         }
-        gs_sp += wk.J * (w.ax * a_sh[3] + w.ay * a_sh[4]) + wk.cdiag * w.a - w.tau - f;
+        gs_sp += wk.J * dot3(w.axw, a_sh + 3) + wk.cdiag * w.a - w.tau - f;
         cs += wk.cdiag + q * wk.flD;
-        ba[0] += wk.J * w.ax; ba[1] += wk.J * w.ay;
+        ba[0] += wk.J * w.axw[0]; ba[1] += wk.J * w.axw[1]; ba[2] += wk.J * w.axw[2];
         if (phase == 0) w.zone0 = zone;
         w.g = gs_sp; w.cw = cs;
         T b8[8], gsh_w[8];
@@ -1156,7 +1223,7 @@ struct Sim {
       }
       team_sum_n(part, TL);
       T S[36];
-      shared_mass(C, S);
+      shared_mass(C, sv, S);
 #pragma unroll
       for (int i = 0; i < 36; ++i) S[i] += part[i];
       T fL, fR, hLL, hLR, hRR;
@@ -1221,6 +1288,11 @@ struct Sim {
       WheelT& w = wh[s];
       collide_wheel(C, e, k, vb, wi, lane & 1, wk, w, diag);
       if (NC > 2) collide_boxes(C, e, k, vb, wi, wk, w, diag);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {   // spin axis and wheel centre in world axes (solver)
+        w.axw[i] = k.R[3 * i] * w.ax + k.R[3 * i + 1] * w.ay;
+        w.cww[i] = k.R[3 * i] * wk.c[0] + k.R[3 * i + 1] * wk.c[1] + k.R[3 * i + 2] * wk.c[2];
+      }
       const T dsteer = wk.isL * e.dst[0] + wk.isR * e.dst[1];
       const T aw[3] = {w.ax, w.ay, T(0)};
       const T ez[3] = {T(0), T(0), T(1)};
@@ -1292,13 +1364,37 @@ struct Sim {
       for (int i = 0; i < 2; ++i)   // unrolled: a rolled loop would index tau_sh / bpart / e.st dynamically and push them to local memory
         tau_sh[6 + i] = -C.h_damping[i] * e.dst[i] - bpart[6 + i] + actuator_force(C, ctrl, i, e.st[i], e.dst[i]);
     }
+    if (tap) for (int i = 0; i < 8; ++i) tap->tau[i] = tau_sh[i];   // body-frame smooth force (MuJoCo's qfrc_smooth up to the frame)
+    // ---- world-axes quantities of this substep for the solver: tau, m c, I_O, steer axis
+    {
+      const T tl[3] = {tau_sh[0], tau_sh[1], tau_sh[2]}, ta[3] = {tau_sh[3], tau_sh[4], tau_sh[5]};
+      T RI[9];   // R I_O
+      const T* I = C.inertiaO;
+      const T Im[9] = {I[0], I[3], I[4], I[3], I[1], I[5], I[4], I[5], I[2]};
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        tau_sh[i] = k.R[3 * i] * tl[0] + k.R[3 * i + 1] * tl[1] + k.R[3 * i + 2] * tl[2];
+        tau_sh[3 + i] = k.R[3 * i] * ta[0] + k.R[3 * i + 1] * ta[1] + k.R[3 * i + 2] * ta[2];
+        sv.mcw[i] = k.R[3 * i] * C.mcom[0] + k.R[3 * i + 1] * C.mcom[1] + k.R[3 * i + 2] * C.mcom[2];
+        sv.ezw[i] = k.R[3 * i + 2];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) RI[3 * i + j] = k.R[3 * i] * Im[j] + k.R[3 * i + 1] * Im[3 + j] + k.R[3 * i + 2] * Im[6 + j];
+      }
+      // I_w = (R I_O) R^T, symmetric: xx yy zz xy xz yz
+      sv.Iw[0] = RI[0] * k.R[0] + RI[1] * k.R[1] + RI[2] * k.R[2];
+      sv.Iw[1] = RI[3] * k.R[3] + RI[4] * k.R[4] + RI[5] * k.R[5];
+      sv.Iw[2] = RI[6] * k.R[6] + RI[7] * k.R[7] + RI[8] * k.R[8];
+      sv.Iw[3] = RI[0] * k.R[3] + RI[1] * k.R[4] + RI[2] * k.R[5];
+      sv.Iw[4] = RI[0] * k.R[6] + RI[1] * k.R[7] + RI[2] * k.R[8];
+      sv.Iw[5] = RI[3] * k.R[6] + RI[4] * k.R[7] + RI[5] * k.R[8];
+    }
 
     // current point a (starts at 0 and takes a unit step along the warm start), M~ a
     T (&a_sh)[8] = sv.a_sh; T (&Ma_sh)[8] = sv.Ma_sh; T (&x_sh)[8] = sv.x_sh;
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      x_sh[i] = k.R[i] * e.warm_l[0] + k.R[3 + i] * e.warm_l[1] + k.R[6 + i] * e.warm_l[2];
-      x_sh[3 + i] = e.warm_a[i];
+    for (int i = 0; i < 3; ++i) {   // MuJoCo keeps the linear part in world axes and the angular part in body axes
+      x_sh[i] = e.warm_l[i];
+      x_sh[3 + i] = k.R[3 * i] * e.warm_a[0] + k.R[3 * i + 1] * e.warm_a[1] + k.R[3 * i + 2] * e.warm_a[2];
     }
     x_sh[6] = e.warm_st[0]; x_sh[7] = e.warm_st[1];
 #pragma unroll
@@ -1324,7 +1420,6 @@ struct Sim {
     // environments of the warp are still iterating, pass 0 returns and they are re-spread over the warp with 4 lanes each
     // (lane = wheel, as in the 4-lane layout): the solver state of environment number r moves to lanes 4r .. 4r+3 by shuffles,
     // the wheel records are reached in place.
-    Kin<T> kl = k;
     WheelT* whp = wh;
     int wb = wheel_index(lane, 0);
     bool tail = false;
@@ -1335,7 +1430,7 @@ struct Sim {
 #endif
 #pragma unroll 1
     for (int pass = 0; pass < 2; ++pass) {
-      solve_loop(C, kl, whp, wb, ncs, sv, tail_ok && pass == 0, tail);
+      solve_loop(C, whp, wb, ncs, sv, tail_ok && pass == 0, tail);
 #if defined(__CUDA_ARCH__)
       if (!TAIL) break;
       const unsigned act = __ballot_sync(0xffffffffu, sv.phase != 2);
@@ -1356,7 +1451,9 @@ struct Sim {
         sv.x_sh[i] = __shfl_sync(0xffffffffu, sv.x_sh[i], owner); sv.tau_sh[i] = __shfl_sync(0xffffffffu, sv.tau_sh[i], owner);
       }
 #pragma unroll
-      for (int i = 0; i < 9; ++i) kl.R[i] = __shfl_sync(0xffffffffu, k.R[i], owner);
+      for (int i = 0; i < 3; ++i) { sv.mcw[i] = __shfl_sync(0xffffffffu, sv.mcw[i], owner); sv.ezw[i] = __shfl_sync(0xffffffffu, sv.ezw[i], owner); }
+#pragma unroll
+      for (int i = 0; i < 6; ++i) sv.Iw[i] = __shfl_sync(0xffffffffu, sv.Iw[i], owner);
       SharedRows<T>& sr2 = sv.sr;
       sr2.eqD = __shfl_sync(0xffffffffu, sr2.eqD, owner); sr2.eq_aref = __shfl_sync(0xffffffffu, sr2.eq_aref, owner);
 #pragma unroll
@@ -1389,6 +1486,14 @@ struct Sim {
     }
 #endif
     const int iter = sv.iter, nls = sv.nls;
+    {   // back to the chassis frame for the rest of the step: a~ = [R^T a_lin ; R^T a_ang ; hinges]
+      const T al[3] = {a_sh[0], a_sh[1], a_sh[2]}, aa[3] = {a_sh[3], a_sh[4], a_sh[5]};
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        a_sh[i] = k.R[i] * al[0] + k.R[3 + i] * al[1] + k.R[6 + i] * al[2];
+        a_sh[3 + i] = k.R[i] * aa[0] + k.R[3 + i] * aa[1] + k.R[6 + i] * aa[2];
+      }
+    }
     diag.niter = iter;
 
     // ---- B16 implicit joint damping.  At the minimiser M~ a = tau + J^T f, so MuJoCo's integration acceleration
@@ -1439,7 +1544,7 @@ struct Sim {
     }
 
     if (tap) {
-      for (int i = 0; i < 8; ++i) { tap->tau[i] = tau_sh[i]; tap->a_smooth[i] = T(0); tap->a[i] = a_sh[i]; tap->fc[i] = T(0); }
+      for (int i = 0; i < 8; ++i) { tap->a_smooth[i] = T(0); tap->a[i] = a_sh[i]; tap->fc[i] = T(0); }
       for (int s = 0; s < WPL; ++s) {
         int wi = wheel_index(lane, s);
         tap->tau[8 + wi] = wh[s].tau; tap->a_smooth[8 + wi] = T(0); tap->a[8 + wi] = wh[s].a; tap->fc[8 + wi] = T(0);
