@@ -145,6 +145,9 @@ def run_reference(args, rank, world):
 
 
 def workload_name(args, world):
+    if getattr(args, "workload", "flat") == "scene":
+        return (f"configs[2]: ackermann obstacle scene (ackermann_maze_flat.xml), {args.envs or 65536} envs per GPU, AckermannController, "
+                f"spawn yaw U(-pi,pi) + xy jitter 0.12 m, random actions, frame_skip={args.frame_skip}")
     if args.envs:
         return f"ackermann flat-floor, {args.envs} envs per GPU, random actions, frame_skip={args.frame_skip}"
     if world == 1:
@@ -162,10 +165,12 @@ def run_cuda(args, rank, local_rank, world):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    n_envs = args.envs or (4096 if world == 1 else 131072)
+    scene = args.workload == "scene"
+    n_envs = args.envs or (65536 if scene else (4096 if world == 1 else 131072))
     fs = args.frame_skip
+    kw = dict(model="scene", spawn_yaw_range=3.141592653589793, spawn_xy_jitter=0.12) if scene else {}
     env = BatchedAckermannEnv(n_envs, device=dev, frame_skip=fs, dtype=args.dtype, seed=1234 + rank, auto_reset=True,
-                              lanes_per_env=args.lanes)
+                              lanes_per_env=args.lanes, **kw)
     env.reset()
     # steady state of a long rollout: episode phases staggered uniformly (resets spread over time instead of all
     # environments resetting in the same step), and the robots already landed on their wheels
@@ -232,6 +237,8 @@ def run_cuda(args, rank, local_rank, world):
     if rank == 0:
         peak, how = measured_peak_gbs()
         algo = ALGO_BYTES_F32 if args.dtype == "float32" else ALGO_BYTES_F64
+        if scene:   # 36-beam observation (43 floats): 506 B per env-step in fp32
+            algo -= (79 - env.obs_dim) * 4
         avg_launch_s = (sum(step_ms) / len(step_ms)) * 1e-3
         achieved = algo * n_envs / avg_launch_s / 1e9
         traffic, traffic_note, warp_inst = measured_traffic(args.dtype, n_envs, fs)
@@ -256,10 +263,12 @@ def run_cuda(args, rank, local_rank, world):
             "gpu_launches": int(launches),
             "clocks": clocks,
             "solver": {"mean_newton_iters_per_env_step": stats["solver_iters"] / max(1, stats["env_steps"]),
-                       "episodes": stats["episodes"], "unsupported_contact_steps": stats["unsupported"]},
+                       "episodes": stats["episodes"], "unsupported_contact_steps": stats["unsupported"],
+                       "mean_ncon_last_substep": stats["contacts_sum"] / max(1, stats["env_steps"]),
+                       "obstacle_contact_step_fraction": stats["obstacle_steps"] / max(1, stats["env_steps"])},
             "wall_s_timed_region": t_wall,
         }
-        if world == 1 and not args.envs and not args.no_aux:
+        if world == 1 and not args.envs and not args.no_aux and not scene:
             # the same kernel at the per-GPU batch of configs[3] (131072 envs), for context next to the 4096-env headline
             env.close()
             big = BatchedAckermannEnv(131072, device=dev, frame_skip=fs, dtype=args.dtype, seed=99, auto_reset=True, lanes_per_env=args.lanes)
@@ -280,7 +289,7 @@ def run_cuda(args, rank, local_rank, world):
                            "value": 131072 / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms,
                            "roofline_frac": algo * 131072 / (ms * 1e-3) / 1e9 / peak}
             big.close()
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not scene:
             cores = os.cpu_count() or 1
             per = max(50, args.cpu_steps // fs)
             v, tmax = cpu_rollout(per, fs, cores)
@@ -306,6 +315,7 @@ def main():
     ap.add_argument("--no-aux", action="store_true", help="skip the extra large-batch measurement at N=1")
     ap.add_argument("--cpu-steps", type=int, default=800000, help="physics substeps per CPU process for the CPU arm sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="flat", choices=["flat", "scene"], help="flat = configs[1]/[3] (default), scene = configs[2]")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
     rank = int(os.environ.get("RANK", 0))

@@ -43,6 +43,8 @@ typedef struct {
   unsigned long long solver_iters;  /* Newton iterations summed over substeps                */
   double return_sum;                /* sum of finished episodes' returns                     */
   double length_sum;                /* sum of finished episodes' lengths                     */
+  unsigned long long obstacle_steps;/* env steps with >= 1 wheel-vs-obstacle contact in their last substep (scene)   */
+  unsigned long long contacts_sum;  /* contacts detected in the last substep of every env step, summed (mean ncon)   */
 } ackb_stats_t;
 
 /* Size, in doubles, of the model-constants blob this build expects (layout: ackb_consts.def). */

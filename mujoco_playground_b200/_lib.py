@@ -13,7 +13,8 @@ _lib = None
 class AckbStats(ctypes.Structure):
     _fields_ = [("episodes", ctypes.c_ulonglong), ("successes", ctypes.c_ulonglong), ("env_steps", ctypes.c_ulonglong),
                 ("collisions", ctypes.c_ulonglong), ("unsupported", ctypes.c_ulonglong), ("solver_iters", ctypes.c_ulonglong),
-                ("return_sum", ctypes.c_double), ("length_sum", ctypes.c_double)]
+                ("return_sum", ctypes.c_double), ("length_sum", ctypes.c_double),
+                ("obstacle_steps", ctypes.c_ulonglong), ("contacts_sum", ctypes.c_ulonglong)]
 
 
 # every symbol include/ackb.h declares: (restype, argtypes)

@@ -264,6 +264,7 @@ struct StepDiag {
   int ncon;         // contacts detected (dist <= 0) over all wheels of this lane
   int unsupported;  // geometry outside the supported contact set
   int niter;
+  int nbox;         // wheel-vs-obstacle contacts among ncon
 };
 
 // index of element (i, j), i >= j, in a packed lower triangle
@@ -843,7 +844,7 @@ struct Sim {
           if (sep > best) { best = sep; bk = kk; bs = sgn; bp[0] = pp[0]; bp[1] = pp[1]; bp[2] = pp[2]; }
         }
       if (best > T(0)) continue;
-      diag.ncon += 1;
+      diag.ncon += 1; diag.nbox += 1;
       if (nfound >= 2) { diag.unsupported = 1; continue; }
       // contact point midway between the surfaces, world -> body frame
       T pw[3] = {bp[0] + bcx - e.p[0], bp[1] + bcy - e.p[1], bp[2] + C.box_z[0] - e.p[2]};

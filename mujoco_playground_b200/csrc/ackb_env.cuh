@@ -166,7 +166,7 @@ struct EnvOps {
           for (int i = 0; i < WPL; ++i) { wh[i].sp = keep[3 * i]; wh[i].dsp = keep[3 * i + 1]; wh[i].warm = keep[3 * i + 2]; }
         }
       }
-      diag.ncon = 0;
+      diag.ncon = 0; diag.nbox = 0;
       S::dynamics(C, e, k, ctrl, lane, wh, diag, tap, rec_stride);
     }
     reward_done(C, ep, dist, minl, out);

@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(Geo<T, LANES, NC>::kBlock, Geo<T, LANES, NC>::
   };
 
   StepOut<T> out;
-  StepDiag diag{0, 0, 0};
+  StepDiag diag{0, 0, 0, 0};
   E::step_env(C, e, wh, ep, a0, a1, a.frame_skip, lane, sink, emit, out, diag, (DebugTap<T>*)nullptr, a.cta_sync != 0, G::kSmemWheels ? G::kStride : 0);
   __syncwarp();
 
@@ -196,6 +196,7 @@ __global__ void __launch_bounds__(Geo<T, LANES, NC>::kBlock, Geo<T, LANES, NC>::
   int ncon = diag.ncon, unsup = diag.unsupported;
   ncon = Team<LANES>::sum(ncon);
   unsup = Team<LANES>::sum(unsup);
+  const int nbox = Team<LANES>::sum(diag.nbox);
 
   const bool done = out.terminated || out.truncated;
   float ret = st.ep_return[env] + out.reward;
@@ -207,6 +208,7 @@ __global__ void __launch_bounds__(Geo<T, LANES, NC>::kBlock, Geo<T, LANES, NC>::
     unsigned v_done = warp_sum_u32(lead && done ? 1u : 0u), v_succ = warp_sum_u32(lead && out.terminated ? 1u : 0u);
     unsigned v_coll = warp_sum_u32(lead && out.collision ? 1u : 0u), v_uns = warp_sum_u32(lead && unsup ? 1u : 0u);
     unsigned v_it = warp_sum_u32(lead ? (unsigned)diag.niter : 0u);
+    unsigned v_box = warp_sum_u32(lead && nbox > 0 ? 1u : 0u), v_con = warp_sum_u32(lead ? (unsigned)ncon : 0u);
     float r_sum = lead && done ? ret : 0.f, l_sum = lead && done ? (float)ep_len : 0.f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { r_sum += __shfl_xor_sync(0xffffffffu, r_sum, o); l_sum += __shfl_xor_sync(0xffffffffu, l_sum, o); }
@@ -216,6 +218,8 @@ __global__ void __launch_bounds__(Geo<T, LANES, NC>::kBlock, Geo<T, LANES, NC>::
       if (v_coll) atomicAdd(&a.stats->collisions, (unsigned long long)v_coll);
       if (v_uns) atomicAdd(&a.stats->unsupported, (unsigned long long)v_uns);
       atomicAdd(&a.stats->solver_iters, (unsigned long long)v_it);
+      if (v_box) atomicAdd(&a.stats->obstacle_steps, (unsigned long long)v_box);
+      atomicAdd(&a.stats->contacts_sum, (unsigned long long)v_con);
     }
   }
 

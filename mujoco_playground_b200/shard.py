@@ -22,17 +22,18 @@ def rank_seed(seed: int, rank: int) -> int:
     return (int(seed) * 0x9E3779B97F4A7C15 + rank * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
 
 
-_KEYS = ("episodes", "successes", "env_steps", "collisions", "unsupported", "solver_iters", "return_sum", "length_sum")
+_KEYS = ("episodes", "successes", "env_steps", "collisions", "unsupported", "solver_iters", "obstacle_steps", "contacts_sum",
+         "return_sum", "length_sum")
 
 
 def reduce_stats(stats: Dict[str, float], device=None, group=None) -> Dict[str, float]:
     """Sum the per-rank ackb_stats dictionaries over the process group (identity when not initialised)."""
     if not (dist.is_available() and dist.is_initialized()):
         return dict(stats)
-    t = torch.tensor([float(stats[k]) for k in _KEYS], dtype=torch.float64, device=device)
+    t = torch.tensor([float(stats.get(k, 0)) for k in _KEYS], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     out = {k: float(v) for k, v in zip(_KEYS, t.tolist())}
-    for k in _KEYS[:6]:
+    for k in _KEYS[:8]:
         out[k] = int(round(out[k]))
     return out
 

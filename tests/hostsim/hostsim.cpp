@@ -41,7 +41,7 @@ void substep(const double* blob, double* qpos, double* qvel, double* warm, const
   E::load_state(acc, 0, e, wh);
   T ctrl[4];
   for (int i = 0; i < 4; ++i) ctrl[i] = (T)ctrl_in[i];
-  StepDiag diag{0, 0, 0};
+  StepDiag diag{0, 0, 0, 0};
   DebugTap<T> tap;
   for (int s = 0; s < nsteps; ++s) {
     Kin<T> k;
@@ -72,7 +72,7 @@ void env_step(const double* blob, double* qpos, double* qvel, double* warm, doub
   ep.step_count = epi[0]; ep.episode = (uint32_t)epi[1];
   ObsSink sink{obs};
   StepOut<T> so;
-  StepDiag diag{0, 0, 0};
+  StepDiag diag{0, 0, 0, 0};
   E::step_env(C, e, wh, ep, action[0], action[1], frame_skip, 0, sink, [] {}, so, diag, (DebugTap<T>*)nullptr);
   E::store_state(acc, 0, e, wh);
   epi[0] = ep.step_count;
@@ -124,7 +124,7 @@ void env_step_team(const double* blob, double* qpos, double* qvel, double* warm,
       ep.step_count = epi[0]; ep.episode = (uint32_t)epi[1];
       ObsSink sink{obs};
       StepOut<T> so;
-      StepDiag diag{0, 0, 0};
+      StepDiag diag{0, 0, 0, 0};
       E::step_env(C, e, wh, ep, action[0], action[1], frame_skip, lane, sink, [] {}, so, diag, (DebugTap<T>*)nullptr);
       bar.arrive_and_wait();           // every lane finished reading the shared state arrays
       E::store_state(acc, lane, e, wh);

@@ -100,7 +100,7 @@ def _gloo_worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     lo, hi = shard_range(1001, rank, world)
     stats = dict(episodes=hi - lo, successes=rank, env_steps=10 * (hi - lo), collisions=1, unsupported=0, solver_iters=3,
-                 return_sum=-1.5 * (rank + 1), length_sum=100.0)
+                 obstacle_steps=2 * rank, contacts_sum=8 * (hi - lo), return_sum=-1.5 * (rank + 1), length_sum=100.0)
     red = reduce_stats(stats)
     t = max_over_ranks(1.0 + rank)
     dist.destroy_process_group()
@@ -121,4 +121,5 @@ def test_sharding_and_stats_reduction_gloo_world2():
     (r0, lo0, hi0, red0, t0), (r1, lo1, hi1, red1, t1) = res
     assert (lo0, hi0, lo1, hi1) == (0, 501, 501, 1001)
     assert red0 == red1 and red0["episodes"] == 1001 and red0["env_steps"] == 10010 and red0["successes"] == 1
+    assert red0["obstacle_steps"] == 2 and red0["contacts_sum"] == 8008
     assert abs(red0["return_sum"] + 4.5) < 1e-12 and t0 == t1 == 2.0

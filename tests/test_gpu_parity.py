@@ -263,3 +263,70 @@ def test_scene_rollout_with_spawn_jitter_stays_supported():
     st = env.stats()
     assert st["unsupported"] < 0.01 * st["env_steps"]
     env.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE.json's full sizes, through size-independent properties
+# ---------------------------------------------------------------------------------------------------------------
+def test_full_size_flat_batch_is_layout_and_size_invariant():
+    """configs[3] size (131072 envs, 1 lane per env, tail mode) against configs[1] size (4096 envs, 4 lanes per env): goals,
+    synthetic actions and resets are keyed by (seed, env id, step), so environment i must follow the same trajectory in both
+    batches whatever the batch size, lane layout or CTA it runs in.  fp32, 12 env-steps of 4 substeps: tolerance 2e-4 on qpos,
+    flags and contact counts exact; plus run-to-run bit reproducibility of the large batch."""
+    from mujoco_playground_b200 import BatchedAckermannEnv
+    steps, small_n, big_n = 12, 4096, 131072
+    out = {}
+    for tag, n in (("small", small_n), ("big", big_n), ("big2", big_n)):
+        env = BatchedAckermannEnv(n, dtype="float32", seed=77, frame_skip=4, auto_reset=True, max_episode_steps=7)
+        env.reset()
+        flags, ncon = [], []
+        for _ in range(steps):
+            obs, rew, term, trunc, info = env.step(None)
+            flags.append(torch.stack([term[:small_n], trunc[:small_n]]).cpu().numpy().copy())
+            ncon.append(info["ncon"][:small_n].cpu().numpy().copy())
+        q, v, _ = env.get_state()
+        out[tag] = (q, v, obs.cpu().numpy().copy(), np.array(flags), np.array(ncon), rew.cpu().numpy().copy())
+        st = env.stats()
+        assert st["unsupported"] == 0 and st["episodes"] == n, "one truncation (auto-reset) per environment in 12 steps"
+        assert np.isfinite(q).all() and np.isfinite(out[tag][2]).all()
+        env.close()
+    qs, vs, os_, fs_, ns, _ = out["small"]
+    qb, vb, ob, fb, nb, _ = out["big"]
+    assert np.array_equal(fs_, fb), "done flags must match exactly"
+    assert np.array_equal(ns, nb), "contact counts must match exactly"
+    assert np.abs(qs - qb[:small_n]).max() < 2e-4
+    assert np.abs(os_ - ob[:small_n]).max() < 2e-3
+    for a, b in zip(out["big"], out["big2"]):
+        assert np.array_equal(a, b), "two runs of the same batch must be bit identical"
+
+
+def test_full_size_scene_rollout_properties():
+    """configs[2] size: 65536 obstacle-scene environments with spawn jitter.  Properties: finite state, robots stay above the
+    floor and inside the maze walls, contact counts in range, a visible fraction of env-steps has wheel-box contacts, the share
+    of env-steps with unsupported contact geometry stays below 1 %."""
+    from mujoco_playground_b200 import BatchedAckermannEnv
+    n = 65536
+    env = BatchedAckermannEnv(n, model="scene", dtype="float32", seed=5, frame_skip=4, spawn_yaw_range=np.pi, spawn_xy_jitter=0.12)
+    env.reset()
+    with_box = 0
+    max_ncon = 0
+    for _ in range(60):
+        obs, rew, term, trunc, info = env.step(None)
+        nc = info["ncon"]
+        with_box += int((nc > 8).sum().item())
+        max_ncon = max(max_ncon, int(nc.max().item()))
+    q, v, _ = env.get_state()
+    assert np.isfinite(q).all() and np.isfinite(v).all() and torch.isfinite(obs).all() and torch.isfinite(rew).all()
+    # (larger jitters start robots overlapping a wall block; those are pushed out violently, as in MuJoCo, and are not a sane workload)
+    assert (q[:, 2] > -0.01).all() and (q[:, 2] < 0.3).all(), f"chassis height stays physical: {q[:, 2].min()} .. {q[:, 2].max()}"
+    assert ((q[:, 2] > 0.05) & (q[:, 2] < 0.09)).mean() > 0.995, "robots drive on the floor"
+    assert (np.abs(q[:, 0]) < 4.5).all() and (np.abs(q[:, 1]) < 4.5).all(), "nobody leaves the maze"
+    assert np.abs(np.linalg.norm(q[:, 3:7], axis=1) - 1).max() < 1e-3
+    assert 8 <= max_ncon <= 16
+    st = env.stats()
+    frac = st["obstacle_steps"] / st["env_steps"]
+    assert frac > 0.002, f"fraction of env-steps with a wheel-obstacle contact {frac}"
+    # random +-50 rad/s wheel commands make the light robot hop: the oracle shows the same 0..8 contact distribution with mean ~2
+    assert 1.0 < st["contacts_sum"] / st["env_steps"] <= 9.0, "mean contact count"
+    assert st["unsupported"] < 0.001 * st["env_steps"]
+    env.close()

@@ -59,7 +59,9 @@ def main():
     st = env.stats()
     print(json.dumps({"tag": a.tag, "lib": os.path.basename(_lib.LIB_PATH), "envs": a.envs, "lanes": a.lanes, "fs": a.fs, "set": a.set,
                       "ms": round(best, 4), "Msteps_s": round(a.envs / best / 1e3, 2),
-                      "iters_per_env_step": round(st["solver_iters"] / max(1, st["env_steps"]), 3), "unsupported": st["unsupported"]}), flush=True)
+                      "iters_per_env_step": round(st["solver_iters"] / max(1, st["env_steps"]), 3), "unsupported": st["unsupported"],
+                      "mean_ncon": round(st["contacts_sum"] / max(1, st["env_steps"]), 3),
+                      "obstacle_frac": round(st["obstacle_steps"] / max(1, st["env_steps"]), 5)}), flush=True)
     env.close()
 
 
