@@ -1,9 +1,12 @@
 """B200-native batched simulator for the Ackermann env-step hot path of ulusoyn/mujoco_playground."""
-__all__ = ["BatchedAckermannEnv", "AckermannRobotEnv"]
+__all__ = ["BatchedAckermannEnv", "AckermannRobotEnv", "make_ackermann_env", "list_available_mazes"]
 
 
 def __getattr__(name):
-    if name in __all__:
+    if name in ("BatchedAckermannEnv", "AckermannRobotEnv"):
         from . import env
         return getattr(env, name)
+    if name in ("make_ackermann_env", "list_available_mazes"):
+        from . import make_env
+        return getattr(make_env, name)
     raise AttributeError(name)

@@ -125,6 +125,7 @@ def ppo_update(policy: ActorCritic, opt: torch.optim.Optimizer, batch: Dict[str,
     n = batch["obs"].shape[0]
     mb = max(1, n // cfg.minibatches)
     stats = dict(pg_loss=0.0, v_loss=0.0, entropy=0.0, approx_kl=0.0, clip_frac=0.0, steps=0, allreduce_bytes=0)
+    acc = torch.zeros(5, device=batch["obs"].device)      # diagnostics accumulate on the device: one host read per update
     params = [p for p in policy.parameters() if p.requires_grad]
     for _ in range(cfg.n_epochs):
         perm = torch.randperm(n, device=batch["obs"].device, generator=generator)
@@ -143,12 +144,11 @@ def ppo_update(policy: ActorCritic, opt: torch.optim.Optimizer, batch: Dict[str,
             torch.nn.utils.clip_grad_norm_(params, cfg.max_grad_norm)
             opt.step()
             with torch.no_grad():
-                stats["pg_loss"] += float(pg); stats["v_loss"] += float(vl); stats["entropy"] += float(ent.mean())
-                stats["approx_kl"] += float(((ratio - 1) - (logp - old_logp)).mean())
-                stats["clip_frac"] += float(((ratio - 1).abs() > cfg.clip_range).float().mean())
+                acc += torch.stack([pg.detach(), vl.detach(), ent.mean(), ((ratio - 1) - (logp - old_logp)).mean(),
+                                    ((ratio - 1).abs() > cfg.clip_range).float().mean()])
                 stats["steps"] += 1
-    for k in ("pg_loss", "v_loss", "entropy", "approx_kl", "clip_frac"):
-        stats[k] /= max(1, stats["steps"])
+    for k, v in zip(("pg_loss", "v_loss", "entropy", "approx_kl", "clip_frac"), (acc / max(1, stats["steps"])).tolist()):
+        stats[k] = v
     return stats
 
 
@@ -180,12 +180,11 @@ class PPOTrainer:
             act, logp, val = self.policy.act(obs)
             b["obs"][t], b["act"][t], b["logp"][t], b["val"][t] = obs, act, logp, val
             nobs, rew, term, trunc, info = env.step(torch.clamp(act, -1.0, 1.0))     # SB3 clips to the Box bounds
-            rew = rew.clone()
-            only_trunc = (trunc != 0) & (term == 0)
-            if bool(only_trunc.any()):                # bootstrap with V(terminal observation) on time-limit truncation
-                tv = self.policy.value(sanitize_obs(info["terminal_observation"][only_trunc]))
-                rew[only_trunc] += cfg.gamma * tv
-            b["rew"][t] = rew
+            # bootstrap with V(terminal observation) on time-limit truncation; evaluated for every environment and masked, so
+            # that the rollout loop has no device->host synchronisation (rows of environments that did not finish are stale, unused)
+            only_trunc = ((trunc != 0) & (term == 0)).float()
+            tv = self.policy.value(sanitize_obs(info["terminal_observation"]))
+            b["rew"][t] = rew + cfg.gamma * tv * only_trunc
             b["done"][t] = ((term != 0) | (trunc != 0)).float()
             self.obs.copy_(nobs)
         self.num_timesteps += cfg.n_steps * env.num_envs * self.world

@@ -22,13 +22,23 @@ from .shard import rank_seed, reduce_stats
 
 
 def main(argv=None):
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--algo", default="random", choices=["random", "ppo"])          # train.py:232
-    ap.add_argument("--timesteps", type=int, default=100000)                          # train.py:236
-    ap.add_argument("--max-velocity", type=float, default=1.0)
-    ap.add_argument("--goal-threshold", type=float, default=0.5)
-    ap.add_argument("--learning-rate", type=float, default=3e-4)
-    ap.add_argument("--save-path", default="")
+    ap = argparse.ArgumentParser(description="Train Ackermann Robot RL Agent (batched B200 environment)")
+    # ---- the reference's flags (src/rl/train.py:231-259), same names, defaults and meaning ---------------------------------
+    ap.add_argument("--algo", default="random", choices=["random", "ppo", "sac", "td3"], help="RL algorithm to use")
+    ap.add_argument("--episodes", type=int, default=1000, help="Number of episodes (for random)")
+    ap.add_argument("--timesteps", type=int, default=100000, help="Number of timesteps (for PPO)")
+    ap.add_argument("--render", action="store_true", help="Render environment during training (not available: no viewer on the GPU path)")
+    ap.add_argument("--max-velocity", type=float, default=1.0, help="Maximum linear velocity (m/s)")
+    ap.add_argument("--goal-threshold", type=float, default=0.5, help="Goal distance threshold (m)")
+    ap.add_argument("--maze", default=None, choices=[None, "umaze", "open", "medium", "large"],
+                    help="Gymnasium Robotics maze (needs the un-vendored gymnasium-robotics XML: falls back to the default environment)")
+    ap.add_argument("--maze-id", default="PointMaze_UMaze-v3", help="Gymnasium Robotics maze environment ID")
+    ap.add_argument("--learning-rate", type=float, default=None, help="Learning rate for the algorithm (PPO default 3e-4)")
+    ap.add_argument("--save-freq", type=int, default=10000, help="Frequency (timesteps) to save model checkpoints (needs --save-path)")
+    ap.add_argument("--eval-freq", type=int, default=10000, help="Frequency (timesteps) to evaluate the model")
+    ap.add_argument("--eval-episodes", type=int, default=10, help="Number of episodes for the final evaluation (0 = skip)")
+    # ---- batched-environment additions --------------------------------------------------------------------------------------
+    ap.add_argument("--save-path", default="", help="prefix for <prefix>_<N>_steps.zip / <prefix>_final.zip (SB3 layout, see sb3_io)")
     ap.add_argument("--num-envs", type=int, default=4096, help="environments per GPU")
     ap.add_argument("--frame-skip", type=int, default=1)
     ap.add_argument("--n-steps", type=int, default=16)
@@ -38,6 +48,13 @@ def main(argv=None):
     ap.add_argument("--seed", type=int, default=0)
     a = ap.parse_args(argv)
 
+    if a.algo in ("sac", "td3"):
+        raise SystemExit(f"--algo {a.algo}: only the PPO path of the reference is built (SAC / TD3 are out of scope, DESIGN.md section 8)")
+    if a.render:
+        raise SystemExit("--render: the viewer is outside the hot path; there is no rendering on the GPU path")
+    if a.maze is not None:
+        print("Warning: gymnasium-robotics not installed. Using default environment.")     # train.py:271
+        print("Install with: pip install gymnasium-robotics")
     world = int(os.environ.get("WORLD_SIZE", 1))
     rank = int(os.environ.get("RANK", 0))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -51,6 +68,7 @@ def main(argv=None):
                               max_linear_velocity=a.max_velocity, goal_distance_threshold=a.goal_threshold)
     if a.algo == "random":
         env.reset()
+        # the reference runs `episodes` episodes of one environment (train.py:189-227); here: until that many episodes finished
         steps = max(1, a.timesteps // (a.num_envs * world))
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
@@ -63,11 +81,27 @@ def main(argv=None):
             print(json.dumps({"algo": "random", "env_steps": st["env_steps"], "env_steps_per_s": st["env_steps"] / dt, "episodes": st["episodes"],
                               "ep_rew_mean": st["return_sum"] / max(1, st["episodes"])}))
     else:
-        cfg = PPOConfig(n_steps=a.n_steps, n_epochs=a.n_epochs, minibatches=a.minibatches, learning_rate=a.learning_rate)
+        from .sb3_io import evaluate_agent, save_sb3_policy
+        cfg = PPOConfig(n_steps=a.n_steps, n_epochs=a.n_epochs, minibatches=a.minibatches,
+                        learning_rate=3e-4 if a.learning_rate is None else a.learning_rate)
         tr = PPOTrainer(env, cfg, seed=a.seed)
-        tr.train(a.timesteps, log=lambda d: print(json.dumps(d), flush=True))
-        if a.save_path:
-            tr.save(a.save_path)
+        next_save = [a.save_freq]
+
+        def log(d):
+            print(json.dumps(d), flush=True)
+            if a.save_path and rank == 0 and d["timesteps"] >= next_save[0]:     # CheckpointCallback (train.py:140-144)
+                save_sb3_policy(tr.policy, f"{a.save_path}_{d['timesteps']}_steps.zip", tr.opt, d["timesteps"])
+                while next_save[0] <= d["timesteps"]:
+                    next_save[0] += max(1, a.save_freq)
+
+        tr.train(a.timesteps, log=log)
+        if a.save_path and rank == 0:                                               # model.save (train.py:182-183)
+            save_sb3_policy(tr.policy, f"{a.save_path}_final.zip", tr.opt, tr.num_timesteps)
+        if a.eval_episodes > 0:                                                     # evaluate_agent (train.py:303-309)
+            ev = evaluate_agent(env, tr.policy, n_steps=min(1000, env.max_episode_steps if hasattr(env, "max_episode_steps") else 1000))
+            ev = {**ev, "evaluation": True}
+            if rank == 0:
+                print(json.dumps(ev), flush=True)
     env.close()
     if world > 1:
         dist.destroy_process_group()

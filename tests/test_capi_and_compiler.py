@@ -123,3 +123,19 @@ def test_sharding_and_stats_reduction_gloo_world2():
     assert red0 == red1 and red0["episodes"] == 1001 and red0["env_steps"] == 10010 and red0["successes"] == 1
     assert red0["obstacle_steps"] == 2 and red0["contacts_sum"] == 8008
     assert abs(red0["return_sum"] + 4.5) < 1e-12 and t0 == t1 == 2.0
+
+
+def test_factory_signature_matches_the_reference_pyc(capsys):
+    """make_ackermann_env / list_available_mazes: argument names, order and defaults recovered from the reference's
+    src/rl/__pycache__/make_env.cpython-312.pyc (the source file is missing upstream)."""
+    import inspect
+    from mujoco_playground_b200 import list_available_mazes, make_ackermann_env
+    sig = inspect.signature(make_ackermann_env)
+    names = list(sig.parameters)
+    assert names[:6] == ["env_type", "maze_id", "render_mode", "max_linear_velocity", "max_angular_velocity", "goal_distance_threshold"]
+    d = {k: v.default for k, v in sig.parameters.items()}
+    assert (d["env_type"], d["maze_id"], d["render_mode"]) == ("maze", "PointMaze_UMaze-v3", None)
+    assert (d["max_linear_velocity"], d["max_angular_velocity"], d["goal_distance_threshold"]) == (0.5, 1.0, 0.3)
+    assert list_available_mazes() == [] and "gymnasium-robotics not installed" in capsys.readouterr().out
+    with pytest.raises(ValueError, match="Unknown environment type"):
+        make_ackermann_env(env_type="nope")
