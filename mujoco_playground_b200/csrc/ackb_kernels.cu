@@ -392,6 +392,8 @@ int launch_one(ackb_handle* h, DevState<T>& st, const StepArgs& a, cudaStream_t 
     using GR = Geo<T, LANES, 2>;   // the reset kernel has its own geometry (records in local storage)
     const int rgrid = (int)((threads + GR::kBlock - 1) / GR::kBlock);
     const size_t smem = (size_t)(GR::kBlock / LANES) * a.obs_dim * sizeof(float);
+    static bool rattr_done = false;
+    if (!rattr_done && smem > 48 * 1024) { CK(cudaFuncSetAttribute(reset_kernel<T, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); rattr_done = true; }
     reset_kernel<T, LANES><<<rgrid, GR::kBlock, smem, stream>>>(st, a);
   } else {
     const size_t smem = G::smem_bytes(a.obs_dim);
