@@ -1,9 +1,9 @@
 """B200-native batched simulator for the Ackermann env-step hot path of ulusoyn/mujoco_playground."""
-__all__ = ["BatchedAckermannEnv", "AckermannRobotEnv", "make_ackermann_env", "list_available_mazes"]
+__all__ = ["BatchedAckermannEnv", "AckermannRobotEnv", "AckermannGymnasiumMazeEnv", "make_ackermann_env", "list_available_mazes"]
 
 
 def __getattr__(name):
-    if name in ("BatchedAckermannEnv", "AckermannRobotEnv"):
+    if name in ("BatchedAckermannEnv", "AckermannRobotEnv", "AckermannGymnasiumMazeEnv"):
         from . import env
         return getattr(env, name)
     if name in ("make_ackermann_env", "list_available_mazes"):

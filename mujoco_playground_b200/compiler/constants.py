@@ -54,6 +54,11 @@ def _mix(M, g1, g2):
     return fr, solref, solimp
 
 
+def consts_get(blob, lay, name):
+    off, cnt = lay[name]
+    return blob[off] if cnt == 1 else blob[off:off + cnt]
+
+
 def _box_grid(centres: np.ndarray, half: np.ndarray):
     """Occupancy grid of identical axis-aligned boxes, or None if they do not sit on a lattice of box-sized cells
     listed in (x, y) lexicographic order (the order fixes the contact slot order of wheel-box contacts)."""
@@ -260,19 +265,21 @@ def build_consts(M: dict, *, model_kind: int, max_episode_steps: int = 1000, goa
     put("w_mu", wmu); put("w_mureg2", wmr); put("w_K", wK); put("w_B", wB); put("w_solimp", np.concatenate(wsi)); put("w_tran", wtr)
     if boxes:
         put("wb_mu", bmu); put("wb_mureg2", bmr); put("wb_K", bK); put("wb_B", bB); put("wb_solimp", np.concatenate(bsi))
-        assert len(boxes) <= 40
         hs = M["geom_size"][boxes[0]]
         for g in boxes:
             assert np.allclose(M["geom_size"][g], hs) and np.allclose(M["geom_quat"][g], [1, 0, 0, 0])
             assert M["body_weldid"][M["geom_bodyid"][g]] == 0 and M["geom_pos"][g][2] == M["geom_pos"][boxes[0]][2]
         put("nbox", len(boxes)); put("box_half", hs); put("box_z", M["geom_pos"][boxes[0]][2])
-        put("box_cx", [M["geom_pos"][g][0] + M["body_pos"][M["geom_bodyid"][g]][0] for g in boxes])
-        put("box_cy", [M["geom_pos"][g][1] + M["body_pos"][M["geom_bodyid"][g]][1] for g in boxes])
+        if len(boxes) <= 40:
+            put("box_cx", [M["geom_pos"][g][0] + M["body_pos"][M["geom_bodyid"][g]][0] for g in boxes])
+            put("box_cy", [M["geom_pos"][g][1] + M["body_pos"][M["geom_bodyid"][g]][1] for g in boxes])
         grid = _box_grid(np.array([[M["geom_pos"][g][0] + M["body_pos"][M["geom_bodyid"][g]][0],
                                     M["geom_pos"][g][1] + M["body_pos"][M["geom_bodyid"][g]][1]] for g in boxes]), np.asarray(hs, float))
         if grid is not None and use_box_grid:
             put("grid_on", 1); put("grid_x0", grid["x0"]); put("grid_y0", grid["y0"]); put("grid_pitch", grid["pitch"])
             put("grid_nx", grid["nx"]); put("grid_ny", grid["ny"]); put("grid_rows", grid["rows"])
+        else:
+            assert len(boxes) <= 40, "more than 40 boxes need the occupancy grid (boxes on a lattice, listed in (x, y) order)"
 
     # plate hull points (only if the plates can collide with the floor)
     pts = []
@@ -332,7 +339,7 @@ def build_consts(M: dict, *, model_kind: int, max_episode_steps: int = 1000, goa
     assert np.allclose(cut, cut[0])
     put("nbeam", nbeam); put("lidar_pos", M["body_pos"][lb]); put("lidar_r", rad[0]); put("lidar_cutoff", cut[0])
     put("lidar_cos", cos_); put("lidar_sin", sin_)
-    if lidar_index_map == "reference" and model_kind == 0:
+    if lidar_index_map == "reference" and model_kind in (0, 2):   # same robot XML and the same _setup_lidar code in both env classes
         # ackermann_env.py:126-141: mj_name2id("lidar-{i}") is -1 for i < 10 (names are zero padded),
         # and model.sensor_adr[-1] is the last sensor's address  => slots 0..9 all read the last beam.
         sn = M["sensor_names"]
@@ -357,6 +364,15 @@ def build_consts(M: dict, *, model_kind: int, max_episode_steps: int = 1000, goa
         if model_kind == 0:
             spawn_qpos[0:3] = [0, 0, 0.1]          # ackermann_env.py:151, simple_map_spawner.py:43-50
             spawn_qpos[3:7] = [1, 0, 0, 0]
+        if model_kind == 2:
+            spawn_qpos[0:3] = [0, 0, float(M["maze_spawn_z"][0])]   # xy: start cell + noise, drawn per episode
+            spawn_qpos[3:7] = [1, 0, 0, 0]
     put("spawn_qpos", spawn_qpos)
     put("spawn_yaw_range", spawn_yaw_range); put("spawn_xy_jitter", spawn_xy_jitter)
+    if model_kind == 2:
+        g = M["maze_grid"]
+        assert consts_get(blob, lay, "grid_on") == 1 and np.allclose([consts_get(blob, lay, "grid_x0"), consts_get(blob, lay, "grid_y0"),
+                                                                        consts_get(blob, lay, "grid_pitch")], g[:3])
+        put("maze_on", 1); put("maze_free_rows", M["maze_free_rows"]); put("maze_xy_noise", float(M["maze_xy_noise"][0]))
+        put("settle_steps", int(M["maze_settle_steps"][0]))
     return blob

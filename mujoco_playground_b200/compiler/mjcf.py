@@ -271,13 +271,14 @@ def _parse_body_children(ctx: _Ctx, el: ET.Element, bid: int, fpos, fquat, suffi
             raise NotImplementedError(f"MJCF element <{ch.tag}> inside <body>")
 
 
-def compile_mjcf(xml_path: str, mesh_inertia: str = "legacy") -> dict:
+def compile_mjcf(xml_path: str, mesh_inertia: str = "legacy", root: Optional[ET.Element] = None) -> dict:
     """Compile the MJCF file into a MuJoCo-style table model (dict of ndarrays).
 
     mesh_inertia: "legacy" | "exact" | "convex"  (MuJoCo mesh ``inertia`` modes; the default of the
     MuJoCo 3.x releases contemporary with the reference's checkpoints is "legacy").
     """
-    root = ET.parse(xml_path).getroot()
+    if root is None:           # `root`: an already parsed / edited tree; xml_path then only anchors relative mesh paths
+        root = ET.parse(xml_path).getroot()
     ctx = _Ctx(xml_path, mesh_inertia)
     _expand_includes(root, ctx.dir)
 

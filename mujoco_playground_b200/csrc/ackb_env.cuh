@@ -126,6 +126,36 @@ struct EnvOps {
       T q0 = e.q[0], q1 = e.q[1], q2 = e.q[2], q3 = e.q[3];  // q <- qz(yaw) * q
       e.q[0] = cz * q0 - sz * q3; e.q[1] = cz * q1 - sz * q2; e.q[2] = cz * q2 + sz * q1; e.q[3] = cz * q3 + sz * q0;
     }
+    const bool maze = C.maze_on[0] != T(0);
+    T maze_goal[2] = {T(0), T(0)};
+    if (maze) {
+      // PointMaze reset (gymnasium_robotics maze.generate_target_goal / generate_reset_pos, restated in compiler/maze.py): goal cell
+      // and a different start cell drawn uniformly from the free cells, each with uniform xy noise; identity orientation
+      uint32_t r3[4];
+      philox4x32(ep.episode, env_id, 3u, 0x41434B42u, (uint32_t)seed, (uint32_t)(seed >> 32), r3);
+      const int nx = (int)C.grid_nx[0], ny = (int)C.grid_ny[0];
+      int nfree = 0;
+      for (int iy = 0; iy < ny; ++iy) { unsigned m = (unsigned)C.maze_free_rows[iy]; for (int ix = 0; ix < nx; ++ix) nfree += (int)((m >> ix) & 1u); }
+      int gi = (int)(u01(r3[0]) * (float)nfree); gi = gi >= nfree ? nfree - 1 : gi;
+      int si = (int)(u01(r3[1]) * (float)(nfree - 1)); si = si >= nfree - 1 ? nfree - 2 : si;
+      if (nfree > 1 && si >= gi) si += 1;          // start cell != goal cell
+      if (nfree <= 1) si = gi;
+      int cnt = 0;
+      T sc[2] = {T(0), T(0)};
+      for (int iy = 0; iy < ny; ++iy) {
+        const unsigned m = (unsigned)C.maze_free_rows[iy];
+        for (int ix = 0; ix < nx; ++ix) {
+          if (!((m >> ix) & 1u)) continue;
+          const T cx = C.grid_x0[0] + (T(ix) + T(0.5)) * C.grid_pitch[0], cy = C.grid_y0[0] + (T(iy) + T(0.5)) * C.grid_pitch[0];
+          if (cnt == gi) { maze_goal[0] = cx; maze_goal[1] = cy; }
+          if (cnt == si) { sc[0] = cx; sc[1] = cy; }
+          ++cnt;
+        }
+      }
+      const T nz = C.maze_xy_noise[0];
+      maze_goal[0] += nz * (T(2) * (T)u01(r3[2]) - T(1)); maze_goal[1] += nz * (T(2) * (T)u01(r3[3]) - T(1));
+      e.p[0] = sc[0] + nz * (T(2) * (T)u01(r[2]) - T(1)); e.p[1] = sc[1] + nz * (T(2) * (T)u01(r[3]) - T(1));
+    }
     for (int i = 0; i < 2; ++i) { e.st[i] = C.spawn_qpos[hinge_qadr(i)]; e.dst[i] = e.warm_st[i] = T(0); }
 #pragma unroll 1
     for (int s = 0; s < WPL; ++s) { wh[s].sp = C.spawn_qpos[hinge_qadr(2 + S::wheel_index(lane, s))]; wh[s].dsp = wh[s].warm = T(0); }
@@ -135,7 +165,31 @@ struct EnvOps {
     const T th = T(6.283185307179586) * (T)u01(r[1]);
     ep.goal[0] = d * N::cos_(th);  // robot_start_position is the odometry origin (0, 0)
     ep.goal[1] = d * N::sin_(th);
+    if (maze) { ep.goal[0] = maze_goal[0]; ep.goal[1] = maze_goal[1]; }   // maze goals are WORLD coordinates (…maze_env.py:405-412), quirk kept
     ep.episode += 1;
+  }
+
+  // Reset observation of models with settle steps (maze scenes: 3 x mj_step with zero controls before the first odometry call,
+  // ackermann_gymnasium_maze_env.py:222-235).  As in step(), what the reference then reads (xpos, sensordata) stems from the
+  // forward pass of the LAST settle step, i.e. from the state before its integration: the odometry reference and the reset
+  // observation are taken there.  Returns false (and does nothing) when the model has no settle steps.  Warp-uniform.
+  template <class Sink>
+  ACKB_HD static bool settle_and_observe(const Consts<T>& C, State& e, WheelT* wh, Episode<T>& ep, int lane, Sink& sink, T* dist, T* minl) {
+    const int n = (int)C.settle_steps[0];
+    if (n <= 0) return false;
+    const T ctrl[4] = {T(0), T(0), T(0), T(0)};
+    StepDiag diag{0, 0, 0, 0};
+#pragma unroll 1
+    for (int i = 0; i < n; ++i) {
+      Kin<T> k;
+      S::kinematics(e, k);
+      if (i == n - 1) {
+        ep.ref[0] = e.p[0]; ep.ref[1] = e.p[1];
+        observe(C, e, k, ep, lane, sink, dist, minl);
+      }
+      S::dynamics(C, e, k, ctrl, lane, wh, diag, (DebugTap<T>*)nullptr, 0);
+    }
+    return true;
   }
 
   // one env.step(): frame_skip x mj_step, observation from the kinematics of the last substep (quirk Q3).

@@ -49,6 +49,8 @@ struct StepArgs {
   unsigned long long seed;
   uint32_t step_index;
   int frame_skip, auto_reset, obs_dim;
+  uint8_t* done_mask;   // defer_reset: per-env done flag for the masked reset launch that follows
+  int defer_reset;      // models with settle steps: the step kernel only marks finished environments, reset_kernel does the rest
   int cta_sync;   // multi-lane kernels: re-converge the CTA once per substep (pays off only when several warps share a scheduler)
 };
 
@@ -223,7 +225,12 @@ __global__ void __launch_bounds__(Geo<T, LANES, NC>::kBlock, Geo<T, LANES, NC>::
     }
   }
 
-  const bool do_reset = done && a.auto_reset;
+  const bool do_reset = done && a.auto_reset && !a.defer_reset;
+  if (a.defer_reset) {   // CTA-uniform
+    if (valid && done && a.terminal_obs)   // the finished episode's last observation was flushed to dev_obs by emit()
+      for (int j = lane; j < a.obs_dim; j += LANES) a.terminal_obs[(size_t)env * a.obs_dim + j] = a.obs[(size_t)env * a.obs_dim + j];
+    if (valid && lane == 0) a.done_mask[env] = (done && a.auto_reset) ? 1 : 0;
+  }
   if (__any_sync(0xffffffffu, do_reset)) {   // warp-uniform: the team collectives inside need the whole warp
     if (do_reset && valid) {
       if (a.terminal_obs)   // the finished episode's last observation was flushed to dev_obs by emit()
@@ -264,9 +271,9 @@ __global__ void __launch_bounds__(Geo<T, LANES, NC>::kBlock, Geo<T, LANES, NC>::
   }
 }
 
-template <typename T, int LANES>
+template <typename T, int LANES, int NC>
 __global__ void __launch_bounds__(Geo<T, LANES, 2>::kBlock) reset_kernel(DevState<T> st, StepArgs a) {
-  using E = EnvOps<T, LANES, 2>;
+  using E = EnvOps<T, LANES, NC>;
   using G = Geo<T, LANES, 2>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Consts<T>& C = dev_consts<T>();
@@ -276,17 +283,19 @@ __global__ void __launch_bounds__(Geo<T, LANES, 2>::kBlock) reset_kernel(DevStat
   const int env = valid ? env_raw : st.n - 1;
   const bool sel = (a.mask ? (a.mask[env] != 0) : true) && valid;   // team-uniform
   // the reset kernel keeps wheel records in local storage and uses shared memory for the observation rows only
-  Wheel<T, 2> wh[G::WPL];
+  Wheel<T, NC> wh[G::WPL];
   float* row = reinterpret_cast<float*>(smem_raw) + (size_t)(threadIdx.x / LANES) * a.obs_dim;
   RowSink<false> sink{row};
   typename E::State e;
   Episode<T> ep;
   ep.episode = st.episode[env];
   E::reset_env(C, e, wh, ep, lane, a.seed, (uint32_t)env);
-  Kin<T> k;
-  E::S::kinematics(e, k);
   T dist, minl;
-  E::observe(C, e, k, ep, lane, sink, &dist, &minl);
+  if (!E::settle_and_observe(C, e, wh, ep, lane, sink, &dist, &minl)) {   // maze scenes settle first; everything else observes the spawn state
+    Kin<T> k;
+    E::S::kinematics(e, k);
+    E::observe(C, e, k, ep, lane, sink, &dist, &minl);
+  }
   __syncwarp();
   if (!sel) return;
   for (int j = lane; j < a.obs_dim; j += LANES) a.obs[(size_t)env * a.obs_dim + j] = sink.row[j];
@@ -334,6 +343,7 @@ struct ackb_handle {
   // staging for ackb_step_host
   float *d_action = nullptr, *d_obs = nullptr, *d_reward = nullptr;
   uint8_t *d_term = nullptr, *d_trunc = nullptr;
+  uint8_t* d_done = nullptr;    // per-env done mask of the deferred reset (models with settle steps)
   cudaStream_t own_stream = nullptr;
   std::string err;
 };
@@ -392,15 +402,15 @@ int launch_one(ackb_handle* h, DevState<T>& st, const StepArgs& a, cudaStream_t 
     using GR = Geo<T, LANES, 2>;   // the reset kernel has its own geometry (records in local storage)
     const int rgrid = (int)((threads + GR::kBlock - 1) / GR::kBlock);
     const size_t smem = (size_t)(GR::kBlock / LANES) * a.obs_dim * sizeof(float);
-    static bool rattr_done = false;
-    if (!rattr_done && smem > 48 * 1024) { CK(cudaFuncSetAttribute(reset_kernel<T, LANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); rattr_done = true; }
-    reset_kernel<T, LANES><<<rgrid, GR::kBlock, smem, stream>>>(st, a);
+    static bool rattr_done[64] = {false};   // per device: function attributes are per-device state
+    if (!rattr_done[h->device] && smem > 48 * 1024) { CK(cudaFuncSetAttribute(reset_kernel<T, LANES, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); rattr_done[h->device] = true; }
+    reset_kernel<T, LANES, NC><<<rgrid, GR::kBlock, smem, stream>>>(st, a);
   } else {
     const size_t smem = G::smem_bytes(a.obs_dim);
     StepArgs a2 = a;
     a2.cta_sync = h->cta_sync >= 0 ? h->cta_sync : 1;   // measured on B200: faster at every batch size from 4096 to 131072 envs
-    static bool attr_done = false;
-    if (!attr_done && smem > 48 * 1024) { CK(cudaFuncSetAttribute(step_kernel<T, LANES, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done = true; }
+    static bool attr_done[64] = {false};    // per device
+    if (!attr_done[h->device] && smem > 48 * 1024) { CK(cudaFuncSetAttribute(step_kernel<T, LANES, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done[h->device] = true; }
     step_kernel<T, LANES, NC><<<grid, G::kBlock, smem, stream>>>(st, a2);
   }
   h->launches++;
@@ -465,6 +475,8 @@ int ackb_create(const double* consts, size_t consts_len, int num_envs, int devic
   CK(cudaMalloc(&h->d_reward, n * sizeof(float)));
   CK(cudaMalloc(&h->d_term, n));
   CK(cudaMalloc(&h->d_trunc, n));
+  CK(cudaMalloc(&h->d_done, n));
+  CK(cudaMemset(h->d_done, 0, n));
   CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   *out = h;
   return ACKB_OK;
@@ -475,7 +487,7 @@ int ackb_destroy(ackb_handle* h) {
   cudaSetDevice(h->device);
   if (g_const_owner[h->device] == h) g_const_owner[h->device] = nullptr;
   cudaFree(h->state); cudaFree(h->stats); cudaFree(h->d_action); cudaFree(h->d_obs); cudaFree(h->d_reward);
-  cudaFree(h->d_term); cudaFree(h->d_trunc);
+  cudaFree(h->d_term); cudaFree(h->d_trunc); cudaFree(h->d_done);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete[] h->consts_host;
   delete h;
@@ -509,7 +521,16 @@ int ackb_step(ackb_handle* h, const float* dev_action, int frame_skip, int auto_
   a.terminal_obs = dev_terminal_obs; a.ncon = dev_ncon; a.stats = h->stats; a.seed = h->seed; a.step_index = h->step_index++;
   h->stat_steps += (unsigned long long)h->n;
   a.frame_skip = frame_skip; a.auto_reset = auto_reset; a.obs_dim = h->obs_dim;
-  return h->dtype == ACKB_F32 ? launch_step(h, h->sf, a, (cudaStream_t)stream, false) : launch_step(h, h->sd, a, (cudaStream_t)stream, false);
+  // models whose reset includes settle steps (maze scenes): the step kernel only marks the finished environments, a masked
+  // reset launch on the same stream then resets, settles and observes them
+  const bool defer = auto_reset && reinterpret_cast<const Consts<double>*>(h->consts_host)->settle_steps[0] > 0.0;
+  a.defer_reset = defer ? 1 : 0;
+  a.done_mask = h->d_done;
+  rc = h->dtype == ACKB_F32 ? launch_step(h, h->sf, a, (cudaStream_t)stream, false) : launch_step(h, h->sd, a, (cudaStream_t)stream, false);
+  if (rc || !defer) return rc;
+  StepArgs r{};
+  r.obs = dev_obs; r.mask = h->d_done; r.seed = h->seed; r.obs_dim = h->obs_dim; r.stats = h->stats;
+  return h->dtype == ACKB_F32 ? launch_step(h, h->sf, r, (cudaStream_t)stream, true) : launch_step(h, h->sd, r, (cudaStream_t)stream, true);
 }
 
 // Device-visible alias of a host pointer: pinned (cudaHostAlloc / cudaHostRegister) memory is mapped into the device address

@@ -15,7 +15,7 @@ import torch
 
 from . import _lib
 from .compiler.constants import build_consts
-from .models import load_model
+from .models import load_model, model_kind
 
 _DTYPES = {"float32": 0, "f32": 0, torch.float32: 0, "float64": 1, "f64": 1, torch.float64: 1}
 
@@ -32,7 +32,7 @@ class BatchedAckermannEnv:
                  max_episode_steps: int = 1000, goal_distance_threshold: float = 0.5, collision_threshold: float = 0.15,
                  max_linear_velocity: float = 1.0, max_angular_velocity: float = 1.0, render_mode=None, map_spawner=None,
                  solver_tolerance: Optional[float] = None, spawn_yaw_range: float = 0.0, spawn_xy_jitter: float = 0.0,
-                 model_table: Optional[dict] = None):
+                 model_table: Optional[dict] = None, settle_steps: Optional[int] = None):
         if render_mode is not None:
             raise NotImplementedError("rendering is outside the hot path (SURVEY.md section 2)")
         if not torch.cuda.is_available():
@@ -44,11 +44,14 @@ class BatchedAckermannEnv:
         self.auto_reset = bool(auto_reset)
         self.model_name = model
         self.table = model_table if model_table is not None else load_model(model)
-        self.consts = build_consts(self.table, model_kind=0 if model == "v2" else 1, max_episode_steps=max_episode_steps,
+        self.consts = build_consts(self.table, model_kind=model_kind(model), max_episode_steps=max_episode_steps,
                                    goal_distance_threshold=goal_distance_threshold, collision_threshold=collision_threshold,
                                    max_linear_velocity=max_linear_velocity, max_angular_velocity=max_angular_velocity,
                                    lidar_index_map=lidar_index_map, tolerance=solver_tolerance,
                                    spawn_yaw_range=spawn_yaw_range, spawn_xy_jitter=spawn_xy_jitter)
+        if settle_steps is not None:     # maze scenes: override the number of settle steps after a reset (tests)
+            from .compiler.constants import consts_layout
+            self.consts[consts_layout()["settle_steps"][0]] = float(settle_steps)
         assert len(self.consts) == self.L.ackb_consts_len(), "constants layout mismatch between Python and libackb.so"
         self.h = ctypes.c_void_p()
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
@@ -174,7 +177,7 @@ class AckermannRobotEnv:
 
     def __init__(self, map_spawner=None, max_episode_steps=1000, goal_distance_threshold=0.5, collision_threshold=0.15,
                  max_linear_velocity=1.0, max_angular_velocity=1.0, render_mode=None, device="cuda:0", dtype="float64",
-                 frame_skip=1, seed=0):
+                 frame_skip=1, seed=0, model="v2"):
         self.max_episode_steps = max_episode_steps
         self.goal_distance_threshold = goal_distance_threshold
         self.collision_threshold = collision_threshold
@@ -183,7 +186,8 @@ class AckermannRobotEnv:
         self._kw = dict(device=device, dtype=dtype, frame_skip=frame_skip, max_episode_steps=max_episode_steps,
                         goal_distance_threshold=goal_distance_threshold, collision_threshold=collision_threshold,
                         max_linear_velocity=max_linear_velocity, max_angular_velocity=max_angular_velocity,
-                        render_mode=render_mode, auto_reset=False)
+                        render_mode=render_mode, auto_reset=False, model=model)
+        self._map_name = "simple_floor" if model == "v2" else model
         self._seed = seed
         self._env = BatchedAckermannEnv(1, seed=seed, **self._kw)
         self.observation_shape, self.action_shape = (self._env.obs_dim,), (2,)
@@ -200,7 +204,9 @@ class AckermannRobotEnv:
         goal, ref, _ = self._env.get_episode()
         self.step_count = 0
         self.goal_position = goal[0].copy()
-        info = {"map_name": "simple_floor", "goal_position": self.goal_position.tolist(),
+        if self._map_name != "simple_floor":
+            self.robot_start_position = ref[0].copy()
+        info = {"map_name": self._map_name, "goal_position": self.goal_position.tolist(),
                 "start_position": self.robot_start_position.tolist()}
         return obs, info
 
@@ -222,3 +228,22 @@ class AckermannRobotEnv:
 
     def close(self):
         self._env.close()
+
+
+class AckermannGymnasiumMazeEnv(AckermannRobotEnv):
+    """Single-environment adapter with the signature of the reference's maze environment
+    (src/rl/envs/ackermann_gymnasium_maze_env.py:50-61): ``maze_env_id`` selects the PointMaze layout (compiler/maze.py)."""
+
+    def __init__(self, maze_env_id="PointMaze_UMaze-v3", max_episode_steps=1000, goal_distance_threshold=0.5, collision_threshold=0.15,
+                 max_linear_velocity=1.0, max_angular_velocity=1.0, render_mode=None, **kw):
+        from .compiler.maze import MAZE_ENV_IDS
+        if maze_env_id not in MAZE_ENV_IDS:
+            raise ValueError(f"Failed to load maze environment '{maze_env_id}': unknown id (known: {sorted(MAZE_ENV_IDS)})")
+        self.maze_env_id = maze_env_id
+        super().__init__(max_episode_steps=max_episode_steps, goal_distance_threshold=goal_distance_threshold,
+                         collision_threshold=collision_threshold, max_linear_velocity=max_linear_velocity,
+                         max_angular_velocity=max_angular_velocity, render_mode=render_mode, model="maze:" + MAZE_ENV_IDS[maze_env_id], **kw)
+
+    def reset(self, seed=None, options=None):
+        obs, info = super().reset(seed=seed, options=options)
+        return obs, {"maze_type": self.maze_env_id, "goal_position": info["goal_position"], "start_position": info["start_position"]}

@@ -6,43 +6,34 @@
     list_available_mazes()
 
 Note the factory's defaults (0.5 m/s, 0.3 m) differ from the class defaults (1.0 m/s, 0.5 m; ackermann_env.py:51-60).
-The PointMaze scenes need the maze XML of the un-vendored ``gymnasium_robotics`` package: as in the reference
-when that package is missing, ``env_type='maze'`` prints the reference's warning and falls back to the simple environment.
-``num_envs`` (new) returns the batched device environment instead of the single-environment gym adapter.
+The maze layouts are built in (compiler/maze.py restates the maps of the un-vendored ``gymnasium_robotics`` package), so the
+reference's "gymnasium-robotics not installed" fallback is never taken.  ``num_envs`` (new) returns the batched device
+environment instead of the single-environment gym adapter.
 """
 from __future__ import annotations
 
 MAZE_IDS = ("PointMaze_UMaze-v3", "PointMaze-Open-v3", "PointMaze-Medium-v3", "PointMaze-Large-v3")
 
 
-def _has_gymnasium_maze() -> bool:
-    try:
-        import gymnasium_robotics  # noqa: F401
-        return True
-    except Exception:
-        return False
-
-
 def list_available_mazes():
-    """List available Gymnasium Robotics maze environments (empty when the package is absent, like the reference)."""
-    if not _has_gymnasium_maze():
-        print("gymnasium-robotics not installed. No maze environments available.")
-        return []
+    """List available maze environment ids (the four PointMaze layouts the reference documents)."""
     return list(MAZE_IDS)
 
 
 def make_ackermann_env(env_type: str = "maze", maze_id: str = "PointMaze_UMaze-v3", render_mode=None, max_linear_velocity: float = 0.5,
                        max_angular_velocity: float = 1.0, goal_distance_threshold: float = 0.3, num_envs: int = 0, **kwargs):
-    from .env import AckermannRobotEnv, BatchedAckermannEnv
-    if env_type == "maze":
-        # the maze scenes are not built (see module docstring); same fallback path as the reference without gymnasium-robotics
-        print("Warning: gymnasium-robotics not installed. Falling back to simple environment.")
-        print("Install with: pip install gymnasium-robotics")
-        env_type = "simple"
-    if env_type != "simple":
-        raise ValueError(f"Unknown environment type: {env_type}. Use 'maze' or 'simple'.")
+    from .compiler.maze import MAZE_ENV_IDS
+    from .env import AckermannGymnasiumMazeEnv, AckermannRobotEnv, BatchedAckermannEnv
     common = dict(render_mode=render_mode, max_linear_velocity=max_linear_velocity, max_angular_velocity=max_angular_velocity,
                   goal_distance_threshold=goal_distance_threshold, **kwargs)
-    if num_envs and num_envs > 0:
-        return BatchedAckermannEnv(num_envs, **common)
-    return AckermannRobotEnv(**common)
+    if env_type == "maze":
+        if num_envs and num_envs > 0:
+            if maze_id not in MAZE_ENV_IDS:
+                raise ValueError(f"Failed to load maze environment '{maze_id}'")
+            return BatchedAckermannEnv(num_envs, model="maze:" + MAZE_ENV_IDS[maze_id], **common)
+        return AckermannGymnasiumMazeEnv(maze_env_id=maze_id, **common)
+    if env_type == "simple":
+        if num_envs and num_envs > 0:
+            return BatchedAckermannEnv(num_envs, **common)
+        return AckermannRobotEnv(**common)
+    raise ValueError(f"Unknown environment type: {env_type}. Use 'maze' or 'simple'.")

@@ -31,7 +31,7 @@ def main(argv=None):
     ap.add_argument("--max-velocity", type=float, default=1.0, help="Maximum linear velocity (m/s)")
     ap.add_argument("--goal-threshold", type=float, default=0.5, help="Goal distance threshold (m)")
     ap.add_argument("--maze", default=None, choices=[None, "umaze", "open", "medium", "large"],
-                    help="Gymnasium Robotics maze (needs the un-vendored gymnasium-robotics XML: falls back to the default environment)")
+                    help="Use a PointMaze scene (layout chosen by --maze-id, as in the reference)")
     ap.add_argument("--maze-id", default="PointMaze_UMaze-v3", help="Gymnasium Robotics maze environment ID")
     ap.add_argument("--learning-rate", type=float, default=None, help="Learning rate for the algorithm (PPO default 3e-4)")
     ap.add_argument("--save-freq", type=int, default=10000, help="Frequency (timesteps) to save model checkpoints (needs --save-path)")
@@ -44,7 +44,7 @@ def main(argv=None):
     ap.add_argument("--n-steps", type=int, default=16)
     ap.add_argument("--n-epochs", type=int, default=10)
     ap.add_argument("--minibatches", type=int, default=4)
-    ap.add_argument("--model", default="v2", choices=["v2", "scene"])
+    ap.add_argument("--model", default="v2", help="v2 | scene | maze:umaze|open|medium|large")
     ap.add_argument("--seed", type=int, default=0)
     a = ap.parse_args(argv)
 
@@ -52,9 +52,12 @@ def main(argv=None):
         raise SystemExit(f"--algo {a.algo}: only the PPO path of the reference is built (SAC / TD3 are out of scope, DESIGN.md section 8)")
     if a.render:
         raise SystemExit("--render: the viewer is outside the hot path; there is no rendering on the GPU path")
-    if a.maze is not None:
-        print("Warning: gymnasium-robotics not installed. Using default environment.")     # train.py:271
-        print("Install with: pip install gymnasium-robotics")
+    if a.maze is not None:                                  # train.py:262-270: --maze switches to the maze env selected by --maze-id
+        from .compiler.maze import MAZE_ENV_IDS
+        if a.maze_id not in MAZE_ENV_IDS:
+            raise SystemExit(f"unknown --maze-id {a.maze_id}; known: {sorted(MAZE_ENV_IDS)}")
+        a.model = "maze:" + MAZE_ENV_IDS[a.maze_id]
+        print(f"Using Gymnasium Robotics maze: {a.maze_id}")
     world = int(os.environ.get("WORLD_SIZE", 1))
     rank = int(os.environ.get("RANK", 0))
     local = int(os.environ.get("LOCAL_RANK", 0))

@@ -38,7 +38,7 @@
 #define MAXJ 16   /* joints   */
 #define MAXV 16   /* dofs     */
 #define MAXQ 20   /* qpos     */
-#define MAXG 64   /* geoms    */
+#define MAXG 96   /* geoms    */
 #define MAXS 80   /* sites    */
 #define MAXSEN 96 /* sensors  */
 #define MAXU 8

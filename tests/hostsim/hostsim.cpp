@@ -90,11 +90,13 @@ void env_reset(const double* blob, double* qpos, double* qvel, double* warm, dou
   Episode<T> ep;
   ep.episode = (uint32_t)epi[1];
   E::reset_env(C, e, wh, ep, 0, seed, env_id);
-  Kin<T> k;
-  E::S::kinematics(e, k);
   ObsSink sink{obs};
   T dist, minl;
-  E::observe(C, e, k, ep, 0, sink, &dist, &minl);
+  if (!E::settle_and_observe(C, e, wh, ep, 0, sink, &dist, &minl)) {
+    Kin<T> k;
+    E::S::kinematics(e, k);
+    E::observe(C, e, k, ep, 0, sink, &dist, &minl);
+  }
   ArrAcc<T> acc{qpos, qvel, warm};
   E::store_state(acc, 0, e, wh);
   epd[0] = (double)ep.goal[0]; epd[1] = (double)ep.goal[1]; epd[2] = (double)ep.ref[0]; epd[3] = (double)ep.ref[1];
@@ -163,19 +165,20 @@ void hs_env_step(int f32, const double* blob, double* qpos, double* qvel, double
 }
 void hs_env_reset(int f32, const double* blob, double* qpos, double* qvel, double* warm, double* epd, int* epi, unsigned long long seed,
                   unsigned env_id, float* obs) {
-  if (f32) env_reset<float, 2>(blob, qpos, qvel, warm, epd, epi, seed, env_id, obs);
-  else env_reset<double, 2>(blob, qpos, qvel, warm, epd, epi, seed, env_id, obs);
+  const bool scene = blob[0] != 0.0;
+  if (f32) { if (scene) env_reset<float, 4>(blob, qpos, qvel, warm, epd, epi, seed, env_id, obs); else env_reset<float, 2>(blob, qpos, qvel, warm, epd, epi, seed, env_id, obs); }
+  else { if (scene) env_reset<double, 4>(blob, qpos, qvel, warm, epd, epi, seed, env_id, obs); else env_reset<double, 2>(blob, qpos, qvel, warm, epd, epi, seed, env_id, obs); }
 }
 // observation of a given state (qpos) with given episode data; out = goal distance, min lidar
 void hs_observe(int f32, const double* blob, double* qpos, double* qvel, double* warm, const double* epd, float* obs, double* out) {
   if (f32) {
-    using E = EnvOps<float, 1, 2>; Consts<float> C; to_consts(blob, C);
-    E::State e; Wheel<float, 2> wh[4]; ArrAcc<float> acc{qpos, qvel, warm}; E::load_state(acc, 0, e, wh);
+    using E = EnvOps<float, 1, 4>; Consts<float> C; to_consts(blob, C);
+    E::State e; Wheel<float, 4> wh[4]; ArrAcc<float> acc{qpos, qvel, warm}; E::load_state(acc, 0, e, wh);
     Episode<float> ep; ep.goal[0] = epd[0]; ep.goal[1] = epd[1]; ep.ref[0] = epd[2]; ep.ref[1] = epd[3]; ep.step_count = 0; ep.episode = 0;
     Kin<float> k; E::S::kinematics(e, k); ObsSink sink{obs}; float d, m; E::observe(C, e, k, ep, 0, sink, &d, &m); out[0] = d; out[1] = m;
   } else {
-    using E = EnvOps<double, 1, 2>; Consts<double> C; to_consts(blob, C);
-    E::State e; Wheel<double, 2> wh[4]; ArrAcc<double> acc{qpos, qvel, warm}; E::load_state(acc, 0, e, wh);
+    using E = EnvOps<double, 1, 4>; Consts<double> C; to_consts(blob, C);
+    E::State e; Wheel<double, 4> wh[4]; ArrAcc<double> acc{qpos, qvel, warm}; E::load_state(acc, 0, e, wh);
     Episode<double> ep; ep.goal[0] = epd[0]; ep.goal[1] = epd[1]; ep.ref[0] = epd[2]; ep.ref[1] = epd[3]; ep.step_count = 0; ep.episode = 0;
     Kin<double> k; E::S::kinematics(e, k); ObsSink sink{obs}; double d, m; E::observe(C, e, k, ep, 0, sink, &d, &m); out[0] = d; out[1] = m;
   }

@@ -362,3 +362,72 @@ def test_long_horizon_statistical_parity_fp32_vs_fp64():
     assert abs(a["st"]["contacts_sum"] - b["st"]["contacts_sum"]) < 0.05 * b["st"]["contacts_sum"]
     # per-environment: the two precisions stay correlated through the slow variables (goal distance after 8 s of random driving)
     assert np.corrcoef(a["ret"], b["ret"])[0, 1] > 0.95
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# PointMaze scenes (v2 robot in the U / Open / Medium / Large mazes): reset with settle steps, deferred auto-reset
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,dtype,tol", [("umaze", "float64", 1e-7), ("large", "float32", 2e-3)])
+def test_maze_env_matches_oracle(name, dtype, tol):
+    from mujoco_playground_b200 import BatchedAckermannEnv
+    from mujoco_playground_b200.models import load_model
+    from oracle.env_oracle import OracleEnv
+    M = load_model("maze:" + name)
+    n, steps = 64, 40
+    env = BatchedAckermannEnv(n, model="maze:" + name, dtype=dtype, seed=21, auto_reset=False,
+                              solver_tolerance=1e-12 if dtype == "float64" else None)
+    assert env.obs_dim == 79
+    # spawn poses: the same reset with the settle steps switched off (state before settling)
+    env0 = BatchedAckermannEnv(n, model="maze:" + name, dtype="float64", seed=21, auto_reset=False, settle_steps=0)
+    env0.reset()
+    spawn = env0.get_state()[0]
+    env0.close()
+    obs0 = env.reset().cpu().numpy().copy()
+    goal, ref, _ = env.get_episode()
+    rng = np.random.default_rng(3)
+    acts = rng.uniform(-1, 1, (steps, n, 2)).astype(np.float32)
+    ks = [0, 7, 33]
+    oracles = []
+    for k in ks:
+        o = OracleEnv(M, kind="maze", tolerance=1e-12)
+        want = o.reset(goal[k], spawn_qpos=spawn[k])
+        assert np.abs(want - obs0[k]).max() < (1e-5 if dtype == "float64" else 2e-4), "reset observation after the settle steps"
+        assert np.abs(o.reference_position[:2] - ref[k]).max() < 1e-6
+        oracles.append(o)
+    for t in range(steps):
+        obs, rew, term, trunc, info = env.step(torch.from_numpy(acts[t]).cuda())
+        for k, o in zip(ks, oracles):
+            oo, r, te, tr, inf = o.step(acts[t, k])
+            if dtype == "float64":
+                assert int(info["ncon"][k].item()) == inf["ncon"] and bool(term[k].item()) == te
+    q, v, _ = env.get_state()
+    for k, o in zip(ks, oracles):
+        assert _rel(q[k], o.sim.qpos) < tol, f"{name} {dtype} env {k}"
+    env.close()
+
+
+def test_maze_auto_reset_uses_the_deferred_reset_launch():
+    """Models with settle steps: the step kernel marks finished environments and a masked reset launch (reset + 3 settle steps +
+    observation) follows on the same stream; the caller sees the same contract as with the fused reset."""
+    from mujoco_playground_b200 import BatchedAckermannEnv
+    n = 300
+    env = BatchedAckermannEnv(n, model="maze:medium", dtype="float32", seed=8, max_episode_steps=6, auto_reset=True, frame_skip=2)
+    env.reset()
+    goal0, ref0, _ = env.get_episode()
+    l0 = env.launch_count
+    for t in range(6):
+        obs, rew, term, trunc, info = env.step(None)
+    assert env.launch_count - l0 == 12, "step kernel + masked reset kernel per step"
+    tr = trunc.cpu().numpy().astype(bool)
+    assert tr.sum() >= n - 10, "a few start/goal pairs in adjacent cells end by reaching the goal and restart earlier"
+    new = obs.cpu().numpy()
+    tobs = info["terminal_observation"].cpu().numpy()
+    assert np.allclose(new[tr, 72:75], 0.0, atol=1e-5), "fresh episode: odometry restarts at zero after the settle steps"
+    assert not np.allclose(tobs[tr, 72:74], 0.0, atol=1e-6), "terminal observation belongs to the old episode"
+    goal1, ref1, sc = env.get_episode()
+    assert (sc[tr] == 0).all() and np.abs(goal1 - goal0).max() > 0.5, "new goals were drawn"
+    st = env.stats()
+    assert st["episodes"] >= n and np.isfinite(new).all()
+    q, _, _ = env.get_state()
+    assert np.all(q[:, 2] > -0.46) and np.all(q[:, 2] < -0.40), "robots rest on the maze floor at z = -0.5"
+    env.close()

@@ -37,6 +37,10 @@ def main():
     save(v2, os.path.join(dst, "ackermann_v2.npz"))
     sc = compile_mjcf(os.path.join(a.reference, "models", "environments", "ackermann_in_mushr_maze.xml"), a.mesh_inertia)
     save(sc, os.path.join(dst, "ackermann_scene.npz"))
+    from mujoco_playground_b200.compiler.maze import MAZES, compile_maze
+    for name in MAZES:   # v2 robot in the PointMaze layouts (compiler/maze.py)
+        save(compile_maze(os.path.join(a.reference, "models", "ackermann_robot_v2.xml"), name, a.mesh_inertia),
+             os.path.join(dst, f"ackermann_maze_{name}.npz"))
     print("wrote", dst)
 
 
