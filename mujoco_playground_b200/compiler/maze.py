@@ -50,7 +50,21 @@ LARGE_MAZE = [[1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1],
               [1, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0, 1],
               [1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1]]
 
-MAZES: Dict[str, list] = {"umaze": U_MAZE, "open": OPEN, "medium": MEDIUM_MAZE, "large": LARGE_MAZE}
+# The obstacle layout of models/environments/ackermann_maze_flat.xml (38 blocks of 1 m x 1 m x 0.2 m on an 8 x 8 lattice, floor at
+# z = 0), for the "v2 robot in the obstacle scene" merge that the reference's SYSTEM_SUMMARY.md:33-39 describes (its MapSpawner is
+# absent upstream).  Row 0 is the +y edge (y = 3), column 0 is x = -4.
+MUSHR = [[1, 1, 1, 1, 1, 1, 1, 1],
+         [1, 0, 0, 1, 0, 0, 0, 1],
+         [1, 0, 1, 0, 0, 1, 0, 1],
+         [1, 0, 0, 0, 1, 0, 0, 1],
+         [1, 1, 1, 0, 0, 0, 1, 1],
+         [1, 0, 0, 0, 1, 0, 0, 1],
+         [1, 0, 0, 1, 1, 0, 0, 1],
+         [1, 1, 1, 1, 1, 1, 1, 1]]
+
+MAZES: Dict[str, list] = {"umaze": U_MAZE, "open": OPEN, "medium": MEDIUM_MAZE, "large": LARGE_MAZE, "mushr": MUSHR}
+# per-layout overrides of (ground z, block half height, spawn z, settle steps, map centre offset)
+PARAMS = {"mushr": dict(ground_z=0.0, half_height=0.1, block_z=0.05, spawn_z=0.1, settle=0, offset=(-0.5, -0.5))}
 MAZE_ENV_IDS = {"PointMaze_UMaze-v3": "umaze", "PointMaze-Open-v3": "open", "PointMaze-Medium-v3": "medium", "PointMaze-Large-v3": "large"}
 
 SCALING = 1.0
@@ -64,7 +78,8 @@ XY_NOISE = 0.25              # gymnasium_robotics maze.add_xy_position_noise (fr
 def cell_xy(name: str, i: int, j: int) -> Tuple[float, float]:
     m = MAZES[name]
     H, W = len(m), len(m[0])
-    return (j + 0.5) * SCALING - W * SCALING / 2.0, H * SCALING / 2.0 - (i + 0.5) * SCALING
+    ox, oy = PARAMS.get(name, {}).get("offset", (0.0, 0.0))
+    return (j + 0.5) * SCALING - W * SCALING / 2.0 + ox, H * SCALING / 2.0 - (i + 0.5) * SCALING + oy
 
 
 def maze_layout(name: str) -> dict:
@@ -75,7 +90,8 @@ def maze_layout(name: str) -> dict:
     for j in range(W):
         for i in range(H - 1, -1, -1):          # ascending y
             (blocks if m[i][j] == 1 else free).append(cell_xy(name, i, j))
-    x0, y0 = -W * SCALING / 2.0, -H * SCALING / 2.0
+    ox, oy = PARAMS.get(name, {}).get("offset", (0.0, 0.0))
+    x0, y0 = -W * SCALING / 2.0 + ox, -H * SCALING / 2.0 + oy
     block_rows, free_rows = np.zeros(16), np.zeros(16)
     for i in range(H):
         iy = H - 1 - i
@@ -91,16 +107,18 @@ def build_maze_root(robot_xml_path: str, name: str) -> ET.Element:
     """MJCF tree of the robot model with the maze blocks added and the floor lowered, following the reference's merge rules."""
     root = copy.deepcopy(ET.parse(robot_xml_path).getroot())
     wb = root.find("worldbody")
+    prm = PARAMS.get(name, {})
+    gz = prm.get("ground_z", GROUND_Z)
     for g in wb.findall("geom"):
         nm = g.get("name", "").lower()
         if "ground" in nm or "floor" in nm:
             p = g.get("pos", "0 0 0").split()
-            g.set("pos", f"{p[0]} {p[1]} {GROUND_Z}")
-    hz = MAZE_HEIGHT / 2.0 * SCALING
+            g.set("pos", f"{p[0]} {p[1]} {gz}")
+    hz = prm.get("half_height", MAZE_HEIGHT / 2.0 * SCALING)
+    bz = prm.get("block_z", gz + hz)
     lay = maze_layout(name)
     for k, (x, y) in enumerate(lay["blocks"]):
-        ET.SubElement(wb, "geom", dict(name=f"block_{k}", type="box", size=f"{0.5 * SCALING} {0.5 * SCALING} {hz}",
-                                       pos=f"{x} {y} {GROUND_Z + hz}"))
+        ET.SubElement(wb, "geom", dict(name=f"block_{k}", type="box", size=f"{0.5 * SCALING} {0.5 * SCALING} {hz}", pos=f"{x} {y} {bz}"))
     return root
 
 
@@ -110,7 +128,7 @@ def compile_maze(robot_xml_path: str, name: str, mesh_inertia: str = "legacy") -
     lay = maze_layout(name)
     M["maze_free_rows"] = lay["free_rows"]
     M["maze_grid"] = np.array([lay["x0"], lay["y0"], lay["pitch"], lay["nx"], lay["ny"]], float)
-    M["maze_spawn_z"] = np.array([SPAWN_Z])
-    M["maze_settle_steps"] = np.array([SETTLE_STEPS])
+    M["maze_spawn_z"] = np.array([PARAMS.get(name, {}).get("spawn_z", SPAWN_Z)])
+    M["maze_settle_steps"] = np.array([PARAMS.get(name, {}).get("settle", SETTLE_STEPS)])
     M["maze_xy_noise"] = np.array([XY_NOISE * SCALING])
     return M

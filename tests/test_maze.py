@@ -109,3 +109,22 @@ def _spawn_xy(blob, seed, env_id):
     h = HostSim(b, False)
     h.reset(seed=seed, env_id=env_id)
     return h.qpos[:2].copy()
+
+
+def test_mushr_layout_is_the_obstacle_scene_with_the_v2_robot():
+    """'maze:mushr' (SURVEY 8f row 4): the v2 robot (79-float observation, BicycleController) among the 38 blocks of
+    models/environments/ackermann_maze_flat.xml; block positions must equal the scene model's, floor at z = 0, no settle steps."""
+    S, Mz = load_model("scene"), load_model("maze:mushr")
+    bs = sorted((round(float(S["geom_pos"][g][0] + S["body_pos"][S["geom_bodyid"][g]][0]), 6), round(float(S["geom_pos"][g][1] + S["body_pos"][S["geom_bodyid"][g]][1]), 6),
+                 round(float(S["geom_pos"][g][2]), 6)) for g in range(S["ngeom"]) if S["geom_type"][g] == 6)
+    bm = sorted((round(float(Mz["geom_pos"][g][0]), 6), round(float(Mz["geom_pos"][g][1]), 6), round(float(Mz["geom_pos"][g][2]), 6))
+                for g in range(Mz["ngeom"]) if Mz["geom_type"][g] == 6)
+    assert bs == bm and len(bm) == 38
+    blob = build_consts(Mz, model_kind=2)
+    assert consts_field(blob, "settle_steps") == 0 and consts_field(blob, "plane_z") == 0 and consts_field(blob, "nbeam") == 72
+    h = HostSim(blob, False)
+    obs = h.reset(seed=3, env_id=5)
+    assert obs.shape == (79,) and np.isfinite(obs).all() and obs[:72].max() < 9.0 and (obs[:72] > 0).all(), "every beam ends on a wall"
+    o = OracleEnv(Mz, kind="v2")
+    want = o.reset(h.epd[:2], spawn_qpos=np.concatenate([h.qpos[:3], [1, 0, 0, 0], np.zeros(6)]))
+    np.testing.assert_allclose(obs, want, atol=5e-6)
