@@ -1,0 +1,38 @@
+/* ackb_ppo.h -- C ABI of the fused PPO minibatch-gradient kernel (learner side of config 5).
+ *
+ * Replaces, for one minibatch, what the reference obtains from Stable-Baselines3's PPO.train() inner loop
+ * (stable_baselines3/ppo/ppo.py: evaluate_actions -> ratio / clipped surrogate / value loss / entropy -> loss.backward();
+ * called through model.learn, src/rl/train.py:175-179) for the MlpPolicy the reference trains
+ * (separate tanh MLPs obs -> 64 -> 64 for policy and value, state-independent log_std; 18 757 parameters for obs = 79).
+ * The optimiser step (gradient clipping + Adam) stays with the caller.
+ *
+ * All pointers are caller-owned DEVICE memory.  Parameter / gradient layout (floats, D = obs_dim):
+ *   W1p[64][D] b1p[64] W2p[64][64] b2p[64]  W1v[64][D] b1v[64] W2v[64][64] b2v[64]  Wa[2][64] ba[2]  Wv[64] bv[1]  log_std[2]
+ * i.e. the parameters of mujoco_playground_b200.ppo.ActorCritic in state_dict order with log_std moved to the end.
+ */
+#ifndef ACKB_PPO_H_
+#define ACKB_PPO_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* number of floats of the parameter / gradient vector for an observation of obs_dim floats */
+int ackb_ppo_num_params(int obs_dim);
+
+/* Gradient of the PPO loss  mean_i[-min(A_i r_i, A_i clip(r_i, 1-c, 1+c))] + vf_coef * mean_i (V_i - R_i)^2 - ent_coef * H
+ * over the minibatch rows idx[0 .. mb-1] of the rollout arrays (A normalised with adv_mean_std = {mean, std} of the minibatch,
+ * A = (adv - mean) / (std + 1e-8)).  grads (zeroed by the call) receives d loss / d params; diag receives
+ * {policy loss, value loss (mean squared error), entropy, approx_kl, clip fraction}.  Asynchronous on `stream`.
+ * Returns 0 or a negative error code (same codes as ackb.h). */
+int ackb_ppo_minibatch_grad(const float* obs, const float* act, const float* old_logp, const float* adv, const float* ret,
+                            const int64_t* idx, int mb, int obs_dim, const float* adv_mean_std, const float* params, float* grads,
+                            float* diag, float clip_range, float vf_coef, float ent_coef, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ACKB_PPO_H_ */

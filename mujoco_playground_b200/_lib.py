@@ -38,6 +38,9 @@ SYMBOLS = {
     "ackb_launch_count": (ctypes.c_ulonglong, [_vp]),
     "ackb_random_actions": (_i, [_vp, _vp, _vp]),
     "ackb_last_error": (ctypes.c_char_p, [_vp]),
+    # include/ackb_ppo.h
+    "ackb_ppo_num_params": (_i, [_i]),
+    "ackb_ppo_minibatch_grad": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp]),
 }
 
 

@@ -129,9 +129,15 @@ def ppo_update(policy: ActorCritic, opt: torch.optim.Optimizer, batch: Dict[str,
     params = [p for p in policy.parameters() if p.requires_grad]
     for _ in range(cfg.n_epochs):
         perm = torch.randperm(n, device=batch["obs"].device, generator=generator)
+        shuffled = graphed.shuffle_epoch(batch, perm) if isinstance(graphed, FusedMinibatchStep) else None
         for i in range(cfg.minibatches):
             idx = perm[i * mb:(i + 1) * mb]
-            if graphed is not None and graphed.mb == idx.numel():
+            if shuffled is not None:
+                stats["allreduce_bytes"] += graphed.run(shuffled, (i * mb, int(idx.numel())), world)
+                acc += graphed.diag
+                stats["steps"] += 1
+                continue
+            if graphed is not None and graphed.mb in (-1, idx.numel()):
                 stats["allreduce_bytes"] += graphed.run(batch, idx, world)
                 acc += graphed.diag
                 stats["steps"] += 1
@@ -230,10 +236,80 @@ class GraphedMinibatchStep:
         return nbytes
 
 
+class FusedMinibatchStep:
+    """One PPO optimiser step with the hand-written fused gradient kernel (csrc/ackb_ppo.cu, include/ackb_ppo.h): forward,
+    PPO loss, backward and weight-gradient accumulation of both 64-wide MLPs in one launch with weights and activations in shared
+    memory.  Parameters and gradients live in two flat device buffers in the kernel's layout (the nn.Parameters become views
+    into them), so there is no packing, the gradient all-reduce is one call on the flat buffer, and clipping + Adam run on the
+    views.  Same arithmetic as the eager loop of ppo_update up to fp32 summation order (tests/test_ppo.py)."""
+
+    def __init__(self, policy: ActorCritic, opt: torch.optim.Optimizer, cfg: PPOConfig, obs_dim: int, device):
+        import ctypes
+        from . import _lib
+        self.L, self.ct = _lib.load(), ctypes
+        self.policy, self.opt, self.cfg, self.obs_dim, self.device = policy, opt, cfg, obs_dim, device
+        pe, ve = policy.mlp_extractor["policy_net"], policy.mlp_extractor["value_net"]
+        self.order = [pe[0].weight, pe[0].bias, pe[2].weight, pe[2].bias, ve[0].weight, ve[0].bias, ve[2].weight, ve[2].bias,
+                      policy.action_net.weight, policy.action_net.bias, policy.value_net.weight, policy.value_net.bias, policy.log_std]
+        total = sum(p.numel() for p in self.order)
+        assert total == self.L.ackb_ppo_num_params(obs_dim), "ActorCritic does not match the kernel's parameter layout"
+        self.flat_p = torch.empty(total, device=device, dtype=torch.float32)
+        self.flat_g = torch.zeros(total, device=device, dtype=torch.float32)
+        off = 0
+        with torch.no_grad():
+            for p in self.order:
+                n = p.numel()
+                self.flat_p[off:off + n].copy_(p.reshape(-1))
+                p.data = self.flat_p[off:off + n].view_as(p)       # parameters become views of the flat buffer
+                p.grad = self.flat_g[off:off + n].view_as(p)       # ... and so do their gradients
+                off += n
+        self.params = list(self.order)
+        self.diag = torch.zeros(5, device=device, dtype=torch.float32)
+        self.adv_stats = torch.zeros(2, device=device, dtype=torch.float32)
+        self.mb = -1      # any minibatch size
+
+    def shuffle_epoch(self, batch: Dict[str, torch.Tensor], perm: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Permuted copy of the rollout (one gather per epoch, 0.1 ms per million samples): the minibatches of the epoch are then
+        contiguous row ranges, which the kernel reads without the per-tile index gather."""
+        if getattr(self, "_shuf", None) is None or self._shuf["obs"].shape != batch["obs"].shape:
+            self._shuf = {k: torch.empty_like(batch[k]) for k in ("obs", "act", "logp", "adv", "ret")}
+        for k, dst in self._shuf.items():
+            torch.index_select(batch[k], 0, perm, out=dst)
+        return self._shuf
+
+    def run(self, batch: Dict[str, torch.Tensor], idx, world: int) -> int:
+        """idx: int64 index tensor (rows of `batch`), or a (start, count) tuple for a contiguous row range."""
+        c, cfg = self.ct, self.cfg
+        ptr = lambda t: c.c_void_p(t.data_ptr())
+        if isinstance(idx, tuple):
+            lo, n = idx
+            view = {k: batch[k][lo:lo + n] for k in ("obs", "act", "logp", "adv", "ret")}
+            a, idx_ptr = view["adv"], None
+        else:
+            idx = idx.contiguous()
+            view, n = batch, int(idx.numel())
+            a, idx_ptr = batch["adv"].index_select(0, idx), ptr(idx)
+        self.adv_stats[0], self.adv_stats[1] = a.mean(), a.std()
+        stream = c.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        rc = self.L.ackb_ppo_minibatch_grad(ptr(view["obs"]), ptr(view["act"]), ptr(view["logp"]), ptr(view["adv"]), ptr(view["ret"]),
+                                            idx_ptr, n, self.obs_dim, ptr(self.adv_stats), ptr(self.flat_p), ptr(self.flat_g),
+                                            ptr(self.diag), cfg.clip_range, cfg.vf_coef, cfg.ent_coef, stream)
+        if rc != 0:
+            raise RuntimeError(f"ackb_ppo_minibatch_grad failed with code {rc}")
+        nbytes = 0
+        if world > 1:
+            dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
+            self.flat_g.div_(world)
+            nbytes = self.flat_g.numel() * 4
+        torch.nn.utils.clip_grad_norm_(self.params, cfg.max_grad_norm)
+        self.opt.step()
+        return nbytes
+
+
 class PPOTrainer:
     """Rollout collection on the batched CUDA environment + PPO updates; one instance per rank."""
 
-    def __init__(self, env, cfg: PPOConfig = PPOConfig(), seed: int = 0, use_cuda_graphs: bool = True):
+    def __init__(self, env, cfg: PPOConfig = PPOConfig(), seed: int = 0, use_cuda_graphs: bool = True, learner: str = "fused"):
         self.env, self.cfg = env, cfg
         self.device = env.device
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
@@ -241,7 +317,9 @@ class PPOTrainer:
         torch.manual_seed(seed)                       # identical initial weights on every rank
         self.policy = ActorCritic(env.obs_dim).to(self.device)
         torch.manual_seed(seed * 1000003 + self.rank)  # distinct exploration noise per rank
-        self.use_graphs = use_cuda_graphs and self.device.type == "cuda"
+        # learner: "fused" = hand-written gradient kernel (default), "graph" = torch ops captured in CUDA graphs, "eager" = torch ops
+        self.learner = learner if self.device.type == "cuda" else "eager"
+        self.use_graphs = use_cuda_graphs and self.learner == "graph"
         self.opt = torch.optim.Adam(self.policy.parameters(), lr=cfg.learning_rate, eps=cfg.adam_eps, capturable=self.use_graphs)
         self.graphed: Optional[GraphedMinibatchStep] = None
         T, N, D = cfg.n_steps, env.num_envs, env.obs_dim
@@ -278,6 +356,8 @@ class PPOTrainer:
             last_val = self.policy.value(sanitize_obs(self.obs))
             adv, ret = compute_gae(b["rew"], b["val"], b["done"], last_val, cfg.gamma, cfg.gae_lambda)
         flat = dict(obs=b["obs"].flatten(0, 1), act=b["act"].flatten(0, 1), logp=b["logp"].flatten(), adv=adv.flatten(), ret=ret.flatten())
+        if self.graphed is None and self.learner == "fused":
+            self.graphed = FusedMinibatchStep(self.policy, self.opt, cfg, flat["obs"].shape[1], self.device)
         if self.use_graphs and self.graphed is None:
             n = flat["obs"].shape[0]
             self.graphed = GraphedMinibatchStep(self.policy, self.opt, cfg, max(1, n // cfg.minibatches), flat["obs"].shape[1], self.device)

@@ -13,15 +13,18 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_library_exports_every_declared_symbol():
     import __graft_entry__ as g
     lib = ctypes.CDLL(g.build_cuda())
-    hdr = open(os.path.join(ROOT, "include", "ackb.h")).read()
-    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
-    names = set(re.findall(r"\b(ackb_[a-z_]+)\s*\(", hdr))
-    assert len(names) >= 18
+    names = set()
+    for h in ("ackb.h", "ackb_ppo.h"):
+        hdr = open(os.path.join(ROOT, "include", h)).read()
+        hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+        names |= set(re.findall(r"\b(ackb_[a-z_]+)\s*\(", hdr))
+    assert len(names) >= 20
     for n in names:
-        assert hasattr(lib, n), f"{n} declared in ackb.h but not exported"
+        assert hasattr(lib, n), f"{n} declared in include/*.h but not exported"
     from mujoco_playground_b200 import _lib
     assert set(_lib.SYMBOLS) == names, "ctypes table and header disagree"
     assert lib.ackb_consts_len() > 0
+    assert lib.ackb_ppo_num_params(79) == 18757, "parameter count of the reference's MlpPolicy (SURVEY 2.1)"
 
 
 def test_no_gpu_means_error_not_fallback():
