@@ -277,8 +277,77 @@ class FusedMinibatchStep:
             torch.index_select(batch[k], 0, perm, out=dst)
         return self._shuf
 
+    def capture(self, shuffled: Dict[str, torch.Tensor], slots) -> None:
+        """CUDA graphs for the minibatch slots (start, count) of the shuffled rollout: per slot {advantage statistics + gradient
+        kernel}, and one graph for {gradient clipping + Adam}.  Needs an optimiser built with capturable=True.  The warm-up steps
+        are undone (weights and optimiser state restored in place)."""
+        dev = self.device
+        saved_p = self.flat_p.clone()
+        saved_s = {id(p): {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in self.opt.state.get(p, {}).items()} for p in self.params}
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                for sl in slots:
+                    self._grad(shuffled, sl)
+                    self._clip_step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.g1, self.g2 = {}, torch.cuda.CUDAGraph()
+        for sl in slots:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._grad(shuffled, sl)
+            self.g1[sl] = g
+        with torch.cuda.graph(self.g2):
+            self._clip_step()
+        with torch.no_grad():
+            self.flat_p.copy_(saved_p)
+            for p in self.params:
+                for k, v in self.opt.state.get(p, {}).items():
+                    if torch.is_tensor(v):
+                        if k in saved_s[id(p)]:
+                            v.copy_(saved_s[id(p)][k])
+                        else:
+                            v.zero_()
+        torch.cuda.synchronize(dev)
+
+    def _clip_step(self):
+        torch.nn.utils.clip_grad_norm_(self.params, self.cfg.max_grad_norm)
+        self.opt.step()
+
+    def _grad(self, batch: Dict[str, torch.Tensor], idx):
+        """Advantage statistics of the minibatch + the gradient kernel (fills flat_g and diag)."""
+        c, cfg = self.ct, self.cfg
+        ptr = lambda t: c.c_void_p(t.data_ptr())
+        if isinstance(idx, tuple):
+            lo, n = idx
+            view = {k: batch[k][lo:lo + n] for k in ("obs", "act", "logp", "adv", "ret")}
+            a, idx_ptr = view["adv"], None
+        else:
+            idx = idx.contiguous()
+            view, n = batch, int(idx.numel())
+            a, idx_ptr = batch["adv"].index_select(0, idx), ptr(idx)
+        self.adv_stats.copy_(torch.stack([a.mean(), a.std()]))
+        stream = c.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        rc = self.L.ackb_ppo_minibatch_grad(ptr(view["obs"]), ptr(view["act"]), ptr(view["logp"]), ptr(view["adv"]), ptr(view["ret"]),
+                                            idx_ptr, n, self.obs_dim, ptr(self.adv_stats), ptr(self.flat_p), ptr(self.flat_g),
+                                            ptr(self.diag), cfg.clip_range, cfg.vf_coef, cfg.ent_coef, stream)
+        if rc != 0:
+            raise RuntimeError(f"ackb_ppo_minibatch_grad failed with code {rc}")
+
     def run(self, batch: Dict[str, torch.Tensor], idx, world: int) -> int:
         """idx: int64 index tensor (rows of `batch`), or a (start, count) tuple for a contiguous row range."""
+        g1 = getattr(self, "g1", None)
+        if g1 is not None and isinstance(idx, tuple) and idx in g1 and batch is getattr(self, "_shuf", None):
+            g1[idx].replay()
+            nbytes = 0
+            if world > 1:
+                dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
+                self.flat_g.div_(world)
+                nbytes = self.flat_g.numel() * 4
+            self.g2.replay()
+            return nbytes
         c, cfg = self.ct, self.cfg
         ptr = lambda t: c.c_void_p(t.data_ptr())
         if isinstance(idx, tuple):
@@ -320,7 +389,9 @@ class PPOTrainer:
         # learner: "fused" = hand-written gradient kernel (default), "graph" = torch ops captured in CUDA graphs, "eager" = torch ops
         self.learner = learner if self.device.type == "cuda" else "eager"
         self.use_graphs = use_cuda_graphs and self.learner == "graph"
-        self.opt = torch.optim.Adam(self.policy.parameters(), lr=cfg.learning_rate, eps=cfg.adam_eps, capturable=self.use_graphs)
+        self.opt = torch.optim.Adam(self.policy.parameters(), lr=cfg.learning_rate, eps=cfg.adam_eps,
+                                    capturable=self.use_graphs or (use_cuda_graphs and self.learner == "fused"))
+        self.fused_graphs = use_cuda_graphs and self.learner == "fused"
         self.graphed: Optional[GraphedMinibatchStep] = None
         T, N, D = cfg.n_steps, env.num_envs, env.obs_dim
         f = dict(device=self.device, dtype=torch.float32)
@@ -358,6 +429,11 @@ class PPOTrainer:
         flat = dict(obs=b["obs"].flatten(0, 1), act=b["act"].flatten(0, 1), logp=b["logp"].flatten(), adv=adv.flatten(), ret=ret.flatten())
         if self.graphed is None and self.learner == "fused":
             self.graphed = FusedMinibatchStep(self.policy, self.opt, cfg, flat["obs"].shape[1], self.device)
+            if self.fused_graphs:
+                n = flat["obs"].shape[0]
+                mb = max(1, n // cfg.minibatches)
+                sh = self.graphed.shuffle_epoch(flat, torch.arange(n, device=self.device))
+                self.graphed.capture(sh, [(i * mb, mb) for i in range(cfg.minibatches)])
         if self.use_graphs and self.graphed is None:
             n = flat["obs"].shape[0]
             self.graphed = GraphedMinibatchStep(self.policy, self.opt, cfg, max(1, n // cfg.minibatches), flat["obs"].shape[1], self.device)

@@ -214,12 +214,23 @@ def test_fused_learner_update_matches_eager_update():
     opt_a = torch.optim.Adam(pol_a.parameters(), lr=cfg.learning_rate, eps=cfg.adam_eps)
     opt_b = torch.optim.Adam(pol_b.parameters(), lr=cfg.learning_rate, eps=cfg.adam_eps)
     f = FusedMinibatchStep(pol_b, opt_b, cfg, D, dev)
-    ga, gb = torch.Generator(device=dev), torch.Generator(device=dev)
-    ga.manual_seed(11); gb.manual_seed(11)
-    sa = ppo_update(pol_a, opt_a, batch, cfg, generator=ga)
-    sb = ppo_update(pol_b, opt_b, batch, cfg, generator=gb, graphed=f)
-    assert sa["steps"] == sb["steps"] == 12
+    # third copy: the same fused step replayed from CUDA graphs (capturable Adam)
+    pol_c = copy.deepcopy(pol_a)
+    opt_c = torch.optim.Adam(pol_c.parameters(), lr=cfg.learning_rate, eps=cfg.adam_eps, capturable=True)
+    fc = FusedMinibatchStep(pol_c, opt_c, cfg, D, dev)
+    fc.capture(fc.shuffle_epoch(batch, torch.arange(n, device=dev)), [(i * (n // 4), n // 4) for i in range(4)])
+    for pa, pc in zip(pol_a.parameters(), pol_c.parameters()):
+        assert torch.equal(pa, pc), "capture must leave the weights untouched"
+    gens = [torch.Generator(device=dev) for _ in range(3)]
+    for g in gens:
+        g.manual_seed(11)
+    sa = ppo_update(pol_a, opt_a, batch, cfg, generator=gens[0])
+    sb = ppo_update(pol_b, opt_b, batch, cfg, generator=gens[1], graphed=f)
+    sc = ppo_update(pol_c, opt_c, batch, cfg, generator=gens[2], graphed=fc)
+    assert sa["steps"] == sb["steps"] == sc["steps"] == 12
     for k in ("pg_loss", "v_loss", "entropy", "approx_kl"):
         assert abs(sa[k] - sb[k]) < 1e-4 * max(1.0, abs(sa[k])), k
-    for pa, pb in zip(pol_a.parameters(), pol_b.parameters()):
+        assert abs(sa[k] - sc[k]) < 1e-4 * max(1.0, abs(sa[k])), k
+    for pa, pb, pc in zip(pol_a.parameters(), pol_b.parameters(), pol_c.parameters()):
         assert torch.allclose(pa, pb, atol=5e-5, rtol=1e-3)
+        assert torch.allclose(pa, pc, atol=5e-5, rtol=1e-3)
