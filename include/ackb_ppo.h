@@ -23,6 +23,11 @@ extern "C" {
 /* number of floats of the parameter / gradient vector for an observation of obs_dim floats */
 int ackb_ppo_num_params(int obs_dim);
 
+/* Arithmetic of the gradient kernel: 1 = TF32 tensor-core mma with fp32 accumulation (default; same operand precision as
+ * torch.backends.cuda.matmul.allow_tf32), 0 = fp32 CUDA-core FMAs.  Process-wide; the environment variable ACKB_PPO_TC sets the
+ * initial value. */
+int ackb_ppo_set_mode(int tensor_cores);
+
 /* Gradient of the PPO loss  mean_i[-min(A_i r_i, A_i clip(r_i, 1-c, 1+c))] + vf_coef * mean_i (V_i - R_i)^2 - ent_coef * H
  * over the minibatch rows idx[0 .. mb-1] of the rollout arrays (A normalised with adv_mean_std = {mean, std} of the minibatch,
  * A = (adv - mean) / (std + 1e-8)).  grads (zeroed by the call) receives d loss / d params; diag receives

@@ -40,6 +40,7 @@ SYMBOLS = {
     "ackb_last_error": (ctypes.c_char_p, [_vp]),
     # include/ackb_ppo.h
     "ackb_ppo_num_params": (_i, [_i]),
+    "ackb_ppo_set_mode": (_i, [_i]),
     "ackb_ppo_minibatch_grad": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp]),
 }
 

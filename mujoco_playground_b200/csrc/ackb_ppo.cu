@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "ackb.h"
 #include "ackb_ppo.h"
@@ -337,11 +338,395 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel(PpoArgs a) {
   }
 }
 
+
+// =================================================================================================================
+// Tensor-core variant: the five GEMMs of a tile (layer 1, layer 2, dH1, dW2, dW1) run on mma.sync m16n8k8 TF32 with fp32
+// accumulation; operands are rounded to TF32 once, when they are written to shared memory.  Tiles of 32 samples; row strides are
+// padded (84 / 132 / 136 / 72 floats) so that fragment loads are (nearly) bank-conflict free.  The weight-gradient accumulators
+// are mma C fragments that live in registers across all tiles of the CTA.  Heads, loss derivatives and the bias / head
+// gradients reuse the CUDA-core code paths.
+// =================================================================================================================
+constexpr int TT = 32;                 // samples per tile
+constexpr int XS = 84, AS = 132, W1S = 136, W2S = 72;
+constexpr int T_W1T = 0;                          // [KP][W1S]
+constexpr int T_W2T = T_W1T + KP * W1S;           // [2][64][W2S]   [net][k][n]
+constexpr int T_W2 = T_W2T + 2 * H * W2S;         // [2][64][W2S]   [net][n][k]
+constexpr int T_W3 = T_W2 + 2 * H * W2S;          // [3][64]
+constexpr int T_B1 = T_W3 + 3 * H;
+constexpr int T_B2 = T_B1 + 128;
+constexpr int T_B3 = T_B2 + 128;
+constexpr int T_LS = T_B3 + 4;
+constexpr int T_X = T_LS + 4;                     // [2][TT][XS]  double buffered: the next tile is fetched with cp.async while this one computes
+constexpr int T_H1 = T_X + 2 * TT * XS;           // [TT][AS]
+constexpr int T_H2 = T_H1 + TT * AS;
+constexpr int T_DH = T_H2 + TT * AS;
+constexpr int T_DO = T_DH + TT * AS;              // [TT][4]
+constexpr int T_TOTAL = T_DO + TT * 4;
+
+__device__ __forceinline__ float tf32r(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// A fragment (16 x 8, row major) of a matrix stored [row][col] with row stride `ld`: rows row0 .. row0+15, cols col0 .. col0+7
+__device__ __forceinline__ void lda_rowmajor(uint32_t (&a)[4], const float* m, int ld, int row0, int col0, int g, int t) {
+  a[0] = __float_as_uint(m[(row0 + g) * ld + col0 + t]);
+  a[1] = __float_as_uint(m[(row0 + g + 8) * ld + col0 + t]);
+  a[2] = __float_as_uint(m[(row0 + g) * ld + col0 + t + 4]);
+  a[3] = __float_as_uint(m[(row0 + g + 8) * ld + col0 + t + 4]);
+}
+// A fragment of the TRANSPOSE of a matrix stored [k][row] (row stride ld): element (row, k) = m[k * ld + row]
+__device__ __forceinline__ void lda_transposed(uint32_t (&a)[4], const float* m, int ld, int row0, int k0, int g, int t) {
+  a[0] = __float_as_uint(m[(k0 + t) * ld + row0 + g]);
+  a[1] = __float_as_uint(m[(k0 + t) * ld + row0 + g + 8]);
+  a[2] = __float_as_uint(m[(k0 + t + 4) * ld + row0 + g]);
+  a[3] = __float_as_uint(m[(k0 + t + 4) * ld + row0 + g + 8]);
+}
+// B fragment (8 x 8, k x n) of a matrix stored [k][n] with row stride ld
+__device__ __forceinline__ void ldb(uint32_t (&b)[2], const float* m, int ld, int k0, int n0, int g, int t) {
+  b[0] = __float_as_uint(m[(k0 + t) * ld + n0 + g]);
+  b[1] = __float_as_uint(m[(k0 + t + 4) * ld + n0 + g]);
+}
+
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc));
+}
+// asynchronous gather of the observation rows of one tile into xbuf (zero padding written directly)
+__device__ __forceinline__ void gather_tile_async(const PpoArgs& a, int tile, float* xbuf, int t) {
+  const int sbase = tile * TT, ns = min(TT, a.mb - sbase), D = a.D;
+  for (int i = t; i < TT * KP; i += NT) {
+    const int s = i / KP, k = i - s * KP;
+    if (s < ns && k < D) {
+      const int64_t row = a.idx ? a.idx[sbase + s] : (int64_t)(sbase + s);
+      cp_async4(&xbuf[s * XS + k], &a.obs[row * D + k]);
+    } else {
+      xbuf[s * XS + k] = 0.0f;
+    }
+  }
+  asm volatile("cp.async.commit_group;");
+}
+
+__global__ void __launch_bounds__(NT, 1) ppo_grad_kernel_tc(PpoArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int g = lane >> 2, q = lane & 3;      // mma fragment coordinates
+  const int D = a.D;
+  const Offsets o = offsets(D);
+  const float* P = a.params;
+
+  for (int i = t; i < KP * 128; i += NT) {
+    const int k = i >> 7, n = i & 127, net = n >> 6, r = n & 63;
+    sm[T_W1T + k * W1S + n] = (k < D) ? tf32r(P[(net ? o.W1v : o.W1p) + r * D + k]) : 0.0f;
+  }
+  for (int i = t; i < 2 * H * H; i += NT) {
+    const int net = i >> 12, n = (i >> 6) & 63, k = i & 63;
+    const float w = tf32r(P[(net ? o.W2v : o.W2p) + n * H + k]);
+    sm[T_W2 + net * H * W2S + n * W2S + k] = w;
+    sm[T_W2T + net * H * W2S + k * W2S + n] = w;
+  }
+  for (int i = t; i < 3 * H; i += NT) sm[T_W3 + i] = (i < 2 * H) ? P[o.Wa + i] : P[o.Wv + (i - 2 * H)];
+  if (t < 128) {
+    const int net = t >> 6, r = t & 63;
+    sm[T_B1 + t] = P[(net ? o.b1v : o.b1p) + r];
+    sm[T_B2 + t] = P[(net ? o.b2v : o.b2p) + r];
+  }
+  if (t < 2) { sm[T_B3 + t] = P[o.ba + t]; sm[T_LS + t] = P[o.ls + t]; }
+  if (t == 2) sm[T_B3 + 2] = P[o.bv];
+  __syncthreads();
+
+  const float adv_mean = a.adv_stats[0], adv_istd = 1.0f / (a.adv_stats[1] + 1e-8f);
+  const float inv_mb = 1.0f / (float)a.mb;
+  const float ls0 = sm[T_LS], ls1 = sm[T_LS + 1];
+  const float iv0 = expf(-2.0f * ls0), iv1 = expf(-2.0f * ls1);
+
+  // weight-gradient accumulators (mma C fragments):
+  //   dW1[n][k]: warp w owns rows n = 16 w .. 16 w + 15 (both nets, 0..127), 10 column tiles of 8 over k = 0..79
+  //   dW2[net][n][k]: warp w owns net = w >> 2, rows n = 16 (w & 3) .. + 15, 8 column tiles over k = 0..63
+  float acc1[10][4], acc2[8][4];
+#pragma unroll
+  for (int i = 0; i < 10; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc1[i][j] = 0.0f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc2[i][j] = 0.0f;
+  float g3 = 0.0f, gb1 = 0.0f, gb2 = 0.0f, gb3 = 0.0f, gls0 = 0.0f, gls1 = 0.0f;
+  float d_pg = 0.0f, d_vl = 0.0f, d_kl = 0.0f, d_cf = 0.0f;
+
+  const int nb0 = 16 * warp;                 // output columns of this warp in the activation GEMMs
+  const int gnet = warp >> 2;                // net of those columns
+  const int w2net = warp >> 2, w2row0 = 16 * (warp & 3);
+
+  const int ntiles = (a.mb + TT - 1) / TT;
+  int buf = 0;
+  if ((int)blockIdx.x < ntiles) gather_tile_async(a, blockIdx.x, &sm[T_X], t);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+    const int sbase = tile * TT;
+    const int ns = min(TT, a.mb - sbase);
+    float* const X = &sm[T_X + buf * TT * XS];
+    // ---- 1. this tile's observation rows have been fetched asynchronously: wait, round to TF32 (each thread its own elements),
+    // then start fetching the next tile into the other buffer
+    asm volatile("cp.async.wait_all;");
+    for (int i = t; i < TT * KP; i += NT) {
+      const int s = i / KP, k = i - s * KP;
+      X[s * XS + k] = tf32r(X[s * XS + k]);
+    }
+    __syncthreads();
+    if (tile + (int)gridDim.x < ntiles) gather_tile_async(a, tile + gridDim.x, &sm[T_X + (buf ^ 1) * TT * XS], t);
+    // ---- 2. layer 1: H1[s][n] = tanh(sum_k X[s][k] W1t[k][n] + b1[n])
+    {
+      float c[2][2][4];
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) c[m][j][e] = 0.0f;
+#pragma unroll 2
+      for (int k0 = 0; k0 < KP; k0 += 8) {
+        uint32_t af[2][4], bf[2][2];
+        lda_rowmajor(af[0], X, XS, 0, k0, g, q);
+        lda_rowmajor(af[1], X, XS, 16, k0, g, q);
+        ldb(bf[0], &sm[T_W1T], W1S, k0, nb0, g, q);
+        ldb(bf[1], &sm[T_W1T], W1S, k0, nb0 + 8, g, q);
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) mma_tf32(c[m][j], af[m], bf[j]);
+      }
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int col = nb0 + 8 * j + 2 * q, row = 16 * m + g;
+          sm[T_H1 + row * AS + col] = tf32r(tanhf(c[m][j][0] + sm[T_B1 + col]));
+          sm[T_H1 + row * AS + col + 1] = tf32r(tanhf(c[m][j][1] + sm[T_B1 + col + 1]));
+          sm[T_H1 + (row + 8) * AS + col] = tf32r(tanhf(c[m][j][2] + sm[T_B1 + col]));
+          sm[T_H1 + (row + 8) * AS + col + 1] = tf32r(tanhf(c[m][j][3] + sm[T_B1 + col + 1]));
+        }
+    }
+    __syncthreads();
+    // ---- 3. layer 2 (block diagonal)
+    {
+      float c[2][2][4];
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) c[m][j][e] = 0.0f;
+      const float* A = &sm[T_H1 + gnet * H];
+      const float* B = &sm[T_W2T + gnet * H * W2S];
+      const int nn0 = nb0 - gnet * H;
+#pragma unroll 2
+      for (int k0 = 0; k0 < H; k0 += 8) {
+        uint32_t af[2][4], bf[2][2];
+        lda_rowmajor(af[0], A, AS, 0, k0, g, q);
+        lda_rowmajor(af[1], A, AS, 16, k0, g, q);
+        ldb(bf[0], B, W2S, k0, nn0, g, q);
+        ldb(bf[1], B, W2S, k0, nn0 + 8, g, q);
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) mma_tf32(c[m][j], af[m], bf[j]);
+      }
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int col = nb0 + 8 * j + 2 * q, row = 16 * m + g;
+          sm[T_H2 + row * AS + col] = tf32r(tanhf(c[m][j][0] + sm[T_B2 + col]));
+          sm[T_H2 + row * AS + col + 1] = tf32r(tanhf(c[m][j][1] + sm[T_B2 + col + 1]));
+          sm[T_H2 + (row + 8) * AS + col] = tf32r(tanhf(c[m][j][2] + sm[T_B2 + col]));
+          sm[T_H2 + (row + 8) * AS + col + 1] = tf32r(tanhf(c[m][j][3] + sm[T_B2 + col + 1]));
+        }
+    }
+    __syncthreads();
+    // ---- 4. heads + PPO loss derivatives: warp w owns samples 4w .. 4w+3 (fp32 CUDA cores)
+#pragma unroll 1
+    for (int si = 0; si < TT / 8; ++si) {
+      const int s = warp * (TT / 8) + si;
+      const float* h2 = &sm[T_H2 + s * AS];
+      float p0 = h2[lane] * sm[T_W3 + lane] + h2[lane + 32] * sm[T_W3 + lane + 32];
+      float p1 = h2[lane] * sm[T_W3 + H + lane] + h2[lane + 32] * sm[T_W3 + H + lane + 32];
+      float pv = h2[H + lane] * sm[T_W3 + 2 * H + lane] + h2[H + lane + 32] * sm[T_W3 + 2 * H + lane + 32];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        p0 += __shfl_xor_sync(0xffffffffu, p0, off); p1 += __shfl_xor_sync(0xffffffffu, p1, off); pv += __shfl_xor_sync(0xffffffffu, pv, off);
+      }
+      if (lane == 0) {
+        float dm0 = 0.0f, dm1 = 0.0f, dv = 0.0f;
+        if (s < ns) {
+          const int64_t row = a.idx ? a.idx[sbase + s] : (int64_t)(sbase + s);
+          const float m0 = p0 + sm[T_B3], m1 = p1 + sm[T_B3 + 1], v = pv + sm[T_B3 + 2];
+          const float e0 = a.act[row * 2] - m0, e1 = a.act[row * 2 + 1] - m1;
+          const float q0 = e0 * e0 * iv0, q1 = e1 * e1 * iv1;
+          const float logp = -0.5f * q0 - ls0 - 0.9189385332046727f - 0.5f * q1 - ls1 - 0.9189385332046727f;
+          const float A_ = (a.adv[row] - adv_mean) * adv_istd;
+          const float lr = logp - a.old_logp[row];
+          const float r = expf(lr);
+          const float rc = fminf(fmaxf(r, 1.0f - a.clip), 1.0f + a.clip);
+          const float s1 = A_ * r, s2 = A_ * rc;
+          const float dlogp = (s1 <= s2) ? -A_ * r : 0.0f;
+          dm0 = dlogp * e0 * iv0 * inv_mb; dm1 = dlogp * e1 * iv1 * inv_mb;
+          gls0 += dlogp * (q0 - 1.0f) * inv_mb; gls1 += dlogp * (q1 - 1.0f) * inv_mb;
+          const float R = a.ret[row];
+          dv = a.vf_coef * 2.0f * (v - R) * inv_mb;
+          d_pg += -fminf(s1, s2); d_vl += (v - R) * (v - R); d_kl += (r - 1.0f) - lr; d_cf += (fabsf(r - 1.0f) > a.clip) ? 1.0f : 0.0f;
+        }
+        sm[T_DO + s * 4] = dm0; sm[T_DO + s * 4 + 1] = dm1; sm[T_DO + s * 4 + 2] = dv; sm[T_DO + s * 4 + 3] = 0.0f;
+      }
+    }
+    __syncthreads();
+    // ---- 5. dH2 = (dOut W3) * (1 - H2^2)   (TF32-rounded: it feeds two GEMMs)
+    for (int i = t; i < TT * 128; i += NT) {
+      const int s = i >> 7, n = i & 127;
+      const float h = sm[T_H2 + s * AS + n];
+      const float gg = (n < H) ? sm[T_DO + s * 4] * sm[T_W3 + n] + sm[T_DO + s * 4 + 1] * sm[T_W3 + H + n]
+                               : sm[T_DO + s * 4 + 2] * sm[T_W3 + 2 * H + (n - H)];
+      sm[T_DH + s * AS + n] = tf32r(gg * (1.0f - h * h));
+    }
+    __syncthreads();
+    // ---- 6. head / bias gradients (CUDA cores), dW2 += dH2^T H1 (tensor cores)
+    if (t < 3 * H) {
+      const int r = t >> 6, c = t & 63, hoff = (r < 2 ? 0 : H) + c;
+#pragma unroll 4
+      for (int s = 0; s < TT; ++s) g3 = fmaf(sm[T_DO + s * 4 + r], sm[T_H2 + s * AS + hoff], g3);
+    }
+    if (t < 3)
+      for (int s = 0; s < TT; ++s) gb3 += sm[T_DO + s * 4 + t];
+    if (t < 128)
+      for (int s = 0; s < TT; ++s) gb2 += sm[T_DH + s * AS + t];
+    {
+      const float* At = &sm[T_DH + w2net * H];      // dH2[s][net*64 + n]  -> A = transpose, element (n, s)
+      const float* B = &sm[T_H1 + w2net * H];       // H1[s][net*64 + k]   -> B[k = s][n = k]
+#pragma unroll
+      for (int s0 = 0; s0 < TT; s0 += 8) {
+        uint32_t af[4];
+        lda_transposed(af, At, AS, w2row0, s0, g, q);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint32_t bf[2];
+          ldb(bf, B, AS, s0, 8 * j, g, q);
+          mma_tf32(acc2[j], af, bf);
+        }
+      }
+    }
+    // ---- 7. dH1 = (dH2 W2) * (1 - H1^2)
+    {
+      float c[2][2][4];
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) c[m][j][e] = 0.0f;
+      const float* A = &sm[T_DH + gnet * H];
+      const float* B = &sm[T_W2 + gnet * H * W2S];
+      const int nn0 = nb0 - gnet * H;
+#pragma unroll 2
+      for (int k0 = 0; k0 < H; k0 += 8) {
+        uint32_t af[2][4], bf[2][2];
+        lda_rowmajor(af[0], A, AS, 0, k0, g, q);
+        lda_rowmajor(af[1], A, AS, 16, k0, g, q);
+        ldb(bf[0], B, W2S, k0, nn0, g, q);
+        ldb(bf[1], B, W2S, k0, nn0 + 8, g, q);
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) mma_tf32(c[m][j], af[m], bf[j]);
+      }
+      __syncthreads();   // all reads of dH2 (steps 6 and 7) are done: the buffer now takes dH1
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int col = nb0 + 8 * j + 2 * q, row = 16 * m + g;
+          const float h00 = sm[T_H1 + row * AS + col], h01 = sm[T_H1 + row * AS + col + 1];
+          const float h10 = sm[T_H1 + (row + 8) * AS + col], h11 = sm[T_H1 + (row + 8) * AS + col + 1];
+          sm[T_DH + row * AS + col] = tf32r(c[m][j][0] * (1.0f - h00 * h00));
+          sm[T_DH + row * AS + col + 1] = tf32r(c[m][j][1] * (1.0f - h01 * h01));
+          sm[T_DH + (row + 8) * AS + col] = tf32r(c[m][j][2] * (1.0f - h10 * h10));
+          sm[T_DH + (row + 8) * AS + col + 1] = tf32r(c[m][j][3] * (1.0f - h11 * h11));
+        }
+    }
+    __syncthreads();
+    // ---- 8. db1, dW1 += dH1^T X
+    if (t < 128)
+      for (int s = 0; s < TT; ++s) gb1 += sm[T_DH + s * AS + t];
+    {
+      const float* At = &sm[T_DH];                  // dH1[s][n] -> element (n, s)
+      const float* B = X;                           // X[s][k]   -> B[k = s][n = k]
+#pragma unroll
+      for (int s0 = 0; s0 < TT; s0 += 8) {
+        uint32_t af[4];
+        lda_transposed(af, At, AS, 16 * warp, s0, g, q);
+#pragma unroll
+        for (int j = 0; j < 10; ++j) {
+          uint32_t bf[2];
+          ldb(bf, B, XS, s0, 8 * j, g, q);
+          mma_tf32(acc1[j], af, bf);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- flush: C fragment element e of tile j: row = r0 + g (+8 for e >= 2), col = 8 j + 2 q + (e & 1)
+  float* G = a.grads;
+#pragma unroll
+  for (int j = 0; j < 10; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int n = 16 * warp + g + ((e & 2) ? 8 : 0), k = 8 * j + 2 * q + (e & 1);
+      const int net = n >> 6, r = n & 63;
+      if (k < D) atomicAdd(&G[(net ? o.W1v : o.W1p) + r * D + k], acc1[j][e]);
+    }
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int n = w2row0 + g + ((e & 2) ? 8 : 0), k = 8 * j + 2 * q + (e & 1);
+      atomicAdd(&G[(w2net ? o.W2v : o.W2p) + n * H + k], acc2[j][e]);
+    }
+  if (t < 3 * H) {
+    const int r = t >> 6, c = t & 63;
+    atomicAdd(&G[r < 2 ? o.Wa + r * H + c : o.Wv + c], g3);
+  }
+  if (t < 128) {
+    const int net = t >> 6, r = t & 63;
+    atomicAdd(&G[(net ? o.b1v : o.b1p) + r], gb1);
+    atomicAdd(&G[(net ? o.b2v : o.b2p) + r], gb2);
+  }
+  if (t < 2) atomicAdd(&G[o.ba + t], gb3);
+  if (t == 2) atomicAdd(&G[o.bv], gb3);
+  if (lane == 0) {
+    atomicAdd(&G[o.ls], gls0); atomicAdd(&G[o.ls + 1], gls1);
+    atomicAdd(&a.diag[0], d_pg * inv_mb); atomicAdd(&a.diag[1], d_vl * inv_mb);
+    atomicAdd(&a.diag[3], d_kl * inv_mb); atomicAdd(&a.diag[4], d_cf * inv_mb);
+  }
+  if (blockIdx.x == 0 && t == 0) {
+    a.diag[2] = 2.0f * 1.4189385332046727f + ls0 + ls1;
+    atomicAdd(&G[o.ls], -a.ent_coef); atomicAdd(&G[o.ls + 1], -a.ent_coef);
+  }
+}
+
 }  // namespace
+
+static int g_use_tc = -1;
 
 extern "C" {
 
 int ackb_ppo_num_params(int obs_dim) { return offsets(obs_dim).total; }
+
+int ackb_ppo_set_mode(int tensor_cores) { g_use_tc = tensor_cores ? 1 : 0; return ACKB_OK; }
 
 int ackb_ppo_minibatch_grad(const float* obs, const float* act, const float* old_logp, const float* adv, const float* ret,
                             const int64_t* idx, int mb, int obs_dim, const float* adv_mean_std, const float* params, float* grads,
@@ -352,9 +737,13 @@ int ackb_ppo_minibatch_grad(const float* obs, const float* act, const float* old
   static bool attr_done[64] = {false};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return ACKB_ERR_NO_DEVICE;
-  const size_t smem = (size_t)S_TOTAL * sizeof(float);
+  // ACKB_PPO_TC=0 (or ackb_ppo_set_mode(0)) selects the fp32 CUDA-core kernel; default: TF32 tensor-core kernel
+  if (g_use_tc < 0) { const char* ev = getenv("ACKB_PPO_TC"); g_use_tc = ev ? (atoi(ev) != 0) : 1; }
+  const int use_tc = g_use_tc;
+  const size_t smem = (size_t)(use_tc ? T_TOTAL : S_TOTAL) * sizeof(float);
   if (dev < 64 && !attr_done[dev]) {
-    if (cudaFuncSetAttribute(ppo_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return ACKB_ERR_CUDA;
+    if (cudaFuncSetAttribute(ppo_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S_TOTAL * sizeof(float))) != cudaSuccess) return ACKB_ERR_CUDA;
+    if (cudaFuncSetAttribute(ppo_grad_kernel_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(T_TOTAL * sizeof(float))) != cudaSuccess) return ACKB_ERR_CUDA;
     attr_done[dev] = true;
   }
   int sms = 148;
@@ -363,9 +752,10 @@ int ackb_ppo_minibatch_grad(const float* obs, const float* act, const float* old
   if (cudaMemsetAsync(grads, 0, sizeof(float) * o.total, s) != cudaSuccess) return ACKB_ERR_CUDA;
   if (cudaMemsetAsync(diag, 0, sizeof(float) * 5, s) != cudaSuccess) return ACKB_ERR_CUDA;
   PpoArgs a{obs, act, old_logp, adv, ret, idx, mb, obs_dim, adv_mean_std, params, grads, diag, clip_range, vf_coef, ent_coef};
-  const int ntiles = (mb + TS - 1) / TS;
+  const int ntiles = (mb + (use_tc ? TT : TS) - 1) / (use_tc ? TT : TS);
   const int grid = ntiles < sms ? ntiles : sms;
-  ppo_grad_kernel<<<grid, NT, smem, s>>>(a);
+  if (use_tc) ppo_grad_kernel_tc<<<grid, NT, smem, s>>>(a);
+  else ppo_grad_kernel<<<grid, NT, smem, s>>>(a);
   return cudaGetLastError() == cudaSuccess ? ACKB_OK : ACKB_ERR_CUDA;
 }
 

@@ -155,8 +155,8 @@ def test_cuda_graph_update_matches_eager_update():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("obs_dim,n", [(79, 4096), (43, 1000)])
-def test_fused_gradient_kernel_matches_autograd(obs_dim, n):
+@pytest.mark.parametrize("obs_dim,n,tc,tol", [(79, 4096, 0, 2e-4), (43, 1000, 0, 2e-4), (79, 4096, 1, 4e-3), (43, 1000, 1, 4e-3)])
+def test_fused_gradient_kernel_matches_autograd(obs_dim, n, tc, tol):
     """csrc/ackb_ppo.cu against torch autograd on the same minibatch: every parameter gradient and the loss diagnostics
     (ragged last tile, index gather, both observation widths)."""
     import copy
@@ -186,16 +186,19 @@ def test_fused_gradient_kernel_matches_autograd(obs_dim, n):
     # fused kernel (lr = 0: the optimiser step inside run() must not move the weights)
     opt = torch.optim.SGD(pol.parameters(), lr=0.0)
     f = FusedMinibatchStep(pol, opt, cfg, obs_dim, dev)
+    f.L.ackb_ppo_set_mode(tc)                      # 0: fp32 CUDA cores, 1: TF32 tensor cores (fp32 accumulation)
     f.cfg = PPOConfig(max_grad_norm=1e30)          # no clipping: compare raw gradients
     f.run(batch, idx, world=1)
     torch.cuda.synchronize()
     for (name, pr), pf in zip(ref.named_parameters(), pol.parameters()):
         scale = max(1e-6, pr.grad.abs().max().item())
-        assert (pr.grad - pf.grad).abs().max().item() < 2e-4 * scale + 1e-7, name
+        assert (pr.grad - pf.grad).abs().max().item() < tol * scale + 1e-7, name
     d = f.diag.cpu().numpy()
-    assert abs(d[0] - pg.item()) < 1e-4 * max(1, abs(pg.item())) and abs(d[1] - vl.item()) < 1e-4 * vl.item()
-    assert abs(d[2] - ent.mean().item()) < 1e-5 and abs(d[4] - clip_frac) < 1e-6
-    assert abs(d[3] - ((ratio - 1) - (logp - old_logp)).mean().item()) < 1e-3 * max(1.0, abs(d[3]))
+    dt = 1e-4 if tc == 0 else 5e-3
+    assert abs(d[0] - pg.item()) < dt * max(1, abs(pg.item())) and abs(d[1] - vl.item()) < dt * vl.item()
+    assert abs(d[2] - ent.mean().item()) < 1e-5 and abs(d[4] - clip_frac) < (1e-6 if tc == 0 else 5e-3)
+    assert abs(d[3] - ((ratio - 1) - (logp - old_logp)).mean().item()) < 10 * dt * max(1.0, abs(d[3]))
+    f.L.ackb_ppo_set_mode(1)
 
 
 @pytest.mark.gpu
@@ -214,6 +217,7 @@ def test_fused_learner_update_matches_eager_update():
     opt_a = torch.optim.Adam(pol_a.parameters(), lr=cfg.learning_rate, eps=cfg.adam_eps)
     opt_b = torch.optim.Adam(pol_b.parameters(), lr=cfg.learning_rate, eps=cfg.adam_eps)
     f = FusedMinibatchStep(pol_b, opt_b, cfg, D, dev)
+    f.L.ackb_ppo_set_mode(0)                       # fp32 CUDA-core arithmetic for the tight comparison with the eager loop
     # third copy: the same fused step replayed from CUDA graphs (capturable Adam)
     pol_c = copy.deepcopy(pol_a)
     opt_c = torch.optim.Adam(pol_c.parameters(), lr=cfg.learning_rate, eps=cfg.adam_eps, capturable=True)
@@ -234,3 +238,4 @@ def test_fused_learner_update_matches_eager_update():
     for pa, pb, pc in zip(pol_a.parameters(), pol_b.parameters(), pol_c.parameters()):
         assert torch.allclose(pa, pb, atol=5e-5, rtol=1e-3)
         assert torch.allclose(pa, pc, atol=5e-5, rtol=1e-3)
+    f.L.ackb_ppo_set_mode(1)
