@@ -681,12 +681,18 @@ struct Sim {
 #ifndef ACKB_CU_SMEM
 #define ACKB_CU_SMEM 2   // contacts of a wheel unrolled (ILP), wheels rolled (code size)
 #endif
-  static constexpr int CU = (WPL == 1) ? NC : ACKB_CU_SMEM;
+  // records live in registers when a lane owns one wheel.  (Measured alternative for NC = 4, ACKB_REG_RECORDS_NC4=0: records in
+  // shared memory with a rolled contact-group loop -- smaller solver loop, but 5 % slower on the scene: 52.0 vs 54.8 M env-steps/s.)
+#ifndef ACKB_REG_RECORDS_NC4
+#define ACKB_REG_RECORDS_NC4 1
+#endif
+  static constexpr bool kRegRecords = (WPL == 1) && (NC <= 2 || ACKB_REG_RECORDS_NC4 != 0);
+  static constexpr int CU = kRegRecords ? NC : ACKB_CU_SMEM;
   // Contact loops of the solver: slots are visited in groups of CSTEP; groups at or beyond `ncs` (a warp-uniform count: 2 when no
   // environment of the warp has a wheel-box contact in this substep) are skipped.  Register records: fully unrolled (static
   // indices); shared-memory records: the group loop stays rolled.
-  static constexpr int CSTEP = (NC >= 2) ? ((WPL == 1) ? 2 : (ACKB_CU_SMEM >= 2 ? 2 : 1)) : 1;
-  static constexpr int CO = (WPL == 1) ? (NC / CSTEP) : 1;
+  static constexpr int CSTEP = (NC >= 2) ? (kRegRecords ? 2 : (ACKB_CU_SMEM >= 2 ? 2 : 1)) : 1;
+  static constexpr int CO = kRegRecords ? (NC / CSTEP) : 1;
 #define ACKB_CONTACTS_BEGIN(c)                                                     \
   _Pragma("unroll(CO)") for (int c##_g = 0; c##_g < NC; c##_g += CSTEP) {          \
     if (c##_g < ncs) {                                                             \

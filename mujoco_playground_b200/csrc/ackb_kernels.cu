@@ -90,7 +90,7 @@ __device__ __forceinline__ unsigned warp_sum_u32(unsigned v) {
 template <typename T, int LANES, int NC>
 struct Geo {
   static constexpr int WPL = LANES == 8 ? 1 : 4 / LANES;
-  static constexpr bool kSmemWheels = WPL > 1;
+  static constexpr bool kSmemWheels = !Sim<T, LANES, NC>::kRegRecords;
   static constexpr int kWheelUnits = sizeof(Wheel<T, NC>) / sizeof(T);          // record size in units of T
   static constexpr int kStride = WPL * kWheelUnits + ((WPL * kWheelUnits) % 2 == 0 ? 1 : 0);   // odd
   // shared-memory layouts: pick the CTA size (128, 64 or 32 threads) that fits the most warps into the 227 KB of an SM
