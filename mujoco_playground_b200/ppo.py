@@ -264,6 +264,13 @@ class FusedMinibatchStep:
                 p.grad = self.flat_g[off:off + n].view_as(p)       # ... and so do their gradients
                 off += n
         self.params = list(self.order)
+        # the optimiser works on ONE flat parameter (Adam and the global-norm clip are elementwise / global, so this is the same
+        # arithmetic as 13 per-tensor updates with a fraction of the kernels); only for a fresh optimiser (no state to remap)
+        if len(opt.param_groups) == 1 and not opt.state:
+            self.flat_param = torch.nn.Parameter(self.flat_p, requires_grad=True)
+            self.flat_param.grad = self.flat_g
+            opt.param_groups[0]["params"] = [self.flat_param]
+            self.params = [self.flat_param]
         self.diag = torch.zeros(5, device=device, dtype=torch.float32)
         self.adv_stats = torch.zeros(2, device=device, dtype=torch.float32)
         self.mb = -1      # any minibatch size
