@@ -37,6 +37,12 @@ int ackb_ppo_minibatch_grad(const float* obs, const float* act, const float* old
                             const int64_t* idx, int mb, int obs_dim, const float* adv_mean_std, const float* params, float* grads,
                             float* diag, float clip_range, float vf_coef, float ent_coef, void* stream);
 
+/* Rollout side (SB3 policy.forward() inside collect_rollouts): value[n] = V(obs) and, unless value_only, mean[n][2] = pi(obs);
+ * if `action` is given also a sample action = mean + exp(log_std) * eps (eps ~ N(0,1), Philox keyed by (seed, step, row)) and,
+ * if `logp` is given, its log-probability.  mean / action / logp may be NULL.  TF32 tensor-core tiles.  Asynchronous on `stream`. */
+int ackb_ppo_act(const float* obs, int n, int obs_dim, const float* params, float* mean, float* value, float* action, float* logp,
+                 uint64_t seed, uint32_t step, int value_only, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

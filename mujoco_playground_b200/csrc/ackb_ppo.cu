@@ -718,6 +718,178 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel_tc(PpoArgs a) {
   }
 }
 
+
+// =================================================================================================================
+// Rollout side: policy / value forward for a whole batch of observations in one launch (what SB3's policy.forward() does per
+// step inside collect_rollouts): mean = pi(obs), value = V(obs), and, if requested, a sampled action a = mean + exp(log_std) * eps
+// with its log-probability.  eps ~ N(0, 1) from Philox4x32-10 keyed by (seed, step, row) through Box-Muller.  Same TF32 tiles as
+// the gradient kernel (forward half), one CTA per SM walking 32-row tiles.
+// =================================================================================================================
+struct ActArgs {
+  const float* obs;
+  int n, D;
+  const float* params;
+  float *mean, *value, *action, *logp;     // mean [n][2] / action [n][2] / logp [n] may be null
+  unsigned long long seed;
+  unsigned step;
+  int value_only;                           // skip the policy net (bootstrap values of terminal observations)
+};
+
+__device__ __forceinline__ void philox_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__global__ void __launch_bounds__(NT, 1) ppo_act_kernel(ActArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const int D = a.D;
+  const Offsets o = offsets(D);
+  const float* P = a.params;
+  for (int i = t; i < KP * 128; i += NT) {
+    const int k = i >> 7, n = i & 127, net = n >> 6, r = n & 63;
+    sm[T_W1T + k * W1S + n] = (k < D) ? tf32r(P[(net ? o.W1v : o.W1p) + r * D + k]) : 0.0f;
+  }
+  for (int i = t; i < 2 * H * H; i += NT) {
+    const int net = i >> 12, n = (i >> 6) & 63, k = i & 63;
+    sm[T_W2T + net * H * W2S + k * W2S + n] = tf32r(P[(net ? o.W2v : o.W2p) + n * H + k]);
+  }
+  for (int i = t; i < 3 * H; i += NT) sm[T_W3 + i] = (i < 2 * H) ? P[o.Wa + i] : P[o.Wv + (i - 2 * H)];
+  if (t < 128) {
+    const int net = t >> 6, r = t & 63;
+    sm[T_B1 + t] = P[(net ? o.b1v : o.b1p) + r];
+    sm[T_B2 + t] = P[(net ? o.b2v : o.b2p) + r];
+  }
+  if (t < 2) { sm[T_B3 + t] = P[o.ba + t]; sm[T_LS + t] = P[o.ls + t]; }
+  if (t == 2) sm[T_B3 + 2] = P[o.bv];
+  __syncthreads();
+  const float ls0 = sm[T_LS], ls1 = sm[T_LS + 1];
+  const float sd0 = expf(ls0), sd1 = expf(ls1);
+  const int nb0 = 16 * warp, gnet = warp >> 2;
+  const bool skip = a.value_only && gnet == 0;     // warps 0..3 own the policy net's columns
+  float* const X = &sm[T_X];
+
+  const int ntiles = (a.n + TT - 1) / TT;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int sbase = tile * TT, ns = min(TT, a.n - sbase);
+    for (int i = t; i < TT * KP; i += NT) {
+      const int s = i / KP, k = i - s * KP;
+      X[s * XS + k] = (s < ns && k < D) ? tf32r(a.obs[(size_t)(sbase + s) * D + k]) : 0.0f;
+    }
+    __syncthreads();
+    if (!skip) {
+      float c[2][2][4];
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) c[m][j][e] = 0.0f;
+#pragma unroll 2
+      for (int k0 = 0; k0 < KP; k0 += 8) {
+        uint32_t af[2][4], bf[2][2];
+        lda_rowmajor(af[0], X, XS, 0, k0, g, q);
+        lda_rowmajor(af[1], X, XS, 16, k0, g, q);
+        ldb(bf[0], &sm[T_W1T], W1S, k0, nb0, g, q);
+        ldb(bf[1], &sm[T_W1T], W1S, k0, nb0 + 8, g, q);
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) mma_tf32(c[m][j], af[m], bf[j]);
+      }
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int col = nb0 + 8 * j + 2 * q, row = 16 * m + g;
+          sm[T_H1 + row * AS + col] = tf32r(tanhf(c[m][j][0] + sm[T_B1 + col]));
+          sm[T_H1 + row * AS + col + 1] = tf32r(tanhf(c[m][j][1] + sm[T_B1 + col + 1]));
+          sm[T_H1 + (row + 8) * AS + col] = tf32r(tanhf(c[m][j][2] + sm[T_B1 + col]));
+          sm[T_H1 + (row + 8) * AS + col + 1] = tf32r(tanhf(c[m][j][3] + sm[T_B1 + col + 1]));
+        }
+    }
+    __syncthreads();
+    if (!skip) {
+      float c[2][2][4];
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) c[m][j][e] = 0.0f;
+      const float* A = &sm[T_H1 + gnet * H];
+      const float* B = &sm[T_W2T + gnet * H * W2S];
+      const int nn0 = nb0 - gnet * H;
+#pragma unroll 2
+      for (int k0 = 0; k0 < H; k0 += 8) {
+        uint32_t af[2][4], bf[2][2];
+        lda_rowmajor(af[0], A, AS, 0, k0, g, q);
+        lda_rowmajor(af[1], A, AS, 16, k0, g, q);
+        ldb(bf[0], B, W2S, k0, nn0, g, q);
+        ldb(bf[1], B, W2S, k0, nn0 + 8, g, q);
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) mma_tf32(c[m][j], af[m], bf[j]);
+      }
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int col = nb0 + 8 * j + 2 * q, row = 16 * m + g;
+          sm[T_H2 + row * AS + col] = tanhf(c[m][j][0] + sm[T_B2 + col]);
+          sm[T_H2 + row * AS + col + 1] = tanhf(c[m][j][1] + sm[T_B2 + col + 1]);
+          sm[T_H2 + (row + 8) * AS + col] = tanhf(c[m][j][2] + sm[T_B2 + col]);
+          sm[T_H2 + (row + 8) * AS + col + 1] = tanhf(c[m][j][3] + sm[T_B2 + col + 1]);
+        }
+    }
+    __syncthreads();
+    // heads: warp w owns rows 4w .. 4w+3 of the tile
+#pragma unroll 1
+    for (int si = 0; si < TT / 8; ++si) {
+      const int s = warp * (TT / 8) + si;
+      const float* h2 = &sm[T_H2 + s * AS];
+      float p0 = 0.0f, p1 = 0.0f;
+      if (!a.value_only) {
+        p0 = h2[lane] * sm[T_W3 + lane] + h2[lane + 32] * sm[T_W3 + lane + 32];
+        p1 = h2[lane] * sm[T_W3 + H + lane] + h2[lane + 32] * sm[T_W3 + H + lane + 32];
+      }
+      float pv = h2[H + lane] * sm[T_W3 + 2 * H + lane] + h2[H + lane + 32] * sm[T_W3 + 2 * H + lane + 32];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        p0 += __shfl_xor_sync(0xffffffffu, p0, off); p1 += __shfl_xor_sync(0xffffffffu, p1, off); pv += __shfl_xor_sync(0xffffffffu, pv, off);
+      }
+      if (lane == 0 && s < ns) {
+        const size_t row = (size_t)(sbase + s);
+        a.value[row] = pv + sm[T_B3 + 2];
+        if (!a.value_only) {
+          const float m0 = p0 + sm[T_B3], m1 = p1 + sm[T_B3 + 1];
+          if (a.mean) { a.mean[row * 2] = m0; a.mean[row * 2 + 1] = m1; }
+          if (a.action) {
+            uint32_t r[4];
+            philox_10(a.step, (uint32_t)row, (uint32_t)(row >> 32), 0x50504F41u, (uint32_t)a.seed, (uint32_t)(a.seed >> 32), r);
+            // Box-Muller on two uniforms in (0, 1]
+            const float u1 = ((float)(r[0] >> 8) + 1.0f) * (1.0f / 16777216.0f), u2 = (float)(r[1] >> 8) * (1.0f / 16777216.0f);
+            const float rad = sqrtf(-2.0f * logf(u1));
+            float sn, cs;
+            sincosf(6.283185307179586f * u2, &sn, &cs);
+            const float e0 = rad * cs, e1 = rad * sn;
+            a.action[row * 2] = m0 + sd0 * e0; a.action[row * 2 + 1] = m1 + sd1 * e1;
+            if (a.logp) a.logp[row] = -0.5f * e0 * e0 - ls0 - 0.9189385332046727f - 0.5f * e1 * e1 - ls1 - 0.9189385332046727f;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace
 
 static int g_use_tc = -1;
@@ -756,6 +928,26 @@ int ackb_ppo_minibatch_grad(const float* obs, const float* act, const float* old
   const int grid = ntiles < sms ? ntiles : sms;
   if (use_tc) ppo_grad_kernel_tc<<<grid, NT, smem, s>>>(a);
   else ppo_grad_kernel<<<grid, NT, smem, s>>>(a);
+  return cudaGetLastError() == cudaSuccess ? ACKB_OK : ACKB_ERR_CUDA;
+}
+
+int ackb_ppo_act(const float* obs, int n, int obs_dim, const float* params, float* mean, float* value, float* action, float* logp,
+                 uint64_t seed, uint32_t step, int value_only, void* stream) {
+  if (!obs || !params || !value || n <= 0 || obs_dim <= 0 || obs_dim > KP) return ACKB_ERR_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return ACKB_ERR_NO_DEVICE;
+  const size_t smem = (size_t)T_TOTAL * sizeof(float);
+  if (dev < 64 && !attr_done[dev]) {
+    if (cudaFuncSetAttribute(ppo_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return ACKB_ERR_CUDA;
+    attr_done[dev] = true;
+  }
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  ActArgs a{obs, n, obs_dim, params, mean, value, action, logp, (unsigned long long)seed, step, value_only};
+  const int ntiles = (n + TT - 1) / TT;
+  ppo_act_kernel<<<ntiles < sms ? ntiles : sms, NT, smem, s>>>(a);
   return cudaGetLastError() == cudaSuccess ? ACKB_OK : ACKB_ERR_CUDA;
 }
 

@@ -275,6 +275,25 @@ class FusedMinibatchStep:
         self.adv_stats = torch.zeros(2, device=device, dtype=torch.float32)
         self.mb = -1      # any minibatch size
 
+    def act(self, obs: torch.Tensor, action: torch.Tensor, logp: torch.Tensor, value: torch.Tensor, seed: int, step: int) -> None:
+        """Fused rollout forward (csrc/ackb_ppo.cu: ppo_act_kernel): fills action (unclipped sample), logp and value in place."""
+        c = self.ct
+        ptr = lambda t: c.c_void_p(t.data_ptr())
+        rc = self.L.ackb_ppo_act(ptr(obs), int(obs.shape[0]), self.obs_dim, ptr(self.flat_p), None, ptr(value), ptr(action), ptr(logp),
+                                 int(seed) & 0xFFFFFFFFFFFFFFFF, int(step) & 0xFFFFFFFF, 0,
+                                 c.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"ackb_ppo_act failed with code {rc}")
+
+    def value(self, obs: torch.Tensor, value: torch.Tensor) -> None:
+        """V(obs) only (bootstrap values of terminal observations): the policy net is skipped."""
+        c = self.ct
+        ptr = lambda t: c.c_void_p(t.data_ptr())
+        rc = self.L.ackb_ppo_act(ptr(obs), int(obs.shape[0]), self.obs_dim, ptr(self.flat_p), None, ptr(value), None, None, 0, 0, 1,
+                                 c.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"ackb_ppo_act failed with code {rc}")
+
     def shuffle_epoch(self, batch: Dict[str, torch.Tensor], perm: torch.Tensor) -> Dict[str, torch.Tensor]:
         """Permuted copy of the rollout (one gather per epoch, 0.1 ms per million samples): the minibatches of the epoch are then
         contiguous row ranges, which the kernel reads without the per-tile index gather."""
@@ -406,6 +425,11 @@ class PPOTrainer:
                         val=torch.empty((T, N), **f), rew=torch.empty((T, N), **f), done=torch.empty((T, N), **f))
         self.obs = env.reset().clone()
         self.num_timesteps = 0
+        self._noise_seed = (seed * 1000003 + self.rank) * 2654435761 + 12345
+        self._act_step = 0
+        self._tv = torch.empty(N, **f)
+        if self.learner == "fused":     # flat parameter buffers exist from the start: the rollout forward uses them too
+            self.graphed = FusedMinibatchStep(self.policy, self.opt, cfg, D, self.device)
 
     @torch.no_grad()
     def collect(self) -> float:
@@ -413,13 +437,24 @@ class PPOTrainer:
         t0 = time.perf_counter()
         for t in range(cfg.n_steps):
             obs = sanitize_obs(self.obs)
-            act, logp, val = self.policy.act(obs)
-            b["obs"][t], b["act"][t], b["logp"][t], b["val"][t] = obs, act, logp, val
+            fused = self.graphed if isinstance(self.graphed, FusedMinibatchStep) else None
+            if fused is not None:     # one launch: both MLPs, Gaussian sample, log-probability, value -> straight into the buffers
+                b["obs"][t].copy_(obs)
+                fused.act(b["obs"][t], b["act"][t], b["logp"][t], b["val"][t], self._noise_seed, self._act_step)
+                self._act_step += 1
+                act = b["act"][t]
+            else:
+                act, logp, val = self.policy.act(obs)
+                b["obs"][t], b["act"][t], b["logp"][t], b["val"][t] = obs, act, logp, val
             nobs, rew, term, trunc, info = env.step(torch.clamp(act, -1.0, 1.0))     # SB3 clips to the Box bounds
             # bootstrap with V(terminal observation) on time-limit truncation; evaluated for every environment and masked, so
             # that the rollout loop has no device->host synchronisation (rows of environments that did not finish are stale, unused)
             only_trunc = ((trunc != 0) & (term == 0)).float()
-            tv = self.policy.value(sanitize_obs(info["terminal_observation"]))
+            if fused is not None:
+                fused.value(info["terminal_observation"], self._tv)
+                tv = self._tv
+            else:
+                tv = self.policy.value(sanitize_obs(info["terminal_observation"]))
             b["rew"][t] = rew + cfg.gamma * tv * only_trunc
             b["done"][t] = ((term != 0) | (trunc != 0)).float()
             self.obs.copy_(nobs)
@@ -434,13 +469,11 @@ class PPOTrainer:
             last_val = self.policy.value(sanitize_obs(self.obs))
             adv, ret = compute_gae(b["rew"], b["val"], b["done"], last_val, cfg.gamma, cfg.gae_lambda)
         flat = dict(obs=b["obs"].flatten(0, 1), act=b["act"].flatten(0, 1), logp=b["logp"].flatten(), adv=adv.flatten(), ret=ret.flatten())
-        if self.graphed is None and self.learner == "fused":
-            self.graphed = FusedMinibatchStep(self.policy, self.opt, cfg, flat["obs"].shape[1], self.device)
-            if self.fused_graphs:
-                n = flat["obs"].shape[0]
-                mb = max(1, n // cfg.minibatches)
-                sh = self.graphed.shuffle_epoch(flat, torch.arange(n, device=self.device))
-                self.graphed.capture(sh, [(i * mb, mb) for i in range(cfg.minibatches)])
+        if self.learner == "fused" and self.fused_graphs and getattr(self.graphed, "g1", None) is None:
+            n = flat["obs"].shape[0]
+            mb = max(1, n // cfg.minibatches)
+            sh = self.graphed.shuffle_epoch(flat, torch.arange(n, device=self.device))
+            self.graphed.capture(sh, [(i * mb, mb) for i in range(cfg.minibatches)])
         if self.use_graphs and self.graphed is None:
             n = flat["obs"].shape[0]
             self.graphed = GraphedMinibatchStep(self.policy, self.opt, cfg, max(1, n // cfg.minibatches), flat["obs"].shape[1], self.device)
