@@ -125,6 +125,34 @@ template <> struct Num<double> {
 };
 
 // ------------------------------------------------------------------------------------------------
+// lookup tables that lanes of one warp index with DIFFERENT indices (occupancy-grid rows, lidar beam directions and the
+// slot -> beam map): on the device they are staged in shared memory once per CTA (`stage_tables`), because a divergent index
+// into __constant__ memory is serialised by the constant cache; the host build reads the constants block directly.
+// ------------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+__shared__ unsigned ackb_s_grid[16];
+__shared__ float ackb_s_lcos[72], ackb_s_lsin[72];
+__shared__ unsigned char ackb_s_lmap[72];
+template <typename T>
+__device__ __forceinline__ void stage_tables(const Consts<T>& C) {   // every thread of the CTA must call it (ends with a barrier)
+  for (int i = threadIdx.x; i < 72; i += blockDim.x) {
+    ackb_s_lcos[i] = (float)C.lidar_cos[i]; ackb_s_lsin[i] = (float)C.lidar_sin[i]; ackb_s_lmap[i] = (unsigned char)C.lidar_map[i];
+    if (i < 16) ackb_s_grid[i] = (unsigned)C.grid_rows[i];
+  }
+  __syncthreads();
+}
+template <typename T> __device__ __forceinline__ unsigned tbl_grid_row(const Consts<T>&, int iy) { return ackb_s_grid[iy]; }
+template <typename T> __device__ __forceinline__ int tbl_lidar_map(const Consts<T>&, int slot) { return (int)ackb_s_lmap[slot]; }
+// beam directions: fp32 tables for the fp32 kernels, the exact constants for fp64 (the index is lane-uniform enough there)
+__device__ __forceinline__ void tbl_beam(const Consts<float>&, int beam, float* c, float* s) { *c = ackb_s_lcos[beam]; *s = ackb_s_lsin[beam]; }
+__device__ __forceinline__ void tbl_beam(const Consts<double>& C, int beam, double* c, double* s) { *c = C.lidar_cos[beam]; *s = C.lidar_sin[beam]; }
+#else
+template <typename T> inline unsigned tbl_grid_row(const Consts<T>& C, int iy) { return (unsigned)C.grid_rows[iy]; }
+template <typename T> inline int tbl_lidar_map(const Consts<T>& C, int slot) { return (int)C.lidar_map[slot]; }
+template <typename T> inline void tbl_beam(const Consts<T>& C, int beam, T* c, T* s) { *c = C.lidar_cos[beam]; *s = C.lidar_sin[beam]; }
+#endif
+
+// ------------------------------------------------------------------------------------------------
 // team of LANES lanes working on one environment
 // ------------------------------------------------------------------------------------------------
 #if !defined(__CUDACC__)
@@ -826,7 +854,7 @@ struct Sim {
       if (grid) {
         const int ix = gx0 + bi / gny, iy = gy0 + bi % gny;
         if (ix < 0 || iy < 0 || ix >= (int)C.grid_nx[0] || iy >= (int)C.grid_ny[0]) continue;
-        if (!(((unsigned)C.grid_rows[iy] >> ix) & 1u)) continue;
+        if (!((tbl_grid_row(C, iy) >> ix) & 1u)) continue;
         bcx = C.grid_x0[0] + (T(ix) + T(0.5)) * C.grid_pitch[0]; bcy = C.grid_y0[0] + (T(iy) + T(0.5)) * C.grid_pitch[0];
       } else { bcx = C.box_cx[bi]; bcy = C.box_cy[bi]; }
       const T c[3] = {cw[0] - bcx, cw[1] - bcy, cw[2] - C.box_z[0]};
@@ -1623,7 +1651,8 @@ struct Sim {
 
   // ---- B9 rangefinder of observation slot `slot` (ray against the floor plane; boxes in the scene)
   ACKB_HD static T lidar_ray(const Consts<T>& C, const State& e, const Kin<T>& k, int beam) {
-    const T cb = C.lidar_cos[beam], sb = C.lidar_sin[beam];
+    T cb, sb;
+    tbl_beam(C, beam, &cb, &sb);
     const T o[3] = {C.lidar_pos[0] + C.lidar_r[0] * cb, C.lidar_pos[1] + C.lidar_r[0] * sb, C.lidar_pos[2]};
     T best = T(-1);
     // floor: local z of the ray = n . d ; height of the origin = n . o + hO
@@ -1655,16 +1684,38 @@ struct Sim {
         T tmx = mx ? ((T)(ix + (sx > 0 ? 1 : 0)) - gx) * pitch * idx : big;
         T tmy = my ? ((T)(iy + (sy > 0 ? 1 : 0)) - gy) * pitch * idy : big;
         const int budget = nx + ny + 2;
+        const bool mz = N::abs_(dw[2]) > N::minval;
+        const T idz = mz ? N::rcp_(dw[2]) : T(0);
+        int entered = -1;                                   // axis of the cell boundary crossed last (-1: the origin's own cell)
 #pragma unroll 1
         for (int step = 0; step < budget; ++step) {
-          if (((unsigned)C.grid_rows[iy] >> ix) & 1u) {
-            const T h = box_ray(C, ow[0] - (C.grid_x0[0] + (T(ix) + T(0.5)) * pitch), ow[1] - (C.grid_y0[0] + (T(iy) + T(0.5)) * pitch),
-                                ow[2] - C.box_z[0], dw);
+          if ((tbl_grid_row(C, iy) >> ix) & 1u) {
+            const T lx = ow[0] - (C.grid_x0[0] + (T(ix) + T(0.5)) * pitch), ly = ow[1] - (C.grid_y0[0] + (T(iy) + T(0.5)) * pitch);
+            const T lz = ow[2] - C.box_z[0];
+            T h;
+            if (entered < 0) h = box_ray(C, lx, ly, lz, dw);      // origin over / inside this box: the general six-face test
+            else {
+              // the box fills the cell, so from outside it can only be hit on the lateral face just crossed or on the z face
+              // turned towards the ray: the same face formulas as box_ray, evaluated for these two faces only
+              h = T(-1);
+              const bool ex = entered == 0;
+              const T side = ex ? T(-sx) : T(-sy);
+              const T sol = ex ? (side * C.box_half[0] - lx) * idx : (side * C.box_half[1] - ly) * idy;
+              const T pa = ex ? ly + sol * dw[1] : lz + sol * dw[2], pb = ex ? lz + sol * dw[2] : lx + sol * dw[0];
+              const T ha = ex ? C.box_half[1] : C.box_half[2], hb = ex ? C.box_half[2] : C.box_half[0];
+              if (sol >= T(0) && N::abs_(pa) <= ha && N::abs_(pb) <= hb) h = sol;
+              if (mz) {
+                const T sz = dw[2] > T(0) ? T(-1) : T(1);
+                const T solz = (sz * C.box_half[2] - lz) * idz;
+                const T px = lx + solz * dw[0], py = ly + solz * dw[1];
+                if (solz >= T(0) && N::abs_(px) <= C.box_half[0] && N::abs_(py) <= C.box_half[1] && (h < T(0) || solz < h)) h = solz;
+              }
+            }
             if (h >= T(0)) { if (best < T(0) || h < best) best = h; break; }
           }
           const T tn = tmx < tmy ? tmx : tmy;             // ray parameter at which the next cell is entered
           if (best >= T(0) && tn > best) break;            // the floor is hit first
-          if (tmx < tmy) { ix += sx; tmx += tdx; } else { iy += sy; tmy += tdy; }
+          if (tmx < tmy) { ix += sx; tmx += tdx; entered = 0; } else { iy += sy; tmy += tdy; entered = 1; }
           if (ix < 0 || iy < 0 || ix >= nx || iy >= ny) break;
         }
       } else {

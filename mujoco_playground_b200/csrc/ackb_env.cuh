@@ -70,7 +70,7 @@ struct EnvOps {
     const int nbeam = (int)C.nbeam[0];
     T mn = T(1e30);
     for (int slot = lane; slot < nbeam; slot += LANES) {
-      T d = S::lidar_ray(C, e, k, (int)C.lidar_map[slot]);
+      T d = S::lidar_ray(C, e, k, tbl_lidar_map(C, slot));
       sink.put(slot, (float)d);
       mn = d < mn ? d : mn;
     }

@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(Geo<T, LANES, NC>::kBlock, Geo<T, LANES, NC>::
   constexpr int EPW = 32 / LANES;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Consts<T>& C = dev_consts<T>();
+  stage_tables(C);
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int env_raw = tid / LANES, lane = tid % LANES;
   const bool valid = env_raw < st.n;
@@ -277,6 +278,7 @@ __global__ void __launch_bounds__(Geo<T, LANES, 2>::kBlock) reset_kernel(DevStat
   using G = Geo<T, LANES, 2>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const Consts<T>& C = dev_consts<T>();
+  stage_tables(C);
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int env_raw = tid / LANES, lane = tid % LANES;
   const bool valid = env_raw < st.n;

@@ -1,5 +1,3 @@
 cd $GRAFT_REPO_ROOT
-timeout 600 ncu --set full --import-source on --clock-control none -k regex:step_kernel --launch-skip 102 -c 1 -f -o gpurun_out/prof_r01j_scene_l4 python tools/gpu/time_step.py --envs 65536 --model scene --fs 4 --lanes 4 --iters 2 > gpurun_out/ncu3.log 2>&1
+timeout 600 ncu --set full --import-source on --clock-control none -k regex:step_kernel --launch-skip 402 -c 1 -f -o gpurun_out/prof_r01o_scene_l4_fs1 python tools/gpu/time_step.py --envs 65536 --model scene --fs 1 --lanes 4 --iters 2 > gpurun_out/ncu3.log 2>&1
 tail -2 gpurun_out/ncu3.log
-timeout 600 ncu --set full --import-source on --clock-control none -k regex:step_kernel --launch-skip 102 -c 1 -f -o gpurun_out/prof_r01j_scene_l1 python tools/gpu/time_step.py --envs 65536 --model scene --fs 4 --lanes 1 --iters 2 > gpurun_out/ncu4.log 2>&1
-tail -2 gpurun_out/ncu4.log
