@@ -361,7 +361,10 @@ constexpr int T_H1 = T_X + 2 * TT * XS;           // [TT][AS]
 constexpr int T_H2 = T_H1 + TT * AS;
 constexpr int T_DH = T_H2 + TT * AS;
 constexpr int T_DO = T_DH + TT * AS;              // [TT][4]
-constexpr int T_TOTAL = T_DO + TT * 4;
+constexpr int T_W3B = T_DO + TT * 4;              // [128][8]  heads as one mma B operand: col 0/1 = Wa rows (k < 64), col 2 = Wv (k >= 64)
+constexpr int T_OUT = T_W3B + 128 * 8;            // [TT][4]   head outputs (mean0, mean1, value) before the bias
+constexpr int T_SC = T_OUT + TT * 4;              // [2][TT][8] per-sample scalars (act0, act1, old_logp, adv, ret), double buffered
+constexpr int T_TOTAL = T_SC + 2 * TT * 8;
 
 __device__ __forceinline__ float tf32r(float x) {
   uint32_t u;
@@ -398,8 +401,16 @@ __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc));
 }
 // asynchronous gather of the observation rows of one tile into xbuf (zero padding written directly)
-__device__ __forceinline__ void gather_tile_async(const PpoArgs& a, int tile, float* xbuf, int t) {
+__device__ __forceinline__ void gather_tile_async(const PpoArgs& a, int tile, float* xbuf, float* scbuf, int t) {
   const int sbase = tile * TT, ns = min(TT, a.mb - sbase), D = a.D;
+  if (t < TT * 5) {   // per-sample scalars ride along with the observation rows
+    const int s = t / 5, j = t - s * 5;
+    if (s < ns) {
+      const int64_t row = a.idx ? a.idx[sbase + s] : (int64_t)(sbase + s);
+      const float* src = j < 2 ? &a.act[row * 2 + j] : (j == 2 ? &a.old_logp[row] : (j == 3 ? &a.adv[row] : &a.ret[row]));
+      cp_async4(&scbuf[s * 8 + j], src);
+    }
+  }
   for (int i = t; i < TT * KP; i += NT) {
     const int s = i / KP, k = i - s * KP;
     if (s < ns && k < D) {
@@ -431,6 +442,13 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel_tc(PpoArgs a) {
     sm[T_W2T + net * H * W2S + k * W2S + n] = w;
   }
   for (int i = t; i < 3 * H; i += NT) sm[T_W3 + i] = (i < 2 * H) ? P[o.Wa + i] : P[o.Wv + (i - 2 * H)];
+  for (int i = t; i < 128 * 8; i += NT) {
+    const int k = i >> 3, n = i & 7;
+    float w = 0.0f;
+    if (n < 2 && k < H) w = P[o.Wa + n * H + k];
+    if (n == 2 && k >= H) w = P[o.Wv + (k - H)];
+    sm[T_W3B + i] = tf32r(w);
+  }
   if (t < 128) {
     const int net = t >> 6, r = t & 63;
     sm[T_B1 + t] = P[(net ? o.b1v : o.b1p) + r];
@@ -466,7 +484,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel_tc(PpoArgs a) {
 
   const int ntiles = (a.mb + TT - 1) / TT;
   int buf = 0;
-  if ((int)blockIdx.x < ntiles) gather_tile_async(a, blockIdx.x, &sm[T_X], t);
+  if ((int)blockIdx.x < ntiles) gather_tile_async(a, blockIdx.x, &sm[T_X], &sm[T_SC], t);
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
     const int sbase = tile * TT;
     const int ns = min(TT, a.mb - sbase);
@@ -479,7 +497,8 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel_tc(PpoArgs a) {
       X[s * XS + k] = tf32r(X[s * XS + k]);
     }
     __syncthreads();
-    if (tile + (int)gridDim.x < ntiles) gather_tile_async(a, tile + gridDim.x, &sm[T_X + (buf ^ 1) * TT * XS], t);
+    if (tile + (int)gridDim.x < ntiles) gather_tile_async(a, tile + gridDim.x, &sm[T_X + (buf ^ 1) * TT * XS], &sm[T_SC + (buf ^ 1) * TT * 8], t);
+    const float* const SC = &sm[T_SC + buf * TT * 8];
     // ---- 2. layer 1: H1[s][n] = tanh(sum_k X[s][k] W1t[k][n] + b1[n])
     {
       float c[2][2][4];
@@ -549,40 +568,45 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel_tc(PpoArgs a) {
         }
     }
     __syncthreads();
-    // ---- 4. heads + PPO loss derivatives: warp w owns samples 4w .. 4w+3 (fp32 CUDA cores)
-#pragma unroll 1
-    for (int si = 0; si < TT / 8; ++si) {
-      const int s = warp * (TT / 8) + si;
-      const float* h2 = &sm[T_H2 + s * AS];
-      float p0 = h2[lane] * sm[T_W3 + lane] + h2[lane + 32] * sm[T_W3 + lane + 32];
-      float p1 = h2[lane] * sm[T_W3 + H + lane] + h2[lane + 32] * sm[T_W3 + H + lane + 32];
-      float pv = h2[H + lane] * sm[T_W3 + 2 * H + lane] + h2[H + lane + 32] * sm[T_W3 + 2 * H + lane + 32];
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        p0 += __shfl_xor_sync(0xffffffffu, p0, off); p1 += __shfl_xor_sync(0xffffffffu, p1, off); pv += __shfl_xor_sync(0xffffffffu, pv, off);
+    // ---- 4. heads as one small GEMM [32 x 128] x [128 x 8] (warps 0 and 1, one 16-row tile each), then the PPO loss
+    // derivatives with one thread per sample
+    if (warp < 2) {
+      float c[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 4
+      for (int k0 = 0; k0 < 128; k0 += 8) {
+        uint32_t af[4], bf[2];
+        lda_rowmajor(af, &sm[T_H2], AS, 16 * warp, k0, g, q);
+        ldb(bf, &sm[T_W3B], 8, k0, 0, g, q);
+        mma_tf32(c, af, bf);
       }
-      if (lane == 0) {
-        float dm0 = 0.0f, dm1 = 0.0f, dv = 0.0f;
-        if (s < ns) {
-          const int64_t row = a.idx ? a.idx[sbase + s] : (int64_t)(sbase + s);
-          const float m0 = p0 + sm[T_B3], m1 = p1 + sm[T_B3 + 1], v = pv + sm[T_B3 + 2];
-          const float e0 = a.act[row * 2] - m0, e1 = a.act[row * 2 + 1] - m1;
-          const float q0 = e0 * e0 * iv0, q1 = e1 * e1 * iv1;
-          const float logp = -0.5f * q0 - ls0 - 0.9189385332046727f - 0.5f * q1 - ls1 - 0.9189385332046727f;
-          const float A_ = (a.adv[row] - adv_mean) * adv_istd;
-          const float lr = logp - a.old_logp[row];
-          const float r = expf(lr);
-          const float rc = fminf(fmaxf(r, 1.0f - a.clip), 1.0f + a.clip);
-          const float s1 = A_ * r, s2 = A_ * rc;
-          const float dlogp = (s1 <= s2) ? -A_ * r : 0.0f;
-          dm0 = dlogp * e0 * iv0 * inv_mb; dm1 = dlogp * e1 * iv1 * inv_mb;
-          gls0 += dlogp * (q0 - 1.0f) * inv_mb; gls1 += dlogp * (q1 - 1.0f) * inv_mb;
-          const float R = a.ret[row];
-          dv = a.vf_coef * 2.0f * (v - R) * inv_mb;
-          d_pg += -fminf(s1, s2); d_vl += (v - R) * (v - R); d_kl += (r - 1.0f) - lr; d_cf += (fabsf(r - 1.0f) > a.clip) ? 1.0f : 0.0f;
-        }
-        sm[T_DO + s * 4] = dm0; sm[T_DO + s * 4 + 1] = dm1; sm[T_DO + s * 4 + 2] = dv; sm[T_DO + s * 4 + 3] = 0.0f;
+      if (q < 2) {   // columns 2q, 2q+1 of rows g and g+8
+        const int row = 16 * warp + g;
+        sm[T_OUT + row * 4 + 2 * q] = c[0]; sm[T_OUT + row * 4 + 2 * q + 1] = c[1];
+        sm[T_OUT + (row + 8) * 4 + 2 * q] = c[2]; sm[T_OUT + (row + 8) * 4 + 2 * q + 1] = c[3];
       }
+    }
+    __syncthreads();
+    if (t < TT) {
+      const int s = t;
+      float dm0 = 0.0f, dm1 = 0.0f, dv = 0.0f;
+      if (s < ns) {
+        const float m0 = sm[T_OUT + s * 4] + sm[T_B3], m1 = sm[T_OUT + s * 4 + 1] + sm[T_B3 + 1], v = sm[T_OUT + s * 4 + 2] + sm[T_B3 + 2];
+        const float e0 = SC[s * 8] - m0, e1 = SC[s * 8 + 1] - m1;
+        const float q0 = e0 * e0 * iv0, q1 = e1 * e1 * iv1;
+        const float logp = -0.5f * q0 - ls0 - 0.9189385332046727f - 0.5f * q1 - ls1 - 0.9189385332046727f;
+        const float A_ = (SC[s * 8 + 3] - adv_mean) * adv_istd;
+        const float lr = logp - SC[s * 8 + 2];
+        const float r = expf(lr);
+        const float rc = fminf(fmaxf(r, 1.0f - a.clip), 1.0f + a.clip);
+        const float s1 = A_ * r, s2 = A_ * rc;
+        const float dlogp = (s1 <= s2) ? -A_ * r : 0.0f;      // d(-min(s1, s2)) / d logp (clipped branch has zero slope)
+        dm0 = dlogp * e0 * iv0 * inv_mb; dm1 = dlogp * e1 * iv1 * inv_mb;
+        gls0 += dlogp * (q0 - 1.0f) * inv_mb; gls1 += dlogp * (q1 - 1.0f) * inv_mb;
+        const float R = SC[s * 8 + 4];
+        dv = a.vf_coef * 2.0f * (v - R) * inv_mb;
+        d_pg += -fminf(s1, s2); d_vl += (v - R) * (v - R); d_kl += (r - 1.0f) - lr; d_cf += (fabsf(r - 1.0f) > a.clip) ? 1.0f : 0.0f;
+      }
+      sm[T_DO + s * 4] = dm0; sm[T_DO + s * 4 + 1] = dm1; sm[T_DO + s * 4 + 2] = dv; sm[T_DO + s * 4 + 3] = 0.0f;
     }
     __syncthreads();
     // ---- 5. dH2 = (dOut W3) * (1 - H2^2)   (TF32-rounded: it feeds two GEMMs)
@@ -707,10 +731,18 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel_tc(PpoArgs a) {
   }
   if (t < 2) atomicAdd(&G[o.ba + t], gb3);
   if (t == 2) atomicAdd(&G[o.bv], gb3);
-  if (lane == 0) {
-    atomicAdd(&G[o.ls], gls0); atomicAdd(&G[o.ls + 1], gls1);
-    atomicAdd(&a.diag[0], d_pg * inv_mb); atomicAdd(&a.diag[1], d_vl * inv_mb);
-    atomicAdd(&a.diag[3], d_kl * inv_mb); atomicAdd(&a.diag[4], d_cf * inv_mb);
+  if (warp == 0) {   // the per-sample sums live in the 32 lanes of warp 0
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      gls0 += __shfl_xor_sync(0xffffffffu, gls0, off); gls1 += __shfl_xor_sync(0xffffffffu, gls1, off);
+      d_pg += __shfl_xor_sync(0xffffffffu, d_pg, off); d_vl += __shfl_xor_sync(0xffffffffu, d_vl, off);
+      d_kl += __shfl_xor_sync(0xffffffffu, d_kl, off); d_cf += __shfl_xor_sync(0xffffffffu, d_cf, off);
+    }
+    if (lane == 0) {
+      atomicAdd(&G[o.ls], gls0); atomicAdd(&G[o.ls + 1], gls1);
+      atomicAdd(&a.diag[0], d_pg * inv_mb); atomicAdd(&a.diag[1], d_vl * inv_mb);
+      atomicAdd(&a.diag[3], d_kl * inv_mb); atomicAdd(&a.diag[4], d_cf * inv_mb);
+    }
   }
   if (blockIdx.x == 0 && t == 0) {
     a.diag[2] = 2.0f * 1.4189385332046727f + ls0 + ls1;
