@@ -311,7 +311,9 @@ def run_cuda(args, rank, local_rank, world):
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if args.dtype == "float32" else "f64", "data": "synthetic",
             "config": {"workload": workload_name(args, world), "envs_per_gpu": n_envs, "frame_skip": fs, "lanes_per_env": args.lanes,
-                       "l2": "flushed between timed iterations (256 MiB memset, untimed)", "physics_substeps_per_s": value * fs},
+                       "l2": "flushed between timed iterations (256 MiB memset, untimed)", "physics_substeps_per_s": value * fs,
+                       "scaling_note": ("N=1 runs configs[1] (4096 envs); N>1 runs configs[3] (131072 envs per GPU, weak scaling). The "
+                                        "single-GPU figure at the configs[3] batch is this line's aux.value at N=1") if not args.envs and not scene else None},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
                          "peak_source": how, "kernel": "step_kernel", "algorithmic_bytes_per_env_step": algo, "algorithmic_bytes_per_launch": algo * n_envs,
                          "note": "compute/latency bound kernel: see DESIGN.md (HBM fraction is small by construction)", "issue": issue},
