@@ -360,6 +360,62 @@ def run_cuda(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def run_ppo(args, rank, local_rank, world):
+    """configs[4]: the PPO training loop (rollout on the batched env + fused learner + NCCL gradient all-reduce).
+    A "step" is one PPO iteration = n_steps env steps of every environment followed by the update."""
+    import torch
+    import torch.distributed as dist
+    from mujoco_playground_b200 import BatchedAckermannEnv
+    from mujoco_playground_b200.ppo import PPOConfig, PPOTrainer
+    from mujoco_playground_b200.shard import rank_seed
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n_envs = args.envs or 65536
+    env = BatchedAckermannEnv(n_envs, device=dev, frame_skip=1, seed=rank_seed(1234, rank))
+    cfg = PPOConfig(n_steps=16)
+    tr = PPOTrainer(env, cfg, seed=0)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        tr.collect(); tr.update()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    steps = min(args.steps, 50)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    roll = upd = 0.0
+    e0.record()
+    for _ in range(steps):
+        roll += tr.collect()
+        upd += tr.update()["update_s"]
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    total_ms = float(ms.item())
+    clocks = sampler.summary() if sampler else None
+    if rank == 0:
+        per_iter = cfg.n_steps * n_envs * world
+        print(json.dumps({
+            "metric": "env-steps/sec", "value": per_iter * steps / (total_ms * 1e-3), "unit": "env-steps/s", "n_gpus": world, "steps": steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 simulator, TF32 tensor-core learner (fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": f"configs[4]: PPO training loop, {n_envs} envs per GPU x {world} GPU, n_steps=16, 10 epochs x 4 minibatches, "
+                                   "frame_skip=1, NCCL gradient all-reduce", "envs_per_gpu": n_envs},
+            "split": {"rollout_ms_per_iteration": 1e3 * roll / steps, "update_ms_per_iteration": 1e3 * upd / steps,
+                      "rollout_env_steps_per_s": per_iter * steps / roll},
+            "clocks": clocks}), flush=True)
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -373,7 +429,8 @@ def main():
     ap.add_argument("--no-aux", action="store_true", help="skip the extra large-batch measurement at N=1")
     ap.add_argument("--cpu-steps", type=int, default=800000, help="physics substeps per CPU process for the CPU arm sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="flat", choices=["flat", "scene"], help="flat = configs[1]/[3] (default), scene = configs[2]")
+    ap.add_argument("--workload", default="flat", choices=["flat", "scene", "ppo"],
+                    help="flat = configs[1]/[3] (default), scene = configs[2], ppo = configs[4] (training loop)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
     rank = int(os.environ.get("RANK", 0))
@@ -381,6 +438,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.workload == "ppo":
+        run_ppo(args, rank, local_rank, world)
     else:
         run_cuda(args, rank, local_rank, world)
 

@@ -117,8 +117,11 @@ struct Geo {
 #ifndef ACKB_L1_MINB
 #define ACKB_L1_MINB (warps_per_sm(pick_block()) * 32 / pick_block())
 #endif
-  static constexpr int kBlock = kSmemWheels ? pick_block() : 128;
-  static constexpr int kMinBlocks = kSmemWheels ? ACKB_L1_MINB : 2;
+#ifndef ACKB_L4_BLOCK
+#define ACKB_L4_BLOCK 128
+#endif
+  static constexpr int kBlock = kSmemWheels ? pick_block() : ACKB_L4_BLOCK;
+  static constexpr int kMinBlocks = kSmemWheels ? ACKB_L1_MINB : (256 / ACKB_L4_BLOCK);
   static size_t smem_bytes(int obs_dim) {
     const size_t tile = (size_t)(kBlock / LANES) * obs_dim * sizeof(float);
     const size_t wheels = kSmemWheels ? (size_t)kBlock * kStride * sizeof(T) : 0;
