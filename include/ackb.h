@@ -53,13 +53,14 @@ int ackb_consts_len(void);
 /* Replaces model loading in SimpleMapSpawner.load_random_environment
  * (src/rl/envs/simple_map_spawner.py:37-38: MjModel.from_xml_path + MjData) and the env constructor
  * (src/rl/envs/ackermann_env.py:51-124).  `consts` is the host blob produced by the model compiler.
- * lanes_per_env: 4 (one lane per wheel, default when 0), 2 or 1. */
+ * lanes_per_env: 0 = automatic (1 lane per environment for flat-floor batches of >= 32768 environments, else 4 = one lane per
+ * wheel), or 1, 4, 8 (8: one lane per floor contact, flat-floor model only). */
 int ackb_create(const double* consts, size_t consts_len, int num_envs, int device, int dtype, uint64_t seed,
                 int lanes_per_env, ackb_handle** out);
 int ackb_destroy(ackb_handle* h);
 
 int ackb_num_envs(const ackb_handle* h);
-int ackb_obs_dim(const ackb_handle* h);   /* 79 for ackermann_robot_v2 (ackermann_env.py:95-100), 43 for the scene */
+int ackb_obs_dim(const ackb_handle* h);   /* 79 for ackermann_robot_v2 and the maze models (ackermann_env.py:95-100), 43 for the scene */
 int ackb_dtype(const ackb_handle* h);
 
 /* Replaces AckermannRobotEnv.reset (src/rl/envs/ackermann_env.py:143-185) for every environment, or for
@@ -81,9 +82,9 @@ int ackb_reset(ackb_handle* h, const uint8_t* dev_mask_or_null, float* dev_obs, 
 int ackb_step(ackb_handle* h, const float* dev_action, int frame_skip, int auto_reset, float* dev_obs, float* dev_reward,
               uint8_t* dev_terminated, uint8_t* dev_truncated, float* dev_terminal_obs, int32_t* dev_ncon, void* stream);
 
-/* Same call with HOST buffers (pinned memory recommended): copies the actions to the device, steps, and copies
- * observation / reward / flags back, synchronising before it returns.  This is the end-to-end path a host-side
- * caller such as src/rl/train.py:199-205 sees. */
+/* Same call with HOST buffers, synchronising before it returns: the end-to-end path a host-side caller such as
+ * src/rl/train.py:199-205 sees.  Pinned buffers (cudaHostAlloc / cudaHostRegister) are read and written by the kernel directly
+ * (mapped host memory, no staging copies); pageable buffers go through cudaMemcpyAsync staging. */
 int ackb_step_host(ackb_handle* h, const float* host_action, int frame_skip, int auto_reset, float* host_obs, float* host_reward,
                    uint8_t* host_terminated, uint8_t* host_truncated);
 
