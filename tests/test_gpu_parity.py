@@ -214,7 +214,7 @@ def _scene_states(S, n, rng):
     return qpos, qvel
 
 
-@pytest.mark.parametrize("dtype,tol,lanes", [("float64", 1e-5, 4), ("float64", 1e-5, 1), ("float32", 1e-3, 4)])
+@pytest.mark.parametrize("dtype,tol,lanes", [("float64", 1e-5, 4), ("float64", 1e-5, 1), ("float32", 1e-3, 4), ("float32", 1e-3, 1)])
 def test_scene_single_step_matches_oracle(dtype, tol, lanes):
     from mujoco_playground_b200 import BatchedAckermannEnv
     from mujoco_playground_b200.models import load_model
