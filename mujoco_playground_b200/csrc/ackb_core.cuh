@@ -746,6 +746,28 @@ struct Sim {
     Tm::sum_n(v);
   }
 
+  // Team sum of the 45 assembly partials (36 packed Hessian entries, 8 reduced right-hand sides, 1 scalar).  With one lane per
+  // wheel (4-lane layout, tail mode) the steer rows are produced by a single lane each -- row / rhs 6 by the front-left wheel's
+  // lane (2), row / rhs 7 by the front-right one (3) -- so those 16 entries are broadcast instead of butterfly-summed
+  // (bit-identical: the other lanes hold exact zeros).
+  ACKB_D static void team_sum_part(T (&part)[45], bool TL) {
+#if defined(__CUDA_ARCH__)
+    if (TL || LANES == 4) {
+      const int base = (int)(threadIdx.x & 28u);     // first lane of this lane's team of 4
+#pragma unroll
+      for (int i = 0; i < 45; ++i) {
+        const bool row6 = (i >= tri(6, 0) && i <= tri(6, 6)) || i == 36 + 6;
+        const bool row7 = (i >= tri(7, 0) && i <= tri(7, 7)) || i == 36 + 7;
+        if (row6) part[i] = __shfl_sync(0xffffffffu, part[i], base + 2);
+        else if (row7) part[i] = __shfl_sync(0xffffffffu, part[i], base + 3);
+        else { part[i] += __shfl_xor_sync(0xffffffffu, part[i], 1); part[i] += __shfl_xor_sync(0xffffffffu, part[i], 2); }
+      }
+      return;
+    }
+#endif
+    team_sum_n(part, TL);
+  }
+
   // ---- B1 kinematics: normalise the quaternion (written back, like mj_kinematics), rotation, floor frame
   ACKB_HD static void kinematics(State& e, Kin<T>& k) {
     T qn = N::sqrt_(e.q[0] * e.q[0] + e.q[1] * e.q[1] + e.q[2] * e.q[2] + e.q[3] * e.q[3]);
@@ -1256,7 +1278,7 @@ struct Sim {
         }
         part[44] += gs_sp * gs_sp * ci;
       }
-      team_sum_n(part, TL);
+      team_sum_part(part, TL);
       T S[36];
       shared_mass(C, sv, S);
 #pragma unroll
