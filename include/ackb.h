@@ -84,7 +84,9 @@ int ackb_step(ackb_handle* h, const float* dev_action, int frame_skip, int auto_
 
 /* Same call with HOST buffers, synchronising before it returns: the end-to-end path a host-side caller such as
  * src/rl/train.py:199-205 sees.  Pinned buffers (cudaHostAlloc / cudaHostRegister) are read and written by the kernel directly
- * (mapped host memory, no staging copies); pageable buffers go through cudaMemcpyAsync staging. */
+ * (mapped host memory, no staging copies); pageable buffers go through cudaMemcpyAsync staging.
+ * Stream order: the call runs on a stream of the handle and returns after it completed; it waits for the ackb_step / ackb_reset
+ * work the caller issued last on another stream.  Calls on two different caller streams are the caller's to order. */
 int ackb_step_host(ackb_handle* h, const float* host_action, int frame_skip, int auto_reset, float* host_obs, float* host_reward,
                    uint8_t* host_terminated, uint8_t* host_truncated);
 

@@ -350,6 +350,11 @@ struct ackb_handle {
   uint8_t *d_term = nullptr, *d_trunc = nullptr;
   uint8_t* d_done = nullptr;    // per-env done mask of the deferred reset (models with settle steps)
   cudaStream_t own_stream = nullptr;
+  // cross-stream ordering: ackb_step_host runs on own_stream, so it has to wait for work the caller issued through
+  // ackb_step / ackb_reset on another stream (last_stream) before it touches the state arrays
+  cudaStream_t last_stream = nullptr;
+  bool last_is_foreign = false;
+  cudaEvent_t order_ev = nullptr;
   std::string err;
 };
 
@@ -425,6 +430,7 @@ int launch_one(ackb_handle* h, DevState<T>& st, const StepArgs& a, cudaStream_t 
 
 template <typename T>
 int launch_step(ackb_handle* h, DevState<T>& st, const StepArgs& a, cudaStream_t stream, bool is_reset) {
+  h->last_stream = stream; h->last_is_foreign = stream != h->own_stream;
   const bool scene = h->consts_host[0] != 0.0;   // model_kind: the obstacle scene needs the two box-contact slots per wheel
 #ifdef ACKB_TUNE_MIN   // tuning builds (tools/gpu/build_variant.sh): fp32 flat-floor kernels only, to keep compile times short
   if constexpr (sizeof(T) == 8) return fail(h, ACKB_ERR_ARG, "tuning build: fp32 only");
@@ -483,6 +489,7 @@ int ackb_create(const double* consts, size_t consts_len, int num_envs, int devic
   CK(cudaMalloc(&h->d_done, n));
   CK(cudaMemset(h->d_done, 0, n));
   CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming));
   *out = h;
   return ACKB_OK;
 }
@@ -493,6 +500,7 @@ int ackb_destroy(ackb_handle* h) {
   if (g_const_owner[h->device] == h) g_const_owner[h->device] = nullptr;
   cudaFree(h->state); cudaFree(h->stats); cudaFree(h->d_action); cudaFree(h->d_obs); cudaFree(h->d_reward);
   cudaFree(h->d_term); cudaFree(h->d_trunc); cudaFree(h->d_done);
+  if (h->order_ev) cudaEventDestroy(h->order_ev);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete[] h->consts_host;
   delete h;
@@ -554,6 +562,10 @@ int ackb_step_host(ackb_handle* h, const float* host_action, int frame_skip, int
   CK(cudaSetDevice(h->device));
   const size_t n = h->n;
   cudaStream_t s = h->own_stream;
+  if (h->last_is_foreign) {   // order after the caller's earlier ackb_step / ackb_reset on its own stream
+    if (cudaEventRecord(h->order_ev, h->last_stream) == cudaSuccess) CK(cudaStreamWaitEvent(s, h->order_ev, 0));
+    else { cudaGetLastError(); CK(cudaDeviceSynchronize()); }   // that stream no longer exists
+  }
   // pinned caller buffers: zero-copy (the kernel's coalesced observation stores go straight to host memory)
   float* z_act = (float*)device_alias(host_action);
   float* z_obs = (float*)device_alias(host_obs);
@@ -594,6 +606,7 @@ namespace {
 template <typename T>
 int xfer(ackb_handle* h, T* dev, double* host, int rows, bool to_host) {
   const size_t n = h->n;
+  CK(cudaDeviceSynchronize());   // the caller's streams may be non-blocking ones that a plain cudaMemcpy does not wait for
   T* tmp = new T[rows * n];
   if (to_host) {
     CK(cudaMemcpy(tmp, dev, rows * n * sizeof(T), cudaMemcpyDeviceToHost));
@@ -619,6 +632,7 @@ int episode_io(ackb_handle* h, DevState<T>& s, double* goal, double* ref, int32_
   if (goal && (rc = xfer(h, s.goal, goal, 2, to_host))) return rc;
   if (ref && (rc = xfer(h, s.ref, ref, 2, to_host))) return rc;
   if (sc) {
+    CK(cudaDeviceSynchronize());
     if (to_host) CK(cudaMemcpy(sc, s.step_count, h->n * sizeof(int32_t), cudaMemcpyDeviceToHost));
     else CK(cudaMemcpy(s.step_count, sc, h->n * sizeof(int32_t), cudaMemcpyHostToDevice));
   }
