@@ -43,6 +43,12 @@ int ackb_ppo_minibatch_grad(const float* obs, const float* act, const float* old
 int ackb_ppo_act(const float* obs, int n, int obs_dim, const float* params, float* mean, float* value, float* action, float* logp,
                  uint64_t seed, uint32_t step, int value_only, void* stream);
 
+/* Generalised advantage estimation over a rollout (SB3 RolloutBuffer.compute_returns_and_advantage, called from
+ * collect_rollouts): rew / val / done / adv / ret are [n_steps][n] device arrays, done[t] = 1 if the episode ended after step t,
+ * last_val[n] = V(observation after the last step).  ret = adv + val.  Asynchronous on `stream`. */
+int ackb_ppo_gae(const float* rew, const float* val, const float* done, const float* last_val, int n_steps, int n, float gamma,
+                 float gae_lambda, float* adv, float* ret, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

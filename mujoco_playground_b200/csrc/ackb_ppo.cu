@@ -364,12 +364,21 @@ constexpr int T_DO = T_DH + TT * AS;              // [TT][4]
 constexpr int T_W3B = T_DO + TT * 4;              // [128][8]  heads as one mma B operand: col 0/1 = Wa rows (k < 64), col 2 = Wv (k >= 64)
 constexpr int T_OUT = T_W3B + 128 * 8;            // [TT][4]   head outputs (mean0, mean1, value) before the bias
 constexpr int T_SC = T_OUT + TT * 4;              // [2][TT][8] per-sample scalars (act0, act1, old_logp, adv, ret), double buffered
-constexpr int T_TOTAL = T_SC + 2 * TT * 8;
+constexpr int T_IDX = T_SC + 2 * TT * 8;         // [2][TT] int64 row numbers of a tile (two floats each), double buffered
+constexpr int T_TOTAL = T_IDX + 2 * TT * 2;
+static_assert(T_IDX % 2 == 0, "row numbers are 8-byte aligned");
 
 __device__ __forceinline__ float tf32r(float x) {
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);
+}
+// MUFU.TANH: one instruction, relative error about 2^-11 -- the precision the TF32 operands of the next GEMM keep anyway (the
+// branchy libm tanhf was a quarter of the instructions of the tensor-core kernels: both of its paths run in every warp)
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -400,13 +409,23 @@ __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc));
 }
-// asynchronous gather of the observation rows of one tile into xbuf (zero padding written directly)
-__device__ __forceinline__ void gather_tile_async(const PpoArgs& a, int tile, float* xbuf, float* scbuf, int t) {
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gsrc));
+}
+// row numbers of a tile -> shared memory, asynchronously (joins the cp.async group that is committed next): the gather of a
+// tile then takes its rows from shared memory instead of stalling every thread on a dependent global load
+__device__ __forceinline__ void stage_rows_async(const PpoArgs& a, int tile, long long* rows, int t) {
+  if (t < TT && a.idx && tile * TT + t < a.mb) cp_async8(&rows[t], &a.idx[tile * TT + t]);
+}
+// asynchronous gather of the observation rows of one tile into xbuf (padding written directly); rows = the tile's row numbers
+// in shared memory (index mode) or null (contiguous rows)
+__device__ __forceinline__ void gather_tile_async(const PpoArgs& a, int tile, float* xbuf, float* scbuf, const long long* rows, int t) {
   const int sbase = tile * TT, ns = min(TT, a.mb - sbase), D = a.D;
   if (t < TT * 5) {   // per-sample scalars ride along with the observation rows
     const int s = t / 5, j = t - s * 5;
     if (s < ns) {
-      const int64_t row = a.idx ? a.idx[sbase + s] : (int64_t)(sbase + s);
+      const int64_t row = rows ? (int64_t)rows[s] : (int64_t)(sbase + s);
       const float* src = j < 2 ? &a.act[row * 2 + j] : (j == 2 ? &a.old_logp[row] : (j == 3 ? &a.adv[row] : &a.ret[row]));
       cp_async4(&scbuf[s * 8 + j], src);
     }
@@ -414,10 +433,11 @@ __device__ __forceinline__ void gather_tile_async(const PpoArgs& a, int tile, fl
   for (int i = t; i < TT * KP; i += NT) {
     const int s = i / KP, k = i - s * KP;
     if (s < ns && k < D) {
-      const int64_t row = a.idx ? a.idx[sbase + s] : (int64_t)(sbase + s);
+      const int64_t row = rows ? (int64_t)rows[s] : (int64_t)(sbase + s);
       cp_async4(&xbuf[s * XS + k], &a.obs[row * D + k]);
     } else {
-      xbuf[s * XS + k] = 0.0f;
+      // padding; with D < KP the last column is 1 for real samples, so that dW1 = dH1^T X also yields db1 (column KP - 1)
+      xbuf[s * XS + k] = (k == KP - 1 && D < KP && s < ns) ? 1.0f : 0.0f;
     }
   }
   asm volatile("cp.async.commit_group;");
@@ -475,8 +495,19 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel_tc(PpoArgs a) {
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc2[i][j] = 0.0f;
-  float g3 = 0.0f, gb1 = 0.0f, gb2 = 0.0f, gb3 = 0.0f, gls0 = 0.0f, gls1 = 0.0f;
+  //   db2: one more column tile of the dW2 product, against a ones vector (column 0 of accb2)
+  //   db1: column KP - 1 of dW1 (the gather writes a ones column into X when D < KP)
+  //   head weights dW3[r][n] = sum_s dOut[s][r] H2[s][n]: rows r < 3 of a 16-row tile, warp w owns column tiles 2 w, 2 w + 1
+  float accb2[4] = {0.0f, 0.0f, 0.0f, 0.0f}, acc3[2][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc3[i][j] = 0.0f;
+  float gb1 = 0.0f, gb3 = 0.0f, gls0 = 0.0f, gls1 = 0.0f;
   float d_pg = 0.0f, d_vl = 0.0f, d_kl = 0.0f, d_cf = 0.0f;
+  const bool b1_by_mma = D < KP;               // the ones column of X exists
+  uint32_t ones_b[2];                          // B fragment of an [8 x 8] matrix whose column 0 is all ones
+  ones_b[0] = ones_b[1] = (g == 0) ? __float_as_uint(1.0f) : 0u;
 
   const int nb0 = 16 * warp;                 // output columns of this warp in the activation GEMMs
   const int gnet = warp >> 2;                // net of those columns
@@ -484,7 +515,13 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel_tc(PpoArgs a) {
 
   const int ntiles = (a.mb + TT - 1) / TT;
   int buf = 0;
-  if ((int)blockIdx.x < ntiles) gather_tile_async(a, blockIdx.x, &sm[T_X], &sm[T_SC], t);
+  long long* const rows_sm = a.idx ? reinterpret_cast<long long*>(&sm[T_IDX]) : nullptr;   // [2][TT]
+  if (rows_sm) {   // row numbers of this CTA's first two tiles (later ones are staged one tile ahead of their gather)
+    if (t < TT && blockIdx.x * TT + t < a.mb) rows_sm[t] = a.idx[blockIdx.x * TT + t];
+    if (t < TT && (blockIdx.x + gridDim.x) * TT + t < a.mb) rows_sm[TT + t] = a.idx[(blockIdx.x + gridDim.x) * TT + t];
+    __syncthreads();
+  }
+  if ((int)blockIdx.x < ntiles) gather_tile_async(a, blockIdx.x, &sm[T_X], &sm[T_SC], rows_sm, t);
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
     const int sbase = tile * TT;
     const int ns = min(TT, a.mb - sbase);
@@ -497,7 +534,12 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel_tc(PpoArgs a) {
       X[s * XS + k] = tf32r(X[s * XS + k]);
     }
     __syncthreads();
-    if (tile + (int)gridDim.x < ntiles) gather_tile_async(a, tile + gridDim.x, &sm[T_X + (buf ^ 1) * TT * XS], &sm[T_SC + (buf ^ 1) * TT * 8], t);
+    if (tile + (int)gridDim.x < ntiles) {
+      // this tile's row numbers are no longer needed (its gather has completed): their slot takes those of the tile after next
+      if (rows_sm && tile + 2 * (int)gridDim.x < ntiles) stage_rows_async(a, tile + 2 * gridDim.x, rows_sm + buf * TT, t);
+      gather_tile_async(a, tile + gridDim.x, &sm[T_X + (buf ^ 1) * TT * XS], &sm[T_SC + (buf ^ 1) * TT * 8],
+                        rows_sm ? rows_sm + (buf ^ 1) * TT : nullptr, t);
+    }
     const float* const SC = &sm[T_SC + buf * TT * 8];
     // ---- 2. layer 1: H1[s][n] = tanh(sum_k X[s][k] W1t[k][n] + b1[n])
     {
@@ -525,10 +567,10 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel_tc(PpoArgs a) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int col = nb0 + 8 * j + 2 * q, row = 16 * m + g;
-          sm[T_H1 + row * AS + col] = tf32r(tanhf(c[m][j][0] + sm[T_B1 + col]));
-          sm[T_H1 + row * AS + col + 1] = tf32r(tanhf(c[m][j][1] + sm[T_B1 + col + 1]));
-          sm[T_H1 + (row + 8) * AS + col] = tf32r(tanhf(c[m][j][2] + sm[T_B1 + col]));
-          sm[T_H1 + (row + 8) * AS + col + 1] = tf32r(tanhf(c[m][j][3] + sm[T_B1 + col + 1]));
+          sm[T_H1 + row * AS + col] = tf32r(tanh_fast(c[m][j][0] + sm[T_B1 + col]));
+          sm[T_H1 + row * AS + col + 1] = tf32r(tanh_fast(c[m][j][1] + sm[T_B1 + col + 1]));
+          sm[T_H1 + (row + 8) * AS + col] = tf32r(tanh_fast(c[m][j][2] + sm[T_B1 + col]));
+          sm[T_H1 + (row + 8) * AS + col + 1] = tf32r(tanh_fast(c[m][j][3] + sm[T_B1 + col + 1]));
         }
     }
     __syncthreads();
@@ -561,10 +603,10 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel_tc(PpoArgs a) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int col = nb0 + 8 * j + 2 * q, row = 16 * m + g;
-          sm[T_H2 + row * AS + col] = tf32r(tanhf(c[m][j][0] + sm[T_B2 + col]));
-          sm[T_H2 + row * AS + col + 1] = tf32r(tanhf(c[m][j][1] + sm[T_B2 + col + 1]));
-          sm[T_H2 + (row + 8) * AS + col] = tf32r(tanhf(c[m][j][2] + sm[T_B2 + col]));
-          sm[T_H2 + (row + 8) * AS + col + 1] = tf32r(tanhf(c[m][j][3] + sm[T_B2 + col + 1]));
+          sm[T_H2 + row * AS + col] = tf32r(tanh_fast(c[m][j][0] + sm[T_B2 + col]));
+          sm[T_H2 + row * AS + col + 1] = tf32r(tanh_fast(c[m][j][1] + sm[T_B2 + col + 1]));
+          sm[T_H2 + (row + 8) * AS + col] = tf32r(tanh_fast(c[m][j][2] + sm[T_B2 + col]));
+          sm[T_H2 + (row + 8) * AS + col + 1] = tf32r(tanh_fast(c[m][j][3] + sm[T_B2 + col + 1]));
         }
     }
     __syncthreads();
@@ -618,17 +660,24 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel_tc(PpoArgs a) {
       sm[T_DH + s * AS + n] = tf32r(gg * (1.0f - h * h));
     }
     __syncthreads();
-    // ---- 6. head / bias gradients (CUDA cores), dW2 += dH2^T H1 (tensor cores)
-    if (t < 3 * H) {
-      const int r = t >> 6, c = t & 63, hoff = (r < 2 ? 0 : H) + c;
-#pragma unroll 4
-      for (int s = 0; s < TT; ++s) g3 = fmaf(sm[T_DO + s * 4 + r], sm[T_H2 + s * AS + hoff], g3);
-    }
+    // ---- 6. head weights dW3 += dOut^T H2, dW2 += dH2^T H1 and db2 += dH2^T 1 (tensor cores)
     if (t < 3)
       for (int s = 0; s < TT; ++s) gb3 += sm[T_DO + s * 4 + t];
-    if (t < 128)
-      for (int s = 0; s < TT; ++s) gb2 += sm[T_DH + s * AS + t];
     {
+      const float* B3 = &sm[T_H2];                  // H2[s][n] -> B[k = s][n]
+#pragma unroll
+      for (int s0 = 0; s0 < TT; s0 += 8) {
+        uint32_t af[4];                             // A = dOut^T: element (r, s) = dOut[s][r]; rows r >= 4 are zero
+        af[0] = (g < 4) ? __float_as_uint(tf32r(sm[T_DO + (s0 + q) * 4 + g])) : 0u;
+        af[2] = (g < 4) ? __float_as_uint(tf32r(sm[T_DO + (s0 + q + 4) * 4 + g])) : 0u;
+        af[1] = af[3] = 0u;
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          uint32_t bf[2];
+          ldb(bf, B3, AS, s0, 8 * (2 * warp + jj), g, q);
+          mma_tf32(acc3[jj], af, bf);
+        }
+      }
       const float* At = &sm[T_DH + w2net * H];      // dH2[s][net*64 + n]  -> A = transpose, element (n, s)
       const float* B = &sm[T_H1 + w2net * H];       // H1[s][net*64 + k]   -> B[k = s][n = k]
 #pragma unroll
@@ -641,6 +690,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel_tc(PpoArgs a) {
           ldb(bf, B, AS, s0, 8 * j, g, q);
           mma_tf32(acc2[j], af, bf);
         }
+        mma_tf32(accb2, af, ones_b);
       }
     }
     // ---- 7. dH1 = (dH2 W2) * (1 - H1^2)
@@ -683,7 +733,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel_tc(PpoArgs a) {
     }
     __syncthreads();
     // ---- 8. db1, dW1 += dH1^T X
-    if (t < 128)
+    if (!b1_by_mma && t < 128)
       for (int s = 0; s < TT; ++s) gb1 += sm[T_DH + s * AS + t];
     {
       const float* At = &sm[T_DH];                  // dH1[s][n] -> element (n, s)
@@ -712,6 +762,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel_tc(PpoArgs a) {
       const int n = 16 * warp + g + ((e & 2) ? 8 : 0), k = 8 * j + 2 * q + (e & 1);
       const int net = n >> 6, r = n & 63;
       if (k < D) atomicAdd(&G[(net ? o.W1v : o.W1p) + r * D + k], acc1[j][e]);
+      else if (b1_by_mma && k == KP - 1) atomicAdd(&G[(net ? o.b1v : o.b1p) + r], acc1[j][e]);
     }
 #pragma unroll
   for (int j = 0; j < 8; ++j)
@@ -720,14 +771,23 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel_tc(PpoArgs a) {
       const int n = w2row0 + g + ((e & 2) ? 8 : 0), k = 8 * j + 2 * q + (e & 1);
       atomicAdd(&G[(w2net ? o.W2v : o.W2p) + n * H + k], acc2[j][e]);
     }
-  if (t < 3 * H) {
-    const int r = t >> 6, c = t & 63;
-    atomicAdd(&G[r < 2 ? o.Wa + r * H + c : o.Wv + c], g3);
+  if (q == 0) {   // db2: column 0 of the ones-vector tile, rows g and g + 8
+    atomicAdd(&G[(w2net ? o.b2v : o.b2p) + w2row0 + g], accb2[0]);
+    atomicAdd(&G[(w2net ? o.b2v : o.b2p) + w2row0 + g + 8], accb2[2]);
   }
-  if (t < 128) {
+  if (g < 3) {    // head weights: row r = g of the two column tiles of this warp (policy heads read H2[:, :64], the value head H2[:, 64:])
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int n = 8 * (2 * warp + jj) + 2 * q + e;
+        if (g < 2 && n < H) atomicAdd(&G[o.Wa + g * H + n], acc3[jj][e]);
+        if (g == 2 && n >= H) atomicAdd(&G[o.Wv + (n - H)], acc3[jj][e]);
+      }
+  }
+  if (!b1_by_mma && t < 128) {
     const int net = t >> 6, r = t & 63;
     atomicAdd(&G[(net ? o.b1v : o.b1p) + r], gb1);
-    atomicAdd(&G[(net ? o.b2v : o.b2p) + r], gb2);
   }
   if (t < 2) atomicAdd(&G[o.ba + t], gb3);
   if (t == 2) atomicAdd(&G[o.bv], gb3);
@@ -840,10 +900,10 @@ __global__ void __launch_bounds__(NT, 1) ppo_act_kernel(ActArgs a) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int col = nb0 + 8 * j + 2 * q, row = 16 * m + g;
-          sm[T_H1 + row * AS + col] = tf32r(tanhf(c[m][j][0] + sm[T_B1 + col]));
-          sm[T_H1 + row * AS + col + 1] = tf32r(tanhf(c[m][j][1] + sm[T_B1 + col + 1]));
-          sm[T_H1 + (row + 8) * AS + col] = tf32r(tanhf(c[m][j][2] + sm[T_B1 + col]));
-          sm[T_H1 + (row + 8) * AS + col + 1] = tf32r(tanhf(c[m][j][3] + sm[T_B1 + col + 1]));
+          sm[T_H1 + row * AS + col] = tf32r(tanh_fast(c[m][j][0] + sm[T_B1 + col]));
+          sm[T_H1 + row * AS + col + 1] = tf32r(tanh_fast(c[m][j][1] + sm[T_B1 + col + 1]));
+          sm[T_H1 + (row + 8) * AS + col] = tf32r(tanh_fast(c[m][j][2] + sm[T_B1 + col]));
+          sm[T_H1 + (row + 8) * AS + col + 1] = tf32r(tanh_fast(c[m][j][3] + sm[T_B1 + col + 1]));
         }
     }
     __syncthreads();
@@ -875,10 +935,10 @@ __global__ void __launch_bounds__(NT, 1) ppo_act_kernel(ActArgs a) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
           const int col = nb0 + 8 * j + 2 * q, row = 16 * m + g;
-          sm[T_H2 + row * AS + col] = tanhf(c[m][j][0] + sm[T_B2 + col]);
-          sm[T_H2 + row * AS + col + 1] = tanhf(c[m][j][1] + sm[T_B2 + col + 1]);
-          sm[T_H2 + (row + 8) * AS + col] = tanhf(c[m][j][2] + sm[T_B2 + col]);
-          sm[T_H2 + (row + 8) * AS + col + 1] = tanhf(c[m][j][3] + sm[T_B2 + col + 1]);
+          sm[T_H2 + row * AS + col] = tanh_fast(c[m][j][0] + sm[T_B2 + col]);
+          sm[T_H2 + row * AS + col + 1] = tanh_fast(c[m][j][1] + sm[T_B2 + col + 1]);
+          sm[T_H2 + (row + 8) * AS + col] = tanh_fast(c[m][j][2] + sm[T_B2 + col]);
+          sm[T_H2 + (row + 8) * AS + col + 1] = tanh_fast(c[m][j][3] + sm[T_B2 + col + 1]);
         }
     }
     __syncthreads();
@@ -922,6 +982,25 @@ __global__ void __launch_bounds__(NT, 1) ppo_act_kernel(ActArgs a) {
   }
 }
 
+// generalised advantage estimate, one thread per environment walking its T rollout steps backwards (arrays are [T][n], so the
+// loads of a warp are coalesced): delta_t = r_t + gamma V_{t+1} (1 - done_t) - V_t,  A_t = delta_t + gamma lam (1 - done_t) A_{t+1}
+__global__ void gae_kernel(const float* __restrict__ rew, const float* __restrict__ val, const float* __restrict__ done,
+                           const float* __restrict__ last_val, int T, int n, float gamma, float lam, float* __restrict__ adv,
+                           float* __restrict__ ret) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  float next = last_val[e], last = 0.0f;
+  for (int t = T - 1; t >= 0; --t) {
+    const size_t i = (size_t)t * n + e;
+    const float nt = 1.0f - done[i], v = val[i];
+    const float delta = rew[i] + gamma * next * nt - v;
+    last = delta + gamma * lam * nt * last;
+    adv[i] = last;
+    ret[i] = last + v;
+    next = v;
+  }
+}
+
 }  // namespace
 
 static int g_use_tc = -1;
@@ -960,6 +1039,13 @@ int ackb_ppo_minibatch_grad(const float* obs, const float* act, const float* old
   const int grid = ntiles < sms ? ntiles : sms;
   if (use_tc) ppo_grad_kernel_tc<<<grid, NT, smem, s>>>(a);
   else ppo_grad_kernel<<<grid, NT, smem, s>>>(a);
+  return cudaGetLastError() == cudaSuccess ? ACKB_OK : ACKB_ERR_CUDA;
+}
+
+int ackb_ppo_gae(const float* rew, const float* val, const float* done, const float* last_val, int n_steps, int n, float gamma,
+                 float gae_lambda, float* adv, float* ret, void* stream) {
+  if (!rew || !val || !done || !last_val || !adv || !ret || n_steps <= 0 || n <= 0) return ACKB_ERR_ARG;
+  gae_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rew, val, done, last_val, n_steps, n, gamma, gae_lambda, adv, ret);
   return cudaGetLastError() == cudaSuccess ? ACKB_OK : ACKB_ERR_CUDA;
 }
 

@@ -13,6 +13,7 @@ gradient all-reduce per optimiser step (18 757 fp32 = 75 KB) and one statistics 
 from __future__ import annotations
 
 import math
+import os
 import time
 from dataclasses import dataclass
 from typing import Dict, Optional
@@ -236,6 +237,9 @@ class GraphedMinibatchStep:
         return nbytes
 
 
+_ROLLOUT_KEYS = ("obs", "act", "logp", "adv", "ret")
+
+
 class FusedMinibatchStep:
     """One PPO optimiser step with the hand-written fused gradient kernel (csrc/ackb_ppo.cu, include/ackb_ppo.h): forward,
     PPO loss, backward and weight-gradient accumulation of both 64-wide MLPs in one launch with weights and activations in shared
@@ -274,6 +278,7 @@ class FusedMinibatchStep:
         self.diag = torch.zeros(5, device=device, dtype=torch.float32)
         self.adv_stats = torch.zeros(2, device=device, dtype=torch.float32)
         self.mb = -1      # any minibatch size
+        self.index_mode = os.environ.get("ACKB_PPO_SHUFFLE", "index") != "copy"
 
     def act(self, obs: torch.Tensor, action: torch.Tensor, logp: torch.Tensor, value: torch.Tensor, seed: int, step: int) -> None:
         """Fused rollout forward (csrc/ackb_ppo.cu: ppo_act_kernel): fills action (unclipped sample), logp and value in place."""
@@ -294,20 +299,50 @@ class FusedMinibatchStep:
         if rc != 0:
             raise RuntimeError(f"ackb_ppo_act failed with code {rc}")
 
+    def gae(self, rew: torch.Tensor, val: torch.Tensor, done: torch.Tensor, last_val: torch.Tensor, adv: torch.Tensor,
+            ret: torch.Tensor) -> None:
+        """compute_gae as one kernel (ackb_ppo_gae): [T, N] contiguous float32 arrays, results written into adv / ret."""
+        c = self.ct
+        ptr = lambda t: c.c_void_p(t.data_ptr())
+        assert all(t.is_contiguous() and t.dtype == torch.float32 for t in (rew, val, done, last_val, adv, ret))
+        rc = self.L.ackb_ppo_gae(ptr(rew), ptr(val), ptr(done), ptr(last_val), int(rew.shape[0]), int(rew.shape[1]), self.cfg.gamma,
+                                 self.cfg.gae_lambda, ptr(adv), ptr(ret), c.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"ackb_ppo_gae failed with code {rc}")
+
     def shuffle_epoch(self, batch: Dict[str, torch.Tensor], perm: torch.Tensor) -> Dict[str, torch.Tensor]:
-        """Permuted copy of the rollout (one gather per epoch, 0.1 ms per million samples): the minibatches of the epoch are then
-        contiguous row ranges, which the kernel reads without the per-tile index gather."""
+        """Prepare one epoch's minibatches as (start, count) ranges.  Index mode (default): the permutation is kept in a persistent
+        index buffer and the gradient kernel gathers the rollout rows through it (its cp.async prefetch hides the gather), so
+        nothing is copied.  Copy mode (ACKB_PPO_SHUFFLE=copy): a permuted copy of the rollout, minibatches are contiguous rows."""
+        if self.index_mode:
+            if getattr(self, "_perm", None) is None or self._perm.shape != perm.shape:
+                self._perm = torch.empty_like(perm)
+            self._perm.copy_(perm)
+            return batch
         if getattr(self, "_shuf", None) is None or self._shuf["obs"].shape != batch["obs"].shape:
-            self._shuf = {k: torch.empty_like(batch[k]) for k in ("obs", "act", "logp", "adv", "ret")}
+            self._shuf = {k: torch.empty_like(batch[k]) for k in _ROLLOUT_KEYS}
         for k, dst in self._shuf.items():
             torch.index_select(batch[k], 0, perm, out=dst)
         return self._shuf
+
+    def _resolve(self, batch: Dict[str, torch.Tensor], idx):
+        """(arrays, count, advantages of the minibatch, index tensor or None) for idx = int64 rows or a (start, count) range."""
+        if isinstance(idx, tuple):
+            lo, n = idx
+            if self.index_mode:
+                rows = self._perm[lo:lo + n]
+                return batch, n, batch["adv"].index_select(0, rows), rows
+            view = {k: batch[k][lo:lo + n] for k in _ROLLOUT_KEYS}
+            return view, n, view["adv"], None
+        idx = idx.contiguous()
+        return batch, int(idx.numel()), batch["adv"].index_select(0, idx), idx
 
     def capture(self, shuffled: Dict[str, torch.Tensor], slots) -> None:
         """CUDA graphs for the minibatch slots (start, count) of the shuffled rollout: per slot {advantage statistics + gradient
         kernel}, and one graph for {gradient clipping + Adam}.  Needs an optimiser built with capturable=True.  The warm-up steps
         are undone (weights and optimiser state restored in place)."""
         dev = self.device
+        self._cap_ptrs = tuple(shuffled[k].data_ptr() for k in _ROLLOUT_KEYS)
         saved_p = self.flat_p.clone()
         saved_s = {id(p): {k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in self.opt.state.get(p, {}).items()} for p in self.params}
         side = torch.cuda.Stream(device=dev)
@@ -346,59 +381,38 @@ class FusedMinibatchStep:
         """Advantage statistics of the minibatch + the gradient kernel (fills flat_g and diag)."""
         c, cfg = self.ct, self.cfg
         ptr = lambda t: c.c_void_p(t.data_ptr())
-        if isinstance(idx, tuple):
-            lo, n = idx
-            view = {k: batch[k][lo:lo + n] for k in ("obs", "act", "logp", "adv", "ret")}
-            a, idx_ptr = view["adv"], None
-        else:
-            idx = idx.contiguous()
-            view, n = batch, int(idx.numel())
-            a, idx_ptr = batch["adv"].index_select(0, idx), ptr(idx)
+        view, n, a, rows = self._resolve(batch, idx)
         self.adv_stats.copy_(torch.stack([a.mean(), a.std()]))
         stream = c.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         rc = self.L.ackb_ppo_minibatch_grad(ptr(view["obs"]), ptr(view["act"]), ptr(view["logp"]), ptr(view["adv"]), ptr(view["ret"]),
-                                            idx_ptr, n, self.obs_dim, ptr(self.adv_stats), ptr(self.flat_p), ptr(self.flat_g),
-                                            ptr(self.diag), cfg.clip_range, cfg.vf_coef, cfg.ent_coef, stream)
+                                            ptr(rows) if rows is not None else None, n, self.obs_dim, ptr(self.adv_stats),
+                                            ptr(self.flat_p), ptr(self.flat_g), ptr(self.diag), cfg.clip_range, cfg.vf_coef,
+                                            cfg.ent_coef, stream)
         if rc != 0:
             raise RuntimeError(f"ackb_ppo_minibatch_grad failed with code {rc}")
 
     def run(self, batch: Dict[str, torch.Tensor], idx, world: int) -> int:
-        """idx: int64 index tensor (rows of `batch`), or a (start, count) tuple for a contiguous row range."""
+        """idx: int64 index tensor (rows of `batch`), or a (start, count) range of the epoch prepared by shuffle_epoch."""
         g1 = getattr(self, "g1", None)
-        if g1 is not None and isinstance(idx, tuple) and idx in g1 and batch is getattr(self, "_shuf", None):
+        graphs = g1 is not None and isinstance(idx, tuple) and idx in g1 and self._same_arrays(batch)
+        if graphs:
             g1[idx].replay()
-            nbytes = 0
-            if world > 1:
-                dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
-                self.flat_g.div_(world)
-                nbytes = self.flat_g.numel() * 4
-            self.g2.replay()
-            return nbytes
-        c, cfg = self.ct, self.cfg
-        ptr = lambda t: c.c_void_p(t.data_ptr())
-        if isinstance(idx, tuple):
-            lo, n = idx
-            view = {k: batch[k][lo:lo + n] for k in ("obs", "act", "logp", "adv", "ret")}
-            a, idx_ptr = view["adv"], None
         else:
-            idx = idx.contiguous()
-            view, n = batch, int(idx.numel())
-            a, idx_ptr = batch["adv"].index_select(0, idx), ptr(idx)
-        self.adv_stats[0], self.adv_stats[1] = a.mean(), a.std()
-        stream = c.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        rc = self.L.ackb_ppo_minibatch_grad(ptr(view["obs"]), ptr(view["act"]), ptr(view["logp"]), ptr(view["adv"]), ptr(view["ret"]),
-                                            idx_ptr, n, self.obs_dim, ptr(self.adv_stats), ptr(self.flat_p), ptr(self.flat_g),
-                                            ptr(self.diag), cfg.clip_range, cfg.vf_coef, cfg.ent_coef, stream)
-        if rc != 0:
-            raise RuntimeError(f"ackb_ppo_minibatch_grad failed with code {rc}")
+            self._grad(batch, idx)
         nbytes = 0
         if world > 1:
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
             self.flat_g.div_(world)
             nbytes = self.flat_g.numel() * 4
-        torch.nn.utils.clip_grad_norm_(self.params, cfg.max_grad_norm)
-        self.opt.step()
+        if graphs:
+            self.g2.replay()
+        else:
+            self._clip_step()
         return nbytes
+
+    def _same_arrays(self, batch: Dict[str, torch.Tensor]) -> bool:
+        """True if `batch` is made of the very arrays the graphs were captured on."""
+        return tuple(batch[k].data_ptr() for k in _ROLLOUT_KEYS) == getattr(self, "_cap_ptrs", None)
 
 
 class PPOTrainer:
@@ -428,6 +442,7 @@ class PPOTrainer:
         self._noise_seed = (seed * 1000003 + self.rank) * 2654435761 + 12345
         self._act_step = 0
         self._tv = torch.empty(N, **f)
+        self._adv, self._ret = torch.empty((T, N), **f), torch.empty((T, N), **f)    # persistent: CUDA graphs are captured on them
         if self.learner == "fused":     # flat parameter buffers exist from the start: the rollout forward uses them too
             self.graphed = FusedMinibatchStep(self.policy, self.opt, cfg, D, self.device)
 
@@ -466,8 +481,13 @@ class PPOTrainer:
         cfg, b = self.cfg, self.buf
         t0 = time.perf_counter()
         with torch.no_grad():
-            last_val = self.policy.value(sanitize_obs(self.obs))
-            adv, ret = compute_gae(b["rew"], b["val"], b["done"], last_val, cfg.gamma, cfg.gae_lambda)
+            if isinstance(self.graphed, FusedMinibatchStep):      # value forward + one GAE kernel into the persistent arrays
+                self.graphed.value(sanitize_obs(self.obs), self._tv)
+                self.graphed.gae(b["rew"], b["val"], b["done"], self._tv, self._adv, self._ret)
+                adv, ret = self._adv, self._ret
+            else:
+                last_val = self.policy.value(sanitize_obs(self.obs))
+                adv, ret = compute_gae(b["rew"], b["val"], b["done"], last_val, cfg.gamma, cfg.gae_lambda)
         flat = dict(obs=b["obs"].flatten(0, 1), act=b["act"].flatten(0, 1), logp=b["logp"].flatten(), adv=adv.flatten(), ret=ret.flatten())
         if self.learner == "fused" and self.fused_graphs and getattr(self.graphed, "g1", None) is None:
             n = flat["obs"].shape[0]

@@ -282,3 +282,54 @@ def test_fused_act_kernel_matches_policy_forward(obs_dim, n):
     f.value(obs, v_only)
     torch.cuda.synchronize()
     assert torch.allclose(v_only, val, atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("T,n", [(16, 1000), (1, 7), (5, 4097)])
+def test_fused_gae_kernel_matches_compute_gae(T, n):
+    """ackb_ppo_gae against the torch loop (SB3 compute_returns_and_advantage) incl. episode ends inside the rollout."""
+    import ctypes
+    from mujoco_playground_b200 import _lib
+    L, dev = _lib.load(), torch.device("cuda:0")
+    g = torch.Generator().manual_seed(T * 131 + n)
+    rew, val = torch.randn(T, n, generator=g).to(dev), torch.randn(T, n, generator=g).to(dev)
+    done = (torch.rand(T, n, generator=g) < 0.2).float().to(dev)
+    last = torch.randn(n, generator=g).to(dev)
+    adv, ret = torch.empty(T, n, device=dev), torch.empty(T, n, device=dev)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    assert L.ackb_ppo_gae(p(rew), p(val), p(done), p(last), T, n, 0.99, 0.95, p(adv), p(ret), None) == 0
+    torch.cuda.synchronize()
+    want_adv, want_ret = compute_gae(rew.double(), val.double(), done.double(), last.double(), 0.99, 0.95)
+    assert (adv.double() - want_adv).abs().max().item() < 1e-5
+    assert (ret.double() - want_ret).abs().max().item() < 1e-5
+    assert L.ackb_ppo_gae(None, p(val), p(done), p(last), T, n, 0.99, 0.95, p(adv), p(ret), None) != 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["index", "copy"])
+def test_fused_update_minibatch_modes_agree_with_eager(mode, monkeypatch):
+    """Index mode (kernel gathers rows through the epoch's permutation) and copy mode (permuted copy, contiguous minibatches)
+    run the same optimiser steps as the eager torch loop for the same permutations."""
+    from mujoco_playground_b200.ppo import FusedMinibatchStep
+    monkeypatch.setenv("ACKB_PPO_SHUFFLE", mode)
+    dev, obs_dim, n = torch.device("cuda:0"), 79, 2048
+    cfg = PPOConfig(n_epochs=2, minibatches=4)
+    g = torch.Generator().manual_seed(5)
+    batch = dict(obs=torch.randn(n, obs_dim, generator=g), act=torch.randn(n, 2, generator=g) * 0.5, logp=-torch.rand(n, generator=g) - 1.0,
+                 adv=torch.randn(n, generator=g), ret=torch.randn(n, generator=g))
+    batch = {k: v.to(dev) for k, v in batch.items()}
+    torch.manual_seed(3)
+    pa = ActorCritic(obs_dim).to(dev)
+    pb = ActorCritic(obs_dim).to(dev)
+    pb.load_state_dict(pa.state_dict())
+    oa, ob = torch.optim.Adam(pa.parameters(), lr=3e-4, eps=1e-5), torch.optim.Adam(pb.parameters(), lr=3e-4, eps=1e-5)
+    fused = FusedMinibatchStep(pb, ob, cfg, obs_dim, dev)
+    assert fused.index_mode == (mode == "index")
+    fused.L.ackb_ppo_set_mode(0)                   # fp32 arithmetic for the tight comparison
+    try:
+        ppo_update(pa, oa, batch, cfg, generator=torch.Generator(device=dev).manual_seed(9))
+        ppo_update(pb, ob, batch, cfg, generator=torch.Generator(device=dev).manual_seed(9), graphed=fused)
+    finally:
+        fused.L.ackb_ppo_set_mode(1)
+    for (name, x), y in zip(pa.state_dict().items(), pb.state_dict().values()):
+        assert torch.allclose(x, y, atol=5e-5, rtol=1e-3), name

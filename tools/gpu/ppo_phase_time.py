@@ -18,8 +18,9 @@ res["collect_ms"], _ = timed(tr.collect)
 cfg, b = tr.cfg, tr.buf
 def gae():
     with torch.no_grad():
-        lv = tr.policy.value(tr.obs)
-        return compute_gae(b["rew"], b["val"], b["done"], lv, cfg.gamma, cfg.gae_lambda)
+        tr.graphed.value(tr.obs, tr._tv)
+        tr.graphed.gae(b["rew"], b["val"], b["done"], tr._tv, tr._adv, tr._ret)
+        return tr._adv, tr._ret
 res["gae_ms"], (adv, ret) = timed(gae)
 flat = dict(obs=b["obs"].flatten(0, 1), act=b["act"].flatten(0, 1), logp=b["logp"].flatten(), adv=adv.flatten(), ret=ret.flatten())
 n = flat["obs"].shape[0]
