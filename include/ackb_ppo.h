@@ -43,6 +43,17 @@ int ackb_ppo_minibatch_grad(const float* obs, const float* act, const float* old
 int ackb_ppo_act(const float* obs, int n, int obs_dim, const float* params, float* mean, float* value, float* action, float* logp,
                  uint64_t seed, uint32_t step, int value_only, void* stream);
 
+/* {mean, unbiased std} of the advantages of one minibatch (rows idx[0 .. n-1] of adv, or the first n rows if idx is NULL): the
+ * adv_mean_std operand of ackb_ppo_minibatch_grad (SB3 normalises advantages per minibatch, ppo.py train()).  Calls on one
+ * device share a pair of device-side accumulators: issue them on one stream (or otherwise ordered). */
+int ackb_ppo_adv_stats(const float* adv, const int64_t* idx, int n, float* mean_std, void* stream);
+
+/* Optimiser step on the flat parameter vector: global-norm clipping of grads to max_grad_norm (torch.nn.utils.clip_grad_norm_)
+ * followed by Adam (torch.optim.Adam without weight decay / amsgrad: SB3's PPO optimiser).  exp_avg / exp_avg_sq / step are the
+ * optimiser state (step: one float on the device, incremented by the call).  grads is not modified. */
+int ackb_ppo_clip_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* step, int n, float max_grad_norm,
+                       float lr, float beta1, float beta2, float eps, void* stream);
+
 /* Generalised advantage estimation over a rollout (SB3 RolloutBuffer.compute_returns_and_advantage, called from
  * collect_rollouts): rew / val / done / adv / ret are [n_steps][n] device arrays, done[t] = 1 if the episode ended after step t,
  * last_val[n] = V(observation after the last step).  ret = adv + val.  Asynchronous on `stream`. */

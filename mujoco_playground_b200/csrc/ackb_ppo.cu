@@ -1001,6 +1001,79 @@ __global__ void gae_kernel(const float* __restrict__ rew, const float* __restric
   }
 }
 
+// block-wide sum of one double per thread (1024 threads); every thread receives the total
+__device__ __forceinline__ double block_sum_1024(double v, double* scratch) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  __syncthreads();                     // scratch may still be read from a previous call
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double tot = 0.0;
+#pragma unroll 8
+  for (int w = 0; w < 32; ++w) tot += scratch[w];
+  return tot;
+}
+
+// mean and unbiased standard deviation (torch.Tensor.std) of the advantages of one minibatch: every CTA adds its partial sums
+// (double) to two device-scope accumulators, the last CTA to finish writes the result and clears them for the next call
+// (calls on one device must not overlap: they share the accumulators)
+__device__ double g_adv_acc[2] = {0.0, 0.0};
+__device__ unsigned g_adv_done = 0;
+__global__ void __launch_bounds__(256) adv_stats_kernel(const float* __restrict__ adv, const int64_t* __restrict__ idx, int n,
+                                                        float* __restrict__ mean_std) {
+  __shared__ double sh[2][8];
+  __shared__ bool last;
+  double s = 0.0, q = 0.0;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    const double x = (double)adv[idx ? idx[i] : (int64_t)i];
+    s += x; q += x * x;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, off); q += __shfl_xor_sync(0xffffffffu, q, off); }
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0.0, tq = 0.0;
+    for (int w = 0; w < 8; ++w) { ts += sh[0][w]; tq += sh[1][w]; }
+    atomicAdd(&g_adv_acc[0], ts); atomicAdd(&g_adv_acc[1], tq);
+    __threadfence();
+    last = atomicAdd(&g_adv_done, 1u) == gridDim.x - 1;
+    if (last) {
+      __threadfence();
+      const double S = atomicAdd(&g_adv_acc[0], 0.0), Q = atomicAdd(&g_adv_acc[1], 0.0);
+      const double mean = S / (double)n;
+      const double var = (Q - S * mean) / (double)(n > 1 ? n - 1 : 1);
+      mean_std[0] = (float)mean; mean_std[1] = (float)sqrt(var > 0.0 ? var : 0.0);
+      g_adv_acc[0] = 0.0; g_adv_acc[1] = 0.0; g_adv_done = 0u;
+      __threadfence();
+    }
+  }
+}
+
+// global-norm gradient clipping (torch.nn.utils.clip_grad_norm_) + Adam (torch.optim.Adam, no weight decay / amsgrad) on the flat
+// parameter vector, one CTA; `step` is the optimiser's device-side step counter (float, as torch keeps it when capturable)
+__global__ void __launch_bounds__(1024, 1) clip_adam_kernel(float* __restrict__ p, const float* __restrict__ gr, float* __restrict__ m,
+                                                             float* __restrict__ v, float* __restrict__ step, int n, float max_norm,
+                                                             float lr, float b1, float b2, float eps) {
+  __shared__ double scratch[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += 1024) { const double g = (double)gr[i]; s += g * g; }
+  const float norm = (float)sqrt(block_sum_1024(s, scratch));
+  const float coef = fminf(max_norm / (norm + 1e-6f), 1.0f);
+  const float t = step[0] + 1.0f;
+  const float bc1 = 1.0f - powf(b1, t), bc2s = sqrtf(1.0f - powf(b2, t));
+  const float step_size = lr / bc1;
+  for (int i = threadIdx.x; i < n; i += 1024) {
+    const float g = gr[i] * coef;
+    const float mi = m[i] + (1.0f - b1) * (g - m[i]);          // lerp, as torch does
+    const float vi = b2 * v[i] + (1.0f - b2) * g * g;
+    m[i] = mi; v[i] = vi;
+    p[i] -= step_size * mi / (sqrtf(vi) / bc2s + eps);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) step[0] = t;
+}
+
 }  // namespace
 
 static int g_use_tc = -1;
@@ -1039,6 +1112,22 @@ int ackb_ppo_minibatch_grad(const float* obs, const float* act, const float* old
   const int grid = ntiles < sms ? ntiles : sms;
   if (use_tc) ppo_grad_kernel_tc<<<grid, NT, smem, s>>>(a);
   else ppo_grad_kernel<<<grid, NT, smem, s>>>(a);
+  return cudaGetLastError() == cudaSuccess ? ACKB_OK : ACKB_ERR_CUDA;
+}
+
+int ackb_ppo_adv_stats(const float* adv, const int64_t* idx, int n, float* mean_std, void* stream) {
+  if (!adv || !mean_std || n <= 0) return ACKB_ERR_ARG;
+  int blocks = (n + 1023) / 1024;                 // >= 4 values per thread
+  if (blocks > 296) blocks = 296;
+  if (blocks < 1) blocks = 1;
+  adv_stats_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(adv, idx, n, mean_std);
+  return cudaGetLastError() == cudaSuccess ? ACKB_OK : ACKB_ERR_CUDA;
+}
+
+int ackb_ppo_clip_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* step, int n, float max_grad_norm,
+                       float lr, float beta1, float beta2, float eps, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !step || n <= 0) return ACKB_ERR_ARG;
+  clip_adam_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, step, n, max_grad_norm, lr, beta1, beta2, eps);
   return cudaGetLastError() == cudaSuccess ? ACKB_OK : ACKB_ERR_CUDA;
 }
 

@@ -277,6 +277,17 @@ class FusedMinibatchStep:
             self.params = [self.flat_param]
         self.diag = torch.zeros(5, device=device, dtype=torch.float32)
         self.adv_stats = torch.zeros(2, device=device, dtype=torch.float32)
+        # optimiser step as one kernel (ackb_ppo_clip_adam) on torch's own Adam state tensors, so that opt.state_dict() stays the
+        # checkpoint format; needs the flat parameter and a device-side step counter (capturable=True), plain Adam only
+        g = opt.param_groups[0]
+        self.native_opt = (getattr(self, "flat_param", None) is not None and type(opt) is torch.optim.Adam and bool(g.get("capturable", False))
+                           and not g.get("amsgrad") and not g.get("maximize") and g.get("weight_decay", 0) == 0
+                           and not torch.is_tensor(g["lr"]) and os.environ.get("ACKB_PPO_NATIVE_OPT", "1") != "0")
+        if self.native_opt:
+            st = opt.state[self.flat_param]
+            if not st:
+                st["step"] = torch.zeros((), dtype=torch.float32, device=device)
+                st["exp_avg"], st["exp_avg_sq"] = torch.zeros_like(self.flat_p), torch.zeros_like(self.flat_p)
         self.mb = -1      # any minibatch size
         self.index_mode = os.environ.get("ACKB_PPO_SHUFFLE", "index") != "copy"
 
@@ -326,16 +337,14 @@ class FusedMinibatchStep:
         return self._shuf
 
     def _resolve(self, batch: Dict[str, torch.Tensor], idx):
-        """(arrays, count, advantages of the minibatch, index tensor or None) for idx = int64 rows or a (start, count) range."""
+        """(arrays, count, index tensor or None) for idx = int64 rows or a (start, count) range."""
         if isinstance(idx, tuple):
             lo, n = idx
             if self.index_mode:
-                rows = self._perm[lo:lo + n]
-                return batch, n, batch["adv"].index_select(0, rows), rows
-            view = {k: batch[k][lo:lo + n] for k in _ROLLOUT_KEYS}
-            return view, n, view["adv"], None
+                return batch, n, self._perm[lo:lo + n]
+            return {k: batch[k][lo:lo + n] for k in _ROLLOUT_KEYS}, n, None
         idx = idx.contiguous()
-        return batch, int(idx.numel()), batch["adv"].index_select(0, idx), idx
+        return batch, int(idx.numel()), idx
 
     def capture(self, shuffled: Dict[str, torch.Tensor], slots) -> None:
         """CUDA graphs for the minibatch slots (start, count) of the shuffled rollout: per slot {advantage statistics + gradient
@@ -374,16 +383,27 @@ class FusedMinibatchStep:
         torch.cuda.synchronize(dev)
 
     def _clip_step(self):
-        torch.nn.utils.clip_grad_norm_(self.params, self.cfg.max_grad_norm)
-        self.opt.step()
+        if not self.native_opt:
+            torch.nn.utils.clip_grad_norm_(self.params, self.cfg.max_grad_norm)
+            self.opt.step()
+            return
+        c, g, st = self.ct, self.opt.param_groups[0], self.opt.state[self.flat_param]
+        ptr = lambda t: c.c_void_p(t.data_ptr())
+        rc = self.L.ackb_ppo_clip_adam(ptr(self.flat_p), ptr(self.flat_g), ptr(st["exp_avg"]), ptr(st["exp_avg_sq"]), ptr(st["step"]),
+                                       int(self.flat_p.numel()), float(self.cfg.max_grad_norm), float(g["lr"]), float(g["betas"][0]),
+                                       float(g["betas"][1]), float(g["eps"]), c.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"ackb_ppo_clip_adam failed with code {rc}")
 
     def _grad(self, batch: Dict[str, torch.Tensor], idx):
         """Advantage statistics of the minibatch + the gradient kernel (fills flat_g and diag)."""
         c, cfg = self.ct, self.cfg
         ptr = lambda t: c.c_void_p(t.data_ptr())
-        view, n, a, rows = self._resolve(batch, idx)
-        self.adv_stats.copy_(torch.stack([a.mean(), a.std()]))
+        view, n, rows = self._resolve(batch, idx)
         stream = c.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        rc = self.L.ackb_ppo_adv_stats(ptr(view["adv"]), ptr(rows) if rows is not None else None, n, ptr(self.adv_stats), stream)
+        if rc != 0:
+            raise RuntimeError(f"ackb_ppo_adv_stats failed with code {rc}")
         rc = self.L.ackb_ppo_minibatch_grad(ptr(view["obs"]), ptr(view["act"]), ptr(view["logp"]), ptr(view["adv"]), ptr(view["ret"]),
                                             ptr(rows) if rows is not None else None, n, self.obs_dim, ptr(self.adv_stats),
                                             ptr(self.flat_p), ptr(self.flat_g), ptr(self.diag), cfg.clip_range, cfg.vf_coef,

@@ -333,3 +333,39 @@ def test_fused_update_minibatch_modes_agree_with_eager(mode, monkeypatch):
         fused.L.ackb_ppo_set_mode(1)
     for (name, x), y in zip(pa.state_dict().items(), pb.state_dict().values()):
         assert torch.allclose(x, y, atol=5e-5, rtol=1e-3), name
+
+
+@pytest.mark.gpu
+def test_native_adv_stats_and_clip_adam_match_torch():
+    """ackb_ppo_adv_stats vs mean()/std(), ackb_ppo_clip_adam vs clip_grad_norm_ + torch.optim.Adam over several steps
+    (clipping active and inactive)."""
+    import ctypes
+    from mujoco_playground_b200 import _lib
+    L, dev = _lib.load(), torch.device("cuda:0")
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    g = torch.Generator().manual_seed(21)
+    adv = (torch.randn(100000, generator=g) * 3 + 0.7).to(dev)
+    idx = torch.randperm(100000, generator=g)[:4097].to(dev)
+    out = torch.zeros(2, device=dev)
+    assert L.ackb_ppo_adv_stats(p(adv), p(idx), 4097, p(out), None) == 0
+    sel = adv[idx]
+    assert torch.allclose(out, torch.stack([sel.mean(), sel.std()]), rtol=1e-5, atol=1e-6)
+    assert L.ackb_ppo_adv_stats(p(adv), None, 1000, p(out), None) == 0
+    assert torch.allclose(out, torch.stack([adv[:1000].mean(), adv[:1000].std()]), rtol=1e-5, atol=1e-6)
+
+    n = 18757
+    w0 = torch.randn(n, generator=g).to(dev)
+    ref = torch.nn.Parameter(w0.clone())
+    opt = torch.optim.Adam([ref], lr=3e-4, eps=1e-5)
+    w, m, v, step = w0.clone(), torch.zeros(n, device=dev), torch.zeros(n, device=dev), torch.zeros((), device=dev)
+    for it in range(6):
+        grad = (torch.randn(n, generator=g) * (0.001 if it % 2 else 0.05)).to(dev)      # norm 0.14 (no clip) / 6.8 (clipped to 0.5)
+        ref.grad = grad.clone()
+        torch.nn.utils.clip_grad_norm_([ref], 0.5)
+        opt.step()
+        assert L.ackb_ppo_clip_adam(p(w), p(grad), p(m), p(v), p(step), n, 0.5, 3e-4, 0.9, 0.999, 1e-5, None) == 0
+    torch.cuda.synchronize()
+    assert step.item() == 6.0
+    assert torch.allclose(w, ref.detach(), atol=1e-6, rtol=1e-5)
+    st = opt.state[ref]
+    assert torch.allclose(m, st["exp_avg"], atol=1e-8, rtol=1e-4) and torch.allclose(v, st["exp_avg_sq"], atol=1e-12, rtol=1e-4)
