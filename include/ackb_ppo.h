@@ -4,7 +4,7 @@
  * (stable_baselines3/ppo/ppo.py: evaluate_actions -> ratio / clipped surrogate / value loss / entropy -> loss.backward();
  * called through model.learn, src/rl/train.py:175-179) for the MlpPolicy the reference trains
  * (separate tanh MLPs obs -> 64 -> 64 for policy and value, state-independent log_std; 18 757 parameters for obs = 79).
- * The optimiser step (gradient clipping + Adam) stays with the caller.
+ * The optimiser step (gradient clipping + Adam) is a separate entry point, ackb_ppo_clip_adam, on caller-owned state.
  *
  * All pointers are caller-owned DEVICE memory.  Parameter / gradient layout (floats, D = obs_dim):
  *   W1p[64][D] b1p[64] W2p[64][64] b2p[64]  W1v[64][D] b1v[64] W2v[64][64] b2v[64]  Wa[2][64] ba[2]  Wv[64] bv[1]  log_std[2]
