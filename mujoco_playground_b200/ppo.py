@@ -244,9 +244,9 @@ class FusedMinibatchStep:
     """One PPO optimiser step with the hand-written fused gradient kernel (csrc/ackb_ppo.cu, include/ackb_ppo.h): forward,
     PPO loss, backward and weight-gradient accumulation of both 64-wide MLPs in one launch with weights and activations in shared
     memory.  Parameters and gradients live in two flat device buffers in the kernel's layout (the nn.Parameters become views
-    into them), so there is no packing, the gradient all-reduce is one call on the flat buffer, and clipping + Adam (one kernel, ackb_ppo_clip_adam, on torch's own optimiser state; torch ops if the optimiser is not a
-    capturable plain Adam) run on the
-    views.  Same arithmetic as the eager loop of ppo_update up to fp32 summation order (tests/test_ppo.py)."""
+    into them), so there is no packing, the gradient all-reduce is one call on the flat buffer, and clipping + Adam run on the
+    flat vector: one kernel (ackb_ppo_clip_adam) on torch's own optimiser-state tensors, or torch ops if the optimiser is not a
+    capturable plain Adam.  Same arithmetic as the eager loop of ppo_update up to fp32 summation order (tests/test_ppo.py)."""
 
     def __init__(self, policy: ActorCritic, opt: torch.optim.Optimizer, cfg: PPOConfig, obs_dim: int, device):
         import ctypes
