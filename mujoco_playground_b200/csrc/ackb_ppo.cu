@@ -348,6 +348,11 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel(PpoArgs a) {
 // =================================================================================================================
 constexpr int TT = 32;                 // samples per tile
 constexpr int XS = 84, AS = 132, W1S = 136, W2S = 72;
+// Gradient kernel: X, H1, H2 and dH are read both as row-major A operands (bank = g ld + t) and, with the sample index as the
+// reduction dimension of the weight-gradient GEMMs, as transposed-A / B operands (bank = t ld + g).  No padding serves both, an
+// XOR swizzle does: column c of row r lives at c ^ swz(r) with row strides that are multiples of 32 floats.
+constexpr int XSW = 96, ASW = 128;
+__device__ __forceinline__ int swz(int r) { return ((r & 3) << 3) | (r & 4); }
 constexpr int T_W1T = 0;                          // [KP][W1S]
 constexpr int T_W2T = T_W1T + KP * W1S;           // [2][64][W2S]   [net][k][n]
 constexpr int T_W2 = T_W2T + 2 * H * W2S;         // [2][64][W2S]   [net][n][k]
@@ -357,7 +362,7 @@ constexpr int T_B2 = T_B1 + 128;
 constexpr int T_B3 = T_B2 + 128;
 constexpr int T_LS = T_B3 + 4;
 constexpr int T_X = T_LS + 4;                     // [2][TT][XS]  double buffered: the next tile is fetched with cp.async while this one computes
-constexpr int T_H1 = T_X + 2 * TT * XS;           // [TT][AS]
+constexpr int T_H1 = T_X + 2 * TT * XSW;          // [TT][AS] (rollout kernel) / [TT][ASW] swizzled (gradient kernel)
 constexpr int T_H2 = T_H1 + TT * AS;
 constexpr int T_DH = T_H2 + TT * AS;
 constexpr int T_DO = T_DH + TT * AS;              // [TT][4]
@@ -405,6 +410,26 @@ __device__ __forceinline__ void ldb(uint32_t (&b)[2], const float* m, int ld, in
   b[1] = __float_as_uint(m[(k0 + t + 4) * ld + n0 + g]);
 }
 
+// the same three fragment loaders for swizzled arrays (row0, col0, k0, n0 multiples of 8)
+__device__ __forceinline__ void lda_rowmajor_sw(uint32_t (&a)[4], const float* m, int ld, int row0, int col0, int g, int t) {
+  const int f = swz(g);
+  a[0] = __float_as_uint(m[(row0 + g) * ld + ((col0 + t) ^ f)]);
+  a[1] = __float_as_uint(m[(row0 + g + 8) * ld + ((col0 + t) ^ f)]);
+  a[2] = __float_as_uint(m[(row0 + g) * ld + ((col0 + t + 4) ^ f)]);
+  a[3] = __float_as_uint(m[(row0 + g + 8) * ld + ((col0 + t + 4) ^ f)]);
+}
+__device__ __forceinline__ void lda_transposed_sw(uint32_t (&a)[4], const float* m, int ld, int row0, int k0, int g, int t) {
+  const int f0 = swz(t), f1 = swz(t + 4);
+  a[0] = __float_as_uint(m[(k0 + t) * ld + ((row0 + g) ^ f0)]);
+  a[1] = __float_as_uint(m[(k0 + t) * ld + ((row0 + g + 8) ^ f0)]);
+  a[2] = __float_as_uint(m[(k0 + t + 4) * ld + ((row0 + g) ^ f1)]);
+  a[3] = __float_as_uint(m[(k0 + t + 4) * ld + ((row0 + g + 8) ^ f1)]);
+}
+__device__ __forceinline__ void ldb_sw(uint32_t (&b)[2], const float* m, int ld, int k0, int n0, int g, int t) {
+  b[0] = __float_as_uint(m[(k0 + t) * ld + ((n0 + g) ^ swz(t))]);
+  b[1] = __float_as_uint(m[(k0 + t + 4) * ld + ((n0 + g) ^ swz(t + 4))]);
+}
+
 __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gsrc));
@@ -434,10 +459,10 @@ __device__ __forceinline__ void gather_tile_async(const PpoArgs& a, int tile, fl
     const int s = i / KP, k = i - s * KP;
     if (s < ns && k < D) {
       const int64_t row = rows ? (int64_t)rows[s] : (int64_t)(sbase + s);
-      cp_async4(&xbuf[s * XS + k], &a.obs[row * D + k]);
+      cp_async4(&xbuf[s * XSW + (k ^ swz(s))], &a.obs[row * D + k]);
     } else {
       // padding; with D < KP the last column is 1 for real samples, so that dW1 = dH1^T X also yields db1 (column KP - 1)
-      xbuf[s * XS + k] = (k == KP - 1 && D < KP && s < ns) ? 1.0f : 0.0f;
+      xbuf[s * XSW + (k ^ swz(s))] = (k == KP - 1 && D < KP && s < ns) ? 1.0f : 0.0f;
     }
   }
   asm volatile("cp.async.commit_group;");
@@ -525,19 +550,20 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel_tc(PpoArgs a) {
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
     const int sbase = tile * TT;
     const int ns = min(TT, a.mb - sbase);
-    float* const X = &sm[T_X + buf * TT * XS];
+    float* const X = &sm[T_X + buf * TT * XSW];
     // ---- 1. this tile's observation rows have been fetched asynchronously: wait, round to TF32 (each thread its own elements),
     // then start fetching the next tile into the other buffer
     asm volatile("cp.async.wait_all;");
     for (int i = t; i < TT * KP; i += NT) {
       const int s = i / KP, k = i - s * KP;
-      X[s * XS + k] = tf32r(X[s * XS + k]);
+      const int xi = s * XSW + (k ^ swz(s));
+      X[xi] = tf32r(X[xi]);
     }
     __syncthreads();
     if (tile + (int)gridDim.x < ntiles) {
       // this tile's row numbers are no longer needed (its gather has completed): their slot takes those of the tile after next
       if (rows_sm && tile + 2 * (int)gridDim.x < ntiles) stage_rows_async(a, tile + 2 * gridDim.x, rows_sm + buf * TT, t);
-      gather_tile_async(a, tile + gridDim.x, &sm[T_X + (buf ^ 1) * TT * XS], &sm[T_SC + (buf ^ 1) * TT * 8],
+      gather_tile_async(a, tile + gridDim.x, &sm[T_X + (buf ^ 1) * TT * XSW], &sm[T_SC + (buf ^ 1) * TT * 8],
                         rows_sm ? rows_sm + (buf ^ 1) * TT : nullptr, t);
     }
     const float* const SC = &sm[T_SC + buf * TT * 8];
@@ -553,8 +579,8 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel_tc(PpoArgs a) {
 #pragma unroll 2
       for (int k0 = 0; k0 < KP; k0 += 8) {
         uint32_t af[2][4], bf[2][2];
-        lda_rowmajor(af[0], X, XS, 0, k0, g, q);
-        lda_rowmajor(af[1], X, XS, 16, k0, g, q);
+        lda_rowmajor_sw(af[0], X, XSW, 0, k0, g, q);
+        lda_rowmajor_sw(af[1], X, XSW, 16, k0, g, q);
         ldb(bf[0], &sm[T_W1T], W1S, k0, nb0, g, q);
         ldb(bf[1], &sm[T_W1T], W1S, k0, nb0 + 8, g, q);
 #pragma unroll
@@ -566,11 +592,11 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel_tc(PpoArgs a) {
       for (int m = 0; m < 2; ++m)
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          const int col = nb0 + 8 * j + 2 * q, row = 16 * m + g;
-          sm[T_H1 + row * AS + col] = tf32r(tanh_fast(c[m][j][0] + sm[T_B1 + col]));
-          sm[T_H1 + row * AS + col + 1] = tf32r(tanh_fast(c[m][j][1] + sm[T_B1 + col + 1]));
-          sm[T_H1 + (row + 8) * AS + col] = tf32r(tanh_fast(c[m][j][2] + sm[T_B1 + col]));
-          sm[T_H1 + (row + 8) * AS + col + 1] = tf32r(tanh_fast(c[m][j][3] + sm[T_B1 + col + 1]));
+          const int col = nb0 + 8 * j + 2 * q, row = 16 * m + g, pc = col ^ swz(g);
+          sm[T_H1 + row * ASW + pc] = tf32r(tanh_fast(c[m][j][0] + sm[T_B1 + col]));
+          sm[T_H1 + row * ASW + pc + 1] = tf32r(tanh_fast(c[m][j][1] + sm[T_B1 + col + 1]));
+          sm[T_H1 + (row + 8) * ASW + pc] = tf32r(tanh_fast(c[m][j][2] + sm[T_B1 + col]));
+          sm[T_H1 + (row + 8) * ASW + pc + 1] = tf32r(tanh_fast(c[m][j][3] + sm[T_B1 + col + 1]));
         }
     }
     __syncthreads();
@@ -589,8 +615,8 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel_tc(PpoArgs a) {
 #pragma unroll 2
       for (int k0 = 0; k0 < H; k0 += 8) {
         uint32_t af[2][4], bf[2][2];
-        lda_rowmajor(af[0], A, AS, 0, k0, g, q);
-        lda_rowmajor(af[1], A, AS, 16, k0, g, q);
+        lda_rowmajor_sw(af[0], A, ASW, 0, k0, g, q);
+        lda_rowmajor_sw(af[1], A, ASW, 16, k0, g, q);
         ldb(bf[0], B, W2S, k0, nn0, g, q);
         ldb(bf[1], B, W2S, k0, nn0 + 8, g, q);
 #pragma unroll
@@ -602,11 +628,11 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel_tc(PpoArgs a) {
       for (int m = 0; m < 2; ++m)
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          const int col = nb0 + 8 * j + 2 * q, row = 16 * m + g;
-          sm[T_H2 + row * AS + col] = tf32r(tanh_fast(c[m][j][0] + sm[T_B2 + col]));
-          sm[T_H2 + row * AS + col + 1] = tf32r(tanh_fast(c[m][j][1] + sm[T_B2 + col + 1]));
-          sm[T_H2 + (row + 8) * AS + col] = tf32r(tanh_fast(c[m][j][2] + sm[T_B2 + col]));
-          sm[T_H2 + (row + 8) * AS + col + 1] = tf32r(tanh_fast(c[m][j][3] + sm[T_B2 + col + 1]));
+          const int col = nb0 + 8 * j + 2 * q, row = 16 * m + g, pc = col ^ swz(g);
+          sm[T_H2 + row * ASW + pc] = tf32r(tanh_fast(c[m][j][0] + sm[T_B2 + col]));
+          sm[T_H2 + row * ASW + pc + 1] = tf32r(tanh_fast(c[m][j][1] + sm[T_B2 + col + 1]));
+          sm[T_H2 + (row + 8) * ASW + pc] = tf32r(tanh_fast(c[m][j][2] + sm[T_B2 + col]));
+          sm[T_H2 + (row + 8) * ASW + pc + 1] = tf32r(tanh_fast(c[m][j][3] + sm[T_B2 + col + 1]));
         }
     }
     __syncthreads();
@@ -617,7 +643,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel_tc(PpoArgs a) {
 #pragma unroll 4
       for (int k0 = 0; k0 < 128; k0 += 8) {
         uint32_t af[4], bf[2];
-        lda_rowmajor(af, &sm[T_H2], AS, 16 * warp, k0, g, q);
+        lda_rowmajor_sw(af, &sm[T_H2], ASW, 16 * warp, k0, g, q);
         ldb(bf, &sm[T_W3B], 8, k0, 0, g, q);
         mma_tf32(c, af, bf);
       }
@@ -654,10 +680,11 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel_tc(PpoArgs a) {
     // ---- 5. dH2 = (dOut W3) * (1 - H2^2)   (TF32-rounded: it feeds two GEMMs)
     for (int i = t; i < TT * 128; i += NT) {
       const int s = i >> 7, n = i & 127;
-      const float h = sm[T_H2 + s * AS + n];
+      const int pn = s * ASW + (n ^ swz(s));
+      const float h = sm[T_H2 + pn];
       const float gg = (n < H) ? sm[T_DO + s * 4] * sm[T_W3 + n] + sm[T_DO + s * 4 + 1] * sm[T_W3 + H + n]
                                : sm[T_DO + s * 4 + 2] * sm[T_W3 + 2 * H + (n - H)];
-      sm[T_DH + s * AS + n] = tf32r(gg * (1.0f - h * h));
+      sm[T_DH + pn] = tf32r(gg * (1.0f - h * h));
     }
     __syncthreads();
     // ---- 6. head weights dW3 += dOut^T H2, dW2 += dH2^T H1 and db2 += dH2^T 1 (tensor cores)
@@ -674,7 +701,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel_tc(PpoArgs a) {
 #pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
           uint32_t bf[2];
-          ldb(bf, B3, AS, s0, 8 * (2 * warp + jj), g, q);
+          ldb_sw(bf, B3, ASW, s0, 8 * (2 * warp + jj), g, q);
           mma_tf32(acc3[jj], af, bf);
         }
       }
@@ -683,11 +710,11 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel_tc(PpoArgs a) {
 #pragma unroll
       for (int s0 = 0; s0 < TT; s0 += 8) {
         uint32_t af[4];
-        lda_transposed(af, At, AS, w2row0, s0, g, q);
+        lda_transposed_sw(af, At, ASW, w2row0, s0, g, q);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           uint32_t bf[2];
-          ldb(bf, B, AS, s0, 8 * j, g, q);
+          ldb_sw(bf, B, ASW, s0, 8 * j, g, q);
           mma_tf32(acc2[j], af, bf);
         }
         mma_tf32(accb2, af, ones_b);
@@ -708,8 +735,8 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel_tc(PpoArgs a) {
 #pragma unroll 2
       for (int k0 = 0; k0 < H; k0 += 8) {
         uint32_t af[2][4], bf[2][2];
-        lda_rowmajor(af[0], A, AS, 0, k0, g, q);
-        lda_rowmajor(af[1], A, AS, 16, k0, g, q);
+        lda_rowmajor_sw(af[0], A, ASW, 0, k0, g, q);
+        lda_rowmajor_sw(af[1], A, ASW, 16, k0, g, q);
         ldb(bf[0], B, W2S, k0, nn0, g, q);
         ldb(bf[1], B, W2S, k0, nn0 + 8, g, q);
 #pragma unroll
@@ -722,30 +749,30 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel_tc(PpoArgs a) {
       for (int m = 0; m < 2; ++m)
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
-          const int col = nb0 + 8 * j + 2 * q, row = 16 * m + g;
-          const float h00 = sm[T_H1 + row * AS + col], h01 = sm[T_H1 + row * AS + col + 1];
-          const float h10 = sm[T_H1 + (row + 8) * AS + col], h11 = sm[T_H1 + (row + 8) * AS + col + 1];
-          sm[T_DH + row * AS + col] = tf32r(c[m][j][0] * (1.0f - h00 * h00));
-          sm[T_DH + row * AS + col + 1] = tf32r(c[m][j][1] * (1.0f - h01 * h01));
-          sm[T_DH + (row + 8) * AS + col] = tf32r(c[m][j][2] * (1.0f - h10 * h10));
-          sm[T_DH + (row + 8) * AS + col + 1] = tf32r(c[m][j][3] * (1.0f - h11 * h11));
+          const int col = nb0 + 8 * j + 2 * q, row = 16 * m + g, pc = col ^ swz(g);
+          const float h00 = sm[T_H1 + row * ASW + pc], h01 = sm[T_H1 + row * ASW + pc + 1];
+          const float h10 = sm[T_H1 + (row + 8) * ASW + pc], h11 = sm[T_H1 + (row + 8) * ASW + pc + 1];
+          sm[T_DH + row * ASW + pc] = tf32r(c[m][j][0] * (1.0f - h00 * h00));
+          sm[T_DH + row * ASW + pc + 1] = tf32r(c[m][j][1] * (1.0f - h01 * h01));
+          sm[T_DH + (row + 8) * ASW + pc] = tf32r(c[m][j][2] * (1.0f - h10 * h10));
+          sm[T_DH + (row + 8) * ASW + pc + 1] = tf32r(c[m][j][3] * (1.0f - h11 * h11));
         }
     }
     __syncthreads();
     // ---- 8. db1, dW1 += dH1^T X
     if (!b1_by_mma && t < 128)
-      for (int s = 0; s < TT; ++s) gb1 += sm[T_DH + s * AS + t];
+      for (int s = 0; s < TT; ++s) gb1 += sm[T_DH + s * ASW + (t ^ swz(s))];
     {
       const float* At = &sm[T_DH];                  // dH1[s][n] -> element (n, s)
       const float* B = X;                           // X[s][k]   -> B[k = s][n = k]
 #pragma unroll
       for (int s0 = 0; s0 < TT; s0 += 8) {
         uint32_t af[4];
-        lda_transposed(af, At, AS, 16 * warp, s0, g, q);
+        lda_transposed_sw(af, At, ASW, 16 * warp, s0, g, q);
 #pragma unroll
         for (int j = 0; j < 10; ++j) {
           uint32_t bf[2];
-          ldb(bf, B, XS, s0, 8 * j, g, q);
+          ldb_sw(bf, B, XSW, s0, 8 * j, g, q);
           mma_tf32(acc1[j], af, bf);
         }
       }
