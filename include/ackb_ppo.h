@@ -43,6 +43,12 @@ int ackb_ppo_minibatch_grad(const float* obs, const float* act, const float* old
 int ackb_ppo_act(const float* obs, int n, int obs_dim, const float* params, float* mean, float* value, float* action, float* logp,
                  uint64_t seed, uint32_t step, int value_only, void* stream);
 
+/* Time-limit bootstrap of one rollout step (SB3 collect_rollouts: rewards[idx] += gamma * V(terminal_observation) where the
+ * episode was truncated but not terminated): reward_out[n] = reward + gamma * V(terminal_obs) for those rows, reward elsewhere;
+ * done_out[n] = (terminated | truncated) as float.  The value network only runs for 32-row tiles that contain such a row. */
+int ackb_ppo_bootstrap(const float* terminal_obs, const uint8_t* terminated, const uint8_t* truncated, const float* reward, int n,
+                       int obs_dim, const float* params, float gamma, float* reward_out, float* done_out, void* stream);
+
 /* {mean, unbiased std} of the advantages of one minibatch (rows idx[0 .. n-1] of adv, or the first n rows if idx is NULL): the
  * adv_mean_std operand of ackb_ppo_minibatch_grad (SB3 normalises advantages per minibatch, ppo.py train()).  Calls on one
  * device share a pair of device-side accumulators: issue them on one stream (or otherwise ordered). */

@@ -852,6 +852,12 @@ struct ActArgs {
   unsigned long long seed;
   unsigned step;
   int value_only;                           // skip the policy net (bootstrap values of terminal observations)
+  // time-limit bootstrap (value_only): reward_out = reward + gamma V(obs) where the episode was truncated but not terminated,
+  // reward elsewhere; done_out = terminated | truncated as float.  Tiles without such a row skip the network.
+  const uint8_t *term, *trunc;
+  const float* reward;
+  float gamma;
+  float *reward_out, *done_out;
 };
 
 __device__ __forceinline__ void philox_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
@@ -897,6 +903,14 @@ __global__ void __launch_bounds__(NT, 1) ppo_act_kernel(ActArgs a) {
   const int ntiles = (a.n + TT - 1) / TT;
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int sbase = tile * TT, ns = min(TT, a.n - sbase);
+    if (a.reward_out) {
+      bool need = false, dn = false;
+      if (t < ns) { const bool tm = a.term[sbase + t] != 0, tr = a.trunc[sbase + t] != 0; need = tr && !tm; dn = tm || tr; }
+      if (!__syncthreads_or(need)) {      // nothing to bootstrap in this tile
+        if (t < ns) { a.reward_out[sbase + t] = a.reward[sbase + t]; a.done_out[sbase + t] = dn ? 1.0f : 0.0f; }
+        continue;
+      }
+    }
     for (int i = t; i < TT * KP; i += NT) {
       const int s = i / KP, k = i - s * KP;
       X[s * XS + k] = (s < ns && k < D) ? tf32r(a.obs[(size_t)(sbase + s) * D + k]) : 0.0f;
@@ -986,7 +1000,13 @@ __global__ void __launch_bounds__(NT, 1) ppo_act_kernel(ActArgs a) {
       }
       if (lane == 0 && s < ns) {
         const size_t row = (size_t)(sbase + s);
-        a.value[row] = pv + sm[T_B3 + 2];
+        const float v = pv + sm[T_B3 + 2];
+        if (a.value) a.value[row] = v;
+        if (a.reward_out) {
+          const bool tm = a.term[row] != 0, tr = a.trunc[row] != 0;
+          a.reward_out[row] = a.reward[row] + ((tr && !tm) ? a.gamma * v : 0.0f);
+          a.done_out[row] = (tm || tr) ? 1.0f : 0.0f;
+        }
         if (!a.value_only) {
           const float m0 = p0 + sm[T_B3], m1 = p1 + sm[T_B3 + 1];
           if (a.mean) { a.mean[row * 2] = m0; a.mean[row * 2 + 1] = m1; }
@@ -1165,10 +1185,7 @@ int ackb_ppo_gae(const float* rew, const float* val, const float* done, const fl
   return cudaGetLastError() == cudaSuccess ? ACKB_OK : ACKB_ERR_CUDA;
 }
 
-int ackb_ppo_act(const float* obs, int n, int obs_dim, const float* params, float* mean, float* value, float* action, float* logp,
-                 uint64_t seed, uint32_t step, int value_only, void* stream) {
-  if (!obs || !params || !value || n <= 0 || obs_dim <= 0 || obs_dim > KP) return ACKB_ERR_ARG;
-  cudaStream_t s = (cudaStream_t)stream;
+static int launch_act(const ActArgs& a, cudaStream_t s) {
   static bool attr_done[64] = {false};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return ACKB_ERR_NO_DEVICE;
@@ -1179,10 +1196,27 @@ int ackb_ppo_act(const float* obs, int n, int obs_dim, const float* params, floa
   }
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  ActArgs a{obs, n, obs_dim, params, mean, value, action, logp, (unsigned long long)seed, step, value_only};
-  const int ntiles = (n + TT - 1) / TT;
+  const int ntiles = (a.n + TT - 1) / TT;
   ppo_act_kernel<<<ntiles < sms ? ntiles : sms, NT, smem, s>>>(a);
   return cudaGetLastError() == cudaSuccess ? ACKB_OK : ACKB_ERR_CUDA;
+}
+
+int ackb_ppo_act(const float* obs, int n, int obs_dim, const float* params, float* mean, float* value, float* action, float* logp,
+                 uint64_t seed, uint32_t step, int value_only, void* stream) {
+  if (!obs || !params || !value || n <= 0 || obs_dim <= 0 || obs_dim > KP) return ACKB_ERR_ARG;
+  ActArgs a{obs, n, obs_dim, params, mean, value, action, logp, (unsigned long long)seed, step, value_only,
+            nullptr, nullptr, nullptr, 0.0f, nullptr, nullptr};
+  return launch_act(a, (cudaStream_t)stream);
+}
+
+int ackb_ppo_bootstrap(const float* terminal_obs, const uint8_t* terminated, const uint8_t* truncated, const float* reward, int n,
+                       int obs_dim, const float* params, float gamma, float* reward_out, float* done_out, void* stream) {
+  if (!terminal_obs || !terminated || !truncated || !reward || !params || !reward_out || !done_out || n <= 0 || obs_dim <= 0 ||
+      obs_dim > KP)
+    return ACKB_ERR_ARG;
+  ActArgs a{terminal_obs, n, obs_dim, params, nullptr, nullptr, nullptr, nullptr, 0ull, 0u, 1,
+            terminated, truncated, reward, gamma, reward_out, done_out};
+  return launch_act(a, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -311,6 +311,19 @@ class FusedMinibatchStep:
         if rc != 0:
             raise RuntimeError(f"ackb_ppo_act failed with code {rc}")
 
+    def bootstrap(self, terminal_obs: torch.Tensor, term: torch.Tensor, trunc: torch.Tensor, rew: torch.Tensor, rew_out: torch.Tensor,
+                  done_out: torch.Tensor) -> None:
+        """rew_out = rew + gamma V(terminal_obs) on time-limit truncation (else rew), done_out = term | trunc, in one launch
+        (ackb_ppo_bootstrap); term / trunc are uint8."""
+        c = self.ct
+        ptr = lambda t: c.c_void_p(t.data_ptr())
+        assert term.dtype == torch.uint8 and trunc.dtype == torch.uint8 and rew_out.is_contiguous() and done_out.is_contiguous()
+        rc = self.L.ackb_ppo_bootstrap(ptr(terminal_obs), ptr(term), ptr(trunc), ptr(rew), int(rew.shape[0]), self.obs_dim, ptr(self.flat_p),
+                                       self.cfg.gamma, ptr(rew_out), ptr(done_out),
+                                       c.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"ackb_ppo_bootstrap failed with code {rc}")
+
     def gae(self, rew: torch.Tensor, val: torch.Tensor, done: torch.Tensor, last_val: torch.Tensor, adv: torch.Tensor,
             ret: torch.Tensor) -> None:
         """compute_gae as one kernel (ackb_ppo_gae): [T, N] contiguous float32 arrays, results written into adv / ret."""
@@ -485,14 +498,13 @@ class PPOTrainer:
             nobs, rew, term, trunc, info = env.step(torch.clamp(act, -1.0, 1.0))     # SB3 clips to the Box bounds
             # bootstrap with V(terminal observation) on time-limit truncation; evaluated for every environment and masked, so
             # that the rollout loop has no device->host synchronisation (rows of environments that did not finish are stale, unused)
-            only_trunc = ((trunc != 0) & (term == 0)).float()
-            if fused is not None:
-                fused.value(info["terminal_observation"], self._tv)
-                tv = self._tv
+            if fused is not None and term.dtype == torch.uint8:
+                fused.bootstrap(info["terminal_observation"], term, trunc, rew, b["rew"][t], b["done"][t])
             else:
+                only_trunc = ((trunc != 0) & (term == 0)).float()
                 tv = self.policy.value(sanitize_obs(info["terminal_observation"]))
-            b["rew"][t] = rew + cfg.gamma * tv * only_trunc
-            b["done"][t] = ((term != 0) | (trunc != 0)).float()
+                b["rew"][t] = rew + cfg.gamma * tv * only_trunc
+                b["done"][t] = ((term != 0) | (trunc != 0)).float()
             self.obs.copy_(nobs)
         self.num_timesteps += cfg.n_steps * env.num_envs * self.world
         torch.cuda.synchronize(self.device)

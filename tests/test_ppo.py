@@ -369,3 +369,30 @@ def test_native_adv_stats_and_clip_adam_match_torch():
     assert torch.allclose(w, ref.detach(), atol=1e-6, rtol=1e-5)
     st = opt.state[ref]
     assert torch.allclose(m, st["exp_avg"], atol=1e-8, rtol=1e-4) and torch.allclose(v, st["exp_avg_sq"], atol=1e-12, rtol=1e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,p_trunc", [(5000, 0.01), (33, 0.5), (4096, 0.0)])
+def test_bootstrap_kernel_matches_torch(n, p_trunc):
+    """ackb_ppo_bootstrap: reward + gamma V(terminal obs) only where truncated and not terminated; done = term | trunc.  Tiles
+    without a truncated row take the shortcut that skips the value network."""
+    from mujoco_playground_b200.ppo import ActorCritic, FusedMinibatchStep
+    dev, D = torch.device("cuda:0"), 79
+    torch.manual_seed(4)
+    pol = ActorCritic(D).to(dev)
+    f = FusedMinibatchStep(pol, torch.optim.SGD(pol.parameters(), lr=0.0), PPOConfig(), D, dev)
+    g = torch.Generator().manual_seed(n)
+    tobs = (torch.randn(n, D, generator=g) * 2).to(dev)
+    term = (torch.rand(n, generator=g) < 0.05).to(torch.uint8).to(dev)
+    trunc = (torch.rand(n, generator=g) < p_trunc).to(torch.uint8).to(dev)
+    rew = torch.randn(n, generator=g).to(dev)
+    rew_out, done_out = torch.full((n,), 7.0, device=dev), torch.full((n,), 7.0, device=dev)
+    f.bootstrap(tobs, term, trunc, rew, rew_out, done_out)
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        v = pol.value(tobs)
+    only = ((trunc != 0) & (term == 0)).float()
+    want = rew + 0.99 * v * only
+    assert torch.equal(done_out, ((term != 0) | (trunc != 0)).float())
+    assert torch.equal(rew_out[only == 0], rew[only == 0]), "rows without a time-limit truncation keep their reward bit for bit"
+    assert (rew_out - want).abs().max().item() < 5e-3 * max(1.0, v.abs().max().item())
