@@ -870,6 +870,23 @@ __device__ __forceinline__ void philox_10(uint32_t c0, uint32_t c1, uint32_t c2,
   out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+// asynchronous fetch of the observation rows of one tile (contiguous rows, stride XS, zero padding written directly)
+__device__ __forceinline__ void fetch_obs_tile_async(const ActArgs& a, int tile, float* xbuf, int t) {
+  const int sbase = tile * TT, ns = min(TT, a.n - sbase), D = a.D;
+  for (int i = t; i < TT * KP; i += NT) {
+    const int s = i / KP, k = i - s * KP;
+    if (s < ns && k < D) cp_async4(&xbuf[s * XS + k], &a.obs[(size_t)(sbase + s) * D + k]);
+    else xbuf[s * XS + k] = 0.0f;
+  }
+}
+// does this tile need the network?  (bootstrap mode: only tiles with a truncated-but-not-terminated row)
+__device__ __forceinline__ bool tile_needs_value(const ActArgs& a, int tile, int t) {
+  if (!a.reward_out) return true;
+  const int row = tile * TT + t;
+  const bool need = t < TT && row < a.n && a.trunc[row] != 0 && a.term[row] == 0;
+  return __syncthreads_or(need) != 0;
+}
+
 __global__ void __launch_bounds__(NT, 1) ppo_act_kernel(ActArgs a) {
   extern __shared__ __align__(16) float sm[];
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -898,24 +915,34 @@ __global__ void __launch_bounds__(NT, 1) ppo_act_kernel(ActArgs a) {
   const float sd0 = expf(ls0), sd1 = expf(ls1);
   const int nb0 = 16 * warp, gnet = warp >> 2;
   const bool skip = a.value_only && gnet == 0;     // warps 0..3 own the policy net's columns
-  float* const X = &sm[T_X];
-
   const int ntiles = (a.n + TT - 1) / TT;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  // the observation rows of the next tile are fetched with cp.async into the other buffer while this tile computes
+  int buf = 0;
+  bool need = (int)blockIdx.x < ntiles && tile_needs_value(a, blockIdx.x, t);
+  if (need) fetch_obs_tile_async(a, blockIdx.x, &sm[T_X], t);
+  asm volatile("cp.async.commit_group;");
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
     const int sbase = tile * TT, ns = min(TT, a.n - sbase);
-    if (a.reward_out) {
-      bool need = false, dn = false;
-      if (t < ns) { const bool tm = a.term[sbase + t] != 0, tr = a.trunc[sbase + t] != 0; need = tr && !tm; dn = tm || tr; }
-      if (!__syncthreads_or(need)) {      // nothing to bootstrap in this tile
-        if (t < ns) { a.reward_out[sbase + t] = a.reward[sbase + t]; a.done_out[sbase + t] = dn ? 1.0f : 0.0f; }
-        continue;
+    float* const X = &sm[T_X + buf * TT * XSW];
+    const bool need_this = need;
+    asm volatile("cp.async.wait_all;");
+    if (need_this)
+      for (int i = t; i < TT * KP; i += NT) {      // round to TF32 (each thread its own elements)
+        const int s = i / KP, k = i - s * KP;
+        X[s * XS + k] = tf32r(X[s * XS + k]);
       }
-    }
-    for (int i = t; i < TT * KP; i += NT) {
-      const int s = i / KP, k = i - s * KP;
-      X[s * XS + k] = (s < ns && k < D) ? tf32r(a.obs[(size_t)(sbase + s) * D + k]) : 0.0f;
-    }
     __syncthreads();
+    const int nxt = tile + gridDim.x;
+    need = nxt < ntiles && tile_needs_value(a, nxt, t);
+    if (need) fetch_obs_tile_async(a, nxt, &sm[T_X + (buf ^ 1) * TT * XSW], t);
+    asm volatile("cp.async.commit_group;");
+    if (!need_this) {      // nothing to bootstrap in this tile: rewards pass through
+      if (t < ns) {
+        a.reward_out[sbase + t] = a.reward[sbase + t];
+        a.done_out[sbase + t] = (a.term[sbase + t] != 0 || a.trunc[sbase + t] != 0) ? 1.0f : 0.0f;
+      }
+      continue;
+    }
     if (!skip) {
       float c[2][2][4];
 #pragma unroll
