@@ -49,6 +49,10 @@ int ackb_ppo_act(const float* obs, int n, int obs_dim, const float* params, floa
 int ackb_ppo_bootstrap(const float* terminal_obs, const uint8_t* terminated, const uint8_t* truncated, const float* reward, int n,
                        int obs_dim, const float* params, float gamma, float* reward_out, float* done_out, void* stream);
 
+/* Pseudo-random permutation of 0 .. n-1 into perm[n] (the per-epoch shuffle of SB3's RolloutBuffer.get, np.random.permutation):
+ * a keyed Feistel bijection with cycle walking, one thread per element, no sort.  (seed, stream_id) select the permutation. */
+int ackb_ppo_permutation(int64_t* perm, long long n, uint64_t seed, uint32_t stream_id, void* stream);
+
 /* {mean, unbiased std} of the advantages of one minibatch (rows idx[0 .. n-1] of adv, or the first n rows if idx is NULL): the
  * adv_mean_std operand of ackb_ppo_minibatch_grad (SB3 normalises advantages per minibatch, ppo.py train()).  Calls on one
  * device share a pair of device-side accumulators: issue them on one stream (or otherwise ordered). */

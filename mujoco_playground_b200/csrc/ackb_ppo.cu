@@ -1075,6 +1075,34 @@ __global__ void gae_kernel(const float* __restrict__ rew, const float* __restric
   }
 }
 
+// Pseudo-random permutation of 0 .. n-1 without a sort: a keyed balanced Feistel network is a bijection of [0, 2^(2h)), and
+// cycle walking (re-encrypt until the value is < n) restricts it to [0, n); 2^(2h) < 4 n, so a value walks < 4 times on average.
+__device__ __forceinline__ uint32_t feistel_f(uint32_t x, uint32_t key) {
+  x = (x ^ key) * 0x9E3779B1u; x ^= x >> 15;
+  x *= 0x85EBCA77u; x ^= x >> 13;
+  x *= 0xC2B2AE3Du; x ^= x >> 16;
+  return x;
+}
+__global__ void permutation_kernel(int64_t* __restrict__ perm, long long n, int half_bits, uint64_t seed, uint32_t stream_id) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t mask = (1u << half_bits) - 1u;
+  uint32_t keys[8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r) keys[r] = feistel_f((uint32_t)seed + 0x632BE5ABu * (uint32_t)r, (uint32_t)(seed >> 32) ^ (stream_id * 0x9E3779B9u + (uint32_t)r));
+  unsigned long long v = (unsigned long long)i;
+  do {
+    uint32_t L = (uint32_t)(v >> half_bits) & mask, R = (uint32_t)v & mask;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const uint32_t nl = R, nr = L ^ (feistel_f(R, keys[r]) & mask);
+      L = nl; R = nr;
+    }
+    v = ((unsigned long long)L << half_bits) | R;
+  } while (v >= (unsigned long long)n);
+  perm[i] = (int64_t)v;
+}
+
 // block-wide sum of one double per thread (1024 threads); every thread receives the total
 __device__ __forceinline__ double block_sum_1024(double v, double* scratch) {
 #pragma unroll
@@ -1186,6 +1214,14 @@ int ackb_ppo_minibatch_grad(const float* obs, const float* act, const float* old
   const int grid = ntiles < sms ? ntiles : sms;
   if (use_tc) ppo_grad_kernel_tc<<<grid, NT, smem, s>>>(a);
   else ppo_grad_kernel<<<grid, NT, smem, s>>>(a);
+  return cudaGetLastError() == cudaSuccess ? ACKB_OK : ACKB_ERR_CUDA;
+}
+
+int ackb_ppo_permutation(int64_t* perm, long long n, uint64_t seed, uint32_t stream_id, void* stream) {
+  if (!perm || n <= 0 || n > (1ll << 40)) return ACKB_ERR_ARG;
+  int half_bits = 1;
+  while ((1ull << (2 * half_bits)) < (unsigned long long)n) ++half_bits;
+  permutation_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(perm, n, half_bits, seed, stream_id);
   return cudaGetLastError() == cudaSuccess ? ACKB_OK : ACKB_ERR_CUDA;
 }
 

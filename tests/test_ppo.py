@@ -396,3 +396,30 @@ def test_bootstrap_kernel_matches_torch(n, p_trunc):
     assert torch.equal(done_out, ((term != 0) | (trunc != 0)).float())
     assert torch.equal(rew_out[only == 0], rew[only == 0]), "rows without a time-limit truncation keep their reward bit for bit"
     assert (rew_out - want).abs().max().item() < 5e-3 * max(1.0, v.abs().max().item())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 2, 5, 1000, 4096, 65537, 1048576])
+def test_native_permutation_is_a_permutation(n):
+    """ackb_ppo_permutation: a bijection of 0..n-1 for any n, reproducible per (seed, stream), different across streams, and
+    not close to the identity (mean displacement ~ n/3 for a random permutation)."""
+    import ctypes
+    from mujoco_playground_b200 import _lib
+    L, dev = _lib.load(), torch.device("cuda:0")
+    a, b, c = (torch.full((n,), -1, dtype=torch.int64, device=dev) for _ in range(3))
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    assert L.ackb_ppo_permutation(p(a), n, 1234567, 1, None) == 0
+    assert L.ackb_ppo_permutation(p(b), n, 1234567, 1, None) == 0
+    assert L.ackb_ppo_permutation(p(c), n, 1234567, 2, None) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(torch.sort(a).values, torch.arange(n, device=dev))
+    assert torch.equal(torch.sort(c).values, torch.arange(n, device=dev))
+    assert torch.equal(a, b)
+    if n >= 1000:
+        assert not torch.equal(a, c)
+        disp = (a - torch.arange(n, device=dev)).abs().double().mean().item() / n
+        assert 0.30 < disp < 0.37, disp
+        # minibatch quarters draw evenly from the whole range
+        q = a[: n // 4].double().mean().item() / n
+        assert 0.45 < q < 0.55, q
+    assert L.ackb_ppo_permutation(None, n, 0, 0, None) != 0
