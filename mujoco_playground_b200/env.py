@@ -91,9 +91,17 @@ class BatchedAckermannEnv:
             _lib.check(self.L.ackb_reset(self.h, mp, ctypes.c_void_p(self.obs.data_ptr()), self._stream()), self.h)
         return self.obs
 
-    def step(self, actions: Optional[torch.Tensor]):
+    def step(self, actions: Optional[torch.Tensor], obs_out: Optional[torch.Tensor] = None):
         """actions: [N, 2] float32 CUDA tensor in [-1, 1] (clipped like the reference), or None for synthetic
-        device-generated U(-1,1) actions.  Returns (obs, reward, terminated, truncated, info) as device tensors."""
+        device-generated U(-1,1) actions.  Returns (obs, reward, terminated, truncated, info) as device tensors.
+        obs_out: optional contiguous [N, obs_dim] float32 tensor on the env's device that receives the observations instead
+        of the environment's own buffer (e.g. the next slot of a rollout buffer: saves the copy)."""
+        obs = self.obs
+        if obs_out is not None:
+            if (obs_out.device != self.device or obs_out.dtype != torch.float32 or not obs_out.is_contiguous()
+                    or tuple(obs_out.shape) != (self.num_envs, self.obs_dim)):
+                raise ValueError(f"obs_out must be a contiguous float32 [{self.num_envs}, {self.obs_dim}] tensor on {self.device}")
+            obs = obs_out
         ap = None
         if actions is not None:
             if actions.device != self.device or actions.dtype != torch.float32 or not actions.is_contiguous():
@@ -102,12 +110,12 @@ class BatchedAckermannEnv:
                 raise ValueError(f"actions must have shape ({self.num_envs}, 2)")
             ap = ctypes.c_void_p(actions.data_ptr())
         with torch.cuda.device(self.device):
-            _lib.check(self.L.ackb_step(self.h, ap, self.frame_skip, int(self.auto_reset), ctypes.c_void_p(self.obs.data_ptr()),
+            _lib.check(self.L.ackb_step(self.h, ap, self.frame_skip, int(self.auto_reset), ctypes.c_void_p(obs.data_ptr()),
                                         ctypes.c_void_p(self.reward.data_ptr()), ctypes.c_void_p(self.terminated.data_ptr()),
                                         ctypes.c_void_p(self.truncated.data_ptr()), ctypes.c_void_p(self.terminal_obs.data_ptr()),
                                         ctypes.c_void_p(self.ncon.data_ptr()), self._stream()), self.h)
         info = {"terminal_observation": self.terminal_obs, "ncon": self.ncon}
-        return self.obs, self.reward, self.terminated, self.truncated, info
+        return obs, self.reward, self.terminated, self.truncated, info
 
     def step_host(self, actions: torch.Tensor, obs: torch.Tensor, reward: torch.Tensor, terminated: torch.Tensor, truncated: torch.Tensor):
         """End-to-end step with HOST (pinned) tensors: H2D actions, step, D2H results; synchronous."""

@@ -497,6 +497,8 @@ class PPOTrainer:
         self._noise_seed = (seed * 1000003 + self.rank) * 2654435761 + 12345
         self._act_step = 0
         self._tv = torch.empty(N, **f)
+        import inspect
+        self._env_takes_obs_out = "obs_out" in inspect.signature(env.step).parameters
         self._adv, self._ret = torch.empty((T, N), **f), torch.empty((T, N), **f)    # persistent: CUDA graphs are captured on them
         if self.learner == "fused":     # flat parameter buffers exist from the start: the rollout forward uses them too
             self.graphed = FusedMinibatchStep(self.policy, self.opt, cfg, D, self.device)
@@ -508,15 +510,20 @@ class PPOTrainer:
         for t in range(cfg.n_steps):
             obs = sanitize_obs(self.obs)
             fused = self.graphed if isinstance(self.graphed, FusedMinibatchStep) else None
+            direct = fused is not None and self._env_takes_obs_out
             if fused is not None:     # one launch: both MLPs, Gaussian sample, log-probability, value -> straight into the buffers
-                b["obs"][t].copy_(obs)
+                if not direct or t == 0:
+                    b["obs"][t].copy_(obs)
                 fused.act(b["obs"][t], b["act"][t], b["logp"][t], b["val"][t], self._noise_seed, self._act_step)
                 self._act_step += 1
                 act = b["act"][t]
             else:
                 act, logp, val = self.policy.act(obs)
                 b["obs"][t], b["act"][t], b["logp"][t], b["val"][t] = obs, act, logp, val
-            nobs, rew, term, trunc, info = env.step(torch.clamp(act, -1.0, 1.0))     # SB3 clips to the Box bounds
+            if direct:      # the step kernel writes the next observation straight into the next rollout slot (or self.obs at the end)
+                nobs, rew, term, trunc, info = env.step(torch.clamp(act, -1.0, 1.0), obs_out=b["obs"][t + 1] if t + 1 < cfg.n_steps else self.obs)
+            else:
+                nobs, rew, term, trunc, info = env.step(torch.clamp(act, -1.0, 1.0))     # SB3 clips to the Box bounds
             # bootstrap with V(terminal observation) on time-limit truncation; evaluated for every environment and masked, so
             # that the rollout loop has no device->host synchronisation (rows of environments that did not finish are stale, unused)
             if fused is not None and term.dtype == torch.uint8:
@@ -526,7 +533,8 @@ class PPOTrainer:
                 tv = self.policy.value(sanitize_obs(info["terminal_observation"]))
                 b["rew"][t] = rew + cfg.gamma * tv * only_trunc
                 b["done"][t] = ((term != 0) | (trunc != 0)).float()
-            self.obs.copy_(nobs)
+            if not direct:
+                self.obs.copy_(nobs)
         self.num_timesteps += cfg.n_steps * env.num_envs * self.world
         torch.cuda.synchronize(self.device)
         return time.perf_counter() - t0

@@ -423,3 +423,29 @@ def test_native_permutation_is_a_permutation(n):
         q = a[: n // 4].double().mean().item() / n
         assert 0.45 < q < 0.55, q
     assert L.ackb_ppo_permutation(None, n, 0, 0, None) != 0
+
+
+@pytest.mark.gpu
+def test_rollout_direct_observation_writes_match_copy_path():
+    """collect() with the step kernel writing observations straight into the rollout buffer (obs_out) fills the same buffers,
+    bit for bit, as the path that copies the environment's observation tensor."""
+    from mujoco_playground_b200 import BatchedAckermannEnv
+    from mujoco_playground_b200.ppo import PPOTrainer
+    bufs = []
+    for direct in (True, False):
+        env = BatchedAckermannEnv(300, seed=5, max_episode_steps=6)
+        tr = PPOTrainer(env, PPOConfig(n_steps=8, n_epochs=1, minibatches=2), seed=2)
+        assert tr._env_takes_obs_out
+        tr._env_takes_obs_out = direct
+        tr.collect()
+        tr.collect()
+        bufs.append({k: v.clone() for k, v in tr.buf.items()} | {"last_obs": tr.obs.clone()})
+        env.close()
+    for k in bufs[0]:
+        assert torch.equal(bufs[0][k], bufs[1][k]), k
+    with pytest.raises(ValueError):
+        env = BatchedAckermannEnv(4, seed=1)
+        try:
+            env.step(None, obs_out=torch.zeros(3, env.obs_dim, device=env.device))
+        finally:
+            env.close()
