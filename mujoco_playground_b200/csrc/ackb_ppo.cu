@@ -455,14 +455,18 @@ __device__ __forceinline__ void gather_tile_async(const PpoArgs& a, int tile, fl
       cp_async4(&scbuf[s * 8 + j], src);
     }
   }
-  for (int i = t; i < TT * KP; i += NT) {
-    const int s = i / KP, k = i - s * KP;
-    if (s < ns && k < D) {
-      const int64_t row = rows ? (int64_t)rows[s] : (int64_t)(sbase + s);
-      cp_async4(&xbuf[s * XSW + (k ^ swz(s))], &a.obs[row * D + k]);
-    } else {
+  {   // 8 threads per row, thread (s, kk) owns columns kk, kk + 8, ... of row s: one row pointer per thread
+    static_assert(NT == TT * 8 && KP % 8 == 0, "gather mapping");
+    const int s = t >> 3, kk = t & 7, f = swz(s);
+    float* const dst = xbuf + s * XSW;
+    const int64_t row = s < ns ? (rows ? (int64_t)rows[s] : (int64_t)(sbase + s)) : 0;
+    const float* const src = a.obs + row * D;
+#pragma unroll
+    for (int j = 0; j < KP / 8; ++j) {
+      const int k = kk + 8 * j;
+      if (s < ns && k < D) cp_async4(&dst[k ^ f], &src[k]);
       // padding; with D < KP the last column is 1 for real samples, so that dW1 = dH1^T X also yields db1 (column KP - 1)
-      xbuf[s * XSW + (k ^ swz(s))] = (k == KP - 1 && D < KP && s < ns) ? 1.0f : 0.0f;
+      else dst[k ^ f] = (k == KP - 1 && D < KP && s < ns) ? 1.0f : 0.0f;
     }
   }
   asm volatile("cp.async.commit_group;");
@@ -554,10 +558,13 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel_tc(PpoArgs a) {
     // ---- 1. this tile's observation rows have been fetched asynchronously: wait, round to TF32 (each thread its own elements),
     // then start fetching the next tile into the other buffer
     asm volatile("cp.async.wait_all;");
-    for (int i = t; i < TT * KP; i += NT) {
-      const int s = i / KP, k = i - s * KP;
-      const int xi = s * XSW + (k ^ swz(s));
-      X[xi] = tf32r(X[xi]);
+    {   // same (row, column) ownership as the gather
+      const int s = t >> 3, kk = t & 7, f = swz(s);
+#pragma unroll
+      for (int j = 0; j < KP / 8; ++j) {
+        const int xi = s * XSW + ((kk + 8 * j) ^ f);
+        X[xi] = tf32r(X[xi]);
+      }
     }
     __syncthreads();
     if (tile + (int)gridDim.x < ntiles) {
