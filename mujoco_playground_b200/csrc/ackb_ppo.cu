@@ -685,13 +685,21 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel_tc(PpoArgs a) {
     }
     __syncthreads();
     // ---- 5. dH2 = (dOut W3) * (1 - H2^2)   (TF32-rounded: it feeds two GEMMs)
-    for (int i = t; i < TT * 128; i += NT) {
-      const int s = i >> 7, n = i & 127;
-      const int pn = s * ASW + (n ^ swz(s));
-      const float h = sm[T_H2 + pn];
-      const float gg = (n < H) ? sm[T_DO + s * 4] * sm[T_W3 + n] + sm[T_DO + s * 4 + 1] * sm[T_W3 + H + n]
-                               : sm[T_DO + s * 4 + 2] * sm[T_W3 + 2 * H + (n - H)];
-      sm[T_DH + pn] = tf32r(gg * (1.0f - h * h));
+    {   // thread = one hidden column n, every second sample: the head weights of the column stay in registers
+      static_assert(NT == 256 && T_DO % 4 == 0, "dH2 mapping");
+      const int n = t & 127, s_off = t >> 7;
+      const bool pol = n < H;                       // warp-uniform
+      const float w_a = pol ? sm[T_W3 + n] : sm[T_W3 + 2 * H + (n - H)];
+      const float w_b = pol ? sm[T_W3 + H + n] : 0.0f;
+#pragma unroll 4
+      for (int j = 0; j < TT / 2; ++j) {
+        const int s = s_off + 2 * j;
+        const float4 d = *reinterpret_cast<const float4*>(&sm[T_DO + s * 4]);
+        const int pn = s * ASW + (n ^ swz(s));
+        const float h = sm[T_H2 + pn];
+        const float gg = pol ? d.x * w_a + d.y * w_b : d.z * w_a;
+        sm[T_DH + pn] = tf32r(gg * (1.0f - h * h));
+      }
     }
     __syncthreads();
     // ---- 6. head weights dW3 += dOut^T H2, dW2 += dH2^T H1 and db2 += dH2^T 1 (tensor cores)
