@@ -45,6 +45,8 @@ typedef struct {
   double length_sum;                /* sum of finished episodes' lengths                     */
   unsigned long long obstacle_steps;/* env steps with >= 1 wheel-vs-obstacle contact in their last substep (scene)   */
   unsigned long long contacts_sum;  /* contacts detected in the last substep of every env step, summed (mean ncon)   */
+  unsigned long long bad_state;     /* simulation states reset by the bad-state guard (MuJoCo's mj_checkPos / mj_checkVel /
+                                       mj_checkAcc -> mj_resetData: NaN or |x| > 1e10 in qpos, qvel or qacc)            */
 } ackb_stats_t;
 
 /* Size, in doubles, of the model-constants blob this build expects (layout: ackb_consts.def). */
@@ -58,6 +60,10 @@ int ackb_consts_len(void);
 int ackb_create(const double* consts, size_t consts_len, int num_envs, int device, int dtype, uint64_t seed,
                 int lanes_per_env, ackb_handle** out);
 int ackb_destroy(ackb_handle* h);
+/* Multi-GPU sharding: global id of this handle's environment 0.  Every random stream (goals, spawn jitter, maze
+ * cells, synthetic actions) is keyed by (seed, GLOBAL environment id, episode / step), so a batch sharded over R handles with the
+ * same seed reproduces the single-handle batch bit for bit.  Default 0.  Call before the first ackb_reset. */
+int ackb_set_env_id_base(ackb_handle* h, uint64_t env_id_base);
 
 int ackb_num_envs(const ackb_handle* h);
 int ackb_obs_dim(const ackb_handle* h);   /* 79 for ackermann_robot_v2 and the maze models (ackermann_env.py:95-100), 43 for the scene */

@@ -14,7 +14,7 @@ class AckbStats(ctypes.Structure):
     _fields_ = [("episodes", ctypes.c_ulonglong), ("successes", ctypes.c_ulonglong), ("env_steps", ctypes.c_ulonglong),
                 ("collisions", ctypes.c_ulonglong), ("unsupported", ctypes.c_ulonglong), ("solver_iters", ctypes.c_ulonglong),
                 ("return_sum", ctypes.c_double), ("length_sum", ctypes.c_double),
-                ("obstacle_steps", ctypes.c_ulonglong), ("contacts_sum", ctypes.c_ulonglong)]
+                ("obstacle_steps", ctypes.c_ulonglong), ("contacts_sum", ctypes.c_ulonglong), ("bad_state", ctypes.c_ulonglong)]
 
 
 # every symbol include/ackb.h declares: (restype, argtypes)
@@ -23,6 +23,7 @@ SYMBOLS = {
     "ackb_consts_len": (_i, []),
     "ackb_create": (_i, [_vp, ctypes.c_size_t, _i, _i, _i, _u64, _i, ctypes.POINTER(_vp)]),
     "ackb_destroy": (_i, [_vp]),
+    "ackb_set_env_id_base": (_i, [_vp, _u64]),
     "ackb_num_envs": (_i, [_vp]),
     "ackb_obs_dim": (_i, [_vp]),
     "ackb_dtype": (_i, [_vp]),

@@ -368,6 +368,7 @@ def build_consts(M: dict, *, model_kind: int, max_episode_steps: int = 1000, goa
             spawn_qpos[0:3] = [0, 0, float(M["maze_spawn_z"][0])]   # xy: start cell + noise, drawn per episode
             spawn_qpos[3:7] = [1, 0, 0, 0]
     put("spawn_qpos", spawn_qpos)
+    put("qpos0", M["qpos0"])
     put("spawn_yaw_range", spawn_yaw_range); put("spawn_xy_jitter", spawn_xy_jitter)
     if model_kind == 2:
         g = M["maze_grid"]

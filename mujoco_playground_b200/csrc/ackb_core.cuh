@@ -293,7 +293,13 @@ struct StepDiag {
   int unsupported;  // geometry outside the supported contact set
   int niter;
   int nbox;         // wheel-vs-obstacle contacts among ncon
+  int bad;          // bad-state resets in this env step (mj_checkPos / mj_checkVel / mj_checkAcc)
+  int bad_acc;      // this lane saw a bad solver acceleration in the last substep (consumed by step_env)
 };
+
+// mju_isBad: NaN or magnitude beyond mjMAXVAL (1e10)
+template <typename T>
+ACKB_HD bool is_bad(T x) { return !(Num<T>::abs_(x) <= T(1e10)); }
 
 // index of element (i, j), i >= j, in a packed lower triangle
 ACKB_HD constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
@@ -1552,6 +1558,14 @@ struct Sim {
       }
     }
     diag.niter = iter;
+    {   // mj_checkAcc: a bad solver acceleration resets the simulation state (handled by the caller, see EnvOps::step_env)
+      bool bad = false;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) bad = bad || is_bad(a_sh[i]);
+#pragma unroll 1
+      for (int s = 0; s < WPL; ++s) bad = bad || is_bad(wh[s].a);
+      diag.bad_acc = bad ? 1 : 0;
+    }
 
     // ---- B16 implicit joint damping.  At the minimiser M~ a = tau + J^T f, so MuJoCo's integration acceleration
     // (M~ + hB)^-1 (tau + J^T f) equals a - y with (M~ + hB) y = hB a.  B acts on the hinges only; after eliminating the

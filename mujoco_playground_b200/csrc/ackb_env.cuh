@@ -178,7 +178,7 @@ struct EnvOps {
     const int n = (int)C.settle_steps[0];
     if (n <= 0) return false;
     const T ctrl[4] = {T(0), T(0), T(0), T(0)};
-    StepDiag diag{0, 0, 0, 0};
+    StepDiag diag{};
 #pragma unroll 1
     for (int i = 0; i < n; ++i) {
       Kin<T> k;
@@ -192,6 +192,28 @@ struct EnvOps {
     return true;
   }
 
+  // mj_resetData after a bad state (mj_checkPos / mj_checkVel / mj_checkAcc): qpos = qpos0, velocities and
+  // warm start zero.  MuJoCo also zeroes data.ctrl; the reference env rewrites ctrl at its next step(), so the remaining
+  // substeps of THIS env step run with zero controls.  The episode (goal, odometry reference, step counter) is the env's, not
+  // MuJoCo's, and is left alone -- exactly what happens to the reference, which never notices the warning.
+  ACKB_HD static void reset_data(const Consts<T>& C, State& e, WheelT* wh, int lane) {
+    for (int i = 0; i < 3; ++i) { e.p[i] = C.qpos0[i]; e.vw[i] = e.om[i] = e.warm_l[i] = e.warm_a[i] = T(0); }
+    for (int i = 0; i < 4; ++i) e.q[i] = C.qpos0[3 + i];
+    for (int i = 0; i < 2; ++i) { e.st[i] = C.qpos0[hinge_qadr(i)]; e.dst[i] = e.warm_st[i] = T(0); }
+#pragma unroll 1
+    for (int s = 0; s < WPL; ++s) { wh[s].sp = C.qpos0[hinge_qadr(2 + S::wheel_index(lane, s))]; wh[s].dsp = wh[s].warm = T(0); }
+  }
+  // mj_checkPos + mj_checkVel of one environment (team-uniform result)
+  ACKB_HD static bool state_is_bad(const State& e, const WheelT* wh) {
+    bool bad = false;
+    for (int i = 0; i < 3; ++i) bad = bad || is_bad(e.p[i]) || is_bad(e.vw[i]) || is_bad(e.om[i]);
+    for (int i = 0; i < 4; ++i) bad = bad || is_bad(e.q[i]);
+    for (int i = 0; i < 2; ++i) bad = bad || is_bad(e.st[i]) || is_bad(e.dst[i]);
+#pragma unroll 1
+    for (int s = 0; s < WPL; ++s) bad = bad || is_bad(wh[s].sp) || is_bad(wh[s].dsp);
+    return Tm::sum(bad ? 1 : 0) != 0;
+  }
+
   // one env.step(): frame_skip x mj_step, observation from the kinematics of the last substep (quirk Q3).
   // `emit` is called right after the observation has been written into the sink (before the last substep's dynamics),
   // so that the sink's storage may alias the wheel records.
@@ -203,6 +225,12 @@ struct EnvOps {
     T dist = T(0), minl = T(0);
     for (int s = 0; s < frame_skip; ++s) {
       if (cta_sync) Tm::block_sync();   // CTA-uniform flag (see Team::block_sync)
+      // mj_step begins with mj_checkPos / mj_checkVel: a NaN or |x| > 1e10 anywhere in qpos / qvel resets the data
+      if (state_is_bad(e, wh)) {
+        reset_data(C, e, wh, lane);
+        for (int i = 0; i < 4; ++i) ctrl[i] = T(0);
+        diag.bad += 1;
+      }
       Kin<T> k;
       S::kinematics(e, k);
       if (s == frame_skip - 1) {
@@ -220,8 +248,15 @@ struct EnvOps {
           for (int i = 0; i < WPL; ++i) { wh[i].sp = keep[3 * i]; wh[i].dsp = keep[3 * i + 1]; wh[i].warm = keep[3 * i + 2]; }
         }
       }
-      diag.ncon = 0; diag.nbox = 0;
+      diag.ncon = 0; diag.nbox = 0; diag.bad_acc = 0;
       S::dynamics(C, e, k, ctrl, lane, wh, diag, tap, rec_stride);
+      // mj_checkAcc: a bad qacc resets the data as well.  (MuJoCo then re-runs mj_forward on the reset state and integrates
+      // that step; here the reset state is kept as it is -- one substep of free motion from rest is skipped, documented.)
+      if (Tm::sum(diag.bad_acc) != 0) {
+        reset_data(C, e, wh, lane);
+        for (int i = 0; i < 4; ++i) ctrl[i] = T(0);
+        diag.bad += 1;
+      }
     }
     reward_done(C, ep, dist, minl, out);
   }

@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <new>
 #include <string>
 
@@ -21,11 +22,10 @@ using namespace ackb;
 
 namespace {
 
-__constant__ Consts<float> g_consts_f;
-__constant__ Consts<double> g_consts_d;
-template <typename T> __device__ __forceinline__ const Consts<T>& dev_consts();
-template <> __device__ __forceinline__ const Consts<float>& dev_consts<float>() { return g_consts_f; }
-template <> __device__ __forceinline__ const Consts<double>& dev_consts<double>() { return g_consts_d; }
+// Model constants travel as a __grid_constant__ kernel parameter (2.7 KB in fp32, 5.5 KB in fp64; the parameter space is
+// constant bank 0, so reads are the same broadcast LDC / c[0][..] operands a __constant__ symbol gives).  Every handle owns its
+// own host copy: handles of different models or precisions on one device never share or re-upload anything, and a launch
+// needs no synchronisation (stream-capture safe).
 
 template <typename T>
 struct DevState {
@@ -51,6 +51,7 @@ struct StepArgs {
   int frame_skip, auto_reset, obs_dim;
   uint8_t* done_mask;   // defer_reset: per-env done flag for the masked reset launch that follows
   int defer_reset;      // models with settle steps: the step kernel only marks finished environments, reset_kernel does the rest
+  uint32_t env_base;    // global id of environment 0 of this handle (Philox streams are keyed by the GLOBAL environment id)
   int cta_sync;   // multi-lane kernels: re-converge the CTA once per substep (pays off only when several warps share a scheduler)
 };
 
@@ -149,12 +150,11 @@ struct WheelStore {
 };
 
 template <typename T, int LANES, int NC>
-__global__ void __launch_bounds__(Geo<T, LANES, NC>::kBlock, Geo<T, LANES, NC>::kMinBlocks) step_kernel(DevState<T> st, StepArgs a) {
+__global__ void __launch_bounds__(Geo<T, LANES, NC>::kBlock, Geo<T, LANES, NC>::kMinBlocks) step_kernel(DevState<T> st, StepArgs a, const __grid_constant__ Consts<T> C) {
   using E = EnvOps<T, LANES, NC>;
   using G = Geo<T, LANES, NC>;
   constexpr int EPW = 32 / LANES;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const Consts<T>& C = dev_consts<T>();
   stage_tables(C);
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int env_raw = tid / LANES, lane = tid % LANES;
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(Geo<T, LANES, NC>::kBlock, Geo<T, LANES, NC>::
   ep.episode = st.episode[env];
   float a0, a1;
   if (a.action) { float2 v = reinterpret_cast<const float2*>(a.action)[env]; a0 = v.x; a1 = v.y; }
-  else synth_action(a.seed, a.step_index, (uint32_t)env, &a0, &a1);
+  else synth_action(a.seed, a.step_index, (uint32_t)env + a.env_base, &a0, &a1);
 
   const int env0 = (blockIdx.x * blockDim.x + warp * 32) / LANES;
   int nrow = st.n - env0;
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(Geo<T, LANES, NC>::kBlock, Geo<T, LANES, NC>::
   };
 
   StepOut<T> out;
-  StepDiag diag{0, 0, 0, 0};
+  StepDiag diag{};
   E::step_env(C, e, wh, ep, a0, a1, a.frame_skip, lane, sink, emit, out, diag, (DebugTap<T>*)nullptr, a.cta_sync != 0, G::kSmemWheels ? G::kStride : 0);
   __syncwarp();
 
@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(Geo<T, LANES, NC>::kBlock, Geo<T, LANES, NC>::
     unsigned v_coll = warp_sum_u32(lead && out.collision ? 1u : 0u), v_uns = warp_sum_u32(lead && unsup ? 1u : 0u);
     unsigned v_it = warp_sum_u32(lead ? (unsigned)diag.niter : 0u);
     unsigned v_box = warp_sum_u32(lead && nbox > 0 ? 1u : 0u), v_con = warp_sum_u32(lead ? (unsigned)ncon : 0u);
+    unsigned v_bad = warp_sum_u32(lead ? (unsigned)diag.bad : 0u);
     float r_sum = lead && done ? ret : 0.f, l_sum = lead && done ? (float)ep_len : 0.f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { r_sum += __shfl_xor_sync(0xffffffffu, r_sum, o); l_sum += __shfl_xor_sync(0xffffffffu, l_sum, o); }
@@ -226,6 +227,7 @@ __global__ void __launch_bounds__(Geo<T, LANES, NC>::kBlock, Geo<T, LANES, NC>::
       atomicAdd(&a.stats->solver_iters, (unsigned long long)v_it);
       if (v_box) atomicAdd(&a.stats->obstacle_steps, (unsigned long long)v_box);
       atomicAdd(&a.stats->contacts_sum, (unsigned long long)v_con);
+      if (v_bad) atomicAdd(&a.stats->bad_state, (unsigned long long)v_bad);
     }
   }
 
@@ -241,7 +243,7 @@ __global__ void __launch_bounds__(Geo<T, LANES, NC>::kBlock, Geo<T, LANES, NC>::
         for (int j = lane; j < a.obs_dim; j += LANES) a.terminal_obs[(size_t)env * a.obs_dim + j] = a.obs[(size_t)env * a.obs_dim + j];
     }
     __syncwarp();
-    if (do_reset) E::reset_env(C, e, wh, ep, lane, a.seed, (uint32_t)env);
+    if (do_reset) E::reset_env(C, e, wh, ep, lane, a.seed, (uint32_t)env + a.env_base);
     Kin<T> k;
     E::S::kinematics(e, k);
     T dist, minl;
@@ -276,17 +278,19 @@ __global__ void __launch_bounds__(Geo<T, LANES, NC>::kBlock, Geo<T, LANES, NC>::
 }
 
 template <typename T, int LANES, int NC>
-__global__ void __launch_bounds__(Geo<T, LANES, 2>::kBlock) reset_kernel(DevState<T> st, StepArgs a) {
+__global__ void __launch_bounds__(Geo<T, LANES, 2>::kBlock) reset_kernel(DevState<T> st, StepArgs a, const __grid_constant__ Consts<T> C) {
   using E = EnvOps<T, LANES, NC>;
   using G = Geo<T, LANES, 2>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const Consts<T>& C = dev_consts<T>();
   stage_tables(C);
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int env_raw = tid / LANES, lane = tid % LANES;
   const bool valid = env_raw < st.n;
   const int env = valid ? env_raw : st.n - 1;
   const bool sel = (a.mask ? (a.mask[env] != 0) : true) && valid;   // team-uniform
+  // masked launch (deferred auto-reset of the maze models after every step): a warp without a selected environment leaves at
+  // once -- the settle steps below are three full physics substeps.  All collectives are intra-warp and no CTA barrier follows.
+  if (!__any_sync(0xffffffffu, sel)) return;
   // the reset kernel keeps wheel records in local storage and uses shared memory for the observation rows only
   Wheel<T, NC> wh[G::WPL];
   float* row = reinterpret_cast<float*>(smem_raw) + (size_t)(threadIdx.x / LANES) * a.obs_dim;
@@ -294,7 +298,7 @@ __global__ void __launch_bounds__(Geo<T, LANES, 2>::kBlock) reset_kernel(DevStat
   typename E::State e;
   Episode<T> ep;
   ep.episode = st.episode[env];
-  E::reset_env(C, e, wh, ep, lane, a.seed, (uint32_t)env);
+  E::reset_env(C, e, wh, ep, lane, a.seed, (uint32_t)env + a.env_base);
   T dist, minl;
   if (!E::settle_and_observe(C, e, wh, ep, lane, sink, &dist, &minl)) {   // maze scenes settle first; everything else observes the spawn state
     Kin<T> k;
@@ -315,11 +319,11 @@ __global__ void __launch_bounds__(Geo<T, LANES, 2>::kBlock) reset_kernel(DevStat
   }
 }
 
-__global__ void random_action_kernel(float* action, int n, unsigned long long seed, uint32_t step) {
+__global__ void random_action_kernel(float* action, int n, unsigned long long seed, uint32_t step, uint32_t env_base) {
   int env = blockIdx.x * blockDim.x + threadIdx.x;
   if (env >= n) return;
   float a0, a1;
-  synth_action(seed, step, (uint32_t)env, &a0, &a1);
+  synth_action(seed, step, (uint32_t)env + env_base, &a0, &a1);
   reinterpret_cast<float2*>(action)[env] = make_float2(a0, a1);
 }
 
@@ -336,10 +340,12 @@ struct ackb_handle {
   int cta_sync = -1;            // -1 = auto (by grid size), 0 / 1 forced through ACKB_CTA_SYNC (tuning)
   int zero_copy = 1;            // ackb_step_host: let the kernel access pinned caller buffers directly (ACKB_ZERO_COPY=0 disables)
   unsigned long long seed = 0;
+  uint32_t env_base = 0;        // global id of local environment 0 (ackb_set_env_id_base)
   uint32_t step_index = 0;
   unsigned long long stat_steps = 0;
   unsigned long long launches = 0;
   double* consts_host = nullptr;
+  Consts<float>* consts_f = nullptr;    // the handle's own copy in the kernels' precision (passed by value at every launch)
   void* state = nullptr;        // one allocation holding every SoA array
   size_t elem = 4;
   DevState<float> sf{};
@@ -359,8 +365,6 @@ struct ackb_handle {
 };
 
 namespace {
-ackb_handle* g_const_owner[64] = {nullptr};   // per device: whose constants are in __constant__ memory
-
 int fail(ackb_handle* h, int code, const std::string& msg) {
   g_last_error = msg;
   if (h) h->err = msg;
@@ -387,19 +391,16 @@ void carve(ackb_handle* h, DevState<T>& s) {
   s.ep_return = reinterpret_cast<float*>(s.episode + n);
 }
 
-int ensure_consts(ackb_handle* h, cudaStream_t stream) {
-  if (g_const_owner[h->device] == h) return ACKB_OK;
-  CK(cudaDeviceSynchronize());
-  if (h->dtype == ACKB_F32) {
-    static thread_local Consts<float> tmp;
-    float* d = reinterpret_cast<float*>(&tmp);
-    for (int i = 0; i < kNumConsts; ++i) d[i] = (float)h->consts_host[i];
-    CK(cudaMemcpyToSymbol(g_consts_f, &tmp, sizeof tmp));
-  } else {
-    CK(cudaMemcpyToSymbol(g_consts_d, h->consts_host, sizeof(Consts<double>)));
-  }
-  g_const_owner[h->device] = h;
-  (void)stream;
+template <typename T> const Consts<T>& handle_consts(const ackb_handle* h);
+template <> const Consts<float>& handle_consts<float>(const ackb_handle* h) { return *h->consts_f; }
+template <> const Consts<double>& handle_consts<double>(const ackb_handle* h) { return *reinterpret_cast<const Consts<double>*>(h->consts_host); }
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per (kernel, device) state: remember the largest value set so far
+template <typename K>
+int ensure_smem_attr(ackb_handle* h, K kernel, std::atomic<int>* set_per_device, size_t smem) {
+  if (smem <= 48 * 1024 || (int)smem <= set_per_device[h->device].load(std::memory_order_acquire)) return ACKB_OK;
+  CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  set_per_device[h->device].store((int)smem, std::memory_order_release);
   return ACKB_OK;
 }
 
@@ -412,16 +413,16 @@ int launch_one(ackb_handle* h, DevState<T>& st, const StepArgs& a, cudaStream_t 
     using GR = Geo<T, LANES, 2>;   // the reset kernel has its own geometry (records in local storage)
     const int rgrid = (int)((threads + GR::kBlock - 1) / GR::kBlock);
     const size_t smem = (size_t)(GR::kBlock / LANES) * a.obs_dim * sizeof(float);
-    static bool rattr_done[64] = {false};   // per device: function attributes are per-device state
-    if (!rattr_done[h->device] && smem > 48 * 1024) { CK(cudaFuncSetAttribute(reset_kernel<T, LANES, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); rattr_done[h->device] = true; }
-    reset_kernel<T, LANES, NC><<<rgrid, GR::kBlock, smem, stream>>>(st, a);
+    static std::atomic<int> rattr[64];
+    if (int rc = ensure_smem_attr(h, reset_kernel<T, LANES, NC>, rattr, smem)) return rc;
+    reset_kernel<T, LANES, NC><<<rgrid, GR::kBlock, smem, stream>>>(st, a, handle_consts<T>(h));
   } else {
     const size_t smem = G::smem_bytes(a.obs_dim);
     StepArgs a2 = a;
     a2.cta_sync = h->cta_sync >= 0 ? h->cta_sync : 1;   // measured on B200: faster at every batch size from 4096 to 131072 envs
-    static bool attr_done[64] = {false};    // per device
-    if (!attr_done[h->device] && smem > 48 * 1024) { CK(cudaFuncSetAttribute(step_kernel<T, LANES, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_done[h->device] = true; }
-    step_kernel<T, LANES, NC><<<grid, G::kBlock, smem, stream>>>(st, a2);
+    static std::atomic<int> attr[64];
+    if (int rc = ensure_smem_attr(h, step_kernel<T, LANES, NC>, attr, smem)) return rc;
+    step_kernel<T, LANES, NC><<<grid, G::kBlock, smem, stream>>>(st, a2, handle_consts<T>(h));
   }
   h->launches++;
   CK(cudaGetLastError());
@@ -469,6 +470,8 @@ int ackb_create(const double* consts, size_t consts_len, int num_envs, int devic
   h->elem = dtype == ACKB_F32 ? 4 : 8;
   h->consts_host = new double[kNumConsts];
   memcpy(h->consts_host, consts, sizeof(double) * kNumConsts);
+  h->consts_f = new Consts<float>;
+  for (int i = 0; i < kNumConsts; ++i) reinterpret_cast<float*>(h->consts_f)[i] = (float)consts[i];
   h->obs_dim = (int)reinterpret_cast<const Consts<double>*>(consts)->nbeam[0] + 7;
   CK(cudaSetDevice(device));
   CK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
@@ -497,13 +500,20 @@ int ackb_create(const double* consts, size_t consts_len, int num_envs, int devic
 int ackb_destroy(ackb_handle* h) {
   if (!h) return ACKB_ERR_ARG;
   cudaSetDevice(h->device);
-  if (g_const_owner[h->device] == h) g_const_owner[h->device] = nullptr;
   cudaFree(h->state); cudaFree(h->stats); cudaFree(h->d_action); cudaFree(h->d_obs); cudaFree(h->d_reward);
   cudaFree(h->d_term); cudaFree(h->d_trunc); cudaFree(h->d_done);
   if (h->order_ev) cudaEventDestroy(h->order_ev);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete[] h->consts_host;
+  delete h->consts_f;
   delete h;
+  return ACKB_OK;
+}
+
+int ackb_set_env_id_base(ackb_handle* h, uint64_t env_id_base) {
+  if (!h) return ACKB_ERR_ARG;
+  if (env_id_base + (uint64_t)h->n > 0xffffffffull) return fail(h, ACKB_ERR_ARG, "ackb_set_env_id_base: global environment ids must fit 32 bits");
+  h->env_base = (uint32_t)env_id_base;
   return ACKB_OK;
 }
 
@@ -515,10 +525,8 @@ unsigned long long ackb_launch_count(const ackb_handle* h) { return h ? h->launc
 int ackb_reset(ackb_handle* h, const uint8_t* dev_mask, float* dev_obs, void* stream) {
   if (!h || !dev_obs) return fail(h, ACKB_ERR_ARG, "ackb_reset: null pointer");
   CK(cudaSetDevice(h->device));
-  int rc = ensure_consts(h, (cudaStream_t)stream);
-  if (rc) return rc;
   StepArgs a{};
-  a.obs = dev_obs; a.mask = dev_mask; a.seed = h->seed; a.obs_dim = h->obs_dim; a.stats = h->stats;
+  a.obs = dev_obs; a.mask = dev_mask; a.seed = h->seed; a.obs_dim = h->obs_dim; a.stats = h->stats; a.env_base = h->env_base;
   return h->dtype == ACKB_F32 ? launch_step(h, h->sf, a, (cudaStream_t)stream, true) : launch_step(h, h->sd, a, (cudaStream_t)stream, true);
 }
 
@@ -527,9 +535,9 @@ int ackb_step(ackb_handle* h, const float* dev_action, int frame_skip, int auto_
   if (!h || !dev_obs || !dev_reward || !dev_terminated || !dev_truncated) return fail(h, ACKB_ERR_ARG, "ackb_step: null output pointer");
   if (frame_skip < 1) return fail(h, ACKB_ERR_ARG, "ackb_step: frame_skip must be >= 1");
   CK(cudaSetDevice(h->device));
-  int rc = ensure_consts(h, (cudaStream_t)stream);
-  if (rc) return rc;
+  int rc = ACKB_OK;
   StepArgs a{};
+  a.env_base = h->env_base;
   a.action = dev_action; a.obs = dev_obs; a.reward = dev_reward; a.terminated = dev_terminated; a.truncated = dev_truncated;
   a.terminal_obs = dev_terminal_obs; a.ncon = dev_ncon; a.stats = h->stats; a.seed = h->seed; a.step_index = h->step_index++;
   h->stat_steps += (unsigned long long)h->n;
@@ -542,7 +550,7 @@ int ackb_step(ackb_handle* h, const float* dev_action, int frame_skip, int auto_
   rc = h->dtype == ACKB_F32 ? launch_step(h, h->sf, a, (cudaStream_t)stream, false) : launch_step(h, h->sd, a, (cudaStream_t)stream, false);
   if (rc || !defer) return rc;
   StepArgs r{};
-  r.obs = dev_obs; r.mask = h->d_done; r.seed = h->seed; r.obs_dim = h->obs_dim; r.stats = h->stats;
+  r.obs = dev_obs; r.mask = h->d_done; r.seed = h->seed; r.obs_dim = h->obs_dim; r.stats = h->stats; r.env_base = h->env_base;
   return h->dtype == ACKB_F32 ? launch_step(h, h->sf, r, (cudaStream_t)stream, true) : launch_step(h, h->sd, r, (cudaStream_t)stream, true);
 }
 
@@ -593,7 +601,7 @@ int ackb_step_host(ackb_handle* h, const float* host_action, int frame_skip, int
 int ackb_random_actions(ackb_handle* h, float* dev_action, void* stream) {
   if (!h || !dev_action) return fail(h, ACKB_ERR_ARG, "ackb_random_actions: null pointer");
   CK(cudaSetDevice(h->device));
-  random_action_kernel<<<(h->n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dev_action, h->n, h->seed, h->step_index);
+  random_action_kernel<<<(h->n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dev_action, h->n, h->seed, h->step_index, h->env_base);
   h->launches++;
   CK(cudaGetLastError());
   return ACKB_OK;

@@ -32,7 +32,7 @@ class BatchedAckermannEnv:
                  max_episode_steps: int = 1000, goal_distance_threshold: float = 0.5, collision_threshold: float = 0.15,
                  max_linear_velocity: float = 1.0, max_angular_velocity: float = 1.0, render_mode=None, map_spawner=None,
                  solver_tolerance: Optional[float] = None, spawn_yaw_range: float = 0.0, spawn_xy_jitter: float = 0.0,
-                 model_table: Optional[dict] = None, settle_steps: Optional[int] = None):
+                 model_table: Optional[dict] = None, settle_steps: Optional[int] = None, env_id_base: int = 0):
         if render_mode is not None:
             raise NotImplementedError("rendering is outside the hot path (SURVEY.md section 2)")
         if not torch.cuda.is_available():
@@ -57,6 +57,11 @@ class BatchedAckermannEnv:
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         _lib.check(self.L.ackb_create(self.consts.ctypes.data_as(ctypes.c_void_p), len(self.consts), self.num_envs, dev_index,
                                       _DTYPES[dtype], int(seed), int(lanes_per_env), ctypes.byref(self.h)))
+        # global id of environment 0: random streams are keyed by (seed, GLOBAL env id), so a batch sharded over several
+        # handles / ranks with the same seed equals the single-handle batch
+        self.env_id_base = int(env_id_base)
+        if self.env_id_base:
+            _lib.check(self.L.ackb_set_env_id_base(self.h, self.env_id_base), self.h)
         self.obs_dim = self.L.ackb_obs_dim(self.h)
         n, d = self.num_envs, self.device
         self.obs = torch.empty((n, self.obs_dim), dtype=torch.float32, device=d)

@@ -23,7 +23,7 @@ def rank_seed(seed: int, rank: int) -> int:
 
 
 _KEYS = ("episodes", "successes", "env_steps", "collisions", "unsupported", "solver_iters", "obstacle_steps", "contacts_sum",
-         "return_sum", "length_sum")
+         "bad_state", "return_sum", "length_sum")
 
 
 def reduce_stats(stats: Dict[str, float], device=None, group=None) -> Dict[str, float]:
@@ -33,7 +33,7 @@ def reduce_stats(stats: Dict[str, float], device=None, group=None) -> Dict[str, 
     t = torch.tensor([float(stats.get(k, 0)) for k in _KEYS], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     out = {k: float(v) for k, v in zip(_KEYS, t.tolist())}
-    for k in _KEYS[:8]:
+    for k in _KEYS[:9]:
         out[k] = int(round(out[k]))
     return out
 

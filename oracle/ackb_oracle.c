@@ -122,6 +122,7 @@ typedef struct {
   double sensordata[MAXSEN];
   int solver_niter, solver_lsiter;
   double solver_cost, solver_gradnorm;
+  int nbad;   /* states reset by mj_checkPos / mj_checkVel / mj_checkAcc */
 } OData;
 
 /* ------------------------------------------------------------------------- */
@@ -1059,8 +1060,20 @@ void orc_forward(const OModel* m, OData* d) {
   o_fwd_constraint(m, d);
   memcpy(d->qacc_warmstart, d->qacc, sizeof(double) * m->nv);
 }
+void orc_reset(const OModel* m, OData* d);
+/* mju_isBad: NaN or |x| > mjMAXVAL */
+static int is_bad(double x) { return !(fabs(x) <= 1e10); }
+/* mj_step: mj_checkPos, mj_checkVel -> mj_resetData on a bad number; mj_forward; mj_checkAcc -> mj_resetData +
+   mj_forward; integrate.  `nbad` counts the resets (MuJoCo's warning counters). */
 void orc_step(const OModel* m, OData* d) {
+  int bad = 0, nbad = d->nbad;
+  for (int i = 0; i < m->nq; i++) bad |= is_bad(d->qpos[i]);
+  for (int i = 0; i < m->nv; i++) bad |= is_bad(d->qvel[i]);
+  if (bad) { orc_reset(m, d); d->nbad = ++nbad; }
   orc_forward(m, d);
+  bad = 0;
+  for (int i = 0; i < m->nv; i++) bad |= is_bad(d->qacc[i]);
+  if (bad) { orc_reset(m, d); d->nbad = ++nbad; orc_forward(m, d); }
   o_euler(m, d);
 }
 void orc_step_n(const OModel* m, OData* d, int n) { for (int i = 0; i < n; i++) orc_step(m, d); }
@@ -1102,7 +1115,7 @@ static const Field data_fields[] = {
     DF(qacc_smooth, 0), DF(qacc, 0), DF(qfrc_constraint, 0), DF(ncon, 1), DF(nefc, 1), DF(unsupported_contact, 1),
     DF(efc_type, 1), DF(efc_id, 1), DF(efc_J, 0), DF(efc_pos, 0), DF(efc_margin, 0), DF(efc_frictionloss, 0),
     DF(efc_diagApprox, 0), DF(efc_R, 0), DF(efc_D, 0), DF(efc_aref, 0), DF(efc_force, 0), DF(sensordata, 0),
-    DF(solver_niter, 1), DF(solver_lsiter, 1), DF(solver_cost, 0), DF(solver_gradnorm, 0), {NULL, 0, 0, 0}};
+    DF(solver_niter, 1), DF(solver_lsiter, 1), DF(nbad, 1), DF(solver_cost, 0), DF(solver_gradnorm, 0), {NULL, 0, 0, 0}};
 
 static const Field* find_field(const Field* t, const char* name) {
   for (; t->name; t++) if (!strcmp(t->name, name)) return t;

@@ -41,7 +41,7 @@ void substep(const double* blob, double* qpos, double* qvel, double* warm, const
   E::load_state(acc, 0, e, wh);
   T ctrl[4];
   for (int i = 0; i < 4; ++i) ctrl[i] = (T)ctrl_in[i];
-  StepDiag diag{0, 0, 0, 0};
+  StepDiag diag{};
   DebugTap<T> tap;
   for (int s = 0; s < nsteps; ++s) {
     Kin<T> k;
@@ -54,7 +54,7 @@ void substep(const double* blob, double* qpos, double* qvel, double* warm, const
     for (int i = 0; i < 12; ++i) { tap_out[i] = tap.tau[i]; tap_out[12 + i] = tap.a_smooth[i]; tap_out[24 + i] = tap.a[i]; tap_out[36 + i] = tap.fc[i]; }
     tap_out[48] = tap.niter; tap_out[49] = tap.nls;
   }
-  if (diag_out) { diag_out[0] = diag.ncon; diag_out[1] = diag.unsupported; diag_out[2] = diag.niter; }
+  if (diag_out) { diag_out[0] = diag.ncon; diag_out[1] = diag.unsupported; diag_out[2] = diag.niter; diag_out[3] = diag.bad; }
 }
 
 template <typename T, int NC>
@@ -72,12 +72,12 @@ void env_step(const double* blob, double* qpos, double* qvel, double* warm, doub
   ep.step_count = epi[0]; ep.episode = (uint32_t)epi[1];
   ObsSink sink{obs};
   StepOut<T> so;
-  StepDiag diag{0, 0, 0, 0};
+  StepDiag diag{};
   E::step_env(C, e, wh, ep, action[0], action[1], frame_skip, 0, sink, [] {}, so, diag, (DebugTap<T>*)nullptr);
   E::store_state(acc, 0, e, wh);
   epi[0] = ep.step_count;
   out[0] = so.reward; out[1] = so.terminated; out[2] = so.truncated; out[3] = so.collision; out[4] = so.goal_distance; out[5] = so.min_lidar;
-  if (diag_out) { diag_out[0] = diag.ncon; diag_out[1] = diag.unsupported; diag_out[2] = diag.niter; }
+  if (diag_out) { diag_out[0] = diag.ncon; diag_out[1] = diag.unsupported; diag_out[2] = diag.niter; diag_out[3] = diag.bad; }
 }
 
 template <typename T, int NC>
@@ -126,7 +126,7 @@ void env_step_team(const double* blob, double* qpos, double* qvel, double* warm,
       ep.step_count = epi[0]; ep.episode = (uint32_t)epi[1];
       ObsSink sink{obs};
       StepOut<T> so;
-      StepDiag diag{0, 0, 0, 0};
+      StepDiag diag{};
       E::step_env(C, e, wh, ep, action[0], action[1], frame_skip, lane, sink, [] {}, so, diag, (DebugTap<T>*)nullptr);
       bar.arrive_and_wait();           // every lane finished reading the shared state arrays
       E::store_state(acc, lane, e, wh);

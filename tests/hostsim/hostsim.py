@@ -41,7 +41,7 @@ class HostSim:
         self.epd = np.zeros(4)                 # goal xy, odometry reference xy
         self.epi = np.zeros(2, np.int32)       # step counter, episode counter
         self.obs = np.zeros(int(round(consts_field(consts, "nbeam"))) + 7, np.float32)
-        self.diag = np.zeros(3, np.int32)
+        self.diag = np.zeros(4, np.int32)
         self.tap = np.zeros(50)
 
     def reset(self, seed=0, env_id=0):
@@ -62,12 +62,12 @@ class HostSim:
                                      frame_skip, _p(self.obs), _p(out), _p(self.diag))
             return self.obs.copy(), float(out[0]), bool(out[1]), bool(out[2]), dict(collision=bool(out[3]), goal_distance=float(out[4]),
                                                                                      min_lidar=float(out[5]), ncon=int(self.diag[0]),
-                                                                                     unsupported=int(self.diag[1]), niter=int(self.diag[2]))
+                                                                                     unsupported=int(self.diag[1]), niter=int(self.diag[2]), bad=int(self.diag[3]))
         self.L.hs_env_step(self.f32, _p(self.blob), _p(self.qpos), _p(self.qvel), _p(self.warm), _p(self.epd), _p(self.epi), _p(a),
                            frame_skip, _p(self.obs), _p(out), _p(self.diag))
         return self.obs.copy(), float(out[0]), bool(out[1]), bool(out[2]), dict(collision=bool(out[3]), goal_distance=float(out[4]),
                                                                                  min_lidar=float(out[5]), ncon=int(self.diag[0]),
-                                                                                 unsupported=int(self.diag[1]), niter=int(self.diag[2]))
+                                                                                 unsupported=int(self.diag[1]), niter=int(self.diag[2]), bad=int(self.diag[3]))
 
     def observe(self):
         out = np.zeros(2)

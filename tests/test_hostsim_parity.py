@@ -208,3 +208,28 @@ def test_multi_lane_code_paths_agree_with_single_lane(lanes):
         assert i1["ncon"] == iL["ncon"] and te1 == teL and tr1 == trL and abs(r1 - rL) < 1e-6
         assert np.abs(o1 - oL).max() < 1e-5
     assert np.abs(h1.qpos - hL.qpos).max() < 1e-9 and np.abs(h1.qvel - hL.qvel).max() < 1e-8
+
+
+def test_bad_state_guard_matches_mj_reset_data():
+    """mj_checkPos / mj_checkVel: a NaN or |x| > 1e10 in qpos / qvel makes mj_step reset the data to qpos0
+    before its forward pass; the env above never notices.  Kernel code (host build) and oracle do the same and count it."""
+    c = build_consts(M, model_kind=0, tolerance=1e-12)
+    for poison in ("nan_qvel", "huge_qpos"):
+        h = HostSim(c, False)
+        h.reset(seed=5)
+        o = OracleEnv(M, tolerance=1e-12)
+        o.reset(h.epd[:2])
+        rng = np.random.default_rng(5)
+        for t in range(30):
+            a = rng.uniform(-1, 1, 2).astype(np.float32)
+            if t == 10:
+                if poison == "nan_qvel":
+                    h.qvel[7] = np.nan; o.sim.qvel[7] = np.nan
+                else:
+                    h.qpos[0] = 3e10; o.sim.qpos[0] = 3e10
+            obs, r, te, tr, info = h.step(a)
+            oo, ro, teo, tro, io = o.step(a)
+            assert info["bad"] == (1 if t == 10 else 0)
+            assert np.isfinite(obs).all() and np.abs(obs - oo).max() < 1e-5
+            assert np.abs(h.qpos - o.sim.qpos).max() < 1e-9 and np.abs(h.qvel - o.sim.qvel).max() < 1e-7
+        assert int(o.sim.f("nbad")[0]) == 1
