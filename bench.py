@@ -5,9 +5,13 @@
     python bench.py --impl reference --gpus N --steps K ...   # CPU restatement of the reference loop
 
 A "step" is one env.step() of every environment of the batch = frame_skip physics substeps of 2 ms.
-Workloads (BASELINE.json configs):
-  N = 1 : configs[1] "ackermann flat-floor, 4096 batched envs on 1 B200, random actions, frame_skip=4"
-  N > 1 : configs[3] "ackermann flat-floor, 131072 envs per GPU sharded across 2/4/8 B200" (no data-path collective)
+
+Headline (every N): configs[3] "ackermann flat-floor, 131072 envs per GPU" (weak scaling: the N=1 point of the
+"env-steps/sec at 1/2/4/8 B200" series is the same per-GPU batch, no data-path collective).
+Sub-records of the same JSON line (`sub`), each with its own roofline / e2e:
+  configs[1]  4096 envs on 1 B200, frame_skip 4                       (N = 1 only)
+  configs[2]  obstacle scene, 65536 envs, frame_skip 1 and 4          (N = 1 only)
+  configs[4]  PPO training loop, 65536 envs per GPU, NCCL all-reduce  (every N; TF32/tcgen05 learner, fp32 learner at N = 1)
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -23,29 +27,27 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-ALGO_BYTES_F32 = 650.0   # algorithmic HBM bytes per env-step, fp32 state (SURVEY.md 8d / DESIGN.md)
+ALGO_BYTES_F32 = 650.0   # algorithmic HBM bytes per env-step, fp32 state, 79-float observation (SURVEY.md 8d / DESIGN.md)
 ALGO_BYTES_F64 = 962.0
 
 
-def measured_traffic(dtype, n_envs, fs):
-    """(DRAM bytes, note, warp instructions) per launch of the step kernel from the committed ncu capture of the same
-    configuration, or Nones."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+def measured_traffic(key):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of the same configuration
+    (profiles/traffic.json: key -> {dram_bytes_read, dram_bytes_write, note, profile}), or None."""
     try:
-        d = json.load(open(p)).get(f"{'f32' if dtype == 'float32' else 'f64'}_{n_envs}_fs{fs}")
-        return (d["dram_bytes_read"] + d["dram_bytes_write"], d["note"], d.get("warp_instructions")) if d else (None, None, None)
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(key)
+        return (d["dram_bytes_read"] + d["dram_bytes_write"], f"{d['note']} [{d['profile']}]") if d else (None, None)
     except Exception:
-        return None, None, None
+        return None, None
 
 
-def measured_peak_gbs():
+def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
-        try:
-            return float(json.load(open(p))["hbm_gbs"]), "measured"
-        except Exception:
-            pass
-    return 6650.0, "fallback"
+    try:
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops", 1628.1)), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, 1628.1, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler(threading.Thread):
@@ -117,7 +119,7 @@ def _cpu_init():
     from mujoco_playground_b200.models import load_model
     from oracle.oracle import OracleSim
     M = load_model("v2")
-    sim = OracleSim(M)
+    sim = OracleSim(M, fast=True)              # -O3 -march=native build of the same C source, compiled on this host
     sq = M["qpos0"].copy()
     sq[0:3] = [0, 0, 0.1]
     sim.rollout(200, 4, 1000, 12345, sq)       # warm-up
@@ -141,6 +143,7 @@ class CpuArm:
         import multiprocessing as mp
         from oracle import oracle as _o
         _o.build()
+        _o.build_fast()
         self.procs = procs
         self.pool = mp.get_context("spawn").Pool(procs, initializer=_cpu_init)
         self.calls = 0
@@ -190,71 +193,70 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * wall / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(args, world), "frame_skip": fs, "l2": "n/a (CPU)"},
+        "config": {"workload": f"configs[3]: ackermann flat-floor, random actions, frame_skip={fs} (the CPU arm steps one environment per host core; the per-GPU batch size does not apply)", "frame_skip": fs, "l2": "n/a (CPU)"},
         "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                         "sample": f"{per} env-steps x {cores} processes per step, {args.steps} steps (C restatement of controller + mj_step; "
-                                   "real mujoco is not installable in this image)"},
+                         "sample": f"{per} env-steps x {cores} processes per step, {args.steps} steps (C restatement of controller + mj_step, -O3 -march=native; "
+                                   "this repo's own CPU port -- real mujoco is not installable in this image)"},
         "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
-def workload_name(args, world):
-    if getattr(args, "workload", "flat") == "scene":
-        return (f"configs[2]: ackermann obstacle scene (ackermann_maze_flat.xml), {args.envs or 65536} envs per GPU, AckermannController, "
-                f"spawn yaw U(-pi,pi) + xy jitter 0.12 m, random actions, frame_skip={args.frame_skip}")
-    if args.envs:
-        return f"ackermann flat-floor, {args.envs} envs per GPU, random actions, frame_skip={args.frame_skip}"
-    if world == 1:
-        return "configs[1]: ackermann flat-floor, 4096 batched envs on 1 B200, random actions, frame_skip=4"
-    return f"configs[3]: ackermann flat-floor, 131072 envs per GPU sharded across {world} B200, frame_skip=4"
+
+def algo_bytes(dtype, obs_dim):
+    """Algorithmic HBM bytes per env-step: state 37 reals r/w + goal/ref 4 reals read + counter r/w + action in, obs/reward/flags out."""
+    return (ALGO_BYTES_F32 if dtype == "float32" else ALGO_BYTES_F64) - (79 - obs_dim) * 4
 
 
-# ----------------------------------------------------------------------------------------------------------
-def run_cuda(args, rank, local_rank, world):
+def make_barrier(world, dev):
     import torch
     import torch.distributed as dist
-    from mujoco_playground_b200 import BatchedAckermannEnv
-
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    scene = args.workload == "scene"
-    n_envs = args.envs or (65536 if scene else (4096 if world == 1 else 131072))
-    fs = args.frame_skip
-    kw = dict(model="scene", spawn_yaw_range=3.141592653589793, spawn_xy_jitter=0.12) if scene else {}
-    env = BatchedAckermannEnv(n_envs, device=dev, frame_skip=fs, dtype=args.dtype, seed=1234 + rank, auto_reset=True,
-                              lanes_per_env=args.lanes, **kw)
-    env.reset()
-    # steady state of a long rollout: episode phases staggered uniformly (resets spread over time instead of all
-    # environments resetting in the same step), and the robots already landed on their wheels
-    import numpy as np
-    env.set_episode(step_count=np.random.default_rng(rank).integers(0, 1000, n_envs).astype(np.int32))
-    for _ in range((400 + fs - 1) // fs):
-        env.step(None)
-    env.stats_reset()
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
+    return barrier
 
-    # ---- kernel-resident throughput: synthetic actions generated in the kernel, state resident in HBM --------------
+
+def max_over_ranks(x, world, dev):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def measure_env(name, traffic_key, *, dev, rank, world, local_rank, n_envs, fs, dtype, lanes, steps, warmup, flush, env_kw=None, e2e=True,
+                env_id_base=0):
+    """One env-step workload: device-timed throughput with the state resident in HBM (L2 flushed between timed launches) and the
+    end-to-end figure through ackb_step_host with pinned HOST buffers.  Returns the record (rank 0) or None."""
+    import numpy as np
+    import torch
+    from mujoco_playground_b200 import BatchedAckermannEnv
+    barrier = make_barrier(world, dev)
+    env = BatchedAckermannEnv(n_envs, device=dev, frame_skip=fs, dtype=dtype, seed=1234, auto_reset=True, lanes_per_env=lanes,
+                              env_id_base=env_id_base, **(env_kw or {}))
+    env.reset()
+    # steady state of a long rollout: episode phases staggered uniformly (resets spread over time), robots landed on their wheels
+    env.set_episode(step_count=np.random.default_rng(rank).integers(0, 1000, n_envs).astype(np.int32))
+    for _ in range((400 + fs - 1) // fs):
+        env.step(None)
+    env.stats_reset()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         env.step(None)
     barrier()
     launches0 = env.launch_count
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     barrier()
     t_wall = time.perf_counter()
     for s0, s1 in evs:
-        flush.zero_()                     # evict state from L2 between timed iterations (not timed)
+        flush.zero_()                     # evict the state from L2 between timed iterations (not timed)
         s0.record()
         env.step(None)
         s1.record()
@@ -262,156 +264,188 @@ def run_cuda(args, rank, local_rank, world):
     t_wall = time.perf_counter() - t_wall
     launches = env.launch_count - launches0
     step_ms = [a.elapsed_time(b) for a, b in evs]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
-    total_ms = float(total_ms.item())
-    value = world * n_envs * args.steps / (total_ms * 1e-3)
+    total_ms = max_over_ranks(sum(step_ms), world, dev)
+    value = world * n_envs * steps / (total_ms * 1e-3)
     stats = env.stats()
 
-    # ---- end to end through the C ABI with HOST buffers (H2D actions, D2H obs/reward/flags inside the timed region) ---
-    h_act = torch.empty((n_envs, 2), dtype=torch.float32).uniform_(-1, 1).pin_memory()
-    h_obs = torch.empty((n_envs, env.obs_dim), dtype=torch.float32).pin_memory()
-    h_rew = torch.empty((n_envs,), dtype=torch.float32).pin_memory()
-    h_term = torch.empty((n_envs,), dtype=torch.uint8).pin_memory()
-    h_trunc = torch.empty((n_envs,), dtype=torch.uint8).pin_memory()
-    for _ in range(args.warmup):
-        env.step_host(h_act, h_obs, h_rew, h_term, h_trunc)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        env.step_host(h_act, h_obs, h_rew, h_term, h_trunc)
-    torch.cuda.synchronize(dev)
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = world * n_envs * args.steps / float(e2e_s.item())
-    h2d = n_envs * 2 * 4
-    d2h = n_envs * (env.obs_dim * 4 + 4 + 1 + 1)
+    e2e_rec = None
+    if e2e:
+        # end to end through the C ABI with HOST buffers (H2D actions, D2H obs / reward / flags inside the timed region)
+        h_act = torch.empty((n_envs, 2), dtype=torch.float32).uniform_(-1, 1).pin_memory()
+        h_obs = torch.empty((n_envs, env.obs_dim), dtype=torch.float32).pin_memory()
+        h_rew = torch.empty((n_envs,), dtype=torch.float32).pin_memory()
+        h_term = torch.empty((n_envs,), dtype=torch.uint8).pin_memory()
+        h_trunc = torch.empty((n_envs,), dtype=torch.uint8).pin_memory()
+        for _ in range(warmup):
+            env.step_host(h_act, h_obs, h_rew, h_term, h_trunc)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            env.step_host(h_act, h_obs, h_rew, h_term, h_trunc)
+        torch.cuda.synchronize(dev)
+        e2e_s = max_over_ranks(time.perf_counter() - t0, world, dev)
+        d2h = n_envs * (env.obs_dim * 4 + 4 + 1 + 1)
+        e2e_rec = {"value": world * n_envs * steps / e2e_s, "unit": "env-steps/s", "h2d_bytes_per_step": n_envs * 2 * 4, "d2h_bytes_per_step": d2h,
+                   "host_link_GBps_per_gpu": (d2h + n_envs * 8) * steps / e2e_s / 1e9,
+                   "path": "ackb_step_host, pinned host buffers mapped into the kernel (zero-copy stores over PCIe)"}
     clocks = sampler.summary() if sampler else None
+    obs_dim = env.obs_dim
+    env.close()
+    if rank != 0:
+        return None
+    peak, _, how = measured_peaks()
+    algo = algo_bytes(dtype, obs_dim)
+    avg_launch_s = (sum(step_ms) / len(step_ms)) * 1e-3
+    achieved = algo * n_envs / avg_launch_s / 1e9
+    traffic, traffic_note = measured_traffic(traffic_key)
+    return {
+        "workload": name, "value": value, "unit": "env-steps/s", "ms_per_step": total_ms / steps, "envs_per_gpu": n_envs, "frame_skip": fs,
+        "physics_substeps_per_s": value * fs, "dtype": "f32" if dtype == "float32" else "f64",
+        "l2": "flushed between timed iterations (256 MiB memset, untimed)",
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "traffic_note": traffic_note, "peak_source": how, "kernel": "step_kernel", "algorithmic_bytes_per_env_step": algo,
+                     "algorithmic_bytes_per_launch": algo * n_envs,
+                     "note": "issue/latency-bound kernel (about 3e4 instructions per environment and substep for 650 B): the HBM fraction is "
+                             "small by construction, DESIGN.md section 4; the binding counters are in the ncu summaries under profiles/"},
+        "e2e": e2e_rec, "gpu_launches": int(launches), "clocks": clocks,
+        "solver": {"mean_newton_iters_per_env_step": stats["solver_iters"] / max(1, stats["env_steps"]), "episodes": stats["episodes"],
+                   "unsupported_contact_steps": stats["unsupported"], "bad_state_resets": stats["bad_state"],
+                   "mean_ncon_last_substep": stats["contacts_sum"] / max(1, stats["env_steps"]),
+                   "obstacle_contact_step_fraction": stats["obstacle_steps"] / max(1, stats["env_steps"])},
+        "wall_s_timed_region": t_wall,
+    }
+
+
+PPO_FLOP_PER_SAMPLE = 2 * 2 * (79 * 64 + 64 * 64) * 3 + 2 * 3 * 64 * 3   # both MLPs: forward + dX + dW (2 flop per MAC), heads
+
+
+def measure_ppo(*, dev, rank, world, local_rank, n_envs, iters, warmup, mode, env_id_base=0):
+    """configs[4]: PPO iterations (n_steps env steps of every environment + the update) with the learner arithmetic `mode`
+    ("tf32" tensor cores or "fp32" CUDA cores).  Device-timed with CUDA events; e2e = wall clock of the same loop as a user
+    runs it (PPOTrainer.collect / update, statistics read back to the host every iteration)."""
+    import torch
+    from mujoco_playground_b200 import BatchedAckermannEnv
+    from mujoco_playground_b200.ppo import PPOConfig, PPOTrainer
+    barrier = make_barrier(world, dev)
+    env = BatchedAckermannEnv(n_envs, device=dev, frame_skip=1, seed=1234, env_id_base=env_id_base)
+    cfg = PPOConfig(n_steps=16)
+    tr = PPOTrainer(env, cfg, seed=0, learner_mode=mode)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    for _ in range(max(warmup, 3)):
+        tr.collect(); tr.update()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    roll = upd = 0.0
+    d2h = 0
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(iters):
+        roll += tr.collect()
+        st = tr.update()
+        upd += st["update_s"]
+        d2h += 5 * 4
+    e1.record()
+    barrier()
+    wall = max_over_ranks(time.perf_counter() - t0, world, dev)
+    total_ms = max_over_ranks(e0.elapsed_time(e1), world, dev)
+    clocks = sampler.summary() if sampler else None
+    gk = tr.grad_kernel_seconds(reps=5) if hasattr(tr, "grad_kernel_seconds") else None
+    env.close()
+    if rank != 0:
+        return None
+    per_iter = cfg.n_steps * n_envs * world
+    _, tf_peak, how = measured_peaks()
+    rec = {
+        "workload": f"configs[4]: PPO training loop, {n_envs} envs per GPU x {world} GPU, n_steps={cfg.n_steps}, {cfg.n_epochs} epochs x "
+                    f"{cfg.minibatches} minibatches, frame_skip=1, NCCL gradient all-reduce, learner arithmetic {mode}",
+        "value": per_iter * iters / (total_ms * 1e-3), "unit": "env-steps/s", "ms_per_step": total_ms / iters, "envs_per_gpu": n_envs,
+        "iterations": iters, "learner": mode,
+        "split": {"rollout_ms_per_iteration": 1e3 * roll / iters, "update_ms_per_iteration": 1e3 * upd / iters,
+                  "rollout_env_steps_per_s": per_iter * iters / roll},
+        "e2e": {"value": per_iter * iters / wall, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": d2h // max(1, iters),
+                "path": "PPOTrainer.collect() + update(): the rollout never leaves the device; the update's diagnostics are read back"},
+        "clocks": clocks,
+    }
+    if gk:
+        mb = cfg.n_steps * n_envs // cfg.minibatches
+        fl = PPO_FLOP_PER_SAMPLE * mb
+        peak = tf_peak * 0.5 if mode != "fp32" else 74.5      # TF32 dense = half the measured bf16 rate; fp32 CUDA-core peak 148 SM x 128 x 2 x 1.965 GHz
+        rec["roofline"] = {"bound": "tensor" if mode != "fp32" else "fp32-cuda-core", "achieved": fl / gk / 1e12, "peak": peak, "unit": "TFLOP/s",
+                           "frac": fl / gk / 1e12 / peak, "traffic": measured_traffic(f"ppo_grad_{mode}")[0], "kernel": "ppo_grad_kernel",
+                           "flop_per_sample": PPO_FLOP_PER_SAMPLE, "samples_per_launch": mb, "ms_per_launch": gk * 1e3, "peak_source": how,
+                           "algorithmic_bytes_per_launch": mb * 336,
+                           "note": "TF32 peak taken as half of the measured dense bf16 rate (no TF32 entry in MEASURED_PEAKS.json)"}
+    return rec
+
+
+def run_cuda(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    fs = args.frame_skip
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+    common = dict(dev=dev, rank=rank, world=world, local_rank=local_rank, dtype=args.dtype, lanes=args.lanes, steps=args.steps,
+                  warmup=args.warmup, flush=flush)
+    scene_kw = dict(model="scene", spawn_yaw_range=3.141592653589793, spawn_xy_jitter=0.12)
+    sub = {}
+    if args.workload == "ppo":
+        n_envs = args.envs or 65536
+        head = measure_ppo(dev=dev, rank=rank, world=world, local_rank=local_rank, n_envs=n_envs, iters=min(args.steps, 50), warmup=args.warmup,
+                           mode=args.learner, env_id_base=rank * n_envs)
+    elif args.workload == "scene":
+        n_envs = args.envs or 65536
+        head = measure_env(f"configs[2]: ackermann obstacle scene (ackermann_maze_flat.xml), {n_envs} envs per GPU, AckermannController, spawn yaw "
+                           f"U(-pi,pi) + xy jitter 0.12 m, random actions, frame_skip={fs}", f"scene_{n_envs}_fs{fs}", n_envs=n_envs, fs=fs,
+                           env_kw=scene_kw, env_id_base=rank * n_envs, **common)
+    else:
+        n_envs = args.envs or 131072
+        nm = (f"configs[3]: ackermann flat-floor, 131072 envs per GPU sharded across {world} B200, random actions, frame_skip={fs}" if not args.envs
+              else f"ackermann flat-floor, {n_envs} envs per GPU, random actions, frame_skip={fs}")
+        head = measure_env(nm, f"flat_{n_envs}_fs{fs}", n_envs=n_envs, fs=fs, env_id_base=rank * n_envs, **common)
+        if not args.no_sub and not args.envs:
+            if world == 1:
+                sub["configs[1]"] = measure_env("configs[1]: ackermann flat-floor, 4096 batched envs on 1 B200, random actions, frame_skip=4",
+                                                "flat_4096_fs4", n_envs=4096, fs=4, **common)
+                for f2 in (1, 4):
+                    sub[f"configs[2] fs={f2}"] = measure_env(
+                        f"configs[2]: ackermann obstacle scene (ackermann_maze_flat.xml), 65536 envs on 1 B200, AckermannController, spawn yaw "
+                        f"U(-pi,pi) + xy jitter 0.12 m, random actions, frame_skip={f2}", f"scene_65536_fs{f2}", n_envs=65536, fs=f2,
+                        env_kw=scene_kw, **common)
+            pk = dict(dev=dev, rank=rank, world=world, local_rank=local_rank, n_envs=65536, iters=10, warmup=3)
+            sub["configs[4]"] = measure_ppo(mode="tf32", env_id_base=rank * 65536, **pk)
+            if world == 1:
+                sub["configs[4] fp32 learner"] = measure_ppo(mode="fp32", **pk)
 
     if rank == 0:
-        peak, how = measured_peak_gbs()
-        algo = ALGO_BYTES_F32 if args.dtype == "float32" else ALGO_BYTES_F64
-        if scene:   # 36-beam observation (43 floats): 506 B per env-step in fp32
-            algo -= (79 - env.obs_dim) * 4
-        avg_launch_s = (sum(step_ms) / len(step_ms)) * 1e-3
-        achieved = algo * n_envs / avg_launch_s / 1e9
-        traffic, traffic_note, warp_inst = measured_traffic(args.dtype, n_envs, fs)
-        # the bound that actually binds: warp-instruction issue.  Peak = SMs x 4 schedulers x SM clock.
-        issue = None
-        if warp_inst:
-            sm_clock = (clocks or {}).get("sm_mhz") or 1965.0
-            peak_issue = 148 * 4 * sm_clock * 1e6
-            issue = {"bound": "issue", "unit": "warp-instr/s", "achieved": warp_inst / avg_launch_s, "peak": peak_issue,
-                     "frac": warp_inst / avg_launch_s / peak_issue, "warp_instructions_per_launch": warp_inst,
-                     "note": "instruction count from the committed ncu capture of this configuration, time measured live"}
         line = {
-            "metric": "env-steps/sec", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.dtype == "float32" else "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args, world), "envs_per_gpu": n_envs, "frame_skip": fs, "lanes_per_env": args.lanes,
-                       "l2": "flushed between timed iterations (256 MiB memset, untimed)", "physics_substeps_per_s": value * fs,
-                       "scaling_note": ("N=1 runs configs[1] (4096 envs); N>1 runs configs[3] (131072 envs per GPU, weak scaling). The "
-                                        "single-GPU figure at the configs[3] batch is this line's aux.value at N=1") if not args.envs and not scene else None},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
-                         "peak_source": how, "kernel": "step_kernel", "algorithmic_bytes_per_env_step": algo, "algorithmic_bytes_per_launch": algo * n_envs,
-                         "note": "compute/latency bound kernel: see DESIGN.md (HBM fraction is small by construction)", "issue": issue},
-            "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "solver": {"mean_newton_iters_per_env_step": stats["solver_iters"] / max(1, stats["env_steps"]),
-                       "episodes": stats["episodes"], "unsupported_contact_steps": stats["unsupported"],
-                       "mean_ncon_last_substep": stats["contacts_sum"] / max(1, stats["env_steps"]),
-                       "obstacle_contact_step_fraction": stats["obstacle_steps"] / max(1, stats["env_steps"])},
-            "wall_s_timed_region": t_wall,
+            "metric": "env-steps/sec", "value": head["value"], "unit": "env-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": head.get("dtype", "f32"), "data": "synthetic",
+            "config": {"workload": head["workload"], "envs_per_gpu": head["envs_per_gpu"], "frame_skip": head.get("frame_skip", 1),
+                       "lanes_per_env": args.lanes, "l2": head.get("l2"), "physics_substeps_per_s": head.get("physics_substeps_per_s"),
+                       "rng": "Philox keyed by (seed, global environment id): the sharded batch equals the single-GPU batch"},
+            "roofline": head.get("roofline"), "e2e": head.get("e2e"), "gpu_launches": head.get("gpu_launches"), "clocks": head.get("clocks"),
+            "solver": head.get("solver"), "wall_s_timed_region": head.get("wall_s_timed_region"),
         }
-        if world == 1 and not args.envs and not args.no_aux and not scene:
-            # the same kernel at the per-GPU batch of configs[3] (131072 envs), for context next to the 4096-env headline
-            env.close()
-            big = BatchedAckermannEnv(131072, device=dev, frame_skip=fs, dtype=args.dtype, seed=99, auto_reset=True, lanes_per_env=args.lanes)
-            big.reset()
-            big.set_episode(step_count=np.random.default_rng(7).integers(0, 1000, 131072).astype(np.int32))
-            for _ in range((400 + fs - 1) // fs):
-                big.step(None)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            nb = 30
-            torch.cuda.synchronize(dev)
-            e0.record()
-            for _ in range(nb):
-                big.step(None)
-            e1.record()
-            torch.cuda.synchronize(dev)
-            ms = e0.elapsed_time(e1) / nb
-            line["aux"] = {"workload": f"131072 envs on 1 B200, frame_skip={fs}, back-to-back launches (state 85 MB < L2)",
-                           "value": 131072 / (ms * 1e-3), "unit": "env-steps/s", "ms_per_step": ms,
-                           "roofline_frac": algo * 131072 / (ms * 1e-3) / 1e9 / peak}
-            big.close()
-        if world == 1 and not args.no_cpu_baseline and not scene:
+        if "split" in head:
+            line["split"] = head["split"]
+        if sub:
+            line["sub"] = {k: v for k, v in sub.items() if v is not None}
+        if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             per = max(50, args.cpu_steps // fs)
             v, tmax = cpu_rollout(per, fs, cores)
             line["cpu_baseline"] = {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
                                     "sample": f"{per} env-steps (frame_skip={fs}) on each of {cores} processes, {tmax:.1f} s; C restatement of "
-                                              "controller + mj_step (real mujoco not installable in this image)"}
+                                              "controller + mj_step, -O3 -march=native (real mujoco is not installable in this image, so this is "
+                                              "this repo's own CPU port, not mujoco.mj_step)"}
         print(json.dumps(line), flush=True)
-    env.close()
-    if world > 1:
-        dist.destroy_process_group()
-
-
-def run_ppo(args, rank, local_rank, world):
-    """configs[4]: the PPO training loop (rollout on the batched env + fused learner + NCCL gradient all-reduce).
-    A "step" is one PPO iteration = n_steps env steps of every environment followed by the update."""
-    import torch
-    import torch.distributed as dist
-    from mujoco_playground_b200 import BatchedAckermannEnv
-    from mujoco_playground_b200.ppo import PPOConfig, PPOTrainer
-    from mujoco_playground_b200.shard import rank_seed
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    n_envs = args.envs or 65536
-    env = BatchedAckermannEnv(n_envs, device=dev, frame_skip=1, seed=rank_seed(1234, rank))
-    cfg = PPOConfig(n_steps=16)
-    tr = PPOTrainer(env, cfg, seed=0)
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    for _ in range(max(args.warmup, 3)):
-        tr.collect(); tr.update()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    steps = min(args.steps, 50)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    roll = upd = 0.0
-    e0.record()
-    for _ in range(steps):
-        roll += tr.collect()
-        upd += tr.update()["update_s"]
-    e1.record()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize(dev)
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    total_ms = float(ms.item())
-    clocks = sampler.summary() if sampler else None
-    if rank == 0:
-        per_iter = cfg.n_steps * n_envs * world
-        print(json.dumps({
-            "metric": "env-steps/sec", "value": per_iter * steps / (total_ms * 1e-3), "unit": "env-steps/s", "n_gpus": world, "steps": steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 simulator, TF32 tensor-core learner (fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": f"configs[4]: PPO training loop, {n_envs} envs per GPU x {world} GPU, n_steps=16, 10 epochs x 4 minibatches, "
-                                   "frame_skip=1, NCCL gradient all-reduce", "envs_per_gpu": n_envs},
-            "split": {"rollout_ms_per_iteration": 1e3 * roll / steps, "update_ms_per_iteration": 1e3 * upd / steps,
-                      "rollout_env_steps_per_s": per_iter * steps / roll},
-            "clocks": clocks}), flush=True)
-    env.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -419,18 +453,19 @@ def run_ppo(args, rank, local_rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=2000)
-    ap.add_argument("--warmup", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--envs", type=int, default=0, help="override environments per GPU")
     ap.add_argument("--frame-skip", type=int, default=4)
     ap.add_argument("--dtype", default="float32", choices=["float32", "float64"])
     ap.add_argument("--lanes", type=int, default=0, help="lanes per env: 0 = auto (1 for >= 32768 envs, else 4)")
-    ap.add_argument("--no-aux", action="store_true", help="skip the extra large-batch measurement at N=1")
+    ap.add_argument("--no-sub", action="store_true", help="skip the sub-records (configs[1], [2], [4])")
     ap.add_argument("--cpu-steps", type=int, default=800000, help="physics substeps per CPU process for the CPU arm sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--learner", default="tf32", choices=["tf32", "fp32"], help="--workload ppo: learner arithmetic")
     ap.add_argument("--workload", default="flat", choices=["flat", "scene", "ppo"],
-                    help="flat = configs[1]/[3] (default), scene = configs[2], ppo = configs[4] (training loop)")
+                    help="flat = configs[3] headline + sub-records (default), scene = configs[2], ppo = configs[4] (training loop)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "cuda" else args.warmup
     rank = int(os.environ.get("RANK", 0))
@@ -438,8 +473,6 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":
         run_reference(args, rank, world)
-    elif args.workload == "ppo":
-        run_ppo(args, rank, local_rank, world)
     else:
         run_cuda(args, rank, local_rank, world)
 

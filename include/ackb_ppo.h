@@ -37,6 +37,12 @@ int ackb_ppo_minibatch_grad(const float* obs, const float* act, const float* old
                             const int64_t* idx, int mb, int obs_dim, const float* adv_mean_std, const float* params, float* grads,
                             float* diag, float clip_range, float vf_coef, float ent_coef, void* stream);
 
+/* Same call with the arithmetic chosen per call (nothing process-wide is read or written): one of ACKB_PPO_MODE_*. */
+enum { ACKB_PPO_MODE_DEFAULT = -1, ACKB_PPO_MODE_FP32 = 0, ACKB_PPO_MODE_TF32 = 1 };
+int ackb_ppo_minibatch_grad_mode(const float* obs, const float* act, const float* old_logp, const float* adv, const float* ret,
+                                 const int64_t* idx, int mb, int obs_dim, const float* adv_mean_std, const float* params, float* grads,
+                                 float* diag, float clip_range, float vf_coef, float ent_coef, int mode, void* stream);
+
 /* Rollout side (SB3 policy.forward() inside collect_rollouts): value[n] = V(obs) and, unless value_only, mean[n][2] = pi(obs);
  * if `action` is given also a sample action = mean + exp(log_std) * eps (eps ~ N(0,1), Philox keyed by (seed, step, row)) and,
  * if `logp` is given, its log-probability.  mean / action / logp may be NULL.  TF32 tensor-core tiles.  Asynchronous on `stream`. */
@@ -57,6 +63,9 @@ int ackb_ppo_permutation(int64_t* perm, long long n, uint64_t seed, uint32_t str
  * adv_mean_std operand of ackb_ppo_minibatch_grad (SB3 normalises advantages per minibatch, ppo.py train()).  Calls on one
  * device share a pair of device-side accumulators: issue them on one stream (or otherwise ordered). */
 int ackb_ppo_adv_stats(const float* adv, const int64_t* idx, int n, float* mean_std, void* stream);
+/* Same with caller-owned accumulators: `workspace` = 3 doubles of device memory, zeroed once by the caller (the call leaves them
+ * zeroed).  Learners with their own workspace may run concurrently on one device. */
+int ackb_ppo_adv_stats_ws(const float* adv, const int64_t* idx, int n, float* mean_std, double* workspace, void* stream);
 
 /* Optimiser step on the flat parameter vector: global-norm clipping of grads to max_grad_norm (torch.nn.utils.clip_grad_norm_)
  * followed by Adam (torch.optim.Adam without weight decay / amsgrad: SB3's PPO optimiser).  exp_avg / exp_avg_sq / step are the

@@ -1134,10 +1134,11 @@ __device__ __forceinline__ double block_sum_1024(double v, double* scratch) {
 // mean and unbiased standard deviation (torch.Tensor.std) of the advantages of one minibatch: every CTA adds its partial sums
 // (double) to two device-scope accumulators, the last CTA to finish writes the result and clears them for the next call
 // (calls on one device must not overlap: they share the accumulators)
-__device__ double g_adv_acc[2] = {0.0, 0.0};
-__device__ unsigned g_adv_done = 0;
+__device__ double g_adv_ws[3] = {0.0, 0.0, 0.0};   // default workspace of ackb_ppo_adv_stats (one learner per device, one stream)
 __global__ void __launch_bounds__(256) adv_stats_kernel(const float* __restrict__ adv, const int64_t* __restrict__ idx, int n,
-                                                        float* __restrict__ mean_std) {
+                                                        float* __restrict__ mean_std, double* __restrict__ ws) {
+  double* g_adv_acc = ws;                                           // [0..1]: sum, sum of squares
+  unsigned* g_adv_done_p = reinterpret_cast<unsigned*>(ws + 2);     // CTAs finished
   __shared__ double sh[2][8];
   __shared__ bool last;
   double s = 0.0, q = 0.0;
@@ -1154,14 +1155,14 @@ __global__ void __launch_bounds__(256) adv_stats_kernel(const float* __restrict_
     for (int w = 0; w < 8; ++w) { ts += sh[0][w]; tq += sh[1][w]; }
     atomicAdd(&g_adv_acc[0], ts); atomicAdd(&g_adv_acc[1], tq);
     __threadfence();
-    last = atomicAdd(&g_adv_done, 1u) == gridDim.x - 1;
+    last = atomicAdd(g_adv_done_p, 1u) == gridDim.x - 1;
     if (last) {
       __threadfence();
       const double S = atomicAdd(&g_adv_acc[0], 0.0), Q = atomicAdd(&g_adv_acc[1], 0.0);
       const double mean = S / (double)n;
       const double var = (Q - S * mean) / (double)(n > 1 ? n - 1 : 1);
       mean_std[0] = (float)mean; mean_std[1] = (float)sqrt(var > 0.0 ? var : 0.0);
-      g_adv_acc[0] = 0.0; g_adv_acc[1] = 0.0; g_adv_done = 0u;
+      g_adv_acc[0] = 0.0; g_adv_acc[1] = 0.0; *g_adv_done_p = 0u;
       __threadfence();
     }
   }
@@ -1204,6 +1205,13 @@ int ackb_ppo_set_mode(int tensor_cores) { g_use_tc = tensor_cores ? 1 : 0; retur
 int ackb_ppo_minibatch_grad(const float* obs, const float* act, const float* old_logp, const float* adv, const float* ret,
                             const int64_t* idx, int mb, int obs_dim, const float* adv_mean_std, const float* params, float* grads,
                             float* diag, float clip_range, float vf_coef, float ent_coef, void* stream) {
+  return ackb_ppo_minibatch_grad_mode(obs, act, old_logp, adv, ret, idx, mb, obs_dim, adv_mean_std, params, grads, diag, clip_range, vf_coef,
+                                      ent_coef, ACKB_PPO_MODE_DEFAULT, stream);
+}
+
+int ackb_ppo_minibatch_grad_mode(const float* obs, const float* act, const float* old_logp, const float* adv, const float* ret,
+                                 const int64_t* idx, int mb, int obs_dim, const float* adv_mean_std, const float* params, float* grads,
+                                 float* diag, float clip_range, float vf_coef, float ent_coef, int mode, void* stream) {
   if (!obs || !act || !old_logp || !adv || !ret || !adv_mean_std || !params || !grads || !diag || mb <= 0) return ACKB_ERR_ARG;
   if (obs_dim <= 0 || obs_dim > KP) return ACKB_ERR_ARG;
   cudaStream_t s = (cudaStream_t)stream;
@@ -1212,7 +1220,8 @@ int ackb_ppo_minibatch_grad(const float* obs, const float* act, const float* old
   if (cudaGetDevice(&dev) != cudaSuccess) return ACKB_ERR_NO_DEVICE;
   // ACKB_PPO_TC=0 (or ackb_ppo_set_mode(0)) selects the fp32 CUDA-core kernel; default: TF32 tensor-core kernel
   if (g_use_tc < 0) { const char* ev = getenv("ACKB_PPO_TC"); g_use_tc = ev ? (atoi(ev) != 0) : 1; }
-  const int use_tc = g_use_tc;
+  if (mode != ACKB_PPO_MODE_DEFAULT && mode != ACKB_PPO_MODE_FP32 && mode != ACKB_PPO_MODE_TF32) return ACKB_ERR_ARG;
+  const int use_tc = mode == ACKB_PPO_MODE_DEFAULT ? g_use_tc : (mode == ACKB_PPO_MODE_TF32 ? 1 : 0);
   const size_t smem = (size_t)(use_tc ? T_TOTAL : S_TOTAL) * sizeof(float);
   if (dev < 64 && !attr_done[dev]) {
     if (cudaFuncSetAttribute(ppo_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(S_TOTAL * sizeof(float))) != cudaSuccess) return ACKB_ERR_CUDA;
@@ -1241,11 +1250,17 @@ int ackb_ppo_permutation(int64_t* perm, long long n, uint64_t seed, uint32_t str
 }
 
 int ackb_ppo_adv_stats(const float* adv, const int64_t* idx, int n, float* mean_std, void* stream) {
-  if (!adv || !mean_std || n <= 0) return ACKB_ERR_ARG;
+  double* ws = nullptr;
+  if (cudaGetSymbolAddress((void**)&ws, g_adv_ws) != cudaSuccess) return ACKB_ERR_CUDA;
+  return ackb_ppo_adv_stats_ws(adv, idx, n, mean_std, ws, stream);
+}
+
+int ackb_ppo_adv_stats_ws(const float* adv, const int64_t* idx, int n, float* mean_std, double* workspace, void* stream) {
+  if (!adv || !mean_std || !workspace || n <= 0) return ACKB_ERR_ARG;
   int blocks = (n + 1023) / 1024;                 // >= 4 values per thread
   if (blocks > 296) blocks = 296;
   if (blocks < 1) blocks = 1;
-  adv_stats_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(adv, idx, n, mean_std);
+  adv_stats_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(adv, idx, n, mean_std, workspace);
   return cudaGetLastError() == cudaSuccess ? ACKB_OK : ACKB_ERR_CUDA;
 }
 

@@ -256,10 +256,14 @@ class FusedMinibatchStep:
     flat vector: one kernel (ackb_ppo_clip_adam) on torch's own optimiser-state tensors, or torch ops if the optimiser is not a
     capturable plain Adam.  Same arithmetic as the eager loop of ppo_update up to fp32 summation order (tests/test_ppo.py)."""
 
-    def __init__(self, policy: ActorCritic, opt: torch.optim.Optimizer, cfg: PPOConfig, obs_dim: int, device):
+    MODES = {"default": -1, "fp32": 0, "tf32": 1}
+
+    def __init__(self, policy: ActorCritic, opt: torch.optim.Optimizer, cfg: PPOConfig, obs_dim: int, device, mode: str = "tf32"):
         import ctypes
         from . import _lib
         self.L, self.ct = _lib.load(), ctypes
+        # arithmetic of the gradient kernel, chosen per learner and passed with every call (include/ackb_ppo.h: ACKB_PPO_MODE_*)
+        self.mode = self.MODES[os.environ.get("ACKB_PPO_MODE", mode)]
         self.policy, self.opt, self.cfg, self.obs_dim, self.device = policy, opt, cfg, obs_dim, device
         pe, ve = policy.mlp_extractor["policy_net"], policy.mlp_extractor["value_net"]
         self.order = [pe[0].weight, pe[0].bias, pe[2].weight, pe[2].bias, ve[0].weight, ve[0].bias, ve[2].weight, ve[2].bias,
@@ -286,6 +290,7 @@ class FusedMinibatchStep:
             self.params = [self.flat_param]
         self.diag = torch.zeros(5, device=device, dtype=torch.float32)
         self.adv_stats = torch.zeros(2, device=device, dtype=torch.float32)
+        self.adv_ws = torch.zeros(3, device=device, dtype=torch.float64)     # this learner's own accumulators (ackb_ppo_adv_stats_ws)
         # optimiser step as one kernel (ackb_ppo_clip_adam) on torch's own Adam state tensors, so that opt.state_dict() stays the
         # checkpoint format; needs the flat parameter and a device-side step counter (capturable=True), plain Adam only
         g = opt.param_groups[0]
@@ -436,13 +441,13 @@ class FusedMinibatchStep:
         ptr = lambda t: c.c_void_p(t.data_ptr())
         view, n, rows = self._resolve(batch, idx)
         stream = c.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        rc = self.L.ackb_ppo_adv_stats(ptr(view["adv"]), ptr(rows) if rows is not None else None, n, ptr(self.adv_stats), stream)
+        rc = self.L.ackb_ppo_adv_stats_ws(ptr(view["adv"]), ptr(rows) if rows is not None else None, n, ptr(self.adv_stats), ptr(self.adv_ws), stream)
         if rc != 0:
             raise RuntimeError(f"ackb_ppo_adv_stats failed with code {rc}")
-        rc = self.L.ackb_ppo_minibatch_grad(ptr(view["obs"]), ptr(view["act"]), ptr(view["logp"]), ptr(view["adv"]), ptr(view["ret"]),
-                                            ptr(rows) if rows is not None else None, n, self.obs_dim, ptr(self.adv_stats),
-                                            ptr(self.flat_p), ptr(self.flat_g), ptr(self.diag), cfg.clip_range, cfg.vf_coef,
-                                            cfg.ent_coef, stream)
+        rc = self.L.ackb_ppo_minibatch_grad_mode(ptr(view["obs"]), ptr(view["act"]), ptr(view["logp"]), ptr(view["adv"]), ptr(view["ret"]),
+                                                 ptr(rows) if rows is not None else None, n, self.obs_dim, ptr(self.adv_stats),
+                                                 ptr(self.flat_p), ptr(self.flat_g), ptr(self.diag), cfg.clip_range, cfg.vf_coef,
+                                                 cfg.ent_coef, self.mode, stream)
         if rc != 0:
             raise RuntimeError(f"ackb_ppo_minibatch_grad failed with code {rc}")
 
@@ -473,7 +478,8 @@ class FusedMinibatchStep:
 class PPOTrainer:
     """Rollout collection on the batched CUDA environment + PPO updates; one instance per rank."""
 
-    def __init__(self, env, cfg: PPOConfig = PPOConfig(), seed: int = 0, use_cuda_graphs: bool = True, learner: str = "fused"):
+    def __init__(self, env, cfg: PPOConfig = PPOConfig(), seed: int = 0, use_cuda_graphs: bool = True, learner: str = "fused",
+                 learner_mode: str = "tf32"):
         self.env, self.cfg = env, cfg
         self.device = env.device
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
@@ -501,7 +507,36 @@ class PPOTrainer:
         self._env_takes_obs_out = "obs_out" in inspect.signature(env.step).parameters
         self._adv, self._ret = torch.empty((T, N), **f), torch.empty((T, N), **f)    # persistent: CUDA graphs are captured on them
         if self.learner == "fused":     # flat parameter buffers exist from the start: the rollout forward uses them too
-            self.graphed = FusedMinibatchStep(self.policy, self.opt, cfg, D, self.device)
+            self.graphed = FusedMinibatchStep(self.policy, self.opt, cfg, D, self.device, mode=learner_mode)
+
+    def grad_kernel_seconds(self, reps: int = 5) -> Optional[float]:
+        """Average device time of ONE launch of the minibatch-gradient kernel on the current rollout (CUDA events on the launching
+        stream; weights and gradients are left untouched apart from flat_g / diag, which the next update overwrites)."""
+        f = self.graphed
+        if not isinstance(f, FusedMinibatchStep) or getattr(f, "_perm", None) is None:
+            return None
+        b = self.buf
+        flat = dict(obs=b["obs"].flatten(0, 1), act=b["act"].flatten(0, 1), logp=b["logp"].flatten(), adv=self._adv.flatten(), ret=self._ret.flatten())
+        n = flat["obs"].shape[0]
+        mb = max(1, n // self.cfg.minibatches)
+        c = f.ct
+        ptr = lambda t: c.c_void_p(t.data_ptr())
+        rows = f._perm[:mb]
+        stream = c.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        def launch():
+            rc = f.L.ackb_ppo_minibatch_grad_mode(ptr(flat["obs"]), ptr(flat["act"]), ptr(flat["logp"]), ptr(flat["adv"]), ptr(flat["ret"]), ptr(rows),
+                                                  mb, f.obs_dim, ptr(f.adv_stats), ptr(f.flat_p), ptr(f.flat_g), ptr(f.diag), self.cfg.clip_range,
+                                                  self.cfg.vf_coef, self.cfg.ent_coef, f.mode, stream)
+            assert rc == 0
+        launch()
+        torch.cuda.synchronize(self.device)
+        e0.record()
+        for _ in range(reps):
+            launch()
+        e1.record()
+        torch.cuda.synchronize(self.device)
+        return e0.elapsed_time(e1) * 1e-3 / reps
 
     @torch.no_grad()
     def collect(self) -> float:

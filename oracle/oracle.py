@@ -13,7 +13,21 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "liback_oracle.so")
+def _cpu_tag() -> str:
+    """Identity of this host's CPU (model + ISA flags): a -march=native binary built elsewhere must never be loaded here."""
+    import hashlib
+    try:
+        txt = open("/proc/cpuinfo").read()
+        key = "".join(sorted({ln.split(":", 1)[1].strip() for ln in txt.splitlines() if ln.startswith(("model name", "flags"))}))
+    except OSError:
+        key = "unknown"
+    return hashlib.sha1(key.encode()).hexdigest()[:10]
+
+
+# -O3 -march=native build for the TIMED CPU baseline (bench.py only), one file per host CPU type
+_FAST_PATH = os.path.join(_HERE, f"liback_oracle_native_{_cpu_tag()}.so")
 _lib = None
+_libs = {}
 
 
 def build(force: bool = False) -> str:
@@ -23,11 +37,20 @@ def build(force: bool = False) -> str:
     return _LIB_PATH
 
 
-def lib():
+def build_fast(force: bool = False) -> str:
+    """Timed-baseline build: same source, -O3 -march=native (compiled on the machine that runs it).  The checker build keeps
+    -O2 -ffp-contract=off so that parity tests do not depend on the host's vector ISA."""
+    src = os.path.join(_HERE, "ackb_oracle.c")
+    if force or not os.path.exists(_FAST_PATH) or os.path.getmtime(_FAST_PATH) < os.path.getmtime(src):
+        subprocess.check_call(["gcc", "-O3", "-march=native", "-fPIC", "-fno-fast-math", "-shared", "-o", _FAST_PATH, src, "-lm"])
+    return _FAST_PATH
+
+
+def lib(fast: bool = False):
     global _lib
-    if _lib is None:
-        build()
-        L = ctypes.CDLL(_LIB_PATH)
+    if fast not in _libs:
+        path = build_fast() if fast else build()
+        L = ctypes.CDLL(path)
         L.orc_model_new.restype = ctypes.c_void_p
         L.orc_data_new.restype = ctypes.c_void_p
         for fn in (L.orc_forward, L.orc_step, L.orc_reset):
@@ -40,8 +63,10 @@ def lib():
         L.orc_contact.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
         L.orc_rollout.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_int, ctypes.c_int, ctypes.c_ulonglong, ctypes.c_void_p]
         L.orc_rollout.restype = ctypes.c_long
-        _lib = L
-    return _lib
+        _libs[fast] = L
+        if not fast:
+            _lib = L
+    return _libs[fast]
 
 
 def _view(fn, handle, name):
@@ -59,8 +84,9 @@ _SCALARS = ["nq", "nv", "nu", "nbody", "njnt", "ngeom", "nsite", "neq", "nsensor
 class OracleSim:
     """One environment's MjModel/MjData analogue driven by the C oracle."""
 
-    def __init__(self, model: dict, tolerance: float | None = None):
-        L = lib()
+    def __init__(self, model: dict, tolerance: float | None = None, fast: bool = False):
+        L = lib(fast)
+        self._L = L
         self.model = model
         self.m = ctypes.c_void_p(L.orc_model_new())
         self.d = ctypes.c_void_p(L.orc_data_new())
@@ -86,17 +112,17 @@ class OracleSim:
 
     def __del__(self):
         try:
-            lib().orc_free(self.m)
-            lib().orc_free(self.d)
+            self._L.orc_free(self.m)
+            self._L.orc_free(self.d)
         except Exception:
             pass
 
     def f(self, name):
         """NumPy view (no copy) of a data field at full capacity."""
-        return _view(lib().orc_data_field, self.d, name)
+        return _view(self._L.orc_data_field, self.d, name)
 
     def mf(self, name):
-        return _view(lib().orc_model_field, self.m, name)
+        return _view(self._L.orc_model_field, self.m, name)
 
     # --- convenience views ------------------------------------------------------------------
     @property
@@ -140,13 +166,13 @@ class OracleSim:
         return int(self.f("nefc")[0])
 
     def qM(self):
-        maxv = lib().orc_maxv()
+        maxv = self._L.orc_maxv()
         return self.f("qM").reshape(maxv, maxv)[: self.nv, : self.nv].copy()
 
     def efc(self, name):
         n = self.nefc
         if name == "J":
-            maxv = lib().orc_maxv()
+            maxv = self._L.orc_maxv()
             return self.f("efc_J")[: n * maxv].reshape(n, maxv)[:, : self.nv].copy()
         return self.f("efc_" + name)[:n].copy()
 
@@ -154,7 +180,7 @@ class OracleSim:
         out = []
         buf = (ctypes.c_double * 18)()
         for i in range(self.ncon):
-            lib().orc_contact(self.d, i, buf)
+            self._L.orc_contact(self.d, i, buf)
             a = np.array(buf)
             out.append(dict(geom1=int(a[0]), geom2=int(a[1]), dim=int(a[2]), exclude=int(a[3]), dist=a[4],
                             pos=a[5:8].copy(), frame=a[8:17].reshape(3, 3).copy(), mu=a[17]))
@@ -162,15 +188,15 @@ class OracleSim:
 
     # --- stepping ---------------------------------------------------------------------------
     def reset(self):
-        lib().orc_reset(self.m, self.d)
+        self._L.orc_reset(self.m, self.d)
 
     def forward(self):
-        lib().orc_forward(self.m, self.d)
+        self._L.orc_forward(self.m, self.d)
 
     def step(self, n: int = 1):
-        lib().orc_step_n(self.m, self.d, n)
+        self._L.orc_step_n(self.m, self.d, n)
 
     def rollout(self, n_steps: int, frame_skip: int = 1, max_steps: int = 1000, seed: int = 0, spawn_qpos=None) -> int:
         """C loop: random action -> BicycleController -> frame_skip x step, with episode resets (bench CPU baseline)."""
         sq = np.ascontiguousarray(self.model["qpos0"] if spawn_qpos is None else spawn_qpos, dtype=np.float64)
-        return int(lib().orc_rollout(self.m, self.d, n_steps, frame_skip, max_steps, seed, sq.ctypes.data_as(ctypes.c_void_p)))
+        return int(self._L.orc_rollout(self.m, self.d, n_steps, frame_skip, max_steps, seed, sq.ctypes.data_as(ctypes.c_void_p)))

@@ -186,7 +186,7 @@ def test_fused_gradient_kernel_matches_autograd(obs_dim, n, tc, tol):
     # fused kernel (lr = 0: the optimiser step inside run() must not move the weights)
     opt = torch.optim.SGD(pol.parameters(), lr=0.0)
     f = FusedMinibatchStep(pol, opt, cfg, obs_dim, dev)
-    f.L.ackb_ppo_set_mode(tc)                      # 0: fp32 CUDA cores, 1: TF32 tensor cores (fp32 accumulation)
+    f.mode = tc                      # 0: fp32 CUDA cores, 1: TF32 tensor cores (fp32 accumulation)
     f.cfg = PPOConfig(max_grad_norm=1e30)          # no clipping: compare raw gradients
     f.run(batch, idx, world=1)
     torch.cuda.synchronize()
@@ -198,7 +198,7 @@ def test_fused_gradient_kernel_matches_autograd(obs_dim, n, tc, tol):
     assert abs(d[0] - pg.item()) < dt * max(1, abs(pg.item())) and abs(d[1] - vl.item()) < dt * vl.item()
     assert abs(d[2] - ent.mean().item()) < 1e-5 and abs(d[4] - clip_frac) < (1e-6 if tc == 0 else 5e-3)
     assert abs(d[3] - ((ratio - 1) - (logp - old_logp)).mean().item()) < 10 * dt * max(1.0, abs(d[3]))
-    f.L.ackb_ppo_set_mode(1)
+    f.mode = 1
 
 
 @pytest.mark.gpu
@@ -217,11 +217,11 @@ def test_fused_learner_update_matches_eager_update():
     opt_a = torch.optim.Adam(pol_a.parameters(), lr=cfg.learning_rate, eps=cfg.adam_eps)
     opt_b = torch.optim.Adam(pol_b.parameters(), lr=cfg.learning_rate, eps=cfg.adam_eps)
     f = FusedMinibatchStep(pol_b, opt_b, cfg, D, dev)
-    f.L.ackb_ppo_set_mode(0)                       # fp32 CUDA-core arithmetic for the tight comparison with the eager loop
+    f.mode = 0                       # fp32 CUDA-core arithmetic for the tight comparison with the eager loop
     # third copy: the same fused step replayed from CUDA graphs (capturable Adam)
     pol_c = copy.deepcopy(pol_a)
     opt_c = torch.optim.Adam(pol_c.parameters(), lr=cfg.learning_rate, eps=cfg.adam_eps, capturable=True)
-    fc = FusedMinibatchStep(pol_c, opt_c, cfg, D, dev)
+    fc = FusedMinibatchStep(pol_c, opt_c, cfg, D, dev, mode="fp32")
     fc.capture(fc.shuffle_epoch(batch, torch.arange(n, device=dev)), [(i * (n // 4), n // 4) for i in range(4)])
     for pa, pc in zip(pol_a.parameters(), pol_c.parameters()):
         assert torch.equal(pa, pc), "capture must leave the weights untouched"
@@ -238,7 +238,7 @@ def test_fused_learner_update_matches_eager_update():
     for pa, pb, pc in zip(pol_a.parameters(), pol_b.parameters(), pol_c.parameters()):
         assert torch.allclose(pa, pb, atol=5e-5, rtol=1e-3)
         assert torch.allclose(pa, pc, atol=5e-5, rtol=1e-3)
-    f.L.ackb_ppo_set_mode(1)
+    f.mode = 1
 
 
 @pytest.mark.gpu
@@ -325,12 +325,12 @@ def test_fused_update_minibatch_modes_agree_with_eager(mode, monkeypatch):
     oa, ob = torch.optim.Adam(pa.parameters(), lr=3e-4, eps=1e-5), torch.optim.Adam(pb.parameters(), lr=3e-4, eps=1e-5)
     fused = FusedMinibatchStep(pb, ob, cfg, obs_dim, dev)
     assert fused.index_mode == (mode == "index")
-    fused.L.ackb_ppo_set_mode(0)                   # fp32 arithmetic for the tight comparison
+    fused.mode = 0                   # fp32 arithmetic for the tight comparison
     try:
         ppo_update(pa, oa, batch, cfg, generator=torch.Generator(device=dev).manual_seed(9))
         ppo_update(pb, ob, batch, cfg, generator=torch.Generator(device=dev).manual_seed(9), graphed=fused)
     finally:
-        fused.L.ackb_ppo_set_mode(1)
+        fused.mode = 1
     for (name, x), y in zip(pa.state_dict().items(), pb.state_dict().values()):
         assert torch.allclose(x, y, atol=5e-5, rtol=1e-3), name
 
