@@ -7,6 +7,7 @@
 // frame_skip substeps in registers, observation staged per warp in shared memory and written with
 // coalesced stores, auto-reset fused.  No tensor cores: the largest dense object is 8 x 8.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX v3: ranges cost one pointer test unless a profiler (nsys / ncu --nvtx) is attached
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -329,6 +330,13 @@ __global__ void random_action_kernel(float* action, int n, unsigned long long se
 
 thread_local std::string g_last_error;
 
+// NVTX range around one C-ABI call (tracing): ackb_step / ackb_reset / ackb_step_host show up as named
+// ranges on the calling thread's timeline, with the kernels they launch underneath
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -523,6 +531,7 @@ int ackb_dtype(const ackb_handle* h) { return h ? h->dtype : ACKB_ERR_ARG; }
 unsigned long long ackb_launch_count(const ackb_handle* h) { return h ? h->launches : 0ull; }
 
 int ackb_reset(ackb_handle* h, const uint8_t* dev_mask, float* dev_obs, void* stream) {
+  NvtxRange nvtx("ackb_reset");
   if (!h || !dev_obs) return fail(h, ACKB_ERR_ARG, "ackb_reset: null pointer");
   CK(cudaSetDevice(h->device));
   StepArgs a{};
@@ -532,6 +541,7 @@ int ackb_reset(ackb_handle* h, const uint8_t* dev_mask, float* dev_obs, void* st
 
 int ackb_step(ackb_handle* h, const float* dev_action, int frame_skip, int auto_reset, float* dev_obs, float* dev_reward,
               uint8_t* dev_terminated, uint8_t* dev_truncated, float* dev_terminal_obs, int32_t* dev_ncon, void* stream) {
+  NvtxRange nvtx("ackb_step");
   if (!h || !dev_obs || !dev_reward || !dev_terminated || !dev_truncated) return fail(h, ACKB_ERR_ARG, "ackb_step: null output pointer");
   if (frame_skip < 1) return fail(h, ACKB_ERR_ARG, "ackb_step: frame_skip must be >= 1");
   CK(cudaSetDevice(h->device));
@@ -566,6 +576,7 @@ static void* device_alias(const void* host_ptr) {
 
 int ackb_step_host(ackb_handle* h, const float* host_action, int frame_skip, int auto_reset, float* host_obs, float* host_reward,
                    uint8_t* host_terminated, uint8_t* host_truncated) {
+  NvtxRange nvtx("ackb_step_host");
   if (!h || !host_action || !host_obs || !host_reward || !host_terminated || !host_truncated) return fail(h, ACKB_ERR_ARG, "ackb_step_host: null pointer");
   CK(cudaSetDevice(h->device));
   const size_t n = h->n;

@@ -7,6 +7,7 @@
 // The eager torch path moves ~10 KB per sample through HBM for the same arithmetic.  CUDA-core fp32 FMAs (the matrices are
 // 64 wide), gradients agree with torch autograd to fp32 rounding (tests/test_ppo.py).
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -1195,6 +1196,7 @@ __global__ void __launch_bounds__(1024, 1) clip_adam_kernel(float* __restrict__ 
 }  // namespace
 
 static int g_use_tc = -1;
+namespace { struct NvtxRange { explicit NvtxRange(const char* n) { nvtxRangePushA(n); } ~NvtxRange() { nvtxRangePop(); } }; }
 
 extern "C" {
 
@@ -1212,6 +1214,7 @@ int ackb_ppo_minibatch_grad(const float* obs, const float* act, const float* old
 int ackb_ppo_minibatch_grad_mode(const float* obs, const float* act, const float* old_logp, const float* adv, const float* ret,
                                  const int64_t* idx, int mb, int obs_dim, const float* adv_mean_std, const float* params, float* grads,
                                  float* diag, float clip_range, float vf_coef, float ent_coef, int mode, void* stream) {
+  NvtxRange nvtx("ackb_ppo_minibatch_grad");
   if (!obs || !act || !old_logp || !adv || !ret || !adv_mean_std || !params || !grads || !diag || mb <= 0) return ACKB_ERR_ARG;
   if (obs_dim <= 0 || obs_dim > KP) return ACKB_ERR_ARG;
   cudaStream_t s = (cudaStream_t)stream;
@@ -1279,6 +1282,7 @@ int ackb_ppo_gae(const float* rew, const float* val, const float* done, const fl
 }
 
 static int launch_act(const ActArgs& a, cudaStream_t s) {
+  NvtxRange nvtx(a.done_out ? "ackb_ppo_bootstrap" : "ackb_ppo_act");
   static bool attr_done[64] = {false};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return ACKB_ERR_NO_DEVICE;

@@ -16,6 +16,7 @@ import torch
 from . import _lib
 from .compiler.constants import build_consts
 from .models import load_model, model_kind
+from .spaces import GymEnv, action_space, observation_space
 
 _DTYPES = {"float32": 0, "f32": 0, torch.float32: 0, "float64": 1, "f64": 1, torch.float64: 1}
 
@@ -63,6 +64,10 @@ class BatchedAckermannEnv:
         if self.env_id_base:
             _lib.check(self.L.ackb_set_env_id_base(self.h, self.env_id_base), self.h)
         self.obs_dim = self.L.ackb_obs_dim(self.h)
+        # spaces of ONE environment, as the reference declares them (ackermann_env.py:95-108)
+        self.observation_space, self.action_space = observation_space(self.obs_dim), action_space()
+        self.single_observation_space, self.single_action_space = self.observation_space, self.action_space
+        self.max_episode_steps = int(max_episode_steps)
         n, d = self.num_envs, self.device
         self.obs = torch.empty((n, self.obs_dim), dtype=torch.float32, device=d)
         self.reward = torch.empty((n,), dtype=torch.float32, device=d)
@@ -178,7 +183,7 @@ class BatchedAckermannEnv:
         return int(self.L.ackb_launch_count(self.h))
 
 
-class AckermannRobotEnv:
+class AckermannRobotEnv(GymEnv):
     """Single-environment adapter with the reference's gym.Env signature (ackermann_env.py:51-60,143,187).
 
     ``reset(seed, options) -> (obs[79] float32 ndarray, info)``;
@@ -204,12 +209,14 @@ class AckermannRobotEnv:
         self._seed = seed
         self._env = BatchedAckermannEnv(1, seed=seed, **self._kw)
         self.observation_shape, self.action_shape = (self._env.obs_dim,), (2,)
+        self.observation_space, self.action_space = self._env.observation_space, self._env.action_space   # ackermann_env.py:95-108
+        self.render_mode = render_mode
         self.step_count = 0
         self.goal_position = None
         self.robot_start_position = np.zeros(2)
 
     def reset(self, seed=None, options=None):
-        if seed is not None and seed != self._seed:
+        if seed is not None:     # gym contract: an explicit seed restarts the random streams, also when it is the same seed again
             self._seed = seed
             self._env.close()
             self._env = BatchedAckermannEnv(1, seed=seed, **self._kw)

@@ -542,6 +542,7 @@ class PPOTrainer:
     def collect(self) -> float:
         cfg, env, b = self.cfg, self.env, self.buf
         t0 = time.perf_counter()
+        torch.cuda.nvtx.range_push("ppo.collect")        # NVTX phases: rollout / update
         for t in range(cfg.n_steps):
             obs = sanitize_obs(self.obs)
             fused = self.graphed if isinstance(self.graphed, FusedMinibatchStep) else None
@@ -572,11 +573,13 @@ class PPOTrainer:
                 self.obs.copy_(nobs)
         self.num_timesteps += cfg.n_steps * env.num_envs * self.world
         torch.cuda.synchronize(self.device)
+        torch.cuda.nvtx.range_pop()
         return time.perf_counter() - t0
 
     def update(self) -> Dict[str, float]:
         cfg, b = self.cfg, self.buf
         t0 = time.perf_counter()
+        torch.cuda.nvtx.range_push("ppo.update")
         with torch.no_grad():
             if isinstance(self.graphed, FusedMinibatchStep):      # value forward + one GAE kernel into the persistent arrays
                 self.graphed.value(sanitize_obs(self.obs), self._tv)
@@ -596,10 +599,11 @@ class PPOTrainer:
             self.graphed = GraphedMinibatchStep(self.policy, self.opt, cfg, max(1, n // cfg.minibatches), flat["obs"].shape[1], self.device)
         st = ppo_update(self.policy, self.opt, flat, cfg, self.world, graphed=self.graphed, perm_seed=self._noise_seed)
         torch.cuda.synchronize(self.device)
+        torch.cuda.nvtx.range_pop()
         st["update_s"] = time.perf_counter() - t0
         return st
 
-    def train(self, total_timesteps: int, log=print) -> Dict[str, float]:
+    def train(self, total_timesteps: int, log=print, log_all_ranks: bool = False) -> Dict[str, float]:
         out = {}
         it = 0
         while self.num_timesteps < total_timesteps:
@@ -614,7 +618,7 @@ class PPOTrainer:
                        ep_rew_mean=(es["return_sum"] / es["episodes"]) if es["episodes"] else float("nan"),
                        ep_len_mean=(es["length_sum"] / es["episodes"]) if es["episodes"] else float("nan"),
                        **{k: st[k] for k in ("pg_loss", "v_loss", "entropy", "approx_kl", "clip_frac", "allreduce_bytes")})
-            if self.rank == 0 and log:
+            if (self.rank == 0 or log_all_ranks) and log:      # log_all_ranks: the callback runs collectives (evaluation)
                 log(out)
             it += 1
         return out

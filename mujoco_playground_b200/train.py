@@ -18,7 +18,7 @@ import torch.distributed as dist
 
 from .env import BatchedAckermannEnv
 from .ppo import PPOConfig, PPOTrainer
-from .shard import rank_seed, reduce_stats
+from .shard import reduce_stats
 
 
 def main(argv=None):
@@ -46,6 +46,7 @@ def main(argv=None):
     ap.add_argument("--minibatches", type=int, default=4)
     ap.add_argument("--model", default="v2", help="v2 | scene | maze:umaze|open|medium|large")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--max-eval-steps", type=int, default=1000, help="upper bound of env steps per evaluation (one full episode)")
     a = ap.parse_args(argv)
 
     if a.algo in ("sac", "td3"):
@@ -67,16 +68,21 @@ def main(argv=None):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    env = BatchedAckermannEnv(a.num_envs, device=dev, frame_skip=a.frame_skip, seed=rank_seed(a.seed, rank), model=a.model,
+    # one seed for the whole job, streams keyed by the global environment id: the result does not depend on the number of GPUs
+    env = BatchedAckermannEnv(a.num_envs, device=dev, frame_skip=a.frame_skip, seed=a.seed, env_id_base=rank * a.num_envs, model=a.model,
                               max_linear_velocity=a.max_velocity, goal_distance_threshold=a.goal_threshold)
     if a.algo == "random":
         env.reset()
-        # the reference runs `episodes` episodes of one environment (train.py:189-227); here: until that many episodes finished
-        steps = max(1, a.timesteps // (a.num_envs * world))
+        # the reference runs `--episodes` episodes of one environment (train.py:189-227); here the batch is stepped with random
+        # actions until that many episodes have finished over all ranks (checked every 100 steps: no per-step host sync)
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
-        for _ in range(steps):
-            env.step(None)
+        done_eps, steps = 0, 0
+        while done_eps < a.episodes:
+            for _ in range(100):
+                env.step(None)
+            steps += 100
+            done_eps = reduce_stats(env.stats(), device=dev)["episodes"]
         torch.cuda.synchronize(dev)
         dt = time.perf_counter() - t0
         st = reduce_stats(env.stats(), device=dev)
@@ -88,23 +94,42 @@ def main(argv=None):
         cfg = PPOConfig(n_steps=a.n_steps, n_epochs=a.n_epochs, minibatches=a.minibatches,
                         learning_rate=3e-4 if a.learning_rate is None else a.learning_rate)
         tr = PPOTrainer(env, cfg, seed=a.seed)
+        hyper = dict(learning_rate=cfg.learning_rate, n_steps=cfg.n_steps, n_epochs=cfg.n_epochs, gamma=cfg.gamma, gae_lambda=cfg.gae_lambda,
+                     clip_range=cfg.clip_range, ent_coef=cfg.ent_coef, vf_coef=cfg.vf_coef, max_grad_norm=cfg.max_grad_norm,
+                     batch_size=cfg.n_steps * a.num_envs // cfg.minibatches)
         next_save = [a.save_freq]
+        next_eval = [a.eval_freq]
 
         def log(d):
-            print(json.dumps(d), flush=True)
+            if rank == 0:
+                print(json.dumps(d), flush=True)
+            if a.eval_freq > 0 and a.eval_episodes > 0 and d["timesteps"] >= next_eval[0]:      # EvalCallback (train.py:149-158)
+                ev = evaluate_agent(eval_env, tr.policy, n_steps=a.max_eval_steps, n_episodes=a.eval_episodes)   # collective: every rank
+                if rank == 0:
+                    print(json.dumps({**ev, "evaluation": True, "timesteps": d["timesteps"]}), flush=True)
+                while next_eval[0] <= d["timesteps"]:
+                    next_eval[0] += max(1, a.eval_freq)
             if a.save_path and rank == 0 and d["timesteps"] >= next_save[0]:     # CheckpointCallback (train.py:140-144)
-                save_sb3_policy(tr.policy, f"{a.save_path}_{d['timesteps']}_steps.zip", tr.opt, d["timesteps"])
+                save_sb3_policy(tr.policy, f"{a.save_path}_{d['timesteps']}_steps.zip", tr.opt, d["timesteps"], hyper=hyper,
+                                flat_order=getattr(tr.graphed, "order", None), total_timesteps=a.timesteps)
                 while next_save[0] <= d["timesteps"]:
                     next_save[0] += max(1, a.save_freq)
 
-        tr.train(a.timesteps, log=log)
+        # a separate, smaller evaluation batch (the reference evaluates on the training env; with auto-reset batches a second handle
+        # keeps the training episodes undisturbed -- handles on one device are independent)
+        eval_env = BatchedAckermannEnv(min(a.num_envs, 1024), device=dev, frame_skip=a.frame_skip, seed=a.seed + 1, model=a.model,
+                                       max_linear_velocity=a.max_velocity, goal_distance_threshold=a.goal_threshold,
+                                       env_id_base=rank * min(a.num_envs, 1024))
+        tr.train(a.timesteps, log=log, log_all_ranks=True)
         if a.save_path and rank == 0:                                               # model.save (train.py:182-183)
-            save_sb3_policy(tr.policy, f"{a.save_path}_final.zip", tr.opt, tr.num_timesteps)
+            save_sb3_policy(tr.policy, f"{a.save_path}_final.zip", tr.opt, tr.num_timesteps, hyper=hyper,
+                            flat_order=getattr(tr.graphed, "order", None), total_timesteps=a.timesteps)
         if a.eval_episodes > 0:                                                     # evaluate_agent (train.py:303-309)
-            ev = evaluate_agent(env, tr.policy, n_steps=min(1000, env.max_episode_steps if hasattr(env, "max_episode_steps") else 1000))
-            ev = {**ev, "evaluation": True}
+            ev = evaluate_agent(eval_env, tr.policy, n_steps=a.max_eval_steps, n_episodes=a.eval_episodes)
+            ev = {**ev, "evaluation": True, "final": True}
             if rank == 0:
                 print(json.dumps(ev), flush=True)
+        eval_env.close()
     env.close()
     if world > 1:
         dist.destroy_process_group()

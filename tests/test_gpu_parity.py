@@ -87,17 +87,29 @@ def test_trajectory_from_reset(dtype, steps, tol_q, tol_obs):
     oracles = [OracleEnv(M, tolerance=1e-12) for _ in range(n)]
     for k, o in enumerate(oracles):
         assert np.abs(o.reset(goal[k]) - obs0[k]).max() < 1e-5
+    ncon_flips = flag_flips = 0
+    worst_obs = 0.0
     for t in range(steps):
         a = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
         obs, rew, term, trunc, info = env.step(torch.from_numpy(a).cuda())
         obs, rew, term, trunc, ncon = (x.cpu().numpy() for x in (obs, rew, term, trunc, info["ncon"]))
         for k, o in enumerate(oracles):
             oo, r, te, tr, inf = o.step(a[k])
+            # north_star: "integer contact counts and done flags must match exactly".  Exact in fp64.  In fp32 a contact whose
+            # distance is within rounding of zero can switch one step early / late: the flip RATE is measured and bounded here
+            # (and reported), never skipped; the done flags must still match exactly.
+            ncon_flips += int(ncon[k] != inf["ncon"])
+            flag_flips += int(bool(term[k]) != te) + int(bool(trunc[k]) != tr)
+            worst_obs = max(worst_obs, float(np.abs(oo - obs[k]).max()))
             if dtype == "float64":
                 assert ncon[k] == inf["ncon"], f"step {t} env {k}: ncon {ncon[k]} vs {inf['ncon']}"
-                assert bool(term[k]) == te and bool(trunc[k]) == tr
-                assert np.abs(oo - obs[k]).max() < tol_obs
-                assert abs(r - rew[k]) < 1e-4 * max(1.0, abs(r))
+            assert abs(r - rew[k]) < (1e-4 if dtype == "float64" else 2e-3) * max(1.0, abs(r))
+    total = steps * n
+    print(f"{dtype}: contact-count flips {ncon_flips}/{total} ({100.0 * ncon_flips / total:.2f} %), done-flag flips {flag_flips}, "
+          f"worst |obs - oracle| {worst_obs:.2e}")
+    assert flag_flips == 0
+    assert worst_obs < tol_obs
+    assert ncon_flips == 0 if dtype == "float64" else ncon_flips <= 0.03 * total, "fp32 contact-count flip rate above 3 % of env steps"
     q, v, _ = env.get_state()
     for k, o in enumerate(oracles):
         assert np.abs(q[k] - o.sim.qpos).max() < tol_q, f"{dtype} env {k}: qpos error {np.abs(q[k] - o.sim.qpos).max()}"
@@ -234,17 +246,21 @@ def test_scene_single_step_matches_oracle(dtype, tol, lanes):
     q2, v2, _ = env.get_state()
     ncon = info["ncon"].cpu().numpy()
     o = OracleEnv(S, kind="scene", tolerance=1e-12)
-    worst, nbox = 0.0, 0
+    worst, nbox, flips, lid_err = 0.0, 0, 0, 0.0
     for i in range(n):
         o.reset(np.zeros(2))
         o.sim.qpos[:] = qpos[i]; o.sim.qvel[:] = qvel[i]
         oo, *_ = o.step(acts[i])
         nbox += int(any(c["geom1"] != 0 for c in o.sim.contacts()))
+        flips += int(ncon[i] != o.sim.ncon)
+        lid_err = max(lid_err, float(np.abs(oo[:36] - obs[i, :36]).max()))
         if dtype == "float64":
             assert ncon[i] == o.sim.ncon
-            assert np.abs(oo[:36] - obs[i, :36]).max() < 1e-4, "36-beam lidar against the maze walls"
         worst = max(worst, _rel(q2[i], o.sim.qpos), _rel(v2[i], o.sim.qvel))
+    print(f"scene {dtype} lanes={lanes}: contact-count flips {flips}/{n}, worst lidar error {lid_err:.2e}, worst rel state error {worst:.2e}")
     assert nbox > 10, "the sample must exercise wheel-box contacts"
+    assert lid_err < (1e-4 if dtype == "float64" else 2e-3), "36-beam lidar against the maze walls"
+    assert flips == 0 if dtype == "float64" else flips <= 3, "fp32: a contact at distance ~0 may switch (bounded, reported)"
     assert worst < tol
     env.close()
 
@@ -367,8 +383,10 @@ def test_long_horizon_statistical_parity_fp32_vs_fp64():
 # ---------------------------------------------------------------------------------------------------------------
 # PointMaze scenes (v2 robot in the U / Open / Medium / Large mazes): reset with settle steps, deferred auto-reset
 # ---------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name,dtype,tol", [("umaze", "float64", 1e-7), ("large", "float32", 2e-3)])
+@pytest.mark.parametrize("name,dtype,tol", [("umaze", "float64", 1e-7), ("large", "float32", 2e-3), ("mushr", "float64", 1e-7),
+                                            ("mushr", "float32", 2e-3)])
 def test_maze_env_matches_oracle(name, dtype, tol):
+    """v2 robot in a block maze; "mushr" = the 38 blocks of ackermann_maze_flat.xml."""
     from mujoco_playground_b200 import BatchedAckermannEnv
     from mujoco_playground_b200.models import load_model
     from oracle.env_oracle import OracleEnv
@@ -459,3 +477,144 @@ def test_odd_batch_sizes_and_layouts_run_clean(model, lanes):
             # changes summation order at the solver tolerance; 16 substeps of the hopping robot amplify that to < 1e-3
             assert np.abs(q[0] - first).max() < 5e-3, "environment 0 does not depend on the batch size (up to fp32 solver tolerance)"
         env.close()
+
+
+def test_sharded_batch_equals_single_batch_bit_for_bit():
+    """random streams are keyed by the GLOBAL environment id, so rank r of R owning envs [r N/R, (r+1) N/R) with the same
+    seed reproduces the single-handle batch exactly (goals, synthetic actions, resets) -- results do not depend on R."""
+    from mujoco_playground_b200 import BatchedAckermannEnv
+    from mujoco_playground_b200.shard import shard_range
+    n, steps = 1000, 40
+    kw = dict(dtype="float32", seed=77, frame_skip=2, max_episode_steps=15, lanes_per_env=4)     # 15-step episodes: auto-resets inside the run
+    full = BatchedAckermannEnv(n, **kw)
+    full.reset()
+    shards = []
+    for r in range(3):
+        b, e = shard_range(n, r, 3)
+        s = BatchedAckermannEnv(e - b, env_id_base=b, **kw)
+        s.reset()
+        shards.append((b, e, s))
+    for t in range(steps):
+        fo, fr, ft, ftr, _ = full.step(None)
+        for b, e, s in shards:
+            so, sr, st, strn, _ = s.step(None)
+            assert torch.equal(fo[b:e], so) and torch.equal(fr[b:e], sr) and torch.equal(ft[b:e], st) and torch.equal(ftr[b:e], strn), f"step {t} shard {b}"
+    qf = full.get_state()[0]
+    for b, e, s in shards:
+        assert np.array_equal(qf[b:e], s.get_state()[0])
+        assert np.array_equal(full.get_episode()[0][b:e], s.get_episode()[0])
+        s.close()
+    assert full.stats()["episodes"] >= 2 * n
+    full.close()
+
+
+def test_interleaved_handles_of_different_models_and_precisions():
+    """Each handle carries its own constants (kernel parameter): alternating calls on handles of different models / precisions on
+    one device give the same results as running each handle alone (round 1 shared one __constant__ block per device)."""
+    from mujoco_playground_b200 import BatchedAckermannEnv
+    specs = [dict(model="v2", dtype="float32"), dict(model="scene", dtype="float32"), dict(model="v2", dtype="float64"), dict(model="maze:umaze", dtype="float32")]
+    n, steps = 130, 12
+    alone = []
+    for sp in specs:
+        e = BatchedAckermannEnv(n, seed=5, **sp)
+        e.reset()
+        for _ in range(steps):
+            obs = e.step(None)[0]
+        alone.append(obs.clone())
+        e.close()
+    envs = [BatchedAckermannEnv(n, seed=5, **sp) for sp in specs]
+    for e in envs:
+        e.reset()
+    for _ in range(steps):
+        outs = [e.step(None)[0] for e in envs]
+    for a, b, sp in zip(alone, outs, specs):
+        assert torch.equal(a, b), sp
+    for e in envs:
+        e.close()
+
+
+@pytest.mark.parametrize("lanes", [1, 4])
+def test_bad_state_guard_on_device(lanes):
+    """mj_checkPos / mj_checkVel: poisoned environments are reset to qpos0 inside the step (counted in stats.bad_state), everything
+    stays finite and the other environments are untouched."""
+    from mujoco_playground_b200 import BatchedAckermannEnv
+    n = 64
+    ref = BatchedAckermannEnv(n, dtype="float32", seed=2, lanes_per_env=lanes, auto_reset=False)
+    env = BatchedAckermannEnv(n, dtype="float32", seed=2, lanes_per_env=lanes, auto_reset=False)
+    ref.reset(); env.reset()
+    for _ in range(20):
+        ref.step(None); env.step(None)
+    q, v, w = env.get_state()
+    q[3, 0] = np.nan; v[10, 7] = np.inf; q[40, 9] = 5e10
+    env.set_state(q, v, w)
+    o1 = env.step(None)[0]
+    o0 = ref.step(None)[0]
+    assert env.stats()["bad_state"] == 3 and ref.stats()["bad_state"] == 0
+    assert torch.isfinite(o1).all()
+    keep = [i for i in range(n) if i not in (3, 10, 40)]
+    assert torch.equal(o1[keep], o0[keep])
+    q2 = env.get_state()[0]
+    assert np.isfinite(q2).all() and abs(q2[3, 2] - 0.065) < 1e-3, "reset to qpos0 (chassis at z = 0.065), then one substep"
+    ref.close(); env.close()
+
+
+def test_evaluate_agent_with_scripted_policies():
+    """sb3_io.evaluate_agent (src/rl/utils.py:20-50) against policies whose outcome is known: a goal-seeking controller built from
+    the observation's goal bearing reaches most goals on the empty floor; a policy that stands still reaches none and every episode
+    runs into the time limit; episode statistics come from the device-side counters."""
+    from mujoco_playground_b200 import BatchedAckermannEnv
+    from mujoco_playground_b200.sb3_io import evaluate_agent
+    env = BatchedAckermannEnv(512, dtype="float32", seed=6, frame_skip=4, max_episode_steps=400)
+
+    def seek(obs):      # obs[:, 78] = wrapped bearing of the goal, obs[:, 77] = distance (ackermann_env.py:248-263)
+        ang = obs[:, 78]
+        return torch.stack([torch.where(ang.abs() < 1.0, torch.ones_like(ang), 0.4 * torch.ones_like(ang)), torch.clamp(2.0 * ang, -1, 1)], dim=1)
+
+    good = evaluate_agent(env, seek, n_steps=400)
+    assert good["episodes"] >= 512 and good["success_rate"] > 0.8, good
+    assert good["mean_length"] < 350 and good["mean_reward"] > -50 * 400 * 1.1
+    idle = evaluate_agent(env, lambda obs: torch.zeros((obs.shape[0], 2), device=obs.device), n_steps=400)
+    assert idle["episodes"] == 512 and idle["success_rate"] == 0.0 and abs(idle["mean_length"] - 400) < 1e-6, idle
+    # n_episodes mode (the reference's argument): stops once that many episodes have finished
+    few = evaluate_agent(env, seek, n_steps=400, n_episodes=100)
+    assert 100 <= few["episodes"] <= 512 * 3
+    env.close()
+
+
+def test_vec_env_contract():
+    """AckermannB200VecEnv: the SB3 VecEnv contract of the reference's DummyVecEnv(Monitor(env)) (src/rl/train.py:70-76)."""
+    from mujoco_playground_b200 import AckermannB200VecEnv
+    venv = AckermannB200VecEnv(40, seed=3, max_episode_steps=7)
+    assert venv.num_envs == 40 and venv.observation_space.shape == (79,) and venv.action_space.shape == (2,)
+    assert venv.action_space.low.min() == -1 and venv.action_space.high.max() == 1 and np.isinf(venv.observation_space.high).all()
+    obs = venv.reset()
+    assert isinstance(obs, np.ndarray) and obs.shape == (40, 79) and obs.dtype == np.float32
+    rng = np.random.default_rng(0)
+    ret = np.zeros(40)
+    for t in range(7):
+        obs, rew, dones, infos = venv.step(rng.uniform(-2, 2, (40, 2)))       # out-of-range actions are clipped like SB3 does
+        ret += rew
+        assert rew.shape == (40,) and dones.dtype == bool and len(infos) == 40
+        if t < 6:
+            assert not dones.any() and all(i == {} for i in infos)
+    assert dones.all(), "time limit after max_episode_steps"
+    for i, info in enumerate(infos):
+        assert info["TimeLimit.truncated"] is True and info["terminal_observation"].shape == (79,)
+        assert info["episode"]["l"] == 7 and abs(info["episode"]["r"] - ret[i]) < 1e-3 * max(1.0, abs(ret[i]))
+    assert np.allclose(obs[:, 72:75], 0.0, atol=1e-6), "auto-reset: the returned observation is the first of the new episode"
+    assert venv.env_is_wrapped(None) == [False] * 40 and venv.get_attr("frame_skip")[0] == 1
+    venv.close()
+
+
+def test_single_env_adapter_spaces_and_reseed():
+    """AckermannRobotEnv: spaces of the reference (ackermann_env.py:95-108); reset(seed=s) restarts the random streams."""
+    from mujoco_playground_b200 import AckermannRobotEnv
+    env = AckermannRobotEnv(dtype="float64")
+    assert env.observation_space.shape == (79,) and env.observation_space.dtype == np.float32
+    assert env.action_space.contains(env.action_space.sample())
+    o1, i1 = env.reset(seed=11)
+    o2, i2 = env.reset(seed=11)
+    o3, i3 = env.reset(seed=12)
+    assert np.array_equal(o1, o2) and i1["goal_position"] == i2["goal_position"] and i1["goal_position"] != i3["goal_position"]
+    assert env.observation_space.contains(o1)
+    env.close()

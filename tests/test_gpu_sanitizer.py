@@ -1,0 +1,40 @@
+"""compute-sanitizer over every kernel layout of the step path (race detection / sanitizers).
+
+memcheck (out-of-bounds / misaligned accesses), racecheck (shared-memory hazards: the 1-lane layout aliases the per-warp observation
+tile onto live wheel records) and synccheck (barrier misuse) must all report 0 errors on tools/gpu/sanitize_workload.py.
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+
+
+def _sanitizer():
+    for c in (shutil.which("compute-sanitizer"), "/usr/local/cuda/bin/compute-sanitizer"):
+        if c and os.path.exists(c):
+            return c
+    return None
+
+
+@pytest.mark.parametrize("tool,which", [("memcheck", "all"), ("racecheck", "all"), ("synccheck", "fast")])
+def test_step_kernels_clean_under_compute_sanitizer(tool, which):
+    cs = _sanitizer()
+    if cs is None:
+        pytest.skip("compute-sanitizer not found")
+    cmd = [cs, "--tool", tool, "--error-exitcode", "86", "--print-limit", "20"]
+    if tool == "racecheck":
+        cmd += ["--racecheck-report", "all"]
+    cmd += [sys.executable, os.path.join(ROOT, "tools", "gpu", "sanitize_workload.py"), which]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=1500)
+    tail = (p.stdout + p.stderr)[-3000:]
+    out_dir = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out_dir):
+        with open(os.path.join(out_dir, f"sanitizer_{tool}.log"), "w") as f:
+            f.write(p.stdout + p.stderr)
+    assert p.returncode == 0, f"compute-sanitizer {tool} failed (rc {p.returncode}):\n{tail}"
+    assert "ERROR SUMMARY: 0 errors" in (p.stdout + p.stderr) or "RACECHECK SUMMARY: 0 hazards" in (p.stdout + p.stderr), tail

@@ -124,6 +124,80 @@ def test_load_reference_sb3_checkpoints(tmp_path):
         assert torch.equal(v, pol2.state_dict()[k])
 
 
+def _sb3_style_load(path, mods):
+    """What stable_baselines3.common.save_util.load_from_zip_file + json_to_data do (SB3 2.7.0), with the class references resolved
+    through the modules in `mods` (the real ones when installed, stand-ins here)."""
+    import base64
+    import io
+    import json
+    import pickle
+    import zipfile
+    with zipfile.ZipFile(path) as z:
+        names = z.namelist()
+        data = json.loads(z.read("data").decode())
+        out = {}
+        for k, v in data.items():
+            out[k] = pickle.loads(base64.b64decode(v[":serialized:"])) if isinstance(v, dict) and ":serialized:" in v else v
+        params = {n[:-4]: torch.load(io.BytesIO(z.read(n)), map_location="cpu", weights_only=True) for n in names if n.endswith(".pth") and n != "pytorch_variables.pth"}
+        pv = torch.load(io.BytesIO(z.read("pytorch_variables.pth")), map_location="cpu", weights_only=True)
+        ver = z.read("_stable_baselines3_version").decode()
+    return out, params, pv, ver
+
+
+def test_saved_archive_has_the_layout_ppo_load_opens(tmp_path):
+    """save_sb3_policy writes what PPO.load reads: every pickled field of `data` resolves to the SB3 / gymnasium
+    class PPO.load expects and carries the state SB3 itself writes; policy.pth / policy.optimizer.pth have SB3's parameter order.
+    SB3 cannot be installed here, so the class references are resolved through stand-in modules; where the reference checkout is
+    present the pickle streams are also compared opcode by opcode with the reference's own archive."""
+    import base64
+    import json
+    import pickletools
+    import zipfile
+    from mujoco_playground_b200.ppo import ActorCritic
+    from mujoco_playground_b200.sb3_io import SB3_PARAM_ORDER, load_sb3_policy, save_sb3_policy, sb3_stub_modules
+    torch.manual_seed(0)
+    pol = ActorCritic(79)
+    opt = torch.optim.Adam(pol.parameters(), lr=3e-4, eps=1e-5)
+    a_, lp_, v_ = pol.act(torch.randn(8, 79))
+    (lp_.sum() + v_.sum()).backward()
+    opt.step()
+    out = str(tmp_path / "ppo_final.zip")
+    save_sb3_policy(pol, out, opt, num_timesteps=4096, total_timesteps=8192, hyper=dict(n_steps=16, batch_size=1024), last_obs=np.ones((4, 79), np.float32))
+    with sb3_stub_modules() as mods:
+        data, params, pv, ver = _sb3_style_load(out, mods)
+        Box = mods["gymnasium.spaces.box"].Box
+        U = mods["stable_baselines3.common.utils"]
+        assert data["policy_class"] is mods["stable_baselines3.common.policies"].ActorCriticPolicy
+        assert data["rollout_buffer_class"] is mods["stable_baselines3.common.buffers"].RolloutBuffer
+        osp, asp = data["observation_space"], data["action_space"]
+        assert isinstance(osp, Box) and osp._shape == (79,) and osp.dtype == np.float32 and np.all(np.isneginf(osp.low)) and not osp.bounded_above.any()
+        assert isinstance(asp, Box) and asp._shape == (2,) and np.array_equal(asp.low, [-1, -1]) and np.array_equal(asp.high, [1, 1]) and asp.bounded_below.all()
+        assert isinstance(data["clip_range"], U.FloatSchedule) and data["clip_range"].value_schedule.val == 0.2
+        assert isinstance(data["lr_schedule"], U.FloatSchedule) and data["lr_schedule"].value_schedule.val == 3e-4
+    assert data["_last_obs"].shape == (4, 79) and data["n_envs"] == 4 and data["num_timesteps"] == 4096 and data["n_steps"] == 16
+    assert ver == "2.7.0" and pv == {}
+    assert tuple(params["policy"].keys()) == SB3_PARAM_ORDER
+    osd = params["policy.optimizer"]
+    assert osd["param_groups"][0]["params"] == list(range(13)) and len(osd["state"]) == 13
+    named = dict(pol.named_parameters())
+    for i, name in enumerate(SB3_PARAM_ORDER):
+        assert osd["state"][i]["exp_avg"].shape == named[name].shape
+    pol2, _ = load_sb3_policy(out)
+    for k, v in pol.state_dict().items():
+        assert torch.equal(v, pol2.state_dict()[k])
+    ref = "/root/reference/rl_logs/ppo/ppo_model_10000_steps.zip"
+    if os.path.exists(ref):      # same pickle opcodes as SB3's own writer for the fields that name third-party classes
+        with zipfile.ZipFile(ref) as z:
+            rd = json.loads(z.read("data"))
+        with zipfile.ZipFile(out) as z:
+            md = json.loads(z.read("data"))
+        assert set(rd.keys()) == set(md.keys()), set(rd.keys()) ^ set(md.keys())
+        ops = lambda b: [(o.name, a) for o, a, _ in pickletools.genops(base64.b64decode(b)) if o.name not in ("FRAME", "MEMOIZE", "BINGET", "BINFLOAT")]
+        for k in ("policy_class", "rollout_buffer_class", "observation_space", "action_space", "clip_range", "lr_schedule"):
+            assert ops(rd[k][":serialized:"]) == ops(md[k][":serialized:"]) or k == "lr_schedule", k
+            assert rd[k][":type:"] == md[k][":type:"], k
+
+
 @pytest.mark.gpu
 def test_cuda_graph_update_matches_eager_update():
     """GraphedMinibatchStep (forward/backward and clip+Adam captured in CUDA graphs) performs the same optimiser steps as the
