@@ -32,6 +32,8 @@ def test_step_kernels_clean_under_compute_sanitizer(tool, which):
     cmd += [sys.executable, os.path.join(ROOT, "tools", "gpu", "sanitize_workload.py"), which]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=1500)
     tail = (p.stdout + p.stderr)[-3000:]
+    if "closed on this pool" in tail:       # the GPU pool's operators disabled the tool (it left GPUs needing a reset)
+        pytest.skip("compute-sanitizer is closed on this GPU pool: " + tail.strip().splitlines()[-1][:200])
     out_dir = os.path.join(ROOT, "gpurun_out")
     if os.path.isdir(out_dir):
         with open(os.path.join(out_dir, f"sanitizer_{tool}.log"), "w") as f:
