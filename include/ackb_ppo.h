@@ -38,7 +38,12 @@ int ackb_ppo_minibatch_grad(const float* obs, const float* act, const float* old
                             float* diag, float clip_range, float vf_coef, float ent_coef, void* stream);
 
 /* Same call with the arithmetic chosen per call (nothing process-wide is read or written): one of ACKB_PPO_MODE_*. */
-enum { ACKB_PPO_MODE_DEFAULT = -1, ACKB_PPO_MODE_FP32 = 0, ACKB_PPO_MODE_TF32 = 1 };
+enum {
+  ACKB_PPO_MODE_DEFAULT = -1,
+  ACKB_PPO_MODE_FP32 = 0,      /* fp32 CUDA-core FMAs (exact-fp32 comparisons)                                                  */
+  ACKB_PPO_MODE_TF32 = 1,      /* TF32 mma.sync m16n8k8 fragments (round-1 kernel)                                              */
+  ACKB_PPO_MODE_TCGEN05 = 2    /* TF32 tcgen05.mma: operands by shared-memory descriptor, accumulators in TMEM (obs_dim < 80)   */
+};
 int ackb_ppo_minibatch_grad_mode(const float* obs, const float* act, const float* old_logp, const float* adv, const float* ret,
                                  const int64_t* idx, int mb, int obs_dim, const float* adv_mean_std, const float* params, float* grads,
                                  float* diag, float clip_range, float vf_coef, float ent_coef, int mode, void* stream);

@@ -14,35 +14,14 @@
 
 #include "ackb.h"
 #include "ackb_ppo.h"
+#include "ackb_ppo_common.cuh"
+
+using namespace ackb_ppo;
 
 namespace {
 
-constexpr int H = 64;        // hidden width of both MLPs
 constexpr int TS = 64;       // samples per tile (weights 105 KB + activations 117 KB fill the 227 KB of an SM)
-constexpr int KP = 80;       // padded observation width in shared memory (obs_dim <= KP)
 constexpr int NT = 256;      // threads per CTA
-
-struct Offsets {
-  int W1p, b1p, W2p, b2p, W1v, b1v, W2v, b2v, Wa, ba, Wv, bv, ls, total;
-};
-__host__ __device__ inline Offsets offsets(int D) {
-  Offsets o;
-  o.W1p = 0; o.b1p = o.W1p + H * D; o.W2p = o.b1p + H; o.b2p = o.W2p + H * H;
-  o.W1v = o.b2p + H; o.b1v = o.W1v + H * D; o.W2v = o.b1v + H; o.b2v = o.W2v + H * H;
-  o.Wa = o.b2v + H; o.ba = o.Wa + 2 * H; o.Wv = o.ba + 2; o.bv = o.Wv + H; o.ls = o.bv + 1; o.total = o.ls + 2;
-  return o;
-}
-
-struct PpoArgs {
-  const float *obs, *act, *old_logp, *adv, *ret;
-  const int64_t* idx;
-  int mb, D;
-  const float* adv_stats;
-  const float* params;
-  float* grads;
-  float* diag;
-  float clip, vf_coef, ent_coef;
-};
 
 // shared-memory layout (floats)
 constexpr int S_W1T = 0;                       // [KP][128]   k-major, n: 0..63 policy, 64..127 value
@@ -1223,7 +1202,14 @@ int ackb_ppo_minibatch_grad_mode(const float* obs, const float* act, const float
   if (cudaGetDevice(&dev) != cudaSuccess) return ACKB_ERR_NO_DEVICE;
   // ACKB_PPO_TC=0 (or ackb_ppo_set_mode(0)) selects the fp32 CUDA-core kernel; default: TF32 tensor-core kernel
   if (g_use_tc < 0) { const char* ev = getenv("ACKB_PPO_TC"); g_use_tc = ev ? (atoi(ev) != 0) : 1; }
-  if (mode != ACKB_PPO_MODE_DEFAULT && mode != ACKB_PPO_MODE_FP32 && mode != ACKB_PPO_MODE_TF32) return ACKB_ERR_ARG;
+  if (mode != ACKB_PPO_MODE_DEFAULT && mode != ACKB_PPO_MODE_FP32 && mode != ACKB_PPO_MODE_TF32 && mode != ACKB_PPO_MODE_TCGEN05) return ACKB_ERR_ARG;
+  if (mode == ACKB_PPO_MODE_TCGEN05) {     // Blackwell path: tcgen05.mma kind::tf32, accumulators in TMEM (ackb_ppo_tcgen05.cu)
+    const Offsets o5 = offsets(obs_dim);
+    if (cudaMemsetAsync(grads, 0, sizeof(float) * o5.total, s) != cudaSuccess) return ACKB_ERR_CUDA;
+    if (cudaMemsetAsync(diag, 0, sizeof(float) * 5, s) != cudaSuccess) return ACKB_ERR_CUDA;
+    PpoArgs a5{obs, act, old_logp, adv, ret, idx, mb, obs_dim, adv_mean_std, params, grads, diag, clip_range, vf_coef, ent_coef};
+    return launch_grad_tcgen05(a5, s);
+  }
   const int use_tc = mode == ACKB_PPO_MODE_DEFAULT ? g_use_tc : (mode == ACKB_PPO_MODE_TF32 ? 1 : 0);
   const size_t smem = (size_t)(use_tc ? T_TOTAL : S_TOTAL) * sizeof(float);
   if (dev < 64 && !attr_done[dev]) {

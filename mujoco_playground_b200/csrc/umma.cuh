@@ -59,6 +59,16 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
       "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
 }
+// same with the A operand in TMEM (128 lanes = rows, one 32-bit column per tf32 element; a_tmem = first column of the K step)
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
 // all MMAs issued so far by this thread arrive on the mbarrier when they have completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void commit(uint64_t* mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
@@ -111,6 +121,40 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
                : "memory");
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// registers -> TMEM: this thread's lane, 16 consecutive columns (warp-collective; completes at tmem_st_wait)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+      "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])),
+      "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])),
+      "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+               "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+               "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// SWIZZLE_128B_BASE32B: the one MN-major layout the tensor core accepts for 32-bit (tf32) operands.  A block holds rows (= K index) of
+// 128 bytes (32 MN elements); 4-row atoms of 512 bytes; the 32-byte chunk c of row r is stored at chunk position c ^ (r & 3).
+__device__ __forceinline__ uint32_t b32_off(int r, int c) {
+  return (uint32_t)((r >> 2) * 512 + (r & 3) * 128 + ((((c >> 3) ^ (r & 3)) & 3) << 5) + (c & 7) * 4);
+}
+// MN-major tf32 operand: MN blocks `block_stride` bytes apart (LBO), 4-row atoms 512 bytes apart (SBO); one K step = 8 rows = 1024 bytes
+__device__ __forceinline__ uint64_t desc_mn32(uint32_t block0_saddr, uint32_t block_stride, int kstep) {
+  uint64_t d = 0;
+  d |= (uint64_t)(((block0_saddr + 1024u * (uint32_t)kstep) >> 4) & 0x3FFF);
+  d |= (uint64_t)((block_stride >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((512u >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                       // SWIZZLE_128B_BASE32B
+  return d;
 }
 
 }  // namespace umma

@@ -256,7 +256,7 @@ class FusedMinibatchStep:
     flat vector: one kernel (ackb_ppo_clip_adam) on torch's own optimiser-state tensors, or torch ops if the optimiser is not a
     capturable plain Adam.  Same arithmetic as the eager loop of ppo_update up to fp32 summation order (tests/test_ppo.py)."""
 
-    MODES = {"default": -1, "fp32": 0, "tf32": 1}
+    MODES = {"default": -1, "fp32": 0, "tf32": 1, "tcgen05": 2}
 
     def __init__(self, policy: ActorCritic, opt: torch.optim.Optimizer, cfg: PPOConfig, obs_dim: int, device, mode: str = "tf32"):
         import ctypes
