@@ -418,8 +418,9 @@ def run_cuda(args, rank, local_rank, world):
                         f"U(-pi,pi) + xy jitter 0.12 m, random actions, frame_skip={f2}", f"scene_65536_fs{f2}", n_envs=65536, fs=f2,
                         env_kw=scene_kw, **common)
             pk = dict(dev=dev, rank=rank, world=world, local_rank=local_rank, n_envs=65536, iters=10, warmup=3)
-            sub["configs[4]"] = measure_ppo(mode="tf32", env_id_base=rank * 65536, **pk)
+            sub["configs[4]"] = measure_ppo(mode="tcgen05", env_id_base=rank * 65536, **pk)
             if world == 1:
+                sub["configs[4] mma.sync tf32 learner"] = measure_ppo(mode="tf32", **pk)
                 sub["configs[4] fp32 learner"] = measure_ppo(mode="fp32", **pk)
 
     if rank == 0:
@@ -463,7 +464,7 @@ def main():
     ap.add_argument("--no-sub", action="store_true", help="skip the sub-records (configs[1], [2], [4])")
     ap.add_argument("--cpu-steps", type=int, default=800000, help="physics substeps per CPU process for the CPU arm sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--learner", default="tf32", choices=["tf32", "fp32"], help="--workload ppo: learner arithmetic")
+    ap.add_argument("--learner", default="tcgen05", choices=["tcgen05", "tf32", "fp32"], help="--workload ppo: learner arithmetic")
     ap.add_argument("--workload", default="flat", choices=["flat", "scene", "ppo"],
                     help="flat = configs[3] headline + sub-records (default), scene = configs[2], ppo = configs[4] (training loop)")
     args = ap.parse_args()

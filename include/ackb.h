@@ -65,6 +65,11 @@ int ackb_destroy(ackb_handle* h);
  * same seed reproduces the single-handle batch bit for bit.  Default 0.  Call before the first ackb_reset. */
 int ackb_set_env_id_base(ackb_handle* h, uint64_t env_id_base);
 
+/* Row pitch, in floats, of the dev_obs / dev_terminal_obs arrays of ackb_reset / ackb_step (default obs_dim = dense rows).  A pitch
+ * of 80 makes every 79-float observation row start on a 16-byte boundary: the PPO learner then fetches rollout rows with vector
+ * loads and whole 32-byte sectors (include/ackb_ppo.h, *_pitched entry points).  The host arrays of ackb_step_host stay dense. */
+int ackb_set_obs_pitch(ackb_handle* h, int pitch_floats);
+
 int ackb_num_envs(const ackb_handle* h);
 int ackb_obs_dim(const ackb_handle* h);   /* 79 for ackermann_robot_v2 and the maze models (ackermann_env.py:95-100), 43 for the scene */
 int ackb_dtype(const ackb_handle* h);

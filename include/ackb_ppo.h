@@ -48,6 +48,17 @@ int ackb_ppo_minibatch_grad_mode(const float* obs, const float* act, const float
                                  const int64_t* idx, int mb, int obs_dim, const float* adv_mean_std, const float* params, float* grads,
                                  float* diag, float clip_range, float vf_coef, float ent_coef, int mode, void* stream);
 
+/* Pitched variants: observation rows obs_pitch floats apart (>= obs_dim).  With obs_pitch = 80 every 79-float row of the rollout
+ * buffer starts on a 16-byte boundary (ackb.h: ackb_set_obs_pitch): the tcgen05 gradient kernel then gathers rows with 16-byte
+ * vector loads over whole 32-byte sectors (column 79 of the buffer is never read). */
+int ackb_ppo_minibatch_grad_pitched(const float* obs, int obs_pitch, const float* act, const float* old_logp, const float* adv, const float* ret,
+                                    const int64_t* idx, int mb, int obs_dim, const float* adv_mean_std, const float* params, float* grads,
+                                    float* diag, float clip_range, float vf_coef, float ent_coef, int mode, void* stream);
+int ackb_ppo_act_pitched(const float* obs, int obs_pitch, int n, int obs_dim, const float* params, float* mean, float* value, float* action,
+                         float* logp, uint64_t seed, uint32_t step, int value_only, void* stream);
+int ackb_ppo_bootstrap_pitched(const float* terminal_obs, int obs_pitch, const uint8_t* terminated, const uint8_t* truncated, const float* reward,
+                               int n, int obs_dim, const float* params, float gamma, float* reward_out, float* done_out, void* stream);
+
 /* Rollout side (SB3 policy.forward() inside collect_rollouts): value[n] = V(obs) and, unless value_only, mean[n][2] = pi(obs);
  * if `action` is given also a sample action = mean + exp(log_std) * eps (eps ~ N(0,1), Philox keyed by (seed, step, row)) and,
  * if `logp` is given, its log-probability.  mean / action / logp may be NULL.  TF32 tensor-core tiles.  Asynchronous on `stream`. */

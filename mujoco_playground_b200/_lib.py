@@ -24,6 +24,7 @@ SYMBOLS = {
     "ackb_create": (_i, [_vp, ctypes.c_size_t, _i, _i, _i, _u64, _i, ctypes.POINTER(_vp)]),
     "ackb_destroy": (_i, [_vp]),
     "ackb_set_env_id_base": (_i, [_vp, _u64]),
+    "ackb_set_obs_pitch": (_i, [_vp, _i]),
     "ackb_num_envs": (_i, [_vp]),
     "ackb_obs_dim": (_i, [_vp]),
     "ackb_dtype": (_i, [_vp]),
@@ -50,6 +51,9 @@ SYMBOLS = {
     "ackb_ppo_gae": (_i, [_vp, _vp, _vp, _vp, _i, _i, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp]),
     "ackb_ppo_adv_stats_ws": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "ackb_ppo_minibatch_grad_mode": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, ctypes.c_float, _i, _vp]),
+    "ackb_ppo_minibatch_grad_pitched": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, ctypes.c_float, _i, _vp]),
+    "ackb_ppo_act_pitched": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _u64, ctypes.c_uint32, _i, _vp]),
+    "ackb_ppo_bootstrap_pitched": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _vp, ctypes.c_float, _vp, _vp, _vp]),
     "ackb_ppo_minibatch_grad": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp]),
 }
 

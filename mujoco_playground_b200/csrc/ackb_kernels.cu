@@ -50,6 +50,7 @@ struct StepArgs {
   unsigned long long seed;
   uint32_t step_index;
   int frame_skip, auto_reset, obs_dim;
+  int obs_pitch;        // floats between consecutive rows of obs / terminal_obs (>= obs_dim; ackb_set_obs_pitch)
   uint8_t* done_mask;   // defer_reset: per-env done flag for the masked reset launch that follows
   int defer_reset;      // models with settle steps: the step kernel only marks finished environments, reset_kernel does the rest
   uint32_t env_base;    // global id of environment 0 of this handle (Philox streams are keyed by the GLOBAL environment id)
@@ -188,9 +189,14 @@ __global__ void __launch_bounds__(Geo<T, LANES, NC>::kBlock, Geo<T, LANES, NC>::
   // the observation exists so that the tile storage can be reused by the last substep
   auto emit = [&]() {
     __syncwarp();
-    const int total = nrow * a.obs_dim;
-    float* dst = a.obs + (size_t)env0 * a.obs_dim;
-    for (int i = lid; i < total; i += 32) dst[i] = wtile[i];
+    float* dst = a.obs + (size_t)env0 * a.obs_pitch;
+    if (a.obs_pitch == a.obs_dim) {      // warp-uniform: contiguous rows, one flat coalesced copy
+      const int total = nrow * a.obs_dim;
+      for (int i = lid; i < total; i += 32) dst[i] = wtile[i];
+    } else {                             // pitched rows (e.g. 80 floats: 16-byte aligned rows for the learner's vector loads)
+      for (int r = 0; r < nrow; ++r)
+        for (int j = lid; j < a.obs_dim; j += 32) dst[(size_t)r * a.obs_pitch + j] = wtile[r * a.obs_dim + j];
+    }
     __syncwarp();
   };
 
@@ -235,13 +241,13 @@ __global__ void __launch_bounds__(Geo<T, LANES, NC>::kBlock, Geo<T, LANES, NC>::
   const bool do_reset = done && a.auto_reset && !a.defer_reset;
   if (a.defer_reset) {   // CTA-uniform
     if (valid && done && a.terminal_obs)   // the finished episode's last observation was flushed to dev_obs by emit()
-      for (int j = lane; j < a.obs_dim; j += LANES) a.terminal_obs[(size_t)env * a.obs_dim + j] = a.obs[(size_t)env * a.obs_dim + j];
+      for (int j = lane; j < a.obs_dim; j += LANES) a.terminal_obs[(size_t)env * a.obs_pitch + j] = a.obs[(size_t)env * a.obs_pitch + j];
     if (valid && lane == 0) a.done_mask[env] = (done && a.auto_reset) ? 1 : 0;
   }
   if (__any_sync(0xffffffffu, do_reset)) {   // warp-uniform: the team collectives inside need the whole warp
     if (do_reset && valid) {
       if (a.terminal_obs)   // the finished episode's last observation was flushed to dev_obs by emit()
-        for (int j = lane; j < a.obs_dim; j += LANES) a.terminal_obs[(size_t)env * a.obs_dim + j] = a.obs[(size_t)env * a.obs_dim + j];
+        for (int j = lane; j < a.obs_dim; j += LANES) a.terminal_obs[(size_t)env * a.obs_pitch + j] = a.obs[(size_t)env * a.obs_pitch + j];
     }
     __syncwarp();
     if (do_reset) E::reset_env(C, e, wh, ep, lane, a.seed, (uint32_t)env + a.env_base);
@@ -256,7 +262,7 @@ __global__ void __launch_bounds__(Geo<T, LANES, NC>::kBlock, Geo<T, LANES, NC>::
     E::observe(C, e, k, ep, lane, psink, &dist, &minl);
     __syncwarp();
     if (do_reset && valid)
-      for (int j = lane; j < a.obs_dim; j += LANES) a.obs[(size_t)env * a.obs_dim + j] = sink.row[j];
+      for (int j = lane; j < a.obs_dim; j += LANES) a.obs[(size_t)env * a.obs_pitch + j] = sink.row[j];
     __syncwarp();
     if (G::kSmemWheels) for (int s = 0; s < G::WPL; ++s) { wh[s].sp = keep[3 * s]; wh[s].dsp = keep[3 * s + 1]; wh[s].warm = keep[3 * s + 2]; }
   }
@@ -308,7 +314,7 @@ __global__ void __launch_bounds__(Geo<T, LANES, 2>::kBlock) reset_kernel(DevStat
   }
   __syncwarp();
   if (!sel) return;
-  for (int j = lane; j < a.obs_dim; j += LANES) a.obs[(size_t)env * a.obs_dim + j] = sink.row[j];
+  for (int j = lane; j < a.obs_dim; j += LANES) a.obs[(size_t)env * a.obs_pitch + j] = sink.row[j];
   SoAAcc<T> acc{st, env};
   E::store_state(acc, lane, e, wh);
   if (lane == 0) {
@@ -344,6 +350,7 @@ struct NvtxRange {
 // ------------------------------------------------------------------------------------------------
 struct ackb_handle {
   int n = 0, device = 0, dtype = ACKB_F32, lanes = 4, obs_dim = 0;
+  int obs_pitch = 0;            // row pitch (floats) of the caller's observation arrays (ackb_set_obs_pitch; default obs_dim)
   int num_sms = 148;
   int cta_sync = -1;            // -1 = auto (by grid size), 0 / 1 forced through ACKB_CTA_SYNC (tuning)
   int zero_copy = 1;            // ackb_step_host: let the kernel access pinned caller buffers directly (ACKB_ZERO_COPY=0 disables)
@@ -481,6 +488,7 @@ int ackb_create(const double* consts, size_t consts_len, int num_envs, int devic
   h->consts_f = new Consts<float>;
   for (int i = 0; i < kNumConsts; ++i) reinterpret_cast<float*>(h->consts_f)[i] = (float)consts[i];
   h->obs_dim = (int)reinterpret_cast<const Consts<double>*>(consts)->nbeam[0] + 7;
+  h->obs_pitch = h->obs_dim;
   CK(cudaSetDevice(device));
   CK(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
   if (const char* ev = getenv("ACKB_CTA_SYNC")) h->cta_sync = atoi(ev);
@@ -525,6 +533,13 @@ int ackb_set_env_id_base(ackb_handle* h, uint64_t env_id_base) {
   return ACKB_OK;
 }
 
+int ackb_set_obs_pitch(ackb_handle* h, int pitch_floats) {
+  if (!h) return ACKB_ERR_ARG;
+  if (pitch_floats < h->obs_dim) return fail(h, ACKB_ERR_ARG, "ackb_set_obs_pitch: pitch must be >= obs_dim");
+  h->obs_pitch = pitch_floats;
+  return ACKB_OK;
+}
+
 int ackb_num_envs(const ackb_handle* h) { return h ? h->n : ACKB_ERR_ARG; }
 int ackb_obs_dim(const ackb_handle* h) { return h ? h->obs_dim : ACKB_ERR_ARG; }
 int ackb_dtype(const ackb_handle* h) { return h ? h->dtype : ACKB_ERR_ARG; }
@@ -535,7 +550,7 @@ int ackb_reset(ackb_handle* h, const uint8_t* dev_mask, float* dev_obs, void* st
   if (!h || !dev_obs) return fail(h, ACKB_ERR_ARG, "ackb_reset: null pointer");
   CK(cudaSetDevice(h->device));
   StepArgs a{};
-  a.obs = dev_obs; a.mask = dev_mask; a.seed = h->seed; a.obs_dim = h->obs_dim; a.stats = h->stats; a.env_base = h->env_base;
+  a.obs = dev_obs; a.mask = dev_mask; a.seed = h->seed; a.obs_dim = h->obs_dim; a.obs_pitch = h->obs_pitch; a.stats = h->stats; a.env_base = h->env_base;
   return h->dtype == ACKB_F32 ? launch_step(h, h->sf, a, (cudaStream_t)stream, true) : launch_step(h, h->sd, a, (cudaStream_t)stream, true);
 }
 
@@ -551,7 +566,7 @@ int ackb_step(ackb_handle* h, const float* dev_action, int frame_skip, int auto_
   a.action = dev_action; a.obs = dev_obs; a.reward = dev_reward; a.terminated = dev_terminated; a.truncated = dev_truncated;
   a.terminal_obs = dev_terminal_obs; a.ncon = dev_ncon; a.stats = h->stats; a.seed = h->seed; a.step_index = h->step_index++;
   h->stat_steps += (unsigned long long)h->n;
-  a.frame_skip = frame_skip; a.auto_reset = auto_reset; a.obs_dim = h->obs_dim;
+  a.frame_skip = frame_skip; a.auto_reset = auto_reset; a.obs_dim = h->obs_dim; a.obs_pitch = h->obs_pitch;
   // models whose reset includes settle steps (maze scenes): the step kernel only marks the finished environments, a masked
   // reset launch on the same stream then resets, settles and observes them
   const bool defer = auto_reset && reinterpret_cast<const Consts<double>*>(h->consts_host)->settle_steps[0] > 0.0;
@@ -560,7 +575,7 @@ int ackb_step(ackb_handle* h, const float* dev_action, int frame_skip, int auto_
   rc = h->dtype == ACKB_F32 ? launch_step(h, h->sf, a, (cudaStream_t)stream, false) : launch_step(h, h->sd, a, (cudaStream_t)stream, false);
   if (rc || !defer) return rc;
   StepArgs r{};
-  r.obs = dev_obs; r.mask = h->d_done; r.seed = h->seed; r.obs_dim = h->obs_dim; r.stats = h->stats; r.env_base = h->env_base;
+  r.obs = dev_obs; r.mask = h->d_done; r.seed = h->seed; r.obs_dim = h->obs_dim; r.obs_pitch = h->obs_pitch; r.stats = h->stats; r.env_base = h->env_base;
   return h->dtype == ACKB_F32 ? launch_step(h, h->sf, r, (cudaStream_t)stream, true) : launch_step(h, h->sd, r, (cudaStream_t)stream, true);
 }
 
@@ -593,13 +608,19 @@ int ackb_step_host(ackb_handle* h, const float* host_action, int frame_skip, int
   uint8_t* z_trunc = (uint8_t*)device_alias(host_truncated);
   const bool zero_copy = h->zero_copy && z_act && z_obs && z_rew && z_term && z_trunc;
   if (zero_copy) {
+    const int pitch_keep = h->obs_pitch;
+    h->obs_pitch = h->obs_dim;            // host observation rows are dense
     int rc = ackb_step(h, z_act, frame_skip, auto_reset, z_obs, z_rew, z_term, z_trunc, nullptr, nullptr, s);
+    h->obs_pitch = pitch_keep;
     if (rc) return rc;
     CK(cudaStreamSynchronize(s));
     return ACKB_OK;
   }
   CK(cudaMemcpyAsync(h->d_action, host_action, n * 2 * sizeof(float), cudaMemcpyHostToDevice, s));
+  const int pitch_keep = h->obs_pitch;
+  h->obs_pitch = h->obs_dim;              // host observation rows are dense
   int rc = ackb_step(h, h->d_action, frame_skip, auto_reset, h->d_obs, h->d_reward, h->d_term, h->d_trunc, nullptr, nullptr, s);
+  h->obs_pitch = pitch_keep;
   if (rc) return rc;
   CK(cudaMemcpyAsync(host_obs, h->d_obs, n * h->obs_dim * sizeof(float), cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(host_reward, h->d_reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));

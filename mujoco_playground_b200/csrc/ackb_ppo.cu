@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel(PpoArgs a) {
       float v = 0.0f;
       if (s < ns && k < D) {
         const int64_t row = a.idx ? a.idx[sbase + s] : (int64_t)(sbase + s);
-        v = a.obs[row * D + k];
+        v = a.obs[row * a.pitch + k];
       }
       sm[S_X + i] = v;
     }
@@ -440,7 +440,7 @@ __device__ __forceinline__ void gather_tile_async(const PpoArgs& a, int tile, fl
     const int s = t >> 3, kk = t & 7, f = swz(s);
     float* const dst = xbuf + s * XSW;
     const int64_t row = s < ns ? (rows ? (int64_t)rows[s] : (int64_t)(sbase + s)) : 0;
-    const float* const src = a.obs + row * D;
+    const float* const src = a.obs + row * a.pitch;
 #pragma unroll
     for (int j = 0; j < KP / 8; ++j) {
       const int k = kk + 8 * j;
@@ -853,6 +853,7 @@ struct ActArgs {
   const float* reward;
   float gamma;
   float *reward_out, *done_out;
+  int pitch;                                // floats between consecutive observation rows (>= D)
 };
 
 __device__ __forceinline__ void philox_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
@@ -870,7 +871,7 @@ __device__ __forceinline__ void fetch_obs_tile_async(const ActArgs& a, int tile,
   const int sbase = tile * TT, ns = min(TT, a.n - sbase), D = a.D;
   for (int i = t; i < TT * KP; i += NT) {
     const int s = i / KP, k = i - s * KP;
-    if (s < ns && k < D) cp_async4(&xbuf[s * XS + k], &a.obs[(size_t)(sbase + s) * D + k]);
+    if (s < ns && k < D) cp_async4(&xbuf[s * XS + k], &a.obs[(size_t)(sbase + s) * a.pitch + k]);
     else xbuf[s * XS + k] = 0.0f;
   }
 }
@@ -1193,7 +1194,15 @@ int ackb_ppo_minibatch_grad(const float* obs, const float* act, const float* old
 int ackb_ppo_minibatch_grad_mode(const float* obs, const float* act, const float* old_logp, const float* adv, const float* ret,
                                  const int64_t* idx, int mb, int obs_dim, const float* adv_mean_std, const float* params, float* grads,
                                  float* diag, float clip_range, float vf_coef, float ent_coef, int mode, void* stream) {
+  return ackb_ppo_minibatch_grad_pitched(obs, obs_dim, act, old_logp, adv, ret, idx, mb, obs_dim, adv_mean_std, params, grads, diag, clip_range,
+                                         vf_coef, ent_coef, mode, stream);
+}
+
+int ackb_ppo_minibatch_grad_pitched(const float* obs, int obs_pitch, const float* act, const float* old_logp, const float* adv, const float* ret,
+                                    const int64_t* idx, int mb, int obs_dim, const float* adv_mean_std, const float* params, float* grads,
+                                    float* diag, float clip_range, float vf_coef, float ent_coef, int mode, void* stream) {
   NvtxRange nvtx("ackb_ppo_minibatch_grad");
+  if (obs_pitch < obs_dim) return ACKB_ERR_ARG;
   if (!obs || !act || !old_logp || !adv || !ret || !adv_mean_std || !params || !grads || !diag || mb <= 0) return ACKB_ERR_ARG;
   if (obs_dim <= 0 || obs_dim > KP) return ACKB_ERR_ARG;
   cudaStream_t s = (cudaStream_t)stream;
@@ -1207,7 +1216,7 @@ int ackb_ppo_minibatch_grad_mode(const float* obs, const float* act, const float
     const Offsets o5 = offsets(obs_dim);
     if (cudaMemsetAsync(grads, 0, sizeof(float) * o5.total, s) != cudaSuccess) return ACKB_ERR_CUDA;
     if (cudaMemsetAsync(diag, 0, sizeof(float) * 5, s) != cudaSuccess) return ACKB_ERR_CUDA;
-    PpoArgs a5{obs, act, old_logp, adv, ret, idx, mb, obs_dim, adv_mean_std, params, grads, diag, clip_range, vf_coef, ent_coef};
+    PpoArgs a5{obs, act, old_logp, adv, ret, idx, mb, obs_dim, adv_mean_std, params, grads, diag, clip_range, vf_coef, ent_coef, obs_pitch};
     return launch_grad_tcgen05(a5, s);
   }
   const int use_tc = mode == ACKB_PPO_MODE_DEFAULT ? g_use_tc : (mode == ACKB_PPO_MODE_TF32 ? 1 : 0);
@@ -1222,7 +1231,7 @@ int ackb_ppo_minibatch_grad_mode(const float* obs, const float* act, const float
   const Offsets o = offsets(obs_dim);
   if (cudaMemsetAsync(grads, 0, sizeof(float) * o.total, s) != cudaSuccess) return ACKB_ERR_CUDA;
   if (cudaMemsetAsync(diag, 0, sizeof(float) * 5, s) != cudaSuccess) return ACKB_ERR_CUDA;
-  PpoArgs a{obs, act, old_logp, adv, ret, idx, mb, obs_dim, adv_mean_std, params, grads, diag, clip_range, vf_coef, ent_coef};
+  PpoArgs a{obs, act, old_logp, adv, ret, idx, mb, obs_dim, adv_mean_std, params, grads, diag, clip_range, vf_coef, ent_coef, obs_pitch};
   const int ntiles = (mb + (use_tc ? TT : TS) - 1) / (use_tc ? TT : TS);
   const int grid = ntiles < sms ? ntiles : sms;
   if (use_tc) ppo_grad_kernel_tc<<<grid, NT, smem, s>>>(a);
@@ -1286,19 +1295,29 @@ static int launch_act(const ActArgs& a, cudaStream_t s) {
 
 int ackb_ppo_act(const float* obs, int n, int obs_dim, const float* params, float* mean, float* value, float* action, float* logp,
                  uint64_t seed, uint32_t step, int value_only, void* stream) {
-  if (!obs || !params || !value || n <= 0 || obs_dim <= 0 || obs_dim > KP) return ACKB_ERR_ARG;
+  return ackb_ppo_act_pitched(obs, obs_dim, n, obs_dim, params, mean, value, action, logp, seed, step, value_only, stream);
+}
+
+int ackb_ppo_act_pitched(const float* obs, int obs_pitch, int n, int obs_dim, const float* params, float* mean, float* value, float* action,
+                         float* logp, uint64_t seed, uint32_t step, int value_only, void* stream) {
+  if (!obs || !params || !value || n <= 0 || obs_dim <= 0 || obs_dim > KP || obs_pitch < obs_dim) return ACKB_ERR_ARG;
   ActArgs a{obs, n, obs_dim, params, mean, value, action, logp, (unsigned long long)seed, step, value_only,
-            nullptr, nullptr, nullptr, 0.0f, nullptr, nullptr};
+            nullptr, nullptr, nullptr, 0.0f, nullptr, nullptr, obs_pitch};
   return launch_act(a, (cudaStream_t)stream);
 }
 
 int ackb_ppo_bootstrap(const float* terminal_obs, const uint8_t* terminated, const uint8_t* truncated, const float* reward, int n,
                        int obs_dim, const float* params, float gamma, float* reward_out, float* done_out, void* stream) {
+  return ackb_ppo_bootstrap_pitched(terminal_obs, obs_dim, terminated, truncated, reward, n, obs_dim, params, gamma, reward_out, done_out, stream);
+}
+
+int ackb_ppo_bootstrap_pitched(const float* terminal_obs, int obs_pitch, const uint8_t* terminated, const uint8_t* truncated, const float* reward,
+                               int n, int obs_dim, const float* params, float gamma, float* reward_out, float* done_out, void* stream) {
   if (!terminal_obs || !terminated || !truncated || !reward || !params || !reward_out || !done_out || n <= 0 || obs_dim <= 0 ||
-      obs_dim > KP)
+      obs_dim > KP || obs_pitch < obs_dim)
     return ACKB_ERR_ARG;
   ActArgs a{terminal_obs, n, obs_dim, params, nullptr, nullptr, nullptr, nullptr, 0ull, 0u, 1,
-            terminated, truncated, reward, gamma, reward_out, done_out};
+            terminated, truncated, reward, gamma, reward_out, done_out, obs_pitch};
   return launch_act(a, (cudaStream_t)stream);
 }
 

@@ -28,6 +28,7 @@ struct PpoArgs {
   float* grads;
   float* diag;
   float clip, vf_coef, ent_coef;
+  int pitch;       // floats between consecutive observation rows (>= D)
 };
 
 // tcgen05 / TMEM gradient kernel (ackb_ppo_tcgen05.cu); grads and diag must be zeroed by the caller.  Returns an ackb_status.

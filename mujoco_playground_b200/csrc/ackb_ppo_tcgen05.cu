@@ -68,8 +68,17 @@ __device__ __forceinline__ float tanh_fast(float x) {
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void cp_async4(uint32_t saddr, const float* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(saddr), "l"(gsrc));
+// read-only global load that the compiler may NOT sink towards its use (volatile asm keeps its place among the other volatile
+// statements): the prefetch of the next tile must be issued a whole tile ahead of its consumer
+__device__ __forceinline__ float ldg_early(const float* p) {
+  float v;
+  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float4 ldg_early4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
 }
 
 // sum over the 32 lanes of a warp of 16 per-lane values; afterwards lane l holds the total of column
@@ -110,7 +119,17 @@ __device__ __forceinline__ float transpose_reduce16(const float (&v)[16], int la
 }
 __device__ __forceinline__ int transpose_reduce16_col(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
 
+#ifdef ACKB_T5_PROFILE
+__device__ long long g_t5_prof[16];
+#define T5_MARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long c_ = clock64(); g_t5_prof[i] += c_ - t5_last; t5_last = c_; } } while (0)
+#else
+#define T5_MARK(i) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a) {
+#ifdef ACKB_T5_PROFILE
+  long long t5_last = clock64();
+#endif
   extern __shared__ unsigned char smem_raw[];
   unsigned char* const sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   float* const F = reinterpret_cast<float*>(sm + O_F);
@@ -173,55 +192,142 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a) {
   };
 
   const int ntiles = (a.mb + TM - 1) / TM;
+  // Gather of a tile's observation rows into registers, one tile ahead of its use.  Two mappings (CTA-uniform choice):
+  //   vec   (row pitch a multiple of 4 floats and a 16-byte aligned base, e.g. pitch 80): 4 threads per row, 16-byte loads -- thread
+  //         (r4 = t >> 2, c = t & 3) holds the float4s c, c + 4, .. c + 16 of rows r4 and r4 + 64;
+  //   scalar (dense 79-float rows): 8 threads per row, 4-byte loads -- thread (rq = t >> 3, kk = t & 7) holds columns kk, kk + 8, ..
+  //         of rows rq, rq + 32, rq + 64, rq + 96.
+  // Threads t < 128 also hold the five scalars of row t.  The loads are issued in four parts spread over the tile body.
+  const bool vec = (a.pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.obs) & 15) == 0);
+  const int PT = a.pitch;
+  float px[40], psc[5];
+  int64_t prow[4], prow_sc = 0;          // global row numbers of the tile fetched NEXT (loaded one fetch earlier: no dependent-load stall)
+  const int rq = t >> 3, kk = t & 7, r4 = t >> 2, c4i = t & 3;
+  auto fetch_rows = [&](int tile) {
+    const int sbase = tile * TM, ns = tile < ntiles ? min(TM, a.mb - sbase) : 0;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int r = vec ? (r4 + 64 * (p & 1)) : (rq + 32 * p);
+      prow[p] = (r < ns) ? (a.idx ? a.idx[sbase + r] : (int64_t)(sbase + r)) : -1;
+    }
+    prow_sc = (t < ns) ? (a.idx ? a.idx[sbase + t] : (int64_t)(sbase + t)) : -1;
+  };
+  auto fetch_part = [&](int p) {
+    if (vec) {        // part p: row pass p >> 1, float4s j = 0..2 (even p) or 3..4 (odd p)
+      const int pass = p >> 1;
+      const bool live = prow[pass] >= 0;
+      const float* src = a.obs + (live ? prow[pass] : 0) * (int64_t)PT;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        if ((j < 3) == ((p & 1) == 0)) {
+          const int f = 4 * (c4i + 4 * j);
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (live && f < PT) v = ldg_early4(src + f);
+          float* d = &px[20 * pass + 4 * j];
+          d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+      }
+    } else {
+      const bool live = prow[p] >= 0;
+      const float* src = a.obs + (live ? prow[p] : 0) * (int64_t)PT;
+#pragma unroll
+      for (int j = 0; j < KP / 8; ++j) {
+        const int k = kk + 8 * j;
+        px[10 * p + j] = (live && k < D) ? ldg_early(src + k) : 0.0f;
+      }
+    }
+  };
+  auto fetch_scalars = [&]() {
+    if (prow_sc >= 0) {
+      const int64_t grow = prow_sc;
+      psc[0] = ldg_early(&a.act[grow * 2]); psc[1] = ldg_early(&a.act[grow * 2 + 1]); psc[2] = ldg_early(&a.old_logp[grow]);
+      psc[3] = ldg_early(&a.adv[grow]); psc[4] = ldg_early(&a.ret[grow]);
+    }
+  };
+  auto fetch_tile = [&](int tile) {      // everything at once (first tile of a pass)
+#pragma unroll
+    for (int p = 0; p < 4; ++p) fetch_part(p);
+    fetch_scalars();
+    fetch_rows(tile + gridDim.x);        // row numbers of the tile after this one
+  };
+  // registers -> BASE32B operand layout, rounded to TF32; columns >= D are zero except column 79 = 1 on real samples (bias gradient)
+  auto store_tile = [&](int ns) {
+    if (vec) {
+#pragma unroll
+      for (int pass = 0; pass < 2; ++pass) {
+        const int r = r4 + 64 * pass;
+        const float one = (r < ns) ? 1.0f : 0.0f;
+        const uint32_t xrow = O_X + (uint32_t)((r >> 2) * 512 + (r & 3) * 128);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+          const int f = 4 * (c4i + 4 * j);
+          float v[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) v[i] = (f + i < D) ? tf32r(px[20 * pass + 4 * j + i]) : ((f + i == KP - 1) ? one : 0.0f);
+          *reinterpret_cast<float4*>(sm + xrow + (uint32_t)(f >> 5) * BLK + (uint32_t)((((((f & 31) >> 3) ^ (r & 3)) & 3) << 5) + (f & 7) * 4)) =
+              make_float4(v[0], v[1], v[2], v[3]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int r = rq + 32 * p;
+        const float one = (r < ns) ? 1.0f : 0.0f;
+        const uint32_t xrow = O_X + (uint32_t)((r >> 2) * 512 + (r & 3) * 128);
+#pragma unroll
+        for (int j = 0; j < KP / 8; ++j) {
+          const int k = kk + 8 * j;     // feature k: block k / 32, 32-byte chunk (k % 32) / 8 = j % 4, position kk inside the chunk
+          const float v = (k < D) ? tf32r(px[10 * p + j]) : ((k == KP - 1) ? one : 0.0f);
+          *reinterpret_cast<float*>(sm + xrow + (uint32_t)(k >> 5) * BLK + (uint32_t)(((((j & 3) ^ (r & 3)) & 3) << 5) + kk * 4)) = v;
+        }
+      }
+    }
+    if (t < TM && t < ns) {
+#pragma unroll
+      for (int i = 0; i < 5; ++i) F[F_SC + t * 8 + i] = psc[i];
+    }
+  };
 #pragma unroll 1
   for (int net = 0; net < 2; ++net) {
-    // ---- weights of this net (TF32-rounded) in the K-major operand layout: W1 [64][80], W2 [out][in], W2^T [in][out]
+    // ---- first tile of this pass on its way, then the weights of this net (TF32-rounded) in the K-major operand layout:
+    // W1 [64][80], W2 [out][in], W2^T [in][out]
     __syncthreads();
-    for (int i = t; i < H * KP; i += NT5) {
-      const int r = i / KP, k = i % KP;
-      const float w = (k < D) ? tf32r(P[(net ? o.W1v : o.W1p) + r * D + k]) : 0.0f;
-      *reinterpret_cast<float*>(sm + O_W1 + (k >> 5) * 8192 + sw128_off(r, k & 31)) = w;
-    }
-    for (int i = t; i < H * H; i += NT5) {
-      const int r = i >> 6, k = i & 63;
-      const float w = tf32r(P[(net ? o.W2v : o.W2p) + r * H + k]);
-      *reinterpret_cast<float*>(sm + O_W2 + (k >> 5) * 8192 + sw128_off(r, k & 31)) = w;
-      *reinterpret_cast<float*>(sm + O_W2T + (r >> 5) * 8192 + sw128_off(k, r & 31)) = w;
-    }
     bool first = true;
+    fetch_rows(blockIdx.x);
+    if ((int)blockIdx.x < ntiles) fetch_tile(blockIdx.x);
+    {
+      const float* W1g = P + (net ? o.W1v : o.W1p);
+      const float* W2g = P + (net ? o.W2v : o.W2p);
+      // W1: thread t owns row r = t / 4 and columns k = (t % 4) + 4 j: consecutive threads read consecutive words
+      {
+        const int r = t >> 2, k0 = t & 3;
+#pragma unroll 5
+        for (int j = 0; j < KP / 4; ++j) {
+          const int k = k0 + 4 * j;
+          const float w = (k < D) ? tf32r(__ldg(W1g + r * D + k)) : 0.0f;
+          *reinterpret_cast<float*>(sm + O_W1 + (k >> 5) * 8192 + sw128_off(r, k & 31)) = w;
+        }
+      }
+#pragma unroll 4
+      for (int i = t; i < H * H; i += NT5) {
+        const int r = i >> 6, k = i & 63;
+        const float w = tf32r(__ldg(W2g + i));
+        *reinterpret_cast<float*>(sm + O_W2 + (k >> 5) * 8192 + sw128_off(r, k & 31)) = w;
+        *reinterpret_cast<float*>(sm + O_W2T + (r >> 5) * 8192 + sw128_off(k, r & 31)) = w;
+      }
+    }
+    T5_MARK(10);
 #pragma unroll 1
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const int sbase = tile * TM;
       const int ns = min(TM, a.mb - sbase);
-      // ---- observation rows + per-sample scalars of the tile: 2 threads per row, 4-byte cp.async into the BASE32B layout
-      {
-        const int r = t >> 1, part = t & 1;
-        const bool live = r < ns;
-        const int64_t grow = live ? (a.idx ? a.idx[sbase + r] : (int64_t)(sbase + r)) : 0;
-        const float* src = a.obs + grow * D;
-        const uint32_t xrow = O_X + (uint32_t)((r >> 2) * 512 + (r & 3) * 128);
-#pragma unroll 8
-        for (int j = 0; j < KP / 2; ++j) {
-          const int k = part * (KP / 2) + j;
-          const uint32_t off = xrow + (uint32_t)(k >> 5) * BLK + (uint32_t)((((((k & 31) >> 3) ^ (r & 3)) & 3) << 5) + (k & 7) * 4);
-          if (live && k < D) cp_async4(sb + off, src + k);
-          else *reinterpret_cast<float*>(sm + off) = (live && k == KP - 1) ? 1.0f : 0.0f;
-        }
-        if (part == 0 && live) {
-          const uint32_t s0 = smem_u32(&F[F_SC + r * 8]);
-          cp_async4(s0, &a.act[grow * 2]); cp_async4(s0 + 4, &a.act[grow * 2 + 1]); cp_async4(s0 + 8, &a.old_logp[grow]);
-          cp_async4(s0 + 12, &a.adv[grow]); cp_async4(s0 + 16, &a.ret[grow]);
-        }
-        asm volatile("cp.async.commit_group;");
-        asm volatile("cp.async.wait_all;" ::: "memory");
-#pragma unroll 8
-        for (int j = 0; j < KP / 2; ++j) {      // round this thread's own elements to TF32 (nearest; the tensor core would truncate)
-          const int k = part * (KP / 2) + j;
-          float* p = reinterpret_cast<float*>(sm + xrow + (uint32_t)(k >> 5) * BLK + (uint32_t)((((((k & 31) >> 3) ^ (r & 3)) & 3) << 5) + (k & 7) * 4));
-          *p = tf32r(*p);
-        }
-      }
+      // ---- this tile's observation rows and scalars were fetched into registers one tile ahead (global latency hidden behind the
+      // previous tile's compute): round to TF32 and store into the BASE32B operand layout, then fetch the next tile
+      store_tile(ns);
+      const bool more = tile + (int)gridDim.x < ntiles;      // CTA-uniform
+      if (more) { fetch_part(0); fetch_scalars(); }
       __syncthreads();
+      T5_MARK(0);
       // ---- X -> TMEM (A operand of (1)): this thread's row, features 40 hf .. 40 hf + 39, into columns C_ZB + 40 hf ..
       {
         float v[16], w8[8];
@@ -247,6 +353,7 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a) {
 #pragma unroll
         for (int k = 0; k < KP / 8; ++k) mma_tf32_ts(tb + C_ZA, tb + C_ZB + 8 * k, desc_kmajor(sb + O_W1 + (k >> 2) * 8192, k & 3), id, k > 0);
       });
+      T5_MARK(1);
       // ---- H1 = tanh(Z1 + b1): back into TMEM in place (A operand of (2)) and into shared memory (B operand of (4), tanh' later)
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
@@ -262,13 +369,17 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a) {
           *reinterpret_cast<float4*>(sm + O_H1 + hf * BLK + rowoff + ((((cc >> 1) ^ rx) & 3) << 5) + (cc & 1) * 16) = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
         }
       }
+      if (more) fetch_part(1);
+      T5_MARK(2);
       // ---- (2) Z2 = H1 W2^T
       run_mma([&] {
         const uint32_t id = idesc_tf32(128, 64, 0, 0);
 #pragma unroll
         for (int k = 0; k < 8; ++k) mma_tf32_ts(tb + C_ZB, tb + C_ZA + 8 * k, desc_kmajor(sb + O_W2 + (k >> 2) * 8192, k & 3), id, k > 0);
       });
-      // ---- heads: partial dot products of this thread's 32 columns of H2 = tanh(Z2 + b2)
+      T5_MARK(3);
+      // ---- heads: H2 = tanh(Z2 + b2) of this thread's 32 columns (kept in registers), partial dot products with the head weights
+      float h2v[32];
       {
         float p0 = 0.f, p1 = 0.f;
 #pragma unroll
@@ -281,13 +392,16 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const float h2 = tanh_fast(v[j] + b2[j]);
+            h2v[16 * ch + j] = h2;
             p0 = fmaf(h2, wa[j], p0);
             if (net == 0) p1 = fmaf(h2, wa[H + j], p1);
           }
         }
         F[F_PART + row * 8 + hf * 4] = p0; F[F_PART + row * 8 + hf * 4 + 1] = p1;
       }
+      if (more) fetch_part(2);
       __syncthreads();
+      T5_MARK(4);
       // ---- PPO loss derivatives, one thread per sample (hf == 0)
       if (hf == 0) {
         float d0 = 0.f, d1 = 0.f;
@@ -319,6 +433,7 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a) {
         F[F_DO + row * 4] = d0; F[F_DO + row * 4 + 1] = d1;
       }
       __syncthreads();
+      T5_MARK(5);
       // ---- dZ2 = (dOut W3) (1 - H2^2): into TMEM in place (A operand of (3)) and shared memory (A operand of (4));
       //      head-weight gradients dOut^T H2 by transpose-reduction over the warp's rows
       {
@@ -326,13 +441,11 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a) {
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
           float v[16], ga[16], gb[16];
-          tmem_ld16(tlane + C_ZB + 32 * hf + 16 * ch, v);
           const int c0 = 32 * hf + 16 * ch;
-          const float* b2 = &F[F_B2 + 64 * net + c0];
           const float* wa = &F[F_W3 + (net ? 2 * H : 0) + c0];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float h2 = tanh_fast(v[j] + b2[j]);
+            const float h2 = h2v[16 * ch + j];
             ga[j] = d0 * h2;
             gb[j] = d1 * h2;
             const float g = (net == 0) ? fmaf(d1, wa[H + j], d0 * wa[j]) : d0 * wa[j];
@@ -351,6 +464,8 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a) {
           } else g3[2][ch] += ra;
         }
       }
+      if (more) { fetch_part(3); fetch_rows(tile + 2 * gridDim.x); }
+      T5_MARK(6);
       // ---- (3) dH1 = dZ2 W2   and   (4) dW2 += dZ2^T [H1 | 1]
       run_mma([&] {
         const uint32_t id3 = idesc_tf32(128, 64, 0, 0);
@@ -360,6 +475,7 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a) {
 #pragma unroll
         for (int k = 0; k < TM / 8; ++k) mma_tf32(tb + C_GW2, desc_mn32(sb + O_DZ, BLK, k), desc_mn32(sb + O_H1, BLK, k), id4, !first || k > 0);
       });
+      T5_MARK(7);
       // ---- dZ1 = dH1 (1 - H1^2) -> shared memory (overwrites dZ2: (3) and (4) have completed)
 #pragma unroll
       for (int ch = 0; ch < 2; ++ch) {
@@ -374,12 +490,14 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a) {
                                                                     tf32r(v[4 * c4 + 2] * (1.0f - h.z * h.z)), tf32r(v[4 * c4 + 3] * (1.0f - h.w * h.w)));
         }
       }
+      T5_MARK(8);
       // ---- (5) dW1 += dZ1^T X
       run_mma([&] {
         const uint32_t id5 = idesc_tf32(128, 80, 1, 1);
 #pragma unroll
         for (int k = 0; k < TM / 8; ++k) mma_tf32(tb + C_GW1, desc_mn32(sb + O_DZ, BLK, k), desc_mn32(sb + O_X, BLK, k), id5, !first || k > 0);
       });
+      T5_MARK(9);
       first = false;
     }
 
@@ -405,6 +523,7 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a) {
         }
       }
     }
+    T5_MARK(11);
     fence_before_sync();     // the accumulator reads above are ordered before the next net's MMAs by the barrier at the loop top
   }
 
@@ -445,6 +564,16 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a) {
 }
 
 }  // namespace
+
+#ifdef ACKB_T5_PROFILE
+extern "C" int ackb_ppo_t5_profile(long long* out16) {
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(out16, g_t5_prof, sizeof(long long) * 16) != cudaSuccess) return -1;
+  long long z[16] = {0};
+  cudaMemcpyToSymbol(g_t5_prof, z, sizeof z);
+  return 0;
+}
+#endif
 
 int launch_grad_tcgen05(const PpoArgs& a, cudaStream_t stream) {
   if (a.D >= KP) return ACKB_ERR_ARG;     // the bias gradient of layer 1 rides in column KP - 1 of the observation tile

@@ -75,6 +75,7 @@ class BatchedAckermannEnv:
         self.truncated = torch.empty((n,), dtype=torch.uint8, device=d)
         self.terminal_obs = torch.zeros((n, self.obs_dim), dtype=torch.float32, device=d)
         self.ncon = torch.zeros((n,), dtype=torch.int32, device=d)
+        self._pitch = self.obs_dim        # row pitch (floats) the handle currently writes observations with
 
     # ------------------------------------------------------------------------------------------
     def close(self):
@@ -91,27 +92,46 @@ class BatchedAckermannEnv:
     def _stream(self):
         return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def reset(self, mask: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Reset all environments (or those where mask != 0); returns the observation tensor [N, obs_dim]."""
+    def _check_obs_out(self, obs_out: torch.Tensor) -> int:
+        """Validates a caller-provided observation array [N, pitch >= obs_dim] and returns its row pitch in floats."""
+        if (obs_out.device != self.device or obs_out.dtype != torch.float32 or obs_out.dim() != 2 or obs_out.shape[0] != self.num_envs
+                or obs_out.shape[1] < self.obs_dim or not obs_out.is_contiguous()):
+            raise ValueError(f"obs_out must be a contiguous float32 [{self.num_envs}, >= {self.obs_dim}] tensor on {self.device}")
+        return int(obs_out.shape[1])
+
+    def _set_pitch(self, pitch: int) -> None:
+        """Row pitch of the observation arrays handed to the next call (ackb_set_obs_pitch); terminal observations follow it."""
+        if pitch != self._pitch:
+            _lib.check(self.L.ackb_set_obs_pitch(self.h, int(pitch)), self.h)
+            self._pitch = int(pitch)
+        if self.terminal_obs.shape[1] != pitch:
+            self.terminal_obs = torch.zeros((self.num_envs, pitch), dtype=torch.float32, device=self.device)
+
+    def reset(self, mask: Optional[torch.Tensor] = None, obs_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Reset all environments (or those where mask != 0); returns the observation tensor [N, obs_dim] (or obs_out, see step)."""
+        obs = self.obs if obs_out is None else obs_out
+        self._set_pitch(self.obs_dim if obs_out is None else self._check_obs_out(obs_out))
         mp = None
         if mask is not None:
             mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
             mp = ctypes.c_void_p(mask.data_ptr())
         with torch.cuda.device(self.device):
-            _lib.check(self.L.ackb_reset(self.h, mp, ctypes.c_void_p(self.obs.data_ptr()), self._stream()), self.h)
-        return self.obs
+            _lib.check(self.L.ackb_reset(self.h, mp, ctypes.c_void_p(obs.data_ptr()), self._stream()), self.h)
+        return obs
 
     def step(self, actions: Optional[torch.Tensor], obs_out: Optional[torch.Tensor] = None):
         """actions: [N, 2] float32 CUDA tensor in [-1, 1] (clipped like the reference), or None for synthetic
         device-generated U(-1,1) actions.  Returns (obs, reward, terminated, truncated, info) as device tensors.
-        obs_out: optional contiguous [N, obs_dim] float32 tensor on the env's device that receives the observations instead
-        of the environment's own buffer (e.g. the next slot of a rollout buffer: saves the copy)."""
+        obs_out: optional contiguous [N, pitch >= obs_dim] float32 tensor on the env's device that receives the observations instead
+        of the environment's own buffer (e.g. the next slot of a rollout buffer: saves the copy).  With pitch > obs_dim (80: rows on
+        16-byte boundaries for the learner) the columns beyond obs_dim are left untouched and info["terminal_observation"] has the
+        same pitch."""
         obs = self.obs
         if obs_out is not None:
-            if (obs_out.device != self.device or obs_out.dtype != torch.float32 or not obs_out.is_contiguous()
-                    or tuple(obs_out.shape) != (self.num_envs, self.obs_dim)):
-                raise ValueError(f"obs_out must be a contiguous float32 [{self.num_envs}, {self.obs_dim}] tensor on {self.device}")
+            self._set_pitch(self._check_obs_out(obs_out))
             obs = obs_out
+        else:
+            self._set_pitch(self.obs_dim)
         ap = None
         if actions is not None:
             if actions.device != self.device or actions.dtype != torch.float32 or not actions.is_contiguous():

@@ -258,12 +258,15 @@ class FusedMinibatchStep:
 
     MODES = {"default": -1, "fp32": 0, "tf32": 1, "tcgen05": 2}
 
-    def __init__(self, policy: ActorCritic, opt: torch.optim.Optimizer, cfg: PPOConfig, obs_dim: int, device, mode: str = "tf32"):
+    def __init__(self, policy: ActorCritic, opt: torch.optim.Optimizer, cfg: PPOConfig, obs_dim: int, device, mode: str = "tcgen05"):
         import ctypes
         from . import _lib
         self.L, self.ct = _lib.load(), ctypes
         # arithmetic of the gradient kernel, chosen per learner and passed with every call (include/ackb_ppo.h: ACKB_PPO_MODE_*)
+        # "tcgen05" (default): TF32 on the Blackwell tensor-core path (TMEM accumulators); "tf32": mma.sync fragments; "fp32": CUDA cores
         self.mode = self.MODES[os.environ.get("ACKB_PPO_MODE", mode)]
+        if self.mode == 2 and obs_dim >= 80:
+            self.mode = 1      # the tcgen05 kernel carries the layer-1 bias gradient in column 79 of the observation tile
         self.policy, self.opt, self.cfg, self.obs_dim, self.device = policy, opt, cfg, obs_dim, device
         pe, ve = policy.mlp_extractor["policy_net"], policy.mlp_extractor["value_net"]
         self.order = [pe[0].weight, pe[0].bias, pe[2].weight, pe[2].bias, ve[0].weight, ve[0].bias, ve[2].weight, ve[2].bias,
@@ -309,9 +312,9 @@ class FusedMinibatchStep:
         """Fused rollout forward (csrc/ackb_ppo.cu: ppo_act_kernel): fills action (unclipped sample), logp and value in place."""
         c = self.ct
         ptr = lambda t: c.c_void_p(t.data_ptr())
-        rc = self.L.ackb_ppo_act(ptr(obs), int(obs.shape[0]), self.obs_dim, ptr(self.flat_p), None, ptr(value), ptr(action), ptr(logp),
-                                 int(seed) & 0xFFFFFFFFFFFFFFFF, int(step) & 0xFFFFFFFF, 0,
-                                 c.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        rc = self.L.ackb_ppo_act_pitched(ptr(obs), int(obs.stride(0)), int(obs.shape[0]), self.obs_dim, ptr(self.flat_p), None, ptr(value),
+                                         ptr(action), ptr(logp), int(seed) & 0xFFFFFFFFFFFFFFFF, int(step) & 0xFFFFFFFF, 0,
+                                         c.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
         if rc != 0:
             raise RuntimeError(f"ackb_ppo_act failed with code {rc}")
 
@@ -319,8 +322,8 @@ class FusedMinibatchStep:
         """V(obs) only (bootstrap values of terminal observations): the policy net is skipped."""
         c = self.ct
         ptr = lambda t: c.c_void_p(t.data_ptr())
-        rc = self.L.ackb_ppo_act(ptr(obs), int(obs.shape[0]), self.obs_dim, ptr(self.flat_p), None, ptr(value), None, None, 0, 0, 1,
-                                 c.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        rc = self.L.ackb_ppo_act_pitched(ptr(obs), int(obs.stride(0)), int(obs.shape[0]), self.obs_dim, ptr(self.flat_p), None, ptr(value), None,
+                                         None, 0, 0, 1, c.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
         if rc != 0:
             raise RuntimeError(f"ackb_ppo_act failed with code {rc}")
 
@@ -331,9 +334,9 @@ class FusedMinibatchStep:
         c = self.ct
         ptr = lambda t: c.c_void_p(t.data_ptr())
         assert term.dtype == torch.uint8 and trunc.dtype == torch.uint8 and rew_out.is_contiguous() and done_out.is_contiguous()
-        rc = self.L.ackb_ppo_bootstrap(ptr(terminal_obs), ptr(term), ptr(trunc), ptr(rew), int(rew.shape[0]), self.obs_dim, ptr(self.flat_p),
-                                       self.cfg.gamma, ptr(rew_out), ptr(done_out),
-                                       c.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        rc = self.L.ackb_ppo_bootstrap_pitched(ptr(terminal_obs), int(terminal_obs.stride(0)), ptr(term), ptr(trunc), ptr(rew), int(rew.shape[0]),
+                                               self.obs_dim, ptr(self.flat_p), self.cfg.gamma, ptr(rew_out), ptr(done_out),
+                                               c.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
         if rc != 0:
             raise RuntimeError(f"ackb_ppo_bootstrap failed with code {rc}")
 
@@ -444,10 +447,10 @@ class FusedMinibatchStep:
         rc = self.L.ackb_ppo_adv_stats_ws(ptr(view["adv"]), ptr(rows) if rows is not None else None, n, ptr(self.adv_stats), ptr(self.adv_ws), stream)
         if rc != 0:
             raise RuntimeError(f"ackb_ppo_adv_stats failed with code {rc}")
-        rc = self.L.ackb_ppo_minibatch_grad_mode(ptr(view["obs"]), ptr(view["act"]), ptr(view["logp"]), ptr(view["adv"]), ptr(view["ret"]),
-                                                 ptr(rows) if rows is not None else None, n, self.obs_dim, ptr(self.adv_stats),
-                                                 ptr(self.flat_p), ptr(self.flat_g), ptr(self.diag), cfg.clip_range, cfg.vf_coef,
-                                                 cfg.ent_coef, self.mode, stream)
+        rc = self.L.ackb_ppo_minibatch_grad_pitched(ptr(view["obs"]), int(view["obs"].stride(0)), ptr(view["act"]), ptr(view["logp"]),
+                                                    ptr(view["adv"]), ptr(view["ret"]), ptr(rows) if rows is not None else None, n,
+                                                    self.obs_dim, ptr(self.adv_stats), ptr(self.flat_p), ptr(self.flat_g), ptr(self.diag),
+                                                    cfg.clip_range, cfg.vf_coef, cfg.ent_coef, self.mode, stream)
         if rc != 0:
             raise RuntimeError(f"ackb_ppo_minibatch_grad failed with code {rc}")
 
@@ -479,7 +482,7 @@ class PPOTrainer:
     """Rollout collection on the batched CUDA environment + PPO updates; one instance per rank."""
 
     def __init__(self, env, cfg: PPOConfig = PPOConfig(), seed: int = 0, use_cuda_graphs: bool = True, learner: str = "fused",
-                 learner_mode: str = "tf32"):
+                 learner_mode: str = "tcgen05"):
         self.env, self.cfg = env, cfg
         self.device = env.device
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
@@ -496,15 +499,22 @@ class PPOTrainer:
         self.graphed: Optional[GraphedMinibatchStep] = None
         T, N, D = cfg.n_steps, env.num_envs, env.obs_dim
         f = dict(device=self.device, dtype=torch.float32)
-        self.buf = dict(obs=torch.empty((T, N, D), **f), act=torch.empty((T, N, 2), **f), logp=torch.empty((T, N), **f),
+        import inspect
+        self._env_takes_obs_out = "obs_out" in inspect.signature(env.step).parameters
+        # fused learner: observation rows padded to 80 floats (16-byte aligned rows: vector gathers over whole 32-byte sectors in the
+        # gradient kernel); the environment writes straight into the padded rollout slots (env.step(obs_out=...))
+        self.pitch = 80 if (self.learner == "fused" and D < 80 and self._env_takes_obs_out and "obs_out" in inspect.signature(env.reset).parameters) else D
+        self.buf = dict(obs=torch.zeros((T, N, self.pitch), **f), act=torch.empty((T, N, 2), **f), logp=torch.empty((T, N), **f),
                         val=torch.empty((T, N), **f), rew=torch.empty((T, N), **f), done=torch.empty((T, N), **f))
-        self.obs = env.reset().clone()
+        if self.pitch != D:
+            self.obs = torch.zeros((N, self.pitch), **f)
+            env.reset(obs_out=self.obs)
+        else:
+            self.obs = env.reset().clone()
         self.num_timesteps = 0
         self._noise_seed = (seed * 1000003 + self.rank) * 2654435761 + 12345
         self._act_step = 0
         self._tv = torch.empty(N, **f)
-        import inspect
-        self._env_takes_obs_out = "obs_out" in inspect.signature(env.step).parameters
         self._adv, self._ret = torch.empty((T, N), **f), torch.empty((T, N), **f)    # persistent: CUDA graphs are captured on them
         if self.learner == "fused":     # flat parameter buffers exist from the start: the rollout forward uses them too
             self.graphed = FusedMinibatchStep(self.policy, self.opt, cfg, D, self.device, mode=learner_mode)
@@ -525,9 +535,9 @@ class PPOTrainer:
         stream = c.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         def launch():
-            rc = f.L.ackb_ppo_minibatch_grad_mode(ptr(flat["obs"]), ptr(flat["act"]), ptr(flat["logp"]), ptr(flat["adv"]), ptr(flat["ret"]), ptr(rows),
-                                                  mb, f.obs_dim, ptr(f.adv_stats), ptr(f.flat_p), ptr(f.flat_g), ptr(f.diag), self.cfg.clip_range,
-                                                  self.cfg.vf_coef, self.cfg.ent_coef, f.mode, stream)
+            rc = f.L.ackb_ppo_minibatch_grad_pitched(ptr(flat["obs"]), int(flat["obs"].stride(0)), ptr(flat["act"]), ptr(flat["logp"]), ptr(flat["adv"]),
+                                                     ptr(flat["ret"]), ptr(rows), mb, f.obs_dim, ptr(f.adv_stats), ptr(f.flat_p), ptr(f.flat_g), ptr(f.diag),
+                                                     self.cfg.clip_range, self.cfg.vf_coef, self.cfg.ent_coef, f.mode, stream)
             assert rc == 0
         launch()
         torch.cuda.synchronize(self.device)
@@ -570,7 +580,7 @@ class PPOTrainer:
                 b["rew"][t] = rew + cfg.gamma * tv * only_trunc
                 b["done"][t] = ((term != 0) | (trunc != 0)).float()
             if not direct:
-                self.obs.copy_(nobs)
+                self.obs[:, :nobs.shape[1]].copy_(nobs)
         self.num_timesteps += cfg.n_steps * env.num_envs * self.world
         torch.cuda.synchronize(self.device)
         torch.cuda.nvtx.range_pop()

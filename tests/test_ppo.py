@@ -229,7 +229,8 @@ def test_cuda_graph_update_matches_eager_update():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("obs_dim,n,tc,tol", [(79, 4096, 0, 2e-4), (43, 1000, 0, 2e-4), (79, 4096, 1, 4e-3), (43, 1000, 1, 4e-3)])
+@pytest.mark.parametrize("obs_dim,n,tc,tol", [(79, 4096, 0, 2e-4), (43, 1000, 0, 2e-4), (79, 4096, 1, 4e-3), (43, 1000, 1, 4e-3),
+                                              (79, 4096, 2, 4e-3), (43, 1000, 2, 4e-3), (79, 131, 2, 4e-3), (79, 40000, 1, 1e-2), (79, 40000, 2, 1e-2)])
 def test_fused_gradient_kernel_matches_autograd(obs_dim, n, tc, tol):
     """csrc/ackb_ppo.cu against torch autograd on the same minibatch: every parameter gradient and the loss diagnostics
     (ragged last tile, index gather, both observation widths)."""
@@ -260,7 +261,7 @@ def test_fused_gradient_kernel_matches_autograd(obs_dim, n, tc, tol):
     # fused kernel (lr = 0: the optimiser step inside run() must not move the weights)
     opt = torch.optim.SGD(pol.parameters(), lr=0.0)
     f = FusedMinibatchStep(pol, opt, cfg, obs_dim, dev)
-    f.mode = tc                      # 0: fp32 CUDA cores, 1: TF32 tensor cores (fp32 accumulation)
+    f.mode = tc                      # 0: fp32 CUDA cores, 1: TF32 mma.sync, 2: TF32 tcgen05 / TMEM (fp32 accumulation)
     f.cfg = PPOConfig(max_grad_norm=1e30)          # no clipping: compare raw gradients
     f.run(batch, idx, world=1)
     torch.cuda.synchronize()
@@ -523,3 +524,56 @@ def test_rollout_direct_observation_writes_match_copy_path():
             env.step(None, obs_out=torch.zeros(3, env.obs_dim, device=env.device))
         finally:
             env.close()
+
+
+@pytest.mark.gpu
+def test_pitched_observation_rows():
+    """Rows padded to 80 floats (ackb_set_obs_pitch + the *_pitched learner entry points): the env writes the same observations into
+    a padded array, terminal observations follow the pitch, and the tcgen05 gradient kernel (16-byte vector gather) returns the same
+    gradients as on dense rows."""
+    from mujoco_playground_b200 import BatchedAckermannEnv
+    from mujoco_playground_b200.ppo import ActorCritic, FusedMinibatchStep
+    dev = torch.device("cuda:0")
+    n = 300
+    a, b = BatchedAckermannEnv(n, seed=4, max_episode_steps=6), BatchedAckermannEnv(n, seed=4, max_episode_steps=6)
+    pad = torch.full((n, 80), 7.0, device=dev)
+    oa = a.reset()
+    ob = b.reset(obs_out=pad)
+    assert torch.equal(oa, ob[:, :79]) and (ob[:, 79] == 7.0).all()
+    for t in range(6):                      # the sixth step ends every episode (time limit)
+        oa, ra, ta, tra, ia = a.step(None)
+        ob, rb, tb, trb, ib = b.step(None, obs_out=pad)
+        assert torch.equal(oa, ob[:, :79]) and torch.equal(ra, rb) and (ob[:, 79] == 7.0).all()
+    assert trb.any() and ib["terminal_observation"].shape == (n, 80)
+    done = trb.bool() | tb.bool()
+    assert torch.equal(ia["terminal_observation"][done], ib["terminal_observation"][done][:, :79])
+    oa2 = a.step(None)[0]                   # back to the dense buffer after pitched calls on the other handle
+    ob2 = b.step(None)[0]
+    assert torch.equal(oa2, ob2) and ob2.shape == (n, 79)
+    a.close(); b.close()
+    # learner: dense vs padded rollout rows
+    torch.manual_seed(5)
+    m, D = 3000, 79
+    obs = torch.randn(m, D, device=dev)
+    obs_p = torch.zeros(m, 80, device=dev)
+    obs_p[:, :D] = obs
+    obs_p[:, 79] = 123.0                     # never read
+    rest = dict(act=torch.randn(m, 2, device=dev).clamp(-1, 1), logp=torch.randn(m, device=dev) * 0.3 - 2.0, adv=torch.randn(m, device=dev),
+                ret=torch.randn(m, device=dev))
+    cfg = PPOConfig(max_grad_norm=1e30)
+    pol = ActorCritic(D).to(dev)
+    f = FusedMinibatchStep(pol, torch.optim.SGD(pol.parameters(), lr=0.0), cfg, D, dev, mode="tcgen05")
+    idx = torch.randperm(m, device=dev)[: m - 5]
+    out = []
+    for o in (obs, obs_p):
+        f.run(dict(obs=o, **rest), idx, world=1)
+        torch.cuda.synchronize()
+        out.append((f.flat_g.clone(), f.diag.clone()))
+    sc = out[0][0].abs().max().item()
+    assert (out[0][0] - out[1][0]).abs().max().item() < 1e-5 * sc, "same TF32 operands, different gather path: only the summation order of atomics differs"
+    assert torch.allclose(out[0][1], out[1][1], rtol=1e-5, atol=1e-6)
+    for mode in ("tf32", "fp32"):            # the older kernels take the pitch too
+        f.mode = f.MODES[mode]
+        f.run(dict(obs=obs_p, **rest), idx, world=1)
+        torch.cuda.synchronize()
+        assert (f.flat_g - out[0][0]).abs().max().item() < 1e-2 * sc
