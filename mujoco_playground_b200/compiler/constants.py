@@ -281,8 +281,48 @@ def build_consts(M: dict, *, model_kind: int, max_episode_steps: int = 1000, goa
         else:
             assert len(boxes) <= 40, "more than 40 boxes need the occupancy grid (boxes on a lattice, listed in (x, y) order)"
 
-    # plate hull points (only if the plates can collide with the floor)
-    pts = []
+    # ---- chassis plates: hull vertices + hull graph in the chassis frame, contact parameters of the plate pairs
+    plates = [g for g in range(M["ngeom"]) if M["geom_type"][g] == 7]
+    def _collides(g1, g2):
+        return bool((M["geom_contype"][g1] & M["geom_conaffinity"][g2]) or (M["geom_contype"][g2] & M["geom_conaffinity"][g1]))
+    pl_floor = [g for g in plates if _collides(g, floor)]
+    pl_box = [g for g in plates if boxes and _collides(g, boxes[0])]
+    active = [g for g in plates if g in pl_floor or g in pl_box]
+    if active:
+        assert len(active) == 2 and (not pl_floor or pl_floor == active) and (not pl_box or pl_box == active), "both plates must share their collision masks"
+        assert "hull_adj" in M, "model table without hull graph: recompile it (tools/compile_models.py)"
+        put("pl_count", 2); put("pl_floor", 1 if pl_floor else 0); put("pl_box", 1 if pl_box else 0)
+        verts, adjs, tols, cens, rads, trans, prm = [], [], [], [], [], [], []
+        for g in active:
+            b = M["geom_bodyid"][g]
+            assert M["body_weldid"][b] == ch, "plates must be welded to the chassis"
+            Rg = kin["xmat"][b] @ _q2m(M["geom_quat"][g])
+            adr, nvv = int(M["geom_hulladr"][g]), int(M["geom_hullnum"][g])
+            assert nvv <= 32
+            pw = kin["xpos"][b] + (kin["xmat"][b] @ M["geom_pos"][g]) + M["hull_vert"][adr:adr + nvv] @ Rg.T
+            v32 = np.zeros((32, 3)); v32[:nvv] = pw
+            verts.append(v32)
+            packed = np.zeros((32, 6))
+            for i in range(nvv):
+                lst = [int(x) for x in M["hull_adj"][adr + i] if x >= 0] + [63] * 24
+                for w_ in range(6):
+                    packed[i, w_] = sum(lst[4 * w_ + q] << (6 * q) for q in range(4))
+            adjs.append(packed)
+            tols.append(0.3 * float(M["geom_rbound"][g]))
+            cen = 0.5 * (pw.min(0) + pw.max(0))
+            cens.append(cen); rads.append(float(np.linalg.norm(pw - cen, axis=1).max()))
+            trans.append(M["body_invweight0"][b][0] + M["body_invweight0"][0][0])
+            for other in ([floor] if pl_floor else []) + ([boxes[0]] if pl_box else []):
+                fr, solref, solimp = _mix(M, other, g)
+                K, B = _KB(solref, solimp, h)
+                prm.append((fr[0], K, B, tuple(solimp)))
+                assert M["geom_condim"][g] == 3 and M["geom_margin"][g] == 0 and M["geom_gap"][g] == 0
+        assert all(p_ == prm[0] for p_ in prm), "plate-floor and plate-box contacts must share friction / solref / solimp (one parameter set in the kernels)"
+        put("pl_nvert", [int(M["geom_hullnum"][g]) for g in active]); put("pl_vert", np.concatenate(verts)); put("pl_adj", np.concatenate(adjs))
+        put("pl_tol", tols); put("pl_center", np.concatenate(cens)); put("pl_radius", rads); put("pl_tran", trans)
+        put("pl_mu", prm[0][0]); put("pl_mureg2", prm[0][0] ** 2 / impratio); put("pl_K", prm[0][1]); put("pl_B", prm[0][2]); put("pl_solimp", prm[0][3])
+    # plate bounding points (cheap "can a plate touch the floor in this pose" test): the 8 corners of the box around both plates
+    allv = []
     for g in range(M["ngeom"]):
         if M["geom_type"][g] != 7:
             continue
@@ -291,12 +331,12 @@ def build_consts(M: dict, *, model_kind: int, max_episode_steps: int = 1000, goa
         b = M["geom_bodyid"][g]
         Rg = kin["xmat"][b] @ _q2m(M["geom_quat"][g])
         hv = M["hull_vert"][M["geom_hulladr"][g]:M["geom_hulladr"][g] + M["geom_hullnum"][g]]
-        pw = kin["xpos"][b] + (kin["xmat"][b] @ M["geom_pos"][g]) + hv @ Rg.T
+        allv.append(kin["xpos"][b] + (kin["xmat"][b] @ M["geom_pos"][g]) + hv @ Rg.T)
+    pts = []
+    if allv:
+        pw = np.concatenate(allv)
         lo, hi = pw.min(0), pw.max(0)
-        for sx in (lo[0], hi[0]):
-            for sy in (lo[1], hi[1]):
-                pts.append([sx, sy, lo[2]])   # conservative: bounding rectangle of the plate at its lowest z
-    assert len(pts) <= 8
+        pts = [[sx, sy, sz] for sx in (lo[0], hi[0]) for sy in (lo[1], hi[1]) for sz in (lo[2], hi[2])]
     put("nhull", len(pts))
     if pts:
         put("hull_pts", np.concatenate(pts))

@@ -90,6 +90,23 @@ def process_mesh(path: str, scale, mode: str = "legacy") -> dict:
     from .mjcf import mat_to_quat
     quat = mat_to_quat(U)
     local = (verts - com) @ U          # vertices in COM-centred principal frame
-    return dict(volume=float(V), com=com, inertia_unit_density=I, quat=quat, principal=w,
+    # hull graph as MuJoCo builds it (user_mesh.cc MakeGraph): walk the triangulated hull faces in qhull's facet order; every vertex
+    # of a face gets the face's other two vertices appended to its edge list unless already there.  mjc_PlaneConvex walks these
+    # lists in order.  (qhull "Qt" through scipy; the facet order of MuJoCo's own qhull build may differ: VERIFY with hull_graph
+    # of tools/dump_mjmodel.py.)
+    loc = {int(g): i for i, g in enumerate(hull_idx)}
+    adj = [[] for _ in hull_idx]
+    for tri in hull.simplices:
+        ids = [loc[int(v)] for v in tri]
+        for a in ids:
+            for b in ids:
+                if b != a and b not in adj[a]:
+                    adj[a].append(b)
+    max_adj = 24
+    assert max(len(x) for x in adj) <= max_adj, "hull vertex degree above the table width"
+    hull_adj = -np.ones((len(hull_idx), max_adj), np.int32)
+    for i, lst in enumerate(adj):
+        hull_adj[i, :len(lst)] = lst
+    return dict(hull_adj_local=hull_adj, volume=float(V), com=com, inertia_unit_density=I, quat=quat, principal=w,
                 hull_vert_local=local[hull_idx].copy(), aabb_half=np.abs(local).max(0),
                 nvert=len(verts), nface=len(faces))

@@ -544,6 +544,8 @@ def _assemble(ctx: _Ctx, root: ET.Element, opt: dict) -> dict:
     hull_adr = -np.ones(ng, np.int32)
     hull_num = np.zeros(ng, np.int32)
     hull_vert: List[np.ndarray] = []
+    hull_adj: List[np.ndarray] = []
+    rbound = np.zeros(ng)
     n_h = 0
     for gi, g in enumerate(G):
         if g["type"] == GEOM_MESH:
@@ -551,9 +553,13 @@ def _assemble(ctx: _Ctx, root: ET.Element, opt: dict) -> dict:
             hv = me["hull_vert_local"]
             hull_adr[gi], hull_num[gi] = n_h, len(hv)
             hull_vert.append(hv)
+            hull_adj.append(me["hull_adj_local"])         # neighbour lists (indices local to this geom's hull), -1 padded
+            rbound[gi] = float(np.linalg.norm(me["aabb_half"]))   # mjCGeom::GetRBound for meshes: norm of the half sizes of the aligned box
             n_h += len(hv)
     M["geom_hulladr"], M["geom_hullnum"] = hull_adr, hull_num
     M["hull_vert"] = np.concatenate(hull_vert) if hull_vert else np.zeros((0, 3))
+    M["hull_adj"] = np.concatenate(hull_adj) if hull_adj else -np.ones((0, 24), np.int32)
+    M["geom_rbound"] = rbound
 
     S = ctx.sites
     M["site_bodyid"] = np.array([s["body"] for s in S], np.int32)

@@ -752,6 +752,12 @@ struct Sim {
     Tm::sum_n(v);
   }
 
+  // frame / kind code of contact slot c of a wheel record: slots 0, 1 are floor contacts of the wheel; slots >= 2 carry a packed frame
+  // permutation (bits 0..4, see Perm) and bit 5 = chassis-plate contact (acts on the chassis only, its own friction coefficient)
+  ACKB_HD static unsigned slot_code(const WheelT& w, int c) { return (NC <= 2 || c < 2) ? perm_pack(0) : ((w.fcode >> (8 * (c - 2))) & 255u); }
+  ACKB_HD static T slot_coupling(unsigned code) { return (NC > 2 && (code & 32u)) ? T(0) : T(1); }
+  ACKB_HD static T slot_mu(const Consts<T>& C, const WheelK<T>& wk, unsigned code) { return (NC > 2 && (code & 32u)) ? C.pl_mu[0] : wk.mu; }
+
   // Team sum of the 45 assembly partials (36 packed Hessian entries, 8 reduced right-hand sides, 1 scalar).  With one lane per
   // wheel (4-lane layout, tail mode) the steer rows are produced by a single lane each -- row / rhs 6 by the front-left wheel's
   // lane (2), row / rhs 7 by the front-right one (3) -- so those 16 entries are broadcast instead of butterfly-summed
@@ -788,8 +794,10 @@ struct Sim {
   }
 
   // ---- B6/B7 floor contacts of one wheel (plane vs cylinder, in the body frame) and their row parameters
+  // `tri` (may be null): receives the two extra "triangle" points mjc_PlaneCylinder adds when the cap faces the floor
+  // (tri[0..2], tri[3..5] = body-frame positions, tri[6] = their common distance, tri[7] = 1 if present).
   ACKB_HD static void collide_wheel(const Consts<T>& C, const State& e, const Kin<T>& k, const T* vb, int wi, int cown, const WheelK<T>& wk,
-                                    WheelT& w, StepDiag& diag) {
+                                    WheelT& w, StepDiag& diag, T* tri = nullptr) {
     const T s = wk.isL * e.st[0] + wk.isR * e.st[1];
     T sn, cs;
     N::sincos_small(s, &sn, &cs);
@@ -805,7 +813,12 @@ struct Sim {
 #pragma unroll
     for (int i = 0; i < 3; ++i) vec[i] = ax[i] * prjaxis - k.n[i];
     T len = N::sqrt_(dot3(vec, vec));
-    if (len < N::minval) { diag.unsupported = 1; len = T(1); }  // disk parallel to the floor
+    if (len < N::minval) {
+      // disk parallel to the floor: mjc_PlaneCylinder takes the cylinder's own x axis, Rz(steer) Ry(spin) e_x in the body frame
+      const T sp_s = N::sin_(w.sp), sp_c = N::cos_(w.sp);
+      vec[0] = cs * sp_c; vec[1] = sn * sp_c; vec[2] = -sp_s;
+      len = T(1);
+    }
     const T rlen = r * N::rcp_(len);
 #pragma unroll
     for (int i = 0; i < 3; ++i) vec[i] *= rlen;
@@ -814,7 +827,28 @@ struct Sim {
     prjaxis *= hl;
     const T d0 = dist + prjaxis + prjvec, d1 = dist - prjaxis + prjvec;
     const bool has0 = d0 <= T(0), has1 = has0 && (d1 <= T(0));
-    if (has0 && (dist + prjaxis - T(0.5) * prjvec <= T(0))) diag.unsupported = 1;  // cap faces the floor
+    {   // cap faces the floor: two more points at +-(sqrt(3)/2) r along vec x axis, half a radius back from the rim point
+      const T dtri = dist + prjaxis - T(0.5) * prjvec;
+      const bool has_tri = has0 && (dtri <= T(0));
+      if (tri) {
+        tri[7] = has_tri ? T(1) : T(0);
+        if (has_tri) {
+          T v1[3];
+          cross3(v1, vec, ax);
+          const T l1 = N::sqrt_(dot3(v1, v1));
+          const T sc = (l1 < N::minval) ? T(0) : r * T(0.8660254037844386) * N::rcp_(l1);
+          // a degenerate cross product (vec parallel to the axis) cannot occur here: vec is the radial direction
+#pragma unroll
+          for (int i = 0; i < 3; ++i) {
+            const T base = wk.c[i] + ax[i] - vec[i] * T(0.5) - k.n[i] * dtri * T(0.5);
+            tri[i] = base + sc * v1[i];
+            tri[3 + i] = base - sc * v1[i];
+          }
+          tri[6] = dtri;
+          if (l1 < N::minval) diag.unsupported = 1;
+        }
+      } else if (has_tri) diag.unsupported = 1;
+    }
     if (PAIR) diag.ncon += (cown == 0) ? (has0 ? 1 : 0) : (has1 ? 1 : 0);
     else diag.ncon += (has0 ? 1 : 0) + (has1 ? 1 : 0);
     const T mu = wk.mu;
@@ -850,7 +884,7 @@ struct Sim {
   // box's face normals with the cylinder's support point (see oracle cylinder_box, DESIGN.md for the deviation).
   // Up to two box contacts per wheel are kept (slots 2, 3); more are flagged as unsupported.
   ACKB_HD static void collide_boxes(const Consts<T>& C, const State& e, const Kin<T>& k, const T* vb, int wi, const WheelK<T>& wk,
-                                    WheelT& w, StepDiag& diag) {
+                                    WheelT& w, StepDiag& diag, int& nfound, unsigned& fcode) {
     const T r = C.w_radius[wi], hl = C.w_halflen[wi];
     // wheel centre and axis in the world frame
     T cw[3], aw[3];
@@ -862,9 +896,6 @@ struct Sim {
     const T dsteer = wk.isL * e.dst[0] + wk.isR * e.dst[1];
     const T reach = N::sqrt_(r * r + hl * hl);
     const int nbox = (int)C.nbox[0];
-    int nfound = 0;
-    unsigned fcode = 0u;
-    if (NC > 2) { w.con[NC - 2].D = T(0); w.con[NC - 1].D = T(0); for (int i = 0; i < 3; ++i) { w.con[NC - 2].x[i] = w.con[NC - 1].x[i] = T(0); w.con[NC - 2].z[i] = w.con[NC - 1].z[i] = T(0); } }
     // candidates: every box (no grid), or the occupied cells under the wheel's bounding square, visited in box order
     const bool grid = C.grid_on[0] != T(0);
     int gx0 = 0, gy0 = 0, gny = 1, ncand = nbox;
@@ -933,7 +964,176 @@ struct Sim {
       if (NC > 2) { if (nfound == 0) w.con[NC > 2 ? NC - 2 : 0] = con; else w.con[NC - 1] = con; }
       ++nfound;
     }
-    w.fcode = fcode;
+  }
+
+
+  // ---- chassis plates (convex hulls welded to the chassis): contacts of plate `p` in MuJoCo's generation order -- floor first
+  // (mjc_PlaneConvex: support vertex, then its hull-graph neighbours within the margin and at least pl_tol away from the first
+  // contact, <= 3), then the obstacle boxes in box order (one contact per box: the box face with the largest separation over the
+  // hull's support distances, point = blend of the deepest vertices; see oracle box_convex).  Up to kMaxPlate contacts are
+  // returned (body-frame point, distance, packed frame permutation | 32); the true count is the return value.
+  static constexpr int kMaxPlate = 4;
+  ACKB_HD static int plate_adj(const Consts<T>& C, int p, int v, int ei) {
+    const unsigned wv = (unsigned)C.pl_adj[(p * 32 + v) * 6 + (ei >> 2)];
+    return (int)((wv >> (6 * (ei & 3))) & 63u);
+  }
+  ACKB_HD static int plate_contacts(const Consts<T>& C, const State& e, const Kin<T>& k, int p, T (*xb)[3], T* dist, unsigned* code) {
+    int cnt = 0;
+    const int nv = (int)C.pl_nvert[p];
+    const T* V = &C.pl_vert[p * 96];
+    if (C.pl_floor[0] != T(0)) {
+      const T hO = e.p[2] - C.plane_z[0];
+      int best = -1;
+      T dbest = T(1e30);
+#pragma unroll 1
+      for (int v = 0; v < nv; ++v) {
+        const T d = dot3(k.n, V + 3 * v) + hO;
+        if (d < dbest) { dbest = d; best = v; }
+      }
+      if (best >= 0 && dbest <= T(0)) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) xb[0][i] = V[3 * best + i] - k.n[i] * dbest * T(0.5);
+        dist[0] = dbest; code[0] = perm_pack(0) | 32u;
+        cnt = 1;
+        const T tol2 = C.pl_tol[p] * C.pl_tol[p];
+#pragma unroll 1
+        for (int ei = 0; ei < 24 && cnt < 3; ++ei) {
+          const int v = plate_adj(C, p, best, ei);
+          if (v == 63) break;
+          const T dx = V[3 * v] - V[3 * best], dy = V[3 * v + 1] - V[3 * best + 1], dz = V[3 * v + 2] - V[3 * best + 2];
+          if (dx * dx + dy * dy + dz * dz < tol2) continue;
+          const T d = dot3(k.n, V + 3 * v) + hO;
+          if (d > T(0)) continue;
+#pragma unroll
+          for (int i = 0; i < 3; ++i) xb[cnt][i] = V[3 * v + i] - k.n[i] * d * T(0.5);
+          dist[cnt] = d; code[cnt] = perm_pack(0) | 32u;
+          ++cnt;
+        }
+      }
+    }
+    if (C.pl_box[0] != T(0) && C.nbox[0] > T(0)) {
+      // plate centre in the world, candidate boxes under its bounding sphere
+      T cw[3];
+      const T* pc = &C.pl_center[3 * p];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) cw[i] = e.p[i] + k.R[3 * i] * pc[0] + k.R[3 * i + 1] * pc[1] + k.R[3 * i + 2] * pc[2];
+      const T reach = C.pl_radius[p];
+      const bool grid = C.grid_on[0] != T(0);
+      int gx0 = 0, gy0 = 0, gny = 1, ncand = (int)C.nbox[0];
+      if (grid) {
+        const T ip = N::rcp_(C.grid_pitch[0]);
+        gx0 = (int)floor((cw[0] - reach - C.grid_x0[0]) * ip); gy0 = (int)floor((cw[1] - reach - C.grid_y0[0]) * ip);
+        const int gx1 = (int)floor((cw[0] + reach - C.grid_x0[0]) * ip), gy1 = (int)floor((cw[1] + reach - C.grid_y0[0]) * ip);
+        gny = gy1 - gy0 + 1;
+        ncand = (gx1 - gx0 + 1) * gny;
+        if (ncand > 16) ncand = 16;
+      }
+#pragma unroll 1
+      for (int bi = 0; bi < ncand; ++bi) {
+        T bcx, bcy;
+        if (grid) {
+          const int ix = gx0 + bi / gny, iy = gy0 + bi % gny;
+          if (ix < 0 || iy < 0 || ix >= (int)C.grid_nx[0] || iy >= (int)C.grid_ny[0]) continue;
+          if (!((tbl_grid_row(C, iy) >> ix) & 1u)) continue;
+          bcx = C.grid_x0[0] + (T(ix) + T(0.5)) * C.grid_pitch[0]; bcy = C.grid_y0[0] + (T(iy) + T(0.5)) * C.grid_pitch[0];
+        } else { bcx = C.box_cx[bi]; bcy = C.box_cy[bi]; }
+        const T bc[3] = {bcx, bcy, C.box_z[0]};
+        if (N::abs_(cw[0] - bc[0]) > C.box_half[0] + reach || N::abs_(cw[1] - bc[1]) > C.box_half[1] + reach ||
+            N::abs_(cw[2] - bc[2]) > C.box_half[2] + reach) continue;
+        // support distances of the hull over the six face normals of the box (vertices in the box frame = world axes)
+        T dmin[6] = {T(1e30), T(1e30), T(1e30), T(1e30), T(1e30), T(1e30)};
+        const T off[3] = {e.p[0] - bc[0], e.p[1] - bc[1], e.p[2] - bc[2]};
+#pragma unroll 1
+        for (int v = 0; v < nv; ++v) {
+#pragma unroll
+          for (int kk = 0; kk < 3; ++kk) {
+            const T pk = off[kk] + k.R[3 * kk] * V[3 * v] + k.R[3 * kk + 1] * V[3 * v + 1] + k.R[3 * kk + 2] * V[3 * v + 2];
+            dmin[2 * kk] = mjmin(dmin[2 * kk], -pk - C.box_half[kk]);
+            dmin[2 * kk + 1] = mjmin(dmin[2 * kk + 1], pk - C.box_half[kk]);
+          }
+        }
+        T best = T(-1e30);
+        int bk = 0, bs = 1;
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk) {      // same visiting order as the oracle: axis, then sign -1, +1
+          if (dmin[2 * kk] > best) { best = dmin[2 * kk]; bk = kk; bs = -1; }
+          if (dmin[2 * kk + 1] > best) { best = dmin[2 * kk + 1]; bk = kk; bs = 1; }
+        }
+        if (best > T(0)) continue;
+        if (cnt < kMaxPlate) {
+          T wsum = T(0), pp[3] = {T(0), T(0), T(0)};
+          const T iblend = T(1000);      // 1 / PLATE_BLEND (1 mm)
+#pragma unroll 1
+          for (int v = 0; v < nv; ++v) {
+            T pv[3];
+#pragma unroll
+            for (int kk = 0; kk < 3; ++kk) pv[kk] = off[kk] + k.R[3 * kk] * V[3 * v] + k.R[3 * kk + 1] * V[3 * v + 1] + k.R[3 * kk + 2] * V[3 * v + 2];
+            const T d = T(bs) * pv[bk] - C.box_half[bk];
+            const T wgt = T(1) - (d - best) * iblend;
+            if (wgt <= T(0)) continue;
+            wsum += wgt;
+            pp[0] += wgt * pv[0]; pp[1] += wgt * pv[1]; pp[2] += wgt * pv[2];
+          }
+          const T iw = N::rcp_(wsum);
+          pp[0] *= iw; pp[1] *= iw; pp[2] *= iw;
+          pp[bk] -= T(bs) * best * T(0.5);
+          // relative to the chassis origin (world axes), then into the body frame
+          const T pw[3] = {pp[0] - off[0], pp[1] - off[1], pp[2] - off[2]};
+#pragma unroll
+          for (int i = 0; i < 3; ++i) xb[cnt][i] = k.R[i] * pw[0] + k.R[3 + i] * pw[1] + k.R[6 + i] * pw[2];
+          dist[cnt] = best;
+          // frame of the normal bs * e_bk pointing from the box to the plate (oracle make_frame), acting on the chassis with a plus sign
+          const unsigned packed = (bk == 0) ? (bs > 0 ? 0u : 20u) : ((bk == 1) ? (bs > 0 ? 1u : 21u) : (bs > 0 ? 18u : 6u));
+          code[cnt] = packed | 32u;
+        }
+        ++cnt;
+      }
+    }
+    return cnt;
+  }
+
+  // one extra (slot >= 2) contact record from a body-frame point: row parameters with the given friction / solref / solimp class
+  ACKB_HD static void make_extra(const Consts<T>& C, const State& e, const Kin<T>& k, const T* vb, const WheelT& w, const WheelK<T>& wk, const T* xb, T dd,
+                                 unsigned code, T dsteer, Contact<T>& con) {
+    const bool chassis = (code & 32u) != 0u;
+    const T mu = chassis ? C.pl_mu[0] : wk.mu;
+    const T* solimp = chassis ? C.pl_solimp : &C.w_solimp[5 * (wk.hidx - 2)];
+    const T tran = chassis ? C.pl_tran[(wk.hidx - 2) >> 1] : C.w_tran[wk.hidx - 2];
+    const T mureg2 = chassis ? C.pl_mureg2[0] : C.w_mureg2[wk.hidx - 2];
+    const T Kc = chassis ? C.pl_K[0] : C.w_K[wk.hidx - 2], Bc = chassis ? C.pl_B[0] : C.w_B[wk.hidx - 2];
+    const T imp = impedance(solimp, dd);
+    const T R0 = mjmax(N::minval, (T(1) - imp) * N::rcp_(imp) * tran * (T(1) + mu * mu));
+    con.D = (dd < T(0)) ? N::rcp_(T(2) * mureg2 * R0) : T(0);
+    T u[3], wv[2], vel[3], fn[3], ft1[3], ft2[3];
+    contact_cols(w, wk, xb, u, wv);
+    if (chassis) { u[0] = u[1] = u[2] = T(0); wv[0] = wv[1] = T(0); }
+    // frame axes in the body frame from the packed permutation: world axis j in body coordinates is row j of R
+    {
+      const Perm<T> pf = perm_unpack<T>(code);
+      const T* Rx = k.R; const T* Ry = k.R + 3; const T* Rz = k.R + 6;
+      const T* an = pf.pat == 0 ? Rx : (pf.pat == 1 ? Ry : Rz);
+      const T* a1 = pf.pat == 1 ? Rz : Ry;
+      const T* a2 = pf.pat == 0 ? Rz : Rx;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { fn[i] = pf.sn * an[i]; ft1[i] = pf.s1 * a1[i]; ft2[i] = pf.s2 * a2[i]; }
+    }
+    project_point(fn, ft1, ft2, xb, u, wv, vb, e.om, chassis ? T(0) : w.dsp, chassis ? T(0) : dsteer, vel);
+    con.z[0] = Bc * vel[0] + Kc * imp * dd;
+    con.z[1] = Bc * vel[1];
+    con.z[2] = Bc * vel[2];
+    con.zv[0] = con.zv[1] = con.zv[2] = T(0);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) con.x[i] = k.R[3 * i] * xb[0] + k.R[3 * i + 1] * xb[1] + k.R[3 * i + 2] * xb[2];
+  }
+  // place an extra contact into the next free extra slot of the wheel record (static slot indices keep register records in registers)
+  ACKB_HD static void place_extra(WheelT& w, const Contact<T>& con, unsigned code, int& nfound, unsigned& fcode, StepDiag& diag) {
+    if (NC > 2) {
+      if (nfound == 0) w.con[NC > 2 ? NC - 2 : 0] = con;
+      else if (nfound == 1) w.con[NC - 1] = con;
+      else { diag.unsupported = 1; return; }
+      fcode |= (code & 255u) << (8 * nfound);
+      ++nfound;
+    } else diag.unsupported = 1;
   }
 
   ACKB_HD static void make_shared_rows(const Consts<T>& C, const State& e, SharedRows<T>& s) {
@@ -1075,9 +1275,11 @@ struct Sim {
           ACKB_CONTACTS_BEGIN(c)
             Contact<T>& con = w.con[c];
             T u[3], wv[3], y[3];
-            contact_cols_w(w, stw, sv.ezw, con.x, u, wv);
-            point_accel_w(con.x, u, wv, x_sh, x_sh + 3, w.x, ast, y);
-            perm_apply(perm_unpack<T>(c < 2 ? perm_pack(0) : ((w.fcode >> (8 * (c - 2))) & 255u)), y, con.zv);
+            const unsigned code = slot_code(w, c);
+            const T cpl = slot_coupling(code);      // 0 for a chassis-plate contact (no spin / steer column), 1 for a wheel contact
+            contact_cols_w(w, stw * cpl, sv.ezw, con.x, u, wv);
+            point_accel_w(con.x, u, wv, x_sh, x_sh + 3, w.x * cpl, ast, y);
+            perm_apply(perm_unpack<T>(code), y, con.zv);
           ACKB_CONTACTS_END
         }
         team_sum_n(acc, TL);
@@ -1108,7 +1310,7 @@ struct Sim {
             unsigned zone = (q != T(0)) ? 1u : (f > T(0) ? 0u : 2u);
             ACKB_CONTACTS_BEGIN(c)
               const Contact<T>& con = w.con[c];
-              const T mu = wk.mu;
+              const T mu = slot_mu(C, wk, slot_code(w, c));
               // rows x_r = z_n +- mu z_t at the trial point and their slopes j_r (select form, no divergent branches)
               const T jn = con.zv[0], j1 = mu * con.zv[1], j2 = mu * con.zv[2];
               const T xn = con.z[0] + alpha * jn, x1 = mu * con.z[1] + alpha * j1, x2 = mu * con.z[2] + alpha * j2;
@@ -1188,11 +1390,13 @@ struct Sim {
         T Hsl[3] = {T(0), T(0), T(0)}, Hsa[3] = {T(0), T(0), T(0)}, Hss = T(0);
         T bl[3] = {T(0), T(0), T(0)}, ba[3] = {T(0), T(0), T(0)}, bs = T(0);
         T gl[3] = {T(0), T(0), T(0)}, ga[3] = {T(0), T(0), T(0)}, gst = T(0);
-        const T mu = wk.mu;
         ACKB_CONTACTS_BEGIN(c)
           const Contact<T>& con = w.con[c];
           T phi[3], qq[4];
-          const Perm<T> pf = perm_unpack<T>(c < 2 ? perm_pack(0) : ((w.fcode >> (8 * (c - 2))) & 255u));
+          const unsigned code = slot_code(w, c);
+          const T mu = slot_mu(C, wk, code);
+          const T cpl = slot_coupling(code);
+          const Perm<T> pf = perm_unpack<T>(code);
           pyramid_rows(con.D, mu, con.z, phi, qq);
           {
             const unsigned zb = (qq[0] != T(0) ? 1u : 0u) | (qq[1] != T(0) ? 2u : 0u) | (qq[2] != T(0) ? 4u : 0u) | (qq[3] != T(0) ? 8u : 0u);
@@ -1205,7 +1409,9 @@ struct Sim {
           perm_sym(pf, con.D * W00, con.D * W11, con.D * W22, con.D * W01, con.D * W02, S3);
           const T X[3] = {con.x[0], con.x[1], con.x[2]};
           T u[3], wv[3];
-          contact_cols_w(w, wk.isL + wk.isR, sv.ezw, X, u, wv);
+          contact_cols_w(w, (wk.isL + wk.isR) * cpl, sv.ezw, X, u, wv);
+#pragma unroll
+          for (int i = 0; i < 3; ++i) u[i] *= cpl;
           Hll[0] += S3[0][0]; Hll[1] += S3[1][0]; Hll[2] += S3[1][1]; Hll[3] += S3[2][0]; Hll[4] += S3[2][1]; Hll[5] += S3[2][2];
           // (ang, lin) block: column j = X x S3[:, j];  (ang, ang) block: column j = X x (S3 g_j), g_j = e_j x X
           T Cj[3][3];
@@ -1344,13 +1550,60 @@ struct Sim {
 #pragma unroll
     for (int i = 0; i < 8; ++i) bpart[i] = T(0);
     bool warm_ok = true;
+    // can a chassis plate touch anything in this pose?  floor: a bounding point of the plates at or below the plane; boxes: the
+    // chassis within reach of an occupied cell (checked per plate inside plate_contacts).  Warp-uniform (the exact routines diverge badly).
+    bool plates_near = false;
+    if (NC > 2 && C.pl_count[0] != T(0)) {
+      bool near = C.pl_box[0] != T(0);
+      const int nh = (int)C.nhull[0];
+      const T hO = e.p[2] - C.plane_z[0];
+#pragma unroll 1
+      for (int i = 0; i < nh; ++i) near = near || (dot3(k.n, &C.hull_pts[3 * i]) + hO <= T(0));
+      plates_near = Tm::any(near);
+    }
 #pragma unroll 1
     for (int s = 0; s < WPL; ++s) {
       const int wi = wheel_index(lane, s);
       const WheelK<T> wk = wheel_consts(C, wi);
       WheelT& w = wh[s];
-      collide_wheel(C, e, k, vb, wi, lane & 1, wk, w, diag);
-      if (NC > 2) collide_boxes(C, e, k, vb, wi, wk, w, diag);
+      T tri[8];
+      tri[7] = T(0);
+      collide_wheel(C, e, k, vb, wi, lane & 1, wk, w, diag, NC > 2 ? tri : nullptr);
+      if (NC > 2) {
+        // extra contact slots of this wheel (NC - 2, NC - 1): wheel-vs-box contacts, the cap-down triangle points of the wheel, and this
+        // wheel's share of the chassis-plate contacts (plate wi / 2: entries 0, 1 of its list go to wheel 2p, entries 2, 3 to wheel 2p + 1)
+        int nfound = 0;
+        unsigned fcode = 0u;
+        w.con[NC - 2].D = T(0); w.con[NC - 1].D = T(0);
+        for (int i = 0; i < 3; ++i) { w.con[NC - 2].x[i] = w.con[NC - 1].x[i] = T(0); w.con[NC - 2].z[i] = w.con[NC - 1].z[i] = T(0); }
+        collide_boxes(C, e, k, vb, wi, wk, w, diag, nfound, fcode);
+        const T dst_w = wk.isL * e.dst[0] + wk.isR * e.dst[1];
+        if (tri[7] != T(0)) {
+          diag.ncon += 2;
+          Contact<T> con;
+          make_extra(C, e, k, vb, w, wk, tri, tri[6], perm_pack(0), dst_w, con);
+          place_extra(w, con, perm_pack(0), nfound, fcode, diag);
+          make_extra(C, e, k, vb, w, wk, tri + 3, tri[6], perm_pack(0), dst_w, con);
+          place_extra(w, con, perm_pack(0), nfound, fcode, diag);
+        }
+        if (C.pl_count[0] != T(0) && plates_near) {
+          T pxb[kMaxPlate][3], pdist[kMaxPlate];
+          unsigned pcode[kMaxPlate];
+          const int np = plate_contacts(C, e, k, wi >> 1, pxb, pdist, pcode);
+          const int part = wi & 1;
+          for (int j = 0; j < 2; ++j) {
+            const int idx = 2 * part + j;
+            if (idx < np) {
+              diag.ncon += 1;
+              Contact<T> con;
+              make_extra(C, e, k, vb, w, wk, pxb[idx], pdist[idx], pcode[idx], dst_w, con);
+              place_extra(w, con, pcode[idx], nfound, fcode, diag);
+            }
+          }
+          if (part == 0 && np > kMaxPlate) { diag.ncon += np - kMaxPlate; diag.unsupported = 1; }
+        }
+        w.fcode = fcode;
+      }
 #pragma unroll
       for (int i = 0; i < 3; ++i) {   // spin axis and wheel centre in world axes (solver)
         w.axw[i] = k.R[3 * i] * w.ax + k.R[3 * i + 1] * w.ay;
@@ -1389,8 +1642,9 @@ struct Sim {
       for (int s = 0; s < WPL; ++s) has_box = has_box || (wh[s].con[NC - 2].D > T(0)) || (wh[s].con[NC - 1].D > T(0));
       ncs = Tm::any(has_box) ? NC : 2;
     }
-    // plate hull vs floor: flagged only (35 mm clearance; reachable only after a roll-over)
-    if (lane == 0) {
+    // plate hull vs floor in a kernel without extra contact slots (NC = 2): flagged; the launcher routes tilted environments to the
+    // NC = 4 kernel before this can happen (ackb_kernels.cu, regime split), so the flag only fires if that guard was outrun
+    if (NC <= 2 && lane == 0) {
       const int nh = (int)C.nhull[0];
       const T hO = e.p[2] - C.plane_z[0];
 #pragma unroll 1

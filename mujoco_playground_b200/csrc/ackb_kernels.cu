@@ -54,8 +54,16 @@ struct StepArgs {
   uint8_t* done_mask;   // defer_reset: per-env done flag for the masked reset launch that follows
   int defer_reset;      // models with settle steps: the step kernel only marks finished environments, reset_kernel does the rest
   uint32_t env_base;    // global id of environment 0 of this handle (Philox streams are keyed by the GLOBAL environment id)
+  // Regime split of the flat-floor model: its fast kernels carry two floor-contact slots per wheel.  Environments tilted beyond
+  // kGeneralTilt at the start of a step (rolled over, on their side, nose down: wheel caps or chassis plates can reach the floor) are
+  // left to a second launch of the general kernel (NC = 4: two extra contact slots per wheel).  regime 0: every environment;
+  // 1: fast pass (skips and marks the tilted ones in gen_mask); 2: general pass (only the marked ones).
+  int regime;
+  uint8_t* gen_mask;
   int cta_sync;   // multi-lane kernels: re-converge the CTA once per substep (pays off only when several warps share a scheduler)
 };
+
+constexpr float kGeneralTilt = 0.8f;   // cos(36.9 deg): a plate needs > 60 deg of tilt to reach the floor, a wheel cap ~88 deg
 
 template <typename T>
 struct SoAAcc {
@@ -160,8 +168,8 @@ __global__ void __launch_bounds__(Geo<T, LANES, NC>::kBlock, Geo<T, LANES, NC>::
   stage_tables(C);
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int env_raw = tid / LANES, lane = tid % LANES;
-  const bool valid = env_raw < st.n;
-  const int env = valid ? env_raw : st.n - 1;
+  const bool valid_in = env_raw < st.n;
+  const int env = valid_in ? env_raw : st.n - 1;
   const int warp = threadIdx.x >> 5, lid = threadIdx.x & 31;
   // per-warp observation tile: its own region (4 lanes) or aliasing the warp's wheel records
   float* wtile = G::kSmemWheels ? reinterpret_cast<float*>(reinterpret_cast<T*>(smem_raw) + (size_t)warp * 32 * G::kStride)
@@ -173,6 +181,21 @@ __global__ void __launch_bounds__(Geo<T, LANES, NC>::kBlock, Geo<T, LANES, NC>::
   typename E::State e;
   SoAAcc<T> acc{st, env};
   E::load_state(acc, lane, e, wh);
+  bool valid = valid_in;
+  if (a.regime != 0) {     // CTA-uniform
+    bool general;
+    if (a.regime == 1) {
+      // cosine of the tilt angle = R_zz of the chassis = (w^2 - x^2 - y^2 + z^2) / |q|^2
+      const T qq = e.q[0] * e.q[0] + e.q[1] * e.q[1] + e.q[2] * e.q[2] + e.q[3] * e.q[3];
+      general = !((e.q[0] * e.q[0] - e.q[1] * e.q[1] - e.q[2] * e.q[2] + e.q[3] * e.q[3]) >= T(kGeneralTilt) * qq);   // NaN -> general
+      if (valid_in && lane == 0) a.gen_mask[env] = general ? 1 : 0;
+      valid = valid_in && !general;
+    } else {
+      general = a.gen_mask[env] != 0;
+      valid = valid_in && general;
+      if (!__any_sync(0xffffffffu, valid)) return;     // no CTA barrier follows in this pass (cta_sync is off)
+    }
+  }
   Episode<T> ep;
   ep.goal[0] = st.goal[env]; ep.goal[1] = st.goal[(size_t)st.n + env];
   ep.ref[0] = st.ref[env]; ep.ref[1] = st.ref[(size_t)st.n + env];
@@ -187,10 +210,17 @@ __global__ void __launch_bounds__(Geo<T, LANES, NC>::kBlock, Geo<T, LANES, NC>::
   nrow = nrow < 0 ? 0 : (nrow > EPW ? EPW : nrow);
   // coalesced store of the warp's observation tile (the warp's environments are consecutive rows), issued as soon as
   // the observation exists so that the tile storage can be reused by the last substep
+  // rows of this warp's tile that belong to environments this pass owns (regime split): bit (row * LANES)
+  const unsigned rowmask = __ballot_sync(0xffffffffu, valid && lane == 0);
+  const unsigned fullmask = __ballot_sync(0xffffffffu, valid_in && lane == 0);
   auto emit = [&]() {
     __syncwarp();
     float* dst = a.obs + (size_t)env0 * a.obs_pitch;
-    if (a.obs_pitch == a.obs_dim) {      // warp-uniform: contiguous rows, one flat coalesced copy
+    if (rowmask != fullmask) {           // warp-uniform: some rows belong to the other pass
+      for (int r = 0; r < nrow; ++r)
+        if ((rowmask >> (r * LANES)) & 1u)
+          for (int j = lid; j < a.obs_dim; j += 32) dst[(size_t)r * a.obs_pitch + j] = wtile[r * a.obs_dim + j];
+    } else if (a.obs_pitch == a.obs_dim) {      // warp-uniform: contiguous rows, one flat coalesced copy
       const int total = nrow * a.obs_dim;
       for (int i = lid; i < total; i += 32) dst[i] = wtile[i];
     } else {                             // pitched rows (e.g. 80 floats: 16-byte aligned rows for the learner's vector loads)
@@ -238,7 +268,7 @@ __global__ void __launch_bounds__(Geo<T, LANES, NC>::kBlock, Geo<T, LANES, NC>::
     }
   }
 
-  const bool do_reset = done && a.auto_reset && !a.defer_reset;
+  const bool do_reset = valid && done && a.auto_reset && !a.defer_reset;
   if (a.defer_reset) {   // CTA-uniform
     if (valid && done && a.terminal_obs)   // the finished episode's last observation was flushed to dev_obs by emit()
       for (int j = lane; j < a.obs_dim; j += LANES) a.terminal_obs[(size_t)env * a.obs_pitch + j] = a.obs[(size_t)env * a.obs_pitch + j];
@@ -370,6 +400,8 @@ struct ackb_handle {
   float *d_action = nullptr, *d_obs = nullptr, *d_reward = nullptr;
   uint8_t *d_term = nullptr, *d_trunc = nullptr;
   uint8_t* d_done = nullptr;    // per-env done mask of the deferred reset (models with settle steps)
+  uint8_t* d_gen = nullptr;     // per-env "tilted: general contact pass" mark of the flat-floor regime split
+  int general_pass = 1;         // flat-floor model: run the general-contact pass after the fast kernel (ACKB_GENERAL_PASS=0 disables)
   cudaStream_t own_stream = nullptr;
   // cross-stream ordering: ackb_step_host runs on own_stream, so it has to wait for work the caller issued through
   // ackb_step / ackb_reset on another stream (last_stream) before it touches the state arrays
@@ -435,6 +467,7 @@ int launch_one(ackb_handle* h, DevState<T>& st, const StepArgs& a, cudaStream_t 
     const size_t smem = G::smem_bytes(a.obs_dim);
     StepArgs a2 = a;
     a2.cta_sync = h->cta_sync >= 0 ? h->cta_sync : 1;   // measured on B200: faster at every batch size from 4096 to 131072 envs
+    if (a.regime == 2) a2.cta_sync = 0;                   // warps without a marked environment leave at once: no CTA barriers in this pass
     static std::atomic<int> attr[64];
     if (int rc = ensure_smem_attr(h, step_kernel<T, LANES, NC>, attr, smem)) return rc;
     step_kernel<T, LANES, NC><<<grid, G::kBlock, smem, stream>>>(st, a2, handle_consts<T>(h));
@@ -452,6 +485,18 @@ int launch_step(ackb_handle* h, DevState<T>& st, const StepArgs& a, cudaStream_t
   if constexpr (sizeof(T) == 8) return fail(h, ACKB_ERR_ARG, "tuning build: fp32 only");
   else return h->lanes >= 4 ? launch_one<T, 4, 2>(h, st, a, stream, is_reset) : launch_one<T, 1, 2>(h, st, a, stream, is_reset);
 #else
+  if (!scene && !is_reset && h->general_pass) {
+    // flat-floor model: fast kernel (two floor-contact slots per wheel) for the upright environments, then the general kernel
+    // (extra slots: cap-down wheel points, chassis plates) for the environments the fast pass marked as tilted
+    StepArgs f = a;
+    f.regime = 1; f.gen_mask = h->d_gen;
+    int rc = h->lanes == 8 ? launch_one<T, 8, 1>(h, st, f, stream, false)
+                           : (h->lanes >= 4 ? launch_one<T, 4, 2>(h, st, f, stream, false) : launch_one<T, 1, 2>(h, st, f, stream, false));
+    if (rc) return rc;
+    StepArgs g = a;
+    g.regime = 2; g.gen_mask = h->d_gen;
+    return launch_one<T, 4, 4>(h, st, g, stream, false);
+  }
   if (h->lanes == 8 && !scene) return launch_one<T, 8, 1>(h, st, a, stream, is_reset);   // one lane per floor contact (flat-floor model)
   if (h->lanes >= 4) return scene ? launch_one<T, 4, 4>(h, st, a, stream, is_reset) : launch_one<T, 4, 2>(h, st, a, stream, is_reset);
   return scene ? launch_one<T, 1, 4>(h, st, a, stream, is_reset) : launch_one<T, 1, 2>(h, st, a, stream, is_reset);
@@ -507,6 +552,9 @@ int ackb_create(const double* consts, size_t consts_len, int num_envs, int devic
   CK(cudaMalloc(&h->d_trunc, n));
   CK(cudaMalloc(&h->d_done, n));
   CK(cudaMemset(h->d_done, 0, n));
+  CK(cudaMalloc(&h->d_gen, n));
+  CK(cudaMemset(h->d_gen, 0, n));
+  if (const char* ev = getenv("ACKB_GENERAL_PASS")) h->general_pass = atoi(ev);
   CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&h->order_ev, cudaEventDisableTiming));
   *out = h;
@@ -517,7 +565,7 @@ int ackb_destroy(ackb_handle* h) {
   if (!h) return ACKB_ERR_ARG;
   cudaSetDevice(h->device);
   cudaFree(h->state); cudaFree(h->stats); cudaFree(h->d_action); cudaFree(h->d_obs); cudaFree(h->d_reward);
-  cudaFree(h->d_term); cudaFree(h->d_trunc); cudaFree(h->d_done);
+  cudaFree(h->d_term); cudaFree(h->d_trunc); cudaFree(h->d_done); cudaFree(h->d_gen);
   if (h->order_ev) cudaEventDestroy(h->order_ev);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete[] h->consts_host;

@@ -46,6 +46,7 @@
 #define MAXCON 64
 #define MAXEFC 300
 #define MAXHULL 128
+#define MAXADJ 24
 
 #define MINVAL 1e-15
 #define MINIMP 0.0001
@@ -82,6 +83,8 @@ typedef struct {
   double geom_size[MAXG * 3], geom_pos[MAXG * 3], geom_quat[MAXG * 4], geom_friction[MAXG * 3], geom_solref[MAXG * 2],
       geom_solimp[MAXG * 5], geom_solmix[MAXG], geom_margin[MAXG], geom_gap[MAXG], geom_alpha[MAXG];
   double hull_vert[MAXHULL * 3];
+  int hull_adj[MAXHULL * MAXADJ];   /* hull graph: neighbours of every hull vertex (local indices, -1 padded), MuJoCo's MakeGraph order */
+  double geom_rbound[MAXG];
   /* sites / sensors */
   int site_bodyid[MAXS];
   double site_pos[MAXS * 3], site_quat[MAXS * 4];
@@ -498,6 +501,86 @@ static int cylinder_box(const double* cpos, const double* cmat, const double* cs
   return 1;
 }
 
+/* Plane (g1) vs convex mesh (g2), MuJoCo's mjc_PlaneConvex [MJ-knowledge, VERIFY against a golden dump]: the support vertex of the
+   hull in the direction -normal gives the first contact (none if its distance exceeds the margin); for meshes the neighbours of
+   that vertex in the hull graph are then tried in graph order: a neighbour within the margin and at least tolplanemesh * rbound
+   (0.3 x bounding radius) away from the first contact adds a contact, up to 3 contacts in all.  pos is midway between the surfaces. */
+static int plane_convex(const OModel* m, int g2, const double* pos1, const double* mat1, const double* pos2, const double* mat2,
+                        double margin, double* dist_out, double* pos_out) {
+  const double normal[3] = {mat1[2], mat1[5], mat1[8]};
+  const int adr = m->geom_hulladr[g2], nv = m->geom_hullnum[g2];
+  double pw[MAXHULL * 3], dist[MAXHULL];
+  int best = -1;
+  for (int v = 0; v < nv; v++) {
+    double t[3], dif[3];
+    mulmatvec3(t, mat2, m->hull_vert + 3 * (adr + v));
+    for (int k = 0; k < 3; k++) { pw[3 * v + k] = t[k] + pos2[k]; dif[k] = pw[3 * v + k] - pos1[k]; }
+    dist[v] = dot3(dif, normal);
+    if (best < 0 || dist[v] < dist[best]) best = v;
+  }
+  if (best < 0 || dist[best] > margin) return 0;
+  int cnt = 0;
+  dist_out[0] = dist[best];
+  for (int k = 0; k < 3; k++) pos_out[k] = pw[3 * best + k] - normal[k] * dist[best] * 0.5;
+  cnt = 1;
+  const double tol = 0.3 * m->geom_rbound[g2];
+  for (int e = 0; e < MAXADJ && cnt < 3; e++) {
+    const int v = m->hull_adj[(adr + best) * MAXADJ + e];
+    if (v < 0) break;
+    double d[3] = {pw[3 * v] - pw[3 * best], pw[3 * v + 1] - pw[3 * best + 1], pw[3 * v + 2] - pw[3 * best + 2]};
+    if (norm3(d) < tol) continue;
+    if (dist[v] > margin) continue;
+    dist_out[cnt] = dist[v];
+    for (int k = 0; k < 3; k++) pos_out[3 * cnt + k] = pw[3 * v + k] - normal[k] * dist[v] * 0.5;
+    cnt++;
+  }
+  return cnt;
+}
+
+/* Box (g1) vs convex mesh (g2): analytic single contact, the counterpart of cylinder_box for the chassis plates against the maze
+   blocks.  MuJoCo sends the pair to its general convex collider (one contact along the minimum-penetration direction).  Here: over
+   the box's face normals n, the hull's support distance d(n) = min over vertices of (n . v - half); the face with the largest d is
+   the contact face, contact if d <= margin.  The contact point is the weighted mean of the hull vertices within `blend` of the
+   deepest one (weights fall linearly to zero), so that an edge or a face of the plate resting against the block gives its
+   middle and the point moves continuously with the pose.  Normal from the box to the mesh.  Edge / corner axes are not tested. */
+#define PLATE_BLEND 1e-3
+static int box_convex(const OModel* m, int g2, const double* bpos, const double* bmat, const double* bsize, const double* pos2,
+                      const double* mat2, double margin, double* dist_out, double* pos_out, double* normal_out) {
+  const int adr = m->geom_hulladr[g2], nv = m->geom_hullnum[g2];
+  double pl[MAXHULL * 3];
+  for (int v = 0; v < nv; v++) {
+    double t[3], rel[3];
+    mulmatvec3(t, mat2, m->hull_vert + 3 * (adr + v));
+    for (int k = 0; k < 3; k++) rel[k] = t[k] + pos2[k] - bpos[k];
+    mulmatTvec3(pl + 3 * v, bmat, rel);       /* vertex in the box frame */
+  }
+  double best = -1e300; int bk = 0, bs = 1;
+  for (int k = 0; k < 3; k++)
+    for (int sg = -1; sg <= 1; sg += 2) {
+      double dmin = 1e300;
+      for (int v = 0; v < nv; v++) { double d = sg * pl[3 * v + k] - bsize[k]; if (d < dmin) dmin = d; }
+      if (dmin > best) { best = dmin; bk = k; bs = sg; }
+    }
+  if (best > margin) return 0;
+  double wsum = 0, p[3] = {0, 0, 0};
+  for (int v = 0; v < nv; v++) {
+    double d = bs * pl[3 * v + bk] - bsize[bk];
+    double w = 1.0 - (d - best) / PLATE_BLEND;
+    if (w <= 0) continue;
+    wsum += w;
+    for (int k = 0; k < 3; k++) p[k] += w * pl[3 * v + k];
+  }
+  for (int k = 0; k < 3; k++) p[k] /= wsum;
+  p[bk] -= bs * best * 0.5;                    /* midway between the surfaces */
+  double n[3] = {0, 0, 0}, pw[3], nw[3];
+  n[bk] = bs;                                  /* from the box towards the mesh */
+  mulmatvec3(pw, bmat, p);
+  mulmatvec3(nw, bmat, n);
+  for (int k = 0; k < 3; k++) { pos_out[k] = pw[k] + bpos[k]; normal_out[k] = nw[k]; }
+  dist_out[0] = best;
+  return 1;
+}
+
 static void mix_params(const OModel* m, OContact* con, int g1, int g2) {
   /* equal priority assumed (all geoms priority 0): condim max, friction max, solref/solimp solmix-weighted */
   con->dim = m->geom_condim[g1] > m->geom_condim[g2] ? m->geom_condim[g1] : m->geom_condim[g2];
@@ -552,14 +635,13 @@ static void o_collision(const OModel* m, OData* d) {
         int n = plane_cylinder(pos1, mat1, pos2, mat2, m->geom_size + 3 * g2, margin, dist, pos);
         for (int k = 0; k < n; k++) add_contact(m, d, g1, g2, dist[k], pos + 3 * k, normal, margin, gap);
       } else if (t1 == G_PLANE && t2 == G_MESH) {
-        /* plane vs convex hull: only reachable after a roll-over (35 mm clearance); flagged, not generated */
-        double normal[3] = {mat1[2], mat1[5], mat1[8]};
-        for (int v = 0; v < m->geom_hullnum[g2]; v++) {
-          double pw[3], dif[3];
-          mulmatvec3(pw, mat2, m->hull_vert + 3 * (m->geom_hulladr[g2] + v));
-          for (int k = 0; k < 3; k++) dif[k] = pw[k] + pos2[k] - pos1[k];
-          if (dot3(dif, normal) <= margin) { d->unsupported_contact = 1; break; }
-        }
+        double dist[3], pos[9], normal[3] = {mat1[2], mat1[5], mat1[8]};
+        int n = plane_convex(m, g2, pos1, mat1, pos2, mat2, margin, dist, pos);
+        for (int k = 0; k < n; k++) add_contact(m, d, g1, g2, dist[k], pos + 3 * k, normal, margin, gap);
+      } else if (t1 == G_BOX && t2 == G_MESH) {
+        double dist[1], pos[3], normal[3];
+        if (box_convex(m, g2, pos1, mat1, m->geom_size + 3 * g1, pos2, mat2, margin, dist, pos, normal))
+          add_contact(m, d, g1, g2, dist[0], pos, normal, margin, gap);
       } else if (t1 == G_CYLINDER && t2 == G_BOX) {
         double dist[1], pos[3], normal[3];
         if (cylinder_box(pos1, mat1, m->geom_size + 3 * g1, pos2, mat2, m->geom_size + 3 * g2, margin, dist, pos, normal))
@@ -1101,7 +1183,7 @@ static const Field model_fields[] = {
     MF(geom_type, 1), MF(geom_bodyid, 1), MF(geom_contype, 1), MF(geom_conaffinity, 1), MF(geom_condim, 1),
     MF(geom_priority, 1), MF(geom_hulladr, 1), MF(geom_hullnum, 1), MF(geom_size, 0), MF(geom_pos, 0), MF(geom_quat, 0),
     MF(geom_friction, 0), MF(geom_solref, 0), MF(geom_solimp, 0), MF(geom_solmix, 0), MF(geom_margin, 0), MF(geom_gap, 0),
-    MF(geom_alpha, 0), MF(hull_vert, 0), MF(site_bodyid, 1), MF(site_pos, 0), MF(site_quat, 0), MF(sensor_type, 1),
+    MF(geom_alpha, 0), MF(hull_vert, 0), MF(hull_adj, 1), MF(geom_rbound, 0), MF(site_bodyid, 1), MF(site_pos, 0), MF(site_quat, 0), MF(sensor_type, 1),
     MF(sensor_objid, 1), MF(sensor_adr, 1), MF(sensor_cutoff, 0), MF(eq_obj1id, 1), MF(eq_obj2id, 1), MF(eq_data, 0),
     MF(eq_solref, 0), MF(eq_solimp, 0), MF(actuator_trnid, 1), MF(actuator_ctrllimited, 1), MF(actuator_forcelimited, 1),
     MF(actuator_gear, 0), MF(actuator_gainprm, 0), MF(actuator_biasprm, 0), MF(actuator_ctrlrange, 0),

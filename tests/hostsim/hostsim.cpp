@@ -8,6 +8,7 @@
 
 using namespace ackb;
 
+static int g_general = 0;
 namespace {
 template <typename T>
 struct ArrAcc {
@@ -148,24 +149,28 @@ extern "C" {
 // multi-lane emulation (v2 model only): lanes = 4 or 8
 void hs_env_step_lanes(int lanes, int f32, const double* blob, double* qpos, double* qvel, double* warm, double* epd, int* epi, const float* action,
                        int frame_skip, float* obs, float* out, int* diag) {
-  if (lanes == 4) { if (f32) env_step_team<float, 4, 2>(blob, qpos, qvel, warm, epd, epi, action, frame_skip, obs, out, diag); else env_step_team<double, 4, 2>(blob, qpos, qvel, warm, epd, epi, action, frame_skip, obs, out, diag); }
+  if (lanes == 4 && (blob[0] != 0.0 || g_general)) { if (f32) env_step_team<float, 4, 4>(blob, qpos, qvel, warm, epd, epi, action, frame_skip, obs, out, diag); else env_step_team<double, 4, 4>(blob, qpos, qvel, warm, epd, epi, action, frame_skip, obs, out, diag); }
+  else if (lanes == 4) { if (f32) env_step_team<float, 4, 2>(blob, qpos, qvel, warm, epd, epi, action, frame_skip, obs, out, diag); else env_step_team<double, 4, 2>(blob, qpos, qvel, warm, epd, epi, action, frame_skip, obs, out, diag); }
   else { if (f32) env_step_team<float, 8, 1>(blob, qpos, qvel, warm, epd, epi, action, frame_skip, obs, out, diag); else env_step_team<double, 8, 1>(blob, qpos, qvel, warm, epd, epi, action, frame_skip, obs, out, diag); }
 }
 int hs_nconsts() { return kNumConsts; }
+// general = 1: use the NC = 4 variants (extra contact slots: cap-down wheel points, chassis plates) for the flat-floor model too,
+// as the launcher does for tilted environments (ackb_kernels.cu, regime split)
+void hs_set_general(int v) { g_general = v; }
 void hs_substep(int f32, const double* blob, double* qpos, double* qvel, double* warm, const double* ctrl, int nsteps, double* tap, int* diag) {
-  const bool scene = blob[0] != 0.0;   // model_kind: the obstacle scene has two extra box-contact slots per wheel
+  const bool scene = blob[0] != 0.0 || g_general;   // model_kind: the obstacle scene has two extra box-contact slots per wheel
   if (f32) { if (scene) substep<float, 4>(blob, qpos, qvel, warm, ctrl, nsteps, tap, diag); else substep<float, 2>(blob, qpos, qvel, warm, ctrl, nsteps, tap, diag); }
   else { if (scene) substep<double, 4>(blob, qpos, qvel, warm, ctrl, nsteps, tap, diag); else substep<double, 2>(blob, qpos, qvel, warm, ctrl, nsteps, tap, diag); }
 }
 void hs_env_step(int f32, const double* blob, double* qpos, double* qvel, double* warm, double* epd, int* epi, const float* action,
                  int frame_skip, float* obs, float* out, int* diag) {
-  const bool scene = blob[0] != 0.0;
+  const bool scene = blob[0] != 0.0 || g_general;
   if (f32) { if (scene) env_step<float, 4>(blob, qpos, qvel, warm, epd, epi, action, frame_skip, obs, out, diag); else env_step<float, 2>(blob, qpos, qvel, warm, epd, epi, action, frame_skip, obs, out, diag); }
   else { if (scene) env_step<double, 4>(blob, qpos, qvel, warm, epd, epi, action, frame_skip, obs, out, diag); else env_step<double, 2>(blob, qpos, qvel, warm, epd, epi, action, frame_skip, obs, out, diag); }
 }
 void hs_env_reset(int f32, const double* blob, double* qpos, double* qvel, double* warm, double* epd, int* epi, unsigned long long seed,
                   unsigned env_id, float* obs) {
-  const bool scene = blob[0] != 0.0;
+  const bool scene = blob[0] != 0.0 || g_general;
   if (f32) { if (scene) env_reset<float, 4>(blob, qpos, qvel, warm, epd, epi, seed, env_id, obs); else env_reset<float, 2>(blob, qpos, qvel, warm, epd, epi, seed, env_id, obs); }
   else { if (scene) env_reset<double, 4>(blob, qpos, qvel, warm, epd, epi, seed, env_id, obs); else env_reset<double, 2>(blob, qpos, qvel, warm, epd, epi, seed, env_id, obs); }
 }

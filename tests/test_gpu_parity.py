@@ -619,3 +619,73 @@ def test_single_env_adapter_spaces_and_reseed():
     assert np.array_equal(o1, o2) and i1["goal_position"] == i2["goal_position"] and i1["goal_position"] != i3["goal_position"]
     assert env.observation_space.contains(o1)
     env.close()
+
+
+@pytest.mark.parametrize("dtype,tol,lanes", [("float64", 1e-6, 4), ("float64", 1e-6, 1), ("float32", 2e-3, 4), ("float32", 2e-3, 1)])
+def test_rollover_regime_split_matches_oracle(dtype, tol, lanes):
+    """Flat-floor model, tumbling robots mixed with upright ones in one batch: the fast kernel steps the upright environments, the
+    general pass (NC = 4) the tilted ones (wheel caps, chassis plates on the floor).  Per step, every environment restarted from the
+    oracle's state: contact counts exact (fp64), velocities within tolerance, unsupported = 0."""
+    from mujoco_playground_b200 import BatchedAckermannEnv
+    from oracle.oracle import OracleSim
+    M = _models()
+
+    def quat(axis, deg):
+        a = np.deg2rad(deg) / 2
+        return np.array([np.cos(a), *(np.sin(a) * np.asarray(axis, float))])
+    rng = np.random.default_rng(3)
+    poses = [(quat([1, 0, 0], 180), 0.12), (quat([0, 1, 0], 80), 0.2), (quat([1, 0, 0], 90), 0.13), (quat([0, 1, 0], -100), 0.25),
+             (quat([0, 0, 1], 30), 0.1), (quat([1, 0, 0], 10), 0.1)]
+    for _ in range(4):
+        q = rng.normal(size=4)
+        poses.append((q / np.linalg.norm(q), 0.25))
+    n = len(poses) * 4        # every pose four times: the warps mix both regimes
+    env = BatchedAckermannEnv(n, dtype=dtype, auto_reset=False, lanes_per_env=lanes, solver_tolerance=1e-12 if dtype == "float64" else None)
+    env.reset()
+    sims = []
+    for i in range(n):
+        q, z = poses[i % len(poses)]
+        o = OracleSim(M, tolerance=1e-12)
+        o.reset()
+        o.qpos[:3] = [0.3 * i, 0, z]; o.qpos[3:7] = q; o.qvel[3:6] = [1.0, -2.0, 0.5]
+        sims.append(o)
+    zero = torch.zeros((n, 2), device="cuda:0")
+    flips, maxn = 0, 0
+    for t in range(150):
+        env.set_state(np.stack([o.qpos for o in sims]), np.stack([o.qvel for o in sims]), np.stack([o.qacc_warmstart for o in sims]))
+        _, _, _, _, info = env.step(zero)
+        qv = env.get_state()[1]
+        ncon = info["ncon"].cpu().numpy()
+        for i, o in enumerate(sims):
+            o.ctrl[:] = 0      # zero action: bicycle controller gives zero controls
+            o.step()
+            flips += int(ncon[i] != o.ncon)
+            maxn = max(maxn, o.ncon)
+            if dtype == "float64":
+                assert ncon[i] == o.ncon, f"step {t} env {i}: ncon {ncon[i]} vs oracle {o.ncon}"
+            assert np.abs(qv[i] - o.qvel).max() < tol * max(1.0, np.abs(o.qvel).max()), f"step {t} env {i}"
+    st = env.stats()
+    print(f"roll-over {dtype} lanes={lanes}: contact-count flips {flips}/{150 * n}, max ncon {maxn}, unsupported {st['unsupported']}")
+    assert st["unsupported"] == 0 and maxn >= 11
+    assert flips == 0 if dtype == "float64" else flips <= 0.02 * 150 * n
+    env.close()
+
+
+def test_maze_wall_hits_use_plate_contacts():
+    """maze:umaze, full throttle into the walls: the plates reach the blocks before the wheels do; the batch stays supported and the
+    environments that drove into a wall stop there (no tunnelling through the block with the chassis)."""
+    from mujoco_playground_b200 import BatchedAckermannEnv
+    env = BatchedAckermannEnv(512, model="maze:umaze", dtype="float32", seed=9, frame_skip=4, auto_reset=False)
+    env.reset()
+    act = torch.zeros((512, 2), device="cuda:0")
+    act[:, 0] = 1.0
+    maxn = 0
+    for _ in range(400):
+        _, _, _, _, info = env.step(act)
+        maxn = max(maxn, int(info["ncon"].max().item()))
+    st = env.stats()
+    q = env.get_state()[0]
+    assert st["unsupported"] == 0 and st["bad_state"] == 0
+    assert maxn >= 9, "wheel contacts plus at least one plate-vs-block contact"
+    assert np.isfinite(q).all() and (np.abs(q[:, 2] + 0.435) < 0.05).all(), "robots stay on the maze floor (z about -0.435)"
+    env.close()

@@ -84,8 +84,10 @@ def test_frame_skip_is_repeated_substeps():
     assert np.abs(h1.qpos - h4.qpos).max() == 0 and h1.epi[0] == 4 * h4.epi[0]
 
 
-def test_unsupported_contact_flag_when_plate_touches_floor():
-    """Chassis pushed 45 mm into the floor: plane-vs-hull contact of the plates is outside the supported set and must be flagged."""
+def test_plate_pushed_into_the_floor():
+    """Chassis pushed 45 mm into the floor (upright, so the launcher's tilt guard does not route it): the fast NC = 2 kernel has no slot
+    for plane-vs-hull contacts and must FLAG the step; the general kernel generates the contacts the oracle generates."""
+    from tests.hostsim.hostsim import lib
     h = HostSim(build_consts(M, model_kind=0))
     h.qpos[:] = M["qpos0"]
     h.qpos[2] = 0.02
@@ -94,7 +96,18 @@ def test_unsupported_contact_flag_when_plate_touches_floor():
     o = OracleSim(M)
     o.qpos[2] = 0.02
     o.forward()
-    assert int(o.f("unsupported_contact")[0]) == 1
+    assert int(o.f("unsupported_contact")[0]) == 0 and any(c["geom2"] in (1, 2) for c in o.contacts())
+    lib().hs_set_general(1)
+    try:
+        g = HostSim(build_consts(M, model_kind=0))
+        g.qpos[:] = M["qpos0"]
+        g.qpos[2] = 0.02
+        g.substep(np.zeros(3))
+        # deep interpenetration: every wheel also has its two cap-independent triangle points (dist <= -r / 2), so the two extra slots
+        # of a wheel cannot hold the plate contacts as well -> flagged, but counted
+        assert g.diag[0] == o.ncon
+    finally:
+        lib().hs_set_general(0)
 
 
 def test_scene_single_substep_matches_oracle():
@@ -233,3 +246,76 @@ def test_bad_state_guard_matches_mj_reset_data():
             assert np.isfinite(obs).all() and np.abs(obs - oo).max() < 1e-5
             assert np.abs(h.qpos - o.sim.qpos).max() < 1e-9 and np.abs(h.qvel - o.sim.qvel).max() < 1e-7
         assert int(o.sim.f("nbad")[0]) == 1
+
+
+def _quat(axis, deg):
+    a = np.deg2rad(deg) / 2
+    return np.array([np.cos(a), *(np.sin(a) * np.asarray(axis, float))])
+
+
+@pytest.mark.parametrize("f32,tol", [(False, 1e-7), (True, 1e-3)])
+def test_rollover_contacts_match_oracle(f32, tol):
+    """Wheel caps on the floor (the two extra mjc_PlaneCylinder points), chassis-plate hulls on the floor (mjc_PlaneConvex) and the
+    disk-parallel-to-the-floor corner: the general (NC = 4) kernel path generates them all -- contact counts exact, nothing flagged
+    unsupported, single-step velocities within tolerance of the oracle, over tumbling trajectories from 11 poses."""
+    from tests.hostsim.hostsim import lib
+    c = build_consts(M, model_kind=0, tolerance=1e-12)
+    lib().hs_set_general(1)
+    try:
+        rng = np.random.default_rng(0)
+        cases = [(_quat([1, 0, 0], 180), 0.12), (_quat([0, 1, 0], 80), 0.2), (_quat([1, 0, 0], 90), 0.13), (_quat([0, 1, 0], 95), 0.25),
+                 (_quat([0, 1, 0], -100), 0.25)]
+        for _ in range(6):
+            q = rng.normal(size=4)
+            cases.append((q / np.linalg.norm(q), 0.25))
+        seen = set()
+        for q, z in cases:
+            o = OracleSim(M, tolerance=1e-12)
+            h = HostSim(c, f32)
+            q0 = M["qpos0"].copy(); q0[:3] = [0, 0, z]; q0[3:7] = q
+            o.reset(); o.qpos[:] = q0; o.qvel[3:6] = [1.0, -2.0, 0.5]
+            for t in range(300):
+                qo, vo, wo = o.qpos.copy(), o.qvel.copy(), o.qacc_warmstart.copy()
+                o.ctrl[:] = 0
+                o.step()
+                h.qpos[:], h.qvel[:], h.warm[:] = qo, vo, wo
+                h.substep(np.zeros(3))
+                assert h.diag[0] == o.ncon and h.diag[1] == 0, f"step {t}: ncon {h.diag[0]} vs {o.ncon}, unsupported {h.diag[1]}"
+                assert np.abs(h.qvel - o.qvel).max() < tol * max(1.0, np.abs(o.qvel).max())
+                seen |= {(cc["geom1"], cc["geom2"]) for cc in o.contacts()}
+                seen.add(("n", o.ncon))
+        assert (0, 1) in seen and (0, 2) in seen, "both plates touched the floor"
+        assert any(k[0] == "n" and k[1] >= 11 for k in seen), "wheel + plate contacts together"
+    finally:
+        lib().hs_set_general(0)
+
+
+@pytest.mark.parametrize("name", ["maze:umaze", "maze:mushr"])
+def test_plate_vs_wall_contacts_match_oracle(name):
+    """Maze models: the chassis plates (contype 2 / conaffinity 1) collide with the wall blocks (1 / 1) and reach 2 cm further forward
+    than the front wheels, so a head-on wall hit is a PLATE contact.  Kernel code and oracle generate it (box face normal, blended
+    deepest hull vertices); driving full throttle into walls: contact counts exact, single-step parity, nothing unsupported."""
+    from mujoco_playground_b200.compiler.constants import consts_layout
+    Mz = load_model(name)
+    c = build_consts(Mz, model_kind=2, tolerance=1e-12)
+    c0 = c.copy()
+    c0[consts_layout()["settle_steps"][0]] = 0
+    plate_steps = 0
+    gt = Mz["geom_type"]
+    for seed in range(3):
+        h = HostSim(c, False)
+        h.reset(seed=seed, env_id=seed)
+        h0 = HostSim(c0, False)
+        h0.reset(seed=seed, env_id=seed)
+        o = OracleEnv(Mz, kind="maze", tolerance=1e-12)
+        o.reset(h.epd[:2], spawn_qpos=h0.qpos.copy())
+        for t in range(500):
+            a = np.array([1.0, 0.3 * np.sin(0.01 * t + seed)], np.float32)
+            qo, vo, wo = o.sim.qpos.copy(), o.sim.qvel.copy(), o.sim.qacc_warmstart.copy()
+            _, _, _, _, io = o.step(a)
+            h.qpos[:], h.qvel[:], h.warm[:] = qo, vo, wo
+            _, _, _, _, info = h.step(a)
+            assert info["ncon"] == io["ncon"] and info["unsupported"] == 0, f"seed {seed} step {t}"
+            assert np.abs(h.qvel - o.sim.qvel).max() < 1e-8 * max(1.0, np.abs(o.sim.qvel).max())
+            plate_steps += int(any(gt[cc["geom1"]] == 6 and gt[cc["geom2"]] == 7 for cc in o.sim.contacts()))
+    assert plate_steps > 100, "the drive must produce plate-vs-block contacts"
