@@ -217,6 +217,7 @@ def main(argv=None):
     ap.add_argument("--backend", default="mujoco", choices=["mujoco", "oracle"])
     ap.add_argument("--efc-steps", type=int, default=50)
     ap.add_argument("--only", default="", help="comma-separated scenario names (default: all)")
+    ap.add_argument("--max-steps", type=int, default=0, help="truncate every scenario to this many steps (small fixtures)")
     a = ap.parse_args(argv)
     be = MujocoBackend if a.backend == "mujoco" else OracleBackend
     out = {"backend": np.array([a.backend], dtype="U16")}
@@ -228,6 +229,8 @@ def main(argv=None):
     for name, sc in scenarios(a.reference).items():
         if a.only and name not in a.only.split(","):
             continue
+        if a.max_steps:
+            sc = dict(sc, steps=min(sc["steps"], a.max_steps))
         rec, table = run_scenario(name, sc, be, a.efc_steps)
         out.update(rec)
         p = os.path.join(tmp, name + ".npz")
