@@ -4,29 +4,38 @@
 // forward of the two 79 -> 64 -> 64 tanh MLPs of SB3's MlpPolicy, PPO loss derivatives per sample, backward, and the weight
 // gradients summed over the minibatch (stable_baselines3 PPO.train(), called through model.learn, src/rl/train.py:175-179).
 //
-// Mapping: one persistent CTA per SM walks its tiles of 128 samples (= UMMA M) once with the policy net and once with the value net
-// (the two nets share nothing but the observation rows, whose second read comes from L2).  Thread = (sample row, half of the 64
-// columns); a thread's sample row is also its TMEM lane, so everything a thread computes stays in its lane:
+// Mapping: one persistent CTA of 512 threads per SM walks its tiles of 128 samples (= UMMA M) ONCE; each tile goes through the policy
+// net and then the value net (the observation rows are gathered from HBM once).  Thread = (sample row, quarter of the 64 columns); a
+// thread's sample row is also its TMEM lane, so everything a thread computes stays in its lane:
 //   * operands whose reduction index is the FEATURE (forward and backward-data GEMMs) are read by the tensor core straight from
-//     TMEM: the epilogue writes H1 / dZ2 back IN PLACE over the accumulator it just consumed (tcgen05.st), X is copied once from
-//     shared memory into TMEM.  No K-major activation copies exist in shared memory.
+//     TMEM: the gathered observation row goes from registers into TMEM (tcgen05.st), the epilogues write H1 / dZ2 back IN PLACE over
+//     the accumulator they just consumed.
 //   * operands whose reduction index is the SAMPLE (weight-gradient GEMMs) are the same arrays stored [sample][feature] in shared
 //     memory in SWIZZLE_128B_BASE32B, the MN-major layout the tensor core accepts for 32-bit operands (umma.cuh; probed in
-//     tools/microbench/umma_probe.cu: MN-major tf32 with any other layout type returns zeros).
-//   * five GEMM groups per tile, issued by ONE thread (58 tcgen05.mma):
-//       (1) Z1  [128 x 64] = X  W1^T        A = X   (TMEM),  B = W1   K-major SW128     -> TMEM ZA
-//       (2) Z2  [128 x 64] = H1 W2^T        A = H1  (TMEM, in place of Z1), B = W2      -> TMEM ZB (over X)
-//       (3) dH1 [128 x 64] = dZ2 W2         A = dZ2 (TMEM, in place of Z2), B = W2^T    -> TMEM ZA
-//       (4) dW2 [ 64 x 65] += dZ2^T [H1|1]  A = dZ2 MN-major, B = [H1 | ones] MN-major  -> TMEM GW2 (kept across tiles)
-//       (5) dW1 [ 64 x 80] += dZ1^T X       A = dZ1 MN-major, B = X MN-major            -> TMEM GW1 (kept across tiles)
-//     Weight-gradient accumulators leave TMEM once per net; bias gradients come out of the same GEMMs (column 79 of X and the ones
-//     block are 1).  (4) and (5) run with M = 128: rows 64..127 of the A operand address the buffer that follows dZ in shared memory
-//     and produce accumulator rows that are never read.
-//   * epilogues (bias + tanh.approx, tanh', Gaussian / value heads, clipped-surrogate derivatives) on all 256 threads;
-//     head-weight gradients (3 x 64) are reduced over the samples of a warp with a transpose-reduction of shuffles.
+//     tools/microbench/umma_probe.cu: MN-major tf32 with any other layout type returns zeros).  The weight-gradient GEMMs are
+//     computed TRANSPOSED (D = activation^T x delta, M = 128 rows of which 64 / 65 / 80 are real, N = 64), so every accumulator is 64
+//     TMEM columns and both nets' accumulators stay resident over all tiles of the CTA.
+//   * the weights (W1, W2, W2^T of one net, K-major SWIZZLE_128B, TF32-rounded) do not fit next to one tile for both nets, so a
+//     small kernel writes their shared-memory images to global memory once per launch and the CTA streams them: as soon as the MMA
+//     group that read a weight buffer has completed, one thread issues the bulk copy (cp.async.bulk, mbarrier completion) of the
+//     OTHER net's matrix into it -- it lands several phases before its first use.
+//   * six GEMM groups per tile and net, issued by ONE thread (74 tcgen05.mma):
+//       (1) Z1  [128 x 64] = X  W1^T         A = X   (TMEM),            B = W1   K-major            -> TMEM ZA
+//       (2) Z2  [128 x 64] = H1 W2^T         A = H1  (TMEM, over Z1),   B = W2                      -> TMEM ZB
+//       (3) dH1 [128 x 64] = dZ2 W2          A = dZ2 (TMEM, over Z2),   B = W2^T                    -> TMEM ZA
+//       (4) dW2^T [65 x 64] += [H1|1]^T dZ2  A = [H1 | ones] MN-major,  B = dZ2 MN-major            -> TMEM GW2[net]
+//       (5) dW1^T [80 x 64] += X^T dZ1       A = X MN-major,            B = dZ1 MN-major            -> TMEM GW1[net]
+//       (6) dW3^T [64 x 3]  += H2^T dOut     A = H2 MN-major,           B = [1 | dOut] MN-major, N = 16 -> TMEM GW3[net]
+//     Bias gradients come out of the same GEMMs (column 79 of X and column 0 of the ones block are 1); the loss derivatives dOut
+//     of a sample are written into columns 1, 2 of its row of the ones block.  Rows of an A operand beyond its real extent address
+//     whatever follows the buffer (inside the allocation) and produce accumulator rows that are never read.
+//   * epilogues (bias + tanh.approx, tanh', Gaussian / value heads, clipped-surrogate derivatives) on all 512 threads.
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+
+#include <type_traits>
+#include <utility>
 
 #include "ackb.h"
 #include "ackb_ppo_common.cuh"
@@ -38,31 +47,32 @@ namespace {
 using namespace umma;
 
 constexpr int TM = 128;          // samples per tile
-constexpr int NT5 = 256;
-constexpr uint32_t BLK = 16384;  // one SW128 block of 128 rows
+constexpr int NT5 = 512;
+constexpr uint32_t BLK = 16384;  // one BASE32B block of 128 rows x 32 columns
 
 // shared-memory map (bytes from a 1024-aligned base)
-constexpr uint32_t O_DZ = 0;                 // [2 blocks] BASE32B  dZ2, then dZ1 [sample][64]
-constexpr uint32_t O_H1 = O_DZ + 2 * BLK;    // [3 blocks] BASE32B  H1 [sample][64] | block 2: column 0 = 1   (blocks 0, 1 double as rows 64..127 of the padded A operand)
-constexpr uint32_t O_X = O_H1 + 3 * BLK;     // [3 blocks] BASE32B  observation tile [sample][80], column 79 = 1 for real samples
-constexpr uint32_t O_W1 = O_X + 3 * BLK;     // [3 blocks of 64 rows] K-major SW128  W1 of the current net
-constexpr uint32_t O_W2 = O_W1 + 3 * 8192;   // [2 blocks of 64 rows] K-major SW128  W2   [out][in]
-constexpr uint32_t O_W2T = O_W2 + 2 * 8192;  // [2 blocks of 64 rows] K-major SW128  W2^T [in][out]
-constexpr uint32_t O_F = O_W2T + 2 * 8192;   // floats from here
-constexpr int F_B1 = 0, F_B2 = 128, F_W3 = 256, F_B3 = 448, F_LS = 452, F_SC = 456, F_DO = F_SC + TM * 8, F_PART = F_DO + TM * 4,
-              F_END = F_PART + TM * 8;
-constexpr uint32_t O_BAR = O_F + F_END * 4;      // mbarrier (8 bytes) + TMEM base (4 bytes)
-constexpr uint32_t SMEM_BYTES = O_BAR + 16 + 1024;   // + alignment slack
+constexpr uint32_t O_DZ = 0;                  // [2 blocks] dZ2, then dZ1 [sample][64]
+constexpr uint32_t O_H1 = O_DZ + 2 * BLK;     // [2 blocks] H1 [sample][64]
+constexpr uint32_t O_ONE = O_H1 + 2 * BLK;    // [1 block]  column 0 = 1, columns 1, 2 = dOut of the current net (must follow H1: row 64 of (4))
+constexpr uint32_t O_H2 = O_ONE + BLK;        // [2 blocks] H2 [sample][64]
+constexpr uint32_t O_X = O_H2 + 2 * BLK;      // [3 blocks] observation tile [sample][80], column 79 = 1 for real samples
+constexpr uint32_t O_W1 = O_X + 3 * BLK;      // [3 blocks of 64 rows] K-major SW128  W1 of the net in flight
+constexpr uint32_t W1_BYTES = 3 * 8192, W2_BYTES = 2 * 8192;
+constexpr uint32_t O_W2 = O_W1 + W1_BYTES;    // [2 blocks of 64 rows] W2   [out][in]
+constexpr uint32_t O_W2T = O_W2 + W2_BYTES;   // [2 blocks of 64 rows] W2^T [in][out]
+constexpr uint32_t IMG_BYTES = W1_BYTES + 2 * W2_BYTES;     // weight images of one net in global memory: W1 | W2 | W2^T
+constexpr uint32_t O_F = O_W2T + W2_BYTES;    // floats from here
+constexpr int F_B1 = 0, F_B2 = 128, F_W3 = 256, F_B3 = 448, F_LS = 452, F_SC = 456, F_PART = F_SC + TM * 5, F_END = F_PART + TM * 8;
+constexpr uint32_t O_BAR = O_F + F_END * 4;          // mbarriers: MMA completion, 3 weight buffers; TMEM base
+constexpr uint32_t SMEM_BYTES = O_BAR + 48 + 1024;   // + alignment slack
 static_assert(SMEM_BYTES <= 232448, "shared memory budget of one SM (227 KB)");
 
-// TMEM columns: ZA = Z1 -> H1 (in place) -> dH1;  ZB = X (80 columns) -> Z2 -> dZ2 (in place);  weight-gradient accumulators of the net
-constexpr uint32_t C_ZA = 0, C_ZB = 64, C_GW1 = 144, C_GW2 = 224;
+// TMEM columns: X (A operand of (1) of both nets); ZA = Z1 -> H1 (in place) -> dH1; ZB = Z2 -> dZ2 (in place); accumulators per net
+constexpr uint32_t C_X = 0, C_ZA = 80, C_ZB = 144, C_GW1 = 208, C_GW2 = 336, C_GW3 = 464;
 
-__device__ __forceinline__ float tf32r(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
-}
+// round to TF32 (10 mantissa bits, nearest, ties away from zero = cvt.rna.tf32.f32) with two integer instructions: the cvt runs on the
+// quarter-rate conversion pipe, which the epilogues (6 conversions per activation element and net) would otherwise saturate
+__device__ __forceinline__ float tf32r(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u); }
 __device__ __forceinline__ float tanh_fast(float x) {
   float y;
   asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -72,84 +82,93 @@ __device__ __forceinline__ float tanh_fast(float x) {
 // statements): the prefetch of the next tile must be issued a whole tile ahead of its consumer
 __device__ __forceinline__ float ldg_early(const float* p) {
   float v;
-  asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  asm volatile("ld.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
   return v;
 }
 __device__ __forceinline__ float4 ldg_early4(const float* p) {
   float4 v;
-  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  asm volatile("ld.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 }
-
-// sum over the 32 lanes of a warp of 16 per-lane values; afterwards lane l holds the total of column
-// 8 * bit4(l) + 4 * bit3(l) + 2 * bit2(l) + bit1(l)  (both lanes of a pair hold the same column)
-__device__ __forceinline__ float transpose_reduce16(const float (&v)[16], int lane) {
-  float a[8], b[4], c[2];
-  {
-    const bool hi = lane & 16;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float send = hi ? v[i] : v[i + 8], keep = hi ? v[i + 8] : v[i];
-      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-  }
-  {
-    const bool hi = lane & 8;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float send = hi ? a[i] : a[i + 4], keep = hi ? a[i + 4] : a[i];
-      b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-  }
-  {
-    const bool hi = lane & 4;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const float send = hi ? b[i] : b[i + 2], keep = hi ? b[i + 2] : b[i];
-      c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-  }
-  float d;
-  {
-    const bool hi = lane & 2;
-    const float send = hi ? c[0] : c[1], keep = hi ? c[1] : c[0];
-    d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-  }
-  return d + __shfl_xor_sync(0xffffffffu, d, 1);
+__device__ __forceinline__ int64_t ldg_early_s64(const int64_t* p) {
+  int64_t v;
+  asm volatile("ld.global.s64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
 }
-__device__ __forceinline__ int transpose_reduce16_col(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
+// byte offset of feature f (a multiple of 4: one 16-byte vector) of a row inside a BASE32B array of 32-column blocks
+__device__ __forceinline__ uint32_t b32_feat(uint32_t rowoff, int rx, int f) {
+  return (uint32_t)(f >> 5) * BLK + rowoff + (uint32_t)((((((f & 31) >> 3) ^ rx) & 3) << 5) + (f & 7) * 4);
+}
+
+// 16 consecutive floats of a 64-byte aligned shared-memory vector (4 x LDS.128; the compiler cannot prove the alignment itself)
+__device__ __forceinline__ void lds16(const float* p, float (&v)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float4 x = reinterpret_cast<const float4*>(p)[i];
+    v[4 * i] = x.x; v[4 * i + 1] = x.y; v[4 * i + 2] = x.z; v[4 * i + 3] = x.w;
+  }
+}
 
 #ifdef ACKB_T5_PROFILE
-__device__ long long g_t5_prof[16];
+__device__ long long g_t5_prof[32];
 #define T5_MARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long c_ = clock64(); g_t5_prof[i] += c_ - t5_last; t5_last = c_; } } while (0)
 #else
 #define T5_MARK(i) do { } while (0)
 #endif
 
-__global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a) {
+// shared-memory images of both nets' weights: [net][W1 | W2 | W2^T], TF32-rounded, K-major SWIZZLE_128B blocks of 64 rows
+__global__ void ppo_t5_weight_images(const float* __restrict__ P, int D, unsigned char* __restrict__ img) {
+  const int net = blockIdx.x;
+  const Offsets o = offsets(D);
+  unsigned char* im = img + (size_t)net * IMG_BYTES;
+  const float* W1g = P + (net ? o.W1v : o.W1p);
+  const float* W2g = P + (net ? o.W2v : o.W2p);
+  for (int i = threadIdx.x; i < H * 96; i += blockDim.x) {
+    const int r = i / 96, k = i % 96;
+    *reinterpret_cast<float*>(im + (k >> 5) * 8192 + sw128_off(r, k & 31)) = (k < D) ? tf32r(W1g[r * D + k]) : 0.0f;
+  }
+  for (int i = threadIdx.x; i < H * H; i += blockDim.x) {
+    const int r = i >> 6, k = i & 63;
+    const float w = tf32r(W2g[i]);
+    *reinterpret_cast<float*>(im + W1_BYTES + (k >> 5) * 8192 + sw128_off(r, k & 31)) = w;
+    *reinterpret_cast<float*>(im + W1_BYTES + W2_BYTES + (r >> 5) * 8192 + sw128_off(k, r & 31)) = w;
+  }
+}
+
+__global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a, const unsigned char* __restrict__ wimg) {
 #ifdef ACKB_T5_PROFILE
   long long t5_last = clock64();
 #endif
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* const sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte aligned base, computed as an OFFSET from the __shared__ symbol: rounding the pointer through an integer makes every
+  // access below a generic LD / ST instead of LDS / STS
+  unsigned char* const sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   float* const F = reinterpret_cast<float*>(sm + O_F);
-  uint64_t* const mbar = reinterpret_cast<uint64_t*>(sm + O_BAR);
-  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(sm + O_BAR + 8);
+  uint64_t* const mbar = reinterpret_cast<uint64_t*>(sm + O_BAR);          // MMA groups
+  uint64_t* const mbw = reinterpret_cast<uint64_t*>(sm + O_BAR + 8);       // [3] weight buffers W1, W2, W2^T
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(sm + O_BAR + 32);
+  uint64_t* const mbar_bg = reinterpret_cast<uint64_t*>(sm + O_BAR + 40);     // MMAs that nothing waits for immediately
   const uint32_t sb = smem_u32(sm);
 
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int q4 = warp & 3, hf = warp >> 2;          // TMEM lane quarter of this warp, column half of this thread
+  const int q4 = warp & 3, part = warp >> 2;        // TMEM lane quarter of this warp, column quarter of this thread
   const int row = 32 * q4 + lane;                   // sample row of the tile = TMEM lane
   const uint32_t rowoff = (uint32_t)((row >> 2) * 512 + (row & 3) * 128);   // BASE32B: 4-row atoms, 32-byte chunks XOR (row & 3)
   const int rx = row & 3;
   const int D = a.D;
   const Offsets o = offsets(D);
   const float* P = a.params;
+  const int ntiles = (a.mb + TM - 1) / TM;
 
-  // ---- one-time setup: TMEM, mbarrier, ones block, small vectors of both nets
+  // ---- one-time setup: TMEM, mbarriers, ones block, small vectors of both nets
   if (warp == 0) tmem_alloc(tmem_slot, 512);
-  if (t == 32) { mbar_init(mbar, 1); mbar_fence_init(); }
-  for (int i = t; i < TM * 32; i += NT5) *reinterpret_cast<float*>(sm + O_H1 + 2 * BLK + b32_off(i >> 5, i & 31)) = ((i & 31) == 0) ? 1.0f : 0.0f;
+  if (t == 32) {
+    mbar_init(mbar, 1);
+    mbar_init(mbar_bg, 1);
+    for (int i = 0; i < 3; ++i) mbar_init(mbw + i, 1);
+    mbar_fence_init();
+  }
+  for (int i = t; i < TM * 32; i += NT5) *reinterpret_cast<float*>(sm + O_ONE + b32_off(i >> 5, i & 31)) = ((i & 31) == 0) ? 1.0f : 0.0f;
   for (int i = t; i < 3 * H; i += NT5) F[F_W3 + i] = (i < 2 * H) ? P[o.Wa + i] : P[o.Wv + (i - 2 * H)];
   if (t < 128) {
     const int net = t >> 6, r = t & 63;
@@ -164,380 +183,418 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a) {
   const uint32_t tb = *tmem_slot;
   const uint32_t tlane = tb + ((uint32_t)(32 * q4) << 16);     // this warp's TMEM lane quarter
 
+  // weight streaming (elected lane of warp 0): buffer `which` (0 W1, 1 W2, 2 W2^T) <- image of `net`
+  uint32_t wph = 0;                                            // parity of the next completion of each weight barrier (bit per buffer), tracked by every thread
+  auto load_w = [&](int which, int net) {
+    const uint32_t bytes = which == 0 ? W1_BYTES : W2_BYTES;
+    const uint32_t dst = sb + (which == 0 ? O_W1 : (which == 1 ? O_W2 : O_W2T));
+    const unsigned char* src = wimg + (size_t)net * IMG_BYTES + (which == 0 ? 0u : (which == 1 ? W1_BYTES : W1_BYTES + W2_BYTES));
+    mbar_expect_tx(mbw + which, bytes);
+    bulk_g2s(dst, src, bytes, mbw + which);
+  };
+  if (warp == 0) {
+    if (elect_one()) { load_w(0, 0); load_w(1, 0); load_w(2, 0); }
+    __syncwarp();
+  }
+
   const float adv_mean = a.adv_stats[0], adv_istd = 1.0f / (a.adv_stats[1] + 1e-8f);
   const float inv_mb = 1.0f / (float)a.mb;
   const float ls0 = F[F_LS], ls1 = F[F_LS + 1];
   const float iv0 = expf(-2.0f * ls0), iv1 = expf(-2.0f * ls1);
 
-  // per-thread sums over all tiles of this CTA
-  float g3[3][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};   // head weights: [mean0, mean1, value][16-column chunk], column = 32 hf + 16 chunk + col(lane)
-  float gb3[3] = {0.f, 0.f, 0.f}, gls0 = 0.f, gls1 = 0.f, d_pg = 0.f, d_vl = 0.f, d_kl = 0.f, d_cf = 0.f;   // threads with hf == 0
+  // per-thread sums over all tiles of this CTA (threads with part == 0: one per sample row)
+  float gb3[3] = {0.f, 0.f, 0.f}, gls0 = 0.f, gls1 = 0.f, d_pg = 0.f, d_vl = 0.f, d_kl = 0.f, d_cf = 0.f;
   uint32_t phase = 0;
   float* G = a.grads;
 
-  // issue a group of MMAs (thread 0) once every thread's shared-memory / TMEM accesses of the previous phase are done, wait for it
-  auto run_mma = [&](auto&& issue) {
-    tmem_st_wait();
-    fence_proxy_async();
+  // issue a group of MMAs once every thread's shared-memory / TMEM accesses of the previous phase are done, wait for it.  The group
+  // is issued by ONE elected lane of warp 0 inside a warp-uniform branch (elect.sync: ptxas then emits the UTCHMMA sequence straight,
+  // a threadIdx-divergent branch makes it wrap every instruction in a lane loop).
+  // ST: this phase wrote TMEM (tcgen05.st);  px_fence: a shared-memory operand written by the threads is read by this group (generic
+  // -> async proxy fence; a later fence also covers the earlier writes of the thread, so groups that read only TMEM and the
+  // bulk-copied weights skip it)
+  // `issue` = the MMAs the next epilogue needs (completion awaited here); `issue_bg` = MMAs off the critical chain, issued behind them
+  // and left running (their operands must stay untouched until wait_bg() or a later awaited group, whose commit covers them)
+  uint32_t phase_bg = 0;
+  auto wait_bg = [&]() {
+    mbar_wait(mbar_bg, phase_bg);
+    phase_bg ^= 1u;
+    fence_after_sync();
+  };
+  auto run_mma = [&](auto st, bool px_fence, auto grp, auto&& issue, auto&& issue_bg) {
+    if (decltype(st)::value) tmem_st_wait();
+    T5_MARK(15);
+    if (px_fence) fence_proxy_async();
     fence_before_sync();
+    T5_MARK(12);
     __syncthreads();
-    if (t == 0) {
-      fence_after_sync();
-      issue();
-      commit(mbar);
+    T5_MARK(13);
+    if (warp == 0) {
+      if (elect_one()) {
+        fence_after_sync();
+        issue();
+        commit(mbar);
+        if (issue_bg()) commit(mbar_bg);
+      }
+      __syncwarp();
     }
+    T5_MARK(16 + decltype(grp)::value);
     mbar_wait(mbar, phase);
     phase ^= 1u;
     fence_after_sync();
   };
+  using Yes = std::true_type;
+  using No = std::false_type;
+  // descriptor low words of the operands (K step 0); the CTA owns all 512 TMEM columns, so its TMEM base is lane 0, column 0 and the
+  // accumulator / operand TMEM addresses below are plain constants for the issuing thread
+  if (tb != 0u) __trap();
+  const uint32_t lo_w1 = kmajor_lo(sb + O_W1), lo_w2 = kmajor_lo(sb + O_W2), lo_w2t = kmajor_lo(sb + O_W2T);
+  const uint32_t lo_dz = mn32_lo(sb + O_DZ, BLK), lo_h1 = mn32_lo(sb + O_H1, BLK), lo_h2 = mn32_lo(sb + O_H2, BLK), lo_one = mn32_lo(sb + O_ONE, BLK),
+                 lo_x = mn32_lo(sb + O_X, BLK);
 
-  const int ntiles = (a.mb + TM - 1) / TM;
-  // Gather of a tile's observation rows into registers, one tile ahead of its use.  Two mappings (CTA-uniform choice):
-  //   vec   (row pitch a multiple of 4 floats and a 16-byte aligned base, e.g. pitch 80): 4 threads per row, 16-byte loads -- thread
-  //         (r4 = t >> 2, c = t & 3) holds the float4s c, c + 4, .. c + 16 of rows r4 and r4 + 64;
-  //   scalar (dense 79-float rows): 8 threads per row, 4-byte loads -- thread (rq = t >> 3, kk = t & 7) holds columns kk, kk + 8, ..
-  //         of rows rq, rq + 32, rq + 64, rq + 96.
-  // Threads t < 128 also hold the five scalars of row t.  The loads are issued in four parts spread over the tile body.
-  const bool vec = (a.pitch % 4 == 0) && ((reinterpret_cast<uintptr_t>(a.obs) & 15) == 0);
+  // Gather of a tile's observation rows into registers, one tile ahead of its use.  Four threads share a row (thread t: row t >> 2,
+  // 16-byte vectors (t & 3) + 4 j): one load instruction of a warp covers 8 rows x 64 contiguous bytes, a quarter of the L1 tag
+  // look-ups of a one-row-part-per-thread mapping.  16-byte loads when the row pitch allows (pitch 80: DRAM sectors are whole), else
+  // 4-byte loads.  Threads t < 128 also fetch the five scalars of row t.
+  const bool vec = (a.pitch % 4 == 0) && a.pitch >= KP && ((reinterpret_cast<uintptr_t>(a.obs) & 15) == 0);
   const int PT = a.pitch;
-  float px[40], psc[5];
-  int64_t prow[4], prow_sc = 0;          // global row numbers of the tile fetched NEXT (loaded one fetch earlier: no dependent-load stall)
-  const int rq = t >> 3, kk = t & 7, r4 = t >> 2, c4i = t & 3;
-  auto fetch_rows = [&](int tile) {
+  const int gr = t >> 2, gc = t & 3;
+  const uint32_t g_rowoff = (uint32_t)((gr >> 2) * 512 + (gr & 3) * 128);
+  float px[20], psn[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+  int64_t prow, prow_sc;          // global rows of the tile fetched NEXT (loaded one fetch earlier: no dependent-load stall)
+  int64_t qrow, qrow_sc;          // ... and of the tile after it: its rows are pulled into L2 a whole tile before they are loaded
+  auto row_index = [&](int tile, int r) -> int64_t {
     const int sbase = tile * TM, ns = tile < ntiles ? min(TM, a.mb - sbase) : 0;
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-      const int r = vec ? (r4 + 64 * (p & 1)) : (rq + 32 * p);
-      prow[p] = (r < ns) ? (a.idx ? a.idx[sbase + r] : (int64_t)(sbase + r)) : -1;
-    }
-    prow_sc = (t < ns) ? (a.idx ? a.idx[sbase + t] : (int64_t)(sbase + t)) : -1;
+    // (a plain load would be sunk by the compiler to its first use a tile later, and the observation loads would wait for it)
+    return (r < ns) ? (a.idx ? ldg_early_s64(a.idx + sbase + r) : (int64_t)(sbase + r)) : (int64_t)-1;
   };
-  auto fetch_part = [&](int p) {
-    if (vec) {        // part p: row pass p >> 1, float4s j = 0..2 (even p) or 3..4 (odd p)
-      const int pass = p >> 1;
-      const bool live = prow[pass] >= 0;
-      const float* src = a.obs + (live ? prow[pass] : 0) * (int64_t)PT;
-#pragma unroll
-      for (int j = 0; j < 5; ++j) {
-        if ((j < 3) == ((p & 1) == 0)) {
-          const int f = 4 * (c4i + 4 * j);
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (live && f < PT) v = ldg_early4(src + f);
-          float* d = &px[20 * pass + 4 * j];
-          d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-        }
-      }
+  // The loads of a tile are issued in several places of the previous tile's body.  Their addresses come from registers computed
+  // ONCE per tile (set_sources) from the row numbers, which were loaded a tile earlier: an address that still depended on a load in
+  // flight would wait on a scoreboard it shares with the observation loads issued just before, i.e. for a full DRAM round trip per
+  // group of loads.
+  const float* gsrc = a.obs;
+  bool glive = false;
+  int64_t gsc = -1;
+  auto set_sources = [&]() {
+    glive = prow >= 0;
+    gsrc = a.obs + (glive ? prow : 0) * (int64_t)PT + 4 * gc;
+    gsc = prow_sc;
+  };
+  auto fetch_part = [&](int j) {      // columns 16 j + 4 gc .. + 3 of row gr
+    const float* src = gsrc + 16 * j;
+    if (vec) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (glive) v = ldg_early4(src);
+      px[4 * j] = v.x; px[4 * j + 1] = v.y; px[4 * j + 2] = v.z; px[4 * j + 3] = v.w;
     } else {
-      const bool live = prow[p] >= 0;
-      const float* src = a.obs + (live ? prow[p] : 0) * (int64_t)PT;
 #pragma unroll
-      for (int j = 0; j < KP / 8; ++j) {
-        const int k = kk + 8 * j;
-        px[10 * p + j] = (live && k < D) ? ldg_early(src + k) : 0.0f;
-      }
+      for (int i = 0; i < 4; ++i) px[4 * j + i] = (glive && 16 * j + 4 * gc + i < D) ? ldg_early(src + i) : 0.0f;
     }
   };
   auto fetch_scalars = [&]() {
-    if (prow_sc >= 0) {
-      const int64_t grow = prow_sc;
-      psc[0] = ldg_early(&a.act[grow * 2]); psc[1] = ldg_early(&a.act[grow * 2 + 1]); psc[2] = ldg_early(&a.old_logp[grow]);
-      psc[3] = ldg_early(&a.adv[grow]); psc[4] = ldg_early(&a.ret[grow]);
+    if (t < TM && gsc >= 0) {
+      psn[0] = ldg_early(&a.act[gsc * 2]); psn[1] = ldg_early(&a.act[gsc * 2 + 1]); psn[2] = ldg_early(&a.old_logp[gsc]);
+      psn[3] = ldg_early(&a.adv[gsc]); psn[4] = ldg_early(&a.ret[gsc]);
     }
   };
-  auto fetch_tile = [&](int tile) {      // everything at once (first tile of a pass)
+  prow = row_index(blockIdx.x, gr); prow_sc = row_index(blockIdx.x, t);
+  set_sources();
 #pragma unroll
-    for (int p = 0; p < 4; ++p) fetch_part(p);
-    fetch_scalars();
-    fetch_rows(tile + gridDim.x);        // row numbers of the tile after this one
-  };
-  // registers -> BASE32B operand layout, rounded to TF32; columns >= D are zero except column 79 = 1 on real samples (bias gradient)
-  auto store_tile = [&](int ns) {
-    if (vec) {
-#pragma unroll
-      for (int pass = 0; pass < 2; ++pass) {
-        const int r = r4 + 64 * pass;
-        const float one = (r < ns) ? 1.0f : 0.0f;
-        const uint32_t xrow = O_X + (uint32_t)((r >> 2) * 512 + (r & 3) * 128);
-#pragma unroll
-        for (int j = 0; j < 5; ++j) {
-          const int f = 4 * (c4i + 4 * j);
-          float v[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) v[i] = (f + i < D) ? tf32r(px[20 * pass + 4 * j + i]) : ((f + i == KP - 1) ? one : 0.0f);
-          *reinterpret_cast<float4*>(sm + xrow + (uint32_t)(f >> 5) * BLK + (uint32_t)((((((f & 31) >> 3) ^ (r & 3)) & 3) << 5) + (f & 7) * 4)) =
-              make_float4(v[0], v[1], v[2], v[3]);
-        }
-      }
-    } else {
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const int r = rq + 32 * p;
-        const float one = (r < ns) ? 1.0f : 0.0f;
-        const uint32_t xrow = O_X + (uint32_t)((r >> 2) * 512 + (r & 3) * 128);
-#pragma unroll
-        for (int j = 0; j < KP / 8; ++j) {
-          const int k = kk + 8 * j;     // feature k: block k / 32, 32-byte chunk (k % 32) / 8 = j % 4, position kk inside the chunk
-          const float v = (k < D) ? tf32r(px[10 * p + j]) : ((k == KP - 1) ? one : 0.0f);
-          *reinterpret_cast<float*>(sm + xrow + (uint32_t)(k >> 5) * BLK + (uint32_t)(((((j & 3) ^ (r & 3)) & 3) << 5) + kk * 4)) = v;
-        }
+  for (int j = 0; j < 5; ++j) fetch_part(j);
+  fetch_scalars();
+  prow = row_index(blockIdx.x + gridDim.x, gr); prow_sc = row_index(blockIdx.x + gridDim.x, t);
+  qrow = row_index(blockIdx.x + 2 * gridDim.x, gr); qrow_sc = row_index(blockIdx.x + 2 * gridDim.x, t);
+  // L2 prefetch of one observation row (bulk prefetch: handled by the copy engine, no register, no L1 miss-queue entry of the warp).
+  // The loads of the row then find it in L2: a third of the DRAM latency, so the L1 miss queue turns over three times faster and the
+  // issuing warps are not held up behind it
+  auto prefetch_row = [&](int64_t r) {
+    if (gc == 0 && r >= 0) {
+      const float* p = a.obs + r * (int64_t)PT;
+      if (vec) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(KP * 4) : "memory");
+      else {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 32));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 64));
       }
     }
-    if (t < TM && t < ns) {
-#pragma unroll
-      for (int i = 0; i < 5; ++i) F[F_SC + t * 8 + i] = psc[i];
-    }
   };
+  prefetch_row(prow);
+  T5_MARK(10);
+
+  bool first = true;
 #pragma unroll 1
-  for (int net = 0; net < 2; ++net) {
-    // ---- first tile of this pass on its way, then the weights of this net (TF32-rounded) in the K-major operand layout:
-    // W1 [64][80], W2 [out][in], W2^T [in][out]
-    __syncthreads();
-    bool first = true;
-    fetch_rows(blockIdx.x);
-    if ((int)blockIdx.x < ntiles) fetch_tile(blockIdx.x);
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int ns = min(TM, a.mb - tile * TM);
+    const bool more = tile + (int)gridDim.x < ntiles;      // CTA-uniform
+    // ---- this tile's observation rows: registers -> TF32 -> shared memory in the operand layout (A operand of (5)); columns >= D
+    // are zero except column 79 = 1 on real samples (bias gradient of layer 1); the row scalars go to shared memory as well
     {
-      const float* W1g = P + (net ? o.W1v : o.W1p);
-      const float* W2g = P + (net ? o.W2v : o.W2p);
-      // W1: thread t owns row r = t / 4 and columns k = (t % 4) + 4 j: consecutive threads read consecutive words
-      {
-        const int r = t >> 2, k0 = t & 3;
-#pragma unroll 5
-        for (int j = 0; j < KP / 4; ++j) {
-          const int k = k0 + 4 * j;
-          const float w = (k < D) ? tf32r(__ldg(W1g + r * D + k)) : 0.0f;
-          *reinterpret_cast<float*>(sm + O_W1 + (k >> 5) * 8192 + sw128_off(r, k & 31)) = w;
+      const float one = (gr < ns) ? 1.0f : 0.0f;
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        float v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int f = 16 * j + 4 * gc + i;
+          v[i] = (f < D) ? tf32r(px[4 * j + i]) : ((f == KP - 1) ? one : 0.0f);
         }
+        *reinterpret_cast<float4*>(sm + O_X + b32_feat(g_rowoff, gr & 3, 16 * j + 4 * gc)) = make_float4(v[0], v[1], v[2], v[3]);
       }
-#pragma unroll 4
-      for (int i = t; i < H * H; i += NT5) {
-        const int r = i >> 6, k = i & 63;
-        const float w = tf32r(__ldg(W2g + i));
-        *reinterpret_cast<float*>(sm + O_W2 + (k >> 5) * 8192 + sw128_off(r, k & 31)) = w;
-        *reinterpret_cast<float*>(sm + O_W2T + (r >> 5) * 8192 + sw128_off(k, r & 31)) = w;
+      if (t < TM) {
+#pragma unroll
+        for (int i = 0; i < 5; ++i) F[F_SC + t * 5 + i] = psn[i];
       }
     }
-    T5_MARK(10);
-#pragma unroll 1
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const int sbase = tile * TM;
-      const int ns = min(TM, a.mb - sbase);
-      // ---- this tile's observation rows and scalars were fetched into registers one tile ahead (global latency hidden behind the
-      // previous tile's compute): round to TF32 and store into the BASE32B operand layout, then fetch the next tile
-      store_tile(ns);
-      const bool more = tile + (int)gridDim.x < ntiles;      // CTA-uniform
-      if (more) { fetch_part(0); fetch_scalars(); }
-      __syncthreads();
-      T5_MARK(0);
-      // ---- X -> TMEM (A operand of (1)): this thread's row, features 40 hf .. 40 hf + 39, into columns C_ZB + 40 hf ..
-      {
-        float v[16], w8[8];
+    T5_MARK(21);
+    // ---- prefetch of the next tile.  Two constraints place the loads: (i) a burst of all 5 x 16-byte loads per thread overruns the
+    // L1 miss queue and blocks the issuing warps for ~5 k cycles, so they are trickled out one or two at a time; (ii)
+    // fence.proxy.async (before every MMA group that reads thread-written shared memory) waits for the thread's outstanding global
+    // loads, so a load issued shortly before a fenced group puts a DRAM round trip on the critical path.  The groups (1) and (2) read
+    // only TMEM and the bulk-copied weights and are not fenced: loads go right here and into the first two phases of each net.
+    if (more) {
+      set_sources();           // rows of the next tile (numbers loaded during the previous tile)
+      fetch_part(0); fetch_part(1);
+      prefetch_row(qrow);      // rows of the tile after it -> L2
+    }
+    __syncthreads();
+    T5_MARK(0);
+    // ---- this thread's part of its own row (columns 20 part .. + 19): shared memory -> TMEM (A operand of (1) of both nets)
+    {
+      float v[16], w4[4];
 #pragma unroll
-        for (int part = 0; part < 3; ++part) {
-          const int nv = part < 2 ? 4 : 2;      // 16 + 16 + 8 features
-#pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            if (c4 < nv) {
-              const int f = 40 * hf + 16 * part + 4 * c4;
-              const float4 x = *reinterpret_cast<const float4*>(sm + O_X + (uint32_t)(f >> 5) * BLK + rowoff + (uint32_t)((((((f & 31) >> 3) ^ rx) & 3) << 5) + (f & 7) * 4));
-              if (part < 2) { v[4 * c4] = x.x; v[4 * c4 + 1] = x.y; v[4 * c4 + 2] = x.z; v[4 * c4 + 3] = x.w; }
-              else { w8[4 * c4] = x.x; w8[4 * c4 + 1] = x.y; w8[4 * c4 + 2] = x.z; w8[4 * c4 + 3] = x.w; }
-            }
-          }
-          if (part < 2) tmem_st16(tlane + C_ZB + 40 * hf + 16 * part, v);
-          else tmem_st8(tlane + C_ZB + 40 * hf + 32, w8);
-        }
+      for (int j = 0; j < 5; ++j) {
+        const float4 x = *reinterpret_cast<const float4*>(sm + O_X + b32_feat(rowoff, rx, 20 * part + 4 * j));
+        if (j < 4) { v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w; }
+        else { w4[0] = x.x; w4[1] = x.y; w4[2] = x.z; w4[3] = x.w; }
       }
-      // ---- (1) Z1 = X W1^T
-      run_mma([&] {
-        const uint32_t id = idesc_tf32(128, 64, 0, 0);
+      tmem_st16(tlane + C_X + 20 * part, v);
+      tmem_st4(tlane + C_X + 20 * part + 16, w4);
+    }
+    T5_MARK(22);
+#pragma unroll 1
+    for (int net = 0; net < 2; ++net) {
+      const bool reload = (net == 0) || more;      // the other net's weights are needed again
+      const uint32_t acc0 = first ? 0u : 1u;
+      // ---- (1) Z1 = X W1^T; for the value net the group starts with (5) of the policy net, dW1^T += X^T dZ1, which nothing of the
+      // value net's chain depends on (its operands X, dZ1 are overwritten only after later groups have completed)
+      {
+        const uint32_t par = (wph >> 0) & 1u;
+        run_mma(Yes{}, net == 1, std::integral_constant<int, 0>{}, [&] {
+          mbar_wait(mbw + 0, par);
+          const uint32_t id = idesc_tf32(128, 64, 0, 0);
 #pragma unroll
-        for (int k = 0; k < KP / 8; ++k) mma_tf32_ts(tb + C_ZA, tb + C_ZB + 8 * k, desc_kmajor(sb + O_W1 + (k >> 2) * 8192, k & 3), id, k > 0);
-      });
+          for (int k = 0; k < KP / 8; ++k) mma_tf32_ts_lohi(C_ZA, C_X + 8 * k, lo_w1 + (k >> 2) * 512 + (k & 3) * 2, KMAJOR_HI, id, k > 0);
+        }, [&] {
+          if (net == 0) return false;
+          const uint32_t id5 = idesc_tf32(128, 64, 1, 1);      // (5) of the policy net runs behind (1) of the value net
+#pragma unroll
+          for (int k = 0; k < TM / 8; ++k) mma_tf32_lohi(C_GW1, lo_x + 64 * k, MN32_HI, lo_dz + 64 * k, MN32_HI, id5, k > 0 ? 1u : acc0);
+          return true;
+        });
+        wph ^= 1u;
+      }
+      if (warp == 0 && reload) { if (elect_one()) load_w(0, net ^ 1); __syncwarp(); }
+      if (more && net == 1) fetch_part(3);
       T5_MARK(1);
-      // ---- H1 = tanh(Z1 + b1): back into TMEM in place (A operand of (2)) and into shared memory (B operand of (4), tanh' later)
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
+      // ---- H1 = tanh(Z1 + b1): back into TMEM in place (A operand of (2)) and into shared memory (A operand of (4), tanh' later)
+      {
         float v[16];
-        tmem_ld16(tlane + C_ZA + 32 * hf + 16 * ch, v);
-        const float* b1 = &F[F_B1 + 64 * net + 32 * hf + 16 * ch];
+        tmem_ld16(tlane + C_ZA + 16 * part, v);
+        float b1[16];
+        lds16(&F[F_B1 + 64 * net + 16 * part], b1);
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = tf32r(tanh_fast(v[j] + b1[j]));
-        tmem_st16(tlane + C_ZA + 32 * hf + 16 * ch, v);
+        tmem_st16(tlane + C_ZA + 16 * part, v);
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          const int cc = 4 * ch + c4;           // 16-byte vector index inside the 128-byte row of block hf
-          *reinterpret_cast<float4*>(sm + O_H1 + hf * BLK + rowoff + ((((cc >> 1) ^ rx) & 3) << 5) + (cc & 1) * 16) = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+        for (int c4 = 0; c4 < 4; ++c4)
+          *reinterpret_cast<float4*>(sm + O_H1 + b32_feat(rowoff, rx, 16 * part + 4 * c4)) = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+      }
+      if (more) {
+        if (net == 0) fetch_part(2);
+        else {
+          fetch_part(4); fetch_scalars();
+          prow = qrow; prow_sc = qrow_sc;
+          qrow = row_index(tile + 3 * (int)gridDim.x, gr); qrow_sc = row_index(tile + 3 * (int)gridDim.x, t);
         }
       }
-      if (more) fetch_part(1);
       T5_MARK(2);
       // ---- (2) Z2 = H1 W2^T
-      run_mma([&] {
-        const uint32_t id = idesc_tf32(128, 64, 0, 0);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) mma_tf32_ts(tb + C_ZB, tb + C_ZA + 8 * k, desc_kmajor(sb + O_W2 + (k >> 2) * 8192, k & 3), id, k > 0);
-      });
-      T5_MARK(3);
-      // ---- heads: H2 = tanh(Z2 + b2) of this thread's 32 columns (kept in registers), partial dot products with the head weights
-      float h2v[32];
       {
-        float p0 = 0.f, p1 = 0.f;
+        const uint32_t par = (wph >> 1) & 1u;
+        run_mma(Yes{}, false, std::integral_constant<int, 1>{}, [&] {
+          mbar_wait(mbw + 1, par);
+          const uint32_t id = idesc_tf32(128, 64, 0, 0);
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          float v[16];
-          tmem_ld16(tlane + C_ZB + 32 * hf + 16 * ch, v);
-          const int c0 = 32 * hf + 16 * ch;
-          const float* b2 = &F[F_B2 + 64 * net + c0];
-          const float* wa = &F[F_W3 + (net ? 2 * H : 0) + c0];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float h2 = tanh_fast(v[j] + b2[j]);
-            h2v[16 * ch + j] = h2;
-            p0 = fmaf(h2, wa[j], p0);
-            if (net == 0) p1 = fmaf(h2, wa[H + j], p1);
-          }
-        }
-        F[F_PART + row * 8 + hf * 4] = p0; F[F_PART + row * 8 + hf * 4 + 1] = p1;
+          for (int k = 0; k < 8; ++k) mma_tf32_ts_lohi(C_ZB, C_ZA + 8 * k, lo_w2 + (k >> 2) * 512 + (k & 3) * 2, KMAJOR_HI, id, k > 0);
+        }, [] { return false; });
+        wph ^= 2u;
+        if (net == 1) wait_bg();      // (5) of the policy net: complete by now (this group's commit covered it); dZ1 may be overwritten
       }
-      if (more) fetch_part(2);
+      if (warp == 0 && reload) { if (elect_one()) load_w(1, net ^ 1); __syncwarp(); }
+      T5_MARK(3);
+      // ---- heads: H2 = tanh(Z2 + b2) of this thread's 16 columns (registers for tanh', shared memory for (6)), partial dot
+      // products with the head weights
+      float h2v[16];
+      const float* wa = &F[F_W3 + (net ? 2 * H : 0) + 16 * part];
+      {
+        float v[16], b2[16], w0[16], p0 = 0.f, p1 = 0.f;
+        tmem_ld16(tlane + C_ZB + 16 * part, v);
+        lds16(&F[F_B2 + 64 * net + 16 * part], b2);
+        lds16(wa, w0);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float h2 = tanh_fast(v[j] + b2[j]);
+          h2v[j] = h2;
+          p0 = fmaf(h2, w0[j], p0);
+          v[j] = tf32r(h2);
+        }
+        if (net == 0) {
+          lds16(wa + H, w0);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) p1 = fmaf(h2v[j], w0[j], p1);
+        }
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4)
+          *reinterpret_cast<float4*>(sm + O_H2 + b32_feat(rowoff, rx, 16 * part + 4 * c4)) = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+        F[F_PART + row * 8 + part * 2] = p0; F[F_PART + row * 8 + part * 2 + 1] = p1;
+      }
       __syncthreads();
       T5_MARK(4);
-      // ---- PPO loss derivatives, one thread per sample (hf == 0)
-      if (hf == 0) {
-        float d0 = 0.f, d1 = 0.f;
-        if (row < ns) {
-          const float* SC = &F[F_SC + row * 8];
-          const float s0 = F[F_PART + row * 8] + F[F_PART + row * 8 + 4], s1 = F[F_PART + row * 8 + 1] + F[F_PART + row * 8 + 5];
-          if (net == 0) {
-            const float m0 = s0 + F[F_B3], m1 = s1 + F[F_B3 + 1];
-            const float e0 = SC[0] - m0, e1 = SC[1] - m1;
-            const float q0 = e0 * e0 * iv0, q1 = e1 * e1 * iv1;
-            const float logp = -0.5f * q0 - ls0 - 0.9189385332046727f - 0.5f * q1 - ls1 - 0.9189385332046727f;
-            const float A_ = (SC[3] - adv_mean) * adv_istd;
-            const float lr = logp - SC[2];
-            const float r = expf(lr);
-            const float rc = fminf(fmaxf(r, 1.0f - a.clip), 1.0f + a.clip);
-            const float u1 = A_ * r, u2 = A_ * rc;
-            const float dlogp = (u1 <= u2) ? -A_ * r : 0.0f;      // d(-min(u1, u2)) / d logp (the clipped branch has zero slope)
-            d0 = dlogp * e0 * iv0 * inv_mb; d1 = dlogp * e1 * iv1 * inv_mb;
+      // ---- PPO loss derivatives of this thread's sample: computed by all four threads of the row (no second barrier), summed into the
+      // per-launch totals and written to the ones block by the thread with part == 0
+      float d0 = 0.f, d1 = 0.f;
+      if (row < ns) {
+        const float* PR = &F[F_PART + row * 8];
+        const float* SC = &F[F_SC + row * 5];
+        const float s0 = (PR[0] + PR[2]) + (PR[4] + PR[6]), s1 = (PR[1] + PR[3]) + (PR[5] + PR[7]);
+        if (net == 0) {
+          const float m0 = s0 + F[F_B3], m1 = s1 + F[F_B3 + 1];
+          const float e0 = SC[0] - m0, e1 = SC[1] - m1;
+          const float q0 = e0 * e0 * iv0, q1 = e1 * e1 * iv1;
+          const float logp = -0.5f * q0 - ls0 - 0.9189385332046727f - 0.5f * q1 - ls1 - 0.9189385332046727f;
+          const float A_ = (SC[3] - adv_mean) * adv_istd;
+          const float lr = logp - SC[2];
+          const float r = expf(lr);
+          const float rc = fminf(fmaxf(r, 1.0f - a.clip), 1.0f + a.clip);
+          const float u1 = A_ * r, u2 = A_ * rc;
+          const float dlogp = (u1 <= u2) ? -A_ * r : 0.0f;      // d(-min(u1, u2)) / d logp (the clipped branch has zero slope)
+          d0 = dlogp * e0 * iv0 * inv_mb; d1 = dlogp * e1 * iv1 * inv_mb;
+          if (part == 0) {
             gls0 += dlogp * (q0 - 1.0f) * inv_mb; gls1 += dlogp * (q1 - 1.0f) * inv_mb;
             d_pg += -fminf(u1, u2); d_kl += (r - 1.0f) - lr; d_cf += (fabsf(r - 1.0f) > a.clip) ? 1.0f : 0.0f;
             gb3[0] += d0; gb3[1] += d1;
-          } else {
-            const float v = s0 + F[F_B3 + 2], R = SC[4];
-            d0 = a.vf_coef * 2.0f * (v - R) * inv_mb;
-            d_vl += (v - R) * (v - R);
-            gb3[2] += d0;
           }
+        } else {
+          const float v = s0 + F[F_B3 + 2], R = SC[4];
+          d0 = a.vf_coef * 2.0f * (v - R) * inv_mb;
+          if (part == 0) { d_vl += (v - R) * (v - R); gb3[2] += d0; }
         }
-        F[F_DO + row * 4] = d0; F[F_DO + row * 4 + 1] = d1;
       }
-      __syncthreads();
+      if (part == 0) {
+        float* ob = reinterpret_cast<float*>(sm + O_ONE + rowoff + (uint32_t)(rx << 5));      // columns 0..7 of this row of the ones block
+        ob[1] = tf32r(d0); ob[2] = tf32r(d1);
+      }
       T5_MARK(5);
-      // ---- dZ2 = (dOut W3) (1 - H2^2): into TMEM in place (A operand of (3)) and shared memory (A operand of (4));
-      //      head-weight gradients dOut^T H2 by transpose-reduction over the warp's rows
+      // ---- dZ2 = (dOut W3) (1 - H2^2): into TMEM in place (A operand of (3)) and shared memory (B operand of (4))
       {
-        const float d0 = F[F_DO + row * 4], d1 = F[F_DO + row * 4 + 1];
+        float v[16], w0[16];
+        lds16(wa, w0);
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-          float v[16], ga[16], gb[16];
-          const int c0 = 32 * hf + 16 * ch;
-          const float* wa = &F[F_W3 + (net ? 2 * H : 0) + c0];
+        for (int j = 0; j < 16; ++j) v[j] = d0 * w0[j];
+        if (net == 0) {
+          lds16(wa + H, w0);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float h2 = h2v[16 * ch + j];
-            ga[j] = d0 * h2;
-            gb[j] = d1 * h2;
-            const float g = (net == 0) ? fmaf(d1, wa[H + j], d0 * wa[j]) : d0 * wa[j];
-            v[j] = tf32r(g * (1.0f - h2 * h2));
-          }
-          tmem_st16(tlane + C_ZB + 32 * hf + 16 * ch, v);
-#pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            const int cc = 4 * ch + c4;
-            *reinterpret_cast<float4*>(sm + O_DZ + hf * BLK + rowoff + ((((cc >> 1) ^ rx) & 3) << 5) + (cc & 1) * 16) = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
-          }
-          const float ra = transpose_reduce16(ga, lane);
-          if (net == 0) {
-            g3[0][ch] += ra;
-            g3[1][ch] += transpose_reduce16(gb, lane);
-          } else g3[2][ch] += ra;
+          for (int j = 0; j < 16; ++j) v[j] = fmaf(d1, w0[j], v[j]);
         }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = tf32r(v[j] * (1.0f - h2v[j] * h2v[j]));
+        tmem_st16(tlane + C_ZB + 16 * part, v);
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4)
+          *reinterpret_cast<float4*>(sm + O_DZ + b32_feat(rowoff, rx, 16 * part + 4 * c4)) = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
       }
-      if (more) { fetch_part(3); fetch_rows(tile + 2 * gridDim.x); }
       T5_MARK(6);
-      // ---- (3) dH1 = dZ2 W2   and   (4) dW2 += dZ2^T [H1 | 1]
-      run_mma([&] {
-        const uint32_t id3 = idesc_tf32(128, 64, 0, 0);
+      // ---- (3) dH1 = dZ2 W2,  (4) dW2^T += [H1 | 1]^T dZ2,  (6) dW3^T += H2^T [1 | dOut]
+      {
+        const uint32_t par = (wph >> 2) & 1u;
+        run_mma(Yes{}, true, std::integral_constant<int, 2>{}, [&] {
+          mbar_wait(mbw + 2, par);
+          const uint32_t id3 = idesc_tf32(128, 64, 0, 0);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) mma_tf32_ts(tb + C_ZA, tb + C_ZB + 8 * k, desc_kmajor(sb + O_W2T + (k >> 2) * 8192, k & 3), id3, k > 0);
-        const uint32_t id4 = idesc_tf32(128, 80, 1, 1);
+          for (int k = 0; k < 8; ++k) mma_tf32_ts_lohi(C_ZA, C_ZB + 8 * k, lo_w2t + (k >> 2) * 512 + (k & 3) * 2, KMAJOR_HI, id3, k > 0);
+        }, [&] {
+          const uint32_t id4 = idesc_tf32(128, 64, 1, 1);
+          const uint32_t gw2 = C_GW2 + 64 * net, gw3 = C_GW3 + 16 * net;
 #pragma unroll
-        for (int k = 0; k < TM / 8; ++k) mma_tf32(tb + C_GW2, desc_mn32(sb + O_DZ, BLK, k), desc_mn32(sb + O_H1, BLK, k), id4, !first || k > 0);
-      });
+          for (int k = 0; k < TM / 8; ++k) mma_tf32_lohi(gw2, lo_h1 + 64 * k, MN32_HI, lo_dz + 64 * k, MN32_HI, id4, k > 0 ? 1u : acc0);
+          const uint32_t id6 = idesc_tf32(128, 16, 1, 1);
+#pragma unroll
+          for (int k = 0; k < TM / 8; ++k) mma_tf32_lohi(gw3, lo_h2 + 64 * k, MN32_HI, lo_one + 64 * k, MN32_HI, id6, k > 0 ? 1u : acc0);
+          return true;
+        });
+        wph ^= 4u;
+      }
+      if (warp == 0 && reload) { if (elect_one()) load_w(2, net ^ 1); __syncwarp(); }
       T5_MARK(7);
-      // ---- dZ1 = dH1 (1 - H1^2) -> shared memory (overwrites dZ2: (3) and (4) have completed)
-#pragma unroll
-      for (int ch = 0; ch < 2; ++ch) {
+      // ---- dZ1 = dH1 (1 - H1^2), computed while (4) and (6) still run; stored over dZ2 once they have completed
+      {
         float v[16];
-        tmem_ld16(tlane + C_ZA + 32 * hf + 16 * ch, v);
+        tmem_ld16(tlane + C_ZA + 16 * part, v);
 #pragma unroll
         for (int c4 = 0; c4 < 4; ++c4) {
-          const int cc = 4 * ch + c4;
-          const uint32_t off = hf * BLK + rowoff + ((((cc >> 1) ^ rx) & 3) << 5) + (cc & 1) * 16;
-          const float4 h = *reinterpret_cast<const float4*>(sm + O_H1 + off);
-          *reinterpret_cast<float4*>(sm + O_DZ + off) = make_float4(tf32r(v[4 * c4] * (1.0f - h.x * h.x)), tf32r(v[4 * c4 + 1] * (1.0f - h.y * h.y)),
-                                                                    tf32r(v[4 * c4 + 2] * (1.0f - h.z * h.z)), tf32r(v[4 * c4 + 3] * (1.0f - h.w * h.w)));
+          const float4 h = *reinterpret_cast<const float4*>(sm + O_H1 + b32_feat(rowoff, rx, 16 * part + 4 * c4));
+          v[4 * c4] = tf32r(v[4 * c4] * (1.0f - h.x * h.x)); v[4 * c4 + 1] = tf32r(v[4 * c4 + 1] * (1.0f - h.y * h.y));
+          v[4 * c4 + 2] = tf32r(v[4 * c4 + 2] * (1.0f - h.z * h.z)); v[4 * c4 + 3] = tf32r(v[4 * c4 + 3] * (1.0f - h.w * h.w));
         }
+        wait_bg();
+#pragma unroll
+        for (int c4 = 0; c4 < 4; ++c4)
+          *reinterpret_cast<float4*>(sm + O_DZ + b32_feat(rowoff, rx, 16 * part + 4 * c4)) = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
       }
       T5_MARK(8);
-      // ---- (5) dW1 += dZ1^T X
-      run_mma([&] {
-        const uint32_t id5 = idesc_tf32(128, 80, 1, 1);
+      // ---- (5) dW1^T += X^T dZ1 of the value net (the policy net's rides in the value net's first group); the next tile overwrites X
+      if (net == 1) {
+        run_mma(No{}, true, std::integral_constant<int, 3>{}, [&] {
+          const uint32_t id5 = idesc_tf32(128, 64, 1, 1);
 #pragma unroll
-        for (int k = 0; k < TM / 8; ++k) mma_tf32(tb + C_GW1, desc_mn32(sb + O_DZ, BLK, k), desc_mn32(sb + O_X, BLK, k), id5, !first || k > 0);
-      });
+          for (int k = 0; k < TM / 8; ++k) mma_tf32_lohi(C_GW1 + 64, lo_x + 64 * k, MN32_HI, lo_dz + 64 * k, MN32_HI, id5, k > 0 ? 1u : acc0);
+        }, [] { return false; });
+      }
       T5_MARK(9);
-      first = false;
     }
+    first = false;
+  }
 
-    // ---- weight-gradient accumulators of this net: TMEM -> global (rows 0..63 of each accumulator are real)
-    if (!first && q4 < 2) {
-      const int i = row;      // output row of the layer (0..63)
+  // ---- weight-gradient accumulators: TMEM -> global.  Accumulator row = input feature (this thread's lane), columns = output unit
 #pragma unroll 1
-      for (int ch = hf; ch < 5; ch += 2) {
-        float v[16];
-        tmem_ld16(tlane + C_GW1 + 16 * ch, v);
+  for (int net = 0; net < 2; ++net) {
+    if (q4 < 3) {
+      const int k = row;
+      float v[16];
+      tmem_ld16(tlane + C_GW1 + 64 * net + 16 * part, v);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int k = 16 * ch + j;
-          if (k < D) atomicAdd(&G[(net ? o.W1v : o.W1p) + i * D + k], v[j]);
-          else if (k == KP - 1) atomicAdd(&G[(net ? o.b1v : o.b1p) + i], v[j]);
-        }
-        tmem_ld16(tlane + C_GW2 + 16 * ch, v);
+      for (int j = 0; j < 16; ++j) {
+        const int i = 16 * part + j;
+        if (k < D) atomicAdd(&G[(net ? o.W1v : o.W1p) + i * D + k], v[j]);
+        else if (k == KP - 1) atomicAdd(&G[(net ? o.b1v : o.b1p) + i], v[j]);
+      }
+      tmem_ld16(tlane + C_GW2 + 64 * net + 16 * part, v);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int k = 16 * ch + j;
-          if (k < H) atomicAdd(&G[(net ? o.W2v : o.W2p) + i * H + k], v[j]);
-          else if (k == H) atomicAdd(&G[(net ? o.b2v : o.b2p) + i], v[j]);
-        }
+      for (int j = 0; j < 16; ++j) {
+        const int i = 16 * part + j;
+        if (k < H) atomicAdd(&G[(net ? o.W2v : o.W2p) + i * H + k], v[j]);
+        else if (k == H) atomicAdd(&G[(net ? o.b2v : o.b2p) + i], v[j]);
       }
     }
-    T5_MARK(11);
-    fence_before_sync();     // the accumulator reads above are ordered before the next net's MMAs by the barrier at the loop top
-  }
-
-  if ((lane & 1) == 0) {   // head weights: even lanes hold the column totals of their warp's 32 rows
-    const int col = transpose_reduce16_col(lane);
-#pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-      const int n = 32 * hf + 16 * ch + col;
-      atomicAdd(&G[o.Wa + n], g3[0][ch]);
-      atomicAdd(&G[o.Wa + H + n], g3[1][ch]);
-      atomicAdd(&G[o.Wv + n], g3[2][ch]);
+    if (part == 0 && q4 < 2) {      // head weights: row = hidden unit, column 1 + head
+      float v[16];
+      tmem_ld16(tlane + C_GW3 + 16 * net, v);
+      if (net == 0) { atomicAdd(&G[o.Wa + row], v[1]); atomicAdd(&G[o.Wa + H + row], v[2]); }
+      else atomicAdd(&G[o.Wv + row], v[1]);
     }
   }
-  if (hf == 0) {           // per-sample sums: one value per thread of warps 0..3
+  T5_MARK(11);
+  if (part == 0) {           // per-sample sums: one value per thread of warps 0..3
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
       gls0 += __shfl_xor_sync(0xffffffffu, gls0, off); gls1 += __shfl_xor_sync(0xffffffffu, gls1, off);
@@ -566,10 +623,10 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a) {
 }  // namespace
 
 #ifdef ACKB_T5_PROFILE
-extern "C" int ackb_ppo_t5_profile(long long* out16) {
+extern "C" int ackb_ppo_t5_profile(long long* out16) {     // 32 counters
   cudaDeviceSynchronize();
-  if (cudaMemcpyFromSymbol(out16, g_t5_prof, sizeof(long long) * 16) != cudaSuccess) return -1;
-  long long z[16] = {0};
+  if (cudaMemcpyFromSymbol(out16, g_t5_prof, sizeof(long long) * 32) != cudaSuccess) return -1;
+  long long z[32] = {0};
   cudaMemcpyToSymbol(g_t5_prof, z, sizeof z);
   return 0;
 }
@@ -577,6 +634,7 @@ extern "C" int ackb_ppo_t5_profile(long long* out16) {
 
 int launch_grad_tcgen05(const PpoArgs& a, cudaStream_t stream) {
   if (a.D >= KP) return ACKB_ERR_ARG;     // the bias gradient of layer 1 rides in column KP - 1 of the observation tile
+  if (a.mb <= 0) return ACKB_ERR_ARG;
   static bool attr_done[64] = {false};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return ACKB_ERR_NO_DEVICE;
@@ -584,11 +642,27 @@ int launch_grad_tcgen05(const PpoArgs& a, cudaStream_t stream) {
     if (cudaFuncSetAttribute(ppo_grad_kernel_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES) != cudaSuccess) return ACKB_ERR_CUDA;
     attr_done[dev] = true;
   }
+  // scratch for the weight images: a stream-ordered allocation, so that concurrent calls on different streams never share it and the
+  // call can be captured into a CUDA graph (the allocation becomes a node of the graph; a plain cudaMalloc would invalidate capture)
+  static bool pool_done[64] = {false};
+  if (dev < 64 && !pool_done[dev]) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+      unsigned long long keep = ~0ull;                  // keep freed blocks cached: the next call re-uses this one
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    pool_done[dev] = true;
+  }
+  void* img = nullptr;
+  if (cudaMallocAsync(&img, 2 * IMG_BYTES, stream) != cudaSuccess || !img) return ACKB_ERR_CUDA;
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int ntiles = (a.mb + TM - 1) / TM;
-  ppo_grad_kernel_tcgen05<<<ntiles < sms ? ntiles : sms, NT5, SMEM_BYTES, stream>>>(a);
-  return cudaGetLastError() == cudaSuccess ? ACKB_OK : ACKB_ERR_CUDA;
+  ppo_t5_weight_images<<<2, 512, 0, stream>>>(a.params, a.D, static_cast<unsigned char*>(img));
+  ppo_grad_kernel_tcgen05<<<ntiles < sms ? ntiles : sms, NT5, SMEM_BYTES, stream>>>(a, static_cast<const unsigned char*>(img));
+  const cudaError_t e = cudaGetLastError();
+  if (cudaFreeAsync(img, stream) != cudaSuccess) return ACKB_ERR_CUDA;
+  return e == cudaSuccess ? ACKB_OK : ACKB_ERR_CUDA;
 }
 
 }  // namespace ackb_ppo

@@ -69,6 +69,53 @@ __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
 }
+// The same two instructions with the descriptors given as (low word, high word): the low word holds the start address (>> 4) and the
+// leading offset, the high word is the same for every K step of an operand -- a K step is then ONE 32-bit add on the low word in the
+// issuing thread (the 64-bit shift/mask construction per instruction costs the single issuing thread ~80 cycles per MMA).
+__device__ __forceinline__ void mma_tf32_lohi(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t"
+      "}\n" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_tf32_ts_lohi(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], db, %4, p;\n\t"
+      "}\n" ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// descriptor words.  K-major SWIZZLE_128B operand (LBO 16 B, SBO 1024 B): K step k of a chain of 8192-byte blocks of 64 rows adds
+// (k >> 2) * 512 + (k & 3) * 2 to the low word.  MN-major SWIZZLE_128B_BASE32B operand (LBO = block stride, SBO 512 B): K step k adds 64 k.
+__device__ __forceinline__ uint32_t kmajor_lo(uint32_t saddr) { return ((saddr >> 4) & 0x3FFFu) | (1u << 16); }
+constexpr uint32_t KMAJOR_HI = (1024u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint32_t mn32_lo(uint32_t saddr, uint32_t block_stride) { return ((saddr >> 4) & 0x3FFFu) | (((block_stride >> 4) & 0x3FFFu) << 16); }
+constexpr uint32_t MN32_HI = (512u >> 4) | (1u << 14) | (1u << 29);
+
+// one lane of a converged warp (the same lane every time for the full mask)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // all MMAs issued so far by this thread arrive on the mbarrier when they have completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void commit(uint64_t* mbar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
@@ -93,6 +140,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
       "DONE_%=:\n\t"
       "}\n" ::"r"(smem_u32(mbar)), "r"(parity)
       : "memory");
+}
+
+// bulk copy global -> shared memory (async proxy), completion counted in bytes on an mbarrier of this CTA
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_saddr, const void* src, uint32_t bytes, uint64_t* mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_saddr), "l"(src), "r"(bytes),
+               "r"(smem_u32(mbar))
+               : "memory");
 }
 
 // TMEM allocation: one warp allocates `cols` (power of two >= 32) columns and publishes the base address in shared memory
@@ -137,6 +194,11 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
                "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
                "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const float (&v)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+               "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
                : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
