@@ -248,6 +248,9 @@ struct EnvOps {
           for (int i = 0; i < WPL; ++i) { wh[i].sp = keep[3 * i]; wh[i].dsp = keep[3 * i + 1]; wh[i].warm = keep[3 * i + 2]; }
         }
       }
+      // the lidar walk is data dependent: bring the warps of the CTA back into step before the long dynamics code (instruction fetch
+      // is shared only while they walk the same lines)
+      if (cta_sync && s == frame_skip - 1) Tm::block_sync();
       diag.ncon = 0; diag.nbox = 0; diag.bad_acc = 0;
       S::dynamics(C, e, k, ctrl, lane, wh, diag, tap, rec_stride);
       // mj_checkAcc: a bad qacc resets the data as well.  (MuJoCo then re-runs mj_forward on the reset state and integrates

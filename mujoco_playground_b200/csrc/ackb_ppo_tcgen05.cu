@@ -64,7 +64,7 @@ constexpr uint32_t IMG_BYTES = W1_BYTES + 2 * W2_BYTES;     // weight images of 
 constexpr uint32_t O_F = O_W2T + W2_BYTES;    // floats from here
 constexpr int F_B1 = 0, F_B2 = 128, F_W3 = 256, F_B3 = 448, F_LS = 452, F_SC = 456, F_PART = F_SC + TM * 5, F_END = F_PART + TM * 8;
 constexpr uint32_t O_BAR = O_F + F_END * 4;          // mbarriers: MMA completion, 3 weight buffers; TMEM base
-constexpr uint32_t SMEM_BYTES = O_BAR + 48 + 1024;   // + alignment slack
+constexpr uint32_t SMEM_BYTES = O_BAR + 56 + 1024;   // + alignment slack
 static_assert(SMEM_BYTES <= 232448, "shared memory budget of one SM (227 KB)");
 
 // TMEM columns: X (A operand of (1) of both nets); ZA = Z1 -> H1 (in place) -> dH1; ZB = Z2 -> dZ2 (in place); accumulators per net
@@ -147,7 +147,8 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a, con
   uint64_t* const mbar = reinterpret_cast<uint64_t*>(sm + O_BAR);          // MMA groups
   uint64_t* const mbw = reinterpret_cast<uint64_t*>(sm + O_BAR + 8);       // [3] weight buffers W1, W2, W2^T
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(sm + O_BAR + 32);
-  uint64_t* const mbar_bg = reinterpret_cast<uint64_t*>(sm + O_BAR + 40);     // MMAs that nothing waits for immediately
+  uint64_t* const mbar_bg = reinterpret_cast<uint64_t*>(sm + O_BAR + 40);     // (4) and (6): two issuing lanes commit to it
+  uint64_t* const mbar_bg1 = reinterpret_cast<uint64_t*>(sm + O_BAR + 48);    // (5) of the policy net behind (1) of the value net
   const uint32_t sb = smem_u32(sm);
 
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -164,7 +165,8 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a, con
   if (warp == 0) tmem_alloc(tmem_slot, 512);
   if (t == 32) {
     mbar_init(mbar, 1);
-    mbar_init(mbar_bg, 1);
+    mbar_init(mbar_bg, 2);
+    mbar_init(mbar_bg1, 1);
     for (int i = 0; i < 3; ++i) mbar_init(mbw + i, 1);
     mbar_fence_init();
   }
@@ -213,15 +215,23 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a, con
   // ST: this phase wrote TMEM (tcgen05.st);  px_fence: a shared-memory operand written by the threads is read by this group (generic
   // -> async proxy fence; a later fence also covers the earlier writes of the thread, so groups that read only TMEM and the
   // bulk-copied weights skip it)
-  // `issue` = the MMAs the next epilogue needs (completion awaited here); `issue_bg` = MMAs off the critical chain, issued behind them
-  // and left running (their operands must stay untouched until wait_bg() or a later awaited group, whose commit covers them)
-  uint32_t phase_bg = 0;
+  // `issue` = the MMAs the next epilogue needs (issued by the elected lane of warp 0, completion awaited here); `bg1` / `bg2` = MMAs off
+  // the critical chain, issued at the same time by the elected lanes of warps 1 and 2 (other schedulers; the accumulators of the three
+  // issuers are disjoint, so their relative order in the tensor pipe does not matter) -- an issuing lane is busy until the pipe has
+  // taken its MMAs, and the whole CTA waits for the slowest warp at the next group.  Each background lambda commits to its own
+  // barrier; the operands of background MMAs stay untouched until that barrier has been waited for.
+  uint32_t phase_bg = 0, phase_bg1 = 0;
   auto wait_bg = [&]() {
     mbar_wait(mbar_bg, phase_bg);
     phase_bg ^= 1u;
     fence_after_sync();
   };
-  auto run_mma = [&](auto st, bool px_fence, auto grp, auto&& issue, auto&& issue_bg) {
+  auto wait_bg1 = [&]() {
+    mbar_wait(mbar_bg1, phase_bg1);
+    phase_bg1 ^= 1u;
+    fence_after_sync();
+  };
+  auto run_mma = [&](auto st, bool px_fence, auto grp, auto&& issue, auto&& bg1, auto&& bg2) {
     if (decltype(st)::value) tmem_st_wait();
     T5_MARK(15);
     if (px_fence) fence_proxy_async();
@@ -229,12 +239,12 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a, con
     T5_MARK(12);
     __syncthreads();
     T5_MARK(13);
-    if (warp == 0) {
+    if (warp < 3) {
       if (elect_one()) {
         fence_after_sync();
-        issue();
-        commit(mbar);
-        if (issue_bg()) commit(mbar_bg);
+        if (warp == 0) { issue(); commit(mbar); }
+        else if (warp == 1) bg1();
+        else bg2();
       }
       __syncwarp();
     }
@@ -243,6 +253,7 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a, con
     phase ^= 1u;
     fence_after_sync();
   };
+  auto none = [] {};
   using Yes = std::true_type;
   using No = std::false_type;
   // descriptor low words of the operands (K step 0); the CTA owns all 512 TMEM columns, so its TMEM base is lane 0, column 0 and the
@@ -385,12 +396,12 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a, con
 #pragma unroll
           for (int k = 0; k < KP / 8; ++k) mma_tf32_ts_lohi(C_ZA, C_X + 8 * k, lo_w1 + (k >> 2) * 512 + (k & 3) * 2, KMAJOR_HI, id, k > 0);
         }, [&] {
-          if (net == 0) return false;
-          const uint32_t id5 = idesc_tf32(128, 64, 1, 1);      // (5) of the policy net runs behind (1) of the value net
+          if (net == 0) return;
+          const uint32_t id5 = idesc_tf32(128, 64, 1, 1);      // (5) of the policy net runs next to (1) of the value net
 #pragma unroll
           for (int k = 0; k < TM / 8; ++k) mma_tf32_lohi(C_GW1, lo_x + 64 * k, MN32_HI, lo_dz + 64 * k, MN32_HI, id5, k > 0 ? 1u : acc0);
-          return true;
-        });
+          commit(mbar_bg1);
+        }, none);
         wph ^= 1u;
       }
       if (warp == 0 && reload) { if (elect_one()) load_w(0, net ^ 1); __syncwarp(); }
@@ -426,9 +437,9 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a, con
           const uint32_t id = idesc_tf32(128, 64, 0, 0);
 #pragma unroll
           for (int k = 0; k < 8; ++k) mma_tf32_ts_lohi(C_ZB, C_ZA + 8 * k, lo_w2 + (k >> 2) * 512 + (k & 3) * 2, KMAJOR_HI, id, k > 0);
-        }, [] { return false; });
+        }, none, none);
         wph ^= 2u;
-        if (net == 1) wait_bg();      // (5) of the policy net: complete by now (this group's commit covered it); dZ1 may be overwritten
+        if (net == 1) wait_bg1();     // (5) of the policy net must be complete before dZ1 is overwritten (it is, long since)
       }
       if (warp == 0 && reload) { if (elect_one()) load_w(1, net ^ 1); __syncwarp(); }
       T5_MARK(3);
@@ -524,13 +535,16 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a, con
           for (int k = 0; k < 8; ++k) mma_tf32_ts_lohi(C_ZA, C_ZB + 8 * k, lo_w2t + (k >> 2) * 512 + (k & 3) * 2, KMAJOR_HI, id3, k > 0);
         }, [&] {
           const uint32_t id4 = idesc_tf32(128, 64, 1, 1);
-          const uint32_t gw2 = C_GW2 + 64 * net, gw3 = C_GW3 + 16 * net;
+          const uint32_t gw2 = C_GW2 + 64 * net;
 #pragma unroll
           for (int k = 0; k < TM / 8; ++k) mma_tf32_lohi(gw2, lo_h1 + 64 * k, MN32_HI, lo_dz + 64 * k, MN32_HI, id4, k > 0 ? 1u : acc0);
+          commit(mbar_bg);
+        }, [&] {
           const uint32_t id6 = idesc_tf32(128, 16, 1, 1);
+          const uint32_t gw3 = C_GW3 + 16 * net;
 #pragma unroll
           for (int k = 0; k < TM / 8; ++k) mma_tf32_lohi(gw3, lo_h2 + 64 * k, MN32_HI, lo_one + 64 * k, MN32_HI, id6, k > 0 ? 1u : acc0);
-          return true;
+          commit(mbar_bg);
         });
         wph ^= 4u;
       }
@@ -558,7 +572,7 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a, con
           const uint32_t id5 = idesc_tf32(128, 64, 1, 1);
 #pragma unroll
           for (int k = 0; k < TM / 8; ++k) mma_tf32_lohi(C_GW1 + 64, lo_x + 64 * k, MN32_HI, lo_dz + 64 * k, MN32_HI, id5, k > 0 ? 1u : acc0);
-        }, [] { return false; });
+        }, none, none);
       }
       T5_MARK(9);
     }
