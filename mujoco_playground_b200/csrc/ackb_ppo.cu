@@ -1213,9 +1213,6 @@ int ackb_ppo_minibatch_grad_pitched(const float* obs, int obs_pitch, const float
   if (g_use_tc < 0) { const char* ev = getenv("ACKB_PPO_TC"); g_use_tc = ev ? (atoi(ev) != 0) : 1; }
   if (mode != ACKB_PPO_MODE_DEFAULT && mode != ACKB_PPO_MODE_FP32 && mode != ACKB_PPO_MODE_TF32 && mode != ACKB_PPO_MODE_TCGEN05) return ACKB_ERR_ARG;
   if (mode == ACKB_PPO_MODE_TCGEN05) {     // Blackwell path: tcgen05.mma kind::tf32, accumulators in TMEM (ackb_ppo_tcgen05.cu)
-    const Offsets o5 = offsets(obs_dim);
-    if (cudaMemsetAsync(grads, 0, sizeof(float) * o5.total, s) != cudaSuccess) return ACKB_ERR_CUDA;
-    if (cudaMemsetAsync(diag, 0, sizeof(float) * 5, s) != cudaSuccess) return ACKB_ERR_CUDA;
     PpoArgs a5{obs, act, old_logp, adv, ret, idx, mb, obs_dim, adv_mean_std, params, grads, diag, clip_range, vf_coef, ent_coef, obs_pitch};
     return launch_grad_tcgen05(a5, s);
   }

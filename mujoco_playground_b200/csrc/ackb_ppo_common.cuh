@@ -31,7 +31,7 @@ struct PpoArgs {
   int pitch;       // floats between consecutive observation rows (>= D)
 };
 
-// tcgen05 / TMEM gradient kernel (ackb_ppo_tcgen05.cu); grads and diag must be zeroed by the caller.  Returns an ackb_status.
+// tcgen05 / TMEM gradient kernel (ackb_ppo_tcgen05.cu); zeroes grads and diag itself (in its weight-image launch).  Returns an ackb_status.
 int launch_grad_tcgen05(const PpoArgs& a, cudaStream_t stream);
 
 }  // namespace ackb_ppo

@@ -117,9 +117,13 @@ __device__ long long g_t5_prof[32];
 #endif
 
 // shared-memory images of both nets' weights: [net][W1 | W2 | W2^T], TF32-rounded, K-major SWIZZLE_128B blocks of 64 rows
-__global__ void ppo_t5_weight_images(const float* __restrict__ P, int D, unsigned char* __restrict__ img) {
+// (the same launch zeroes the gradient vector and the diagnostics, which the gradient kernel accumulates into)
+__global__ void ppo_t5_weight_images(const float* __restrict__ P, int D, unsigned char* __restrict__ img, float* __restrict__ grads,
+                                     float* __restrict__ diag) {
   const int net = blockIdx.x;
   const Offsets o = offsets(D);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < o.total; i += gridDim.x * blockDim.x) grads[i] = 0.0f;
+  if (blockIdx.x == 0 && threadIdx.x < 5) diag[threadIdx.x] = 0.0f;
   unsigned char* im = img + (size_t)net * IMG_BYTES;
   const float* W1g = P + (net ? o.W1v : o.W1p);
   const float* W2g = P + (net ? o.W2v : o.W2p);
@@ -672,7 +676,7 @@ int launch_grad_tcgen05(const PpoArgs& a, cudaStream_t stream) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int ntiles = (a.mb + TM - 1) / TM;
-  ppo_t5_weight_images<<<2, 512, 0, stream>>>(a.params, a.D, static_cast<unsigned char*>(img));
+  ppo_t5_weight_images<<<2, 512, 0, stream>>>(a.params, a.D, static_cast<unsigned char*>(img), a.grads, a.diag);
   ppo_grad_kernel_tcgen05<<<ntiles < sms ? ntiles : sms, NT5, SMEM_BYTES, stream>>>(a, static_cast<const unsigned char*>(img));
   const cudaError_t e = cudaGetLastError();
   if (cudaFreeAsync(img, stream) != cudaSuccess) return ACKB_ERR_CUDA;

@@ -29,7 +29,7 @@ class BatchedAckermannEnv:
     """
 
     def __init__(self, num_envs: int, device="cuda:0", frame_skip: int = 1, dtype="float32", seed: int = 0, model: str = "v2",
-                 auto_reset: bool = True, lanes_per_env: int = 4, lidar_index_map: str = "reference",
+                 auto_reset: bool = True, lanes_per_env: int = 0, lidar_index_map: str = "reference",
                  max_episode_steps: int = 1000, goal_distance_threshold: float = 0.5, collision_threshold: float = 0.15,
                  max_linear_velocity: float = 1.0, max_angular_velocity: float = 1.0, render_mode=None, map_spawner=None,
                  solver_tolerance: Optional[float] = None, spawn_yaw_range: float = 0.0, spawn_xy_jitter: float = 0.0,

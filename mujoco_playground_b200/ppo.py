@@ -567,7 +567,8 @@ class PPOTrainer:
                 act, logp, val = self.policy.act(obs)
                 b["obs"][t], b["act"][t], b["logp"][t], b["val"][t] = obs, act, logp, val
             if direct:      # the step kernel writes the next observation straight into the next rollout slot (or self.obs at the end)
-                nobs, rew, term, trunc, info = env.step(torch.clamp(act, -1.0, 1.0), obs_out=b["obs"][t + 1] if t + 1 < cfg.n_steps else self.obs)
+                # (the step kernel clips the action to the Box bounds itself, like the reference env: no clamp launch here)
+                nobs, rew, term, trunc, info = env.step(act, obs_out=b["obs"][t + 1] if t + 1 < cfg.n_steps else self.obs)
             else:
                 nobs, rew, term, trunc, info = env.step(torch.clamp(act, -1.0, 1.0))     # SB3 clips to the Box bounds
             # bootstrap with V(terminal observation) on time-limit truncation; evaluated for every environment and masked, so

@@ -35,3 +35,18 @@ res["env_step_ms"], _ = timed(lambda: env.step(torch.clamp(b["act"][0], -1, 1)),
 res["act_kernel_ms"], _ = timed(lambda: tr.graphed.act(b["obs"][0], b["act"][0], b["logp"][0], b["val"][0], 1, 1), 20)
 res["value_kernel_ms"], _ = timed(lambda: tr.graphed.value(b["obs"][0], tr._tv), 20)
 print(json.dumps({k: round(v, 3) for k, v in res.items()}))
+# rollout: host time to ISSUE one collect() (no sync inside) against the device time of the same work
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+import mujoco_playground_b200.ppo as P
+_sync = torch.cuda.synchronize
+t0 = time.perf_counter(); e0.record()
+torch.cuda.synchronize = lambda *a, **k: None      # collect() ends with a synchronize: measure the issue time alone
+try:
+    tr.collect()
+finally:
+    torch.cuda.synchronize = _sync
+t_issue = (time.perf_counter() - t0) * 1e3
+e1.record(); torch.cuda.synchronize()
+print(json.dumps({"collect_host_issue_ms": round(t_issue, 3), "collect_device_ms": round(e0.elapsed_time(e1), 3),
+                  "lanes": int(getattr(env, "lanes_per_env", -1)) if hasattr(env, "lanes_per_env") else None}))
