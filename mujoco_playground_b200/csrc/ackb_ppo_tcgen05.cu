@@ -109,6 +109,30 @@ __device__ __forceinline__ void lds16(const float* p, float (&v)[16]) {
   }
 }
 
+// This thread's 16 consecutive columns (col0 a multiple of 4) of its own row of a BASE32B array, as four 16-byte vectors.  Lanes are
+// consecutive rows; rows r and r + 4 (neighbouring 4-row atoms) map to the same banks, so a quarter-warp would hit every bank twice.
+// Rows of odd atoms (swap = 1) therefore take the two halves of each 32-byte chunk in the opposite order: the same instruction then
+// touches the other 16 banks.
+__device__ __forceinline__ void sts_row16(unsigned char* base, uint32_t rowoff, int rx, int swap, int col0, const float (&v)[16]) {
+#pragma unroll
+  for (int c4 = 0; c4 < 4; ++c4) {
+    const int o = c4 ^ 1;
+    const float4 x = make_float4(swap ? v[4 * o] : v[4 * c4], swap ? v[4 * o + 1] : v[4 * c4 + 1], swap ? v[4 * o + 2] : v[4 * c4 + 2],
+                                 swap ? v[4 * o + 3] : v[4 * c4 + 3]);
+    *reinterpret_cast<float4*>(base + b32_feat(rowoff, rx, col0 + 4 * (c4 ^ swap))) = x;
+  }
+}
+__device__ __forceinline__ void lds_row16(const unsigned char* base, uint32_t rowoff, int rx, int swap, int col0, float (&v)[16]) {
+  float4 t[4];
+#pragma unroll
+  for (int c4 = 0; c4 < 4; ++c4) t[c4] = *reinterpret_cast<const float4*>(base + b32_feat(rowoff, rx, col0 + 4 * (c4 ^ swap)));
+#pragma unroll
+  for (int c4 = 0; c4 < 4; ++c4) {
+    const float4 x = swap ? t[c4 ^ 1] : t[c4];
+    v[4 * c4] = x.x; v[4 * c4 + 1] = x.y; v[4 * c4 + 2] = x.z; v[4 * c4 + 3] = x.w;
+  }
+}
+
 #ifdef ACKB_T5_PROFILE
 __device__ long long g_t5_prof[32];
 #define T5_MARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) { const long long c_ = clock64(); g_t5_prof[i] += c_ - t5_last; t5_last = c_; } } while (0)
@@ -159,7 +183,7 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a, con
   const int q4 = warp & 3, part = warp >> 2;        // TMEM lane quarter of this warp, column quarter of this thread
   const int row = 32 * q4 + lane;                   // sample row of the tile = TMEM lane
   const uint32_t rowoff = (uint32_t)((row >> 2) * 512 + (row & 3) * 128);   // BASE32B: 4-row atoms, 32-byte chunks XOR (row & 3)
-  const int rx = row & 3;
+  const int rx = row & 3, swp = (row >> 2) & 1;
   const int D = a.D;
   const Offsets o = offsets(D);
   const float* P = a.params;
@@ -376,11 +400,10 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a, con
     // ---- this thread's part of its own row (columns 20 part .. + 19): shared memory -> TMEM (A operand of (1) of both nets)
     {
       float v[16], w4[4];
-#pragma unroll
-      for (int j = 0; j < 5; ++j) {
-        const float4 x = *reinterpret_cast<const float4*>(sm + O_X + b32_feat(rowoff, rx, 20 * part + 4 * j));
-        if (j < 4) { v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w; }
-        else { w4[0] = x.x; w4[1] = x.y; w4[2] = x.z; w4[3] = x.w; }
+      lds_row16(sm + O_X, rowoff, rx, swp, 20 * part, v);      // (any 4-aligned first column works: the vectors are swapped in pairs)
+      {
+        const float4 x = *reinterpret_cast<const float4*>(sm + O_X + b32_feat(rowoff, rx, 20 * part + 16));
+        w4[0] = x.x; w4[1] = x.y; w4[2] = x.z; w4[3] = x.w;
       }
       tmem_st16(tlane + C_X + 20 * part, v);
       tmem_st4(tlane + C_X + 20 * part + 16, w4);
@@ -420,9 +443,7 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a, con
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = tf32r(tanh_fast(v[j] + b1[j]));
         tmem_st16(tlane + C_ZA + 16 * part, v);
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4)
-          *reinterpret_cast<float4*>(sm + O_H1 + b32_feat(rowoff, rx, 16 * part + 4 * c4)) = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+        sts_row16(sm + O_H1, rowoff, rx, swp, 16 * part, v);
       }
       if (more) {
         if (net == 0) fetch_part(2);
@@ -468,9 +489,7 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a, con
 #pragma unroll
           for (int j = 0; j < 16; ++j) p1 = fmaf(h2v[j], w0[j], p1);
         }
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4)
-          *reinterpret_cast<float4*>(sm + O_H2 + b32_feat(rowoff, rx, 16 * part + 4 * c4)) = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+        sts_row16(sm + O_H2, rowoff, rx, swp, 16 * part, v);
         F[F_PART + row * 8 + part * 2] = p0; F[F_PART + row * 8 + part * 2 + 1] = p1;
       }
       __syncthreads();
@@ -524,9 +543,7 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a, con
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = tf32r(v[j] * (1.0f - h2v[j] * h2v[j]));
         tmem_st16(tlane + C_ZB + 16 * part, v);
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4)
-          *reinterpret_cast<float4*>(sm + O_DZ + b32_feat(rowoff, rx, 16 * part + 4 * c4)) = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+        sts_row16(sm + O_DZ, rowoff, rx, swp, 16 * part, v);
       }
       T5_MARK(6);
       // ---- (3) dH1 = dZ2 W2,  (4) dW2^T += [H1 | 1]^T dZ2,  (6) dW3^T += H2^T [1 | dOut]
@@ -556,18 +573,13 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a, con
       T5_MARK(7);
       // ---- dZ1 = dH1 (1 - H1^2), computed while (4) and (6) still run; stored over dZ2 once they have completed
       {
-        float v[16];
+        float v[16], h1[16];
         tmem_ld16(tlane + C_ZA + 16 * part, v);
+        lds_row16(sm + O_H1, rowoff, rx, swp, 16 * part, h1);
 #pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          const float4 h = *reinterpret_cast<const float4*>(sm + O_H1 + b32_feat(rowoff, rx, 16 * part + 4 * c4));
-          v[4 * c4] = tf32r(v[4 * c4] * (1.0f - h.x * h.x)); v[4 * c4 + 1] = tf32r(v[4 * c4 + 1] * (1.0f - h.y * h.y));
-          v[4 * c4 + 2] = tf32r(v[4 * c4 + 2] * (1.0f - h.z * h.z)); v[4 * c4 + 3] = tf32r(v[4 * c4 + 3] * (1.0f - h.w * h.w));
-        }
+        for (int j = 0; j < 16; ++j) v[j] = tf32r(v[j] * (1.0f - h1[j] * h1[j]));
         wait_bg();
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4)
-          *reinterpret_cast<float4*>(sm + O_DZ + b32_feat(rowoff, rx, 16 * part + 4 * c4)) = make_float4(v[4 * c4], v[4 * c4 + 1], v[4 * c4 + 2], v[4 * c4 + 3]);
+        sts_row16(sm + O_DZ, rowoff, rx, swp, 16 * part, v);
       }
       T5_MARK(8);
       // ---- (5) dW1^T += X^T dZ1 of the value net (the policy net's rides in the value net's first group); the next tile overwrites X
