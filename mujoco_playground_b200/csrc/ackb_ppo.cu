@@ -1307,6 +1307,15 @@ int ackb_ppo_act(const float* obs, int n, int obs_dim, const float* params, floa
 int ackb_ppo_act_pitched(const float* obs, int obs_pitch, int n, int obs_dim, const float* params, float* mean, float* value, float* action,
                          float* logp, uint64_t seed, uint32_t step, int value_only, void* stream) {
   if (!obs || !params || !value || n <= 0 || obs_dim <= 0 || obs_dim > KP || obs_pitch < obs_dim) return ACKB_ERR_ARG;
+  // full forward on rows the bulk-copy engine can fetch (pitch a multiple of 4 floats, <= 80, 16-byte aligned base): tcgen05 / TMEM
+  // kernel (ackb_ppo_tcgen05.cu); ACKB_PPO_ACT_T5=0 keeps the mma.sync kernel
+  static int use_t5 = -1;
+  if (use_t5 < 0) { const char* ev = getenv("ACKB_PPO_ACT_T5"); use_t5 = ev ? (atoi(ev) != 0) : 1; }
+  if (use_t5 && !value_only && (obs_pitch & 3) == 0 && obs_pitch <= KP && (reinterpret_cast<uintptr_t>(obs) & 15) == 0) {
+    NvtxRange nvtx("ackb_ppo_act");
+    ActT5Args a5{obs, n, obs_dim, obs_pitch, params, mean, value, action, logp, (unsigned long long)seed, step};
+    return launch_act_tcgen05(a5, (cudaStream_t)stream);
+  }
   ActArgs a{obs, n, obs_dim, params, mean, value, action, logp, (unsigned long long)seed, step, value_only,
             nullptr, nullptr, nullptr, 0.0f, nullptr, nullptr, obs_pitch};
   return launch_act(a, (cudaStream_t)stream);

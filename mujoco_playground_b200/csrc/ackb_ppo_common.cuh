@@ -34,4 +34,17 @@ struct PpoArgs {
 // tcgen05 / TMEM gradient kernel (ackb_ppo_tcgen05.cu); zeroes grads and diag itself (in its weight-image launch).  Returns an ackb_status.
 int launch_grad_tcgen05(const PpoArgs& a, cudaStream_t stream);
 
+// rollout forward on the same path (ackb_ppo_tcgen05.cu): mean [n][2] (may be null), value [n], and, if `action` is given, the sampled
+// action and (if `logp` is given) its log-probability, same random stream as ppo_act_kernel.  Rows `pitch` floats apart, pitch a
+// multiple of 4 and obs 16-byte aligned (the tiles are fetched with bulk copies).
+struct ActT5Args {
+  const float* obs;
+  int n, D, pitch;
+  const float* params;
+  float *mean, *value, *action, *logp;
+  unsigned long long seed;
+  unsigned step;
+};
+int launch_act_tcgen05(const ActT5Args& a, cudaStream_t stream);
+
 }  // namespace ackb_ppo

@@ -650,6 +650,212 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a, con
   if (warp == 0) tmem_dealloc(tb, 512);
 }
 
+
+// =================================================================================================================
+// Rollout forward (SB3 policy.forward() inside collect_rollouts) on the same path: both MLPs of a 128-row tile, Gaussian sample,
+// log-probability and value.  Rows are contiguous here, so a tile is ONE bulk copy (cp.async.bulk, double buffered, issued a tile
+// ahead by one thread: no registers, no load instructions in the epilogue warps).  Two MMA groups per tile:
+//   (1) [Z1p | Z1v] [128 x 128] = X [W1p ; W1v]^T    A = X (TMEM),  B = both W1 stacked, N = 128
+//   (2) Z2p = H1p W2p^T,  Z2v = H1v W2v^T            A = H1 (TMEM, in place of Z1), N = 64 each
+// Both nets' weights stay in shared memory (80 KB, staged by the CTA itself).  Same random stream as ppo_act_kernel (ackb_ppo.cu).
+// =================================================================================================================
+constexpr uint32_t A_XS = 0;                               // [2] staging buffers, row-major [128][pitch <= 80] floats
+constexpr uint32_t A_XBYTES = TM * KP * 4;
+constexpr uint32_t A_W1 = A_XS + 2 * A_XBYTES;             // [3 blocks of 128 rows] K-major SW128: rows 0..63 policy, 64..127 value
+constexpr uint32_t A_W2 = A_W1 + 3 * 16384;                // [2 nets][2 blocks of 64 rows]
+constexpr uint32_t A_F = A_W2 + 2 * W2_BYTES;
+constexpr int AF_B1 = 0, AF_B2 = 128, AF_W3 = 256, AF_B3 = 448, AF_LS = 452, AF_PART = 456, AF_END = AF_PART + TM * 12;
+constexpr uint32_t A_BAR = A_F + AF_END * 4;               // mbarriers: MMA, 2 x tile landed; TMEM base
+constexpr uint32_t A_SMEM = A_BAR + 32 + 1024;
+constexpr uint32_t CA_X = 0, CA_Z1 = 128, CA_Z2 = 256;
+
+__device__ __forceinline__ void philox_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1, uint32_t* out) {
+  for (int r = 0; r < 10; ++r) {
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1, n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__global__ void __launch_bounds__(NT5, 1) ppo_act_kernel_tcgen05(ActT5Args a) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* const sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  float* const F = reinterpret_cast<float*>(sm + A_F);
+  uint64_t* const mbar = reinterpret_cast<uint64_t*>(sm + A_BAR);
+  uint64_t* const mbx = reinterpret_cast<uint64_t*>(sm + A_BAR + 8);        // [2] tile landed
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(sm + A_BAR + 24);
+  const uint32_t sb = smem_u32(sm);
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const int q4 = warp & 3, part = warp >> 2;
+  const int row = 32 * q4 + lane;
+  const int D = a.D, PT = a.pitch;
+  const Offsets o = offsets(D);
+  const float* P = a.params;
+  const int ntiles = (a.n + TM - 1) / TM;
+
+  if (warp == 0) tmem_alloc(tmem_slot, 512);
+  if (t == 32) {
+    mbar_init(mbar, 1);
+    mbar_init(mbx, 1);
+    mbar_init(mbx + 1, 1);
+    mbar_fence_init();
+  }
+  // weights -> K-major SWIZZLE_128B operand images, TF32-rounded.  W1: 128 rows (policy, value) x 96 columns in 3 blocks of 16 KB
+  for (int i = t; i < 128 * 96; i += NT5) {
+    const int r = i / 96, k = i % 96, net = r >> 6;
+    const float w = (k < D) ? tf32r(__ldg(P + (net ? o.W1v : o.W1p) + (r & 63) * D + k)) : 0.0f;
+    *reinterpret_cast<float*>(sm + A_W1 + (k >> 5) * 16384 + sw128_off(r, k & 31)) = w;
+  }
+  for (int i = t; i < 2 * H * H; i += NT5) {
+    const int net = i >> 12, r = (i >> 6) & 63, k = i & 63;
+    *reinterpret_cast<float*>(sm + A_W2 + net * W2_BYTES + (k >> 5) * 8192 + sw128_off(r, k & 31)) = tf32r(__ldg(P + (net ? o.W2v : o.W2p) + r * H + k));
+  }
+  for (int i = t; i < 3 * H; i += NT5) F[AF_W3 + i] = (i < 2 * H) ? P[o.Wa + i] : P[o.Wv + (i - 2 * H)];
+  if (t < 128) {
+    const int net = t >> 6, r = t & 63;
+    F[AF_B1 + t] = P[(net ? o.b1v : o.b1p) + r];
+    F[AF_B2 + t] = P[(net ? o.b2v : o.b2p) + r];
+  }
+  if (t < 2) { F[AF_B3 + t] = P[o.ba + t]; F[AF_LS + t] = P[o.ls + t]; }
+  if (t == 2) F[AF_B3 + 2] = P[o.bv];
+  fence_proxy_async();           // the weight images are read by the tensor core (async proxy)
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tb = *tmem_slot;
+  if (tb != 0u) __trap();        // the CTA owns all 512 TMEM columns
+  const uint32_t tlane = ((uint32_t)(32 * q4) << 16);
+  const float ls0 = F[AF_LS], ls1 = F[AF_LS + 1];
+  const float sd0 = expf(ls0), sd1 = expf(ls1);
+  const uint32_t lo_w1 = kmajor_lo(sb + A_W1), lo_w2 = kmajor_lo(sb + A_W2);
+
+  // one thread fetches tiles: rows are contiguous, a tile is one bulk copy of ns * pitch floats
+  auto fetch = [&](int tile, int buf) {
+    const int sbase = tile * TM, ns = min(TM, a.n - sbase);
+    const uint32_t bytes = (uint32_t)ns * (uint32_t)PT * 4u;
+    mbar_expect_tx(mbx + buf, bytes);
+    bulk_g2s(sb + A_XS + buf * A_XBYTES, a.obs + (size_t)sbase * PT, bytes, mbx + buf);
+  };
+  const bool lead = (warp == 0) && elect_one();
+  if (lead && (int)blockIdx.x < ntiles) fetch(blockIdx.x, 0);
+  uint32_t phase = 0, xph = 0;       // xph: parity bit per staging buffer
+  auto run_mma = [&](auto&& issue) {
+    tmem_st_wait();
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) {
+      if (elect_one()) {
+        fence_after_sync();
+        issue();
+        commit(mbar);
+      }
+      __syncwarp();
+    }
+    mbar_wait(mbar, phase);
+    phase ^= 1u;
+    fence_after_sync();
+  };
+
+  int buf = 0;
+#pragma unroll 1
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+    const int sbase = tile * TM, ns = min(TM, a.n - sbase);
+    // ---- this thread's part of its own row (columns 20 part .. + 19): staging buffer -> TF32 -> TMEM; rows >= ns and columns >= D are 0.
+    // The other staging buffer was read by every thread before the first MMA group of the previous tile: refill it now.
+    if (lead && tile + (int)gridDim.x < ntiles) fetch(tile + gridDim.x, buf ^ 1);
+    mbar_wait(mbx + buf, (xph >> buf) & 1u);
+    xph ^= 1u << buf;
+    {
+      const float* xr = reinterpret_cast<const float*>(sm + A_XS + buf * A_XBYTES) + row * PT + 20 * part;
+      float v[16], w4[4];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (row < ns) x = *reinterpret_cast<const float4*>(xr + 4 * j);
+        const int f = 20 * part + 4 * j;
+        const float e0 = (f < D) ? tf32r(x.x) : 0.0f, e1 = (f + 1 < D) ? tf32r(x.y) : 0.0f, e2 = (f + 2 < D) ? tf32r(x.z) : 0.0f,
+                    e3 = (f + 3 < D) ? tf32r(x.w) : 0.0f;
+        if (j < 4) { v[4 * j] = e0; v[4 * j + 1] = e1; v[4 * j + 2] = e2; v[4 * j + 3] = e3; }
+        else { w4[0] = e0; w4[1] = e1; w4[2] = e2; w4[3] = e3; }
+      }
+      tmem_st16(tlane + CA_X + 20 * part, v);
+      tmem_st4(tlane + CA_X + 20 * part + 16, w4);
+    }
+    // ---- (1) [Z1p | Z1v] = X [W1p ; W1v]^T
+    run_mma([&] {
+      const uint32_t id = idesc_tf32(128, 128, 0, 0);
+#pragma unroll
+      for (int k = 0; k < KP / 8; ++k) mma_tf32_ts_lohi(CA_Z1, CA_X + 8 * k, lo_w1 + (k >> 2) * 1024 + (k & 3) * 2, KMAJOR_HI, id, k > 0);
+    });
+    // ---- H1 = tanh(Z1 + b1) of both nets, back into TMEM in place
+#pragma unroll
+    for (int net = 0; net < 2; ++net) {
+      float v[16], b1[16];
+      tmem_ld16(tlane + CA_Z1 + 64 * net + 16 * part, v);
+      lds16(&F[AF_B1 + 64 * net + 16 * part], b1);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = tf32r(tanh_fast(v[j] + b1[j]));
+      tmem_st16(tlane + CA_Z1 + 64 * net + 16 * part, v);
+    }
+    // ---- (2) Z2p = H1p W2p^T, Z2v = H1v W2v^T
+    run_mma([&] {
+      const uint32_t id = idesc_tf32(128, 64, 0, 0);
+#pragma unroll
+      for (int net = 0; net < 2; ++net)
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          mma_tf32_ts_lohi(CA_Z2 + 64 * net, CA_Z1 + 64 * net + 8 * k, lo_w2 + net * (W2_BYTES >> 4) + (k >> 2) * 512 + (k & 3) * 2, KMAJOR_HI, id, k > 0);
+    });
+    // ---- heads: partial dot products of this thread's 16 columns of H2 = tanh(Z2 + b2) with the head weights
+    {
+      float v[16], b2[16], w0[16], p0 = 0.f, p1 = 0.f, pv = 0.f;
+      tmem_ld16(tlane + CA_Z2 + 16 * part, v);
+      lds16(&F[AF_B2 + 16 * part], b2);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = tanh_fast(v[j] + b2[j]);
+      lds16(&F[AF_W3 + 16 * part], w0);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) p0 = fmaf(v[j], w0[j], p0);
+      lds16(&F[AF_W3 + H + 16 * part], w0);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) p1 = fmaf(v[j], w0[j], p1);
+      tmem_ld16(tlane + CA_Z2 + 64 + 16 * part, v);
+      lds16(&F[AF_B2 + 64 + 16 * part], b2);
+      lds16(&F[AF_W3 + 2 * H + 16 * part], w0);
+#pragma unroll
+      for (int j = 0; j < 16; ++j) pv = fmaf(tanh_fast(v[j] + b2[j]), w0[j], pv);
+      F[AF_PART + row * 12 + part * 3] = p0; F[AF_PART + row * 12 + part * 3 + 1] = p1; F[AF_PART + row * 12 + part * 3 + 2] = pv;
+    }
+    __syncthreads();
+    if (part == 0 && row < ns) {
+      const float* PR = &F[AF_PART + row * 12];
+      const float m0 = (PR[0] + PR[3]) + (PR[6] + PR[9]) + F[AF_B3], m1 = (PR[1] + PR[4]) + (PR[7] + PR[10]) + F[AF_B3 + 1];
+      const float vv = (PR[2] + PR[5]) + (PR[8] + PR[11]) + F[AF_B3 + 2];
+      const size_t grow = (size_t)(sbase + row);
+      a.value[grow] = vv;
+      if (a.mean) { a.mean[grow * 2] = m0; a.mean[grow * 2 + 1] = m1; }
+      if (a.action) {
+        uint32_t r[4];
+        philox_10(a.step, (uint32_t)grow, (uint32_t)(grow >> 32), 0x50504F41u, (uint32_t)a.seed, (uint32_t)(a.seed >> 32), r);
+        // Box-Muller on two uniforms in (0, 1]
+        const float u1 = ((float)(r[0] >> 8) + 1.0f) * (1.0f / 16777216.0f), u2 = (float)(r[1] >> 8) * (1.0f / 16777216.0f);
+        const float rad = sqrtf(-2.0f * logf(u1));
+        float sn, cs;
+        sincosf(6.283185307179586f * u2, &sn, &cs);
+        const float e0 = rad * cs, e1 = rad * sn;
+        a.action[grow * 2] = m0 + sd0 * e0; a.action[grow * 2 + 1] = m1 + sd1 * e1;
+        if (a.logp) a.logp[grow] = -0.5f * e0 * e0 - ls0 - 0.9189385332046727f - 0.5f * e1 * e1 - ls1 - 0.9189385332046727f;
+      }
+    }
+    // (the partial sums are overwritten two MMA groups later: no barrier needed here)
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
 }  // namespace
 
 #ifdef ACKB_T5_PROFILE
@@ -693,6 +899,22 @@ int launch_grad_tcgen05(const PpoArgs& a, cudaStream_t stream) {
   const cudaError_t e = cudaGetLastError();
   if (cudaFreeAsync(img, stream) != cudaSuccess) return ACKB_ERR_CUDA;
   return e == cudaSuccess ? ACKB_OK : ACKB_ERR_CUDA;
+}
+
+int launch_act_tcgen05(const ActT5Args& a, cudaStream_t stream) {
+  if (a.D <= 0 || a.D > KP || a.n <= 0 || a.pitch < a.D || a.pitch > KP || (a.pitch & 3) || (reinterpret_cast<uintptr_t>(a.obs) & 15)) return ACKB_ERR_ARG;
+  static bool attr_done[64] = {false};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return ACKB_ERR_NO_DEVICE;
+  if (dev < 64 && !attr_done[dev]) {
+    if (cudaFuncSetAttribute(ppo_act_kernel_tcgen05, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A_SMEM) != cudaSuccess) return ACKB_ERR_CUDA;
+    attr_done[dev] = true;
+  }
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int ntiles = (a.n + TM - 1) / TM;
+  ppo_act_kernel_tcgen05<<<ntiles < sms ? ntiles : sms, NT5, A_SMEM, stream>>>(a);
+  return cudaGetLastError() == cudaSuccess ? ACKB_OK : ACKB_ERR_CUDA;
 }
 
 }  // namespace ackb_ppo

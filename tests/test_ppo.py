@@ -317,11 +317,12 @@ def test_fused_learner_update_matches_eager_update():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("obs_dim,n", [(79, 5000), (43, 777)])
-def test_fused_act_kernel_matches_policy_forward(obs_dim, n):
-    """ppo_act_kernel (rollout forward on TF32 tiles): mean and value against the torch policy, the sampled action is
-    mean + exp(log_std) * eps with eps ~ N(0, 1) (moments checked), its log-probability matches the Gaussian density, the noise
-    stream is reproducible per (seed, step) and differs between steps; value-only mode gives the same values."""
+@pytest.mark.parametrize("obs_dim,n,pitch", [(79, 5000, 0), (43, 777, 0), (79, 5000, 80), (79, 131, 80), (79, 70000, 80), (43, 777, 44)])
+def test_fused_act_kernel_matches_policy_forward(obs_dim, n, pitch):
+    """Rollout forward (ppo_act_kernel on mma.sync TF32 tiles for dense rows; ppo_act_kernel_tcgen05 for rows pitched to a multiple of
+    4 floats, what PPOTrainer feeds it): mean and value against the torch policy, the sampled action is mean + exp(log_std) * eps
+    with eps ~ N(0, 1) (moments checked), its log-probability matches the Gaussian density, the noise stream is reproducible per
+    (seed, step) and differs between steps; value-only mode gives the same values; both kernels draw the same noise."""
     import ctypes
     from mujoco_playground_b200.ppo import ActorCritic, FusedMinibatchStep
     dev = torch.device("cuda:0")
@@ -330,22 +331,34 @@ def test_fused_act_kernel_matches_policy_forward(obs_dim, n):
     with torch.no_grad():
         pol.log_std.copy_(torch.tensor([-0.4, 0.3], device=dev))
         pol.action_net.weight.mul_(20.0)
-    obs = torch.randn(n, obs_dim, device=dev) * 2
+    dense = torch.randn(n, obs_dim, device=dev) * 2
     with torch.no_grad():
-        mean_t, _ = pol.dist_params(obs)
-        val_t = pol.value(obs)
+        mean_t, _ = pol.dist_params(dense)
+        val_t = pol.value(dense)
+    if pitch:
+        buf = torch.full((n, pitch), 55.0, device=dev)     # padding columns hold junk: never used
+        buf[:, :obs_dim] = dense
+        obs = buf[:, :obs_dim]                             # row stride = pitch
+    else:
+        obs = dense
     f = FusedMinibatchStep(pol, torch.optim.SGD(pol.parameters(), lr=0.0), PPOConfig(), obs_dim, dev)
     act, logp, val = torch.empty(n, 2, device=dev), torch.empty(n, device=dev), torch.empty(n, device=dev)
     f.act(obs, act, logp, val, seed=77, step=3)
     mean = torch.empty(n, 2, device=dev)
     p = lambda t: ctypes.c_void_p(t.data_ptr())
-    assert f.L.ackb_ppo_act(p(obs), n, obs_dim, p(f.flat_p), p(mean), p(val), None, None, 0, 0, 0, None) == 0
+    assert f.L.ackb_ppo_act_pitched(p(obs), int(obs.stride(0)), n, obs_dim, p(f.flat_p), p(mean), p(val), None, None, 0, 0, 0, None) == 0
     torch.cuda.synchronize()
+    if pitch:      # same random stream as the dense-row kernel
+        act_d, logp_d, val_d = torch.empty_like(act), torch.empty_like(logp), torch.empty_like(val)
+        f.act(dense, act_d, logp_d, val_d, seed=77, step=3)
+        torch.cuda.synchronize()
+        assert (act - act_d).abs().max().item() < 1e-2 * max(1.0, mean_t.abs().max().item()) and (logp - logp_d).abs().max().item() < 1e-5
     assert (mean - mean_t).abs().max().item() < 5e-3 * max(1.0, mean_t.abs().max().item())
     assert (val - val_t).abs().max().item() < 5e-3 * max(1.0, val_t.abs().max().item())
     eps = (act - mean) / torch.exp(pol.log_std.detach())
-    assert abs(eps.mean().item()) < 0.06 and abs(eps.var().item() - 1.0) < 0.08
-    assert abs((eps[:, 0] * eps[:, 1]).mean().item()) < 0.06, "the two action noises are independent"
+    if n >= 700:        # sample moments need samples
+        assert abs(eps.mean().item()) < 0.06 and abs(eps.var().item() - 1.0) < 0.08
+        assert abs((eps[:, 0] * eps[:, 1]).mean().item()) < 0.06, "the two action noises are independent"
     want_logp = ActorCritic.log_prob(mean, pol.log_std.detach(), act)
     assert (logp - want_logp).abs().max().item() < 1e-3
     act2, logp2, val2 = torch.empty_like(act), torch.empty_like(logp), torch.empty_like(val)
