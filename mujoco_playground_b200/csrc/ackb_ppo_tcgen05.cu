@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a, con
       }
       if (t < TM) {
 #pragma unroll
-        for (int i = 0; i < 5; ++i) F[F_SC + t * 5 + i] = psn[i];
+        for (int i = 0; i < 5; ++i) F[F_SC + i * TM + t] = psn[i];
       }
     }
     T5_MARK(21);
@@ -490,7 +490,7 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a, con
           for (int j = 0; j < 16; ++j) p1 = fmaf(h2v[j], w0[j], p1);
         }
         sts_row16(sm + O_H2, rowoff, rx, swp, 16 * part, v);
-        F[F_PART + row * 8 + part * 2] = p0; F[F_PART + row * 8 + part * 2 + 1] = p1;
+        F[F_PART + (part * 2) * TM + row] = p0; F[F_PART + (part * 2 + 1) * TM + row] = p1;      // [part, head][row]: conflict free
       }
       __syncthreads();
       T5_MARK(4);
@@ -498,9 +498,10 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a, con
       // per-launch totals and written to the ones block by the thread with part == 0
       float d0 = 0.f, d1 = 0.f;
       if (row < ns) {
-        const float* PR = &F[F_PART + row * 8];
-        const float* SC = &F[F_SC + row * 5];
-        const float s0 = (PR[0] + PR[2]) + (PR[4] + PR[6]), s1 = (PR[1] + PR[3]) + (PR[5] + PR[7]);
+        const float* PR = &F[F_PART + row];
+        const float* SCp = &F[F_SC + row];
+        const float SC[5] = {SCp[0], SCp[TM], SCp[2 * TM], SCp[3 * TM], SCp[4 * TM]};
+        const float s0 = (PR[0] + PR[2 * TM]) + (PR[4 * TM] + PR[6 * TM]), s1 = (PR[TM] + PR[3 * TM]) + (PR[5 * TM] + PR[7 * TM]);
         if (net == 0) {
           const float m0 = s0 + F[F_B3], m1 = s1 + F[F_B3 + 1];
           const float e0 = SC[0] - m0, e1 = SC[1] - m1;
@@ -826,13 +827,13 @@ __global__ void __launch_bounds__(NT5, 1) ppo_act_kernel_tcgen05(ActT5Args a) {
       lds16(&F[AF_W3 + 2 * H + 16 * part], w0);
 #pragma unroll
       for (int j = 0; j < 16; ++j) pv = fmaf(tanh_fast(v[j] + b2[j]), w0[j], pv);
-      F[AF_PART + row * 12 + part * 3] = p0; F[AF_PART + row * 12 + part * 3 + 1] = p1; F[AF_PART + row * 12 + part * 3 + 2] = pv;
+      F[AF_PART + (part * 3) * TM + row] = p0; F[AF_PART + (part * 3 + 1) * TM + row] = p1; F[AF_PART + (part * 3 + 2) * TM + row] = pv;
     }
     __syncthreads();
     if (part == 0 && row < ns) {
-      const float* PR = &F[AF_PART + row * 12];
-      const float m0 = (PR[0] + PR[3]) + (PR[6] + PR[9]) + F[AF_B3], m1 = (PR[1] + PR[4]) + (PR[7] + PR[10]) + F[AF_B3 + 1];
-      const float vv = (PR[2] + PR[5]) + (PR[8] + PR[11]) + F[AF_B3 + 2];
+      const float* PR = &F[AF_PART + row];
+      const float m0 = (PR[0] + PR[3 * TM]) + (PR[6 * TM] + PR[9 * TM]) + F[AF_B3], m1 = (PR[TM] + PR[4 * TM]) + (PR[7 * TM] + PR[10 * TM]) + F[AF_B3 + 1];
+      const float vv = (PR[2 * TM] + PR[5 * TM]) + (PR[8 * TM] + PR[11 * TM]) + F[AF_B3 + 2];
       const size_t grow = (size_t)(sbase + row);
       a.value[grow] = vv;
       if (a.mean) { a.mean[grow * 2] = m0; a.mean[grow * 2 + 1] = m1; }
