@@ -38,7 +38,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t block_saddr, int kstep_in_block) {
   return make_desc(block_saddr + 32u * (uint32_t)kstep_in_block, 16u, 1024u);
 }
-// MN-major operand: MN blocks (32 elements each) `block_stride` bytes apart, one K step = 8 rows = one 1024-byte atom
+// MN-major operand in the plain SWIZZLE_128B layout: MN blocks (32 elements each) `block_stride` bytes apart, one K step = 8 rows = one
+// 1024-byte atom.  Valid for 16-bit operands only: for tf32 the tensor core returns zeros (tools/microbench/umma_probe.cu shows it);
+// the kernels use desc_mn32 / mn32_lo (SWIZZLE_128B_BASE32B) below.
 __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t block0_saddr, uint32_t block_stride, int kstep) {
   return make_desc(block0_saddr + 1024u * (uint32_t)kstep, block_stride, 1024u);
 }
@@ -128,9 +130,6 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* mbar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(mbar)) : "memory");
-}
 __device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
   asm volatile(
@@ -192,12 +191,6 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const float (&v)[16]) 
       "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])),
       "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
       : "memory");
-}
-__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
-               "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
-               "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
-               : "memory");
 }
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, const float (&v)[4]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
