@@ -890,6 +890,26 @@ __global__ void __launch_bounds__(NT, 1) ppo_act_kernel(ActArgs a) {
   const int D = a.D;
   const Offsets o = offsets(D);
   const float* P = a.params;
+  if (a.reward_out) {
+    // bootstrap mode: most calls have no truncated episode at all -- look at this CTA's rows first and leave before the weights are
+    // staged (the staging is 30 us of a call that otherwise only copies rewards and flags)
+    const int nt = (a.n + TT - 1) / TT;
+    bool any = false;
+    for (int tile = blockIdx.x; tile < nt; tile += gridDim.x) {
+      const int row = tile * TT + t;
+      any = any || (t < TT && row < a.n && a.trunc[row] != 0 && a.term[row] == 0);
+    }
+    if (!__syncthreads_or(any)) {
+      for (int tile = blockIdx.x; tile < nt; tile += gridDim.x) {
+        const int row = tile * TT + t;
+        if (t < TT && row < a.n) {
+          a.reward_out[row] = a.reward[row];
+          a.done_out[row] = (a.term[row] != 0 || a.trunc[row] != 0) ? 1.0f : 0.0f;
+        }
+      }
+      return;
+    }
+  }
   for (int i = t; i < KP * 128; i += NT) {
     const int k = i >> 7, n = i & 127, net = n >> 6, r = n & 63;
     sm[T_W1T + k * W1S + n] = (k < D) ? tf32r(P[(net ? o.W1v : o.W1p) + r * D + k]) : 0.0f;

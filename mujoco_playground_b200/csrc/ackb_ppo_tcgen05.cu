@@ -144,18 +144,19 @@ __device__ long long g_t5_prof[32];
 // (the same launch zeroes the gradient vector and the diagnostics, which the gradient kernel accumulates into)
 __global__ void ppo_t5_weight_images(const float* __restrict__ P, int D, unsigned char* __restrict__ img, float* __restrict__ grads,
                                      float* __restrict__ diag) {
-  const int net = blockIdx.x;
+  const int net = blockIdx.x;                                   // grid (2 nets, IMG_SLICES slices of the elements)
   const Offsets o = offsets(D);
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < o.total; i += gridDim.x * blockDim.x) grads[i] = 0.0f;
-  if (blockIdx.x == 0 && threadIdx.x < 5) diag[threadIdx.x] = 0.0f;
+  const int tid = blockIdx.y * blockDim.x + threadIdx.x, nth = gridDim.y * blockDim.x;
+  for (int i = net * nth + tid; i < o.total; i += 2 * nth) grads[i] = 0.0f;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 5) diag[threadIdx.x] = 0.0f;
   unsigned char* im = img + (size_t)net * IMG_BYTES;
   const float* W1g = P + (net ? o.W1v : o.W1p);
   const float* W2g = P + (net ? o.W2v : o.W2p);
-  for (int i = threadIdx.x; i < H * 96; i += blockDim.x) {
+  for (int i = tid; i < H * 96; i += nth) {
     const int r = i / 96, k = i % 96;
     *reinterpret_cast<float*>(im + (k >> 5) * 8192 + sw128_off(r, k & 31)) = (k < D) ? tf32r(W1g[r * D + k]) : 0.0f;
   }
-  for (int i = threadIdx.x; i < H * H; i += blockDim.x) {
+  for (int i = tid; i < H * H; i += nth) {
     const int r = i >> 6, k = i & 63;
     const float w = tf32r(W2g[i]);
     *reinterpret_cast<float*>(im + W1_BYTES + (k >> 5) * 8192 + sw128_off(r, k & 31)) = w;
@@ -895,7 +896,7 @@ int launch_grad_tcgen05(const PpoArgs& a, cudaStream_t stream) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int ntiles = (a.mb + TM - 1) / TM;
-  ppo_t5_weight_images<<<2, 512, 0, stream>>>(a.params, a.D, static_cast<unsigned char*>(img), a.grads, a.diag);
+  ppo_t5_weight_images<<<dim3(2, 8), 256, 0, stream>>>(a.params, a.D, static_cast<unsigned char*>(img), a.grads, a.diag);
   ppo_grad_kernel_tcgen05<<<ntiles < sms ? ntiles : sms, NT5, SMEM_BYTES, stream>>>(a, static_cast<const unsigned char*>(img));
   const cudaError_t e = cudaGetLastError();
   if (cudaFreeAsync(img, stream) != cudaSuccess) return ACKB_ERR_CUDA;
