@@ -89,6 +89,23 @@ int ackb_ppo_adv_stats_ws(const float* adv, const int64_t* idx, int n, float* me
 int ackb_ppo_clip_adam(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, float* step, int n, float max_grad_norm,
                        float lr, float beta1, float beta2, float eps, void* stream);
 
+/* The same optimiser step for data-parallel learners on the GPUs of one node, with the gradient all-reduce INSIDE the kernel (no
+ * NCCL call between the gradient kernel and the optimiser step; SB3 has one learner, the reference's multi-GPU counterpart is the
+ * 75 KB all-reduce of SURVEY.md section 8(e)).  Every rank passes
+ *   peer_grad_ptrs  device array [world] of addresses: rank q's gradient storage, mapped into this process (CUDA IPC / symmetric
+ *                   memory), two buffers of buf_stride floats each; *cur_buf (device int, 0 / 1) selects the buffer that the
+ *                   gradient kernels of ALL ranks wrote for this step -- consecutive steps must alternate the buffers;
+ *   peer_flag_ptrs  device array [world] of addresses of each rank's flag words (uint32[world], zero-initialised, peer mapped);
+ *   epoch           this rank's step counter (device uint32, starts at 0, incremented by the call);
+ *   gsum            scratch of n floats (this rank).
+ * The kernel announces "my gradient is complete" on every peer's flags, waits for all peers, sums the world gradients in rank
+ * order over NVLink peer loads (identical bits on every rank), divides by world, then clips and applies Adam as ackb_ppo_clip_adam.
+ * A peer that does not arrive within ~2 s sets *error (device int) instead of hanging.  Asynchronous on `stream`. */
+int ackb_ppo_clip_adam_allreduce(float* params, const uint64_t* peer_grad_ptrs, const uint64_t* peer_flag_ptrs, const int* cur_buf,
+                                 int buf_stride, int world, int rank, float* gsum, uint32_t* epoch, int* error, float* exp_avg,
+                                 float* exp_avg_sq, float* step, int n, float max_grad_norm, float lr, float beta1, float beta2,
+                                 float eps, void* stream);
+
 /* Generalised advantage estimation over a rollout (SB3 RolloutBuffer.compute_returns_and_advantage, called from
  * collect_rollouts): rew / val / done / adv / ret are [n_steps][n] device arrays, done[t] = 1 if the episode ended after step t,
  * last_val[n] = V(observation after the last step).  ret = adv + val.  Asynchronous on `stream`. */

@@ -48,6 +48,7 @@ SYMBOLS = {
     "ackb_ppo_permutation": (_i, [_vp, ctypes.c_longlong, _u64, ctypes.c_uint32, _vp]),
     "ackb_ppo_adv_stats": (_i, [_vp, _vp, _i, _vp, _vp]),
     "ackb_ppo_clip_adam": (_i, [_vp, _vp, _vp, _vp, _vp, _i] + [ctypes.c_float] * 5 + [_vp]),
+    "ackb_ppo_clip_adam_allreduce": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _i] + [ctypes.c_float] * 5 + [_vp]),
     "ackb_ppo_gae": (_i, [_vp, _vp, _vp, _vp, _i, _i, ctypes.c_float, ctypes.c_float, _vp, _vp, _vp]),
     "ackb_ppo_adv_stats_ws": (_i, [_vp, _vp, _i, _vp, _vp, _vp]),
     "ackb_ppo_minibatch_grad_mode": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, ctypes.c_float, _i, _vp]),

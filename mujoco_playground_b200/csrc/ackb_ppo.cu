@@ -1202,6 +1202,76 @@ __global__ void __cluster_dims__(ADAM_CTAS, 1, 1) __launch_bounds__(1024, 1)
   if (blockIdx.x == 0 && threadIdx.x == 0) step[0] = t;
 }
 
+// clip_adam_kernel with the data-parallel gradient all-reduce in front (include/ackb_ppo.h: ackb_ppo_clip_adam_allreduce): flags and
+// gradients of the peers are read / written through NVLink peer mappings with system-scope release / acquire.
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_relaxed_sys_f32(const float* p) {
+  float v;
+  asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+  return v;
+}
+__global__ void __cluster_dims__(ADAM_CTAS, 1, 1) __launch_bounds__(1024, 1)
+    clip_adam_allreduce_kernel(float* __restrict__ p, const uint64_t* __restrict__ peer_g, const uint64_t* __restrict__ peer_f,
+                               const int* __restrict__ cur_buf, int buf_stride, int world, int rank, float* __restrict__ gsum,
+                               uint32_t* __restrict__ epoch, int* __restrict__ error, float* __restrict__ m, float* __restrict__ v,
+                               float* __restrict__ step, int n, float max_norm, float lr, float b1, float b2, float eps) {
+  __shared__ double scratch[32];
+  const uint32_t e = epoch[0] + 1u;                       // every thread reads it; CTA 0 stores the new value after the last cluster barrier
+  const size_t goff = (size_t)(cur_buf[0] & 1) * (size_t)buf_stride;
+  // 1. my gradient (written by the kernels before this one on the stream) is complete: tell every rank, myself included
+  if (blockIdx.x == 0 && (int)threadIdx.x < world) {
+    __threadfence_system();
+    st_release_sys_u32(reinterpret_cast<uint32_t*>(peer_f[threadIdx.x]) + rank, e);
+  }
+  // 2. wait until every rank has announced this step (bounded: a missing peer raises *error instead of hanging the GPU)
+  if ((int)threadIdx.x < world) {
+    const uint32_t* mine = reinterpret_cast<const uint32_t*>(peer_f[rank]) + threadIdx.x;
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys_u32(mine) - e) < 0) {
+      if (clock64() - t0 > 4000000000ll) { atomicExch(error, 1); break; }
+      __nanosleep(200);
+    }
+  }
+  __syncthreads();
+  // 3. this CTA's share of the elements: sum over the ranks in rank order (same bits everywhere), mean -> gsum
+  const float inv_w = 1.0f / (float)world;
+  for (int k = blockIdx.x * 1024 + threadIdx.x; k < n; k += ADAM_CTAS * 1024) {
+    float s = 0.0f;
+    for (int q = 0; q < world; ++q) s += ld_relaxed_sys_f32(reinterpret_cast<const float*>(peer_g[q]) + goff + k);
+    gsum[k] = s * inv_w;
+  }
+  __threadfence();
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  // 4. clip + Adam on the averaged gradient, as clip_adam_kernel
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int i = threadIdx.x;
+  for (; i + 3 * 1024 < n; i += 4 * 1024) {
+    const double g0 = (double)__ldcg(gsum + i), g1 = (double)__ldcg(gsum + i + 1024), g2 = (double)__ldcg(gsum + i + 2048),
+                 g3 = (double)__ldcg(gsum + i + 3072);
+    s0 += g0 * g0; s1 += g1 * g1; s2 += g2 * g2; s3 += g3 * g3;
+  }
+  for (; i < n; i += 1024) { const double g = (double)__ldcg(gsum + i); s0 += g * g; }
+  const float norm = (float)sqrt(block_sum_1024((s0 + s1) + (s2 + s3), scratch));
+  const float coef = fminf(max_norm / (norm + 1e-6f), 1.0f);
+  const float t = step[0] + 1.0f;
+  const float bc1 = 1.0f - powf(b1, t), bc2s = sqrtf(1.0f - powf(b2, t));
+  const float step_size = lr / bc1;
+  for (int k = blockIdx.x * 1024 + threadIdx.x; k < n; k += ADAM_CTAS * 1024) {
+    const float g = __ldcg(gsum + k) * coef;
+    const float mi = m[k] + (1.0f - b1) * (g - m[k]);
+    const float vi = b2 * v[k] + (1.0f - b2) * g * g;
+    m[k] = mi; v[k] = vi;
+    p[k] -= step_size * mi / (sqrtf(vi) / bc2s + eps);
+  }
+  asm volatile("barrier.cluster.arrive.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");     // every CTA has read step[0] and epoch[0]
+  if (blockIdx.x == 0 && threadIdx.x == 0) { step[0] = t; epoch[0] = e; }
+}
+
 }  // namespace
 
 static int g_use_tc = -1;
@@ -1292,6 +1362,19 @@ int ackb_ppo_clip_adam(float* params, const float* grads, float* exp_avg, float*
                        float lr, float beta1, float beta2, float eps, void* stream) {
   if (!params || !grads || !exp_avg || !exp_avg_sq || !step || n <= 0) return ACKB_ERR_ARG;
   clip_adam_kernel<<<ADAM_CTAS, 1024, 0, (cudaStream_t)stream>>>(params, grads, exp_avg, exp_avg_sq, step, n, max_grad_norm, lr, beta1, beta2, eps);
+  return cudaGetLastError() == cudaSuccess ? ACKB_OK : ACKB_ERR_CUDA;
+}
+
+int ackb_ppo_clip_adam_allreduce(float* params, const uint64_t* peer_grad_ptrs, const uint64_t* peer_flag_ptrs, const int* cur_buf,
+                                 int buf_stride, int world, int rank, float* gsum, uint32_t* epoch, int* error, float* exp_avg,
+                                 float* exp_avg_sq, float* step, int n, float max_grad_norm, float lr, float beta1, float beta2,
+                                 float eps, void* stream) {
+  if (!params || !peer_grad_ptrs || !peer_flag_ptrs || !cur_buf || !gsum || !epoch || !error || !exp_avg || !exp_avg_sq || !step) return ACKB_ERR_ARG;
+  if (n <= 0 || world < 1 || world > 32 || rank < 0 || rank >= world || buf_stride < n) return ACKB_ERR_ARG;
+  NvtxRange nvtx("ackb_ppo_clip_adam_allreduce");
+  clip_adam_allreduce_kernel<<<ADAM_CTAS, 1024, 0, (cudaStream_t)stream>>>(params, peer_grad_ptrs, peer_flag_ptrs, cur_buf, buf_stride, world, rank,
+                                                                            gsum, epoch, error, exp_avg, exp_avg_sq, step, n, max_grad_norm, lr,
+                                                                            beta1, beta2, eps);
   return cudaGetLastError() == cudaSuccess ? ACKB_OK : ACKB_ERR_CUDA;
 }
 

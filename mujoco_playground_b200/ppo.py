@@ -307,6 +307,46 @@ class FusedMinibatchStep:
                 st["exp_avg"], st["exp_avg_sq"] = torch.zeros_like(self.flat_p), torch.zeros_like(self.flat_p)
         self.mb = -1      # any minibatch size
         self.index_mode = os.environ.get("ACKB_PPO_SHUFFLE", "index") != "copy"
+        self.peer = None  # peer-memory gradient all-reduce inside the optimiser-step kernel (enable_peer_allreduce)
+        self._mbc = 0     # optimiser steps taken: its parity selects the gradient buffer of the peer path
+
+    def enable_peer_allreduce(self, world: int, rank: int) -> bool:
+        """Data-parallel learners on one node: move the 75 KB gradient all-reduce INTO the optimiser-step kernel
+        (ackb_ppo_clip_adam_allreduce: flags + peer loads over NVLink instead of an NCCL call per optimiser step).  Collective: every
+        rank must call it at the same point.  The gradient kernels then write into one of two buffers of a symmetric-memory
+        allocation (torch.distributed._symmetric_memory), alternating per optimiser step.  Returns False (and keeps the NCCL path)
+        if the optimiser step is not the native kernel, symmetric memory is unavailable, or ACKB_PPO_PEER_ALLREDUCE=0."""
+        if world <= 1 or not self.native_opt or os.environ.get("ACKB_PPO_PEER_ALLREDUCE", "1") == "0":
+            return False
+        dev, n = self.device, self.flat_p.numel()
+        stride = (n + 31) // 32 * 32
+        ok, st = 1, None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            buf = symm.empty(2 * stride + 64, dtype=torch.float32, device=dev)       # two gradient buffers + 64 flag words
+            hdl = symm.rendezvous(buf, dist.group.WORLD)
+            buf.zero_()
+            torch.cuda.synchronize(dev)
+            ptrs = [int(x) for x in hdl.buffer_ptrs]
+            st = dict(buf=buf, hdl=hdl, stride=stride, world=world, rank=rank, g=[buf[0:n], buf[stride:stride + n]],
+                      gptrs=torch.tensor(ptrs, dtype=torch.int64, device=dev),
+                      fptrs=torch.tensor([x + 2 * stride * 4 for x in ptrs], dtype=torch.int64, device=dev),
+                      cur=torch.zeros(1, dtype=torch.int32, device=dev), epoch=torch.zeros(1, dtype=torch.int32, device=dev),
+                      err=torch.zeros(1, dtype=torch.int32, device=dev), gsum=torch.zeros(stride, dtype=torch.float32, device=dev))
+        except Exception as ex:      # noqa: BLE001 -- any failure means "use NCCL"
+            ok = 0
+            print(f"[ppo] peer-memory all-reduce unavailable on rank {rank}: {type(ex).__name__}: {ex}", flush=True)
+        agree = torch.tensor([ok], dtype=torch.int32, device=dev)
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN)       # all ranks or none; also orders the zeroing before the first flag write
+        torch.cuda.synchronize(dev)
+        if int(agree.item()) == 0:
+            return False
+        self.peer = st
+        return True
+
+    def check_peer_error(self) -> None:
+        if self.peer is not None and int(self.peer["err"].item()) != 0:
+            raise RuntimeError("ackb_ppo_clip_adam_allreduce: a peer rank did not arrive within the time limit")
 
     def act(self, obs: torch.Tensor, action: torch.Tensor, logp: torch.Tensor, value: torch.Tensor, seed: int, step: int) -> None:
         """Fused rollout forward (csrc/ackb_ppo.cu: ppo_act_kernel): fills action (unclipped sample), logp and value in place."""
@@ -402,15 +442,17 @@ class FusedMinibatchStep:
         with torch.cuda.stream(side):
             for _ in range(2):
                 for sl in slots:
-                    self._grad(shuffled, sl)
+                    self._grad(shuffled, sl, self._mbc & 1)
                     self._clip_step()
+                    self._mbc += 1
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.g1, self.g2 = {}, torch.cuda.CUDAGraph()
+        self._slot_parity = {sl: i & 1 for i, sl in enumerate(slots)}      # gradient buffer baked into the slot's graph (peer path)
         for sl in slots:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self._grad(shuffled, sl)
+                self._grad(shuffled, sl, self._slot_parity[sl])
             self.g1[sl] = g
         with torch.cuda.graph(self.g2):
             self._clip_step()
@@ -432,16 +474,32 @@ class FusedMinibatchStep:
             return
         c, g, st = self.ct, self.opt.param_groups[0], self.opt.state[self.flat_param]
         ptr = lambda t: c.c_void_p(t.data_ptr())
+        if self.peer is not None:      # all-reduce over peer memory + clip + Adam in one kernel
+            pr = self.peer
+            rc = self.L.ackb_ppo_clip_adam_allreduce(ptr(self.flat_p), ptr(pr["gptrs"]), ptr(pr["fptrs"]), ptr(pr["cur"]), int(pr["stride"]),
+                                                     int(pr["world"]), int(pr["rank"]), ptr(pr["gsum"]), ptr(pr["epoch"]), ptr(pr["err"]),
+                                                     ptr(st["exp_avg"]), ptr(st["exp_avg_sq"]), ptr(st["step"]), int(self.flat_p.numel()),
+                                                     float(self.cfg.max_grad_norm), float(g["lr"]), float(g["betas"][0]),
+                                                     float(g["betas"][1]), float(g["eps"]),
+                                                     c.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+            if rc != 0:
+                raise RuntimeError(f"ackb_ppo_clip_adam_allreduce failed with code {rc}")
+            return
         rc = self.L.ackb_ppo_clip_adam(ptr(self.flat_p), ptr(self.flat_g), ptr(st["exp_avg"]), ptr(st["exp_avg_sq"]), ptr(st["step"]),
                                        int(self.flat_p.numel()), float(self.cfg.max_grad_norm), float(g["lr"]), float(g["betas"][0]),
                                        float(g["betas"][1]), float(g["eps"]), c.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
         if rc != 0:
             raise RuntimeError(f"ackb_ppo_clip_adam failed with code {rc}")
 
-    def _grad(self, batch: Dict[str, torch.Tensor], idx):
-        """Advantage statistics of the minibatch + the gradient kernel (fills flat_g and diag)."""
+    def _grad(self, batch: Dict[str, torch.Tensor], idx, parity: int = 0):
+        """Advantage statistics of the minibatch + the gradient kernel (fills flat_g -- or, on the peer all-reduce path, gradient
+        buffer `parity` of the symmetric allocation -- and diag)."""
         c, cfg = self.ct, self.cfg
         ptr = lambda t: c.c_void_p(t.data_ptr())
+        gbuf = self.flat_g
+        if self.peer is not None:
+            gbuf = self.peer["g"][parity & 1]
+            self.peer["cur"].fill_(parity & 1)
         view, n, rows = self._resolve(batch, idx)
         stream = c.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
         rc = self.L.ackb_ppo_adv_stats_ws(ptr(view["adv"]), ptr(rows) if rows is not None else None, n, ptr(self.adv_stats), ptr(self.adv_ws), stream)
@@ -449,7 +507,7 @@ class FusedMinibatchStep:
             raise RuntimeError(f"ackb_ppo_adv_stats failed with code {rc}")
         rc = self.L.ackb_ppo_minibatch_grad_pitched(ptr(view["obs"]), int(view["obs"].stride(0)), ptr(view["act"]), ptr(view["logp"]),
                                                     ptr(view["adv"]), ptr(view["ret"]), ptr(rows) if rows is not None else None, n,
-                                                    self.obs_dim, ptr(self.adv_stats), ptr(self.flat_p), ptr(self.flat_g), ptr(self.diag),
+                                                    self.obs_dim, ptr(self.adv_stats), ptr(self.flat_p), ptr(gbuf), ptr(self.diag),
                                                     cfg.clip_range, cfg.vf_coef, cfg.ent_coef, self.mode, stream)
         if rc != 0:
             raise RuntimeError(f"ackb_ppo_minibatch_grad failed with code {rc}")
@@ -457,13 +515,19 @@ class FusedMinibatchStep:
     def run(self, batch: Dict[str, torch.Tensor], idx, world: int) -> int:
         """idx: int64 index tensor (rows of `batch`), or a (start, count) range of the epoch prepared by shuffle_epoch."""
         g1 = getattr(self, "g1", None)
+        parity = self._mbc & 1
         graphs = g1 is not None and isinstance(idx, tuple) and idx in g1 and self._same_arrays(batch)
+        if graphs and self.peer is not None and self._slot_parity.get(idx) != parity:
+            graphs = False      # the buffers must alternate from step to step: this slot's graph has the other one baked in
         if graphs:
             g1[idx].replay()
         else:
-            self._grad(batch, idx)
+            self._grad(batch, idx, parity)
+        self._mbc += 1
         nbytes = 0
-        if world > 1:
+        if world > 1 and self.peer is not None:
+            nbytes = self.flat_g.numel() * 4      # moved by the optimiser-step kernel over peer memory
+        elif world > 1:
             dist.all_reduce(self.flat_g, op=dist.ReduceOp.SUM)
             self.flat_g.div_(world)
             nbytes = self.flat_g.numel() * 4
@@ -518,6 +582,7 @@ class PPOTrainer:
         self._adv, self._ret = torch.empty((T, N), **f), torch.empty((T, N), **f)    # persistent: CUDA graphs are captured on them
         if self.learner == "fused":     # flat parameter buffers exist from the start: the rollout forward uses them too
             self.graphed = FusedMinibatchStep(self.policy, self.opt, cfg, D, self.device, mode=learner_mode)
+            self.peer_allreduce = self.graphed.enable_peer_allreduce(self.world, self.rank) if (self.world > 1 and self.device.type == "cuda") else False
 
     def grad_kernel_seconds(self, reps: int = 5) -> Optional[float]:
         """Average device time of ONE launch of the minibatch-gradient kernel on the current rollout (CUDA events on the launching
@@ -610,6 +675,8 @@ class PPOTrainer:
             self.graphed = GraphedMinibatchStep(self.policy, self.opt, cfg, max(1, n // cfg.minibatches), flat["obs"].shape[1], self.device)
         st = ppo_update(self.policy, self.opt, flat, cfg, self.world, graphed=self.graphed, perm_seed=self._noise_seed)
         torch.cuda.synchronize(self.device)
+        if isinstance(self.graphed, FusedMinibatchStep):
+            self.graphed.check_peer_error()
         torch.cuda.nvtx.range_pop()
         st["update_s"] = time.perf_counter() - t0
         return st

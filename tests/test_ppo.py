@@ -590,3 +590,20 @@ def test_pitched_observation_rows():
         f.run(dict(obs=obs_p, **rest), idx, world=1)
         torch.cuda.synchronize()
         assert (f.flat_g - out[0][0]).abs().max().item() < 1e-2 * sc
+
+
+@pytest.mark.gpu
+def test_peer_memory_allreduce_matches_nccl_on_two_gpus():
+    """ackb_ppo_clip_adam_allreduce (gradient all-reduce over NVLink peer memory inside the optimiser-step kernel) against the NCCL
+    path: same parameters after four PPO iterations, bit-identical on every rank.  Needs two GPUs (tools/gpu/ppo_peer_check.py under
+    torchrun); skipped on a single-GPU box."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(root, "tools", "gpu", "ppo_peer_check.py"), "4096"],
+                       capture_output=True, text=True, timeout=600)
+    assert "PEER CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
