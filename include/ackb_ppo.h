@@ -100,7 +100,7 @@ int ackb_ppo_clip_adam(float* params, const float* grads, float* exp_avg, float*
  *   gsum            scratch of n floats (this rank).
  * The kernel announces "my gradient is complete" on every peer's flags, waits for all peers, sums the world gradients in rank
  * order over NVLink peer loads (identical bits on every rank), divides by world, then clips and applies Adam as ackb_ppo_clip_adam.
- * A peer that does not arrive within ~2 s sets *error (device int) instead of hanging.  Asynchronous on `stream`. */
+ * A peer that does not arrive within ~20 s sets *error (device int) instead of hanging.  Asynchronous on `stream`. */
 int ackb_ppo_clip_adam_allreduce(float* params, const uint64_t* peer_grad_ptrs, const uint64_t* peer_flag_ptrs, const int* cur_buf,
                                  int buf_stride, int world, int rank, float* gsum, uint32_t* epoch, int* error, float* exp_avg,
                                  float* exp_avg_sq, float* step, int n, float max_grad_norm, float lr, float beta1, float beta2,

@@ -1233,7 +1233,7 @@ __global__ void __cluster_dims__(ADAM_CTAS, 1, 1) __launch_bounds__(1024, 1)
     const uint32_t* mine = reinterpret_cast<const uint32_t*>(peer_f[rank]) + threadIdx.x;
     const long long t0 = clock64();
     while ((int32_t)(ld_acquire_sys_u32(mine) - e) < 0) {
-      if (clock64() - t0 > 4000000000ll) { atomicExch(error, 1); break; }
+      if (clock64() - t0 > 40000000000ll) { atomicExch(error, 1); break; }      // ~20 s: ranks may be seconds apart at start-up
       __nanosleep(200);
     }
   }
