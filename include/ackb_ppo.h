@@ -54,6 +54,12 @@ int ackb_ppo_minibatch_grad_mode(const float* obs, const float* act, const float
 int ackb_ppo_minibatch_grad_pitched(const float* obs, int obs_pitch, const float* act, const float* old_logp, const float* adv, const float* ret,
                                     const int64_t* idx, int mb, int obs_dim, const float* adv_mean_std, const float* params, float* grads,
                                     float* diag, float clip_range, float vf_coef, float ent_coef, int mode, void* stream);
+/* ackb_ppo_adv_stats_ws + ackb_ppo_minibatch_grad_pitched in one call: adv_mean_std (OUT, then used by the gradient) = mean / std of
+ * adv over the minibatch, adv_workspace as for ackb_ppo_adv_stats_ws.  In ACKB_PPO_MODE_TCGEN05 the statistics are computed by extra
+ * CTAs of the kernel's prologue launch (weight images + gradient zeroing), which saves a launch per optimiser step. */
+int ackb_ppo_minibatch_grad_stats(const float* obs, int obs_pitch, const float* act, const float* old_logp, const float* adv, const float* ret,
+                                  const int64_t* idx, int mb, int obs_dim, float* adv_mean_std, double* adv_workspace, const float* params,
+                                  float* grads, float* diag, float clip_range, float vf_coef, float ent_coef, int mode, void* stream);
 int ackb_ppo_act_pitched(const float* obs, int obs_pitch, int n, int obs_dim, const float* params, float* mean, float* value, float* action,
                          float* logp, uint64_t seed, uint32_t step, int value_only, void* stream);
 int ackb_ppo_bootstrap_pitched(const float* terminal_obs, int obs_pitch, const uint8_t* terminated, const uint8_t* truncated, const float* reward,

@@ -54,6 +54,7 @@ SYMBOLS = {
     "ackb_ppo_minibatch_grad_mode": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, ctypes.c_float, _i, _vp]),
     "ackb_ppo_minibatch_grad_pitched": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, ctypes.c_float, _i, _vp]),
     "ackb_ppo_act_pitched": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _u64, ctypes.c_uint32, _i, _vp]),
+    "ackb_ppo_minibatch_grad_stats": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, ctypes.c_float, _i, _vp]),
     "ackb_ppo_bootstrap_pitched": (_i, [_vp, _i, _vp, _vp, _vp, _i, _i, _vp, ctypes.c_float, _vp, _vp, _vp]),
     "ackb_ppo_minibatch_grad": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp, ctypes.c_float, ctypes.c_float, ctypes.c_float, _vp]),
 }

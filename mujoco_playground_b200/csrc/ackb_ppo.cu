@@ -1138,35 +1138,7 @@ __device__ __forceinline__ double block_sum_1024(double v, double* scratch) {
 __device__ double g_adv_ws[3] = {0.0, 0.0, 0.0};   // default workspace of ackb_ppo_adv_stats (one learner per device, one stream)
 __global__ void __launch_bounds__(256) adv_stats_kernel(const float* __restrict__ adv, const int64_t* __restrict__ idx, int n,
                                                         float* __restrict__ mean_std, double* __restrict__ ws) {
-  double* g_adv_acc = ws;                                           // [0..1]: sum, sum of squares
-  unsigned* g_adv_done_p = reinterpret_cast<unsigned*>(ws + 2);     // CTAs finished
-  __shared__ double sh[2][8];
-  __shared__ bool last;
-  double s = 0.0, q = 0.0;
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
-    const double x = (double)adv[idx ? idx[i] : (int64_t)i];
-    s += x; q += x * x;
-  }
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, off); q += __shfl_xor_sync(0xffffffffu, q, off); }
-  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = q; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double ts = 0.0, tq = 0.0;
-    for (int w = 0; w < 8; ++w) { ts += sh[0][w]; tq += sh[1][w]; }
-    atomicAdd(&g_adv_acc[0], ts); atomicAdd(&g_adv_acc[1], tq);
-    __threadfence();
-    last = atomicAdd(g_adv_done_p, 1u) == gridDim.x - 1;
-    if (last) {
-      __threadfence();
-      const double S = atomicAdd(&g_adv_acc[0], 0.0), Q = atomicAdd(&g_adv_acc[1], 0.0);
-      const double mean = S / (double)n;
-      const double var = (Q - S * mean) / (double)(n > 1 ? n - 1 : 1);
-      mean_std[0] = (float)mean; mean_std[1] = (float)sqrt(var > 0.0 ? var : 0.0);
-      g_adv_acc[0] = 0.0; g_adv_acc[1] = 0.0; *g_adv_done_p = 0u;
-      __threadfence();
-    }
-  }
+  adv_stats_block(adv, idx, n, mean_std, ws, blockIdx.x, gridDim.x);      // ackb_ppo_common.cuh
 }
 
 // global-norm gradient clipping (torch.nn.utils.clip_grad_norm_) + Adam (torch.optim.Adam, no weight decay / amsgrad) on the flat
@@ -1313,7 +1285,7 @@ int ackb_ppo_minibatch_grad_pitched(const float* obs, int obs_pitch, const float
   if (mode != ACKB_PPO_MODE_DEFAULT && mode != ACKB_PPO_MODE_FP32 && mode != ACKB_PPO_MODE_TF32 && mode != ACKB_PPO_MODE_TCGEN05) return ACKB_ERR_ARG;
   if (mode == ACKB_PPO_MODE_TCGEN05) {     // Blackwell path: tcgen05.mma kind::tf32, accumulators in TMEM (ackb_ppo_tcgen05.cu)
     PpoArgs a5{obs, act, old_logp, adv, ret, idx, mb, obs_dim, adv_mean_std, params, grads, diag, clip_range, vf_coef, ent_coef, obs_pitch};
-    return launch_grad_tcgen05(a5, s);
+    return launch_grad_tcgen05(a5, s, nullptr, nullptr);
   }
   const int use_tc = mode == ACKB_PPO_MODE_DEFAULT ? g_use_tc : (mode == ACKB_PPO_MODE_TF32 ? 1 : 0);
   const size_t smem = (size_t)(use_tc ? T_TOTAL : S_TOTAL) * sizeof(float);
@@ -1341,6 +1313,22 @@ int ackb_ppo_permutation(int64_t* perm, long long n, uint64_t seed, uint32_t str
   while ((1ull << (2 * half_bits)) < (unsigned long long)n) ++half_bits;
   permutation_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(perm, n, half_bits, seed, stream_id);
   return cudaGetLastError() == cudaSuccess ? ACKB_OK : ACKB_ERR_CUDA;
+}
+
+int ackb_ppo_minibatch_grad_stats(const float* obs, int obs_pitch, const float* act, const float* old_logp, const float* adv, const float* ret,
+                                  const int64_t* idx, int mb, int obs_dim, float* adv_mean_std, double* adv_workspace, const float* params,
+                                  float* grads, float* diag, float clip_range, float vf_coef, float ent_coef, int mode, void* stream) {
+  if (!adv || !adv_mean_std || !adv_workspace || mb <= 0) return ACKB_ERR_ARG;
+  if (mode == ACKB_PPO_MODE_TCGEN05 && obs_dim < KP) {      // statistics in the prologue launch of the tcgen05 kernel
+    NvtxRange nvtx("ackb_ppo_minibatch_grad");
+    if (!obs || !act || !old_logp || !ret || !params || !grads || !diag || obs_dim <= 0 || obs_pitch < obs_dim) return ACKB_ERR_ARG;
+    PpoArgs a5{obs, act, old_logp, adv, ret, idx, mb, obs_dim, adv_mean_std, params, grads, diag, clip_range, vf_coef, ent_coef, obs_pitch};
+    return launch_grad_tcgen05(a5, (cudaStream_t)stream, adv_mean_std, adv_workspace);
+  }
+  const int rc = ackb_ppo_adv_stats_ws(adv, idx, mb, adv_mean_std, adv_workspace, stream);
+  if (rc != ACKB_OK) return rc;
+  return ackb_ppo_minibatch_grad_pitched(obs, obs_pitch, act, old_logp, adv, ret, idx, mb, obs_dim, adv_mean_std, params, grads, diag, clip_range,
+                                         vf_coef, ent_coef, mode, stream);
 }
 
 int ackb_ppo_adv_stats(const float* adv, const int64_t* idx, int n, float* mean_std, void* stream) {

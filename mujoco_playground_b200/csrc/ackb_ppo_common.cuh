@@ -31,8 +31,45 @@ struct PpoArgs {
   int pitch;       // floats between consecutive observation rows (>= D)
 };
 
-// tcgen05 / TMEM gradient kernel (ackb_ppo_tcgen05.cu); zeroes grads and diag itself (in its weight-image launch).  Returns an ackb_status.
-int launch_grad_tcgen05(const PpoArgs& a, cudaStream_t stream);
+// tcgen05 / TMEM gradient kernel (ackb_ppo_tcgen05.cu); zeroes grads and diag itself (in its prologue launch, which also writes the
+// weight images and, if adv_out / adv_ws are given, the advantage statistics of the minibatch).  Returns an ackb_status.
+int launch_grad_tcgen05(const PpoArgs& a, cudaStream_t stream, float* adv_out, double* adv_ws);
+
+// Mean and unbiased standard deviation (torch.Tensor.std) of the advantages of one minibatch, one CTA of 256 threads out of `nblocks`:
+// every CTA adds its partial sums (double) to two device-scope accumulators in `ws`, the last CTA to finish writes the result and
+// clears them for the next call (ws: double[3], zero-initialised once; calls sharing a workspace must not overlap).
+#ifdef __CUDACC__
+__device__ __forceinline__ void adv_stats_block(const float* __restrict__ adv, const int64_t* __restrict__ idx, int n, float* __restrict__ mean_std,
+                                                double* __restrict__ ws, int bid, int nblocks) {
+  double* acc = ws;                                           // [0..1]: sum, sum of squares
+  unsigned* done_p = reinterpret_cast<unsigned*>(ws + 2);     // CTAs finished
+  __shared__ double sh[2][8];
+  double s = 0.0, q = 0.0;
+  for (int i = bid * 256 + threadIdx.x; i < n; i += nblocks * 256) {
+    const double x = (double)adv[idx ? idx[i] : (int64_t)i];
+    s += x; q += x * x;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, off); q += __shfl_xor_sync(0xffffffffu, q, off); }
+  if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = s; sh[1][threadIdx.x >> 5] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0.0, tq = 0.0;
+    for (int w = 0; w < 8; ++w) { ts += sh[0][w]; tq += sh[1][w]; }
+    atomicAdd(&acc[0], ts); atomicAdd(&acc[1], tq);
+    __threadfence();
+    if (atomicAdd(done_p, 1u) == (unsigned)nblocks - 1u) {
+      __threadfence();
+      const double S = atomicAdd(&acc[0], 0.0), Q = atomicAdd(&acc[1], 0.0);
+      const double mean = S / (double)n;
+      const double var = (Q - S * mean) / (double)(n > 1 ? n - 1 : 1);
+      mean_std[0] = (float)mean; mean_std[1] = (float)sqrt(var > 0.0 ? var : 0.0);
+      acc[0] = 0.0; acc[1] = 0.0; *done_p = 0u;
+      __threadfence();
+    }
+  }
+}
+#endif
 
 // rollout forward on the same path (ackb_ppo_tcgen05.cu): mean [n][2] (may be null), value [n], and, if `action` is given, the sampled
 // action and (if `logp` is given) its log-probability, same random stream as ppo_act_kernel.  Rows `pitch` floats apart, pitch a

@@ -142,13 +142,20 @@ __device__ long long g_t5_prof[32];
 
 // shared-memory images of both nets' weights: [net][W1 | W2 | W2^T], TF32-rounded, K-major SWIZZLE_128B blocks of 64 rows
 // (the same launch zeroes the gradient vector and the diagnostics, which the gradient kernel accumulates into)
-__global__ void ppo_t5_weight_images(const float* __restrict__ P, int D, unsigned char* __restrict__ img, float* __restrict__ grads,
-                                     float* __restrict__ diag) {
-  const int net = blockIdx.x;                                   // grid (2 nets, IMG_SLICES slices of the elements)
+// Blocks 16 .. of the grid (if any) compute the advantage statistics of the minibatch (adv_stats_block) at the same time.
+constexpr int IMG_BLOCKS = 16;       // 2 nets x 8 slices of the elements, 256 threads each
+__global__ void __launch_bounds__(256) ppo_t5_weight_images(const float* __restrict__ P, int D, unsigned char* __restrict__ img, float* __restrict__ grads,
+                                                            float* __restrict__ diag, const float* __restrict__ adv, const int64_t* __restrict__ idx,
+                                                            int mb, float* __restrict__ adv_out, double* __restrict__ adv_ws) {
+  if ((int)blockIdx.x >= IMG_BLOCKS) {
+    adv_stats_block(adv, idx, mb, adv_out, adv_ws, (int)blockIdx.x - IMG_BLOCKS, (int)gridDim.x - IMG_BLOCKS);
+    return;
+  }
+  const int net = blockIdx.x & 1, slice = blockIdx.x >> 1;
   const Offsets o = offsets(D);
-  const int tid = blockIdx.y * blockDim.x + threadIdx.x, nth = gridDim.y * blockDim.x;
+  const int tid = slice * blockDim.x + threadIdx.x, nth = (IMG_BLOCKS / 2) * blockDim.x;
   for (int i = net * nth + tid; i < o.total; i += 2 * nth) grads[i] = 0.0f;
-  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x < 5) diag[threadIdx.x] = 0.0f;
+  if (blockIdx.x == 0 && threadIdx.x < 5) diag[threadIdx.x] = 0.0f;
   unsigned char* im = img + (size_t)net * IMG_BYTES;
   const float* W1g = P + (net ? o.W1v : o.W1p);
   const float* W2g = P + (net ? o.W2v : o.W2p);
@@ -870,7 +877,7 @@ extern "C" int ackb_ppo_t5_profile(long long* out16) {     // 32 counters
 }
 #endif
 
-int launch_grad_tcgen05(const PpoArgs& a, cudaStream_t stream) {
+int launch_grad_tcgen05(const PpoArgs& a, cudaStream_t stream, float* adv_out, double* adv_ws) {
   if (a.D >= KP) return ACKB_ERR_ARG;     // the bias gradient of layer 1 rides in column KP - 1 of the observation tile
   if (a.mb <= 0) return ACKB_ERR_ARG;
   static bool attr_done[64] = {false};
@@ -896,7 +903,13 @@ int launch_grad_tcgen05(const PpoArgs& a, cudaStream_t stream) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int ntiles = (a.mb + TM - 1) / TM;
-  ppo_t5_weight_images<<<dim3(2, 8), 256, 0, stream>>>(a.params, a.D, static_cast<unsigned char*>(img), a.grads, a.diag);
+  int stat_blocks = 0;
+  if (adv_out && adv_ws) {
+    stat_blocks = (a.mb + 1023) / 1024;                 // >= 4 values per thread
+    stat_blocks = stat_blocks > 280 ? 280 : (stat_blocks < 1 ? 1 : stat_blocks);
+  }
+  ppo_t5_weight_images<<<IMG_BLOCKS + stat_blocks, 256, 0, stream>>>(a.params, a.D, static_cast<unsigned char*>(img), a.grads, a.diag, a.adv, a.idx,
+                                                                     a.mb, adv_out, adv_ws);
   ppo_grad_kernel_tcgen05<<<ntiles < sms ? ntiles : sms, NT5, SMEM_BYTES, stream>>>(a, static_cast<const unsigned char*>(img));
   const cudaError_t e = cudaGetLastError();
   if (cudaFreeAsync(img, stream) != cudaSuccess) return ACKB_ERR_CUDA;

@@ -502,13 +502,11 @@ class FusedMinibatchStep:
             self.peer["cur"].fill_(parity & 1)
         view, n, rows = self._resolve(batch, idx)
         stream = c.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        rc = self.L.ackb_ppo_adv_stats_ws(ptr(view["adv"]), ptr(rows) if rows is not None else None, n, ptr(self.adv_stats), ptr(self.adv_ws), stream)
-        if rc != 0:
-            raise RuntimeError(f"ackb_ppo_adv_stats failed with code {rc}")
-        rc = self.L.ackb_ppo_minibatch_grad_pitched(ptr(view["obs"]), int(view["obs"].stride(0)), ptr(view["act"]), ptr(view["logp"]),
-                                                    ptr(view["adv"]), ptr(view["ret"]), ptr(rows) if rows is not None else None, n,
-                                                    self.obs_dim, ptr(self.adv_stats), ptr(self.flat_p), ptr(gbuf), ptr(self.diag),
-                                                    cfg.clip_range, cfg.vf_coef, cfg.ent_coef, self.mode, stream)
+        # advantage statistics of the minibatch + gradient (one call; on the tcgen05 path the statistics ride in the prologue launch)
+        rc = self.L.ackb_ppo_minibatch_grad_stats(ptr(view["obs"]), int(view["obs"].stride(0)), ptr(view["act"]), ptr(view["logp"]),
+                                                  ptr(view["adv"]), ptr(view["ret"]), ptr(rows) if rows is not None else None, n,
+                                                  self.obs_dim, ptr(self.adv_stats), ptr(self.adv_ws), ptr(self.flat_p), ptr(gbuf), ptr(self.diag),
+                                                  cfg.clip_range, cfg.vf_coef, cfg.ent_coef, self.mode, stream)
         if rc != 0:
             raise RuntimeError(f"ackb_ppo_minibatch_grad failed with code {rc}")
 
