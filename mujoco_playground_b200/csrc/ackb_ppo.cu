@@ -893,16 +893,17 @@ __global__ void __launch_bounds__(NT, 1) ppo_act_kernel(ActArgs a) {
   if (a.reward_out) {
     // bootstrap mode: most calls have no truncated episode at all -- look at this CTA's rows first and leave before the weights are
     // staged (the staging is 30 us of a call that otherwise only copies rewards and flags)
+    // (all 256 threads scan: NT / TT tiles per pass, independent loads -- a per-tile loop of dependent byte loads costs 20 us)
     const int nt = (a.n + TT - 1) / TT;
     bool any = false;
-    for (int tile = blockIdx.x; tile < nt; tile += gridDim.x) {
-      const int row = tile * TT + t;
-      any = any || (t < TT && row < a.n && a.trunc[row] != 0 && a.term[row] == 0);
+    for (int k = t / TT; blockIdx.x + k * gridDim.x < nt; k += NT / TT) {
+      const int row = (blockIdx.x + k * gridDim.x) * TT + (t % TT);
+      if (row < a.n) any = any | ((a.trunc[row] != 0) & (a.term[row] == 0));
     }
     if (!__syncthreads_or(any)) {
-      for (int tile = blockIdx.x; tile < nt; tile += gridDim.x) {
-        const int row = tile * TT + t;
-        if (t < TT && row < a.n) {
+      for (int k = t / TT; blockIdx.x + k * gridDim.x < nt; k += NT / TT) {
+        const int row = (blockIdx.x + k * gridDim.x) * TT + (t % TT);
+        if (row < a.n) {
           a.reward_out[row] = a.reward[row];
           a.done_out[row] = (a.term[row] != 0 || a.trunc[row] != 0) ? 1.0f : 0.0f;
         }
@@ -1402,9 +1403,11 @@ int ackb_ppo_act_pitched(const float* obs, int obs_pitch, int n, int obs_dim, co
   // kernel (ackb_ppo_tcgen05.cu); ACKB_PPO_ACT_T5=0 keeps the mma.sync kernel
   static int use_t5 = -1;
   if (use_t5 < 0) { const char* ev = getenv("ACKB_PPO_ACT_T5"); use_t5 = ev ? (atoi(ev) != 0) : 1; }
-  if (use_t5 && !value_only && (obs_pitch & 3) == 0 && obs_pitch <= KP && (reinterpret_cast<uintptr_t>(obs) & 15) == 0) {
+  // (value-only calls take it too: the policy net rides along, still half the time of the mma.sync kernel's value-only pass)
+  if (use_t5 && (obs_pitch & 3) == 0 && obs_pitch <= KP && (reinterpret_cast<uintptr_t>(obs) & 15) == 0) {
     NvtxRange nvtx("ackb_ppo_act");
-    ActT5Args a5{obs, n, obs_dim, obs_pitch, params, mean, value, action, logp, (unsigned long long)seed, step};
+    ActT5Args a5{obs, n, obs_dim, obs_pitch, params, value_only ? nullptr : mean, value, value_only ? nullptr : action, value_only ? nullptr : logp,
+                 (unsigned long long)seed, step};
     return launch_act_tcgen05(a5, (cudaStream_t)stream);
   }
   ActArgs a{obs, n, obs_dim, params, mean, value, action, logp, (unsigned long long)seed, step, value_only,
