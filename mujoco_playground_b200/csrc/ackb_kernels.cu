@@ -57,10 +57,13 @@ struct StepArgs {
   // Regime split of the flat-floor model: its fast kernels carry two floor-contact slots per wheel.  Environments tilted beyond
   // kGeneralTilt at the start of a step (rolled over, on their side, nose down: wheel caps or chassis plates can reach the floor) are
   // left to a second launch of the general kernel (NC = 4: two extra contact slots per wheel).  regime 0: every environment;
-  // 1: fast pass (skips and marks the tilted ones in gen_mask); 2: general pass (only the marked ones).
+  // 1: fast pass (skips the tilted ones and lists them); 2: general pass (only the listed ones).
+  // The fast pass appends the tilted environments to gen_list (length in gen_count[0]); the general pass is a small fixed grid
+  // that walks the list, leaves at once when it is empty, and zeroes the counter for the next step (the next fast pass starts
+  // only after this grid has finished).
   int regime;
-  uint8_t* gen_mask;
-  int pdl_wait;             // general pass launched by the host with programmatic stream serialisation
+  int* gen_list;
+  int* gen_count;
   int cta_sync;   // multi-lane kernels: re-converge the CTA once per substep (pays off only when several warps share a scheduler)
 };
 
@@ -160,26 +163,25 @@ struct WheelStore {
   }
 };
 
-template <typename T, int LANES, int NC>
-__device__ __forceinline__ void step_body(DevState<T>& st, const StepArgs& a, const Consts<T>& C) {
+// LIST = general pass of the regime split: the environments come from the list the fast pass wrote (blk = virtual block index of
+// the grid-stride loop in step_kernel_list, count = list length); otherwise thread -> environment is the identity map.
+template <typename T, int LANES, int NC, bool LIST>
+__device__ __forceinline__ void step_body(DevState<T>& st, const StepArgs& a, const Consts<T>& C, int blk, int count) {
   using E = EnvOps<T, LANES, NC>;
   using G = Geo<T, LANES, NC>;
   constexpr int EPW = 32 / LANES;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int tid = blk * blockDim.x + threadIdx.x;
   const int env_raw = tid / LANES, lane = tid % LANES;
-  const bool valid_in = env_raw < st.n;
-  const int env = valid_in ? env_raw : st.n - 1;
+  const bool valid_in = env_raw < (LIST ? count : st.n);
+  const int env = LIST ? a.gen_list[valid_in ? env_raw : 0] : (valid_in ? env_raw : st.n - 1);
   const int warp = threadIdx.x >> 5, lid = threadIdx.x & 31;
-  // general pass of the regime split: a warp without a marked environment leaves before it touches anything else (one byte per
-  // environment read; exited warps do not take part in the CTA barriers below, and this pass runs without per-substep barriers)
 #if defined(__CUDA_ARCH__)
-  // programmatic dependent launch of the general pass
-  if (a.regime == 1) asm volatile("griddepcontrol.launch_dependents;");                            // may be scheduled while this grid drains
-  if (a.regime == 2 && a.pdl_wait) asm volatile("griddepcontrol.wait;" ::: "memory");              // ... reads nothing before this grid's writes are visible
+  // programmatic dependent launch of the general pass: it may be scheduled while this grid drains
+  if (!LIST && a.regime == 1) asm volatile("griddepcontrol.launch_dependents;");
 #endif
-  if (a.regime == 2 && !__any_sync(0xffffffffu, valid_in && a.gen_mask[env] != 0)) return;
-  stage_tables(C);
+  if (LIST && !__any_sync(0xffffffffu, valid_in)) return;   // no CTA barriers in this pass (cta_sync = 0)
+  if (!LIST) stage_tables(C);
   // per-warp observation tile: its own region (4 lanes) or aliasing the warp's wheel records
   float* wtile = G::kSmemWheels ? reinterpret_cast<float*>(reinterpret_cast<T*>(smem_raw) + (size_t)warp * 32 * G::kStride)
                                 : reinterpret_cast<float*>(smem_raw) + (size_t)warp * EPW * a.obs_dim;
@@ -191,20 +193,15 @@ __device__ __forceinline__ void step_body(DevState<T>& st, const StepArgs& a, co
   SoAAcc<T> acc{st, env};
   E::load_state(acc, lane, e, wh);
   bool valid = valid_in;
-  if (a.regime != 0) {     // CTA-uniform
-    bool general;
-    if (a.regime == 1) {
-      // cosine of the tilt angle = R_zz of the chassis = (w^2 - x^2 - y^2 + z^2) / |q|^2
-      const T qq = e.q[0] * e.q[0] + e.q[1] * e.q[1] + e.q[2] * e.q[2] + e.q[3] * e.q[3];
-      general = !((e.q[0] * e.q[0] - e.q[1] * e.q[1] - e.q[2] * e.q[2] + e.q[3] * e.q[3]) >= T(kGeneralTilt) * qq);   // NaN -> general
-      if (valid_in && lane == 0) {
-        a.gen_mask[env] = general ? 1 : 0;
-      }
-      valid = valid_in && !general;
-    } else {
-      general = a.gen_mask[env] != 0;
-      valid = valid_in && general;
+  if (!LIST && a.regime == 1) {     // CTA-uniform
+    // cosine of the tilt angle = R_zz of the chassis = (w^2 - x^2 - y^2 + z^2) / |q|^2
+    const T qq = e.q[0] * e.q[0] + e.q[1] * e.q[1] + e.q[2] * e.q[2] + e.q[3] * e.q[3];
+    const bool general = !((e.q[0] * e.q[0] - e.q[1] * e.q[1] - e.q[2] * e.q[2] + e.q[3] * e.q[3]) >= T(kGeneralTilt) * qq);   // NaN -> general
+    if (general && valid_in && lane == 0) {      // rare: left to the general pass
+      const int slot = atomicAdd(a.gen_count, 1);
+      if (slot < st.n) a.gen_list[slot] = env;
     }
+    valid = valid_in && !general;
   }
   Episode<T> ep;
   ep.goal[0] = st.goal[env]; ep.goal[1] = st.goal[(size_t)st.n + env];
@@ -215,8 +212,8 @@ __device__ __forceinline__ void step_body(DevState<T>& st, const StepArgs& a, co
   if (a.action) { float2 v = reinterpret_cast<const float2*>(a.action)[env]; a0 = v.x; a1 = v.y; }
   else synth_action(a.seed, a.step_index, (uint32_t)env + a.env_base, &a0, &a1);
 
-  const int env0 = (blockIdx.x * blockDim.x + warp * 32) / LANES;
-  int nrow = st.n - env0;
+  const int env0 = (blk * blockDim.x + warp * 32) / LANES;     // LIST: position in the list
+  int nrow = (LIST ? count : st.n) - env0;
   nrow = nrow < 0 ? 0 : (nrow > EPW ? EPW : nrow);
   // coalesced store of the warp's observation tile (the warp's environments are consecutive rows), issued as soon as
   // the observation exists so that the tile storage can be reused by the last substep
@@ -225,6 +222,14 @@ __device__ __forceinline__ void step_body(DevState<T>& st, const StepArgs& a, co
   const unsigned fullmask = __ballot_sync(0xffffffffu, valid_in && lane == 0);
   auto emit = [&]() {
     __syncwarp();
+    if constexpr (LIST) {                // rows of listed environments: scattered
+      for (int r = 0; r < nrow; ++r) {
+        float* drow = a.obs + (size_t)__shfl_sync(0xffffffffu, env, r * LANES) * a.obs_pitch;
+        for (int j = lid; j < a.obs_dim; j += 32) drow[j] = wtile[r * a.obs_dim + j];
+      }
+      __syncwarp();
+      return;
+    }
     float* dst = a.obs + (size_t)env0 * a.obs_pitch;
     if (rowmask != fullmask) {           // warp-uniform: some rows belong to the other pass
       for (int r = 0; r < nrow; ++r)
@@ -329,7 +334,35 @@ __device__ __forceinline__ void step_body(DevState<T>& st, const StepArgs& a, co
 // slows the fast kernel by more than the second launch costs.  Removed.)
 template <typename T, int LANES, int NC>
 __global__ void __launch_bounds__(Geo<T, LANES, NC>::kBlock, Geo<T, LANES, NC>::kMinBlocks) step_kernel(DevState<T> st, StepArgs a, const __grid_constant__ Consts<T> C) {
-  step_body<T, LANES, NC>(st, a, C);
+  step_body<T, LANES, NC, false>(st, a, C, (int)blockIdx.x, 0);
+}
+
+// General pass of the regime split (flat-floor model): a small fixed grid, launched as a programmatic dependent of the fast pass,
+// walks the list of tilted environments.  Almost always the list is empty and every CTA leaves after one load.
+template <typename T, int LANES, int NC>
+__global__ void __launch_bounds__(Geo<T, LANES, NC>::kBlock, Geo<T, LANES, NC>::kMinBlocks) step_kernel_list(DevState<T> st, StepArgs a, const __grid_constant__ Consts<T> C) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("griddepcontrol.wait;" ::: "memory");     // nothing is read before the fast pass's writes are visible
+#endif
+  // list length; the last CTA to have read it zeroes it for the next step (ticket in gen_count[1]: no step parity baked into the
+  // launch, so a captured step can be replayed)
+  __shared__ int s_count;
+  if (threadIdx.x == 0) {
+    const int c = *reinterpret_cast<volatile int*>(a.gen_count);
+    __threadfence();
+    if (atomicAdd(a.gen_count + 1, 1) == (int)gridDim.x - 1) { a.gen_count[0] = 0; a.gen_count[1] = 0; }
+    s_count = c;
+  }
+  __syncthreads();
+  int count = s_count;
+  count = count > st.n ? st.n : count;
+  const int per_block = Geo<T, LANES, NC>::kBlock / LANES;
+  if ((long long)blockIdx.x * per_block >= count) return;
+  stage_tables(C);
+  for (int blk = blockIdx.x; (long long)blk * per_block < count; blk += gridDim.x) {
+    step_body<T, LANES, NC, true>(st, a, C, blk, count);
+    __syncwarp();
+  }
 }
 
 template <typename T, int LANES, int NC>
@@ -418,7 +451,8 @@ struct ackb_handle {
   float *d_action = nullptr, *d_obs = nullptr, *d_reward = nullptr;
   uint8_t *d_term = nullptr, *d_trunc = nullptr;
   uint8_t* d_done = nullptr;    // per-env done mask of the deferred reset (models with settle steps)
-  uint8_t* d_gen = nullptr;     // per-env "tilted: general contact pass" mark of the flat-floor regime split
+  int* d_gen_list = nullptr;    // flat-floor regime split: environments the fast pass left to the general contact pass ...
+  int* d_gen_count = nullptr;   // ... [0] their number, [1] the general pass's read ticket (both back to zero after every step)
   int general_pass = 1;         // flat-floor model: run the general-contact pass after the fast kernel (ACKB_GENERAL_PASS=0 disables)
   cudaStream_t own_stream = nullptr;
   // cross-stream ordering: ackb_step_host runs on own_stream, so it has to wait for work the caller issued through
@@ -485,19 +519,26 @@ int launch_one(ackb_handle* h, DevState<T>& st, const StepArgs& a, cudaStream_t 
     const size_t smem = G::smem_bytes(a.obs_dim);
     StepArgs a2 = a;
     a2.cta_sync = h->cta_sync >= 0 ? h->cta_sync : 1;   // measured on B200: faster at every batch size from 4096 to 131072 envs
-    if (a.regime == 2) a2.cta_sync = 0;                   // warps without a marked environment leave at once: no CTA barriers in this pass
     static std::atomic<int> attr[64];
-    if (int rc = ensure_smem_attr(h, step_kernel<T, LANES, NC>, attr, smem)) return rc;
-    if (a.regime == 2) {
-      // programmatic dependent launch: this grid is scheduled while the fast pass drains (its blocks wait in griddepcontrol.wait)
+    if constexpr (LANES == 4 && NC == 4) if (a.regime == 2) {
+      // general pass: a grid of at most one CTA per SM walks the list of tilted environments; programmatic dependent launch:
+      // the grid is scheduled while the fast pass drains (its blocks sit in griddepcontrol.wait)
+      a2.cta_sync = 0;
+      static std::atomic<int> lattr[64];
+      if (int rc = ensure_smem_attr(h, step_kernel_list<T, LANES, NC>, lattr, smem)) return rc;
+      const int lgrid = grid < h->num_sms ? grid : h->num_sms;
       cudaLaunchConfig_t cfg{};
-      cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3((unsigned)G::kBlock); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+      cfg.gridDim = dim3((unsigned)lgrid); cfg.blockDim = dim3((unsigned)G::kBlock); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
       cudaLaunchAttribute at{};
       at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
       at.val.programmaticStreamSerializationAllowed = 1;
       cfg.attrs = &at; cfg.numAttrs = 1;
-      CK(cudaLaunchKernelEx(&cfg, step_kernel<T, LANES, NC>, st, a2, handle_consts<T>(h)));
-    } else
+      CK(cudaLaunchKernelEx(&cfg, step_kernel_list<T, LANES, NC>, st, a2, handle_consts<T>(h)));
+      h->launches++;
+      CK(cudaGetLastError());
+      return ACKB_OK;
+    }
+    if (int rc = ensure_smem_attr(h, step_kernel<T, LANES, NC>, attr, smem)) return rc;
     step_kernel<T, LANES, NC><<<grid, G::kBlock, smem, stream>>>(st, a2, handle_consts<T>(h));
   }
   h->launches++;
@@ -517,12 +558,12 @@ int launch_step(ackb_handle* h, DevState<T>& st, const StepArgs& a, cudaStream_t
     // flat-floor model: fast kernel (two floor-contact slots per wheel) for the upright environments, then the general kernel
     // (extra slots: cap-down wheel points, chassis plates) for the environments the fast pass marked as tilted
     StepArgs f = a;
-    f.regime = 1; f.gen_mask = h->d_gen;
+    f.regime = 1; f.gen_list = h->d_gen_list; f.gen_count = h->d_gen_count;
     int rc = h->lanes == 8 ? launch_one<T, 8, 1>(h, st, f, stream, false)
                            : (h->lanes >= 4 ? launch_one<T, 4, 2>(h, st, f, stream, false) : launch_one<T, 1, 2>(h, st, f, stream, false));
     if (rc) return rc;
-    StepArgs g = a;
-    g.regime = 2; g.gen_mask = h->d_gen; g.pdl_wait = 1;
+    StepArgs g = f;
+    g.regime = 2;
     return launch_one<T, 4, 4>(h, st, g, stream, false);
   }
   if (h->lanes == 8 && !scene) return launch_one<T, 8, 1>(h, st, a, stream, is_reset);   // one lane per floor contact (flat-floor model)
@@ -580,8 +621,10 @@ int ackb_create(const double* consts, size_t consts_len, int num_envs, int devic
   CK(cudaMalloc(&h->d_trunc, n));
   CK(cudaMalloc(&h->d_done, n));
   CK(cudaMemset(h->d_done, 0, n));
-  CK(cudaMalloc(&h->d_gen, n));
-  CK(cudaMemset(h->d_gen, 0, n));
+  CK(cudaMalloc(&h->d_gen_list, n * sizeof(int)));
+  CK(cudaMemset(h->d_gen_list, 0, n * sizeof(int)));
+  CK(cudaMalloc(&h->d_gen_count, 2 * sizeof(int)));
+  CK(cudaMemset(h->d_gen_count, 0, 2 * sizeof(int)));
   if (const char* ev = getenv("ACKB_GENERAL_PASS")) h->general_pass = atoi(ev);
 
   CK(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
@@ -594,7 +637,7 @@ int ackb_destroy(ackb_handle* h) {
   if (!h) return ACKB_ERR_ARG;
   cudaSetDevice(h->device);
   cudaFree(h->state); cudaFree(h->stats); cudaFree(h->d_action); cudaFree(h->d_obs); cudaFree(h->d_reward);
-  cudaFree(h->d_term); cudaFree(h->d_trunc); cudaFree(h->d_done); cudaFree(h->d_gen);
+  cudaFree(h->d_term); cudaFree(h->d_trunc); cudaFree(h->d_done); cudaFree(h->d_gen_list); cudaFree(h->d_gen_count);
   if (h->order_ev) cudaEventDestroy(h->order_ev);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   delete[] h->consts_host;

@@ -689,3 +689,93 @@ def test_maze_wall_hits_use_plate_contacts():
     assert maxn >= 9, "wheel contacts plus at least one plate-vs-block contact"
     assert np.isfinite(q).all() and (np.abs(q[:, 2] + 0.435) < 0.05).all(), "robots stay on the maze floor (z about -0.435)"
     env.close()
+
+
+def _tumble_poses():
+    def quat(axis, deg):
+        a = np.deg2rad(deg) / 2
+        return np.array([np.cos(a), *(np.sin(a) * np.asarray(axis, float))])
+    return [(quat([1, 0, 0], 180), 0.12), (quat([0, 1, 0], 80), 0.2), (quat([1, 0, 0], 90), 0.13), (quat([0, 1, 0], -100), 0.25),
+            (quat([0, 0, 1], 30), 0.1), (quat([1, 0, 0], 10), 0.1), (quat([1, 1, 0] / np.sqrt(2.0), 120), 0.2)]
+
+
+@pytest.mark.parametrize("lanes", [1, 4])
+def test_general_pass_list_longer_than_its_grid(lanes):
+    """Regime split of the flat-floor model: the fast pass LISTS the tilted environments and the general pass is a fixed grid of one
+    CTA per SM (32 environments each) walking that list.  8192 environments, five of seven poses tilted: the list (5852 entries) needs
+    the grid-stride loop, its order is whatever the atomics gave, and the listed environments are scattered through the batch.
+    Every copy of a pose must stay bit-identical to the first one (the same property a 70-environment batch, whose list fits one
+    CTA pair, is checked for against the oracle in test_rollover_regime_split_matches_oracle), and the list must be empty again
+    after every step (an upright batch stepped afterwards is not touched by stale entries)."""
+    from mujoco_playground_b200 import BatchedAckermannEnv
+    M = _models()
+    poses = _tumble_poses()
+    n, P = 8192, len(poses)
+    env = BatchedAckermannEnv(n, dtype="float32", auto_reset=False, lanes_per_env=lanes)
+    small = BatchedAckermannEnv(P, dtype="float32", auto_reset=False, lanes_per_env=4)
+    for e, m in ((env, n), (small, P)):
+        e.reset()
+        qpos, qvel = np.tile(M["qpos0"], (m, 1)), np.zeros((m, 12))
+        for i in range(m):
+            q, z = poses[i % P]
+            qpos[i, 2] = z; qpos[i, 3:7] = q; qvel[i, 3:6] = [1.0, -2.0, 0.5]
+        e.set_state(qpos, qvel, np.zeros((m, 12)))
+    act = torch.zeros((n, 2), device="cuda:0")
+    act[:, 0] = 0.3
+    for t in range(12):
+        env.step(act)
+        small.step(act[:P].contiguous())
+        q, v, _ = env.get_state()
+        qs, vs, _ = small.get_state()
+        for p in range(P):
+            assert (q[p::P] == q[p]).all() and (v[p::P] == v[p]).all(), f"step {t}: copies of pose {p} differ"
+        if lanes == 4:      # the small batch runs the 4-lane fast kernel: same arithmetic as the big one only in that layout
+            assert np.array_equal(q[:P], qs) and np.array_equal(v[:P], vs), f"step {t}: 8192-env batch differs from the {P}-env batch"
+    assert env.stats()["bad_state"] == 0
+    # back to an upright batch: nothing may be left in the list
+    qpos, qvel = np.tile(M["qpos0"], (n, 1)), np.zeros((n, 12))
+    env.set_state(qpos, qvel, np.zeros((n, 12)))
+    for _ in range(3):
+        env.step(act)
+    q, v, _ = env.get_state()
+    assert (q == q[0]).all() and (v == v[0]).all()
+    env.close(); small.close()
+
+
+def test_step_replays_from_a_cuda_graph():
+    """ackb_step is stream-capture safe (constants travel as a kernel parameter, the general pass is a programmatic dependent launch,
+    its list counter is reset on the device): a step captured once and replayed equals the same steps launched one by one, bit for
+    bit, including environments that go through the general pass and through the fused auto-reset."""
+    from mujoco_playground_b200 import BatchedAckermannEnv
+    M = _models()
+    poses = _tumble_poses()
+    n, P = 512, len(poses)
+    envs = [BatchedAckermannEnv(n, dtype="float32", auto_reset=True, seed=5, max_episode_steps=25, lanes_per_env=4) for _ in range(2)]
+    qpos, qvel = np.tile(M["qpos0"], (n, 1)), np.zeros((n, 12))
+    for i in range(0, n, 3):
+        q, z = poses[i % P]
+        qpos[i, 2] = z; qpos[i, 3:7] = q; qvel[i, 3:6] = [1.0, -2.0, 0.5]
+    act = torch.zeros((n, 2), device="cuda:0")
+    act[:, 0] = 0.5; act[:, 1] = 0.2
+    for e in envs:
+        e.reset()
+        e.set_state(qpos, qvel, np.zeros((n, 12)))
+        e.step(act)                      # warm-up: function attributes are set outside the capture
+    eager, graphed = envs
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        graphed.step(act)
+    # the captured launch did not run: both environments are one step in
+    for t in range(60):
+        eager.step(act)
+        g.replay()
+    torch.cuda.synchronize()
+    qa, va, _ = eager.get_state()
+    qb, vb, _ = graphed.get_state()
+    assert np.array_equal(qa, qb) and np.array_equal(va, vb)
+    assert torch.equal(eager.obs, graphed.obs) and torch.equal(eager.reward, graphed.reward)
+    sa, sb = eager.stats(), graphed.stats()
+    assert sa["episodes"] == sb["episodes"] and sa["episodes"] >= 2 * n and sa["unsupported"] == sb["unsupported"] == 0
+    for e in envs:
+        e.close()
