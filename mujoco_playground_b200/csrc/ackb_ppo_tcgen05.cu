@@ -147,6 +147,7 @@ constexpr int IMG_BLOCKS = 16;       // 2 nets x 8 slices of the elements, 256 t
 __global__ void __launch_bounds__(256) ppo_t5_weight_images(const float* __restrict__ P, int D, unsigned char* __restrict__ img, float* __restrict__ grads,
                                                             float* __restrict__ diag, const float* __restrict__ adv, const int64_t* __restrict__ idx,
                                                             int mb, float* __restrict__ adv_out, double* __restrict__ adv_ws) {
+  asm volatile("griddepcontrol.launch_dependents;");      // the gradient kernel's set-up and first gather overlap this launch
   if ((int)blockIdx.x >= IMG_BLOCKS) {
     adv_stats_block(adv, idx, mb, adv_out, adv_ws, (int)blockIdx.x - IMG_BLOCKS, (int)gridDim.x - IMG_BLOCKS);
     return;
@@ -230,12 +231,6 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a, con
     mbar_expect_tx(mbw + which, bytes);
     bulk_g2s(dst, src, bytes, mbw + which);
   };
-  if (warp == 0) {
-    if (elect_one()) { load_w(0, 0); load_w(1, 0); load_w(2, 0); }
-    __syncwarp();
-  }
-
-  const float adv_mean = a.adv_stats[0], adv_istd = 1.0f / (a.adv_stats[1] + 1e-8f);
   const float inv_mb = 1.0f / (float)a.mb;
   const float ls0 = F[F_LS], ls1 = F[F_LS + 1];
   const float iv0 = expf(-2.0f * ls0), iv1 = expf(-2.0f * ls1);
@@ -366,6 +361,15 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a, con
     }
   };
   prefetch_row(prow);
+  // Everything above reads only what earlier launches produced (parameters, rollout arrays, the epoch's permutation) and overlaps
+  // the prologue launch (weight images, gradient / diagnostics zeroing, advantage statistics), of which this grid is a programmatic
+  // dependent.  From here on its results are needed: every thread waits (the gradient atomics at the end must follow the zeroing).
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (warp == 0) {
+    if (elect_one()) { load_w(0, 0); load_w(1, 0); load_w(2, 0); }
+    __syncwarp();
+  }
+  const float adv_mean = a.adv_stats[0], adv_istd = 1.0f / (a.adv_stats[1] + 1e-8f);
   T5_MARK(10);
 
   bool first = true;
@@ -910,8 +914,16 @@ int launch_grad_tcgen05(const PpoArgs& a, cudaStream_t stream, float* adv_out, d
   }
   ppo_t5_weight_images<<<IMG_BLOCKS + stat_blocks, 256, 0, stream>>>(a.params, a.D, static_cast<unsigned char*>(img), a.grads, a.diag, a.adv, a.idx,
                                                                      a.mb, adv_out, adv_ws);
-  ppo_grad_kernel_tcgen05<<<ntiles < sms ? ntiles : sms, NT5, SMEM_BYTES, stream>>>(a, static_cast<const unsigned char*>(img));
-  const cudaError_t e = cudaGetLastError();
+  // programmatic dependent launch: the gradient kernel's CTAs are scheduled while the prologue runs and wait (griddepcontrol.wait)
+  // after their set-up and the gather of their first tile
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(ntiles < sms ? ntiles : sms)); cfg.blockDim = dim3(NT5); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = stream;
+  cudaLaunchAttribute at{};
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &at; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, ppo_grad_kernel_tcgen05, a, static_cast<const unsigned char*>(img));
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (cudaFreeAsync(img, stream) != cudaSuccess) return ACKB_ERR_CUDA;
   return e == cudaSuccess ? ACKB_OK : ACKB_ERR_CUDA;
 }
