@@ -42,7 +42,10 @@ enum {
   ACKB_PPO_MODE_DEFAULT = -1,
   ACKB_PPO_MODE_FP32 = 0,      /* fp32 CUDA-core FMAs (exact-fp32 comparisons)                                                  */
   ACKB_PPO_MODE_TF32 = 1,      /* TF32 mma.sync m16n8k8 fragments (round-1 kernel)                                              */
-  ACKB_PPO_MODE_TCGEN05 = 2    /* TF32 tcgen05.mma: operands by shared-memory descriptor, accumulators in TMEM (obs_dim < 80)   */
+  ACKB_PPO_MODE_TCGEN05 = 2,   /* TF32 tcgen05.mma: operands by shared-memory descriptor, accumulators in TMEM (obs_dim < 80)   */
+  /* flag, OR-ed onto one of the three modes above: diag is NOT zeroed by the call; the minibatch's five values are added to it
+   * (zero it once per update and divide by the number of optimiser steps: no per-step accumulation launch on the caller's side) */
+  ACKB_PPO_DIAG_ACCUMULATE = 0x100
 };
 int ackb_ppo_minibatch_grad_mode(const float* obs, const float* act, const float* old_logp, const float* adv, const float* ret,
                                  const int64_t* idx, int mb, int obs_dim, const float* adv_mean_std, const float* params, float* grads,

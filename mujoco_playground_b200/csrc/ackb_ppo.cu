@@ -313,7 +313,8 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel(PpoArgs a) {
   }
   if (blockIdx.x == 0 && t == 0) {
     // entropy of the state-independent Gaussian: sum_j (0.5 + 0.5 log 2 pi + log_std_j); -ent_coef * H enters the loss
-    a.diag[2] = 2.0f * 1.4189385332046727f + ls0 + ls1;
+    if (a.diag_keep) atomicAdd(&a.diag[2], 2.0f * 1.4189385332046727f + ls0 + ls1);
+    else a.diag[2] = 2.0f * 1.4189385332046727f + ls0 + ls1;
     atomicAdd(&G[o.ls], -a.ent_coef); atomicAdd(&G[o.ls + 1], -a.ent_coef);
   }
 }
@@ -827,7 +828,8 @@ __global__ void __launch_bounds__(NT, 1) ppo_grad_kernel_tc(PpoArgs a) {
     }
   }
   if (blockIdx.x == 0 && t == 0) {
-    a.diag[2] = 2.0f * 1.4189385332046727f + ls0 + ls1;
+    if (a.diag_keep) atomicAdd(&a.diag[2], 2.0f * 1.4189385332046727f + ls0 + ls1);
+    else a.diag[2] = 2.0f * 1.4189385332046727f + ls0 + ls1;
     atomicAdd(&G[o.ls], -a.ent_coef); atomicAdd(&G[o.ls + 1], -a.ent_coef);
   }
 }
@@ -1274,6 +1276,8 @@ int ackb_ppo_minibatch_grad_pitched(const float* obs, int obs_pitch, const float
                                     const int64_t* idx, int mb, int obs_dim, const float* adv_mean_std, const float* params, float* grads,
                                     float* diag, float clip_range, float vf_coef, float ent_coef, int mode, void* stream) {
   NvtxRange nvtx("ackb_ppo_minibatch_grad");
+  const int diag_keep = (mode >= 0 && (mode & ACKB_PPO_DIAG_ACCUMULATE)) ? 1 : 0;
+  if (mode >= 0) mode &= ~ACKB_PPO_DIAG_ACCUMULATE;
   if (obs_pitch < obs_dim) return ACKB_ERR_ARG;
   if (!obs || !act || !old_logp || !adv || !ret || !adv_mean_std || !params || !grads || !diag || mb <= 0) return ACKB_ERR_ARG;
   if (obs_dim <= 0 || obs_dim > KP) return ACKB_ERR_ARG;
@@ -1285,7 +1289,7 @@ int ackb_ppo_minibatch_grad_pitched(const float* obs, int obs_pitch, const float
   if (g_use_tc < 0) { const char* ev = getenv("ACKB_PPO_TC"); g_use_tc = ev ? (atoi(ev) != 0) : 1; }
   if (mode != ACKB_PPO_MODE_DEFAULT && mode != ACKB_PPO_MODE_FP32 && mode != ACKB_PPO_MODE_TF32 && mode != ACKB_PPO_MODE_TCGEN05) return ACKB_ERR_ARG;
   if (mode == ACKB_PPO_MODE_TCGEN05) {     // Blackwell path: tcgen05.mma kind::tf32, accumulators in TMEM (ackb_ppo_tcgen05.cu)
-    PpoArgs a5{obs, act, old_logp, adv, ret, idx, mb, obs_dim, adv_mean_std, params, grads, diag, clip_range, vf_coef, ent_coef, obs_pitch};
+    PpoArgs a5{obs, act, old_logp, adv, ret, idx, mb, obs_dim, adv_mean_std, params, grads, diag, clip_range, vf_coef, ent_coef, obs_pitch, diag_keep};
     return launch_grad_tcgen05(a5, s, nullptr, nullptr);
   }
   const int use_tc = mode == ACKB_PPO_MODE_DEFAULT ? g_use_tc : (mode == ACKB_PPO_MODE_TF32 ? 1 : 0);
@@ -1299,8 +1303,8 @@ int ackb_ppo_minibatch_grad_pitched(const float* obs, int obs_pitch, const float
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const Offsets o = offsets(obs_dim);
   if (cudaMemsetAsync(grads, 0, sizeof(float) * o.total, s) != cudaSuccess) return ACKB_ERR_CUDA;
-  if (cudaMemsetAsync(diag, 0, sizeof(float) * 5, s) != cudaSuccess) return ACKB_ERR_CUDA;
-  PpoArgs a{obs, act, old_logp, adv, ret, idx, mb, obs_dim, adv_mean_std, params, grads, diag, clip_range, vf_coef, ent_coef, obs_pitch};
+  if (!diag_keep && cudaMemsetAsync(diag, 0, sizeof(float) * 5, s) != cudaSuccess) return ACKB_ERR_CUDA;
+  PpoArgs a{obs, act, old_logp, adv, ret, idx, mb, obs_dim, adv_mean_std, params, grads, diag, clip_range, vf_coef, ent_coef, obs_pitch, diag_keep};
   const int ntiles = (mb + (use_tc ? TT : TS) - 1) / (use_tc ? TT : TS);
   const int grid = ntiles < sms ? ntiles : sms;
   if (use_tc) ppo_grad_kernel_tc<<<grid, NT, smem, s>>>(a);
@@ -1320,10 +1324,11 @@ int ackb_ppo_minibatch_grad_stats(const float* obs, int obs_pitch, const float* 
                                   const int64_t* idx, int mb, int obs_dim, float* adv_mean_std, double* adv_workspace, const float* params,
                                   float* grads, float* diag, float clip_range, float vf_coef, float ent_coef, int mode, void* stream) {
   if (!adv || !adv_mean_std || !adv_workspace || mb <= 0) return ACKB_ERR_ARG;
-  if (mode == ACKB_PPO_MODE_TCGEN05 && obs_dim < KP) {      // statistics in the prologue launch of the tcgen05 kernel
+  const int diag_keep = (mode >= 0 && (mode & ACKB_PPO_DIAG_ACCUMULATE)) ? 1 : 0;
+  if ((mode >= 0 ? (mode & ~ACKB_PPO_DIAG_ACCUMULATE) : mode) == ACKB_PPO_MODE_TCGEN05 && obs_dim < KP) {      // statistics in the prologue launch of the tcgen05 kernel
     NvtxRange nvtx("ackb_ppo_minibatch_grad");
     if (!obs || !act || !old_logp || !ret || !params || !grads || !diag || obs_dim <= 0 || obs_pitch < obs_dim) return ACKB_ERR_ARG;
-    PpoArgs a5{obs, act, old_logp, adv, ret, idx, mb, obs_dim, adv_mean_std, params, grads, diag, clip_range, vf_coef, ent_coef, obs_pitch};
+    PpoArgs a5{obs, act, old_logp, adv, ret, idx, mb, obs_dim, adv_mean_std, params, grads, diag, clip_range, vf_coef, ent_coef, obs_pitch, diag_keep};
     return launch_grad_tcgen05(a5, (cudaStream_t)stream, adv_mean_std, adv_workspace);
   }
   const int rc = ackb_ppo_adv_stats_ws(adv, idx, mb, adv_mean_std, adv_workspace, stream);

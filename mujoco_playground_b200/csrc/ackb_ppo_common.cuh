@@ -29,6 +29,7 @@ struct PpoArgs {
   float* diag;
   float clip, vf_coef, ent_coef;
   int pitch;       // floats between consecutive observation rows (>= D)
+  int diag_keep;   // ACKB_PPO_DIAG_ACCUMULATE: diag is not zeroed by the call, this minibatch's five values are added to it
 };
 
 // tcgen05 / TMEM gradient kernel (ackb_ppo_tcgen05.cu); zeroes grads and diag itself (in its prologue launch, which also writes the

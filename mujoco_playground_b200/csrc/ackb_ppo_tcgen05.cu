@@ -146,7 +146,7 @@ __device__ long long g_t5_prof[32];
 constexpr int IMG_BLOCKS = 16;       // 2 nets x 8 slices of the elements, 256 threads each
 __global__ void __launch_bounds__(256) ppo_t5_weight_images(const float* __restrict__ P, int D, unsigned char* __restrict__ img, float* __restrict__ grads,
                                                             float* __restrict__ diag, const float* __restrict__ adv, const int64_t* __restrict__ idx,
-                                                            int mb, float* __restrict__ adv_out, double* __restrict__ adv_ws) {
+                                                            int mb, float* __restrict__ adv_out, double* __restrict__ adv_ws, int diag_keep) {
   asm volatile("griddepcontrol.launch_dependents;");      // the gradient kernel's set-up and first gather overlap this launch
   if ((int)blockIdx.x >= IMG_BLOCKS) {
     adv_stats_block(adv, idx, mb, adv_out, adv_ws, (int)blockIdx.x - IMG_BLOCKS, (int)gridDim.x - IMG_BLOCKS);
@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(256) ppo_t5_weight_images(const float* __restr
   const Offsets o = offsets(D);
   const int tid = slice * blockDim.x + threadIdx.x, nth = (IMG_BLOCKS / 2) * blockDim.x;
   for (int i = net * nth + tid; i < o.total; i += 2 * nth) grads[i] = 0.0f;
-  if (blockIdx.x == 0 && threadIdx.x < 5) diag[threadIdx.x] = 0.0f;
+  if (blockIdx.x == 0 && threadIdx.x < 5 && !diag_keep) diag[threadIdx.x] = 0.0f;
   unsigned char* im = img + (size_t)net * IMG_BYTES;
   const float* W1g = P + (net ? o.W1v : o.W1p);
   const float* W2g = P + (net ? o.W2v : o.W2p);
@@ -655,7 +655,8 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a, con
   }
   if (blockIdx.x == 0 && t == 0) {
     // entropy of the state-independent Gaussian: sum_j (0.5 + 0.5 log 2 pi + log_std_j); -ent_coef * H enters the loss
-    a.diag[2] = 2.0f * 1.4189385332046727f + ls0 + ls1;
+    if (a.diag_keep) atomicAdd(&a.diag[2], 2.0f * 1.4189385332046727f + ls0 + ls1);
+    else a.diag[2] = 2.0f * 1.4189385332046727f + ls0 + ls1;
     atomicAdd(&G[o.ls], -a.ent_coef); atomicAdd(&G[o.ls + 1], -a.ent_coef);
   }
   fence_before_sync();
@@ -913,7 +914,7 @@ int launch_grad_tcgen05(const PpoArgs& a, cudaStream_t stream, float* adv_out, d
     stat_blocks = stat_blocks > 280 ? 280 : (stat_blocks < 1 ? 1 : stat_blocks);
   }
   ppo_t5_weight_images<<<IMG_BLOCKS + stat_blocks, 256, 0, stream>>>(a.params, a.D, static_cast<unsigned char*>(img), a.grads, a.diag, a.adv, a.idx,
-                                                                     a.mb, adv_out, adv_ws);
+                                                                     a.mb, adv_out, adv_ws, a.diag_keep);
   // programmatic dependent launch: the gradient kernel's CTAs are scheduled while the prologue runs and wait (griddepcontrol.wait)
   // after their set-up and the gather of their first tile
   cudaLaunchConfig_t cfg{};

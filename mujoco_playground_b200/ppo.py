@@ -128,6 +128,9 @@ def ppo_update(policy: ActorCritic, opt: torch.optim.Optimizer, batch: Dict[str,
     mb = max(1, n // cfg.minibatches)
     stats = dict(pg_loss=0.0, v_loss=0.0, entropy=0.0, approx_kl=0.0, clip_frac=0.0, steps=0, allreduce_bytes=0)
     acc = torch.zeros(5, device=batch["obs"].device)      # diagnostics accumulate on the device: one host read per update
+    in_kernel = isinstance(graphed, FusedMinibatchStep) and graphed.accumulate_diag      # ... inside the gradient kernel itself
+    if in_kernel:
+        graphed.diag.zero_()
     params = [p for p in policy.parameters() if p.requires_grad]
     # native per-epoch permutation (no sort) for the fused learner in index mode; an explicit generator keeps torch.randperm
     native_perm = (isinstance(graphed, FusedMinibatchStep) and graphed.index_mode and generator is None
@@ -139,16 +142,23 @@ def ppo_update(policy: ActorCritic, opt: torch.optim.Optimizer, batch: Dict[str,
         else:
             perm = torch.randperm(n, device=batch["obs"].device, generator=generator)
             shuffled = graphed.shuffle_epoch(batch, perm) if isinstance(graphed, FusedMinibatchStep) else None
+        if shuffled is not None and in_kernel:      # a whole epoch of optimiser steps: one graph launch when it was captured
+            slots = [(i * mb, min(mb, n - i * mb)) for i in range(cfg.minibatches)]
+            stats["allreduce_bytes"] += graphed.run_epoch(shuffled, slots, world)
+            stats["steps"] += len(slots)
+            continue
         for i in range(cfg.minibatches):
             if shuffled is not None:
                 stats["allreduce_bytes"] += graphed.run(shuffled, (i * mb, min(mb, n - i * mb)), world)
-                acc += graphed.diag
+                if not in_kernel:
+                    acc += graphed.diag
                 stats["steps"] += 1
                 continue
             idx = perm[i * mb:(i + 1) * mb]
             if graphed is not None and graphed.mb in (-1, idx.numel()):
                 stats["allreduce_bytes"] += graphed.run(batch, idx, world)
-                acc += graphed.diag
+                if not in_kernel:
+                    acc += graphed.diag
                 stats["steps"] += 1
                 continue
             obs, act, old_logp, adv, ret = (batch[k][idx] for k in ("obs", "act", "logp", "adv", "ret"))
@@ -167,6 +177,8 @@ def ppo_update(policy: ActorCritic, opt: torch.optim.Optimizer, batch: Dict[str,
                 acc += torch.stack([pg.detach(), vl.detach(), ent.mean(), ((ratio - 1) - (logp - old_logp)).mean(),
                                     ((ratio - 1).abs() > cfg.clip_range).float().mean()])
                 stats["steps"] += 1
+    if in_kernel:
+        acc = graphed.diag
     for k, v in zip(("pg_loss", "v_loss", "entropy", "approx_kl", "clip_frac"), (acc / max(1, stats["steps"])).tolist()):
         stats[k] = v
     return stats
@@ -292,6 +304,10 @@ class FusedMinibatchStep:
             opt.param_groups[0]["params"] = [self.flat_param]
             self.params = [self.flat_param]
         self.diag = torch.zeros(5, device=device, dtype=torch.float32)
+        # True: the gradient call ADDS the minibatch's diagnostics to `diag` (ACKB_PPO_DIAG_ACCUMULATE) instead of overwriting it;
+        # ppo_update then zeroes it once per update and launches nothing per step.  Set before capture() (the flag is baked into
+        # the captured launches).
+        self.accumulate_diag = False
         self.adv_stats = torch.zeros(2, device=device, dtype=torch.float32)
         self.adv_ws = torch.zeros(3, device=device, dtype=torch.float64)     # this learner's own accumulators (ackb_ppo_adv_stats_ws)
         # optimiser step as one kernel (ackb_ppo_clip_adam) on torch's own Adam state tensors, so that opt.state_dict() stays the
@@ -429,10 +445,12 @@ class FusedMinibatchStep:
         idx = idx.contiguous()
         return batch, int(idx.numel()), idx
 
-    def capture(self, shuffled: Dict[str, torch.Tensor], slots) -> None:
+    def capture(self, shuffled: Dict[str, torch.Tensor], slots, epoch_graph: bool = False) -> None:
         """CUDA graphs for the minibatch slots (start, count) of the shuffled rollout: per slot {advantage statistics + gradient
         kernel}, and one graph for {gradient clipping + Adam}.  Needs an optimiser built with capturable=True.  The warm-up steps
-        are undone (weights and optimiser state restored in place)."""
+        are undone (weights and optimiser state restored in place).  epoch_graph: additionally ONE graph holding all optimiser
+        steps of an epoch back to back (run_epoch; needs accumulate_diag, and no NCCL call between gradient and optimiser step,
+        i.e. a single rank or the peer-memory all-reduce)."""
         dev = self.device
         self._cap_ptrs = tuple(shuffled[k].data_ptr() for k in _ROLLOUT_KEYS)
         saved_p = self.flat_p.clone()
@@ -456,6 +474,13 @@ class FusedMinibatchStep:
             self.g1[sl] = g
         with torch.cuda.graph(self.g2):
             self._clip_step()
+        self.g_epoch = None
+        if epoch_graph and self.accumulate_diag and (len(slots) % 2 == 0 or self.peer is None):
+            self.g_epoch, self._epoch_slots = torch.cuda.CUDAGraph(), tuple(slots)
+            with torch.cuda.graph(self.g_epoch):
+                for i, sl in enumerate(slots):
+                    self._grad(shuffled, sl, i & 1)
+                    self._clip_step()
         with torch.no_grad():
             self.flat_p.copy_(saved_p)
             for p in self.params:
@@ -506,7 +531,8 @@ class FusedMinibatchStep:
         rc = self.L.ackb_ppo_minibatch_grad_stats(ptr(view["obs"]), int(view["obs"].stride(0)), ptr(view["act"]), ptr(view["logp"]),
                                                   ptr(view["adv"]), ptr(view["ret"]), ptr(rows) if rows is not None else None, n,
                                                   self.obs_dim, ptr(self.adv_stats), ptr(self.adv_ws), ptr(self.flat_p), ptr(gbuf), ptr(self.diag),
-                                                  cfg.clip_range, cfg.vf_coef, cfg.ent_coef, self.mode, stream)
+                                                  cfg.clip_range, cfg.vf_coef, cfg.ent_coef,
+                                                  self.mode | (0x100 if self.accumulate_diag else 0), stream)
         if rc != 0:
             raise RuntimeError(f"ackb_ppo_minibatch_grad failed with code {rc}")
 
@@ -534,6 +560,17 @@ class FusedMinibatchStep:
         else:
             self._clip_step()
         return nbytes
+
+    def run_epoch(self, batch: Dict[str, torch.Tensor], slots, world: int) -> int:
+        """All optimiser steps of one epoch (slots = the (start, count) ranges of its minibatches): one graph launch when capture()
+        recorded an epoch graph for exactly these slots and arrays, else step by step.  Returns the all-reduced bytes."""
+        ge = getattr(self, "g_epoch", None)
+        if (ge is not None and tuple(slots) == self._epoch_slots and self._same_arrays(batch) and (world == 1 or self.peer is not None)
+                and (self.peer is None or (self._mbc & 1) == 0)):
+            ge.replay()
+            self._mbc += len(slots)
+            return len(slots) * self.flat_g.numel() * 4 if world > 1 else 0
+        return sum(self.run(batch, sl, world) for sl in slots)
 
     def _same_arrays(self, batch: Dict[str, torch.Tensor]) -> bool:
         """True if `batch` is made of the very arrays the graphs were captured on."""
@@ -580,6 +617,7 @@ class PPOTrainer:
         self._adv, self._ret = torch.empty((T, N), **f), torch.empty((T, N), **f)    # persistent: CUDA graphs are captured on them
         if self.learner == "fused":     # flat parameter buffers exist from the start: the rollout forward uses them too
             self.graphed = FusedMinibatchStep(self.policy, self.opt, cfg, D, self.device, mode=learner_mode)
+            self.graphed.accumulate_diag = True      # no per-step accumulation launch in update()
             self.peer_allreduce = self.graphed.enable_peer_allreduce(self.world, self.rank) if (self.world > 1 and self.device.type == "cuda") else False
 
     def grad_kernel_seconds(self, reps: int = 5) -> Optional[float]:
@@ -667,7 +705,8 @@ class PPOTrainer:
             n = flat["obs"].shape[0]
             mb = max(1, n // cfg.minibatches)
             sh = self.graphed.shuffle_epoch(flat, torch.arange(n, device=self.device))
-            self.graphed.capture(sh, [(i * mb, mb) for i in range(cfg.minibatches)])
+            self.graphed.capture(sh, [(i * mb, mb) for i in range(cfg.minibatches)],
+                                 epoch_graph=(self.world == 1 or self.graphed.peer is not None) and os.environ.get("ACKB_PPO_EPOCH_GRAPH", "1") != "0")
         if self.use_graphs and self.graphed is None:
             n = flat["obs"].shape[0]
             self.graphed = GraphedMinibatchStep(self.policy, self.opt, cfg, max(1, n // cfg.minibatches), flat["obs"].shape[1], self.device)

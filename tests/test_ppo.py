@@ -607,3 +607,35 @@ def test_peer_memory_allreduce_matches_nccl_on_two_gpus():
                         "--master-port", "29533", os.path.join(root, "tools", "gpu", "ppo_peer_check.py"), "4096"],
                        capture_output=True, text=True, timeout=600)
     assert "PEER CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["tcgen05", "tf32", "fp32"])
+def test_diag_accumulate_flag_sums_the_minibatch_diagnostics(mode):
+    """ACKB_PPO_DIAG_ACCUMULATE: the gradient call adds its five diagnostics to `diag` instead of overwriting it (ppo_update then
+    launches nothing per optimiser step to accumulate them); the gradient itself is unchanged."""
+    from mujoco_playground_b200.ppo import FusedMinibatchStep
+    dev = torch.device("cuda:0")
+    torch.manual_seed(11)
+    m, D = 4096, 79
+    obs = torch.zeros(m, 80, device=dev)
+    obs[:, :D] = torch.randn(m, D, device=dev)
+    batch = dict(obs=obs, act=torch.randn(m, 2, device=dev).clamp(-1, 1), logp=torch.randn(m, device=dev) * 0.3 - 2.0,
+                 adv=torch.randn(m, device=dev), ret=torch.randn(m, device=dev))
+    pol = ActorCritic(D).to(dev)
+    f = FusedMinibatchStep(pol, torch.optim.SGD(pol.parameters(), lr=0.0), PPOConfig(max_grad_norm=1e30), D, dev, mode=mode)
+    parts = [torch.randperm(m, device=dev)[:1500 + 300 * i] for i in range(3)]
+    single = []
+    for ix in parts:
+        f.run(batch, ix, world=1)
+        torch.cuda.synchronize()
+        single.append((f.diag.clone(), f.flat_g.clone()))
+    f.accumulate_diag = True
+    f.diag.zero_()
+    for i, ix in enumerate(parts):
+        f.run(batch, ix, world=1)
+        torch.cuda.synchronize()
+        sc = single[i][1].abs().max().item()
+        assert (f.flat_g - single[i][1]).abs().max().item() < 1e-5 * sc
+    want = sum(d for d, _ in single)
+    assert torch.allclose(f.diag, want, rtol=1e-5, atol=1e-6), (f.diag, want)
