@@ -1940,23 +1940,38 @@ struct Sim {
   }
 
   // ---- B9 rangefinder of observation slot `slot` (ray against the floor plane; boxes in the scene)
-  ACKB_HD static T lidar_ray(const Consts<T>& C, const State& e, const Kin<T>& k, int beam) {
+  // Per-environment part, computed once for all beams: B = world position of the lidar centre (beam origins sit on a circle of
+  // radius lidar_r around it, along the beam direction: o = B + r dw), h0 = its height above the floor plane.
+  struct LidarBase { T B[3]; T h0; };
+  ACKB_HD static void lidar_base(const Consts<T>& C, const State& e, const Kin<T>& k, LidarBase& b) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) b.B[i] = e.p[i] + k.R[3 * i] * C.lidar_pos[0] + k.R[3 * i + 1] * C.lidar_pos[1] + k.R[3 * i + 2] * C.lidar_pos[2];
+    b.h0 = b.B[2] - C.plane_z[0];
+  }
+  ACKB_HD static T lidar_ray(const Consts<T>& C, const Kin<T>& k, const LidarBase& b, int beam) {
     T cb, sb;
     tbl_beam(C, beam, &cb, &sb);
-    const T o[3] = {C.lidar_pos[0] + C.lidar_r[0] * cb, C.lidar_pos[1] + C.lidar_r[0] * sb, C.lidar_pos[2]};
     T best = T(-1);
-    // floor: local z of the ray = n . d ; height of the origin = n . o + hO
+    // ray direction in world axes; its z component is the floor normal (body frame) dotted with the beam direction
     const T lvz = k.n[0] * cb + k.n[1] * sb;
-    const T ow[3] = {e.p[0] + k.R[0] * o[0] + k.R[1] * o[1] + k.R[2] * o[2], e.p[1] + k.R[3] * o[0] + k.R[4] * o[1] + k.R[5] * o[2],
-                     e.p[2] + k.R[6] * o[0] + k.R[7] * o[1] + k.R[8] * o[2]};
     const T dw[3] = {k.R[0] * cb + k.R[1] * sb, k.R[3] * cb + k.R[4] * sb, lvz};
+    const T r = C.lidar_r[0];
+    // floor: the origin's height is h0 + r lvz, so the ray parameter of the plane is x = -(h0 + r lvz) / lvz = s - r with
+    // s = -h0 / lvz, and the hit point is B + s dw (mj_ray's plane test: x >= 0, hit point inside the plane's half sizes)
     if (!(lvz > -N::minval)) {
-      T x = -(ow[2] - C.plane_z[0]) * N::rcp_(lvz);
+      const T sp = -b.h0 * N::rcp_(lvz);
+      const T x = sp - r;
       if (x >= T(0)) {
-        T px = ow[0] + x * dw[0], py = ow[1] + x * dw[1];
-        if ((C.plane_half[0] <= T(0) || N::abs_(px) <= C.plane_half[0]) && (C.plane_half[1] <= T(0) || N::abs_(py) <= C.plane_half[1])) best = x;
+        const T px = b.B[0] + sp * dw[0], py = b.B[1] + sp * dw[1];
+        const bool in = (C.plane_half[0] <= T(0) || N::abs_(px) <= C.plane_half[0]) && (C.plane_half[1] <= T(0) || N::abs_(py) <= C.plane_half[1]);
+        best = in ? x : best;
       }
     }
+    if (C.nbox[0] == T(0)) {      // no obstacles (flat-floor model): done
+      if (C.lidar_cutoff[0] > T(0) && best > C.lidar_cutoff[0]) best = C.lidar_cutoff[0];
+      return best;
+    }
+    const T ow[3] = {b.B[0] + r * dw[0], b.B[1] + r * dw[1], b.B[2] + r * dw[2]};
     const int nbox = (int)C.nbox[0];
     if (C.grid_on[0] != T(0)) {
       // boxes on a lattice: walk the cells along the ray (2-D DDA) and test only the boxes met; the first box hit is the

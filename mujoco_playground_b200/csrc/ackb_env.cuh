@@ -69,8 +69,10 @@ struct EnvOps {
                               T* goal_distance, T* min_lidar) {
     const int nbeam = (int)C.nbeam[0];
     T mn = T(1e30);
+    typename S::LidarBase lb;
+    S::lidar_base(C, e, k, lb);
     for (int slot = lane; slot < nbeam; slot += LANES) {
-      T d = S::lidar_ray(C, e, k, tbl_lidar_map(C, slot));
+      T d = S::lidar_ray(C, k, lb, tbl_lidar_map(C, slot));
       sink.put(slot, (float)d);
       mn = d < mn ? d : mn;
     }
