@@ -283,6 +283,7 @@ __global__ void __launch_bounds__(NT5, 1) ppo_grad_kernel_tcgen05(PpoArgs a, con
     mbar_wait(mbar, phase);
     phase ^= 1u;
     fence_after_sync();
+    T5_MARK(24 + decltype(grp)::value);
   };
   auto none = [] {};
   using Yes = std::true_type;

@@ -36,7 +36,9 @@ for i, n in enumerate(names):
     print(f"{n:18s} {per:9.0f} cycles per tile{'' if i == 0 else ' and net'}  {100.0 * out[i] / tot:5.1f} %")
 print(f"inside the 4 MMA steps per tile and net: own tcgen05.wait::st {out[15] / 5 / tiles / 2:.0f}, fences {out[12] / 5 / tiles / 2:.0f}, CTA barrier {out[13] / 5 / tiles / 2:.0f}, "
       f"issue by thread 0: (1) {out[16] / 5 / tiles / 2:.0f}, (2) {out[17] / 5 / tiles / 2:.0f}, (3)(4)(6) {out[18] / 5 / tiles / 2:.0f}, (5) {out[19] / 5 / tiles / 2:.0f} cycles (the mma rows above are what remains: execution + completion wait)")
-tot += out[12] + out[13] + out[15] + sum(out[16:20])
+print(f"completion wait after the issue (mbarrier + fence), per tile and net: (1) {out[24] / 5 / tiles / 2:.0f}, (2) {out[25] / 5 / tiles / 2:.0f}, (3)(4)(6) {out[26] / 5 / tiles / 2:.0f}, "
+      f"(5) {out[27] / 5 / tiles / 2:.0f} cycles (now excluded from the mma rows above, which keep what follows the wait: weight reload issue, loads)")
+tot += out[12] + out[13] + out[15] + sum(out[16:20]) + sum(out[24:28])
 print(f"X step per tile: convert + store to smem {out[21] / 5 / tiles:.0f}, issue next loads + barrier {out[0] / 5 / tiles:.0f}, smem -> TMEM {out[22] / 5 / tiles:.0f}")
 tot += out[21] + out[22]
 print(f"total {tot / 5 / tiles:.0f} cycles per tile, both nets ({tot / 5:.0f} per launch)")
