@@ -319,3 +319,51 @@ def test_plate_vs_wall_contacts_match_oracle(name):
             assert np.abs(h.qvel - o.sim.qvel).max() < 1e-8 * max(1.0, np.abs(o.sim.qvel).max())
             plate_steps += int(any(gt[cc["geom1"]] == 6 and gt[cc["geom2"]] == 7 for cc in o.sim.contacts()))
     assert plate_steps > 100, "the drive must produce plate-vs-block contacts"
+
+
+@pytest.mark.parametrize("f32,tol", [(False, 1e-9), (True, 2e-4)])
+def test_flat_floor_lidar_matches_oracle_rays(f32, tol):
+    """Flat-floor model (72 slots, beam origins on a 0.035 m circle, 12 m cutoff, 40 m floor plane): the kernel's floor test works from
+    a per-environment base (lidar centre B, height h0: ray parameter -h0 / lvz - r, hit point B - (h0 / lvz) dw), the oracle casts every
+    ray from its own origin like mj_ray.  Upright, tilted, tumbling and high poses, robots at the edge of the plane (hits beyond the
+    half size do not count: -1) and rays above the horizon."""
+    o = OracleEnv(M)
+    h = HostSim(build_consts(M, model_kind=0), f32)
+    rng = np.random.default_rng(21)
+    seen_miss = seen_cut = seen_near = 0
+    for i in range(300):
+        qpos = M["qpos0"].copy()
+        mode = i % 5
+        if mode == 0:      # driving pose
+            qpos[:2] = rng.uniform(-20, 20, 2); qpos[2] = 0.0645 + rng.uniform(0, 0.002)
+            q = np.array([1.0, *(rng.normal(size=3) * 0.03)])
+        elif mode == 1:    # tilted, in the air
+            qpos[:2] = rng.uniform(-20, 20, 2); qpos[2] = rng.uniform(0.1, 0.6)
+            q = np.array([1.0, *(rng.normal(size=3) * 0.3)])
+        elif mode == 2:    # tumbling
+            qpos[:2] = rng.uniform(-20, 20, 2); qpos[2] = rng.uniform(0.2, 1.0)
+            q = rng.normal(size=4)
+        elif mode == 3:    # at the edge of the 40 m plane, nose down: near hits inside, far hits beyond the edge
+            qpos[0] = rng.choice([-1, 1]) * rng.uniform(39.0, 39.99); qpos[1] = rng.uniform(-39.9, 39.9); qpos[2] = rng.uniform(0.07, 0.3)
+            q = np.array([1.0, *(rng.normal(size=3) * 0.1)])
+        else:              # high up: every downward ray is longer than the cutoff
+            qpos[:2] = rng.uniform(-5, 5, 2); qpos[2] = rng.uniform(3.0, 8.0)
+            q = np.array([1.0, *(rng.normal(size=3) * 0.2)])
+        qpos[3:7] = q / np.linalg.norm(q)
+        goal = rng.uniform(-3, 3, 2)
+        want = o.reset(goal, spawn_qpos=qpos)
+        h.qpos[:] = qpos
+        h.epd[:2] = goal
+        h.epd[2:4] = qpos[:2]
+        got, _, _ = h.observe()
+        lid_w, lid_g = want[:72], got[:72]
+        # a ray within rounding of the horizon or of the plane's edge may flip between hit and miss in fp32: compare where both agree
+        miss_w, miss_g = lid_w < 0, lid_g < 0
+        flips = int((miss_w != miss_g).sum())
+        assert flips <= (2 if f32 else 0), f"pose {i}: {flips} hit / miss flips"
+        both = ~miss_w & ~miss_g
+        # (relative: a grazing ray's length is h0 / lvz with lvz close to zero)
+        assert np.all(np.abs(lid_g[both] - lid_w[both]) <= tol * np.maximum(1.0, np.abs(lid_w[both]))), f"pose {i}"
+        np.testing.assert_allclose(got[72:], want[72:], atol=2e-6 if not f32 else 2e-4)
+        seen_miss += int(miss_w.sum()); seen_cut += int((lid_w == 12.0).sum()); seen_near += int((both & (lid_w < 1.0)).sum())
+    assert seen_miss > 1000 and seen_cut > 1000 and seen_near > 300, (seen_miss, seen_cut, seen_near)
