@@ -269,6 +269,7 @@ class FusedMinibatchStep:
     capturable plain Adam.  Same arithmetic as the eager loop of ppo_update up to fp32 summation order (tests/test_ppo.py)."""
 
     MODES = {"default": -1, "fp32": 0, "tf32": 1, "tcgen05": 2}
+    DIAG_ACCUMULATE = 0x100      # ACKB_PPO_DIAG_ACCUMULATE (include/ackb_ppo.h): flag OR-ed onto the per-call mode
 
     def __init__(self, policy: ActorCritic, opt: torch.optim.Optimizer, cfg: PPOConfig, obs_dim: int, device, mode: str = "tcgen05"):
         import ctypes
@@ -532,7 +533,7 @@ class FusedMinibatchStep:
                                                   ptr(view["adv"]), ptr(view["ret"]), ptr(rows) if rows is not None else None, n,
                                                   self.obs_dim, ptr(self.adv_stats), ptr(self.adv_ws), ptr(self.flat_p), ptr(gbuf), ptr(self.diag),
                                                   cfg.clip_range, cfg.vf_coef, cfg.ent_coef,
-                                                  self.mode | (0x100 if self.accumulate_diag else 0), stream)
+                                                  self.mode | (self.DIAG_ACCUMULATE if self.accumulate_diag else 0), stream)
         if rc != 0:
             raise RuntimeError(f"ackb_ppo_minibatch_grad failed with code {rc}")
 
