@@ -533,9 +533,19 @@ class FusedMinibatchStep:
                                                   ptr(view["adv"]), ptr(view["ret"]), ptr(rows) if rows is not None else None, n,
                                                   self.obs_dim, ptr(self.adv_stats), ptr(self.adv_ws), ptr(self.flat_p), ptr(gbuf), ptr(self.diag),
                                                   cfg.clip_range, cfg.vf_coef, cfg.ent_coef,
-                                                  self.mode | (self.DIAG_ACCUMULATE if self.accumulate_diag else 0), stream)
+                                                  self._call_mode(), stream)
         if rc != 0:
             raise RuntimeError(f"ackb_ppo_minibatch_grad failed with code {rc}")
+
+    def _call_mode(self) -> int:
+        """Per-call arithmetic mode (+ the diagnostics flag).  The flag needs a concrete mode: "default" (-1: the library's
+        process-wide setting, ACKB_PPO_TC) is resolved here."""
+        m = self.mode
+        if self.accumulate_diag:
+            if m < 0:
+                m = 0 if os.environ.get("ACKB_PPO_TC") == "0" else 1
+            m |= self.DIAG_ACCUMULATE
+        return m
 
     def run(self, batch: Dict[str, torch.Tensor], idx, world: int) -> int:
         """idx: int64 index tensor (rows of `batch`), or a (start, count) range of the epoch prepared by shuffle_epoch."""
