@@ -27,9 +27,15 @@
 #if defined(__CUDACC__)
 #define ACKB_HD __host__ __device__ __forceinline__
 #define ACKB_D __device__ __forceinline__
+#ifdef ACKB_COLD_INLINE                                 // tuning: everything inline, as before
+#define ACKB_COLD __host__ __device__ __forceinline__
+#else
+#define ACKB_COLD __host__ __device__ __noinline__      // rarely executed blocks kept out of the hot instruction stream
+#endif
 #else
 #define ACKB_HD inline
 #define ACKB_D inline
+#define ACKB_COLD inline
 #endif
 
 namespace ackb {
@@ -977,6 +983,12 @@ struct Sim {
     const unsigned wv = (unsigned)C.pl_adj[(p * 32 + v) * 6 + (ei >> 2)];
     return (int)((wv >> (6 * (ei & 3))) & 63u);
   }
+  // out-of-line entry for the step kernels: state and kinematics travel BY VALUE, so that the caller's copies stay in registers (an
+  // address passed to a real call would pin them in local memory for the whole substep); executed only when a plate can touch
+  // something (warp-uniform test in dynamics), which is rare
+  ACKB_COLD static int plate_contacts_cold(const Consts<T>& C, State e, Kin<T> k, int p, T (*xb)[3], T* dist, unsigned* code) {
+    return plate_contacts(C, e, k, p, xb, dist, code);
+  }
   ACKB_HD static int plate_contacts(const Consts<T>& C, const State& e, const Kin<T>& k, int p, T (*xb)[3], T* dist, unsigned* code) {
     int cnt = 0;
     const int nv = (int)C.pl_nvert[p];
@@ -1589,7 +1601,7 @@ struct Sim {
         if (C.pl_count[0] != T(0) && plates_near) {
           T pxb[kMaxPlate][3], pdist[kMaxPlate];
           unsigned pcode[kMaxPlate];
-          const int np = plate_contacts(C, e, k, wi >> 1, pxb, pdist, pcode);
+          const int np = plate_contacts_cold(C, e, k, wi >> 1, pxb, pdist, pcode);
           const int part = wi & 1;
           for (int j = 0; j < 2; ++j) {
             const int idx = 2 * part + j;
