@@ -639,3 +639,56 @@ def test_diag_accumulate_flag_sums_the_minibatch_diagnostics(mode):
         assert (f.flat_g - single[i][1]).abs().max().item() < 1e-5 * sc
     want = sum(d for d, _ in single)
     assert torch.allclose(f.diag, want, rtol=1e-5, atol=1e-6), (f.diag, want)
+
+
+def test_ppo_update_host_logic_with_in_kernel_diagnostics():
+    """ppo_update around a FusedMinibatchStep whose gradient calls accumulate the diagnostics themselves (accumulate_diag): the
+    accumulator is zeroed once per update, every epoch goes through run_epoch with the (start, count) ranges of its minibatches, no
+    per-step accumulation happens on the host side, and the reported losses are the accumulated sums divided by the number of
+    optimiser steps.  The learner is a stand-in without CUDA: this is the host logic only (the kernels are covered by the gpu tests)."""
+    from mujoco_playground_b200.ppo import FusedMinibatchStep
+    import ctypes
+
+    def header_flag():
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        for line in open(os.path.join(root, "include", "ackb_ppo.h")):
+            if line.strip().startswith("ACKB_PPO_DIAG_ACCUMULATE"):
+                return int(line.split("=")[1].strip().rstrip(",").split()[0], 0)
+        raise AssertionError("ACKB_PPO_DIAG_ACCUMULATE not declared in include/ackb_ppo.h")
+    assert FusedMinibatchStep.DIAG_ACCUMULATE == header_flag()
+
+    class Stub(FusedMinibatchStep):
+        def __init__(self):      # no library, no device
+            self.accumulate_diag, self.index_mode, self.mode = True, True, 2
+            self.diag = torch.full((5,), 123.0)      # stale values of an earlier update: must be zeroed
+            self.calls, self.epochs = [], []
+            self.ct = ctypes
+
+        def new_epoch(self, batch, seed, epoch):
+            self.epochs.append((seed, epoch))
+            return batch
+
+        def run_epoch(self, batch, slots, world):
+            self.calls.append(tuple(slots))
+            for _ in slots:
+                self.diag += torch.tensor([1.0, 2.0, 3.0, 4.0, 5.0])
+            return 10 * len(slots)
+
+        def run(self, *a, **k):
+            raise AssertionError("per-step path taken although the diagnostics accumulate in the kernel")
+
+    n, cfg = 1000, PPOConfig(n_epochs=3, minibatches=4)
+    batch = dict(obs=torch.zeros(n, 79), act=torch.zeros(n, 2), logp=torch.zeros(n), adv=torch.zeros(n), ret=torch.zeros(n))
+    pol = ActorCritic(79)
+    f = Stub()
+    st = ppo_update(pol, torch.optim.SGD(pol.parameters(), lr=0.0), batch, cfg, world=1, graphed=f, perm_seed=77)
+    assert f.calls == [((0, 250), (250, 250), (500, 250), (750, 250))] * 3
+    assert [s for s, _ in f.epochs] == [77] * 3 and len({e for _, e in f.epochs}) == 3      # a fresh permutation per epoch
+    assert st["steps"] == 12 and st["allreduce_bytes"] == 120
+    assert (st["pg_loss"], st["v_loss"], st["entropy"], st["approx_kl"], st["clip_frac"]) == (1.0, 2.0, 3.0, 4.0, 5.0)
+    # the flag travels on the per-call mode; "default" (-1) is resolved to a concrete arithmetic first
+    assert f._call_mode() == (2 | FusedMinibatchStep.DIAG_ACCUMULATE)
+    f.mode = -1
+    assert f._call_mode() in (0 | FusedMinibatchStep.DIAG_ACCUMULATE, 1 | FusedMinibatchStep.DIAG_ACCUMULATE)
+    f.accumulate_diag = False
+    assert f._call_mode() == -1
