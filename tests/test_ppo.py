@@ -692,3 +692,44 @@ def test_ppo_update_host_logic_with_in_kernel_diagnostics():
     assert f._call_mode() in (0 | FusedMinibatchStep.DIAG_ACCUMULATE, 1 | FusedMinibatchStep.DIAG_ACCUMULATE)
     f.accumulate_diag = False
     assert f._call_mode() == -1
+
+
+def test_run_epoch_graph_selection_logic():
+    """FusedMinibatchStep.run_epoch replays the epoch graph only for exactly the captured slots and arrays, on a single rank or with the
+    peer-memory all-reduce, and (peer path) only when the gradient-buffer parity is back at zero; otherwise it steps one by one."""
+    from mujoco_playground_b200.ppo import FusedMinibatchStep
+
+    class FakeGraph:
+        def __init__(self):
+            self.n = 0
+
+        def replay(self):
+            self.n += 1
+
+    class Stub(FusedMinibatchStep):
+        def __init__(self):
+            self.g_epoch, self._epoch_slots, self._mbc, self.peer = FakeGraph(), ((0, 4), (4, 4)), 0, None
+            self.flat_g = torch.zeros(10)
+            self.same, self.steps = True, []
+
+        def _same_arrays(self, batch):
+            return self.same
+
+        def run(self, batch, idx, world):
+            self.steps.append(idx)
+            self._mbc += 1
+            return 7
+
+    f, slots = Stub(), [(0, 4), (4, 4)]
+    assert f.run_epoch({}, slots, 1) == 0 and f.g_epoch.n == 1 and f._mbc == 2 and f.steps == []
+    assert f.run_epoch({}, [(0, 4), (4, 3)], 1) == 14 and f.g_epoch.n == 1 and f.steps == [(0, 4), (4, 3)]       # other slots
+    f.same = False
+    assert f.run_epoch({}, slots, 1) == 14 and f.g_epoch.n == 1                                                 # other arrays
+    f.same = True
+    assert f.run_epoch({}, slots, 2) == 14 and f.g_epoch.n == 1        # two ranks without the peer path: NCCL sits between the launches
+    f.peer = {"any": 1}
+    assert f.run_epoch({}, slots, 2) == 2 * 40 and f.g_epoch.n == 2    # peer all-reduce: one launch, bytes moved by the kernel
+    f._mbc += 1
+    assert f.run_epoch({}, slots, 2) == 14 and f.g_epoch.n == 2        # odd parity: the captured buffers would not alternate
+    f.g_epoch = None
+    assert f.run_epoch({}, slots, 1) == 14
