@@ -163,3 +163,38 @@ def test_scene_model_tables():
     assert s.ncon == 8 and abs(s.qpos[2] - 0.0648) < 1e-3
     lidar = s.sensordata[6:42]
     assert (lidar > 0).all() and lidar.max() < 8.0, "36 beams at z=0.10 hit the 0.15 m high maze walls"
+
+
+def test_rest_on_wheel_caps_and_on_chassis_plates_supports_weight():
+    """Statics of the contacts beyond the eight rim points (no MuJoCo needed: at rest the normal components of the pyramid-row forces
+    add up to the weight, whatever the impedance parameters).  On its side the robot lies on two wheel caps: rim points plus the two
+    cap-down "triangle" points each.  Nose down it stands on the front edges of the chassis plates (convex hulls of the meshes: support
+    vertex + hull-graph neighbours); that pose chatters between 4 and 6 contacts, so the force is averaged over time and the robot
+    must neither sink through its plates nor fly off."""
+    def quat(axis, deg):
+        a = np.deg2rad(deg) / 2
+        return np.array([np.cos(a), *(np.sin(a) * np.asarray(axis, float))])
+    weight = 10.3 * 9.81
+
+    def contact_force(s):
+        ninc = sum(1 for c in s.contacts() if not c["exclude"])
+        return s.efc("force")[-4 * ninc:].sum() if ninc else 0.0
+
+    s = OracleSim(M, tolerance=1e-12)
+    s.qpos[2] = 0.14; s.qpos[3:7] = quat([1, 0, 0], 90)
+    s.step(6000)
+    geoms = {(c["geom1"], c["geom2"]) for c in s.contacts()}
+    assert s.ncon == 6 and len(geoms) == 2 and all(g1 == 0 and g2 >= 3 for g1, g2 in geoms), "two wheels, three points each"
+    assert abs(contact_force(s) - weight) < 1e-6 and np.abs(s.qvel).max() < 1e-6
+
+    s = OracleSim(M, tolerance=1e-12)
+    s.qpos[2] = 0.22; s.qpos[3:7] = quat([0, 1, 0], 88)
+    s.step(5000)
+    forces, heights, counts = [], [], set()
+    for _ in range(2000):
+        s.step()
+        forces.append(contact_force(s)); heights.append(s.qpos[2]); counts.add(s.ncon)
+        assert {(c["geom1"], c["geom2"]) for c in s.contacts()} <= {(0, 1), (0, 2)}, "only the two plates touch the floor"
+    assert abs(np.mean(forces) - weight) < 0.005 * weight
+    assert max(heights) - min(heights) < 1e-4 and abs(np.mean(heights) - 0.1499) < 2e-4
+    assert np.abs(s.qvel).max() < 2e-2 and counts <= {3, 4, 5, 6}
